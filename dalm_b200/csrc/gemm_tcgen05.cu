@@ -1,0 +1,347 @@
+// dalm_b200 — bf16 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands fed by TMA).
+//
+//     D[M,N] = epilogue( alpha * A[M,K] . B[N,K]^T )            A, B bf16 row-major ("TN": both K-contiguous)
+//
+// This single kernel is every dense contraction of the training step: the linear layers of the encoder / decoder
+// forward (B = W[out,in]), their dgrad (B = W^T[in,out], kept as a resident transposed copy - weights are frozen in
+// PEFT mode and HBM is 180 GB), the LoRA adapters (folded into the K dimension: A = [x | x A_l^T], B = [W | s B_l])
+// and the lm_head. It replaces the cuBLAS calls made by HF modeling code under
+// dalm/models/rag_e2e_base_model.py:93,105 (reference) and the autograd backward of those.
+//
+// Structure (one persistent CTA per SM, 256 threads):
+//   warp 0      : TMA producer   - cp.async.bulk.tensor 128B-swizzled tiles into a STAGES-deep smem ring
+//   warp 1      : MMA issuer     - one elected lane issues tcgen05.mma (128 x BN x 16) into a double-buffered TMEM
+//                                  accumulator, tcgen05.commit releases smem slots / publishes the accumulator
+//   warp 2      : TMEM allocator
+//   warps 4..7  : epilogue       - tcgen05.ld 32x32b -> registers -> alpha/bias/GELU/residual -> bf16|fp32 -> HBM,
+//                                  overlapped with the next tile's MMAs through the second accumulator stage
+#include "common.cuh"
+#include "ptx.cuh"
+#include <cudaTypedefs.h>
+#include <mutex>
+#include <unordered_map>
+
+namespace dalm {
+using namespace ptx;
+
+struct GemmEpilogue {
+  void* out;            // [M, ldo]
+  long long ldo;
+  int out_f32;          // 0: bf16, 1: fp32
+  const float* bias;    // [N] fp32 or nullptr
+  const void* resid;    // [M, ldr] added after activation, or nullptr (may alias out)
+  long long ldr;
+  int resid_f32;
+  int act;              // 0: none, 1: GELU(erf)
+  float alpha;
+  int M, N, K;
+};
+
+template <int BN> struct GemmCfg {
+  static constexpr int BM = 128, BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int ACC_STAGES = 2;
+  static constexpr int TMEM_COLS = ACC_STAGES * BN;              // 128 / 256 / 512: powers of two
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmEpilogue ep) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
+  extern __shared__ unsigned char smem_raw[];
+  // 128B swizzle atoms need 1024-byte aligned tile bases
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar   = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar  = full_bar + STAGES;
+  uint64_t* tfull_bar  = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + Cfg::ACC_STAGES;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + Cfg::ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int M = ep.M, N = ep.N, K = ep.K;
+  const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < Cfg::ACC_STAGES; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* sa = smem + stage * Cfg::STAGE_BYTES;
+          unsigned char* sb = sa + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);            // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);                  // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t adesc = make_sw128_kmajor_desc(sa);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sb);
+          const int krem = K - kb * BK;
+          const int ksteps = krem >= BK ? (BK / 16) : ((krem + 15) / 16);   // skip all-zero (OOB) k-slices
+          for (int k = 0; k < ksteps; ++k) {
+            // advance 16 bf16 = 32 B inside the 128B swizzle atom: +2 in the 16-byte-unit start address field
+            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);                           // accumulator complete -> epilogue
+        if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================== epilogue ===============================
+    const int q = warp - 4;                                     // TMEM lane quarter == warp % 4
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      const int row = m_blk * BM + q * 32 + lane;
+      const bool row_ok = row < M;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        const int col0 = n_blk * BN + c;
+        if (col0 >= N) break;                                   // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (row_ok) {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * ep.alpha;
+          if (ep.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (col0 + i < N) f[i] += __ldg(ep.bias + col0 + i);
+          }
+          if (ep.act == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+          }
+          if (ep.resid) {
+            if (ep.resid_f32) {
+              const float* r = reinterpret_cast<const float*>(ep.resid) + (size_t)row * ep.ldr + col0;
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                if (col0 + g * 4 < N) {
+                  const float4 t = *reinterpret_cast<const float4*>(r + g * 4);
+                  f[g * 4 + 0] += t.x; f[g * 4 + 1] += t.y; f[g * 4 + 2] += t.z; f[g * 4 + 3] += t.w;
+                }
+              }
+            } else {
+              const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(ep.resid) + (size_t)row * ep.ldr + col0;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (col0 + g * 8 < N) {
+                  const bf16x8 t = *reinterpret_cast<const bf16x8*>(r + g * 8);
+                  float tf[8];
+                  unpack8(t, tf);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[g * 8 + i] += tf[i];
+                }
+              }
+            }
+          }
+          if (ep.out_f32) {
+            float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col0;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              if (col0 + g * 4 < N)
+                *reinterpret_cast<float4*>(o + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldo + col0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (col0 + g * 8 < N) *reinterpret_cast<bf16x8*>(o + g * 8) = pack8(f + g * 8);
+          }
+        }
+      }
+      // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side: tensor-map construction (driver entry point fetched at run time, no libcuda link dependency) + cache
+// ------------------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr; long long rows, cols, ld; int box_rows;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.cols;
+    h = h * 1000003u ^ (size_t)k.ld;   h = h * 1000003u ^ (size_t)k.box_rows;
+    return h;
+  }
+};
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
+static std::mutex g_tmap_mu;
+
+// bf16 row-major [rows, cols] with row stride ld (elements); box = {64 cols (128 B), box_rows}, 128B swizzle, OOB -> 0
+static int get_tmap(const void* ptr, long long rows, long long cols, long long ld, int box_rows, CUtensorMap* out) {
+  TmapKey key{ptr, rows, cols, ld, box_rows};
+  {
+    std::lock_guard<std::mutex> g(g_tmap_mu);
+    auto it = g_tmaps.find(key);
+    if (it != g_tmaps.end()) { *out = it->second; return 0; }
+  }
+  auto fn = get_encode_fn();
+  DALM_REQUIRE(fn != nullptr, "gemm: cuTensorMapEncodeTiled driver entry point unavailable");
+  DALM_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "gemm: operand base %p is not 16-byte aligned", ptr);
+  DALM_REQUIRE((ld % 8) == 0, "gemm: operand row stride %lld must be a multiple of 8 bf16 (16 B)", ld);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUtensorMap m;
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DALM_REQUIRE(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%d",
+               (int)r, rows, cols, ld, box_rows);
+  {
+    std::lock_guard<std::mutex> g(g_tmap_mu);
+    if (g_tmaps.size() > 8192) g_tmaps.clear();
+    g_tmaps[key] = m;
+  }
+  *out = m;
+  return 0;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int max_ctas,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DALM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int num_tiles = ((ep.M + 127) / 128) * ((ep.N + BN - 1) / BN);
+  int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  gemm_bf16_tn_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, ep);
+  count_launch();
+  return check_launch("gemm_bf16_tn_kernel");
+}
+
+}  // namespace dalm
+
+using namespace dalm;
+
+// D[M,N] = act(alpha * A[M,K] B[N,K]^T + bias) + resid
+//   A: bf16 [M,K] row stride lda;  B: bf16 [N,K] row stride ldb;  out: bf16|fp32 [M,N] row stride ldo
+//   block_n: 0 = auto, or one of 64/128/256.   max_ctas: 0 = all SMs (used by tests to force multi-tile-per-CTA paths)
+extern "C" int dalm_b200_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* out,
+                                      long long ldo, int out_f32, int M, int N, int K, float alpha, const float* bias,
+                                      int act, const void* resid, long long ldr, int resid_f32, int block_n,
+                                      int max_ctas, void* stream) {
+  DALM_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  DALM_REQUIRE((N % 8) == 0, "gemm: N=%d must be a multiple of 8", N);
+  DALM_REQUIRE((K % 8) == 0, "gemm: K=%d must be a multiple of 8", K);
+  DALM_REQUIRE(lda >= K && ldb >= K && ldo >= N, "gemm: leading dimensions too small");
+  DALM_REQUIRE((ldo % (out_f32 ? 4 : 8)) == 0, "gemm: ldo=%lld breaks 16-byte row alignment", ldo);
+  DALM_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "gemm: out is not 16-byte aligned");
+  if (resid) {
+    DALM_REQUIRE((ldr % (resid_f32 ? 4 : 8)) == 0, "gemm: ldr=%lld breaks 16-byte row alignment", ldr);
+    DALM_REQUIRE((reinterpret_cast<uintptr_t>(resid) & 15) == 0, "gemm: resid is not 16-byte aligned");
+  }
+  DALM_REQUIRE(act == 0 || act == 1, "gemm: act must be 0 (none) or 1 (gelu)");
+  int bn = block_n;
+  if (bn == 0) {
+    // pick the widest tile that still yields >= ~1 wave of CTAs
+    const long long m_tiles = (M + 127) / 128;
+    if (m_tiles * ((N + 255) / 256) >= kNumSMs) bn = 256;
+    else if (m_tiles * ((N + 127) / 128) >= kNumSMs) bn = 128;
+    else bn = 64;
+    if (bn > 64 && N <= 64) bn = 64;
+  }
+  DALM_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: block_n must be 0/64/128/256");
+  CUtensorMap ta, tb;
+  if (int e = get_tmap(A, M, K, lda, 128, &ta)) return e;
+  if (int e = get_tmap(B, N, K, ldb, bn, &tb)) return e;
+  GemmEpilogue ep{out, ldo, out_f32, bias, resid, ldr, resid_f32, act, alpha, M, N, K};
+  if (bn == 256) return launch_gemm<256>(ta, tb, ep, max_ctas, (cudaStream_t)stream);
+  if (bn == 128) return launch_gemm<128>(ta, tb, ep, max_ctas, (cudaStream_t)stream);
+  return launch_gemm<64>(ta, tb, ep, max_ctas, (cudaStream_t)stream);
+}
+
+// drop cached tensor maps (call when operand buffers are freed / re-allocated at the same address with other shapes)
+extern "C" void dalm_b200_gemm_clear_cache() {
+  std::lock_guard<std::mutex> g(g_tmap_mu);
+  g_tmaps.clear();
+}

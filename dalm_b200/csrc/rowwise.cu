@@ -1,0 +1,504 @@
+// dalm_b200 — HBM-bound row-wise kernels of the encoder/decoder blocks (everything that is not a tensor-core tile):
+// LayerNorm / RMSNorm forward+backward, embedding gathers, RoPE, SwiGLU, GELU, masked mean-pool + L2 normalise,
+// LoRA weight-gradients, fused Adam. All use 16-byte vector accesses, warp-shuffle reductions and one CTA per row
+// (rows = tokens; 3204..26700 per launch => several waves over 148 SMs).
+//
+// Reference semantics: HF BertModel / LlamaForCausalLM blocks reached via dalm/models/rag_e2e_base_model.py:93,105;
+// mean_pooling + F.normalize: rag_e2e_base_model.py:96-97,108-111; torch.optim.Adam: train_rage2e.py:336.
+#include "common.cuh"
+
+namespace dalm {
+
+// ------------------------------------------------------------------------------------------------------------
+// LayerNorm forward: z fp32 [M,H] -> y = (z-mean)*rstd*gamma+beta, written as fp32 (residual path) and bf16 (GEMM input)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float* __restrict__ y32,
+                                                            __nv_bfloat16* __restrict__ y16, long long ld16,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            int H, float eps) {
+  extern __shared__ float row[];
+  __shared__ float red[32];
+  const size_t r = blockIdx.x;
+  const float* zr = z + r * H;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) { const float v = zr[i]; row[i] = v; s += v; }
+  const float mean = block_sum(s, red) / H;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) { const float d = row[i] - mean; q += d * d; }
+  const float var = block_sum(q, red) / H;
+  const float rstd = rsqrtf(var + eps);
+  if (threadIdx.x == 0) { mean_out[r] = mean; rstd_out[r] = rstd; }
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    const float v = (row[i] - mean) * rstd * gamma[i] + beta[i];
+    if (y32) y32[r * H + i] = v;
+    y16[r * ld16 + i] = __float2bfloat16_rn(v);
+  }
+}
+
+// LayerNorm backward (input gradient only; gamma/beta frozen in PEFT mode, see layernorm_bwd_params_kernel):
+//   dz = rstd * (g - mean(g) - zhat * mean(g*zhat)),  g = dy*gamma ; dy = dy_a (fp32, residual stream) + dy_b (bf16, GEMM dgrad)
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
+                                                            const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                            const float* __restrict__ dy_a, const __nv_bfloat16* __restrict__ dy_b,
+                                                            long long ldb, float* __restrict__ dz32,
+                                                            __nv_bfloat16* __restrict__ dz16, long long ld16, int H) {
+  extern __shared__ float sm[];
+  float* gbuf = sm;          // g = dy*gamma
+  float* zh = sm + H;        // zhat
+  __shared__ float red[32];
+  const size_t r = blockIdx.x;
+  const float mean = mean_in[r], rstd = rstd_in[r];
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    float dy = 0.f;
+    if (dy_a) dy += dy_a[r * H + i];
+    if (dy_b) dy += __bfloat162float(dy_b[r * ldb + i]);
+    const float g = dy * gamma[i];
+    const float zz = (z[r * H + i] - mean) * rstd;
+    gbuf[i] = g; zh[i] = zz;
+    s1 += g; s2 += g * zz;
+  }
+  s1 = block_sum(s1, red) / H;
+  s2 = block_sum(s2, red) / H;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    const float d = rstd * (gbuf[i] - s1 - zh[i] * s2);
+    if (dz32) dz32[r * H + i] = d;
+    if (dz16) dz16[r * ld16 + i] = __float2bfloat16_rn(d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// RMSNorm forward: x fp32 [M,H] -> h bf16 = x * rsqrt(mean(x^2)+eps) * g
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                          __nv_bfloat16* __restrict__ h, long long ldh,
+                                                          float* __restrict__ rstd_out, int H, float eps) {
+  extern __shared__ float row[];
+  __shared__ float red[32];
+  const size_t r = blockIdx.x;
+  const float4* x4 = reinterpret_cast<const float4*>(x + r * H);
+  float4* row4 = reinterpret_cast<float4*>(row);
+  float q = 0.f;
+  for (int i = threadIdx.x; i < H / 4; i += blockDim.x) {
+    const float4 v = x4[i]; row4[i] = v;
+    q += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  const float rstd = rsqrtf(block_sum(q, red) / H + eps);
+  if (threadIdx.x == 0) rstd_out[r] = rstd;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (int i = threadIdx.x; i < H / 4; i += blockDim.x) {
+    const float4 v = row4[i], w = g4[i];
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x * rstd * w.x, v.y * rstd * w.y);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v.z * rstd * w.z, v.w * rstd * w.w);
+    uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(h + r * ldh + i * 4) = pk;
+  }
+}
+
+// RMSNorm backward, fused with the residual-gradient stream:
+//   dx = rstd * (gd - xhat * mean(gd * xhat)), gd = dh * g;   dres_out = dres_in + dx  (fp32) and its bf16 copy
+__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                          const float* __restrict__ rstd_in,
+                                                          const __nv_bfloat16* __restrict__ dh, long long lddh,
+                                                          const float* __restrict__ dres_in, float* __restrict__ dres_out,
+                                                          __nv_bfloat16* __restrict__ dres16, long long ld16, int H) {
+  extern __shared__ float sm[];
+  float* gd = sm;
+  float* xh = sm + H;
+  __shared__ float red[32];
+  const size_t r = blockIdx.x;
+  const float rstd = rstd_in[r];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    const float a = __bfloat162float(dh[r * lddh + i]) * g[i];
+    const float b = x[r * H + i] * rstd;
+    gd[i] = a; xh[i] = b; s += a * b;
+  }
+  s = block_sum(s, red) / H;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    float d = rstd * (gd[i] - xh[i] * s);
+    if (dres_in) d += dres_in[r * H + i];
+    dres_out[r * H + i] = d;
+    if (dres16) dres16[r * ld16 + i] = __float2bfloat16_rn(d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// embeddings
+// ------------------------------------------------------------------------------------------------------------
+// BERT: z = word[id] + pos[l] + type[0]  (fp32 sum, LayerNorm follows as a separate launch)
+__global__ void bert_embed_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restrict__ word,
+                                  const __nv_bfloat16* __restrict__ pos, const __nv_bfloat16* __restrict__ type0,
+                                  float* __restrict__ z, int L, int H, int V) {
+  const size_t r = blockIdx.x;
+  const int l = (int)(r % L);
+  int64_t id = ids[r];
+  if (id < 0 || id >= V) id = 0;
+  for (int i = threadIdx.x; i < H; i += blockDim.x)
+    z[r * H + i] = __bfloat162float(word[(size_t)id * H + i]) + __bfloat162float(pos[(size_t)l * H + i]) +
+                   __bfloat162float(type0[i]);
+}
+// decoder: x[r,:] = table[id,:] (bf16 -> fp32 residual stream)
+__global__ void embed_gather_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restrict__ table,
+                                    float* __restrict__ x, int H, int V) {
+  const size_t r = blockIdx.x;
+  int64_t id = ids[r];
+  if (id < 0 || id >= V) id = 0;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) x[r * H + i] = __bfloat162float(table[(size_t)id * H + i]);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// RoPE (HF rotate_half convention), in place on `nheads` heads of width D starting at column col0 of a token-major
+// bf16 buffer. position = row % L. sign = +1 forward, -1 backward (inverse rotation = transpose of the forward map).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void rope_kernel(__nv_bfloat16* __restrict__ buf, long long ld, int col0, int nheads, int D,
+                            const float* __restrict__ cos_t, const float* __restrict__ sin_t, int L, float sign) {
+  const size_t r = blockIdx.x;
+  const int l = (int)(r % L), half = D / 2;
+  __nv_bfloat16* base = buf + r * ld + col0;
+  for (int i = threadIdx.x; i < nheads * half; i += blockDim.x) {
+    const int hd = i / half, j = i - hd * half;
+    const float c = cos_t[(size_t)l * half + j], s = sin_t[(size_t)l * half + j] * sign;
+    __nv_bfloat16* p = base + hd * D;
+    const float x1 = __bfloat162float(p[j]), x2 = __bfloat162float(p[j + half]);
+    p[j] = __float2bfloat16_rn(x1 * c - x2 * s);
+    p[j + half] = __float2bfloat16_rn(x2 * c + x1 * s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// SwiGLU: gu = [gate | up] (bf16 [M,2F]);  act = silu(gate) * up
+// ------------------------------------------------------------------------------------------------------------
+__global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gu, long long ldgu, __nv_bfloat16* __restrict__ act,
+                                  long long lda, int F) {
+  const size_t r = blockIdx.y;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= F) return;
+  float g[8], u[8], o[8];
+  unpack8(*reinterpret_cast<const bf16x8*>(gu + r * ldgu + i), g);
+  unpack8(*reinterpret_cast<const bf16x8*>(gu + r * ldgu + F + i), u);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = g[k] / (1.f + __expf(-g[k])) * u[k];
+  *reinterpret_cast<bf16x8*>(act + r * lda + i) = pack8(o);
+}
+// in place: gu <- [dgate | dup]
+__global__ void swiglu_bwd_kernel(__nv_bfloat16* __restrict__ gu, long long ldgu, const __nv_bfloat16* __restrict__ dact,
+                                  long long ldd, int F) {
+  const size_t r = blockIdx.y;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= F) return;
+  float g[8], u[8], d[8], dg[8], du[8];
+  unpack8(*reinterpret_cast<const bf16x8*>(gu + r * ldgu + i), g);
+  unpack8(*reinterpret_cast<const bf16x8*>(gu + r * ldgu + F + i), u);
+  unpack8(*reinterpret_cast<const bf16x8*>(dact + r * ldd + i), d);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float sg = 1.f / (1.f + __expf(-g[k]));
+    const float silu = g[k] * sg;
+    dg[k] = d[k] * u[k] * sg * (1.f + g[k] * (1.f - sg));
+    du[k] = d[k] * silu;
+  }
+  *reinterpret_cast<bf16x8*>(gu + r * ldgu + i) = pack8(dg);
+  *reinterpret_cast<bf16x8*>(gu + r * ldgu + F + i) = pack8(du);
+}
+
+// GELU(erf) forward on a pre-activation buffer, and backward in place on the incoming gradient
+__global__ void gelu_fwd_kernel(const __nv_bfloat16* __restrict__ pre, long long ldp, __nv_bfloat16* __restrict__ act,
+                                long long lda, int F) {
+  const size_t r = blockIdx.y;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= F) return;
+  float x[8];
+  unpack8(*reinterpret_cast<const bf16x8*>(pre + r * ldp + i), x);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = gelu_erf(x[k]);
+  *reinterpret_cast<bf16x8*>(act + r * lda + i) = pack8(x);
+}
+__global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, long long ldp, __nv_bfloat16* __restrict__ dact,
+                                long long ldd, int F) {
+  const size_t r = blockIdx.y;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= F) return;
+  float x[8], d[8];
+  unpack8(*reinterpret_cast<const bf16x8*>(pre + r * ldp + i), x);
+  unpack8(*reinterpret_cast<const bf16x8*>(dact + r * ldd + i), d);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) d[k] *= gelu_erf_grad(x[k]);
+  *reinterpret_cast<bf16x8*>(dact + r * ldd + i) = pack8(d);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// masked mean-pool + L2 normalise (forward) and its backward. hidden fp32 [B,L,H]; mask int64 [B,L].
+//   pooled = sum_l h*m / clamp(sum_l m, 1e-9);  emb = pooled / max(||pooled||, 1e-12)   (if normalize)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pool_norm_fwd_kernel(const float* __restrict__ hidden, const int64_t* __restrict__ mask,
+                                                            float* __restrict__ pooled, float* __restrict__ emb,
+                                                            float* __restrict__ norm_out, int L, int H, int normalize) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float cnt = 0.f;
+  for (int l = 0; l < L; ++l) cnt += (float)mask[(size_t)b * L + l];
+  const float inv = 1.f / fmaxf(cnt, 1e-9f);
+  float sq = 0.f;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < L; ++l) {
+      const float m = (float)mask[(size_t)b * L + l];
+      if (m != 0.f) acc += hidden[((size_t)b * L + l) * H + i] * m;
+    }
+    acc *= inv;
+    pooled[(size_t)b * H + i] = acc;
+    sq += acc * acc;
+  }
+  const float nrm = sqrtf(block_sum(sq, red));
+  if (threadIdx.x == 0) norm_out[b] = nrm;
+  const float s = normalize ? 1.f / fmaxf(nrm, 1e-12f) : 1.f;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) emb[(size_t)b * H + i] = pooled[(size_t)b * H + i] * s;
+}
+// d_hidden[b,l,:] = m[b,l]/cnt * d_pooled;  d_pooled = (d_emb - emb*(emb.d_emb)) / max(norm,eps)  (if normalize)
+__global__ void __launch_bounds__(256) pool_norm_bwd_kernel(const float* __restrict__ emb, const float* __restrict__ norm_in,
+                                                            const float* __restrict__ d_emb, const int64_t* __restrict__ mask,
+                                                            float* __restrict__ d_hidden, int L, int H, int normalize) {
+  extern __shared__ float dp[];     // [H] d_pooled
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float cnt = 0.f;
+  for (int l = 0; l < L; ++l) cnt += (float)mask[(size_t)b * L + l];
+  const float inv = 1.f / fmaxf(cnt, 1e-9f);
+  float dot = 0.f;
+  if (normalize) {
+    for (int i = threadIdx.x; i < H; i += blockDim.x) dot += emb[(size_t)b * H + i] * d_emb[(size_t)b * H + i];
+    dot = block_sum(dot, red);
+  }
+  const float nrm = norm_in[b];
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    float d = d_emb[(size_t)b * H + i];
+    if (normalize) {
+      if (nrm > 1e-12f) d = (d - emb[(size_t)b * H + i] * dot) / nrm;
+      else d = d / 1e-12f;
+    }
+    dp[i] = d * inv;
+  }
+  __syncthreads();
+  for (int l = 0; l < L; ++l) {
+    const float m = (float)mask[(size_t)b * L + l];
+    for (int i = threadIdx.x; i < H; i += blockDim.x) d_hidden[((size_t)b * L + l) * H + i] = m * dp[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LoRA weight gradients: out[r, k] (+)= scale * sum_m G[m, r] * X[m, k]     (G: [M,R<=32] bf16, X: [M,K] bf16)
+// grid (ceil(K/256), splits over M); partial sums are combined with fp32 atomics (R*K*splits adds, tiny).
+// ------------------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(128) lora_wgrad_kernel(const __nv_bfloat16* __restrict__ X, long long ldx,
+                                                         const __nv_bfloat16* __restrict__ G, long long ldg,
+                                                         float* __restrict__ out, long long so_r, long long so_k,
+                                                         int M, int K, int rows_per_cta, float scale) {
+  __shared__ float gs[64][R];
+  const int k2 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;          // two adjacent columns per thread
+  const int m0 = blockIdx.y * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
+  float acc0[R], acc1[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
+  for (int mb = m0; mb < m1; mb += 64) {
+    const int nm = min(64, m1 - mb);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * R; i += blockDim.x) {
+      const int mm = i / R, r = i - mm * R;
+      gs[mm][r] = mm < nm ? __bfloat162float(G[(size_t)(mb + mm) * ldg + r]) : 0.f;
+    }
+    __syncthreads();
+    if (k2 < K) {
+      for (int mm = 0; mm < nm; ++mm) {
+        const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(X + (size_t)(mb + mm) * ldx + k2));
+#pragma unroll
+        for (int r = 0; r < R; ++r) { acc0[r] = fmaf(gs[mm][r], x.x, acc0[r]); acc1[r] = fmaf(gs[mm][r], x.y, acc1[r]); }
+      }
+    }
+  }
+  if (k2 < K) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      atomicAdd(out + r * so_r + (long long)k2 * so_k, acc0[r] * scale);
+      if (k2 + 1 < K) atomicAdd(out + r * so_r + (long long)(k2 + 1) * so_k, acc1[r] * scale);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// fused Adam over a flat fp32 buffer (torch.optim.Adam semantics, no weight decay, no amsgrad), optional bf16 shadow copy
+// ------------------------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float beta1, float beta2, float eps, float bc1, float bc2_sqrt,
+                            float grad_scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * grad_scale;
+  const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+  const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+
+// out_bf16[r*ldo + c] = scale * in_f32[r*si_r + c*si_c]   (LoRA factor packing into the augmented weights)
+__global__ void pack_scaled_bf16_kernel(const float* __restrict__ in, long long si_r, long long si_c,
+                                        __nv_bfloat16* __restrict__ out, long long ldo, int rows, int cols, float scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+  out[(size_t)r * ldo + c] = __float2bfloat16_rn(in[r * si_r + c * si_c] * scale);
+}
+
+// out_bf16 [rows, ldo] <- fp32 [rows, cols]  (plain cast, vectorised)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, long long ldi, __nv_bfloat16* __restrict__ out,
+                                     long long ldo, int rows, int cols) {
+  const size_t r = blockIdx.y;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= cols) return;
+  const float4 v = *reinterpret_cast<const float4*>(in + r * ldi + c);
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(out + r * ldo + c) = pk;
+}
+
+}  // namespace dalm
+
+using namespace dalm;
+#define ST(s) ((cudaStream_t)(s))
+
+extern "C" int dalm_b200_layernorm_fwd(const float* z, const float* gamma, const float* beta, float* y32, void* y16,
+                                       long long ld16, float* mean, float* rstd, int M, int H, float eps, void* stream) {
+  DALM_REQUIRE(M > 0 && H > 0 && H * 4 <= 64 * 1024, "layernorm_fwd: bad shape M=%d H=%d", M, H);
+  layernorm_fwd_kernel<<<M, 256, H * sizeof(float), ST(stream)>>>(z, gamma, beta, y32, (__nv_bfloat16*)y16, ld16, mean, rstd, H, eps);
+  count_launch();
+  return check_launch("layernorm_fwd_kernel");
+}
+extern "C" int dalm_b200_layernorm_bwd(const float* z, const float* gamma, const float* mean, const float* rstd,
+                                       const float* dy_f32, const void* dy_bf16, long long ldb, float* dz32, void* dz16,
+                                       long long ld16, int M, int H, void* stream) {
+  DALM_REQUIRE(M > 0 && H > 0 && H * 8 <= 48 * 1024, "layernorm_bwd: bad shape M=%d H=%d", M, H);
+  DALM_REQUIRE(dy_f32 || dy_bf16, "layernorm_bwd: no incoming gradient");
+  layernorm_bwd_kernel<<<M, 256, 2 * H * sizeof(float), ST(stream)>>>(z, gamma, mean, rstd, dy_f32, (const __nv_bfloat16*)dy_bf16, ldb,
+                                                                     dz32, (__nv_bfloat16*)dz16, ld16, H);
+  count_launch();
+  return check_launch("layernorm_bwd_kernel");
+}
+extern "C" int dalm_b200_rmsnorm_fwd(const float* x, const float* g, void* h, long long ldh, float* rstd, int M, int H,
+                                     float eps, void* stream) {
+  DALM_REQUIRE(M > 0 && H > 0 && (H % 4) == 0 && H * 4 <= 48 * 1024 && (ldh % 4) == 0, "rmsnorm_fwd: bad shape M=%d H=%d", M, H);
+  rmsnorm_fwd_kernel<<<M, 256, H * sizeof(float), ST(stream)>>>(x, g, (__nv_bfloat16*)h, ldh, rstd, H, eps);
+  count_launch();
+  return check_launch("rmsnorm_fwd_kernel");
+}
+extern "C" int dalm_b200_rmsnorm_bwd(const float* x, const float* g, const float* rstd, const void* dh, long long lddh,
+                                     const float* dres_in, float* dres_out, void* dres16, long long ld16, int M, int H,
+                                     void* stream) {
+  DALM_REQUIRE(M > 0 && H > 0 && H * 8 <= 96 * 1024, "rmsnorm_bwd: bad shape M=%d H=%d", M, H);
+  static bool attr = false;
+  if (!attr) { DALM_CUDA(cudaFuncSetAttribute(rmsnorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+  rmsnorm_bwd_kernel<<<M, 256, 2 * H * sizeof(float), ST(stream)>>>(x, g, rstd, (const __nv_bfloat16*)dh, lddh, dres_in, dres_out,
+                                                                   (__nv_bfloat16*)dres16, ld16, H);
+  count_launch();
+  return check_launch("rmsnorm_bwd_kernel");
+}
+extern "C" int dalm_b200_bert_embed(const int64_t* ids, const void* word, const void* pos, const void* type0, float* z,
+                                    int M, int L, int H, int V, void* stream) {
+  bert_embed_kernel<<<M, 256, 0, ST(stream)>>>(ids, (const __nv_bfloat16*)word, (const __nv_bfloat16*)pos,
+                                               (const __nv_bfloat16*)type0, z, L, H, V);
+  count_launch();
+  return check_launch("bert_embed_kernel");
+}
+extern "C" int dalm_b200_embed_gather(const int64_t* ids, const void* table, float* x, int M, int H, int V, void* stream) {
+  embed_gather_kernel<<<M, 256, 0, ST(stream)>>>(ids, (const __nv_bfloat16*)table, x, H, V);
+  count_launch();
+  return check_launch("embed_gather_kernel");
+}
+extern "C" int dalm_b200_rope(void* buf, long long ld, int col0, int nheads, int D, const float* cos_t, const float* sin_t,
+                              int M, int L, int backward, void* stream) {
+  DALM_REQUIRE((D % 2) == 0, "rope: odd head_dim");
+  rope_kernel<<<M, 256, 0, ST(stream)>>>((__nv_bfloat16*)buf, ld, col0, nheads, D, cos_t, sin_t, L, backward ? -1.f : 1.f);
+  count_launch();
+  return check_launch("rope_kernel");
+}
+extern "C" int dalm_b200_swiglu_fwd(const void* gu, long long ldgu, void* act, long long lda, int M, int F, void* stream) {
+  DALM_REQUIRE((F % 8) == 0 && (ldgu % 8) == 0 && (lda % 8) == 0, "swiglu: F and strides must be multiples of 8");
+  dim3 grid((F / 8 + 255) / 256, M);
+  swiglu_fwd_kernel<<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)gu, ldgu, (__nv_bfloat16*)act, lda, F);
+  count_launch();
+  return check_launch("swiglu_fwd_kernel");
+}
+extern "C" int dalm_b200_swiglu_bwd(void* gu, long long ldgu, const void* dact, long long ldd, int M, int F, void* stream) {
+  DALM_REQUIRE((F % 8) == 0 && (ldgu % 8) == 0 && (ldd % 8) == 0, "swiglu: F and strides must be multiples of 8");
+  dim3 grid((F / 8 + 255) / 256, M);
+  swiglu_bwd_kernel<<<grid, 256, 0, ST(stream)>>>((__nv_bfloat16*)gu, ldgu, (const __nv_bfloat16*)dact, ldd, F);
+  count_launch();
+  return check_launch("swiglu_bwd_kernel");
+}
+extern "C" int dalm_b200_gelu_fwd(const void* pre, long long ldp, void* act, long long lda, int M, int F, void* stream) {
+  DALM_REQUIRE((F % 8) == 0 && (ldp % 8) == 0 && (lda % 8) == 0, "gelu: F and strides must be multiples of 8");
+  dim3 grid((F / 8 + 255) / 256, M);
+  gelu_fwd_kernel<<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)pre, ldp, (__nv_bfloat16*)act, lda, F);
+  count_launch();
+  return check_launch("gelu_fwd_kernel");
+}
+extern "C" int dalm_b200_gelu_bwd(const void* pre, long long ldp, void* dact, long long ldd, int M, int F, void* stream) {
+  DALM_REQUIRE((F % 8) == 0 && (ldp % 8) == 0 && (ldd % 8) == 0, "gelu: F and strides must be multiples of 8");
+  dim3 grid((F / 8 + 255) / 256, M);
+  gelu_bwd_kernel<<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)pre, ldp, (__nv_bfloat16*)dact, ldd, F);
+  count_launch();
+  return check_launch("gelu_bwd_kernel");
+}
+extern "C" int dalm_b200_pool_norm_fwd(const float* hidden, const int64_t* mask, float* pooled, float* emb, float* norm,
+                                       int B, int L, int H, int normalize, void* stream) {
+  pool_norm_fwd_kernel<<<B, 256, 0, ST(stream)>>>(hidden, mask, pooled, emb, norm, L, H, normalize);
+  count_launch();
+  return check_launch("pool_norm_fwd_kernel");
+}
+extern "C" int dalm_b200_pool_norm_bwd(const float* emb, const float* norm, const float* d_emb, const int64_t* mask,
+                                       float* d_hidden, int B, int L, int H, int normalize, void* stream) {
+  DALM_REQUIRE(H * 4 <= 48 * 1024, "pool_norm_bwd: H too large");
+  pool_norm_bwd_kernel<<<B, 256, H * sizeof(float), ST(stream)>>>(emb, norm, d_emb, mask, d_hidden, L, H, normalize);
+  count_launch();
+  return check_launch("pool_norm_bwd_kernel");
+}
+extern "C" int dalm_b200_lora_wgrad(const void* X, long long ldx, const void* G, long long ldg, float* out,
+                                    long long so_r, long long so_k, int M, int K, int R, float scale, void* stream) {
+  DALM_REQUIRE(R == 8 || R == 16, "lora_wgrad: rank %d unsupported (8/16)", R);
+  DALM_REQUIRE((K % 2) == 0 && (ldx % 2) == 0, "lora_wgrad: K and ldx must be even");
+  const int rows_per_cta = 256;
+  dim3 grid((K / 2 + 127) / 128, (M + rows_per_cta - 1) / rows_per_cta);
+  if (R == 8)
+    lora_wgrad_kernel<8><<<grid, 128, 0, ST(stream)>>>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)G, ldg, out, so_r, so_k, M, K, rows_per_cta, scale);
+  else
+    lora_wgrad_kernel<16><<<grid, 128, 0, ST(stream)>>>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)G, ldg, out, so_r, so_k, M, K, rows_per_cta, scale);
+  count_launch();
+  return check_launch("lora_wgrad_kernel");
+}
+extern "C" int dalm_b200_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                                   float beta2, float eps, int step, float grad_scale, void* stream) {
+  DALM_REQUIRE(n >= 0 && step >= 1, "adam: bad n/step");
+  if (n == 0) return 0;
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2s, grad_scale);
+  count_launch();
+  return check_launch("adam_kernel");
+}
+extern "C" int dalm_b200_pack_scaled_bf16(const float* in, long long si_r, long long si_c, void* out, long long ldo,
+                                          int rows, int cols, float scale, void* stream) {
+  const long long n = (long long)rows * cols;
+  if (n == 0) return 0;
+  pack_scaled_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(in, si_r, si_c, (__nv_bfloat16*)out, ldo, rows, cols, scale);
+  count_launch();
+  return check_launch("pack_scaled_bf16_kernel");
+}
+extern "C" int dalm_b200_cast_f32_bf16(const float* in, long long ldi, void* out, long long ldo, int rows, int cols, void* stream) {
+  DALM_REQUIRE((cols % 4) == 0 && (ldi % 4) == 0 && (ldo % 4) == 0, "cast: cols/strides must be multiples of 4");
+  dim3 grid((cols / 4 + 255) / 256, rows);
+  cast_f32_bf16_kernel<<<grid, 256, 0, ST(stream)>>>(in, ldi, (__nv_bfloat16*)out, ldo, rows, cols);
+  count_launch();
+  return check_launch("cast_f32_bf16_kernel");
+}

@@ -1,0 +1,186 @@
+"""Llama decoder (Llama-2-7B shape and smaller) forward + backward as a launch sequence over the C-ABI kernels.
+
+Mirrors `self.generator_model(input_ids=..., attention_mask=...).logits` of the reference
+(dalm/models/rag_e2e_base_model.py:104-106) through HF LlamaForCausalLM: embed -> N x [RMSNorm -> QKV(+LoRA on q,v)
+-> RoPE -> causal+padding attention -> o_proj + residual -> RMSNorm -> SwiGLU MLP + residual] -> RMSNorm -> lm_head.
+
+HBM layout per layer (bf16 unless noted):
+  Wqkv_aug [Nq+2Nkv, H+Ra]  fused q|k|v rows, last Ra = 2r columns = (alpha/r)*B_q | (alpha/r)*B_v  (LoRA folded into K)
+  WqkvT_aug [H, Nq+2Nkv+Ra] resident transpose for dgrad, last Ra columns = A_q^T | A_v^T
+  A_stack [64,H], Bblk [64, Nq+2Nkv]   LoRA down / mid-gradient operands (see bert.py)
+  Wo [H,Nq], WoT; Wgu [2F,H] (gate rows, then up rows), WguT [H,2F]; Wd [H,F], WdT [F,H]; RMSNorm gains fp32
+Residual stream and its gradient are fp32; every GEMM operand is bf16.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import ops
+from .lora import LoraBank
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+class _Ctx:
+    pass
+
+
+class LlamaDecoder(torch.nn.Module):
+    LORA_TARGETS = ("q_proj", "v_proj")               # reference rag_e2e_base_model.py:76-77
+
+    def __init__(self, cfg: Dict, state_dict: Dict[str, torch.Tensor], device="cuda", lora: bool = False,
+                 lora_seed: int = 1):
+        super().__init__()
+        self.cfg = cfg
+        self.H = H = cfg["hidden_size"]
+        self.F = F = cfg["intermediate_size"]
+        self.nl = cfg["num_hidden_layers"]
+        self.nh = cfg["num_attention_heads"]
+        self.nkv = cfg.get("num_key_value_heads", self.nh)
+        self.hd = cfg.get("head_dim") or H // self.nh
+        self.V = cfg["vocab_size"]
+        self.eps = float(cfg.get("rms_norm_eps", 1e-5))
+        rp = cfg.get("rope_parameters") or {}
+        self.theta = float(cfg.get("rope_theta", rp.get("rope_theta", 10000.0)))
+        self.dev = torch.device(device)
+        if self.hd not in (32, 64, 128):
+            raise NotImplementedError(f"head_dim {self.hd} not supported by the attention kernels")
+        self.Nq, self.Nkv = self.nh * self.hd, self.nkv * self.hd
+        self.Nqkv = self.Nq + 2 * self.Nkv
+        self.r = 8
+        self.Ra = 2 * self.r if lora else 0
+        sd = state_dict
+        g = lambda k, dt: sd[k].to(device=self.dev, dtype=dt).contiguous()
+        self.embed = g("model.embed_tokens.weight", bf16)
+        self.norm_g = g("model.norm.weight", f32)
+        self.lm_head = g("lm_head.weight", bf16) if "lm_head.weight" in sd else self.embed
+        self.lm_headT = self.lm_head.t().contiguous()
+        self.layers: List[Dict[str, torch.Tensor]] = []
+        H_, Ra = H, self.Ra
+        for l in range(self.nl):
+            p = f"model.layers.{l}."
+            W = {}
+            wqkv = torch.cat([g(p + "self_attn.q_proj.weight", bf16), g(p + "self_attn.k_proj.weight", bf16),
+                              g(p + "self_attn.v_proj.weight", bf16)], 0)
+            W["Wqkv_aug"] = torch.zeros(self.Nqkv, H_ + Ra, dtype=bf16, device=self.dev)
+            W["Wqkv_aug"][:, :H_] = wqkv
+            W["WqkvT_aug"] = torch.zeros(H_, self.Nqkv + Ra, dtype=bf16, device=self.dev)
+            W["WqkvT_aug"][:, :self.Nqkv] = wqkv.t()
+            del wqkv
+            if lora:
+                W["A_stack"] = torch.zeros(64, H_, dtype=bf16, device=self.dev)
+                W["Bblk"] = torch.zeros(64, self.Nqkv, dtype=bf16, device=self.dev)
+            W["Wo"] = g(p + "self_attn.o_proj.weight", bf16)
+            W["WoT"] = W["Wo"].t().contiguous()
+            W["Wgu"] = torch.cat([g(p + "mlp.gate_proj.weight", bf16), g(p + "mlp.up_proj.weight", bf16)], 0)
+            W["WguT"] = W["Wgu"].t().contiguous()
+            W["Wd"] = g(p + "mlp.down_proj.weight", bf16)
+            W["WdT"] = W["Wd"].t().contiguous()
+            W["g1"] = g(p + "input_layernorm.weight", f32)
+            W["g2"] = g(p + "post_attention_layernorm.weight", f32)
+            self.layers.append(W)
+        self._rope_cache: Dict[int, tuple] = {}
+        self.lora: Optional[LoraBank] = None
+        if lora:
+            outs = {"q_proj": self.Nq, "v_proj": self.Nkv}
+            specs = [(f"model.layers.{l}.self_attn.{n}", H, outs[n]) for l in range(self.nl) for n in self.LORA_TARGETS]
+            self.lora = LoraBank(specs, r=self.r, alpha=16, dropout=0.05, device=self.dev, seed=lora_seed)
+            self.lora_flat = torch.nn.Parameter(self.lora.flat, requires_grad=True)
+            self.lora_flat.grad = self.lora.grad
+            self.repack_lora()
+
+    # column offset / width of each LoRA target inside the fused qkv output
+    def _target_cols(self, n: str):
+        return (0, self.Nq) if n == "q_proj" else (self.Nq + self.Nkv, self.Nkv)
+
+    def repack_lora(self) -> None:
+        if self.lora is None:
+            return
+        H, r, s = self.H, self.r, self.lora.scale
+        for l, W in enumerate(self.layers):
+            for j, n in enumerate(self.LORA_TARGETS):
+                name = f"model.layers.{l}.self_attn.{n}"
+                A, B = self.lora.A[name], self.lora.B[name]             # [r,H], [out,r]
+                c0, w = self._target_cols(n)
+                ops.pack_scaled_bf16_(B, r, 1, W["Wqkv_aug"][c0:c0 + w, H + j * r:], w, r, s)
+                ops.pack_scaled_bf16_(A, 1, H, W["WqkvT_aug"][:, self.Nqkv + j * r:], H, r, 1.0)
+                ops.pack_scaled_bf16_(A, H, 1, W["A_stack"][j * r:(j + 1) * r], r, H, 1.0)
+                ops.pack_scaled_bf16_(B, 1, r, W["Bblk"][j * r:(j + 1) * r, c0:], r, w, s)
+
+    def _rope(self, L: int):
+        if L not in self._rope_cache:
+            half = self.hd // 2
+            inv = 1.0 / (self.theta ** (torch.arange(0, self.hd, 2, dtype=torch.float32) / self.hd))   # HF inv_freq
+            fr = torch.outer(torch.arange(L, dtype=torch.float32), inv)                                 # [L, hd/2]
+            self._rope_cache[L] = (fr.cos().to(self.dev).contiguous(), fr.sin().to(self.dev).contiguous())
+            assert fr.shape[1] == half
+        return self._rope_cache[L]
+
+    # ------------------------------------------------------------------------------------------------------------
+    def forward_logits(self, ids: torch.Tensor, mask: torch.Tensor, save: bool = True):
+        """ids, mask int64 [B,L] -> (logits bf16 [B,L,V], ctx)"""
+        B, L = ids.shape
+        M, H, F, Ra = B * L, self.H, self.F, self.Ra
+        cos_t, sin_t = self._rope(L)
+        ctx = _Ctx()
+        ctx.B, ctx.L, ctx.mask, ctx.layers = B, L, mask.contiguous(), []
+        x = ops.embed_gather(ids, self.embed)                                    # fp32 residual stream [M,H]
+        for W in self.layers:
+            a = _Ctx()
+            a.x_in = x
+            a.h1_aug = torch.empty(M, H + Ra, dtype=bf16, device=self.dev)
+            _, a.rstd1 = ops.rmsnorm_fwd(x, W["g1"], self.eps, h=a.h1_aug[:, :H])
+            if Ra:
+                ops.gemm(a.h1_aug[:, :H], W["A_stack"], out=a.h1_aug[:, H:], N=Ra, block_n=64)
+            a.qkv = ops.gemm(a.h1_aug, W["Wqkv_aug"])                            # [M, Nq+2Nkv]
+            ops.rope_(a.qkv, 0, self.nh + self.nkv, self.hd, cos_t, sin_t, L)    # q heads then k heads are adjacent
+            a.att, a.lse = ops.attention_fwd(a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + self.Nkv],
+                                             a.qkv[:, self.Nq + self.Nkv:], ctx.mask, B, L, self.nh, self.nkv, self.hd,
+                                             causal=True)
+            a.x_mid = ops.gemm(a.att, W["Wo"], out_dtype=f32, resid=x)
+            a.h2, a.rstd2 = ops.rmsnorm_fwd(a.x_mid, W["g2"], self.eps)
+            a.gu = ops.gemm(a.h2, W["Wgu"])                                       # [M,2F]
+            a.act = ops.swiglu_fwd(a.gu, F)
+            x = ops.gemm(a.act, W["Wd"], out_dtype=f32, resid=a.x_mid)
+            if save:
+                ctx.layers.append(a)
+        ctx.x_final = x
+        ctx.hf, ctx.rstdf = ops.rmsnorm_fwd(x, self.norm_g, self.eps)
+        logits = ops.gemm(ctx.hf, self.lm_head)                                   # bf16 [M,V]
+        return logits.view(B, L, self.V), ctx
+
+    # ------------------------------------------------------------------------------------------------------------
+    def backward_logits(self, ctx: _Ctx, dlogits: torch.Tensor) -> None:
+        """dlogits bf16 [B,L,V]; accumulates LoRA gradients (base weights frozen: PEFT mode)."""
+        if self.lora is None:
+            return
+        B, L = ctx.B, ctx.L
+        M, H, F, Ra, r = B * L, self.H, self.F, self.Ra, self.r
+        cos_t, sin_t = self._rope(L)
+        dhf = ops.gemm(dlogits.view(M, self.V), self.lm_headT)                    # [M,H]
+        dx32, dx16 = ops.rmsnorm_bwd(ctx.x_final, self.norm_g, ctx.rstdf, dhf)
+        for l in range(self.nl - 1, -1, -1):
+            W, a = self.layers[l], ctx.layers[l]
+            dact = ops.gemm(dx16, W["WdT"])                                        # [M,F]
+            ops.swiglu_bwd_(a.gu, dact, F)                                         # gu <- [dgate | dup]
+            dh2 = ops.gemm(a.gu, W["WguT"])                                        # [M,H]
+            dmid32, dmid16 = ops.rmsnorm_bwd(a.x_mid, W["g2"], a.rstd2, dh2, dres_in=dx32)
+            datt = ops.gemm(dmid16, W["WoT"])                                      # [M,Nq]
+            dqkv = torch.empty(M, self.Nqkv + Ra, dtype=bf16, device=self.dev)
+            ops.attention_bwd(a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + self.Nkv], a.qkv[:, self.Nq + self.Nkv:],
+                              ctx.mask, a.att, a.lse, datt, B, L, self.nh, self.nkv, self.hd, causal=True,
+                              dq=dqkv[:, :self.Nq], dk=dqkv[:, self.Nq:self.Nq + self.Nkv],
+                              dv=dqkv[:, self.Nq + self.Nkv:self.Nqkv])
+            ops.rope_(dqkv, 0, self.nh + self.nkv, self.hd, cos_t, sin_t, L, backward=True)
+            ops.gemm(dqkv[:, :self.Nqkv], W["Bblk"], out=dqkv[:, self.Nqkv:], N=Ra, block_n=64)
+            for j, n in enumerate(self.LORA_TARGETS):
+                name = f"model.layers.{l}.self_attn.{n}"
+                c0, w = self._target_cols(n)
+                ops.lora_wgrad_(a.h1_aug[:, :H], dqkv[:, self.Nqkv + j * r:], self.lora.gA[name], H, 1, H, r, 1.0)
+                ops.lora_wgrad_(dqkv[:, c0:c0 + w], a.h1_aug[:, H + j * r:], self.lora.gB[name], 1, r, w, r, self.lora.scale)
+            if l == 0:
+                break                                                              # embeddings frozen
+            dh1 = ops.gemm(dqkv, W["WqkvT_aug"])                                   # [M,H]
+            dx32, dx16 = ops.rmsnorm_bwd(a.x_in, W["g1"], a.rstd1, dh1, dres_in=dmid32)

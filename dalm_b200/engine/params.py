@@ -1,0 +1,101 @@
+"""HF-named parameter dictionaries: seeded random init (no checkpoints are reachable offline) and directory loading."""
+from __future__ import annotations
+
+import json
+import os
+from typing import Dict
+
+import torch
+
+
+def _normal(gen: torch.Generator, shape, std: float, dtype, device) -> torch.Tensor:
+    # generate on CPU in fp32 for cross-device reproducibility, chunked to bound host memory
+    t = torch.empty(shape, dtype=torch.float32)
+    t.normal_(mean=0.0, std=std, generator=gen)
+    return t.to(device=device, dtype=dtype)
+
+
+def random_state_dict(kind: str, cfg: Dict, seed: int = 0, dtype=torch.float32, device="cpu") -> Dict[str, torch.Tensor]:
+    """HF parameter names for BertModel (no prefix) / LlamaForCausalLM, init N(0, initializer_range), LN = (1, 0)."""
+    gen = torch.Generator().manual_seed(seed)
+    std = float(cfg.get("initializer_range", 0.02))
+    H = cfg["hidden_size"]
+    sd: Dict[str, torch.Tensor] = {}
+    ones = lambda n: torch.ones(n, dtype=dtype, device=device)
+    zeros = lambda n: torch.zeros(n, dtype=dtype, device=device)
+    if kind == "bert":
+        F, V = cfg["intermediate_size"], cfg["vocab_size"]
+        sd["embeddings.word_embeddings.weight"] = _normal(gen, (V, H), std, dtype, device)
+        sd["embeddings.position_embeddings.weight"] = _normal(gen, (cfg["max_position_embeddings"], H), std, dtype, device)
+        sd["embeddings.token_type_embeddings.weight"] = _normal(gen, (cfg["type_vocab_size"], H), std, dtype, device)
+        sd["embeddings.LayerNorm.weight"] = ones(H)
+        sd["embeddings.LayerNorm.bias"] = zeros(H)
+        for l in range(cfg["num_hidden_layers"]):
+            p = f"encoder.layer.{l}."
+            for n in ("query", "key", "value"):
+                sd[p + f"attention.self.{n}.weight"] = _normal(gen, (H, H), std, dtype, device)
+                sd[p + f"attention.self.{n}.bias"] = _normal(gen, (H,), std, dtype, device)
+            sd[p + "attention.output.dense.weight"] = _normal(gen, (H, H), std, dtype, device)
+            sd[p + "attention.output.dense.bias"] = _normal(gen, (H,), std, dtype, device)
+            sd[p + "attention.output.LayerNorm.weight"] = ones(H) + _normal(gen, (H,), std, dtype, device)
+            sd[p + "attention.output.LayerNorm.bias"] = _normal(gen, (H,), std, dtype, device)
+            sd[p + "intermediate.dense.weight"] = _normal(gen, (F, H), std, dtype, device)
+            sd[p + "intermediate.dense.bias"] = _normal(gen, (F,), std, dtype, device)
+            sd[p + "output.dense.weight"] = _normal(gen, (H, F), std, dtype, device)
+            sd[p + "output.dense.bias"] = _normal(gen, (H,), std, dtype, device)
+            sd[p + "output.LayerNorm.weight"] = ones(H) + _normal(gen, (H,), std, dtype, device)
+            sd[p + "output.LayerNorm.bias"] = _normal(gen, (H,), std, dtype, device)
+        sd["pooler.dense.weight"] = _normal(gen, (H, H), std, dtype, device)   # loaded by AutoModel, unused by the path
+        sd["pooler.dense.bias"] = zeros(H)
+    elif kind == "llama":
+        F, V = cfg["intermediate_size"], cfg["vocab_size"]
+        nh, nkv = cfg["num_attention_heads"], cfg.get("num_key_value_heads", cfg["num_attention_heads"])
+        hd = cfg.get("head_dim", H // nh)
+        sd["model.embed_tokens.weight"] = _normal(gen, (V, H), std, dtype, device)
+        for l in range(cfg["num_hidden_layers"]):
+            p = f"model.layers.{l}."
+            sd[p + "self_attn.q_proj.weight"] = _normal(gen, (nh * hd, H), std, dtype, device)
+            sd[p + "self_attn.k_proj.weight"] = _normal(gen, (nkv * hd, H), std, dtype, device)
+            sd[p + "self_attn.v_proj.weight"] = _normal(gen, (nkv * hd, H), std, dtype, device)
+            sd[p + "self_attn.o_proj.weight"] = _normal(gen, (H, nh * hd), std, dtype, device)
+            sd[p + "mlp.gate_proj.weight"] = _normal(gen, (F, H), std, dtype, device)
+            sd[p + "mlp.up_proj.weight"] = _normal(gen, (F, H), std, dtype, device)
+            sd[p + "mlp.down_proj.weight"] = _normal(gen, (H, F), std, dtype, device)
+            sd[p + "input_layernorm.weight"] = ones(H) + _normal(gen, (H,), std, dtype, device)
+            sd[p + "post_attention_layernorm.weight"] = ones(H) + _normal(gen, (H,), std, dtype, device)
+        sd["model.norm.weight"] = ones(H) + _normal(gen, (H,), std, dtype, device)
+        sd["lm_head.weight"] = _normal(gen, (V, H), std, dtype, device)
+    else:
+        raise ValueError(f"unknown model kind {kind!r}")
+    return sd
+
+
+def load_config(path: str) -> Dict:
+    with open(os.path.join(path, "config.json")) as f:
+        return json.load(f)
+
+
+def load_state_dict(path: str) -> Dict[str, torch.Tensor]:
+    """Reads *.safetensors (single or sharded) or pytorch_model.bin from an HF-layout directory."""
+    from safetensors.torch import load_file
+
+    files = sorted(f for f in os.listdir(path) if f.endswith(".safetensors") and not f.startswith("adapter"))
+    sd: Dict[str, torch.Tensor] = {}
+    if files:
+        for f in files:
+            sd.update(load_file(os.path.join(path, f)))
+        return sd
+    binf = os.path.join(path, "pytorch_model.bin")
+    if os.path.exists(binf):
+        return torch.load(binf, map_location="cpu", weights_only=True)
+    raise FileNotFoundError(f"no weights (model.safetensors / pytorch_model.bin) under {path}")
+
+
+def model_kind(cfg: Dict) -> str:
+    mt = cfg.get("model_type", "")
+    if mt == "bert":
+        return "bert"
+    if mt == "llama":
+        return "llama"
+    raise NotImplementedError(
+        f"model_type {mt!r} is not built yet in dalm_b200 (supported: bert encoders, llama decoders); see DESIGN.md")

@@ -1,0 +1,297 @@
+"""Tensor-level wrappers over the C ABI (one function per kernel entry point).
+
+PyTorch is used here only to own device memory and the current stream; all arithmetic happens in libdalm_b200.so.
+Every wrapper validates device / dtype / contiguity and then passes raw pointers.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+i64 = torch.int64
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype, name: str, inner_contig: bool = True) -> None:
+    if not t.is_cuda:
+        raise _lib.DalmB200Error(f"{name}: expected a CUDA tensor (dalm_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.DalmB200Error(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if inner_contig and t.dim() > 0 and t.stride(-1) != 1:
+        raise _lib.DalmB200Error(f"{name}: innermost dimension must be contiguous")
+
+
+def _ld(t: torch.Tensor) -> int:
+    """row stride (elements) of a 2-D row-major view"""
+    return t.stride(0) if t.dim() == 2 else t.stride(-2)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# loss path
+# ----------------------------------------------------------------------------------------------------------------
+def marginal_counts(gen_mask: torch.Tensor, qlen: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    _chk(gen_mask, i64, "gen_mask"); _chk(qlen, i64, "qlen")
+    gen_mask = gen_mask.contiguous(); qlen = qlen.contiguous()
+    B, L = gen_mask.shape
+    cvec = torch.empty(B, dtype=f32, device=gen_mask.device)
+    nsum = torch.empty(1, dtype=f32, device=gen_mask.device)
+    _lib.call("dalm_b200_marginal_counts", _p(gen_mask), _p(qlen), B, L, _p(cvec), _p(nsum), _stream())
+    return cvec, nsum
+
+
+def inbatch_loss(q: torch.Tensor, p: torch.Tensor, logit_scale: float, cvec: Optional[torch.Tensor] = None,
+                 nsum: Optional[torch.Tensor] = None, need_grad: bool = True, grad_out: float = 1.0):
+    """returns dict(S, dlp, losses[4]={Lc, doc, Lc+doc, N}, dQ, dP)"""
+    _chk(q, f32, "q"); _chk(p, f32, "p")
+    q = q.contiguous(); p = p.contiguous()
+    B, D = q.shape
+    if p.shape != q.shape:
+        raise _lib.DalmB200Error(f"inbatch_loss: q {tuple(q.shape)} and p {tuple(p.shape)} must match (in-batch negatives)")
+    dev = q.device
+    S = torch.empty(B, B, dtype=f32, device=dev)
+    dlp = torch.empty(B, dtype=f32, device=dev)
+    losses = torch.empty(4, dtype=f32, device=dev)
+    dQ = torch.empty_like(q) if need_grad else None
+    dP = torch.empty_like(p) if need_grad else None
+    _lib.call("dalm_b200_inbatch_loss_fwd_bwd", _p(q), _p(p), B, D, float(logit_scale), _p(cvec), _p(nsum), _p(S),
+              _p(dlp), _p(losses), _p(dQ), _p(dP), float(grad_out), _stream())
+    return {"S": S, "dlp": dlp, "losses": losses, "dQ": dQ, "dP": dP}
+
+
+def ce_marginal(logits: torch.Tensor, ids: torch.Tensor, mask: torch.Tensor, nsum: torch.Tensor,
+                need_grad: bool = True, inplace: bool = False, grad_out: float = 1.0):
+    """logits [B,L,V] bf16|fp32 -> (tok_lp [B,L] fp32, dlogits or None)"""
+    if logits.dtype not in (bf16, f32):
+        raise _lib.DalmB200Error(f"ce_marginal: logits dtype {logits.dtype} unsupported")
+    _chk(logits, logits.dtype, "logits"); _chk(ids, i64, "ids"); _chk(mask, i64, "mask")
+    B, L, V = logits.shape
+    logits = logits if logits.is_contiguous() else logits.contiguous()
+    ids = ids.contiguous(); mask = mask.contiguous()
+    tok_lp = torch.empty(B, L, dtype=f32, device=logits.device)
+    dl = None
+    if need_grad:
+        dl = logits if inplace else torch.empty_like(logits)
+    _lib.call("dalm_b200_ce_marginal_fwd_bwd", _p(logits), _p(dl), 0 if logits.dtype == bf16 else 1, _p(ids), _p(mask),
+              _p(nsum), _p(tok_lp), B, L, V, V, float(grad_out), _stream())
+    return tok_lp, dl
+
+
+def finalize_loss(tok_lp: torch.Tensor, mask: torch.Tensor, nsum: torch.Tensor,
+                  inbatch_losses: Optional[torch.Tensor]) -> torch.Tensor:
+    B, L = tok_lp.shape
+    out = torch.empty(4, dtype=f32, device=tok_lp.device)
+    _lib.call("dalm_b200_finalize_loss", _p(tok_lp), _p(mask.contiguous()), B, L, _p(nsum), _p(inbatch_losses), _p(out), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GEMM
+# ----------------------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, out_dtype=bf16, alpha: float = 1.0,
+         bias: Optional[torch.Tensor] = None, act: int = 0, resid: Optional[torch.Tensor] = None, block_n: int = 0,
+         max_ctas: int = 0, K: Optional[int] = None, N: Optional[int] = None) -> torch.Tensor:
+    """out[M,N] = act(alpha * a[M,K] @ b[N,K]^T + bias) + resid.   a, b: bf16 2-D views with contiguous rows."""
+    _chk(a, bf16, "gemm a"); _chk(b, bf16, "gemm b")
+    M = a.shape[0]
+    K = a.shape[1] if K is None else K
+    N = b.shape[0] if N is None else N
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=a.device)
+    if out.dtype not in (bf16, f32):
+        raise _lib.DalmB200Error("gemm: out must be bf16 or fp32")
+    if bias is not None:
+        _chk(bias, f32, "gemm bias")
+    rf32 = 0
+    if resid is not None:
+        if resid.dtype not in (bf16, f32):
+            raise _lib.DalmB200Error("gemm: resid must be bf16 or fp32")
+        rf32 = 1 if resid.dtype == f32 else 0
+    _lib.call("dalm_b200_gemm_bf16_tn", _p(a), _ld(a), _p(b), _ld(b), _p(out), _ld(out), 1 if out.dtype == f32 else 0,
+              M, N, K, float(alpha), _p(bias), int(act), _p(resid), _ld(resid) if resid is not None else 0, rf32,
+              int(block_n), int(max_ctas), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# attention
+# ----------------------------------------------------------------------------------------------------------------
+def attention_fwd(q, k, v, mask, B: int, L: int, Hq: int, Hkv: int, D: int, causal: bool, out=None,
+                  scale: Optional[float] = None):
+    """q/k/v: bf16 token-major 2-D views [B*L, H*D] (may be column slices of one qkv buffer). -> (out, lse)"""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _chk(t, bf16, n)
+    if out is None:
+        out = torch.empty(B * L, Hq * D, dtype=bf16, device=q.device)
+    lse = torch.empty(B, Hq, L, dtype=f32, device=q.device)
+    scale = 1.0 / math.sqrt(D) if scale is None else scale
+    _lib.call("dalm_b200_attention_fwd", _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(mask), _p(out), _ld(out),
+              _p(lse), B, L, Hq, Hkv, D, float(scale), 1 if causal else 0, _stream())
+    return out, lse
+
+
+def attention_bwd(q, k, v, mask, out, lse, d_out, B: int, L: int, Hq: int, Hkv: int, D: int, causal: bool,
+                  dq=None, dk=None, dv=None, scale: Optional[float] = None):
+    dev = q.device
+    if dq is None: dq = torch.empty(B * L, Hq * D, dtype=bf16, device=dev)
+    if dk is None: dk = torch.empty(B * L, Hkv * D, dtype=bf16, device=dev)
+    if dv is None: dv = torch.empty(B * L, Hkv * D, dtype=bf16, device=dev)
+    delta = torch.empty(B, Hq, L, dtype=f32, device=dev)
+    scale = 1.0 / math.sqrt(D) if scale is None else scale
+    _lib.call("dalm_b200_attention_bwd", _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(mask), _p(out), _ld(out),
+              _p(lse), _p(d_out), _ld(d_out), _p(delta), _p(dq), _ld(dq), _p(dk), _ld(dk), _p(dv), _ld(dv),
+              B, L, Hq, Hkv, D, float(scale), 1 if causal else 0, _stream())
+    return dq, dk, dv
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# row-wise
+# ----------------------------------------------------------------------------------------------------------------
+def layernorm_fwd(z, gamma, beta, eps: float, y16=None, want_f32: bool = True):
+    _chk(z, f32, "z")
+    M, H = z.shape
+    y32 = torch.empty_like(z) if want_f32 else None
+    if y16 is None:
+        y16 = torch.empty(M, H, dtype=bf16, device=z.device)
+    mean = torch.empty(M, dtype=f32, device=z.device); rstd = torch.empty_like(mean)
+    _lib.call("dalm_b200_layernorm_fwd", _p(z), _p(gamma), _p(beta), _p(y32), _p(y16), _ld(y16), _p(mean), _p(rstd), M, H,
+              float(eps), _stream())
+    return y32, y16, mean, rstd
+
+
+def layernorm_bwd(z, gamma, mean, rstd, dy_f32=None, dy_bf16=None, want_f32: bool = True, dz16=None, want_bf16: bool = True):
+    M, H = z.shape
+    dz32 = torch.empty_like(z) if want_f32 else None
+    if want_bf16 and dz16 is None:
+        dz16 = torch.empty(M, H, dtype=bf16, device=z.device)
+    _lib.call("dalm_b200_layernorm_bwd", _p(z), _p(gamma), _p(mean), _p(rstd), _p(dy_f32), _p(dy_bf16),
+              _ld(dy_bf16) if dy_bf16 is not None else 0, _p(dz32), _p(dz16), _ld(dz16) if dz16 is not None else 0, M, H,
+              _stream())
+    return dz32, dz16
+
+
+def rmsnorm_fwd(x, g, eps: float, h=None):
+    _chk(x, f32, "x")
+    M, H = x.shape
+    if h is None:
+        h = torch.empty(M, H, dtype=bf16, device=x.device)
+    rstd = torch.empty(M, dtype=f32, device=x.device)
+    _lib.call("dalm_b200_rmsnorm_fwd", _p(x), _p(g), _p(h), _ld(h), _p(rstd), M, H, float(eps), _stream())
+    return h, rstd
+
+
+def rmsnorm_bwd(x, g, rstd, dh, dres_in=None, dres_out=None, dres16=None, want_bf16: bool = True):
+    M, H = x.shape
+    if dres_out is None:
+        dres_out = torch.empty_like(x)
+    if want_bf16 and dres16 is None:
+        dres16 = torch.empty(M, H, dtype=bf16, device=x.device)
+    _lib.call("dalm_b200_rmsnorm_bwd", _p(x), _p(g), _p(rstd), _p(dh), _ld(dh), _p(dres_in), _p(dres_out), _p(dres16),
+              _ld(dres16) if dres16 is not None else 0, M, H, _stream())
+    return dres_out, dres16
+
+
+def bert_embed(ids, word, pos, type_emb):
+    B, L = ids.shape
+    V, H = word.shape
+    z = torch.empty(B * L, H, dtype=f32, device=ids.device)
+    _lib.call("dalm_b200_bert_embed", _p(ids.contiguous()), _p(word), _p(pos), _p(type_emb), _p(z), B * L, L, H, V, _stream())
+    return z
+
+
+def embed_gather(ids, table):
+    M = ids.numel()
+    V, H = table.shape
+    x = torch.empty(M, H, dtype=f32, device=ids.device)
+    _lib.call("dalm_b200_embed_gather", _p(ids.contiguous()), _p(table), _p(x), M, H, V, _stream())
+    return x
+
+
+def rope_(buf, col0: int, nheads: int, D: int, cos_t, sin_t, L: int, backward: bool = False):
+    M = buf.shape[0]
+    _lib.call("dalm_b200_rope", _p(buf), _ld(buf), col0, nheads, D, _p(cos_t), _p(sin_t), M, L, 1 if backward else 0, _stream())
+    return buf
+
+
+def swiglu_fwd(gu, F: int, act=None):
+    M = gu.shape[0]
+    if act is None:
+        act = torch.empty(M, F, dtype=bf16, device=gu.device)
+    _lib.call("dalm_b200_swiglu_fwd", _p(gu), _ld(gu), _p(act), _ld(act), M, F, _stream())
+    return act
+
+
+def swiglu_bwd_(gu, dact, F: int):
+    _lib.call("dalm_b200_swiglu_bwd", _p(gu), _ld(gu), _p(dact), _ld(dact), gu.shape[0], F, _stream())
+    return gu
+
+
+def gelu_fwd(pre, act=None):
+    M, F = pre.shape
+    if act is None:
+        act = torch.empty(M, F, dtype=bf16, device=pre.device)
+    _lib.call("dalm_b200_gelu_fwd", _p(pre), _ld(pre), _p(act), _ld(act), M, F, _stream())
+    return act
+
+
+def gelu_bwd_(pre, dact):
+    M, F = pre.shape
+    _lib.call("dalm_b200_gelu_bwd", _p(pre), _ld(pre), _p(dact), _ld(dact), M, F, _stream())
+    return dact
+
+
+def pool_norm_fwd(hidden, mask, normalize: bool = True):
+    B, L, H = hidden.shape
+    _chk(hidden, f32, "hidden"); _chk(mask, i64, "mask")
+    pooled = torch.empty(B, H, dtype=f32, device=hidden.device)
+    emb = torch.empty_like(pooled)
+    norm = torch.empty(B, dtype=f32, device=hidden.device)
+    _lib.call("dalm_b200_pool_norm_fwd", _p(hidden.contiguous()), _p(mask.contiguous()), _p(pooled), _p(emb), _p(norm), B, L, H,
+              1 if normalize else 0, _stream())
+    return emb, norm
+
+
+def pool_norm_bwd(emb, norm, d_emb, mask, L: int, normalize: bool = True):
+    B, H = emb.shape
+    d_hidden = torch.empty(B, L, H, dtype=f32, device=emb.device)
+    _lib.call("dalm_b200_pool_norm_bwd", _p(emb), _p(norm), _p(d_emb.contiguous()), _p(mask.contiguous()), _p(d_hidden), B, L, H,
+              1 if normalize else 0, _stream())
+    return d_hidden
+
+
+def lora_wgrad_(x, g, out, so_r: int, so_k: int, K: int, R: int, scale: float = 1.0):
+    """out[r*so_r + k*so_k] += scale * sum_m g[m,r] x[m,k]"""
+    M = x.shape[0]
+    _lib.call("dalm_b200_lora_wgrad", _p(x), _ld(x), _p(g), _ld(g), _p(out), so_r, so_k, M, K, R, float(scale), _stream())
+    return out
+
+
+def pack_scaled_bf16_(src, si_r: int, si_c: int, dst, rows: int, cols: int, scale: float):
+    _lib.call("dalm_b200_pack_scaled_bf16", _p(src), si_r, si_c, _p(dst), _ld(dst), rows, cols, float(scale), _stream())
+    return dst
+
+
+def cast_f32_bf16(src, dst=None):
+    M, N = src.shape
+    if dst is None:
+        dst = torch.empty(M, N, dtype=bf16, device=src.device)
+    _lib.call("dalm_b200_cast_f32_bf16", _p(src), _ld(src), _p(dst), _ld(dst), M, N, _stream())
+    return dst
+
+
+def adam_step_(p, g, m, v, lr: float, beta1: float, beta2: float, eps: float, step: int, grad_scale: float = 1.0):
+    _lib.call("dalm_b200_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+              int(step), float(grad_scale), _stream())
+    return p

@@ -1,0 +1,100 @@
+/* dalm_b200 — C ABI of the B200-native RAG-e2e / retriever-only training-step kernels.
+ *
+ * The reference (arcee-ai/DALM) has no FFI: its hot path is Python calling PyTorch/HF/PEFT library kernels. Each entry
+ * point below cites the reference call site whose library work it replaces (paths relative to the reference root).
+ *
+ * Conventions: plain pointers to DEVICE memory + sizes, a cudaStream_t passed as void*, no torch types. Every function
+ * returns 0 on success; on failure it returns non-zero and dalm_b200_last_error() holds the message. Functions never
+ * allocate or free caller memory. bf16 = raw 16-bit bfloat16; "token-major" = row index b*L + l.
+ */
+#ifndef DALM_B200_H
+#define DALM_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library plumbing ---- */
+const char* dalm_b200_last_error(void);
+const char* dalm_b200_version(void);
+long long   dalm_b200_launch_count(void);          /* kernels launched by this library since the last reset */
+void        dalm_b200_reset_launch_count(void);
+int         dalm_b200_probe_device(void);          /* 0 iff the current device is sm_100 */
+
+/* ---- loss path ----
+ * marginal_counts: c_b / N of marginalize_log_probs + the mask normaliser
+ *   (dalm/training/utils/train_utils.py:96-110,135-136). */
+int dalm_b200_marginal_counts(const int64_t* gen_mask, const int64_t* qlen, int B, int L, float* cvec, float* nsum,
+                              void* stream);
+/* inbatch_loss_fwd_bwd: get_cosine_sim + get_nt_xent_loss(S) + get_nt_xent_loss(S^T), the doc log-prob
+ *   log_softmax(S,1).diag() and the backward of all of them in ONE launch
+ *   (train_utils.py:76-88,124; loop body dalm/training/rag_e2e/train_rage2e.py:441-446,
+ *    dalm/training/retriever_only/train_retriever_only.py:371-373).
+ *   losses[4] = {Lc, doc_term, Lc+doc_term, N}. cvec/nsum NULL => retriever-only (no marginal term). dQ/dP NULL => fwd only. */
+int dalm_b200_inbatch_loss_fwd_bwd(const float* Q, const float* P, int B, int D, float logit_scale, const float* cvec,
+                                   const float* nsum, float* S, float* dlp, float* losses, float* dQ, float* dP,
+                                   float grad_out, void* stream);
+/* ce_marginal_fwd_bwd: log_softmax over the vocabulary + gather + mask weights + d(logits)
+ *   (train_utils.py:113-138). dtype 0 = bf16, 1 = fp32. dlogits may alias logits or be NULL. tok_lp: [B,L]. */
+int dalm_b200_ce_marginal_fwd_bwd(const void* logits, void* dlogits, int dtype, const int64_t* ids, const int64_t* mask,
+                                  const float* nsum, float* tok_lp, int B, int L, int V, long long ld, float grad_out,
+                                  void* stream);
+/* finalize_loss: out4 = {Lc, Lm, Lc+Lm, N}; combined_loss of train_rage2e.py:467. */
+int dalm_b200_finalize_loss(const float* tok_lp, const int64_t* mask, int B, int L, const float* nsum,
+                            const float* inbatch_losses, float* out4, void* stream);
+
+/* ---- dense contractions (tcgen05 / TMEM / TMA) ----
+ * out[M,N] = act(alpha * A[M,K] B[N,K]^T + bias) + resid. Replaces every nn.Linear forward / dgrad reached through
+ * dalm/models/rag_e2e_base_model.py:93,105 and dalm/models/retriever_only_base_model.py:58 (HF modeling code -> cuBLAS). */
+int dalm_b200_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo,
+                           int out_f32, int M, int N, int K, float alpha, const float* bias, int act, const void* resid,
+                           long long ldr, int resid_f32, int block_n, int max_ctas, void* stream);
+void dalm_b200_gemm_clear_cache(void);
+
+/* ---- attention (same call sites; HF eager/SDPA attention) ---- */
+int dalm_b200_attention_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                            const int64_t* mask, void* out, long long ldo, float* lse, int B, int L, int Hq, int Hkv,
+                            int D, float scale, int causal, void* stream);
+int dalm_b200_attention_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                            const int64_t* mask, const void* out, long long ldo, const float* lse, const void* d_out,
+                            long long lddo, float* delta, void* dq, long long lddq, void* dk, long long lddk, void* dv,
+                            long long lddv, int B, int L, int Hq, int Hkv, int D, float scale, int causal, void* stream);
+
+/* ---- row-wise pieces of the encoder / decoder blocks ---- */
+int dalm_b200_layernorm_fwd(const float* z, const float* gamma, const float* beta, float* y32, void* y16, long long ld16,
+                            float* mean, float* rstd, int M, int H, float eps, void* stream);
+int dalm_b200_layernorm_bwd(const float* z, const float* gamma, const float* mean, const float* rstd, const float* dy_f32,
+                            const void* dy_bf16, long long ldb, float* dz32, void* dz16, long long ld16, int M, int H,
+                            void* stream);
+int dalm_b200_rmsnorm_fwd(const float* x, const float* g, void* h, long long ldh, float* rstd, int M, int H, float eps,
+                          void* stream);
+int dalm_b200_rmsnorm_bwd(const float* x, const float* g, const float* rstd, const void* dh, long long lddh,
+                          const float* dres_in, float* dres_out, void* dres16, long long ld16, int M, int H, void* stream);
+int dalm_b200_bert_embed(const int64_t* ids, const void* word, const void* pos, const void* type0, float* z, int M, int L,
+                         int H, int V, void* stream);
+int dalm_b200_embed_gather(const int64_t* ids, const void* table, float* x, int M, int H, int V, void* stream);
+int dalm_b200_rope(void* buf, long long ld, int col0, int nheads, int D, const float* cos_t, const float* sin_t, int M,
+                   int L, int backward, void* stream);
+int dalm_b200_swiglu_fwd(const void* gu, long long ldgu, void* act, long long lda, int M, int F, void* stream);
+int dalm_b200_swiglu_bwd(void* gu, long long ldgu, const void* dact, long long ldd, int M, int F, void* stream);
+int dalm_b200_gelu_fwd(const void* pre, long long ldp, void* act, long long lda, int M, int F, void* stream);
+int dalm_b200_gelu_bwd(const void* pre, long long ldp, void* dact, long long ldd, int M, int F, void* stream);
+/* mean_pooling + F.normalize (rag_e2e_base_model.py:96-97,108-111; retriever_only_base_model.py:60-68) */
+int dalm_b200_pool_norm_fwd(const float* hidden, const int64_t* mask, float* pooled, float* emb, float* norm, int B, int L,
+                            int H, int normalize, void* stream);
+int dalm_b200_pool_norm_bwd(const float* emb, const float* norm, const float* d_emb, const int64_t* mask, float* d_hidden,
+                            int B, int L, int H, int normalize, void* stream);
+
+/* ---- LoRA (peft.LoraConfig r=8 alpha=16: rag_e2e_base_model.py:144-160) and optimizer (train_rage2e.py:336) ---- */
+int dalm_b200_lora_wgrad(const void* X, long long ldx, const void* G, long long ldg, float* out, long long so_r,
+                         long long so_k, int M, int K, int R, float scale, void* stream);
+int dalm_b200_pack_scaled_bf16(const float* in, long long si_r, long long si_c, void* out, long long ldo, int rows,
+                               int cols, float scale, void* stream);
+int dalm_b200_cast_f32_bf16(const float* in, long long ldi, void* out, long long ldo, int rows, int cols, void* stream);
+int dalm_b200_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                        float eps, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DALM_B200_H */

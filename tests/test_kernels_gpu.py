@@ -1,0 +1,291 @@
+"""-m gpu: every C-ABI kernel against a plain torch fp32/fp64 reference of the same op (floating-point kernels), on
+seeded inputs. Tolerances are written next to each check."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GEMM (tcgen05)
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 64, 64, 64), (128, 128, 128, 128), (128, 256, 256, 256),       # single tile per config
+    (256, 512, 1024, 0), (900, 1024, 1024, 0), (3204, 3072, 1048, 0),     # ragged M, K-augmented (1024+24)
+    (4608, 4096, 4112, 256), (300, 24, 1024, 64), (77, 4096, 512, 128),   # LoRA-down shape N=24, tiny M
+    (1000, 1000, 72, 0),                                                  # K tail inside one k-block
+])
+def test_gemm_plain(cuda_dev, M, N, K, bn):
+    from dalm_b200 import ops
+    torch.manual_seed(M + N + K)
+    a = (torch.randn(M, K, device=cuda_dev) * 0.5).to(bf16)
+    b = (torch.randn(N, K, device=cuda_dev) * 0.5).to(bf16)
+    out = ops.gemm(a, b, block_n=bn)
+    ref = a.float() @ b.float().t()
+    # bf16 output rounding: rel 2^-9 per element; accumulate order differs only in fp32
+    assert _rel(out.float(), ref) < 4e-3
+    assert torch.isfinite(out.float()).all()
+
+
+def test_gemm_multi_tile_per_cta(cuda_dev):
+    """force few CTAs so each walks many tiles: exercises the smem ring wrap-around and both TMEM accumulator stages"""
+    from dalm_b200 import ops
+    torch.manual_seed(0)
+    M, N, K = 1024, 2048, 768
+    a = (torch.randn(M, K, device=cuda_dev) * 0.5).to(bf16)
+    b = (torch.randn(N, K, device=cuda_dev) * 0.5).to(bf16)
+    ref = a.float() @ b.float().t()
+    for bn in (64, 128, 256):
+        for ctas in (1, 3, 7):
+            out = ops.gemm(a, b, block_n=bn, max_ctas=ctas, out_dtype=f32)
+            assert _rel(out, ref) < 1e-5, (bn, ctas)
+
+
+def test_gemm_epilogues(cuda_dev):
+    from dalm_b200 import ops
+    torch.manual_seed(1)
+    M, N, K = 515, 1032, 520
+    a = (torch.randn(M, K, device=cuda_dev) * 0.3).to(bf16)
+    b = (torch.randn(N, K, device=cuda_dev) * 0.3).to(bf16)
+    bias = torch.randn(N, device=cuda_dev)
+    r32 = torch.randn(M, N, device=cuda_dev)
+    r16 = torch.randn(M, N, device=cuda_dev).to(bf16)
+    acc = a.float() @ b.float().t()
+    out = ops.gemm(a, b, out_dtype=f32, bias=bias, resid=r32, alpha=0.5)
+    assert _rel(out, 0.5 * acc + bias + r32) < 1e-5
+    out = ops.gemm(a, b, out_dtype=f32, bias=bias, act=1)
+    assert _rel(out, torch.nn.functional.gelu(acc + bias)) < 1e-5
+    out = ops.gemm(a, b, out_dtype=bf16, resid=r16)
+    assert _rel(out.float(), acc + r16.float()) < 4e-3
+    # strided views: A and output are column slices of wider buffers (the LoRA K-augmentation layout)
+    wide_a = torch.zeros(M, K + 24, device=cuda_dev, dtype=bf16); wide_a[:, :K] = a
+    wide_o = torch.zeros(M, N + 40, device=cuda_dev, dtype=bf16)
+    ops.gemm(wide_a[:, :K], b, out=wide_o[:, 40:])
+    assert _rel(wide_o[:, 40:].float(), acc) < 4e-3
+    assert wide_o[:, :40].abs().max().item() == 0
+
+
+def test_gemm_rejects_bad_args(cuda_dev):
+    from dalm_b200 import ops, _lib
+    a = torch.zeros(16, 12, device=cuda_dev, dtype=bf16)
+    b = torch.zeros(16, 12, device=cuda_dev, dtype=bf16)
+    with pytest.raises(_lib.DalmB200Error):
+        ops.gemm(a, b)                       # K=12 not a multiple of 8
+    with pytest.raises(_lib.DalmB200Error):
+        ops.gemm(a.cpu(), b.cpu())           # no CPU path
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# attention
+# ----------------------------------------------------------------------------------------------------------------
+def _attn_ref(q, k, v, mask, causal, B, L, Hq, Hkv, D):
+    # q: [B*L, Hq*D] etc. fp64 reference with the same masking convention (-inf on dropped keys)
+    qh = q.double().view(B, L, Hq, D).transpose(1, 2)
+    kh = k.double().view(B, L, Hkv, D).transpose(1, 2).repeat_interleave(Hq // Hkv, dim=1)
+    vh = v.double().view(B, L, Hkv, D).transpose(1, 2).repeat_interleave(Hq // Hkv, dim=1)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(D)
+    if mask is not None:
+        s = s.masked_fill(mask.view(B, 1, 1, L) == 0, float("-inf"))
+    if causal:
+        s = s.masked_fill(torch.triu(torch.ones(L, L, device=q.device, dtype=torch.bool), 1), float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    p = torch.nan_to_num(p, nan=0.0)          # fully masked rows -> zero output
+    o = (p @ vh).transpose(1, 2).reshape(B * L, Hq * D)
+    return o
+
+
+@pytest.mark.parametrize("B,L,Hq,Hkv,D,causal,pad", [
+    (2, 50, 4, 4, 64, False, "right"), (3, 128, 2, 2, 64, False, "right"), (2, 37, 3, 3, 32, False, "right"),
+    (2, 256, 2, 2, 128, True, "none"), (2, 200, 4, 4, 128, True, "right"), (2, 96, 4, 4, 128, True, "left"),
+    (1, 130, 4, 1, 64, True, "right"),
+])
+def test_attention_fwd_bwd(cuda_dev, B, L, Hq, Hkv, D, causal, pad):
+    from dalm_b200 import ops
+    torch.manual_seed(B * 1000 + L)
+    dev = cuda_dev
+    qkv = (torch.randn(B * L, (Hq + 2 * Hkv) * D, device=dev)).to(bf16)
+    q, k, v = qkv[:, :Hq * D], qkv[:, Hq * D:(Hq + Hkv) * D], qkv[:, (Hq + Hkv) * D:]
+    mask = torch.ones(B, L, dtype=torch.int64, device=dev)
+    if pad == "right":
+        for b in range(B):
+            mask[b, L - 3 - 5 * b:] = 0
+    elif pad == "left":
+        for b in range(B):
+            mask[b, :4 + 3 * b] = 0
+    out, lse = ops.attention_fwd(q, k, v, mask, B, L, Hq, Hkv, D, causal)
+    qd, kd, vd = (t.detach().double().requires_grad_(True) for t in (q, k, v))
+    ref = _attn_ref(qd, kd, vd, mask, causal, B, L, Hq, Hkv, D)
+    valid = torch.ones(B, L, dtype=torch.bool, device=dev)
+    if causal and pad == "left":
+        valid = mask.bool()                   # fully-masked (left pad) query rows: compared separately below
+    vrows = valid.view(-1)
+    # bf16 P and bf16 output: ~1e-2 relative on the tile
+    assert _rel(out.float()[vrows], ref[vrows]) < 1.5e-2
+    if causal and pad == "left":
+        assert out.float()[~vrows].abs().max().item() == 0.0      # fully masked rows produce zeros
+    d_out = torch.randn(B * L, Hq * D, device=dev).to(bf16)
+    d_out_eff = d_out.clone()
+    d_out_eff[~vrows] = 0
+    ref.backward(d_out_eff.double())
+    dq, dk, dv = ops.attention_bwd(q, k, v, mask, out, lse, d_out_eff, B, L, Hq, Hkv, D, causal)
+    assert _rel(dq.float(), qd.grad) < 3e-2
+    assert _rel(dk.float(), kd.grad) < 3e-2
+    assert _rel(dv.float(), vd.grad) < 3e-2
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# row-wise kernels
+# ----------------------------------------------------------------------------------------------------------------
+def test_layernorm_fwd_bwd(cuda_dev):
+    from dalm_b200 import ops
+    torch.manual_seed(2)
+    M, H = 333, 1024
+    z = torch.randn(M, H, device=cuda_dev) * 2 + 0.3
+    g = torch.randn(H, device=cuda_dev); b = torch.randn(H, device=cuda_dev)
+    y32, y16, mean, rstd = ops.layernorm_fwd(z, g, b, 1e-12)
+    zd = z.double().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(zd, (H,), g.double(), b.double(), 1e-12)
+    assert _rel(y32, ref) < 1e-5
+    assert _rel(y16.float(), ref) < 4e-3
+    dy_a = torch.randn(M, H, device=cuda_dev)
+    dy_b = torch.randn(M, H, device=cuda_dev).to(bf16)
+    ref.backward(dy_a.double() + dy_b.double())
+    dz32, dz16 = ops.layernorm_bwd(z, g, mean, rstd, dy_f32=dy_a, dy_bf16=dy_b)
+    assert _rel(dz32, zd.grad) < 1e-4
+    assert _rel(dz16.float(), zd.grad) < 4e-3
+
+
+def test_rmsnorm_fwd_bwd(cuda_dev):
+    from dalm_b200 import ops
+    torch.manual_seed(3)
+    M, H = 257, 4096
+    x = torch.randn(M, H, device=cuda_dev) * 1.7
+    g = torch.rand(H, device=cuda_dev) + 0.5
+    h, rstd = ops.rmsnorm_fwd(x, g, 1e-5)
+    xd = x.double().requires_grad_(True)
+    ref = xd * torch.rsqrt(xd.pow(2).mean(-1, keepdim=True) + 1e-5) * g.double()
+    assert _rel(h.float(), ref) < 4e-3
+    dh = torch.randn(M, H, device=cuda_dev).to(bf16)
+    dres = torch.randn(M, H, device=cuda_dev)
+    ref.backward(dh.double())
+    out32, out16 = ops.rmsnorm_bwd(x, g, rstd, dh, dres_in=dres)
+    assert _rel(out32, xd.grad + dres.double()) < 1e-5
+    assert _rel(out16.float(), xd.grad + dres.double()) < 4e-3
+
+
+def test_embeddings_rope_swiglu_gelu(cuda_dev):
+    from dalm_b200 import ops
+    torch.manual_seed(4)
+    dev = cuda_dev
+    B, L, H, V = 3, 17, 128, 500
+    ids = torch.randint(0, V, (B, L), device=dev)
+    word = torch.randn(V, H, device=dev).to(bf16); pos = torch.randn(64, H, device=dev).to(bf16)
+    typ = torch.randn(H, device=dev).to(bf16)
+    z = ops.bert_embed(ids, word, pos, typ)
+    ref = word[ids.view(-1)].float() + pos[torch.arange(L, device=dev).repeat(B)].float() + typ.float()
+    assert torch.equal(z, ref)
+    x = ops.embed_gather(ids, word)
+    assert torch.equal(x, word[ids.view(-1)].float())
+    # rope (HF rotate_half convention)
+    D, nh = 64, 3
+    buf = torch.randn(B * L, nh * D + 8, device=dev).to(bf16)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, D, 2, dtype=torch.float32) / D))
+    fr = torch.outer(torch.arange(L, dtype=torch.float32), inv)
+    cos_t, sin_t = fr.cos().to(dev), fr.sin().to(dev)
+    xh = buf[:, :nh * D].float().view(B, L, nh, D)
+    c = torch.cat([cos_t, cos_t], -1)[None, :, None, :]; s = torch.cat([sin_t, sin_t], -1)[None, :, None, :]
+    rot = torch.cat([-xh[..., D // 2:], xh[..., :D // 2]], -1)
+    ref = (xh * c + rot * s).reshape(B * L, nh * D)
+    tail = buf[:, nh * D:].clone()
+    work = buf.clone()
+    ops.rope_(work, 0, nh, D, cos_t, sin_t, L)
+    assert _rel(work[:, :nh * D].float(), ref) < 4e-3
+    assert torch.equal(work[:, nh * D:], tail)
+    ops.rope_(work, 0, nh, D, cos_t, sin_t, L, backward=True)          # inverse rotation restores the input
+    assert _rel(work[:, :nh * D].float(), buf[:, :nh * D].float()) < 8e-3
+    # swiglu
+    M, F = 50, 264
+    gu = torch.randn(M, 2 * F, device=dev).to(bf16)
+    act = ops.swiglu_fwd(gu, F)
+    gd = gu.double().requires_grad_(True)
+    ref = torch.nn.functional.silu(gd[:, :F]) * gd[:, F:]
+    assert _rel(act.float(), ref) < 4e-3
+    dact = torch.randn(M, F, device=dev).to(bf16)
+    ref.backward(dact.double())
+    g2 = gu.clone()
+    ops.swiglu_bwd_(g2, dact, F)
+    assert _rel(g2.float(), gd.grad) < 4e-3
+    # gelu
+    pre = torch.randn(M, F, device=dev).to(bf16)
+    a = ops.gelu_fwd(pre)
+    pd = pre.double().requires_grad_(True)
+    ref = torch.nn.functional.gelu(pd)
+    assert _rel(a.float(), ref) < 4e-3
+    d = torch.randn(M, F, device=dev).to(bf16)
+    ref.backward(d.double())
+    d2 = d.clone()
+    ops.gelu_bwd_(pre, d2)
+    assert _rel(d2.float(), pd.grad) < 4e-3
+
+
+def test_pool_norm(cuda_dev):
+    from dalm_b200 import ops
+    from oracle import pooling
+    torch.manual_seed(5)
+    B, L, H = 5, 23, 384
+    hid = torch.randn(B, L, H, device=cuda_dev)
+    mask = torch.ones(B, L, dtype=torch.int64, device=cuda_dev)
+    mask[0, 10:] = 0; mask[3, 1:] = 0
+    emb, norm = ops.pool_norm_fwd(hid, mask, True)
+    hd = hid.double().cpu().requires_grad_(True)
+    ref = pooling.normalize(pooling.mean_pooling(hd, mask.cpu()).double())
+    assert _rel(emb.cpu(), ref) < 1e-5
+    d = torch.randn(B, H, device=cuda_dev)
+    ref.backward(d.double().cpu())
+    dh = ops.pool_norm_bwd(emb, norm, d, mask, L, True)
+    assert _rel(dh.cpu(), hd.grad) < 1e-5
+    emb2, _ = ops.pool_norm_fwd(hid, mask, False)
+    assert _rel(emb2.cpu(), pooling.mean_pooling(hid.cpu(), mask.cpu())) < 1e-5
+
+
+def test_lora_wgrad_pack_adam(cuda_dev):
+    from dalm_b200 import ops
+    torch.manual_seed(6)
+    dev = cuda_dev
+    M, K, R = 1000, 520, 8
+    x = torch.randn(M, K + 24, device=dev).to(bf16)
+    g = torch.randn(M, 40, device=dev).to(bf16)
+    out = torch.zeros(R, K, device=dev)
+    ops.lora_wgrad_(x[:, :K], g[:, 16:], out, K, 1, K, R, 2.0)
+    ref = 2.0 * g[:, 16:24].double().t() @ x[:, :K].double()
+    assert _rel(out, ref) < 1e-5
+    outT = torch.zeros(K, R, device=dev)
+    ops.lora_wgrad_(x[:, :K], g[:, 16:], outT, 1, R, K, R, 2.0)
+    ops.lora_wgrad_(x[:, :K], g[:, 16:], outT, 1, R, K, R, 2.0)          # accumulates
+    assert _rel(outT, 2 * ref.t()) < 1e-5
+    # pack
+    src = torch.randn(K, R, device=dev)
+    dst = torch.zeros(R + 2, K + 8, device=dev, dtype=bf16)
+    ops.pack_scaled_bf16_(src, 1, R, dst[1:, 8:], R, K, 2.0)
+    assert torch.equal(dst[1:R + 1, 8:], (src.t() * 2.0).to(bf16))
+    assert dst[0].abs().max() == 0 and dst[:, :8].abs().max() == 0
+    # adam vs torch.optim.Adam
+    n = 10007
+    p = torch.randn(n, device=dev); p_ref = p.clone().requires_grad_(True)
+    m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev)
+    opt = torch.optim.Adam([p_ref], lr=1e-3)
+    for step in range(1, 4):
+        grad = torch.randn(n, device=dev)
+        p_ref.grad = grad.clone()
+        opt.step()
+        ops.adam_step_(p, grad, m, v, 1e-3, 0.9, 0.999, 1e-8, step)
+    assert (p - p_ref.detach()).abs().max().item() < 1e-6
