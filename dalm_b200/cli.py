@@ -1,0 +1,146 @@
+"""`dalm` command line — the hot-path commands of the reference's typer app (dalm/cli.py:17,35-38,41-167,170-277):
+`version`, `train-rag-e2e`, `train-retriever-only`, same argument order / option names / defaults. The remaining
+reference commands (qa-gen, eval-rag, eval-retriever) belong to subsystems outside this build's scope and say so."""
+from __future__ import annotations
+
+from enum import Enum
+from typing import Optional
+
+import typer
+from typing_extensions import Annotated
+
+from . import __version__
+
+cli = typer.Typer(add_completion=False, help="B200-native DALM training step")
+
+
+class DALMSchedulerType(str, Enum):
+    LINEAR = "linear"
+    COSINE = "cosine"
+    COSINE_WITH_RESTARTS = "cosine_with_restarts"
+    POLYNOMIAL = "polynomial"
+    CONSTANT = "constant"
+    CONSTANT_WITH_WARMUP = "constant_with_warmup"
+
+
+class PeftMode(str, Enum):
+    generator = "generator"
+    retriever = "retriever"
+    both = "both"
+
+
+Arg, Opt = typer.Argument, typer.Option
+
+
+@cli.command()
+def version() -> None:
+    """Print the current version of DALM"""
+    print(f"🐾You are running DALM version: {__version__}")
+
+
+@cli.command()
+def train_rag_e2e(
+    dataset_path: Annotated[str, Arg(help="hf dataset dir or csv file", show_default=False)],
+    retriever_name_or_path: Annotated[str, Arg(help="retriever model directory / id", show_default=False)],
+    generator_name_or_path: Annotated[str, Arg(help="(causal) generator model directory / id", show_default=False)],
+    passage_column_name: Annotated[str, Opt(help="column holding the passage")] = "Abstract",
+    query_column_name: Annotated[str, Opt(help="column holding the query")] = "Question",
+    answer_column_name: Annotated[str, Opt(help="column holding the answer")] = "Answer",
+    query_max_len: Annotated[int, Opt(help="max query tokens (truncation)")] = 50,
+    passage_max_len: Annotated[int, Opt(help="max passage tokens (truncation)")] = 128,
+    generator_max_len: Annotated[int, Opt(help="max generator-input tokens (truncation)")] = 256,
+    per_device_train_batch_size: Annotated[int, Opt(help="batch size per GPU")] = 32,
+    learning_rate: Annotated[float, Opt(help="initial learning rate after warmup")] = 1e-4,
+    logit_scale: Annotated[int, Opt(help="similarity logit scale")] = 100,
+    weight_decay: Annotated[float, Opt(help="accepted for compatibility (unused by the reference too)")] = 0.0,
+    num_train_epochs: Annotated[int, Opt(help="epochs")] = 1,
+    max_train_steps: Annotated[Optional[int], Opt(help="overrides num_train_epochs")] = None,
+    gradient_accumulation_steps: Annotated[int, Opt(help="micro-steps per optimizer step")] = 1,
+    lr_scheduler_type: Annotated[DALMSchedulerType, Opt(help="scheduler")] = DALMSchedulerType.LINEAR,
+    num_warmup_steps: Annotated[int, Opt(help="warmup steps")] = 100,
+    output_dir: Annotated[Optional[str], Opt(help="where to store the final adapters")] = None,
+    seed: Annotated[int, Opt(help="seed")] = 42,
+    hub_model_id: Annotated[Optional[str], Opt(help="accepted, unused")] = None,
+    hub_token: Annotated[Optional[str], Opt(help="accepted, unused")] = None,
+    checkpointing_steps: Annotated[Optional[str], Opt(help="save state every N steps or 'epoch'")] = None,
+    resume_from_checkpoint: Annotated[Optional[str], Opt(help="checkpoint folder to resume from")] = None,
+    with_tracking: Annotated[bool, Opt(help="enable experiment tracking")] = True,
+    report_to: Annotated[str, Opt(help="tracker selection")] = "all",
+    sanity_test: Annotated[bool, Opt(help="accepted, unused")] = True,
+    use_peft: Annotated[Optional[PeftMode], Opt(help="which sub-models get LoRA adapters")] = None,
+    use_bnb: Annotated[Optional[PeftMode], Opt(help="NF4 quantisation (not built)")] = None,
+    retriever_is_autoregressive: Annotated[bool, Opt(help="autoregressive retriever (not built)")] = False,
+) -> None:
+    """End-to-end train an in-domain model, including the retriever and generator"""
+    from transformers import SchedulerType
+
+    from .models.rag_e2e_base_model import Mode
+    from .training.rag_e2e.train_rage2e import train_e2e
+
+    kw = dict(locals())
+    for k in ("SchedulerType", "Mode", "train_e2e"):
+        kw.pop(k, None)
+    kw["dataset_or_path"] = kw.pop("dataset_path")
+    kw["lr_scheduler_type"] = SchedulerType(lr_scheduler_type.value)
+    kw["use_peft"] = Mode(use_peft.value) if use_peft is not None else None
+    kw["use_bnb"] = Mode(use_bnb.value) if use_bnb is not None else None
+    train_e2e(**kw)
+
+
+@cli.command()
+def train_retriever_only(
+    retriever_name_or_path: Annotated[str, Arg(help="retriever model directory / id", show_default=False)],
+    dataset_path: Annotated[str, Arg(help="hf dataset dir or csv file", show_default=False)],
+    passage_column_name: Annotated[str, Opt(help="column holding the passage")] = "Abstract",
+    query_column_name: Annotated[str, Opt(help="column holding the query")] = "Question",
+    query_max_len: Annotated[int, Opt(help="max query tokens (truncation)")] = 50,
+    passage_max_len: Annotated[int, Opt(help="max passage tokens (truncation)")] = 128,
+    per_device_train_batch_size: Annotated[int, Opt(help="batch size per GPU")] = 32,
+    learning_rate: Annotated[float, Opt(help="initial learning rate after warmup")] = 1e-4,
+    logit_scale: Annotated[int, Opt(help="similarity logit scale")] = 100,
+    weight_decay: Annotated[float, Opt(help="accepted, unused")] = 0.0,
+    num_train_epochs: Annotated[int, Opt(help="epochs")] = 3,
+    max_train_steps: Annotated[Optional[int], Opt(help="overrides num_train_epochs")] = None,
+    gradient_accumulation_steps: Annotated[int, Opt(help="micro-steps per optimizer step")] = 1,
+    lr_scheduler_type: Annotated[DALMSchedulerType, Opt(help="scheduler")] = DALMSchedulerType.LINEAR,
+    num_warmup_steps: Annotated[int, Opt(help="warmup steps")] = 0,
+    output_dir: Annotated[Optional[str], Opt(help="where to store the final adapter")] = None,
+    seed: Annotated[int, Opt(help="seed")] = 42,
+    hub_model_id: Annotated[Optional[str], Opt(help="accepted, unused")] = None,
+    hub_token: Annotated[Optional[str], Opt(help="accepted, unused")] = None,
+    checkpointing_steps: Annotated[Optional[str], Opt(help="save state every N steps or 'epoch'")] = None,
+    resume_from_checkpoint: Annotated[Optional[str], Opt(help="checkpoint folder to resume from")] = None,
+    with_tracking: Annotated[bool, Opt(help="enable experiment tracking")] = True,
+    report_to: Annotated[str, Opt(help="tracker selection")] = "all",
+    sanity_test: Annotated[bool, Opt(help="accepted, unused")] = True,
+    use_peft: Annotated[bool, Opt(help="train LoRA adapters")] = True,
+    use_bnb: Annotated[bool, Opt(help="NF4 quantisation (not built: runs bf16)")] = True,
+    is_autoregressive: Annotated[bool, Opt(help="autoregressive retriever (not built)")] = False,
+) -> None:
+    """Train only the retriever using contrastive training"""
+    from transformers import SchedulerType
+
+    from .training.retriever_only.train_retriever_only import train_retriever
+
+    kw = dict(locals())
+    for k in ("SchedulerType", "train_retriever"):
+        kw.pop(k, None)
+    kw["dataset_or_path"] = kw.pop("dataset_path")
+    kw["lr_scheduler_type"] = SchedulerType(lr_scheduler_type.value)
+    train_retriever(**kw)
+
+
+def _out_of_scope(name: str):
+    def cmd() -> None:
+        print(f"`dalm {name}` belongs to a reference subsystem outside dalm_b200's scope (training hot path only); "
+              "see DESIGN.md.")
+        raise typer.Exit(code=2)
+    cmd.__doc__ = f"(reference command, not part of the B200 hot-path build)"
+    return cmd
+
+
+for _n in ("qa-gen", "eval-rag", "eval-retriever"):
+    cli.command(name=_n)(_out_of_scope(_n))
+
+if __name__ == "__main__":
+    cli()

@@ -409,3 +409,36 @@ extern "C" int dalm_b200_finalize_loss(const float* tok_lp, const int64_t* mask,
   count_launch();
   return check_launch("finalize_loss_kernel");
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// small fp32 matmul for the stand-alone (non-fused) API functions: get_cosine_sim forward/backward on [B,D] x [B,D]
+// (reference train_utils.py:76-77). C[M,N] = alpha * opA(A)[M,K] * opB(B)[K,N]; row-major; 16x16 smem tiles.
+// ------------------------------------------------------------------------------------------------------------
+namespace dalm {
+__global__ void small_matmul_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                                        int M, int N, int K, int transA, int transB, float alpha) {
+  __shared__ float sa[16][17], sb[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    const int ka = k0 + tx, kb = k0 + ty;
+    sa[ty][tx] = (row < M && ka < K) ? (transA ? A[(size_t)ka * M + row] : A[(size_t)row * K + ka]) : 0.f;
+    sb[ty][tx] = (kb < K && col < N) ? (transB ? B[(size_t)col * K + kb] : B[(size_t)kb * N + col]) : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = fmaf(sa[ty][k], sb[k][tx], acc);
+    __syncthreads();
+  }
+  if (row < M && col < N) C[(size_t)row * N + col] = acc * alpha;
+}
+}  // namespace dalm
+
+extern "C" int dalm_b200_small_matmul_f32(const float* A, const float* B, float* C, int M, int N, int K, int transA,
+                                          int transB, float alpha, void* stream) {
+  DALM_REQUIRE(M > 0 && N > 0 && K > 0, "small_matmul: empty problem");
+  dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
+  dalm::small_matmul_f32_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(A, B, C, M, N, K, transA, transB, alpha);
+  dalm::count_launch();
+  return dalm::check_launch("small_matmul_f32_kernel");
+}

@@ -1,0 +1,137 @@
+"""B200-native `AutoModelForRagE2E` — same constructor, attributes and methods as the reference wrapper
+(dalm/models/rag_e2e_base_model.py:16-160), with the HF/PEFT modules behind it replaced by the dalm_b200 engine
+(hand-written sm_100a kernels through the C ABI). There is no CPU or eager-PyTorch fallback.
+"""
+from __future__ import annotations
+
+import logging
+import os
+from enum import Enum
+from typing import Dict, Optional
+
+import torch
+
+from .. import ops
+from ..engine import params
+from ..engine.bert import BertEncoder
+from ..engine.bridge import EncodeFn, GenerateFn, PoolFn
+from ..engine.llama import LlamaDecoder
+
+logger = logging.getLogger(__name__)
+
+
+class Mode(str, Enum):                       # reference :16-19
+    GENERATOR = "generator"
+    RETRIEVER = "retriever"
+    BOTH = "both"
+
+
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("dalm_b200 needs a CUDA (sm_100a) device: there is no CPU path for the training step")
+    return torch.device("cuda", int(os.environ.get("LOCAL_RANK", torch.cuda.current_device())))
+
+
+def load_tokenizer(name_or_path: str):
+    from transformers import AutoTokenizer
+
+    return AutoTokenizer.from_pretrained(name_or_path)
+
+
+def build_encoder(name_or_path: str, lora: bool, device: torch.device, state_dict: Optional[Dict] = None,
+                  cfg: Optional[Dict] = None) -> BertEncoder:
+    cfg = cfg or params.load_config(name_or_path)
+    if params.model_kind(cfg) != "bert":
+        raise NotImplementedError("retriever must be a BERT-family encoder (bge-*) in this build; autoregressive "
+                                  "retrievers are listed as 'next' in DESIGN.md")
+    sd = state_dict if state_dict is not None else params.load_state_dict(name_or_path)
+    return BertEncoder(cfg, sd, device=device, lora=lora)
+
+
+def build_decoder(name_or_path: str, lora: bool, device: torch.device, state_dict: Optional[Dict] = None,
+                  cfg: Optional[Dict] = None) -> LlamaDecoder:
+    cfg = cfg or params.load_config(name_or_path)
+    params.model_kind(cfg)                       # raises for unsupported families (e.g. falcon: DESIGN.md "next")
+    sd = state_dict if state_dict is not None else params.load_state_dict(name_or_path)
+    return LlamaDecoder(cfg, sd, device=device, lora=lora)
+
+
+class AutoModelForRagE2E(torch.nn.Module):
+    def __init__(
+        self,
+        retriever_name: str,
+        generator_name: str,
+        normalize: bool = True,
+        get_peft: Optional[Mode] = None,
+        use_bnb: Optional[Mode] = None,
+        retriever_is_autoregressive: bool = False,
+        *,
+        _retriever: Optional[BertEncoder] = None,
+        _generator: Optional[LlamaDecoder] = None,
+        _load_tokenizers: bool = True,
+    ) -> None:
+        super().__init__()
+        if use_bnb is not None:
+            raise NotImplementedError("use_bnb (bitsandbytes NF4) is outside BASELINE.json's configs (bf16 forward); "
+                                      "not built — see DESIGN.md")
+        if retriever_is_autoregressive:
+            raise NotImplementedError("retriever_is_autoregressive is not built yet — see DESIGN.md")
+        get_peft = Mode(get_peft) if get_peft is not None else None
+        dev = _device()
+        lora_r = get_peft in (Mode.RETRIEVER, Mode.BOTH)
+        lora_g = get_peft in (Mode.GENERATOR, Mode.BOTH)
+        if not (lora_r and lora_g):
+            logger.warning("dalm_b200 trains LoRA adapters only (PEFT mode); sub-models without adapters are frozen. "
+                           "Full fine-tuning (reference default use_peft=None) is not built yet — see DESIGN.md")
+        self.retriever_model = _retriever if _retriever is not None else build_encoder(retriever_name, lora_r, dev)
+        self.generator_model = _generator if _generator is not None else build_decoder(generator_name, lora_g, dev)
+        self.retriever_tokenizer = load_tokenizer(retriever_name) if _load_tokenizers else None
+        self.generator_tokenizer = load_tokenizer(generator_name) if _load_tokenizers else None
+        self.normalize = normalize
+        self.retriever_is_autoregressive = retriever_is_autoregressive
+
+    # ---- reference :83-99 -------------------------------------------------------------------------------------
+    def retrieval_forward(self, input_ids: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
+        enc = self.retriever_model
+        ids = input_ids.to(enc.dev, torch.int64).contiguous()
+        mask = attention_mask.to(enc.dev, torch.int64).contiguous()
+        if enc.lora is not None and torch.is_grad_enabled():
+            return EncodeFn.apply(enc.lora_flat, enc, ids, mask, self.normalize)
+        hid, _ = enc.forward_hidden(ids, mask, save=False)
+        emb, _ = ops.pool_norm_fwd(hid, mask, self.normalize)
+        return emb
+
+    # ---- reference :101-106 -----------------------------------------------------------------------------------
+    def forward(self, task: str, input_ids: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
+        if task == "retrieval":
+            return self.retrieval_forward(input_ids, attention_mask)
+        dec = self.generator_model
+        ids = input_ids.to(dec.dev, torch.int64).contiguous()
+        mask = attention_mask.to(dec.dev, torch.int64).contiguous()
+        if dec.lora is not None and torch.is_grad_enabled():
+            return GenerateFn.apply(dec.lora_flat, dec, ids, mask)
+        logits, _ = dec.forward_logits(ids, mask, save=False)
+        return logits
+
+    # ---- reference :108-111 -----------------------------------------------------------------------------------
+    def mean_pooling(self, model_output: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
+        return PoolFn.apply(model_output, attention_mask.to(model_output.device, torch.int64).contiguous())
+
+    # ---- reference :113-134 -----------------------------------------------------------------------------------
+    def attach_pre_trained_peft_layers(self, peft_retriever_path: Optional[str], peft_generator_path: Optional[str],
+                                       device: str) -> None:
+        from ..training.utils.train_utils import load_adapter_dir
+
+        if peft_retriever_path is not None:
+            load_adapter_dir(self.retriever_model, peft_retriever_path)
+        if peft_generator_path is not None:
+            load_adapter_dir(self.generator_model, peft_generator_path)
+
+    # ---- optimizer-facing helpers -----------------------------------------------------------------------------
+    def trainable_banks(self):
+        return [m.lora for m in (self.retriever_model, self.generator_model) if m.lora is not None]
+
+    def repack(self) -> None:
+        """refresh the bf16 LoRA blocks inside the fused weights after an optimizer step"""
+        self.retriever_model.repack_lora()
+        self.generator_model.repack_lora()

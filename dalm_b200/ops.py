@@ -97,6 +97,17 @@ def finalize_loss(tok_lp: torch.Tensor, mask: torch.Tensor, nsum: torch.Tensor,
     return out
 
 
+def small_matmul(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: bool = False, alpha: float = 1.0) -> torch.Tensor:
+    """fp32 C = alpha * op(a) @ op(b) for the small [B,D] matrices of the stand-alone similarity API"""
+    _chk(a, f32, "a"); _chk(b, f32, "b")
+    a = a.contiguous(); b = b.contiguous()
+    M, K = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    N = b.shape[0] if trans_b else b.shape[1]
+    c = torch.empty(M, N, dtype=f32, device=a.device)
+    _lib.call("dalm_b200_small_matmul_f32", _p(a), _p(b), _p(c), M, N, K, 1 if trans_a else 0, 1 if trans_b else 0, float(alpha), _stream())
+    return c
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # GEMM
 # ----------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,181 @@
+"""Shared skeleton of the two trainers. The reference duplicates ~300 lines between
+dalm/training/rag_e2e/train_rage2e.py:229-527 and dalm/training/retriever_only/train_retriever_only.py:175-421; here the
+common part (tokenise -> DataLoader -> Adam + scheduler -> resume -> epoch/step loop -> checkpoints -> final artefacts)
+is one function parameterised by a small `Recipe`, and the per-step work is dalm_b200's fused launch sequence.
+"""
+from __future__ import annotations
+
+import argparse
+import math
+import os
+import random
+from dataclasses import dataclass
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch.utils.data import DataLoader
+
+from ...accel import Accelerator, get_logger, set_seed
+from ...optim import FusedAdam
+from .train_utils import load_model_hook, save_model_hook
+
+logger = get_logger(__name__)
+
+
+@dataclass
+class Recipe:
+    title: str                                   # log banner
+    tracker_project: str                         # accelerator.init_trackers name (reference :368 / :306)
+    build_model: Callable[[], torch.nn.Module]
+    tokenize: Callable[[torch.nn.Module, Any], Any]            # (model, raw_dataset) -> tokenised dataset
+    step: Callable[[torch.nn.Module, Dict[str, torch.Tensor], float, float], Dict[str, torch.Tensor]]
+    banks: Callable[[torch.nn.Module], List[Any]]              # trainable LoRA banks
+    repack: Callable[[torch.nn.Module], None]
+    save_final: Callable[[torch.nn.Module, str], None]
+    map_num_proc: Optional[int] = None
+
+
+def collate(features: List[Dict[str, Any]]) -> Dict[str, torch.Tensor]:
+    """transformers.default_data_collator for this path's features: python int lists -> int64 tensors (reference :331)"""
+    return {k: torch.tensor([f[k] for f in features], dtype=torch.int64) for k in features[0]}
+
+
+def parse_resume(path: str, steps_per_epoch: int, loader_len: int, gas: int) -> Tuple[int, Optional[int], int]:
+    """`epoch_{i}` / `step_{i}` directory names -> (starting_epoch, resume_step, completed_steps); reference :399-411"""
+    tag = os.path.splitext(os.path.basename(os.path.normpath(path)))[0]
+    if "epoch" in tag:
+        start = int(tag.replace("epoch_", "")) + 1
+        return start, None, start * steps_per_epoch
+    resume = int(tag.replace("step_", "")) * gas
+    start = resume // loader_len
+    resume -= start * loader_len
+    return start, resume, resume // gas
+
+
+def run_training(recipe: Recipe, *, dataset_or_path: Any, per_device_train_batch_size: int, learning_rate: float,
+                 logit_scale: float, num_train_epochs: int, max_train_steps: Optional[int],
+                 gradient_accumulation_steps: int, lr_scheduler_type: Any, num_warmup_steps: int,
+                 output_dir: Optional[str], seed: Optional[int], checkpointing_steps: Optional[Any],
+                 resume_from_checkpoint: Optional[str], with_tracking: bool, report_to: str,
+                 config_for_tracker: Dict[str, Any]) -> Dict[str, Any]:
+    from transformers import get_scheduler
+    from tqdm.auto import tqdm
+
+    from ...utils import load_dataset
+
+    accelerator = (Accelerator(log_with=report_to, project_dir=output_dir,
+                               gradient_accumulation_steps=gradient_accumulation_steps)
+                   if with_tracking else Accelerator(gradient_accumulation_steps=gradient_accumulation_steps))
+    logger.info(accelerator.state, main_process_only=False)
+    if seed is not None:
+        set_seed(seed)
+    if accelerator.is_main_process and output_dir is not None:
+        os.makedirs(output_dir, exist_ok=True)
+    accelerator.wait_for_everyone()
+
+    model = recipe.build_model()
+    dataset = load_dataset(dataset_or_path)
+    processed = recipe.tokenize(model, dataset)
+    for index in random.sample(range(len(processed)), min(2, len(processed))):
+        logger.info(f"Sample {index} of the training set: {processed[index]}.")
+
+    gen = torch.Generator()
+    gen.manual_seed(seed if seed is not None else 0)          # same permutation on every rank (accelerate semantics)
+    loader = DataLoader(processed, shuffle=True, collate_fn=collate, batch_size=per_device_train_batch_size,
+                        pin_memory=torch.cuda.is_available(), generator=gen)
+
+    optimizer = FusedAdam(model.parameters(), lr=learning_rate)     # Adam, no weight decay (reference ignores the flag)
+    steps_per_epoch = math.ceil(len(loader) / gradient_accumulation_steps)
+    if max_train_steps is None:
+        max_train_steps = num_train_epochs * steps_per_epoch
+    sched_name = getattr(lr_scheduler_type, "value", lr_scheduler_type)
+    scheduler = get_scheduler(name=sched_name, optimizer=optimizer, num_warmup_steps=num_warmup_steps,
+                              num_training_steps=max_train_steps)
+    model, optimizer, loader, scheduler = accelerator.prepare(model, optimizer, loader, scheduler)
+    steps_per_epoch = math.ceil(len(loader) / gradient_accumulation_steps)
+    num_train_epochs = math.ceil(max_train_steps / steps_per_epoch)
+    if checkpointing_steps is not None and str(checkpointing_steps).isdigit():
+        checkpointing_steps = int(checkpointing_steps)
+    if with_tracking:
+        accelerator.init_trackers(recipe.tracker_project, config_for_tracker)
+    accelerator.register_save_state_pre_hook(save_model_hook)
+    accelerator.register_load_state_pre_hook(load_model_hook)
+
+    total_bs = per_device_train_batch_size * accelerator.num_processes * gradient_accumulation_steps
+    logger.info(f"***** {recipe.title} *****")
+    logger.info(f"  Num examples = {len(processed)}")
+    logger.info(f"  Num Epochs = {num_train_epochs}")
+    logger.info(f"  Instantaneous batch size per device = {per_device_train_batch_size}")
+    logger.info(f"  Total train batch size (w. parallel, distributed & accumulation) = {total_bs}")
+    logger.info(f"  Gradient Accumulation steps = {gradient_accumulation_steps}")
+    logger.info(f"  Total optimization steps = {max_train_steps}")
+
+    progress = tqdm(range(max_train_steps), disable=not accelerator.is_local_main_process)
+    completed, start_epoch, resume_step = 0, 0, None
+    if resume_from_checkpoint:
+        logger.info(f"Resumed from checkpoint: {resume_from_checkpoint}")
+        accelerator.load_state(resume_from_checkpoint)
+        recipe.repack(model)
+        start_epoch, resume_step, completed = parse_resume(resume_from_checkpoint, steps_per_epoch, len(loader),
+                                                           gradient_accumulation_steps)
+    progress.update(completed)
+
+    banks = recipe.banks(model)
+    last_loss = None
+    for epoch in range(start_epoch, num_train_epochs):
+        model.train()
+        total_loss = torch.zeros((), dtype=torch.float32, device=accelerator.device)
+        active = loader
+        if resume_from_checkpoint and epoch == start_epoch and resume_step is not None:
+            active = accelerator.skip_first_batches(loader, resume_step)
+            accelerator._loader = active
+        for step, batch in enumerate(active):
+            with accelerator.accumulate(model):
+                out = recipe.step(model, batch, float(logit_scale), 1.0 / gradient_accumulation_steps)
+                total_loss += accelerator.reduce(out["loss"].detach().float(), reduction="sum")   # rank-SUM (reference :469)
+                accelerator.average_gradients(b.grad for b in banks)
+                if accelerator.sync_gradients:
+                    optimizer.step()
+                    recipe.repack(model)
+                scheduler.step()
+                if accelerator.sync_gradients:
+                    optimizer.zero_grad()
+            if accelerator.sync_gradients:
+                progress.update(1)
+                completed += 1
+            if (step + 1) % 100 == 0:
+                last_loss = (total_loss / (step + 1)).item()
+                logger.info(f"Step: {step + 1}, Loss: {last_loss}")
+                if with_tracking:
+                    accelerator.log({"train/loss": last_loss}, step=completed)
+            if isinstance(checkpointing_steps, int) and checkpointing_steps > 0:
+                if completed % checkpointing_steps == 0 and output_dir is not None and accelerator.sync_gradients:
+                    accelerator.save_state(os.path.join(output_dir, f"step_{completed}"))
+            if completed >= max_train_steps:
+                break
+        epoch_loss = total_loss.item() / max(len(loader), 1)
+        last_loss = epoch_loss
+        logger.info(f"epoch {epoch}: train/epoch_loss = {epoch_loss}")
+        if with_tracking:
+            accelerator.log({"train/epoch_loss": epoch_loss}, step=completed)
+        if output_dir is not None:
+            accelerator.wait_for_everyone()
+            if isinstance(checkpointing_steps, str):
+                accelerator.save_state(os.path.join(output_dir, f"epoch_{epoch}"))
+            if accelerator.is_main_process:
+                recipe.save_final(model, output_dir)
+            accelerator.wait_for_everyone()
+    if with_tracking:
+        accelerator.end_training()
+    return {"completed_steps": completed, "last_loss": last_loss, "model": model}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# argparse tables (the script entry points keep the reference's flag names and ITS argparse defaults, which differ from
+# the function / CLI defaults in several places: SURVEY §5 "Config / flags")
+# ----------------------------------------------------------------------------------------------------------------
+def build_parser(description: str, flags: Sequence[Tuple[str, Dict[str, Any]]]) -> argparse.ArgumentParser:
+    parser = argparse.ArgumentParser(description=description)
+    for name, kw in flags:
+        parser.add_argument(f"--{name}", **kw)
+    return parser

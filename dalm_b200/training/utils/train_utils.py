@@ -1,0 +1,251 @@
+"""Loss functions and checkpoint hooks of the training step — same names and argument meaning as the reference's
+dalm/training/utils/train_utils.py:12-138, executed by the dalm_b200 CUDA kernels.
+
+Two ways in:
+  * the stand-alone functions (`get_cosine_sim`, `get_nt_xent_loss`, `compute_marginalized_loss_from_logits`, ...)
+    are differentiable through torch.autograd so a caller can keep the reference's loop body verbatim;
+  * `fused_rag_step` / `fused_retriever_step` run the whole loop body (reference train_rage2e.py:431-471,
+    train_retriever_only.py:365-376) as one launch sequence without autograd — what dalm_b200's own trainers use.
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import Dict, List, Optional
+
+import torch
+
+from ... import ops
+
+f32, bf16, i64 = torch.float32, torch.bfloat16, torch.int64
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# stand-alone differentiable functions
+# ----------------------------------------------------------------------------------------------------------------
+class _CosineSimFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, p, scale):
+        ctx.save_for_backward(q, p)
+        ctx.scale = float(scale)
+        return ops.small_matmul(q, p, trans_b=True, alpha=float(scale))
+
+    @staticmethod
+    def backward(ctx, dS):
+        q, p = ctx.saved_tensors
+        dS = dS.contiguous().float()
+        dq = ops.small_matmul(dS, p, alpha=ctx.scale)                    # dQ = s * dS P
+        dp = ops.small_matmul(dS, q, trans_a=True, alpha=ctx.scale)      # dP = s * dS^T Q
+        return dq, dp, None
+
+
+def get_cosine_sim(query_embs: torch.Tensor, passage_embs: torch.Tensor, logit_scale: int) -> torch.Tensor:
+    """reference :76-77"""
+    return _CosineSimFn.apply(query_embs.float().contiguous(), passage_embs.float().contiguous(), logit_scale)
+
+
+def _ce_square(scores: torch.Tensor, weights: torch.Tensor, nsum: torch.Tensor):
+    """log_softmax(scores,1).diag() and d/dscores of  -(sum_i w_i * lsm_ii)/nsum  via the vocabulary-CE kernel:
+    the [n,n] matrix is viewed as one sequence of n 'positions' over a vocabulary of n (+1 padding row)."""
+    n = scores.shape[0]
+    dev = scores.device
+    lg = torch.zeros(1, n + 1, n, dtype=f32, device=dev)
+    lg[0, :n] = scores
+    ids = torch.zeros(1, n + 1, dtype=i64, device=dev)
+    ids[0, 1:] = torch.arange(n, device=dev)
+    w = torch.zeros(1, n + 1, dtype=i64, device=dev)
+    w[0, 1:] = weights
+    tok_lp, dl = ops.ce_marginal(lg, ids, w, nsum, need_grad=True)
+    return tok_lp[0, :n], dl[0, :n], w
+
+
+class _NtXentFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scores):
+        n = scores.shape[0]
+        nsum = torch.full((1,), float(n), dtype=f32, device=scores.device)
+        diag_lp, dS, w = _ce_square(scores.float().contiguous(), torch.ones(n, dtype=i64, device=scores.device), nsum)
+        out = ops.finalize_loss(torch.cat([diag_lp, diag_lp.new_zeros(1)]).view(1, n + 1), w, nsum, None)
+        ctx.save_for_backward(dS)
+        return out[1].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        (dS,) = ctx.saved_tensors
+        return dS * g
+
+
+def get_nt_xent_loss(sim_scores: torch.Tensor) -> torch.Tensor:
+    """reference :80-88 — cross_entropy(sim, arange(n)), mean-reduced"""
+    return _NtXentFn.apply(sim_scores)
+
+
+def get_nll(log_probs: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """reference :91-93 (pure indexing: no arithmetic)"""
+    return -torch.gather(log_probs, 2, labels.unsqueeze(2)).squeeze(-1)
+
+
+def marginalize_log_probs(logprobs_logits: torch.Tensor, doc_logprobs: torch.Tensor,
+                          query_token_length: torch.Tensor) -> torch.Tensor:
+    """reference :96-110 (slice / broadcast-add / concat on one sample; kept for API completeness — the training path
+    uses the closed form inside ce_marginal + inbatch kernels)"""
+    q = int(query_token_length)
+    head = logprobs_logits[: q - 1, :]
+    tail = logprobs_logits[q - 1:, :] + doc_logprobs
+    return torch.cat([head, tail], dim=0)
+
+
+class _MarginalizedLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, input_ids, attention_mask, scores, qlen):
+        dev = logits.device
+        ids = input_ids.to(dev, i64).contiguous()
+        mask = attention_mask.to(dev, i64).contiguous()
+        cvec, nsum = ops.marginal_counts(mask, qlen.to(dev, i64).contiguous())
+        lg = logits if logits.dtype in (bf16, f32) else logits.float()
+        tok_lp, dl = ops.ce_marginal(lg.contiguous(), ids, mask, nsum, need_grad=True)
+        # doc term: weights c_b (integer token counts) over the same normaliser N
+        diag_lp, dS, w = _ce_square(scores.float().contiguous(), cvec.to(i64), nsum)
+        n = scores.shape[0]
+        lm_tok = ops.finalize_loss(tok_lp, mask, nsum, None)[1]
+        doc = ops.finalize_loss(torch.cat([diag_lp, diag_lp.new_zeros(1)]).view(1, n + 1), w, nsum, None)[1]
+        ctx.save_for_backward(dl, dS)
+        ctx.logits_dtype = logits.dtype
+        return (lm_tok + doc).clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        dl, dS = ctx.saved_tensors
+        return (dl * g.to(dl.dtype)).to(ctx.logits_dtype), None, None, dS * g, None
+
+
+def compute_marginalized_loss_from_logits(logits: torch.Tensor, input_tensors: torch.Tensor,
+                                          attention_mask: torch.Tensor, scores: torch.Tensor,
+                                          query_token_length: torch.Tensor) -> torch.Tensor:
+    """reference :113-138"""
+    if logits.shape[0] != scores.shape[0] or logits.shape[0] != query_token_length.shape[0]:
+        # zip(..., strict=True) in the reference (:127-129)
+        raise ValueError("logits, scores and query_token_length must have the same batch size")
+    return _MarginalizedLossFn.apply(logits, input_tensors, attention_mask, scores, query_token_length)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# fused loop bodies
+# ----------------------------------------------------------------------------------------------------------------
+def fused_rag_step(rag_model, batch: Dict[str, torch.Tensor], logit_scale: float, backward: bool = True,
+                   grad_scale: float = 1.0) -> Dict[str, torch.Tensor]:
+    """reference train_rage2e.py:431-471 as one launch sequence. Gradients (LoRA) are ACCUMULATED into the banks.
+    returns {"loss": 0-d fp32 tensor, "losses": [Lc, Lm, total, N], "S": [B,B]}"""
+    enc, dec = rag_model.retriever_model, rag_model.generator_model
+    dev = enc.dev
+    g = lambda k: batch[k].to(dev, i64, non_blocking=True).contiguous()
+    q_ids, q_mask = g("retriever_query_input_ids"), g("retriever_query_attention_mask")
+    p_ids, p_mask = g("retriever_passage_input_ids"), g("retriever_passage_attention_mask")
+    g_ids, g_mask, qlen = g("generator_input_input_ids"), g("generator_input_attention_mask"), g("query_passage_input_len")
+    train_enc = backward and enc.lora is not None
+    train_dec = backward and dec.lora is not None
+    hq, cq = enc.forward_hidden(q_ids, q_mask, save=train_enc)
+    q_emb, q_norm = ops.pool_norm_fwd(hq, q_mask, rag_model.normalize)
+    hp, cp = enc.forward_hidden(p_ids, p_mask, save=train_enc)
+    p_emb, p_norm = ops.pool_norm_fwd(hp, p_mask, rag_model.normalize)
+    cvec, nsum = ops.marginal_counts(g_mask, qlen)
+    r = ops.inbatch_loss(q_emb, p_emb, float(logit_scale), cvec, nsum, need_grad=train_enc, grad_out=grad_scale)
+    logits, cg = dec.forward_logits(g_ids, g_mask, save=train_dec)
+    tok_lp, dl = ops.ce_marginal(logits, g_ids, g_mask, nsum, need_grad=train_dec, inplace=True, grad_out=grad_scale)
+    out = ops.finalize_loss(tok_lp, g_mask, nsum, r["losses"])
+    if train_dec:
+        dec.backward_logits(cg, dl)
+    if train_enc:
+        L_p, L_q = p_ids.shape[1], q_ids.shape[1]
+        enc.backward_hidden(cp, ops.pool_norm_bwd(p_emb, p_norm, r["dP"], p_mask, L_p, rag_model.normalize))
+        enc.backward_hidden(cq, ops.pool_norm_bwd(q_emb, q_norm, r["dQ"], q_mask, L_q, rag_model.normalize))
+    return {"loss": out[2], "losses": out, "S": r["S"]}
+
+
+def fused_retriever_step(model, batch: Dict[str, torch.Tensor], logit_scale: float, backward: bool = True,
+                         grad_scale: float = 1.0) -> Dict[str, torch.Tensor]:
+    """reference train_retriever_only.py:365-376"""
+    enc = model.model
+    dev = enc.dev
+    g = lambda k: batch[k].to(dev, i64, non_blocking=True).contiguous()
+    q_ids, q_mask, p_ids, p_mask = g("query_input_ids"), g("query_attention_mask"), g("passage_input_ids"), g("passage_attention_mask")
+    train = backward and enc.lora is not None
+    hq, cq = enc.forward_hidden(q_ids, q_mask, save=train)
+    q_emb, q_norm = ops.pool_norm_fwd(hq, q_mask, model.normalize)
+    hp, cp = enc.forward_hidden(p_ids, p_mask, save=train)
+    p_emb, p_norm = ops.pool_norm_fwd(hp, p_mask, model.normalize)
+    r = ops.inbatch_loss(q_emb, p_emb, float(logit_scale), None, None, need_grad=train, grad_out=grad_scale)
+    if train:
+        enc.backward_hidden(cp, ops.pool_norm_bwd(p_emb, p_norm, r["dP"], p_mask, p_ids.shape[1], model.normalize))
+        enc.backward_hidden(cq, ops.pool_norm_bwd(q_emb, q_norm, r["dQ"], q_mask, q_ids.shape[1], model.normalize))
+    return {"loss": r["losses"][0], "losses": r["losses"], "S": r["S"]}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# checkpoint hooks / adapter IO  (reference :12-73; PEFT adapter layout adapter_config.json + adapter_model.*)
+# ----------------------------------------------------------------------------------------------------------------
+ADAPTER_CONFIG = {
+    "peft_type": "LORA", "r": 8, "lora_alpha": 16, "lora_dropout": 0.05, "bias": "none", "fan_in_fan_out": False,
+    "inference_mode": False, "init_lora_weights": True,
+}
+
+
+def save_adapter_dir(engine_model, out_dir: str, task_type: str, base_name: Optional[str] = None) -> None:
+    os.makedirs(out_dir, exist_ok=True)
+    if engine_model.lora is None:
+        return
+    cfg = dict(ADAPTER_CONFIG, task_type=task_type, target_modules=list(engine_model.LORA_TARGETS),
+               base_model_name_or_path=base_name)
+    with open(os.path.join(out_dir, "adapter_config.json"), "w") as f:
+        json.dump(cfg, f, indent=1)
+    torch.save(engine_model.lora.peft_state_dict(), os.path.join(out_dir, "adapter_model.bin"))
+
+
+def load_adapter_dir(engine_model, in_dir: str) -> None:
+    if engine_model.lora is None:
+        raise RuntimeError("model was built without adapters (get_peft) — nothing to load into")
+    path = os.path.join(in_dir, "adapter_model.bin")
+    if os.path.exists(path):
+        sd = torch.load(path, map_location="cpu", weights_only=True)
+    else:
+        from safetensors.torch import load_file
+
+        sd = load_file(os.path.join(in_dir, "adapter_model.safetensors"))
+    engine_model.lora.load_peft_state_dict(sd)
+    engine_model.repack_lora()
+
+
+def save_model_hook(models: List[torch.nn.Module], weights: List[Dict], output_dir: str) -> None:
+    """reference :16-31: route wrapper weights to <dir>/retriever + <dir>/generator (RAG) or <dir> (sentence embedding)"""
+    from ...models.rag_e2e_base_model import AutoModelForRagE2E
+    from ...models.retriever_only_base_model import AutoModelForSentenceEmbedding
+
+    for i, model in enumerate(models):
+        if isinstance(model, AutoModelForSentenceEmbedding):
+            save_adapter_dir(model.model, output_dir, "FEATURE_EXTRACTION")
+        elif isinstance(model, AutoModelForRagE2E):
+            save_adapter_dir(model.generator_model, os.path.join(output_dir, "generator"), "CAUSAL_LM")
+            save_adapter_dir(model.retriever_model, os.path.join(output_dir, "retriever"), "FEATURE_EXTRACTION")
+        else:
+            raise NotImplementedError(f"Model type {type(model)} not supported")
+        if weights:
+            weights.pop()
+
+
+def load_model_hook(models: List[torch.nn.Module], input_dir: str) -> None:
+    """reference :34-73"""
+    from ...models.rag_e2e_base_model import AutoModelForRagE2E
+    from ...models.retriever_only_base_model import AutoModelForSentenceEmbedding
+
+    while len(models) > 0:
+        model = models.pop()
+        if isinstance(model, AutoModelForRagE2E):
+            for sub, name in ((model.generator_model, "generator"), (model.retriever_model, "retriever")):
+                d = os.path.join(input_dir, name)
+                if sub.lora is not None and os.path.exists(os.path.join(d, "adapter_config.json")):
+                    load_adapter_dir(sub, d)
+        elif isinstance(model, AutoModelForSentenceEmbedding):
+            if model.model.lora is not None and os.path.exists(os.path.join(input_dir, "adapter_config.json")):
+                load_adapter_dir(model.model, input_dir)
+        else:
+            raise NotImplementedError(f"Model type {type(model)} not supported")

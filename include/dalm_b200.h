@@ -43,6 +43,11 @@ int dalm_b200_ce_marginal_fwd_bwd(const void* logits, void* dlogits, int dtype, 
 int dalm_b200_finalize_loss(const float* tok_lp, const int64_t* mask, int B, int L, const float* nsum,
                             const float* inbatch_losses, float* out4, void* stream);
 
+/* small_matmul_f32: stand-alone get_cosine_sim forward / backward (train_utils.py:76-77) for callers that do not use the
+ *   fused in-batch kernel. C[M,N] = alpha * opA(A) * opB(B), row-major fp32. */
+int dalm_b200_small_matmul_f32(const float* A, const float* B, float* C, int M, int N, int K, int transA, int transB,
+                               float alpha, void* stream);
+
 /* ---- dense contractions (tcgen05 / TMEM / TMA) ----
  * out[M,N] = act(alpha * A[M,K] B[N,K]^T + bias) + resid. Replaces every nn.Linear forward / dgrad reached through
  * dalm/models/rag_e2e_base_model.py:93,105 and dalm/models/retriever_only_base_model.py:58 (HF modeling code -> cuBLAS). */
