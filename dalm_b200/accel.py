@@ -86,8 +86,10 @@ class ShardedLoader:
                 emitted += 1
                 group = []
         if group:
+            pad = 0
             while len(group) < self.world:
-                group.append(first[len(group) % len(first)])
+                group.append(first[pad % len(first)])
+                pad += 1
             self.end_of_dataloader = True
             yield group[self.rank]
 

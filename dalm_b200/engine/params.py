@@ -9,7 +9,10 @@ import torch
 
 
 def _normal(gen: torch.Generator, shape, std: float, dtype, device) -> torch.Tensor:
-    # generate on CPU in fp32 for cross-device reproducibility, chunked to bound host memory
+    # CPU generator: reproducible across devices (tests, fixtures). A CUDA generator (bench-scale 7B models) draws on
+    # the device directly.
+    if gen.device.type == "cuda":
+        return torch.empty(shape, dtype=torch.float32, device=gen.device).normal_(0.0, std, generator=gen).to(dtype)
     t = torch.empty(shape, dtype=torch.float32)
     t.normal_(mean=0.0, std=std, generator=gen)
     return t.to(device=device, dtype=dtype)
@@ -17,7 +20,9 @@ def _normal(gen: torch.Generator, shape, std: float, dtype, device) -> torch.Ten
 
 def random_state_dict(kind: str, cfg: Dict, seed: int = 0, dtype=torch.float32, device="cpu") -> Dict[str, torch.Tensor]:
     """HF parameter names for BertModel (no prefix) / LlamaForCausalLM, init N(0, initializer_range), LN = (1, 0)."""
-    gen = torch.Generator().manual_seed(seed)
+    on_device = torch.device(device).type == "cuda" and cfg.get("_device_rng", False)
+    gen = torch.Generator(device=device) if on_device else torch.Generator()
+    gen.manual_seed(seed)
     std = float(cfg.get("initializer_range", 0.02))
     H = cfg["hidden_size"]
     sd: Dict[str, torch.Tensor] = {}

@@ -130,10 +130,46 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
         if resid.dtype not in (bf16, f32):
             raise _lib.DalmB200Error("gemm: resid must be bf16 or fp32")
         rf32 = 1 if resid.dtype == f32 else 0
+    timer = GEMM_TIMER
+    if timer is not None:
+        timer.begin(2.0 * M * N * K)
     _lib.call("dalm_b200_gemm_bf16_tn", _p(a), _ld(a), _p(b), _ld(b), _p(out), _ld(out), 1 if out.dtype == f32 else 0,
               M, N, K, float(alpha), _p(bias), int(act), _p(resid), _ld(resid) if resid is not None else 0, rf32,
               int(block_n), int(max_ctas), _stream())
+    if timer is not None:
+        timer.end()
     return out
+
+
+class GemmTimer:
+    """CUDA-event bracket around every GEMM launch on the launching stream (bench.py's live roofline measurement)."""
+
+    def __init__(self, capacity: int = 4096):
+        self.ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(capacity)]
+        self.flops = []
+        self.n = 0
+
+    def begin(self, flops: float) -> None:
+        if self.n < len(self.ev):
+            self.ev[self.n][0].record()
+            self.flops.append(flops)
+
+    def end(self) -> None:
+        if self.n < len(self.ev):
+            self.ev[self.n][1].record()
+            self.n += 1
+
+    def reset(self) -> None:
+        self.n = 0
+        self.flops = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        ms = [self.ev[i][0].elapsed_time(self.ev[i][1]) for i in range(self.n)]
+        return {"launches": self.n, "total_ms": sum(ms), "total_flops": sum(self.flops[: self.n])}
+
+
+GEMM_TIMER = None
 
 
 # ----------------------------------------------------------------------------------------------------------------

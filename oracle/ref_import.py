@@ -31,6 +31,10 @@ def load() -> SimpleNamespace:
     for name in ("peft", "accelerate", "accelerate.logging", "accelerate.utils"):
         if name not in sys.modules:
             sys.modules[name] = MagicMock()
+    # the repo's own `dalm` alias package installs a meta-path finder mapping dalm.* -> dalm_b200.*: park it
+    parked = [f for f in sys.meta_path if getattr(f, "__name__", "") == "_LazyAlias"]
+    for f in parked:
+        sys.meta_path.remove(f)
     sys.path.insert(0, REFERENCE_ROOT)
     try:
         from dalm.training.utils import train_utils
@@ -41,6 +45,8 @@ def load() -> SimpleNamespace:
         from dalm.utils import eos_mask
     finally:
         sys.path.remove(REFERENCE_ROOT)
+        for f in parked:
+            sys.meta_path.insert(0, f)
         ref_modules = {k: v for k, v in sys.modules.items() if k == "dalm" or k.startswith("dalm.")}
         for k in ref_modules:
             del sys.modules[k]

@@ -1,0 +1,61 @@
+"""CPU, world_size 2 on gloo: the data-parallel plumbing of the trainers (gradient averaging == DDP mean, scalar loss
+sum, disjoint rank-strided batches). The reference gets these from accelerate/DDP implicitly
+(train_rage2e.py:416-418,469,471)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from dalm_b200.accel import Accelerator
+    acc = Accelerator(cpu=True)
+    assert acc.num_processes == world and acc.process_index == rank
+    # gradient averaging of two flat buffers == mean over ranks (what DDP does)
+    g1 = torch.full((1000,), float(rank + 1)); g2 = torch.arange(10.0) * (rank + 1)
+    acc.average_gradients([g1, g2])
+    ok = torch.allclose(g1, torch.full((1000,), 1.5)) and torch.allclose(g2, torch.arange(10.0) * 1.5)
+    # not averaged while accumulating
+    acc.sync_gradients = False
+    g3 = torch.full((4,), float(rank))
+    acc.average_gradients([g3])
+    ok = ok and torch.equal(g3, torch.full((4,), float(rank)))
+    acc.sync_gradients = True
+    # scalar loss: rank SUM (reference :469)
+    tot = acc.reduce(torch.tensor(float(rank + 1)), reduction="sum").item()
+    ok = ok and tot == 3.0
+    # loader sharding: same permutation on both ranks, disjoint batches
+    ds = list(range(23))
+    gen = torch.Generator().manual_seed(42)
+    dl = torch.utils.data.DataLoader(ds, batch_size=4, shuffle=True, generator=gen)
+    sl = acc.prepare(dl)
+    mine = [b.tolist() for b in sl]
+    gathered = [None, None]
+    dist.all_gather_object(gathered, mine)
+    flat0, flat1 = sum(gathered[0], []), sum(gathered[1], [])
+    ok = ok and len(gathered[0]) == len(gathered[1]) == 3 and not (set(flat0[:8]) & set(flat1[:8]))
+    ok = ok and set(flat0) | set(flat1) == set(range(23))
+    acc.wait_for_everyone()
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_data_parallel_plumbing():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs: p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

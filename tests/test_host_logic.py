@@ -1,0 +1,124 @@
+"""CPU: host-side logic of the drop-in surface — CLI, argparse defaults, resume parsing, loader sharding, scheduler."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cli_version_string():
+    """reference tests/test_cli.py:6-8"""
+    import dalm_b200
+    out = subprocess.run([sys.executable, "-m", "dalm_b200.cli", "version"], capture_output=True, text=True, cwd=ROOT,
+                         env=dict(os.environ, PYTHONIOENCODING="utf-8")).stdout.strip()
+    assert out == f"🐾You are running DALM version: {dalm_b200.__version__}"
+
+
+def test_cli_surface():
+    import typer
+    from typer.testing import CliRunner
+    from dalm_b200.cli import cli
+    group = typer.main.get_command(cli)
+    e2e = group.commands["train-rag-e2e"]
+    opts = {o for p in e2e.params for o in p.opts}
+    for opt in ("--passage-column-name", "--query-max-len", "--generator-max-len", "--per-device-train-batch-size",
+                "--logit-scale", "--lr-scheduler-type", "--num-warmup-steps", "--checkpointing-steps", "--use-peft",
+                "--retriever-is-autoregressive", "--with-tracking", "--use-bnb", "--resume-from-checkpoint"):
+        assert opt in opts, opt
+    # positional order differs between the two commands (reference cli.py:41-60 vs :170-185)
+    assert [p.name for p in e2e.params[:3]] == ["dataset_path", "retriever_name_or_path", "generator_name_or_path"]
+    ro = group.commands["train-retriever-only"]
+    assert [p.name for p in ro.params[:2]] == ["retriever_name_or_path", "dataset_path"]
+    d = {p.name: p.default for p in ro.params}
+    assert d["num_train_epochs"] == 3 and d["num_warmup_steps"] == 0 and d["use_peft"] is True and d["passage_max_len"] == 128
+    d = {p.name: p.default for p in e2e.params}
+    assert d["num_warmup_steps"] == 100 and d["per_device_train_batch_size"] == 32 and d["seed"] == 42
+    assert CliRunner().invoke(cli, ["eval-rag"]).exit_code == 2
+
+
+def test_dalm_alias_package():
+    import dalm
+    from dalm.models.rag_e2e_base_model import AutoModelForRagE2E, Mode
+    from dalm.training.utils.train_utils import get_cosine_sim, compute_marginalized_loss_from_logits  # noqa: F401
+    from dalm.training.rag_e2e.train_rage2e import train_e2e  # noqa: F401
+    import dalm_b200.models.rag_e2e_base_model as real
+    assert AutoModelForRagE2E is real.AutoModelForRagE2E and Mode.BOTH.value == "both"
+    assert dalm.__version__ == "0.0.5"
+
+
+def test_script_defaults_differ_like_reference(monkeypatch):
+    """argparse defaults != function defaults (passage_max_len 160 vs 128, retriever bs 8 vs 32, ...)"""
+    import inspect
+    from dalm_b200.training.rag_e2e import train_rage2e as e2e
+    from dalm_b200.training.retriever_only import train_retriever_only as ro
+    monkeypatch.setattr(sys, "argv", ["x", "--retriever_name_or_path", "r", "--generator_name_or_path", "g"])
+    a = e2e.parse_args()
+    assert a.passage_max_len == 160 and a.seed is None and a.with_tracking is False and a.num_warmup_steps == 100
+    sig = inspect.signature(e2e.train_e2e).parameters
+    assert sig["passage_max_len"].default == 128 and sig["seed"].default == 42 and sig["with_tracking"].default is True
+    assert sig["per_device_train_batch_size"].default == 32 and sig["use_peft"].default is None
+    monkeypatch.setattr(sys, "argv", ["x", "--model_name_or_path", "r"])
+    b = ro.parse_args()
+    assert b.per_device_train_batch_size == 8 and b.num_train_epochs == 3 and b.use_peft is False
+    sig = inspect.signature(ro.train_retriever).parameters
+    assert sig["per_device_train_batch_size"].default == 32 and sig["num_train_epochs"].default == 1
+    assert sig["use_peft"].default is True and list(sig)[:2] == ["retriever_name_or_path", "dataset_or_path"]
+
+
+def test_resume_parsing():
+    from dalm_b200.training.utils.loop import parse_resume
+    assert parse_resume("/x/out/epoch_2", steps_per_epoch=50, loader_len=100, gas=2) == (3, None, 150)
+    # step_30 with gas=2 -> 60 loader steps in; loader_len 25 -> epoch 2, 10 steps into it, 5 optimizer steps
+    assert parse_resume("out/step_30/", steps_per_epoch=13, loader_len=25, gas=2) == (2, 10, 5)
+
+
+def test_sharded_loader_matches_accelerate_semantics():
+    from dalm_b200.accel import ShardedLoader
+    batches = list(range(10))
+    seen = [list(ShardedLoader(batches, r, 4)) for r in range(4)]
+    assert seen[0] == [0, 4, 8] and seen[1] == [1, 5, 9] and seen[2] == [2, 6, 0] and seen[3] == [3, 7, 1]
+    assert all(len(ShardedLoader(batches, r, 4)) == 3 for r in range(4))
+    assert list(ShardedLoader(batches, 0, 1, skip=7)) == [7, 8, 9]
+    sl = ShardedLoader(batches, 1, 2)
+    out = []
+    for b in sl:
+        out.append((b, sl.end_of_dataloader))
+    assert out[-1] == (9, True) and not out[0][1]
+
+
+def test_scheduler_wrapper_and_accumulate():
+    from dalm_b200.accel import Accelerator
+    acc = Accelerator(gradient_accumulation_steps=2, cpu=True)
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=1.0)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0 / (1 + s))
+    opt2, sched2 = acc.prepare(opt, sched)
+    steps = []
+    for i in range(4):
+        with acc.accumulate(None):
+            steps.append(acc.sync_gradients)
+            sched2.step()
+    assert steps == [False, True, False, True]
+    assert sched.last_epoch == 2               # stepped only on sync steps (x num_processes == 1)
+    assert acc.reduce(torch.tensor(3.0)).item() == 3.0
+
+
+def test_collate_and_lora_bank_layout():
+    from dalm_b200.training.utils.loop import collate
+    b = collate([{"a": [1, 2], "n": 3}, {"a": [4, 5], "n": 6}])
+    assert b["a"].dtype == torch.int64 and b["a"].tolist() == [[1, 2], [4, 5]] and b["n"].tolist() == [3, 6]
+    from dalm_b200.engine.lora import LoraBank
+    bank = LoraBank([("m.q", 16, 24), ("m.v", 16, 8)], device="cpu")
+    assert bank.numel() == 8 * 16 + 24 * 8 + 8 * 16 + 8 * 8
+    assert bank.A["m.q"].shape == (8, 16) and bank.B["m.q"].shape == (24, 8)
+    assert bank.B["m.q"].abs().max() == 0 and bank.A["m.q"].abs().max() <= 0.25 + 1e-6      # U(-1/sqrt(in), 1/sqrt(in))
+    bank.gA["m.v"].fill_(1.0)
+    assert bank.grad.sum().item() == 8 * 16                  # views alias the flat gradient buffer
+    sd = bank.peft_state_dict()
+    assert "base_model.model.m.q.lora_A.weight" in sd
+    bank2 = LoraBank([("m.q", 16, 24), ("m.v", 16, 8)], device="cpu", seed=5)
+    bank2.load_peft_state_dict(sd)
+    assert torch.equal(bank2.flat, bank.flat)
