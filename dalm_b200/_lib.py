@@ -44,8 +44,10 @@ SIGNATURES = {
     "dalm_b200_gelu_bwd": [_P, _L, _P, _L, _I, _I, _P],
     "dalm_b200_pool_norm_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "dalm_b200_pool_norm_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
-    "dalm_b200_lora_wgrad": [_P, _L, _P, _L, _P, _L, _L, _I, _I, _I, _F, _P],
+    "dalm_b200_lora_wgrad": [_P, _L, _P, _L, _P, _P, _L, _L, _I, _I, _I, _F, _P],
+    "dalm_b200_skinny_gemm": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P],
     "dalm_b200_pack_scaled_bf16": [_P, _L, _L, _P, _L, _I, _I, _F, _P],
+    "dalm_b200_pack_table": [_P, _I, _P],
     "dalm_b200_cast_f32_bf16": [_P, _L, _P, _L, _I, _I, _P],
     "dalm_b200_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P],
 }

@@ -37,6 +37,100 @@ struct GemmEpilogue {
   int M, N, K;
 };
 
+// Epilogue math for one thread = one output row, 32 consecutive columns [col0, col0+32): alpha, bias, GELU, residual.
+__device__ __forceinline__ void epilogue_math(const GemmEpilogue& ep, const uint32_t* v, float* f, int row, int col0, bool row_ok) {
+  const int N = ep.N;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * ep.alpha;
+  if (ep.bias) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) if (col0 + i < N) f[i] += __ldg(ep.bias + col0 + i);
+  }
+  if (ep.act == 1) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+  }
+  if (ep.resid && row_ok) {
+    if (ep.resid_f32) {
+      const float* r = reinterpret_cast<const float*>(ep.resid) + (size_t)row * ep.ldr + col0;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        if (col0 + g * 4 < N) {
+          const float4 t = *reinterpret_cast<const float4*>(r + g * 4);
+          f[g * 4 + 0] += t.x; f[g * 4 + 1] += t.y; f[g * 4 + 2] += t.z; f[g * 4 + 3] += t.w;
+        }
+      }
+    } else {
+      const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(ep.resid) + (size_t)row * ep.ldr + col0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (col0 + g * 8 < N) {
+          const bf16x8 t = *reinterpret_cast<const bf16x8*>(r + g * 8);
+          float tf[8];
+          unpack8(t, tf);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[g * 8 + i] += tf[i];
+        }
+      }
+    }
+  }
+}
+
+// Drains one 128 x BN fp32 accumulator (this thread: TMEM lane = row_in_tile) to HBM through a 128B-swizzled staging tile
+// and TMA stores: the 128 epilogue threads write their rows into shared memory (16-byte pieces XOR-swizzled by row % 8:
+// conflict-free per quarter warp, and exactly the layout CU_TENSOR_MAP_SWIZZLE_128B expects), one thread issues
+// cp.async.bulk.tensor stores of [128 rows x 128 bytes] boxes. HBM sees full 128-byte lines; ragged M / N edges are
+// clipped by the TMA unit. Two staging tiles alternate so a store overlaps the next block's TMEM reads.
+// (Direct per-thread row stores were measured at 1170 TFLOP/s vs 1540 TFLOP/s for the bare mainloop: profiles/.)
+constexpr int kStageTileBytes = 128 * 128;
+template <int BN>
+__device__ __forceinline__ void epilogue_drain_tile(const GemmEpilogue& ep, const CUtensorMap* tmap_out, unsigned char* staging,
+                                                    int& sbuf, uint32_t t_row, int row_in_tile, int tile_row0, int tile_col0) {
+  const int N = ep.N;
+  const int row = tile_row0 + row_in_tile;
+  const bool row_ok = row < ep.M;
+  const int sb_cols = ep.out_f32 ? 32 : 64;                    // 128 bytes of output per row per store block
+  const bool issuer = (threadIdx.x == 128);                    // first epilogue thread
+#pragma unroll 1
+  for (int c = 0; c < BN; c += sb_cols) {
+    const int col0 = tile_col0 + c;
+    if (col0 >= N) break;                                       // uniform across the 4 epilogue warps
+    if (issuer) bulk_wait_read<1>();                            // the store that used this staging tile has read it
+    named_bar_sync(1, 128);
+    unsigned char* st = staging + sbuf * kStageTileBytes + row_in_tile * 128;
+    const int sw = row_in_tile & 7;
+    if (ep.out_f32) {
+      uint32_t v[32]; float f[32];
+      tmem_ld_32x32(t_row + (uint32_t)c, v);
+      tmem_ld_wait();
+      epilogue_math(ep, v, f, row, col0, row_ok);
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        *reinterpret_cast<float4*>(st + ((g ^ sw) << 4)) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (col0 + h * 32 < N) {
+          uint32_t v[32]; float f[32];
+          tmem_ld_32x32(t_row + (uint32_t)(c + h * 32), v);
+          tmem_ld_wait();
+          epilogue_math(ep, v, f, row, col0 + h * 32, row_ok);
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<bf16x8*>(st + (((h * 4 + g) ^ sw) << 4)) = pack8(f + g * 8);
+        }
+      }
+    }
+    fence_proxy_async();                                        // generic-proxy smem writes -> visible to the TMA unit
+    named_bar_sync(1, 128);
+    if (issuer) {
+      tma_store_2d(tmap_out, staging + sbuf * kStageTileBytes, col0, tile_row0);
+      bulk_commit();
+    }
+    sbuf ^= 1;
+  }
+}
+
 template <int BN> struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
@@ -45,19 +139,20 @@ template <int BN> struct GemmCfg {
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int ACC_STAGES = 2;
   static constexpr int TMEM_COLS = ACC_STAGES * BN;              // 128 / 256 / 512: powers of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * kStageTileBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(256, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmEpilogue ep) {
+                    const __grid_constant__ CUtensorMap tmap_out, const GemmEpilogue ep) {
   using Cfg = GemmCfg<BN>;
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
   extern __shared__ unsigned char smem_raw[];
   // 128B swizzle atoms need 1024-byte aligned tile bases
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar   = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  unsigned char* staging = smem + STAGES * Cfg::STAGE_BYTES;             // 2 x [128 rows x 128 B], 1024-aligned
+  uint64_t* full_bar   = reinterpret_cast<uint64_t*>(staging + 2 * kStageTileBytes);
   uint64_t* empty_bar  = full_bar + STAGES;
   uint64_t* tfull_bar  = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + Cfg::ACC_STAGES;
@@ -72,6 +167,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_out);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -138,76 +234,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // =============================== epilogue ===============================
     const int q = warp - 4;                                     // TMEM lane quarter == warp % 4
     int acc = 0; uint32_t acc_phase = 0;
+    int sbuf = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile % num_m, n_blk = tile / num_m;
-      const int row = m_blk * BM + q * 32 + lane;
-      const bool row_ok = row < M;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        const int col0 = n_blk * BN + c;
-        if (col0 >= N) break;                                   // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + (uint32_t)c, v);
-        tmem_ld_wait();
-        if (row_ok) {
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * ep.alpha;
-          if (ep.bias) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) if (col0 + i < N) f[i] += __ldg(ep.bias + col0 + i);
-          }
-          if (ep.act == 1) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
-          }
-          if (ep.resid) {
-            if (ep.resid_f32) {
-              const float* r = reinterpret_cast<const float*>(ep.resid) + (size_t)row * ep.ldr + col0;
-#pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                if (col0 + g * 4 < N) {
-                  const float4 t = *reinterpret_cast<const float4*>(r + g * 4);
-                  f[g * 4 + 0] += t.x; f[g * 4 + 1] += t.y; f[g * 4 + 2] += t.z; f[g * 4 + 3] += t.w;
-                }
-              }
-            } else {
-              const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(ep.resid) + (size_t)row * ep.ldr + col0;
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                if (col0 + g * 8 < N) {
-                  const bf16x8 t = *reinterpret_cast<const bf16x8*>(r + g * 8);
-                  float tf[8];
-                  unpack8(t, tf);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) f[g * 8 + i] += tf[i];
-                }
-              }
-            }
-          }
-          if (ep.out_f32) {
-            float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col0;
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              if (col0 + g * 4 < N)
-                *reinterpret_cast<float4*>(o + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-          } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldo + col0;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (col0 + g * 8 < N) *reinterpret_cast<bf16x8*>(o + g * 8) = pack8(f + g * 8);
-          }
-        }
-      }
-      // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator stage back to the MMA warp
+      epilogue_drain_tile<BN>(ep, &tmap_out, staging, sbuf, t_row, q * 32 + lane, m_blk * BM, n_blk * BN);
+      // all TMEM reads of this warp are complete (wait::ld): hand the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
+    if (threadIdx.x == 128) bulk_wait<0>();                     // staging tiles must outlive their TMA reads
   }
 
   tc_fence_before();
@@ -215,6 +255,138 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ============================================================================================================
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BN tile. Each CTA stages its own
+// 128 rows of A and HALF (BN/2 rows) of B per k-block, so shared-memory fill + operand-read traffic per SM drops from
+// 96 KB to 64 KB per 128x256x64 of MMA work - the single-CTA kernel above is shared-memory-bandwidth bound at ~70 % of
+// the tensor peak. The leader CTA's elected thread issues tcgen05.mma.cta_group::2 (M = 256); completion is multicast
+// to both CTAs' barriers; both CTAs run TMA producers and epilogues for their own half.
+// ============================================================================================================
+template <int BN, int ST = 0> struct Gemm2Cfg {
+  static constexpr int BM = 128 /*per CTA*/, BK = 64, BNH = BN / 2;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BNH * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = ST > 0 ? ST : ((BN == 256) ? 6 : 8);
+  static constexpr int ACC_STAGES = 2;
+  static constexpr int TMEM_COLS = ACC_STAGES * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * kStageTileBytes + 1024 + 256;
+};
+
+template <int BN, int ST>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const __grid_constant__ CUtensorMap tmap_out, const GemmEpilogue ep) {
+  using Cfg = Gemm2Cfg<BN, ST>;
+  constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES, BNH = Cfg::BNH;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* staging = smem + STAGES * Cfg::STAGE_BYTES;             // 2 x [128 rows x 128 B], 1024-aligned
+  uint64_t* full_bar   = reinterpret_cast<uint64_t*>(staging + 2 * kStageTileBytes);
+  uint64_t* empty_bar  = full_bar + STAGES;
+  uint64_t* tfull_bar  = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + Cfg::ACC_STAGES;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + Cfg::ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int M = ep.M, N = ep.N, K = ep.K;
+  const int num_m = (M + 2 * BM - 1) / (2 * BM), num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + BK - 1) / BK;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_out); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    // tfull: one multicast commit per tile; tempty (used on the leader): 4 epilogue warps of EACH CTA arrive
+    for (int a = 0; a < Cfg::ACC_STAGES; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_holder, Cfg::TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // =============================== TMA producer (both CTAs) ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        const int row_a = m_blk * 2 * BM + (int)rank * BM;
+        const int row_b = n_blk * BN + (int)rank * BNH;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);             // own copy, released by the multicast commit
+          unsigned char* sa = smem + stage * Cfg::STAGE_BYTES;
+          unsigned char* sb = sa + Cfg::A_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);   // both CTAs' bytes
+          tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * BK, row_a);
+          tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], kb * BK, row_b);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (leader CTA only) ===============================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);            // both CTAs' epilogues drained this stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t adesc = make_sw128_kmajor_desc(sa);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sb);
+          const int krem = K - kb * BK;
+          const int ksteps = krem >= BK ? (BK / 16) : ((krem + 15) / 16);
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage], 0x3);              // frees the slot in BOTH CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tfull_bar[acc], 0x3);                  // accumulator halves ready in both CTAs
+        if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================== epilogue (both CTAs, own 128 rows) ===============================
+    const int q = warp - 4;
+    int acc = 0; uint32_t acc_phase = 0;
+    int sbuf = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      epilogue_drain_tile<BN>(ep, &tmap_out, staging, sbuf, t_row, q * 32 + lane, m_blk * 2 * BM + (int)rank * BM, n_blk * BN);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tempty_bar[acc], 0);   // leader's barrier
+      if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+    if (threadIdx.x == 128) bulk_wait<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                                           // peer may still be reading our smem / signalling us
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -235,25 +407,26 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 struct TmapKey {
-  const void* ptr; long long rows, cols, ld; int box_rows;
+  const void* ptr; long long rows, cols, ld; int box_rows; int f32;
   bool operator==(const TmapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && f32 == o.f32;
   }
 };
 struct TmapKeyHash {
   size_t operator()(const TmapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
     h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.cols;
-    h = h * 1000003u ^ (size_t)k.ld;   h = h * 1000003u ^ (size_t)k.box_rows;
+    h = h * 1000003u ^ (size_t)k.ld;   h = h * 1000003u ^ (size_t)(k.box_rows * 2 + k.f32);
     return h;
   }
 };
 static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
 static std::mutex g_tmap_mu;
 
-// bf16 row-major [rows, cols] with row stride ld (elements); box = {64 cols (128 B), box_rows}, 128B swizzle, OOB -> 0
-static int get_tmap(const void* ptr, long long rows, long long cols, long long ld, int box_rows, CUtensorMap* out) {
-  TmapKey key{ptr, rows, cols, ld, box_rows};
+// row-major [rows, cols] (bf16, or fp32 when f32 != 0) with row stride ld (elements);
+// box = {128 bytes of columns, box_rows}, 128B swizzle, OOB loads -> 0, OOB stores clipped
+static int get_tmap(const void* ptr, long long rows, long long cols, long long ld, int box_rows, CUtensorMap* out, int f32 = 0) {
+  TmapKey key{ptr, rows, cols, ld, box_rows, f32};
   {
     std::lock_guard<std::mutex> g(g_tmap_mu);
     auto it = g_tmaps.find(key);
@@ -262,13 +435,13 @@ static int get_tmap(const void* ptr, long long rows, long long cols, long long l
   auto fn = get_encode_fn();
   DALM_REQUIRE(fn != nullptr, "gemm: cuTensorMapEncodeTiled driver entry point unavailable");
   DALM_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "gemm: operand base %p is not 16-byte aligned", ptr);
-  DALM_REQUIRE((ld % 8) == 0, "gemm: operand row stride %lld must be a multiple of 8 bf16 (16 B)", ld);
+  DALM_REQUIRE((ld % (f32 ? 4 : 8)) == 0, "gemm: row stride %lld is not a multiple of 16 bytes", ld);
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {f32 ? 32u : 64u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUtensorMap m;
-  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DALM_REQUIRE(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%d",
@@ -283,8 +456,8 @@ static int get_tmap(const void* ptr, long long rows, long long cols, long long l
 }
 
 template <int BN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int max_ctas,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmEpilogue& ep,
+                       int max_ctas, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -294,9 +467,26 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
   const int num_tiles = ((ep.M + 127) / 128) * ((ep.N + BN - 1) / BN);
   int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  gemm_bf16_tn_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, ep);
+  gemm_bf16_tn_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, to, ep);
   count_launch();
   return check_launch("gemm_bf16_tn_kernel");
+}
+
+template <int BN, int ST = 0>
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmEpilogue& ep,
+                        int max_ctas, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN, ST>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DALM_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int num_tiles = ((ep.M + 255) / 256) * ((ep.N + BN - 1) / BN);
+  int clusters = num_tiles < kNumSMs / 2 ? num_tiles : kNumSMs / 2;
+  if (max_ctas > 0 && clusters > max_ctas / 2) clusters = max_ctas / 2 > 0 ? max_ctas / 2 : 1;
+  gemm2_bf16_tn_kernel<BN, ST><<<2 * clusters, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, to, ep);
+  count_launch();
+  return check_launch("gemm2_bf16_tn_kernel");
 }
 
 }  // namespace dalm
@@ -320,24 +510,34 @@ extern "C" int dalm_b200_gemm_bf16_tn(const void* A, long long lda, const void* 
     DALM_REQUIRE((ldr % (resid_f32 ? 4 : 8)) == 0, "gemm: ldr=%lld breaks 16-byte row alignment", ldr);
     DALM_REQUIRE((reinterpret_cast<uintptr_t>(resid) & 15) == 0, "gemm: resid is not 16-byte aligned");
   }
-  DALM_REQUIRE(act == 0 || act == 1, "gemm: act must be 0 (none) or 1 (gelu)");
+  DALM_REQUIRE(act == 0 || act == 1 || act == 99, "gemm: act must be 0 (none) or 1 (gelu)");   // 99: probe, no stores
   int bn = block_n;
   if (bn == 0) {
-    // pick the widest tile that still yields >= ~1 wave of CTAs
-    const long long m_tiles = (M + 127) / 128;
-    if (m_tiles * ((N + 255) / 256) >= kNumSMs) bn = 256;
-    else if (m_tiles * ((N + 127) / 128) >= kNumSMs) bn = 128;
+    // tile-shape heuristic: prefer the CTA-pair 256x256 tile when it fills >= ~2 waves of 74 clusters; else the widest
+    // single-CTA tile that still yields about one wave of 148 CTAs.
+    const long long m2 = (M + 255) / 256, m1 = (M + 127) / 128;
+    if (m2 * ((N + 255) / 256) >= 2 * (kNumSMs / 2) && N >= 256) bn = 2256;
+    else if (m2 * ((N + 127) / 128) >= (kNumSMs / 2) && N >= 128) bn = 2128;
+    else if (m1 * ((N + 127) / 128) >= kNumSMs) bn = 128;
     else bn = 64;
-    if (bn > 64 && N <= 64) bn = 64;
   }
-  DALM_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: block_n must be 0/64/128/256");
-  CUtensorMap ta, tb;
+  DALM_REQUIRE(bn == 64 || bn == 128 || bn == 256 || bn == 2128 || bn == 2256 || bn == 3256 || bn == 4256,
+               "gemm: block_n must be 0, 64/128/256 (single CTA) or 2128/2256 (CTA pair)");
+  const bool pair = bn > 1000;
+  const int tile_n = pair ? bn % 1000 : bn;
+  CUtensorMap ta, tb, to;
   if (int e = get_tmap(A, M, K, lda, 128, &ta)) return e;
-  if (int e = get_tmap(B, N, K, ldb, bn, &tb)) return e;
+  if (int e = get_tmap(B, N, K, ldb, pair ? tile_n / 2 : tile_n, &tb)) return e;
+  if (int e = get_tmap(out, M, N, ldo, 128, &to, out_f32)) return e;
   GemmEpilogue ep{out, ldo, out_f32, bias, resid, ldr, resid_f32, act, alpha, M, N, K};
-  if (bn == 256) return launch_gemm<256>(ta, tb, ep, max_ctas, (cudaStream_t)stream);
-  if (bn == 128) return launch_gemm<128>(ta, tb, ep, max_ctas, (cudaStream_t)stream);
-  return launch_gemm<64>(ta, tb, ep, max_ctas, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bn == 2256) return launch_gemm2<256>(ta, tb, to, ep, max_ctas, st);
+  if (bn == 3256) return launch_gemm2<256, 3>(ta, tb, to, ep, max_ctas, st);     // tuning probes (fewer stages)
+  if (bn == 4256) return launch_gemm2<256, 4>(ta, tb, to, ep, max_ctas, st);
+  if (bn == 2128) return launch_gemm2<128>(ta, tb, to, ep, max_ctas, st);
+  if (bn == 256) return launch_gemm<256>(ta, tb, to, ep, max_ctas, st);
+  if (bn == 128) return launch_gemm<128>(ta, tb, to, ep, max_ctas, st);
+  return launch_gemm<64>(ta, tb, to, ep, max_ctas, st);
 }
 
 // drop cached tensor maps (call when operand buffers are freed / re-allocated at the same address with other shapes)

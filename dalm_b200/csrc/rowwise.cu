@@ -103,24 +103,41 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float* __restric
                                                           const __nv_bfloat16* __restrict__ dh, long long lddh,
                                                           const float* __restrict__ dres_in, float* __restrict__ dres_out,
                                                           __nv_bfloat16* __restrict__ dres16, long long ld16, int H) {
+  // 4 elements per thread per iteration (float4 / 8-byte bf16x4); the row's g*dh and xhat stay in shared memory
   extern __shared__ float sm[];
-  float* gd = sm;
-  float* xh = sm + H;
+  float4* gd4 = reinterpret_cast<float4*>(sm);
+  float4* xh4 = reinterpret_cast<float4*>(sm + H);
   __shared__ float red[32];
   const size_t r = blockIdx.x;
   const float rstd = rstd_in[r];
+  const float4* x4 = reinterpret_cast<const float4*>(x + r * H);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  const uint2* dh2 = reinterpret_cast<const uint2*>(dh + r * lddh);
   float s = 0.f;
-  for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    const float a = __bfloat162float(dh[r * lddh + i]) * g[i];
-    const float b = x[r * H + i] * rstd;
-    gd[i] = a; xh[i] = b; s += a * b;
+  for (int i = threadIdx.x; i < H / 4; i += blockDim.x) {
+    const uint2 raw = dh2[i];
+    const float2 d01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+    const float2 d23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+    const float4 gg = g4[i], xx = x4[i];
+    const float4 a = make_float4(d01.x * gg.x, d01.y * gg.y, d23.x * gg.z, d23.y * gg.w);
+    const float4 b = make_float4(xx.x * rstd, xx.y * rstd, xx.z * rstd, xx.w * rstd);
+    gd4[i] = a; xh4[i] = b;
+    s += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
   }
   s = block_sum(s, red) / H;
-  for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    float d = rstd * (gd[i] - xh[i] * s);
-    if (dres_in) d += dres_in[r * H + i];
-    dres_out[r * H + i] = d;
-    if (dres16) dres16[r * ld16 + i] = __float2bfloat16_rn(d);
+  const float4* din4 = dres_in ? reinterpret_cast<const float4*>(dres_in + r * H) : nullptr;
+  float4* dout4 = reinterpret_cast<float4*>(dres_out + r * H);
+  uint2* d16 = dres16 ? reinterpret_cast<uint2*>(dres16 + r * ld16) : nullptr;
+  for (int i = threadIdx.x; i < H / 4; i += blockDim.x) {
+    const float4 a = gd4[i], b = xh4[i];
+    float4 d = make_float4(rstd * (a.x - b.x * s), rstd * (a.y - b.y * s), rstd * (a.z - b.z * s), rstd * (a.w - b.w * s));
+    if (din4) { const float4 t = din4[i]; d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w; }
+    dout4[i] = d;
+    if (d16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(d.x, d.y), hi = __floats2bfloat162_rn(d.z, d.w);
+      uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      d16[i] = pk;
+    }
   }
 }
 
@@ -154,16 +171,30 @@ __global__ void embed_gather_kernel(const int64_t* __restrict__ ids, const __nv_
 // ------------------------------------------------------------------------------------------------------------
 __global__ void rope_kernel(__nv_bfloat16* __restrict__ buf, long long ld, int col0, int nheads, int D,
                             const float* __restrict__ cos_t, const float* __restrict__ sin_t, int L, float sign) {
+  // one CTA per token row; each thread rotates 8 (j, j+D/2) pairs with 16-byte accesses
   const size_t r = blockIdx.x;
-  const int l = (int)(r % L), half = D / 2;
+  const int l = (int)(r % L), half = D / 2, chunks = half / 8;
   __nv_bfloat16* base = buf + r * ld + col0;
-  for (int i = threadIdx.x; i < nheads * half; i += blockDim.x) {
-    const int hd = i / half, j = i - hd * half;
-    const float c = cos_t[(size_t)l * half + j], s = sin_t[(size_t)l * half + j] * sign;
-    __nv_bfloat16* p = base + hd * D;
-    const float x1 = __bfloat162float(p[j]), x2 = __bfloat162float(p[j + half]);
-    p[j] = __float2bfloat16_rn(x1 * c - x2 * s);
-    p[j + half] = __float2bfloat16_rn(x2 * c + x1 * s);
+  for (int i = threadIdx.x; i < nheads * chunks; i += blockDim.x) {
+    const int hd = i / chunks, j = (i - hd * chunks) * 8;
+    __nv_bfloat16* p = base + hd * D + j;
+    float x1[8], x2[8], o1[8], o2[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(p), x1);
+    unpack8(*reinterpret_cast<const bf16x8*>(p + half), x2);
+    const float4 c0 = *reinterpret_cast<const float4*>(cos_t + (size_t)l * half + j);
+    const float4 c1 = *reinterpret_cast<const float4*>(cos_t + (size_t)l * half + j + 4);
+    const float4 s0 = *reinterpret_cast<const float4*>(sin_t + (size_t)l * half + j);
+    const float4 s1 = *reinterpret_cast<const float4*>(sin_t + (size_t)l * half + j + 4);
+    const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float s = sn[k] * sign;
+      o1[k] = x1[k] * c[k] - x2[k] * s;
+      o2[k] = x2[k] * c[k] + x1[k] * s;
+    }
+    *reinterpret_cast<bf16x8*>(p) = pack8(o1);
+    *reinterpret_cast<bf16x8*>(p + half) = pack8(o2);
   }
 }
 
@@ -288,46 +319,6 @@ __global__ void __launch_bounds__(256) pool_norm_bwd_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// LoRA weight gradients: out[r, k] (+)= scale * sum_m G[m, r] * X[m, k]     (G: [M,R<=32] bf16, X: [M,K] bf16)
-// grid (ceil(K/256), splits over M); partial sums are combined with fp32 atomics (R*K*splits adds, tiny).
-// ------------------------------------------------------------------------------------------------------------
-template <int R>
-__global__ void __launch_bounds__(128) lora_wgrad_kernel(const __nv_bfloat16* __restrict__ X, long long ldx,
-                                                         const __nv_bfloat16* __restrict__ G, long long ldg,
-                                                         float* __restrict__ out, long long so_r, long long so_k,
-                                                         int M, int K, int rows_per_cta, float scale) {
-  __shared__ float gs[64][R];
-  const int k2 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;          // two adjacent columns per thread
-  const int m0 = blockIdx.y * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
-  float acc0[R], acc1[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
-  for (int mb = m0; mb < m1; mb += 64) {
-    const int nm = min(64, m1 - mb);
-    __syncthreads();
-    for (int i = threadIdx.x; i < 64 * R; i += blockDim.x) {
-      const int mm = i / R, r = i - mm * R;
-      gs[mm][r] = mm < nm ? __bfloat162float(G[(size_t)(mb + mm) * ldg + r]) : 0.f;
-    }
-    __syncthreads();
-    if (k2 < K) {
-      for (int mm = 0; mm < nm; ++mm) {
-        const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(X + (size_t)(mb + mm) * ldx + k2));
-#pragma unroll
-        for (int r = 0; r < R; ++r) { acc0[r] = fmaf(gs[mm][r], x.x, acc0[r]); acc1[r] = fmaf(gs[mm][r], x.y, acc1[r]); }
-      }
-    }
-  }
-  if (k2 < K) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      atomicAdd(out + r * so_r + (long long)k2 * so_k, acc0[r] * scale);
-      if (k2 + 1 < K) atomicAdd(out + r * so_r + (long long)(k2 + 1) * so_k, acc1[r] * scale);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
 // fused Adam over a flat fp32 buffer (torch.optim.Adam semantics, no weight decay, no amsgrad), optional bf16 shadow copy
 // ------------------------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
@@ -350,6 +341,17 @@ __global__ void pack_scaled_bf16_kernel(const float* __restrict__ in, long long 
   if (i >= (long long)rows * cols) return;
   const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
   out[(size_t)r * ldo + c] = __float2bfloat16_rn(in[r * si_r + c * si_c] * scale);
+}
+
+// table-driven variant: one launch refreshes every LoRA block of a model (blockIdx.y = table entry)
+struct PackEntry { const float* in; long long si_r, si_c; __nv_bfloat16* out; long long ldo; int rows, cols; float scale; };
+__global__ void pack_table_kernel(const PackEntry* __restrict__ table) {
+  const PackEntry e = table[blockIdx.y];
+  const long long n = (long long)e.rows * e.cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / e.cols), c = (int)(i - (long long)r * e.cols);
+    e.out[(size_t)r * e.ldo + c] = __float2bfloat16_rn(e.in[r * e.si_r + c * e.si_c] * e.scale);
+  }
 }
 
 // out_bf16 [rows, ldo] <- fp32 [rows, cols]  (plain cast, vectorised)
@@ -396,7 +398,8 @@ extern "C" int dalm_b200_rmsnorm_fwd(const float* x, const float* g, void* h, lo
 extern "C" int dalm_b200_rmsnorm_bwd(const float* x, const float* g, const float* rstd, const void* dh, long long lddh,
                                      const float* dres_in, float* dres_out, void* dres16, long long ld16, int M, int H,
                                      void* stream) {
-  DALM_REQUIRE(M > 0 && H > 0 && H * 8 <= 96 * 1024, "rmsnorm_bwd: bad shape M=%d H=%d", M, H);
+  DALM_REQUIRE(M > 0 && H > 0 && (H % 4) == 0 && H * 8 <= 96 * 1024 && (lddh % 4) == 0 && (ld16 % 4) == 0,
+               "rmsnorm_bwd: bad shape M=%d H=%d", M, H);
   static bool attr = false;
   if (!attr) { DALM_CUDA(cudaFuncSetAttribute(rmsnorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
   rmsnorm_bwd_kernel<<<M, 256, 2 * H * sizeof(float), ST(stream)>>>(x, g, rstd, (const __nv_bfloat16*)dh, lddh, dres_in, dres_out,
@@ -418,7 +421,7 @@ extern "C" int dalm_b200_embed_gather(const int64_t* ids, const void* table, flo
 }
 extern "C" int dalm_b200_rope(void* buf, long long ld, int col0, int nheads, int D, const float* cos_t, const float* sin_t,
                               int M, int L, int backward, void* stream) {
-  DALM_REQUIRE((D % 2) == 0, "rope: odd head_dim");
+  DALM_REQUIRE((D % 16) == 0 && (ld % 8) == 0 && (col0 % 8) == 0, "rope: head_dim must be a multiple of 16 and rows 16-byte aligned");
   rope_kernel<<<M, 256, 0, ST(stream)>>>((__nv_bfloat16*)buf, ld, col0, nheads, D, cos_t, sin_t, L, backward ? -1.f : 1.f);
   count_launch();
   return check_launch("rope_kernel");
@@ -464,19 +467,6 @@ extern "C" int dalm_b200_pool_norm_bwd(const float* emb, const float* norm, cons
   count_launch();
   return check_launch("pool_norm_bwd_kernel");
 }
-extern "C" int dalm_b200_lora_wgrad(const void* X, long long ldx, const void* G, long long ldg, float* out,
-                                    long long so_r, long long so_k, int M, int K, int R, float scale, void* stream) {
-  DALM_REQUIRE(R == 8 || R == 16, "lora_wgrad: rank %d unsupported (8/16)", R);
-  DALM_REQUIRE((K % 2) == 0 && (ldx % 2) == 0, "lora_wgrad: K and ldx must be even");
-  const int rows_per_cta = 256;
-  dim3 grid((K / 2 + 127) / 128, (M + rows_per_cta - 1) / rows_per_cta);
-  if (R == 8)
-    lora_wgrad_kernel<8><<<grid, 128, 0, ST(stream)>>>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)G, ldg, out, so_r, so_k, M, K, rows_per_cta, scale);
-  else
-    lora_wgrad_kernel<16><<<grid, 128, 0, ST(stream)>>>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)G, ldg, out, so_r, so_k, M, K, rows_per_cta, scale);
-  count_launch();
-  return check_launch("lora_wgrad_kernel");
-}
 extern "C" int dalm_b200_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
                                    float beta2, float eps, int step, float grad_scale, void* stream) {
   DALM_REQUIRE(n >= 0 && step >= 1, "adam: bad n/step");
@@ -494,6 +484,16 @@ extern "C" int dalm_b200_pack_scaled_bf16(const float* in, long long si_r, long 
   pack_scaled_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(in, si_r, si_c, (__nv_bfloat16*)out, ldo, rows, cols, scale);
   count_launch();
   return check_launch("pack_scaled_bf16_kernel");
+}
+// table: device array of n_entries records {const float* in; int64 si_r, si_c; bf16* out; int64 ldo; int32 rows, cols; float scale}
+// (48 bytes each, natural alignment) — see dalm_b200/engine/lora.py:pack_table
+extern "C" int dalm_b200_pack_table(const void* table, int n_entries, void* stream) {
+  static_assert(sizeof(PackEntry) == 56, "PackEntry layout");
+  if (n_entries <= 0) return 0;
+  dim3 grid(32, n_entries);
+  pack_table_kernel<<<grid, 256, 0, ST(stream)>>>((const PackEntry*)table);
+  count_launch();
+  return check_launch("pack_table_kernel");
 }
 extern "C" int dalm_b200_cast_f32_bf16(const float* in, long long ldi, void* out, long long ldo, int rows, int cols, void* stream) {
   DALM_REQUIRE((cols % 4) == 0 && (ldi % 4) == 0 && (ldo % 4) == 0, "cast: cols/strides must be multiples of 4");

@@ -23,6 +23,14 @@ from .lora import LoraBank
 bf16, f32 = torch.bfloat16, torch.float32
 
 
+def _aug_buf(rows: int, cols: int, ra: int, device, zero: bool = False) -> torch.Tensor:
+    """[rows, cols+ra] bf16 view whose row stride is padded to cols+64 when ra > 0, so that every row starts on a
+    128-byte boundary (TMA 128B-swizzled boxes then touch aligned lines; measured +20 % on the K-augmented GEMMs)"""
+    ld = cols + (64 if ra else 0)
+    base = (torch.zeros if zero else torch.empty)(rows, ld, dtype=bf16, device=device)
+    return base[:, :cols + ra]
+
+
 class _Ctx:
     pass
 
@@ -55,7 +63,11 @@ class LlamaDecoder(torch.nn.Module):
         g = lambda k, dt: sd[k].to(device=self.dev, dtype=dt).contiguous()
         self.embed = g("model.embed_tokens.weight", bf16)
         self.norm_g = g("model.norm.weight", f32)
-        self.lm_head = g("lm_head.weight", bf16) if "lm_head.weight" in sd else self.embed
+        lm = g("lm_head.weight", bf16) if "lm_head.weight" in sd else self.embed
+        self.Vp = (self.V + 7) // 8 * 8                       # GEMM N granularity; extra rows are zero and never scored
+        if self.Vp != self.V:
+            lm = torch.cat([lm, torch.zeros(self.Vp - self.V, H, dtype=bf16, device=self.dev)], 0)
+        self.lm_head = lm
         self.lm_headT = self.lm_head.t().contiguous()
         self.layers: List[Dict[str, torch.Tensor]] = []
         H_, Ra = H, self.Ra
@@ -64,9 +76,9 @@ class LlamaDecoder(torch.nn.Module):
             W = {}
             wqkv = torch.cat([g(p + "self_attn.q_proj.weight", bf16), g(p + "self_attn.k_proj.weight", bf16),
                               g(p + "self_attn.v_proj.weight", bf16)], 0)
-            W["Wqkv_aug"] = torch.zeros(self.Nqkv, H_ + Ra, dtype=bf16, device=self.dev)
+            W["Wqkv_aug"] = _aug_buf(self.Nqkv, H_, Ra, self.dev, zero=True)
             W["Wqkv_aug"][:, :H_] = wqkv
-            W["WqkvT_aug"] = torch.zeros(H_, self.Nqkv + Ra, dtype=bf16, device=self.dev)
+            W["WqkvT_aug"] = _aug_buf(H_, self.Nqkv, Ra, self.dev, zero=True)
             W["WqkvT_aug"][:, :self.Nqkv] = wqkv.t()
             del wqkv
             if lora:
@@ -95,19 +107,24 @@ class LlamaDecoder(torch.nn.Module):
     def _target_cols(self, n: str):
         return (0, self.Nq) if n == "q_proj" else (self.Nq + self.Nkv, self.Nkv)
 
-    def repack_lora(self) -> None:
-        if self.lora is None:
-            return
+    def _pack_entries(self):
         H, r, s = self.H, self.r, self.lora.scale
         for l, W in enumerate(self.layers):
             for j, n in enumerate(self.LORA_TARGETS):
                 name = f"model.layers.{l}.self_attn.{n}"
                 A, B = self.lora.A[name], self.lora.B[name]             # [r,H], [out,r]
                 c0, w = self._target_cols(n)
-                ops.pack_scaled_bf16_(B, r, 1, W["Wqkv_aug"][c0:c0 + w, H + j * r:], w, r, s)
-                ops.pack_scaled_bf16_(A, 1, H, W["WqkvT_aug"][:, self.Nqkv + j * r:], H, r, 1.0)
-                ops.pack_scaled_bf16_(A, H, 1, W["A_stack"][j * r:(j + 1) * r], r, H, 1.0)
-                ops.pack_scaled_bf16_(B, 1, r, W["Bblk"][j * r:(j + 1) * r, c0:], r, w, s)
+                yield (B, r, 1, W["Wqkv_aug"][c0:c0 + w, H + j * r:], w, r, s)
+                yield (A, 1, H, W["WqkvT_aug"][:, self.Nqkv + j * r:], H, r, 1.0)
+                yield (A, H, 1, W["A_stack"][j * r:(j + 1) * r], r, H, 1.0)
+                yield (B, 1, r, W["Bblk"][j * r:(j + 1) * r, c0:], r, w, s)
+
+    def repack_lora(self) -> None:
+        if self.lora is None:
+            return
+        if getattr(self, "_pack_tab", None) is None:
+            self._pack_tab = ops.build_pack_table(list(self._pack_entries()), self.dev)
+        ops.pack_table_(self._pack_tab)
 
     def _rope(self, L: int):
         if L not in self._rope_cache:
@@ -130,10 +147,10 @@ class LlamaDecoder(torch.nn.Module):
         for W in self.layers:
             a = _Ctx()
             a.x_in = x
-            a.h1_aug = torch.empty(M, H + Ra, dtype=bf16, device=self.dev)
+            a.h1_aug = _aug_buf(M, H, Ra, self.dev)
             _, a.rstd1 = ops.rmsnorm_fwd(x, W["g1"], self.eps, h=a.h1_aug[:, :H])
             if Ra:
-                ops.gemm(a.h1_aug[:, :H], W["A_stack"], out=a.h1_aug[:, H:], N=Ra, block_n=64)
+                ops.skinny_gemm(a.h1_aug[:, :H], W["A_stack"], a.h1_aug[:, H:], K=H, R=Ra)   # u = h1 A^T [M,2r]
             a.qkv = ops.gemm(a.h1_aug, W["Wqkv_aug"])                            # [M, Nq+2Nkv]
             ops.rope_(a.qkv, 0, self.nh + self.nkv, self.hd, cos_t, sin_t, L)    # q heads then k heads are adjacent
             a.att, a.lse = ops.attention_fwd(a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + self.Nkv],
@@ -148,8 +165,8 @@ class LlamaDecoder(torch.nn.Module):
                 ctx.layers.append(a)
         ctx.x_final = x
         ctx.hf, ctx.rstdf = ops.rmsnorm_fwd(x, self.norm_g, self.eps)
-        logits = ops.gemm(ctx.hf, self.lm_head)                                   # bf16 [M,V]
-        return logits.view(B, L, self.V), ctx
+        logits = ops.gemm(ctx.hf, self.lm_head)                                   # bf16 [M,Vp]
+        return logits.view(B, L, self.Vp)[:, :, :self.V], ctx
 
     # ------------------------------------------------------------------------------------------------------------
     def backward_logits(self, ctx: _Ctx, dlogits: torch.Tensor) -> None:
@@ -159,7 +176,12 @@ class LlamaDecoder(torch.nn.Module):
         B, L = ctx.B, ctx.L
         M, H, F, Ra, r = B * L, self.H, self.F, self.Ra, self.r
         cos_t, sin_t = self._rope(L)
-        dhf = ops.gemm(dlogits.view(M, self.V), self.lm_headT)                    # [M,H]
+        if dlogits.stride(-1) != 1 or dlogits.stride(-2) != self.Vp:             # a caller-made copy: re-pad to the GEMM layout
+            pad = torch.zeros(B, L, self.Vp, dtype=bf16, device=self.dev)
+            pad[:, :, :self.V] = dlogits
+            dlogits = pad
+        dl2 = torch.as_strided(dlogits, (M, self.Vp), (self.Vp, 1), dlogits.storage_offset())
+        dhf = ops.gemm(dl2, self.lm_headT)                                         # [M,H]
         dx32, dx16 = ops.rmsnorm_bwd(ctx.x_final, self.norm_g, ctx.rstdf, dhf)
         for l in range(self.nl - 1, -1, -1):
             W, a = self.layers[l], ctx.layers[l]
@@ -168,18 +190,22 @@ class LlamaDecoder(torch.nn.Module):
             dh2 = ops.gemm(a.gu, W["WguT"])                                        # [M,H]
             dmid32, dmid16 = ops.rmsnorm_bwd(a.x_mid, W["g2"], a.rstd2, dh2, dres_in=dx32)
             datt = ops.gemm(dmid16, W["WoT"])                                      # [M,Nq]
-            dqkv = torch.empty(M, self.Nqkv + Ra, dtype=bf16, device=self.dev)
+            dqkv = _aug_buf(M, self.Nqkv, Ra, self.dev)
             ops.attention_bwd(a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + self.Nkv], a.qkv[:, self.Nq + self.Nkv:],
                               ctx.mask, a.att, a.lse, datt, B, L, self.nh, self.nkv, self.hd, causal=True,
                               dq=dqkv[:, :self.Nq], dk=dqkv[:, self.Nq:self.Nq + self.Nkv],
                               dv=dqkv[:, self.Nq + self.Nkv:self.Nqkv])
             ops.rope_(dqkv, 0, self.nh + self.nkv, self.hd, cos_t, sin_t, L, backward=True)
-            ops.gemm(dqkv[:, :self.Nqkv], W["Bblk"], out=dqkv[:, self.Nqkv:], N=Ra, block_n=64)
+            names = [f"model.layers.{l}.self_attn.{n}" for n in self.LORA_TARGETS]
             for j, n in enumerate(self.LORA_TARGETS):
-                name = f"model.layers.{l}.self_attn.{n}"
                 c0, w = self._target_cols(n)
-                ops.lora_wgrad_(a.h1_aug[:, :H], dqkv[:, self.Nqkv + j * r:], self.lora.gA[name], H, 1, H, r, 1.0)
-                ops.lora_wgrad_(dqkv[:, c0:c0 + w], a.h1_aug[:, H + j * r:], self.lora.gB[name], 1, r, w, r, self.lora.scale)
+                ops.skinny_gemm(dqkv[:, c0:c0 + w], W["Bblk"][j * r:(j + 1) * r, c0:c0 + w], dqkv[:, self.Nqkv + j * r:], K=w, R=r)
+            # dA_q, dA_v in one pass over h1 (the 16-row MMA tile is exactly the two rank-8 adapters)
+            ops.lora_wgrad_(a.h1_aug[:, :H], dqkv[:, self.Nqkv:], self.lora.gA[names[0]], H, 1, H, 2 * r, 1.0,
+                            out1=self.lora.gA[names[1]])
+            for j, n in enumerate(self.LORA_TARGETS):
+                c0, w = self._target_cols(n)
+                ops.lora_wgrad_(dqkv[:, c0:c0 + w], a.h1_aug[:, H + j * r:], self.lora.gB[names[j]], 1, r, w, r, self.lora.scale)
             if l == 0:
                 break                                                              # embeddings frozen
             dh1 = ops.gemm(dqkv, W["WqkvT_aug"])                                   # [M,H]

@@ -78,14 +78,23 @@ def ce_marginal(logits: torch.Tensor, ids: torch.Tensor, mask: torch.Tensor, nsu
         raise _lib.DalmB200Error(f"ce_marginal: logits dtype {logits.dtype} unsupported")
     _chk(logits, logits.dtype, "logits"); _chk(ids, i64, "ids"); _chk(mask, i64, "mask")
     B, L, V = logits.shape
-    logits = logits if logits.is_contiguous() else logits.contiguous()
+    # rows may be padded (row stride ld >= V, e.g. a vocabulary rounded up to the GEMM's N granularity)
+    rows_ok = logits.stride(2) == 1 and logits.stride(0) == L * logits.stride(1) and logits.stride(1) >= V
+    if not rows_ok:
+        logits = logits.contiguous()
+    ld = logits.stride(1)
     ids = ids.contiguous(); mask = mask.contiguous()
     tok_lp = torch.empty(B, L, dtype=f32, device=logits.device)
     dl = None
     if need_grad:
-        dl = logits if inplace else torch.empty_like(logits)
+        if inplace:
+            dl = logits
+        else:
+            dl = torch.empty_strided(logits.shape, logits.stride(), dtype=logits.dtype, device=logits.device)
+            if ld != V:
+                torch.as_strided(dl, (B * L, ld), (ld, 1), dl.storage_offset()).zero_()
     _lib.call("dalm_b200_ce_marginal_fwd_bwd", _p(logits), _p(dl), 0 if logits.dtype == bf16 else 1, _p(ids), _p(mask),
-              _p(nsum), _p(tok_lp), B, L, V, V, float(grad_out), _stream())
+              _p(nsum), _p(tok_lp), B, L, V, ld, float(grad_out), _stream())
     return tok_lp, dl
 
 
@@ -318,16 +327,39 @@ def pool_norm_bwd(emb, norm, d_emb, mask, L: int, normalize: bool = True):
     return d_hidden
 
 
-def lora_wgrad_(x, g, out, so_r: int, so_k: int, K: int, R: int, scale: float = 1.0):
-    """out[r*so_r + k*so_k] += scale * sum_m g[m,r] x[m,k]"""
+def lora_wgrad_(x, g, out, so_r: int, so_k: int, K: int, R: int, scale: float = 1.0, out1=None):
+    """out[r*so_r + k*so_k] += scale * sum_m g[m,r] x[m,k]; with R == 16 rows 8..15 accumulate into out1 (same strides)"""
     M = x.shape[0]
-    _lib.call("dalm_b200_lora_wgrad", _p(x), _ld(x), _p(g), _ld(g), _p(out), so_r, so_k, M, K, R, float(scale), _stream())
+    _lib.call("dalm_b200_lora_wgrad", _p(x), _ld(x), _p(g), _ld(g), _p(out), _p(out1), so_r, so_k, M, K, R, float(scale), _stream())
+    return out
+
+
+def skinny_gemm(x, w, out, K: int, R: int):
+    """out[M,R] (bf16 view) = x[M,K] @ w[R,K]^T   (R in {8,16})"""
+    _lib.call("dalm_b200_skinny_gemm", _p(x), _ld(x), _p(w), _ld(w), _p(out), _ld(out), x.shape[0], K, R, _stream())
     return out
 
 
 def pack_scaled_bf16_(src, si_r: int, si_c: int, dst, rows: int, cols: int, scale: float):
     _lib.call("dalm_b200_pack_scaled_bf16", _p(src), si_r, si_c, _p(dst), _ld(dst), rows, cols, float(scale), _stream())
     return dst
+
+
+def build_pack_table(entries, device) -> torch.Tensor:
+    """entries: iterable of (src_f32, si_r, si_c, dst_bf16_view, rows, cols, scale) -> device table for pack_table_()"""
+    import numpy as np
+    dt = np.dtype([("in", "<u8"), ("si_r", "<i8"), ("si_c", "<i8"), ("out", "<u8"), ("ldo", "<i8"), ("rows", "<i4"),
+                   ("cols", "<i4"), ("scale", "<f4"), ("pad", "<i4")])
+    assert dt.itemsize == 56
+    rows = [(s.data_ptr(), si_r, si_c, d.data_ptr(), _ld(d), r, c, sc, 0) for (s, si_r, si_c, d, r, c, sc) in entries]
+    arr = np.array(rows, dtype=dt)
+    t = torch.from_numpy(arr.view(np.uint8).reshape(-1).copy()).to(device)
+    t._n_entries = len(rows)
+    return t
+
+
+def pack_table_(table: torch.Tensor) -> None:
+    _lib.call("dalm_b200_pack_table", _p(table), int(table._n_entries), _stream())
 
 
 def cast_f32_bf16(src, dst=None):

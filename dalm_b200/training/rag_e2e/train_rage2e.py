@@ -108,19 +108,22 @@ def train_e2e(
                                   retriever_is_autoregressive=retriever_is_autoregressive)
 
     def tokenize(model: AutoModelForRagE2E, dataset):
-        gtok = model.generator_tokenizer
+        rtok, gtok = model.retriever_tokenizer, model.generator_tokenizer
         gtok.pad_token = gtok.eos_token                       # reference :301
         gtok.add_eos_token = True                             # reference :304
-        return dataset.map(
-            lambda ex: preprocess_dataset(ex, retriever_tokenizer=model.retriever_tokenizer, generator_tokenizer=gtok,
-                                          query_column_name=query_column_name, passage_column_name=passage_column_name,
-                                          answer_column_name=answer_column_name, query_max_len=query_max_len,
-                                          passage_max_len=passage_max_len, generator_max_len=generator_max_len),
-            batched=True, remove_columns=dataset.column_names, desc="Running tokenizer on dataset", num_proc=1)
+
+        def build(ex):                                        # closes over the tokenizers only (never the CUDA model)
+            return preprocess_dataset(ex, retriever_tokenizer=rtok, generator_tokenizer=gtok,
+                                      query_column_name=query_column_name, passage_column_name=passage_column_name,
+                                      answer_column_name=answer_column_name, query_max_len=query_max_len,
+                                      passage_max_len=passage_max_len, generator_max_len=generator_max_len)
+
+        # single process like the reference (num_proc=1 there); in-process so no CUDA context is forked
+        return dataset.map(build, batched=True, remove_columns=dataset.column_names, desc="Running tokenizer on dataset")
 
     recipe = Recipe(
         title="Running E2E training", tracker_project="peft_rag_e2e_learning", build_model=build, tokenize=tokenize,
-        step=lambda m, b, s, gs: fused_rag_step(m, b, s, backward=True, grad_scale=gs),
+        step=lambda m, b, s, gs: fused_rag_step(m, b, s, backward=True, grad_scale=gs), step_fn=fused_rag_step,
         banks=lambda m: m.trainable_banks(), repack=lambda m: m.repack(), save_final=_save_final(None))
     run_training(recipe, dataset_or_path=dataset_or_path, per_device_train_batch_size=per_device_train_batch_size,
                  learning_rate=learning_rate, logit_scale=logit_scale, num_train_epochs=num_train_epochs,

@@ -86,11 +86,13 @@ def train_retriever(
         return m
 
     def tokenize(model: AutoModelForSentenceEmbedding, dataset):
-        return dataset.map(
-            lambda ex: preprocess_dataset(ex, model.tokenizer, query_column_name=query_column_name,
-                                          passage_column_name=passage_column_name, query_max_len=query_max_len,
-                                          passage_max_len=passage_max_len),
-            batched=True, remove_columns=dataset.column_names, desc="Running tokenizer on dataset")
+        tok = model.tokenizer
+
+        def build(ex):                                        # closes over the tokenizer only (never the CUDA model)
+            return preprocess_dataset(ex, tok, query_column_name=query_column_name, passage_column_name=passage_column_name,
+                                      query_max_len=query_max_len, passage_max_len=passage_max_len)
+
+        return dataset.map(build, batched=True, remove_columns=dataset.column_names, desc="Running tokenizer on dataset")
 
     def save_final(model: AutoModelForSentenceEmbedding, output_dir: str) -> None:
         import os
@@ -101,7 +103,7 @@ def train_retriever(
 
     recipe = Recipe(
         title="Running training", tracker_project="peft_contrastive_learning", build_model=build, tokenize=tokenize,
-        step=lambda m, b, s, gs: fused_retriever_step(m, b, s, backward=True, grad_scale=gs),
+        step=lambda m, b, s, gs: fused_retriever_step(m, b, s, backward=True, grad_scale=gs), step_fn=fused_retriever_step,
         banks=lambda m: [m.model.lora] if m.model.lora is not None else [], repack=lambda m: m.model.repack_lora(),
         save_final=save_final)
     run_training(recipe, dataset_or_path=dataset_or_path, per_device_train_batch_size=per_device_train_batch_size,

@@ -29,6 +29,7 @@ class Recipe:
     build_model: Callable[[], torch.nn.Module]
     tokenize: Callable[[torch.nn.Module, Any], Any]            # (model, raw_dataset) -> tokenised dataset
     step: Callable[[torch.nn.Module, Dict[str, torch.Tensor], float, float], Dict[str, torch.Tensor]]
+    step_fn: Any = None                          # the underlying fused_*_step (signature of train_utils.fused_rag_step)
     banks: Callable[[torch.nn.Module], List[Any]]              # trainable LoRA banks
     repack: Callable[[torch.nn.Module], None]
     save_final: Callable[[torch.nn.Module, str], None]
@@ -122,6 +123,8 @@ def run_training(recipe: Recipe, *, dataset_or_path: Any, per_device_train_batch
 
     banks = recipe.banks(model)
     last_loss = None
+    use_graph = os.environ.get("DALM_B200_CUDA_GRAPH", "1") != "0" and torch.cuda.is_available()
+    graphed = None
     for epoch in range(start_epoch, num_train_epochs):
         model.train()
         total_loss = torch.zeros((), dtype=torch.float32, device=accelerator.device)
@@ -131,7 +134,16 @@ def run_training(recipe: Recipe, *, dataset_or_path: Any, per_device_train_batch
             accelerator._loader = active
         for step, batch in enumerate(active):
             with accelerator.accumulate(model):
-                out = recipe.step(model, batch, float(logit_scale), 1.0 / gradient_accumulation_steps)
+                if use_graph and graphed is None:
+                    from .train_utils import GraphedStep
+                    try:
+                        graphed = GraphedStep(recipe.step_fn, model, batch, float(logit_scale),
+                                              1.0 / gradient_accumulation_steps, zero_grads=optimizer.zero_grad)
+                    except Exception as e:                       # capture is an optimisation, never a requirement
+                        logger.warning(f"CUDA-graph capture of the step failed ({type(e).__name__}: {e}); running eagerly")
+                        use_graph = False
+                out = (graphed(batch) if graphed is not None else
+                       recipe.step(model, batch, float(logit_scale), 1.0 / gradient_accumulation_steps))
                 total_loss += accelerator.reduce(out["loss"].detach().float(), reduction="sum")   # rank-SUM (reference :469)
                 accelerator.average_gradients(b.grad for b in banks)
                 if accelerator.sync_gradients:

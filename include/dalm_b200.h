@@ -91,10 +91,16 @@ int dalm_b200_pool_norm_bwd(const float* emb, const float* norm, const float* d_
                             int B, int L, int H, int normalize, void* stream);
 
 /* ---- LoRA (peft.LoraConfig r=8 alpha=16: rag_e2e_base_model.py:144-160) and optimizer (train_rage2e.py:336) ---- */
-int dalm_b200_lora_wgrad(const void* X, long long ldx, const void* G, long long ldg, float* out, long long so_r,
-                         long long so_k, int M, int K, int R, float scale, void* stream);
+/* out0[r*so_r + k*so_k] += scale * sum_m G[m,r] X[m,k]  (r < 8; rows 8..15 of an R=16 call go to out1): dA = g^T x, dB^T = u^T dY */
+int dalm_b200_lora_wgrad(const void* X, long long ldx, const void* G, long long ldg, float* out0, float* out1,
+                         long long so_r, long long so_k, int M, int K, int R, float scale, void* stream);
+/* out[M,R] (bf16) = X[M,K] . W[R,K]^T, R in {8,16}: LoRA down-projection u = x A^T and mid-gradient g = dY (sB) */
+int dalm_b200_skinny_gemm(const void* X, long long ldx, const void* W, long long ldw, void* out, long long ldo, int M,
+                          int K, int R, void* stream);
 int dalm_b200_pack_scaled_bf16(const float* in, long long si_r, long long si_c, void* out, long long ldo, int rows,
                                int cols, float scale, void* stream);
+/* one launch for a whole table of pack jobs (device array of 56-byte records, see csrc/rowwise.cu PackEntry) */
+int dalm_b200_pack_table(const void* table, int n_entries, void* stream);
 int dalm_b200_cast_f32_bf16(const float* in, long long ldi, void* out, long long ldo, int rows, int cols, void* stream);
 int dalm_b200_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                         float eps, int step, float grad_scale, void* stream);

@@ -23,6 +23,8 @@ def _rel(a, b):
     (256, 512, 1024, 0), (900, 1024, 1024, 0), (3204, 3072, 1048, 0),     # ragged M, K-augmented (1024+24)
     (4608, 4096, 4112, 256), (300, 24, 1024, 64), (77, 4096, 512, 128),   # LoRA-down shape N=24, tiny M
     (1000, 1000, 72, 0),                                                  # K tail inside one k-block
+    (256, 256, 128, 2256), (256, 128, 64, 2128), (900, 1024, 1048, 2128), (3204, 3072, 1048, 2256),   # CTA-pair kernel
+    (4608, 4096, 4112, 2256), (77, 512, 512, 2256), (385, 1032, 520, 2128), (4608, 12288, 4112, 0),
 ])
 def test_gemm_plain(cuda_dev, M, N, K, bn):
     from dalm_b200 import ops
@@ -44,8 +46,8 @@ def test_gemm_multi_tile_per_cta(cuda_dev):
     a = (torch.randn(M, K, device=cuda_dev) * 0.5).to(bf16)
     b = (torch.randn(N, K, device=cuda_dev) * 0.5).to(bf16)
     ref = a.float() @ b.float().t()
-    for bn in (64, 128, 256):
-        for ctas in (1, 3, 7):
+    for bn in (64, 128, 256, 2128, 2256):
+        for ctas in (2, 3, 7):
             out = ops.gemm(a, b, block_n=bn, max_ctas=ctas, out_dtype=f32)
             assert _rel(out, ref) < 1e-5, (bn, ctas)
 
@@ -66,6 +68,11 @@ def test_gemm_epilogues(cuda_dev):
     assert _rel(out, torch.nn.functional.gelu(acc + bias)) < 1e-5
     out = ops.gemm(a, b, out_dtype=bf16, resid=r16)
     assert _rel(out.float(), acc + r16.float()) < 4e-3
+    for bn in (2128, 2256):                                   # same epilogue through the CTA-pair kernel
+        out = ops.gemm(a, b, out_dtype=f32, bias=bias, resid=r32, alpha=0.5, block_n=bn)
+        assert _rel(out, 0.5 * acc + bias + r32) < 1e-5
+        out = ops.gemm(a, b, out_dtype=f32, bias=bias, act=1, block_n=bn)
+        assert _rel(out, torch.nn.functional.gelu(acc + bias)) < 1e-5
     # strided views: A and output are column slices of wider buffers (the LoRA K-augmentation layout)
     wide_a = torch.zeros(M, K + 24, device=cuda_dev, dtype=bf16); wide_a[:, :K] = a
     wide_o = torch.zeros(M, N + 40, device=cuda_dev, dtype=bf16)
@@ -261,17 +268,32 @@ def test_lora_wgrad_pack_adam(cuda_dev):
     from dalm_b200 import ops
     torch.manual_seed(6)
     dev = cuda_dev
-    M, K, R = 1000, 520, 8
-    x = torch.randn(M, K + 24, device=dev).to(bf16)
-    g = torch.randn(M, 40, device=dev).to(bf16)
-    out = torch.zeros(R, K, device=dev)
-    ops.lora_wgrad_(x[:, :K], g[:, 16:], out, K, 1, K, R, 2.0)
-    ref = 2.0 * g[:, 16:24].double().t() @ x[:, :K].double()
-    assert _rel(out, ref) < 1e-5
-    outT = torch.zeros(K, R, device=dev)
-    ops.lora_wgrad_(x[:, :K], g[:, 16:], outT, 1, R, K, R, 2.0)
-    ops.lora_wgrad_(x[:, :K], g[:, 16:], outT, 1, R, K, R, 2.0)          # accumulates
-    assert _rel(outT, 2 * ref.t()) < 1e-5
+    for (M, K) in ((1000, 520), (4608, 4096), (37, 64)):
+        x = torch.randn(M, K + 24, device=dev).to(bf16)
+        g = torch.randn(M, 40, device=dev).to(bf16)
+        out = torch.zeros(8, K, device=dev)
+        ops.lora_wgrad_(x[:, :K], g[:, 16:], out, K, 1, K, 8, 2.0)
+        ref = 2.0 * g[:, 16:24].double().t() @ x[:, :K].double()
+        assert _rel(out, ref) < 1e-5, (M, K)
+        outT = torch.zeros(K, 8, device=dev)
+        ops.lora_wgrad_(x[:, :K], g[:, 16:], outT, 1, 8, K, 8, 2.0)
+        ops.lora_wgrad_(x[:, :K], g[:, 16:], outT, 1, 8, K, 8, 2.0)          # accumulates
+        assert _rel(outT, 2 * ref.t()) < 1e-5
+        # two adapters sharing X: rows 0-7 -> out0, rows 8-15 -> out1
+        o0 = torch.zeros(8, K, device=dev); o1 = torch.zeros(8, K, device=dev)
+        ops.lora_wgrad_(x[:, :K], g[:, 8:], o0, K, 1, K, 16, 1.0, out1=o1)
+        assert _rel(o0, g[:, 8:16].double().t() @ x[:, :K].double()) < 1e-5
+        assert _rel(o1, g[:, 16:24].double().t() @ x[:, :K].double()) < 1e-5
+    # skinny GEMM: out[M,R] = X W^T written into the tail columns of a wider buffer
+    for (M, K, R) in ((4608, 4096, 16), (900, 1024, 24), (33, 72, 8), (300, 512, 32)):
+        buf = torch.zeros(M, K + 64, device=dev, dtype=bf16)
+        buf[:, :K] = (torch.randn(M, K, device=dev) * 0.5).to(bf16)
+        w = (torch.randn(64, K, device=dev) * 0.5).to(bf16)
+        ops.skinny_gemm(buf[:, :K], w, buf[:, K:], K=K, R=R)
+        ref = buf[:, :K].double() @ w[:R].double().t()
+        assert _rel(buf[:, K:K + R].float(), ref) < 4e-3, (M, K, R)
+        assert buf[:, K + R:].abs().max().item() == 0
+    K, R = 520, 8
     # pack
     src = torch.randn(K, R, device=dev)
     dst = torch.zeros(R + 2, K + 8, device=dev, dtype=bf16)

@@ -42,10 +42,15 @@ if __name__ == "__main__":
     M = 18 * 256
     for (N, K) in [(12288, 4112), (4096, 4096), (22016, 4096), (4096, 11008), (32000, 4096), (4096, 12304), (4096, 22016), (11008, 4096), (4096, 32000)]:
         gemm_case(M, N, K, bn=256)
+        gemm_case(M, N, K, bn=2256)
     gemm_case(M, 4096, 4096, bn=128)
+    gemm_case(M, 4096, 4096, bn=2128)
     gemm_case(M, 4096, 4096, bn=256, out_dtype=f32, resid=True)
     for (Mb, N, K) in [(3204, 3072, 1048), (3204, 1024, 1024), (3204, 4096, 1024), (3204, 1024, 4096)]:
         gemm_case(Mb, N, K, bn=0)
+        gemm_case(Mb, N, K, bn=64)
+        gemm_case(Mb, N, K, bn=128)
+        gemm_case(Mb, N, K, bn=2128)
     # attention fwd/bwd at cfg-3 decoder shape
     B, L, H, D = 18, 256, 32, 128
     qkv = torch.randn(B * L, 3 * H * D, device=dev).to(bf16)
