@@ -106,7 +106,7 @@ class ClockSampler(threading.Thread):
 # ----------------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle (reference loss code + HF modeling on CPU fp32) on a bounded sample of the same workload
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_samples_per_s(batch, steps: int = 1, rows: int = 3):
+def cpu_reference_samples_per_s(batch, steps: int = 1, rows: int = 6):
     """Times the oracle's train step (reference loss code + HF modeling code, fp32, all host threads) on a BOUNDED sample
     of the workload: the first `rows` samples of a bs-18 batch at the real widths and sequence lengths, with truncated
     depth at three (encoder, decoder) settings; the per-layer and fixed costs identified from the three timings are
@@ -146,7 +146,7 @@ def cpu_reference_samples_per_s(batch, steps: int = 1, rows: int = 3):
     times = {}
     for i, (ne, nd) in enumerate(((1, 1), (1, 2), (3, 2))):
         bert, llama = build(ne, nd)
-        times[(ne, nd)] = time_step(bert, llama, warm=(i == 0))
+        times[(ne, nd)] = time_step(bert, llama, warm=False)
         del bert, llama
     d = max(times[(1, 2)] - times[(1, 1)], 1e-9)
     e = max((times[(3, 2)] - times[(1, 2)]) / 2.0, 0.0)

@@ -29,11 +29,11 @@ class Recipe:
     build_model: Callable[[], torch.nn.Module]
     tokenize: Callable[[torch.nn.Module, Any], Any]            # (model, raw_dataset) -> tokenised dataset
     step: Callable[[torch.nn.Module, Dict[str, torch.Tensor], float, float], Dict[str, torch.Tensor]]
-    step_fn: Any = None                          # the underlying fused_*_step (signature of train_utils.fused_rag_step)
     banks: Callable[[torch.nn.Module], List[Any]]              # trainable LoRA banks
     repack: Callable[[torch.nn.Module], None]
     save_final: Callable[[torch.nn.Module, str], None]
     map_num_proc: Optional[int] = None
+    step_fn: Any = None                          # the underlying fused_*_step (signature of train_utils.fused_rag_step)
 
 
 def collate(features: List[Dict[str, Any]]) -> Dict[str, torch.Tensor]:
