@@ -12,7 +12,10 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libdalm_b200.so")
 
-_I, _L, _F, _P = c_int, c_longlong, c_float, c_void_p
+from ctypes import c_ulonglong
+
+_I, _L, _F, _P, _U = c_int, c_longlong, c_float, c_void_p, c_ulonglong
+_DROP = [_F, _U, _U, _P]          # drop_p, drop_seed, drop_stream_id, drop_offset
 
 # name -> argtypes (restype is int unless listed in _RESTYPES). Mirrors include/dalm_b200.h one to one.
 SIGNATURES = {
@@ -25,14 +28,17 @@ SIGNATURES = {
     "dalm_b200_inbatch_loss_fwd_bwd": [_P, _P, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _F, _P],
     "dalm_b200_ce_marginal_fwd_bwd": [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _L, _F, _P],
     "dalm_b200_finalize_loss": [_P, _P, _I, _I, _P, _P, _P, _P],
+    "dalm_b200_bump_counter": [_P, _P],
+    "dalm_b200_dropout_scale": [_P, _L, _F, _U, _U, _P, _P],
+    "dalm_b200_lora_dx": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _F, _U, _U, _P, _P],
     "dalm_b200_small_matmul_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
-    "dalm_b200_gemm_bf16_tn": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _F, _P, _I, _P, _L, _I, _I, _I, _P],
+    "dalm_b200_gemm_bf16_tn": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _F, _P, _I, _P, _L, _I, _I, _I, *_DROP, _P],
     "dalm_b200_gemm_clear_cache": [],
-    "dalm_b200_attention_fwd": [_P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _I, _I, _I, _I, _I, _F, _I, _P],
+    "dalm_b200_attention_fwd": [_P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _I, _I, _I, _I, _I, _F, _I, *_DROP, _P],
     "dalm_b200_attention_bwd": [_P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _P, _L, _P, _P, _L, _P, _L, _P, _L,
-                                _I, _I, _I, _I, _I, _F, _I, _P],
-    "dalm_b200_layernorm_fwd": [_P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _F, _P],
-    "dalm_b200_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _L, _P, _P, _L, _I, _I, _P],
+                                _I, _I, _I, _I, _I, _F, _I, *_DROP, _P],
+    "dalm_b200_layernorm_fwd": [_P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _F, *_DROP, _P],
+    "dalm_b200_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _L, _P, _P, _L, _I, _I, *_DROP, _P],
     "dalm_b200_rmsnorm_fwd": [_P, _P, _P, _L, _P, _I, _I, _F, _P],
     "dalm_b200_rmsnorm_bwd": [_P, _P, _P, _P, _L, _P, _P, _P, _L, _I, _I, _P],
     "dalm_b200_bert_embed": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
@@ -44,8 +50,8 @@ SIGNATURES = {
     "dalm_b200_gelu_bwd": [_P, _L, _P, _L, _I, _I, _P],
     "dalm_b200_pool_norm_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "dalm_b200_pool_norm_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
-    "dalm_b200_lora_wgrad": [_P, _L, _P, _L, _P, _P, _L, _L, _I, _I, _I, _F, _P],
-    "dalm_b200_skinny_gemm": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P],
+    "dalm_b200_lora_wgrad": [_P, _L, _P, _L, _P, _P, _L, _L, _I, _I, _I, _F, *_DROP, _P],
+    "dalm_b200_skinny_gemm": [_P, _L, _P, _L, _P, _L, _I, _I, _I, *_DROP, _P],
     "dalm_b200_pack_scaled_bf16": [_P, _L, _L, _P, _L, _I, _I, _F, _P],
     "dalm_b200_pack_table": [_P, _I, _P],
     "dalm_b200_cast_f32_bf16": [_P, _L, _P, _L, _I, _I, _P],

@@ -29,6 +29,8 @@ struct AttnParams {
   int B, L, Hq, Hkv;
   float scale;                      // 1/sqrt(D)
   int causal;
+  DropCfg drop;                     // attention-probability dropout (BERT attention_probs_dropout_prob); p = 0 => off.
+                                    // element index of P[b,h,i,j] = ((b*Hq + h)*L + i)*L + j
 };
 
 // ---------------------------------------------------------------- fragment helpers
@@ -87,7 +89,7 @@ __device__ __forceinline__ void load_b_frag_kn(uint32_t* b, const __nv_bfloat16*
 // ============================================================================================================
 // forward
 // ============================================================================================================
-template <int D>
+template <int D, bool DROP>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnParams p) {
   constexpr int BQ = 64, BKV = 64, LDS = D + 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -187,6 +189,20 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnParams p) {
       o_acc[i][0] *= corr[0]; o_acc[i][1] *= corr[0];
       o_acc[i][2] *= corr[1]; o_acc[i][3] *= corr[1];
     }
+    if (DROP) {
+      // dropout acts on the normalised probabilities; the row sum above used the un-dropped values
+      const unsigned long long dstream = drop_stream(p.drop);
+      const unsigned long long rbase = ((unsigned long long)b * p.Hq + h) * L;
+#pragma unroll
+      for (int nt = 0; nt < BKV / 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = kv0 + nt * 8 + t * 2 + (e & 1);
+          const int qr = (e < 2) ? row_a : row_b;
+          if (qr < L && key < L) s[nt][e] *= drop_scale1(p.drop, dstream, (rbase + qr) * L + key);
+        }
+      }
+    }
     // ---- O += P V ----
 #pragma unroll
     for (int kk = 0; kk < BKV / 16; ++kk) {
@@ -254,7 +270,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long
 // ============================================================================================================
 // backward: dK, dV.  Each warp owns 16 keys; queries streamed in 32-row tiles.
 // ============================================================================================================
-template <int D>
+template <int D, bool DROP>
 __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(AttnParams p) {
   constexpr int BKV = 64, BQ = 32, LDS = D + 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -335,14 +351,36 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(AttnParams p) {
           st[nt][e] = exp2f(val - sLse[qc]);                     // -inf - x -> 0 ; x - (+inf) -> 0
         }
       }
-      // ---- dV += P^T dO ----
+      // dropout scale of each (key, query) element this thread holds (1 when dropout is off)
+      float ms[DROP ? BQ / 8 : 1][4];
+      if (DROP) {
+        const unsigned long long dstream = drop_stream(p.drop);
+        const unsigned long long rbase = ((unsigned long long)b * p.Hq + hq) * L;
+#pragma unroll
+        for (int nt = 0; nt < BQ / 8; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int qi = q0 + nt * 8 + t * 2 + (e & 1);
+            const int key = (e < 2) ? key_a : key_b;
+            ms[nt][e] = (qi < L && key < L) ? drop_scale1(p.drop, dstream, (rbase + qi) * L + key) : 0.f;
+          }
+        }
+      }
+      // ---- dV += P_drop^T dO ----
       uint32_t pa[BQ / 16][4];
 #pragma unroll
       for (int kk = 0; kk < BQ / 16; ++kk) {
-        pa[kk][0] = pack_bf16(st[2 * kk][0], st[2 * kk][1]);
-        pa[kk][1] = pack_bf16(st[2 * kk][2], st[2 * kk][3]);
-        pa[kk][2] = pack_bf16(st[2 * kk + 1][0], st[2 * kk + 1][1]);
-        pa[kk][3] = pack_bf16(st[2 * kk + 1][2], st[2 * kk + 1][3]);
+        if (DROP) {
+          pa[kk][0] = pack_bf16(st[2 * kk][0] * ms[2 * kk][0], st[2 * kk][1] * ms[2 * kk][1]);
+          pa[kk][1] = pack_bf16(st[2 * kk][2] * ms[2 * kk][2], st[2 * kk][3] * ms[2 * kk][3]);
+          pa[kk][2] = pack_bf16(st[2 * kk + 1][0] * ms[2 * kk + 1][0], st[2 * kk + 1][1] * ms[2 * kk + 1][1]);
+          pa[kk][3] = pack_bf16(st[2 * kk + 1][2] * ms[2 * kk + 1][2], st[2 * kk + 1][3] * ms[2 * kk + 1][3]);
+        } else {
+          pa[kk][0] = pack_bf16(st[2 * kk][0], st[2 * kk][1]);
+          pa[kk][1] = pack_bf16(st[2 * kk][2], st[2 * kk][3]);
+          pa[kk][2] = pack_bf16(st[2 * kk + 1][0], st[2 * kk + 1][1]);
+          pa[kk][3] = pack_bf16(st[2 * kk + 1][2], st[2 * kk + 1][3]);
+        }
       }
 #pragma unroll
       for (int kk = 0; kk < BQ / 16; ++kk) {
@@ -381,7 +419,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(AttnParams p) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int qc = nt * 8 + t * 2 + (e & 1);
-            ds[half][e] = st[nt][e] * (dpt[nt][e] - sDelta[qc]) * p.scale;
+            const float dpv = DROP ? dpt[nt][e] * ms[nt][e] : dpt[nt][e];
+            ds[half][e] = st[nt][e] * (dpv - sDelta[qc]) * p.scale;
           }
         }
         da[kk][0] = pack_bf16(ds[0][0], ds[0][1]);
@@ -420,7 +459,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(AttnParams p) {
 // ============================================================================================================
 // backward: dQ.  Each warp owns 16 queries; keys streamed in 64-row tiles.
 // ============================================================================================================
-template <int D>
+template <int D, bool DROP>
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(AttnParams p) {
   constexpr int BQ = 64, BKV = 64, LDS = D + 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -500,7 +539,13 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(AttnParams p) {
         float val = s[nt][e] * sl2 + sMask[kc];
         if (p.causal && (kv0 + kc) > qr) val = -INFINITY;
         const float pv = exp2f(val - lse2[e >> 1]);
-        s[nt][e] = pv * (dp[nt][e] - dl[e >> 1]) * p.scale;
+        float dpv = dp[nt][e];
+        if (DROP) {
+          const unsigned long long rbase = ((unsigned long long)b * p.Hq + h) * L;
+          const int key = kv0 + kc;
+          dpv *= (qr < L && key < L) ? drop_scale1(p.drop, drop_stream(p.drop), (rbase + qr) * L + key) : 0.f;
+        }
+        s[nt][e] = pv * (dpv - dl[e >> 1]) * p.scale;
       }
     }
     // dQ += dS K
@@ -536,29 +581,29 @@ template <int D> static size_t fwd_smem() { return (size_t)(64 * 3) * (D + 8) * 
 template <int D> static size_t dkv_smem() { return (size_t)(64 * 2 + 32 * 2) * (D + 8) * 2 + (32 + 32 + 64) * 4; }
 template <int D> static size_t dq_smem()  { return (size_t)(64 * 4) * (D + 8) * 2 + 64 * 4; }
 
-template <int D> static int launch_fwd(const AttnParams& p, cudaStream_t st) {
+template <int D, bool DROP> static int launch_fwd(const AttnParams& p, cudaStream_t st) {
   static bool attr = false;
-  if (!attr) { DALM_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<D>())); attr = true; }
+  if (!attr) { DALM_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<D>())); attr = true; }
   dim3 grid((p.L + 63) / 64, p.Hq, p.B);
-  attn_fwd_kernel<D><<<grid, 128, fwd_smem<D>(), st>>>(p);
+  attn_fwd_kernel<D, DROP><<<grid, 128, fwd_smem<D>(), st>>>(p);
   count_launch();
   return check_launch("attn_fwd_kernel");
 }
-template <int D> static int launch_bwd(const AttnParams& p, cudaStream_t st) {
+template <int D, bool DROP> static int launch_bwd(const AttnParams& p, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    DALM_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dkv_smem<D>()));
-    DALM_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dq_smem<D>()));
+    DALM_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<D, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dkv_smem<D>()));
+    DALM_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<D, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dq_smem<D>()));
     attr = true;
   }
   const int total_warps = p.B * p.L * p.Hq;
   attn_delta_kernel<<<(total_warps * 32 + 255) / 256, 256, 0, st>>>(p.o, p.ldo, p.d_o, p.lddo, p.delta, p.B, p.L, p.Hq, D);
   if (int e = check_launch("attn_delta_kernel")) return e;
   dim3 gkv((p.L + 63) / 64, p.Hkv, p.B);
-  attn_bwd_dkv_kernel<D><<<gkv, 128, dkv_smem<D>(), st>>>(p);
+  attn_bwd_dkv_kernel<D, DROP><<<gkv, 128, dkv_smem<D>(), st>>>(p);
   if (int e = check_launch("attn_bwd_dkv_kernel")) return e;
   dim3 gq((p.L + 63) / 64, p.Hq, p.B);
-  attn_bwd_dq_kernel<D><<<gq, 128, dq_smem<D>(), st>>>(p);
+  attn_bwd_dq_kernel<D, DROP><<<gq, 128, dq_smem<D>(), st>>>(p);
   count_launch(3);
   return check_launch("attn_bwd_dq_kernel");
 }
@@ -577,15 +622,22 @@ using namespace dalm;
 // q/k/v: bf16 token-major views (row b*L+l, head h at column h*D); mask: int64 [B,L] or NULL; out: bf16; lse: fp32 [B,Hq,L]
 extern "C" int dalm_b200_attention_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v,
                                        long long ldv, const int64_t* mask, void* out, long long ldo, float* lse, int B,
-                                       int L, int Hq, int Hkv, int D, float scale, int causal, void* stream) {
+                                       int L, int Hq, int Hkv, int D, float scale, int causal, float drop_p,
+                                       unsigned long long drop_seed, unsigned long long drop_stream_id,
+                                       const void* drop_offset, void* stream) {
   AttnParams p{};
   p.q = (const __nv_bfloat16*)q; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v;
   p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.mask = mask; p.o = (__nv_bfloat16*)out; p.ldo = ldo; p.lse = lse;
   p.B = B; p.L = L; p.Hq = Hq; p.Hkv = Hkv; p.scale = scale; p.causal = causal;
+  p.drop = make_drop(drop_p, drop_seed, drop_stream_id, drop_offset);
   if (int e = check_common(p, D)) return e;
-  if (D == 32) return launch_fwd<32>(p, (cudaStream_t)stream);
-  if (D == 64) return launch_fwd<64>(p, (cudaStream_t)stream);
-  return launch_fwd<128>(p, (cudaStream_t)stream);
+  DALM_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "attention: dropout p must be in [0,1)");
+  DALM_REQUIRE(drop_p == 0.f || D <= 64, "attention: probability dropout is built for head_dim <= 64 (encoder); Llama has attention_dropout = 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (drop_p > 0.f) return D == 32 ? launch_fwd<32, true>(p, st) : launch_fwd<64, true>(p, st);
+  if (D == 32) return launch_fwd<32, false>(p, st);
+  if (D == 64) return launch_fwd<64, false>(p, st);
+  return launch_fwd<128, false>(p, st);
 }
 
 // delta: fp32 workspace [B,Hq,L]; dq/dk/dv: bf16 token-major outputs (dk/dv have Hkv heads)
@@ -593,7 +645,9 @@ extern "C" int dalm_b200_attention_bwd(const void* q, long long ldq, const void*
                                        long long ldv, const int64_t* mask, const void* out, long long ldo,
                                        const float* lse, const void* d_out, long long lddo, float* delta, void* dq,
                                        long long lddq, void* dk, long long lddk, void* dv, long long lddv, int B, int L,
-                                       int Hq, int Hkv, int D, float scale, int causal, void* stream) {
+                                       int Hq, int Hkv, int D, float scale, int causal, float drop_p,
+                                       unsigned long long drop_seed, unsigned long long drop_stream_id,
+                                       const void* drop_offset, void* stream) {
   AttnParams p{};
   p.q = (const __nv_bfloat16*)q; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v;
   p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.mask = mask; p.o = (__nv_bfloat16*)const_cast<void*>(out); p.ldo = ldo;
@@ -603,7 +657,11 @@ extern "C" int dalm_b200_attention_bwd(const void* q, long long ldq, const void*
   p.B = B; p.L = L; p.Hq = Hq; p.Hkv = Hkv; p.scale = scale; p.causal = causal;
   if (int e = check_common(p, D)) return e;
   DALM_REQUIRE(lddo % 8 == 0 && ((uintptr_t)d_out & 15) == 0, "attention_bwd: d_out alignment");
-  if (D == 32) return launch_bwd<32>(p, (cudaStream_t)stream);
-  if (D == 64) return launch_bwd<64>(p, (cudaStream_t)stream);
-  return launch_bwd<128>(p, (cudaStream_t)stream);
+  DALM_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || D <= 64), "attention_bwd: dropout needs p in [0,1) and head_dim <= 64");
+  p.drop = make_drop(drop_p, drop_seed, drop_stream_id, drop_offset);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (drop_p > 0.f) return D == 32 ? launch_bwd<32, true>(p, st) : launch_bwd<64, true>(p, st);
+  if (D == 32) return launch_bwd<32, false>(p, st);
+  if (D == 64) return launch_bwd<64, false>(p, st);
+  return launch_bwd<128, false>(p, st);
 }

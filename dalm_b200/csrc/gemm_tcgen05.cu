@@ -35,6 +35,7 @@ struct GemmEpilogue {
   int act;              // 0: none, 1: GELU(erf)
   float alpha;
   int M, N, K;
+  DropCfg drop;         // dropout on act(alpha*acc+bias) BEFORE the residual add (BertSelfOutput / BertOutput); p = 0 => off
 };
 
 // Epilogue math for one thread = one output row, 32 consecutive columns [col0, col0+32): alpha, bias, GELU, residual.
@@ -49,6 +50,18 @@ __device__ __forceinline__ void epilogue_math(const GemmEpilogue& ep, const uint
   if (ep.act == 1) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+  }
+  if (ep.drop.p > 0.f) {
+    const unsigned long long dstream = drop_stream(ep.drop);
+    const unsigned long long base = ((unsigned long long)row * (unsigned long long)N + (unsigned long long)col0) >> 2;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const uint4 r = drop_rand4(ep.drop, dstream, base + g);
+      f[g * 4 + 0] *= (r.x >= ep.drop.thresh ? ep.drop.inv_keep : 0.f);
+      f[g * 4 + 1] *= (r.y >= ep.drop.thresh ? ep.drop.inv_keep : 0.f);
+      f[g * 4 + 2] *= (r.z >= ep.drop.thresh ? ep.drop.inv_keep : 0.f);
+      f[g * 4 + 3] *= (r.w >= ep.drop.thresh ? ep.drop.inv_keep : 0.f);
+    }
   }
   if (ep.resid && row_ok) {
     if (ep.resid_f32) {
@@ -499,7 +512,8 @@ using namespace dalm;
 extern "C" int dalm_b200_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* out,
                                       long long ldo, int out_f32, int M, int N, int K, float alpha, const float* bias,
                                       int act, const void* resid, long long ldr, int resid_f32, int block_n,
-                                      int max_ctas, void* stream) {
+                                      int max_ctas, float drop_p, unsigned long long drop_seed,
+                                      unsigned long long drop_stream_id, const void* drop_offset, void* stream) {
   DALM_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   DALM_REQUIRE((N % 8) == 0, "gemm: N=%d must be a multiple of 8", N);
   DALM_REQUIRE((K % 8) == 0, "gemm: K=%d must be a multiple of 8", K);
@@ -510,15 +524,15 @@ extern "C" int dalm_b200_gemm_bf16_tn(const void* A, long long lda, const void* 
     DALM_REQUIRE((ldr % (resid_f32 ? 4 : 8)) == 0, "gemm: ldr=%lld breaks 16-byte row alignment", ldr);
     DALM_REQUIRE((reinterpret_cast<uintptr_t>(resid) & 15) == 0, "gemm: resid is not 16-byte aligned");
   }
-  DALM_REQUIRE(act == 0 || act == 1 || act == 99, "gemm: act must be 0 (none) or 1 (gelu)");   // 99: probe, no stores
+  DALM_REQUIRE(act == 0 || act == 1, "gemm: act must be 0 (none) or 1 (gelu)");
   int bn = block_n;
   if (bn == 0) {
-    // tile-shape heuristic: prefer the CTA-pair 256x256 tile when it fills >= ~2 waves of 74 clusters; else the widest
-    // single-CTA tile that still yields about one wave of 148 CTAs.
-    const long long m2 = (M + 255) / 256, m1 = (M + 127) / 128;
-    if (m2 * ((N + 255) / 256) >= 2 * (kNumSMs / 2) && N >= 256) bn = 2256;
-    else if (m2 * ((N + 127) / 128) >= (kNumSMs / 2) && N >= 128) bn = 2128;
-    else if (m1 * ((N + 127) / 128) >= kNumSMs) bn = 128;
+    // tile-shape heuristic (measured, profiles/r01_gemm_probe_tma_store_epilogue.jsonl): the single-CTA 128x256 tile is
+    // the fastest whenever it yields >= 1 wave of 148 CTAs; smaller problems take the widest tile that still does.
+    // The CTA-pair kernel (block_n 2128/2256) is correct and tested but not faster on these shapes, so never auto-picked.
+    const long long m1 = (M + 127) / 128;
+    if (m1 * ((N + 255) / 256) >= kNumSMs && N >= 256) bn = 256;
+    else if (m1 * ((N + 127) / 128) >= kNumSMs && N >= 128) bn = 128;
     else bn = 64;
   }
   DALM_REQUIRE(bn == 64 || bn == 128 || bn == 256 || bn == 2128 || bn == 2256 || bn == 3256 || bn == 4256,
@@ -529,7 +543,9 @@ extern "C" int dalm_b200_gemm_bf16_tn(const void* A, long long lda, const void* 
   if (int e = get_tmap(A, M, K, lda, 128, &ta)) return e;
   if (int e = get_tmap(B, N, K, ldb, pair ? tile_n / 2 : tile_n, &tb)) return e;
   if (int e = get_tmap(out, M, N, ldo, 128, &to, out_f32)) return e;
-  GemmEpilogue ep{out, ldo, out_f32, bias, resid, ldr, resid_f32, act, alpha, M, N, K};
+  DALM_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "gemm: dropout p must be in [0,1)");
+  GemmEpilogue ep{out, ldo, out_f32, bias, resid, ldr, resid_f32, act, alpha, M, N, K,
+                  make_drop(drop_p, drop_seed, drop_stream_id, drop_offset)};
   cudaStream_t st = (cudaStream_t)stream;
   if (bn == 2256) return launch_gemm2<256>(ta, tb, to, ep, max_ctas, st);
   if (bn == 3256) return launch_gemm2<256, 3>(ta, tb, to, ep, max_ctas, st);     // tuning probes (fewer stages)

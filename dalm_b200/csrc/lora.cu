@@ -34,6 +34,28 @@ __device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, uint32_t b
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// in-place dropout of a [rows x 128-col] bf16 smem tile (row stride lds) whose element (r, c) is x[m0 + r, k0 + c] of a
+// logical [M, K] tensor: the SAME (seed, stream, m*K + k) indexing in the forward skinny GEMM, the wgrad and lora_dx
+template <int NT>
+__device__ __forceinline__ void drop_tile(__nv_bfloat16* tile, int lds, int rows, int m0, int k0, int M, int K,
+                                          const DropCfg& d, unsigned long long dstream) {
+  for (int i = threadIdx.x; i < rows * 16; i += NT) {
+    const int r = i >> 4, p = i & 15;
+    const int m = m0 + r, k = k0 + p * 8;
+    if (m < M && k < K) {
+      const unsigned long long idx = (unsigned long long)m * K + k;          // multiple of 8 (K % 8 == 0)
+      const uint4 r0 = drop_rand4(d, dstream, idx >> 2), r1 = drop_rand4(d, dstream, (idx >> 2) + 1);
+      const unsigned int rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      float f[8];
+      bf16x8* ptr = reinterpret_cast<bf16x8*>(tile + r * lds + p * 8);
+      unpack8(*ptr, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] *= (rr[j] >= d.thresh ? d.inv_keep : 0.f);
+      *ptr = pack8(f);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // wgrad: grid (ceil(K/128), ceil(M/TOK)); 4 warps, warp w owns columns [w*32, w*32+32) of the CTA's 128-column slab.
 // G has R (8 or 16) valid columns; rows 0-7 of the result go to out0, rows 8-15 to out1 (two adapters that share X).
@@ -43,7 +65,8 @@ constexpr int WG_TOK = 512, WG_CH = 64, WG_XS = 128 + 8, WG_GS = 16 + 8;
 __global__ void __launch_bounds__(128) lora_wgrad_mma_kernel(const __nv_bfloat16* __restrict__ X, long long ldx,
                                                              const __nv_bfloat16* __restrict__ G, long long ldg, int R,
                                                              float* __restrict__ out0, float* __restrict__ out1,
-                                                             long long so_r, long long so_k, int M, int K, float scale) {
+                                                             long long so_r, long long so_k, int M, int K, float scale,
+                                                             DropCfg dropx) {
   __shared__ __align__(16) __nv_bfloat16 Xs[2][WG_CH][WG_XS];
   __shared__ __align__(16) __nv_bfloat16 Gs[2][WG_CH][WG_GS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -81,6 +104,10 @@ __global__ void __launch_bounds__(128) lora_wgrad_mma_kernel(const __nv_bfloat16
     const int buf = c & 1;
     if (c + 1 < nchunks) { load_chunk(c + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
+    if (dropx.p > 0.f) {                                         // X is the LoRA branch input: dA = g^T dropout(x)
+      drop_tile<128>(&Xs[buf][0][0], WG_XS, WG_CH, m_begin + c * WG_CH, col0, m_end, K, dropx, drop_stream(dropx));
+      __syncthreads();
+    }
 #pragma unroll
     for (int ks = 0; ks < WG_CH / 16; ++ks) {
       const int tok0 = ks * 16;
@@ -112,33 +139,37 @@ __global__ void __launch_bounds__(128) lora_wgrad_mma_kernel(const __nv_bfloat16
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// skinny GEMM: out[m, 0..R) = X[m,:] . W[0..R,:]^T   (R = 8 or 16 rows of W, zero-padded to 16 in smem).
-// grid = ceil(M/32) CTAs of 64 threads: warp w owns rows [w*16, w*16+16) of the CTA's 32-token slab; K streamed in
-// 128-wide chunks with cp.async double buffering. Output is written bf16 with row stride ldo (the tail columns of an
-// augmented activation buffer).
+// skinny GEMM: out[m, 0..R) = X[m,:] . W[0..R,:]^T   (R in {8,16,24,32} rows of W, zero-padded in smem).
+// grid = ceil(M/32) CTAs of 256 threads. The 8 warps split the CTA's work 2 (row halves of 16) x 4 (quarters of each
+// 128-wide K chunk), so every SM holds enough warps to keep HBM busy; the 4 partial sums per row half are combined through
+// shared memory at the end. X is streamed once with cp.async double buffering. Output is written bf16 with row stride ldo
+// (the tail columns of an augmented activation buffer).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int SK_ROWS = 32, SK_KC = 128, SK_LD = SK_KC + 8;
 
-__global__ void __launch_bounds__(64) skinny_gemm_kernel(const __nv_bfloat16* __restrict__ X, long long ldx,
-                                                         const __nv_bfloat16* __restrict__ W, long long ldw, int R,
-                                                         __nv_bfloat16* __restrict__ out, long long ldo, int M, int K) {
+__global__ void __launch_bounds__(256) skinny_gemm_kernel(const __nv_bfloat16* __restrict__ X, long long ldx,
+                                                          const __nv_bfloat16* __restrict__ W, long long ldw, int R,
+                                                          __nv_bfloat16* __restrict__ out, long long ldo, int M, int K,
+                                                          DropCfg dropx) {
   __shared__ __align__(16) __nv_bfloat16 Xs[2][SK_ROWS][SK_LD];
   __shared__ __align__(16) __nv_bfloat16 Ws[2][32][SK_LD];
+  __shared__ float red[3][2][4][4][32];                          // partial sums of k-quarters 1..3: [kq-1][rg][nt][e][lane]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int rg = warp & 1, kq = warp >> 1;                       // row half, K quarter
   const int m0 = blockIdx.x * SK_ROWS;
   const int nchunks = (K + SK_KC - 1) / SK_KC;
-  for (int i = tid; i < 2 * 32 * SK_LD; i += 64) (&Ws[0][0][0])[i] = __float2bfloat16(0.f);
+  for (int i = tid; i < 2 * 32 * SK_LD; i += 256) (&Ws[0][0][0])[i] = __float2bfloat16(0.f);
   __syncthreads();
 
   auto load_chunk = [&](int c, int buf) {
     const int k0 = c * SK_KC;
-    for (int i = tid; i < SK_ROWS * 16; i += 64) {
+    for (int i = tid; i < SK_ROWS * 16; i += 256) {
       const int r = i >> 4, p = i & 15;
       const int m = m0 + r, k = k0 + p * 8;
       const bool ok = (m < M) && (k < K);
       cp_async16(&Xs[buf][r][p * 8], X + (size_t)(ok ? m : 0) * ldx + (ok ? k : 0), ok);
     }
-    for (int i = tid; i < R * 16; i += 64) {
+    for (int i = tid; i < R * 16; i += 256) {
       const int r = i >> 4, p = i & 15;
       const int k = k0 + p * 8;
       const bool ok = k < K;
@@ -156,27 +187,46 @@ __global__ void __launch_bounds__(64) skinny_gemm_kernel(const __nv_bfloat16* __
     const int buf = c & 1;
     if (c + 1 < nchunks) { load_chunk(c + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
+    if (dropx.p > 0.f) {                                         // u = dropout(x) A^T (peft LoRA input dropout)
+      drop_tile<256>(&Xs[buf][0][0], SK_LD, SK_ROWS, m0, c * SK_KC, M, K, dropx, drop_stream(dropx));
+      __syncthreads();
+    }
 #pragma unroll
-    for (int ks = 0; ks < SK_KC / 16; ++ks) {
+    for (int kk = 0; kk < 2; ++kk) {
+      const int ks = kq * 2 + kk;                                // this warp's two 16-wide k-steps of the chunk
       uint32_t a[4], b[4];
-      ldsm4(a, &Xs[buf][warp * 16 + (lane & 15)][ks * 16 + ((lane >> 4) << 3)]);           // A: rows x k, K-contiguous
-      for (int np = 0; np < npairs; ++np) {
-        ldsm4(b, &Ws[buf][np * 16 + (lane & 7) + ((lane >> 4) << 3)][ks * 16 + (((lane >> 3) & 1) << 3)]);   // B stored [n][k]
-        mma_bf16(acc[2 * np], a, b[0], b[1]);                    // W rows np*16 + 0..7
-        mma_bf16(acc[2 * np + 1], a, b[2], b[3]);                // W rows np*16 + 8..15
+      ldsm4(a, &Xs[buf][rg * 16 + (lane & 15)][ks * 16 + ((lane >> 4) << 3)]);             // A: rows x k, K-contiguous
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        if (np < npairs) {
+          ldsm4(b, &Ws[buf][np * 16 + (lane & 7) + ((lane >> 4) << 3)][ks * 16 + (((lane >> 3) & 1) << 3)]);   // B stored [n][k]
+          mma_bf16(acc[2 * np], a, b[0], b[1]);
+          mma_bf16(acc[2 * np + 1], a, b[2], b[3]);
+        }
       }
     }
     __syncthreads();
   }
+  if (kq > 0) {
 #pragma unroll
-  for (int nt = 0; nt < 4; ++nt) {
-    if (nt * 8 >= R) break;
+    for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int m = m0 + warp * 16 + g + h * 8;
-      if (m < M) {
-        __nv_bfloat162 v = __floats2bfloat162_rn(acc[nt][2 * h], acc[nt][2 * h + 1]);
-        *reinterpret_cast<__nv_bfloat162*>(out + (size_t)m * ldo + nt * 8 + t * 2) = v;
+      for (int e = 0; e < 4; ++e) red[kq - 1][rg][nt][e][lane] = acc[nt][e];
+  }
+  __syncthreads();
+  if (kq == 0) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      if (nt * 8 >= R) break;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nt][e] += red[0][rg][nt][e][lane] + red[1][rg][nt][e][lane] + red[2][rg][nt][e][lane];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int m = m0 + rg * 16 + g + h * 8;
+        if (m < M) {
+          __nv_bfloat162 v = __floats2bfloat162_rn(acc[nt][2 * h], acc[nt][2 * h + 1]);
+          *reinterpret_cast<__nv_bfloat162*>(out + (size_t)m * ldo + nt * 8 + t * 2) = v;
+        }
       }
     }
   }
@@ -189,7 +239,8 @@ using namespace dalm;
 // out0[r*so_r + k*so_k] += scale * sum_m G[m,r] X[m,k] for r<8 ; rows 8..R-1 go to out1 (R == 16). G: bf16 [M, >=R].
 extern "C" int dalm_b200_lora_wgrad(const void* X, long long ldx, const void* G, long long ldg, float* out0,
                                     float* out1, long long so_r, long long so_k, int M, int K, int R, float scale,
-                                    void* stream) {
+                                    float drop_p, unsigned long long drop_seed, unsigned long long drop_stream_id,
+                                    const void* drop_offset, void* stream) {
   DALM_REQUIRE(R == 8 || R == 16, "lora_wgrad: rank rows %d unsupported (8 or 16)", R);
   DALM_REQUIRE(R == 8 || out1 != nullptr, "lora_wgrad: R=16 needs a second output");
   DALM_REQUIRE((ldx % 8) == 0 && (ldg % 8) == 0 && (K % 8) == 0, "lora_wgrad: K and strides must be multiples of 8");
@@ -197,20 +248,23 @@ extern "C" int dalm_b200_lora_wgrad(const void* X, long long ldx, const void* G,
   DALM_REQUIRE(M > 0 && K > 0, "lora_wgrad: empty problem");
   dim3 grid((K + 127) / 128, (M + WG_TOK - 1) / WG_TOK);
   lora_wgrad_mma_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)G, ldg, R,
-                                                               out0, out1, so_r, so_k, M, K, scale);
+                                                               out0, out1, so_r, so_k, M, K, scale,
+                                                               make_drop(drop_p, drop_seed, drop_stream_id, drop_offset));
   count_launch();
   return check_launch("lora_wgrad_mma_kernel");
 }
 
 // out[M, R] (bf16, row stride ldo) = X[M,K] . W[R,K]^T
 extern "C" int dalm_b200_skinny_gemm(const void* X, long long ldx, const void* W, long long ldw, void* out, long long ldo,
-                                     int M, int K, int R, void* stream) {
+                                     int M, int K, int R, float drop_p, unsigned long long drop_seed,
+                                     unsigned long long drop_stream_id, const void* drop_offset, void* stream) {
   DALM_REQUIRE(R == 8 || R == 16 || R == 24 || R == 32, "skinny_gemm: R=%d unsupported (8/16/24/32)", R);
   DALM_REQUIRE((ldx % 8) == 0 && (ldw % 8) == 0 && (K % 8) == 0 && (ldo % 2) == 0, "skinny_gemm: alignment");
   DALM_REQUIRE(((uintptr_t)X & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 3) == 0, "skinny_gemm: pointer alignment");
   DALM_REQUIRE(M > 0 && K > 0, "skinny_gemm: empty problem");
-  skinny_gemm_kernel<<<(M + SK_ROWS - 1) / SK_ROWS, 64, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)W,
-                                                                                  ldw, R, (__nv_bfloat16*)out, ldo, M, K);
+  skinny_gemm_kernel<<<(M + SK_ROWS - 1) / SK_ROWS, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)W,
+                                                                                  ldw, R, (__nv_bfloat16*)out, ldo, M, K,
+                                                                                  make_drop(drop_p, drop_seed, drop_stream_id, drop_offset));
   count_launch();
   return check_launch("skinny_gemm_kernel");
 }

@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                             const float* __restrict__ beta, float* __restrict__ y32,
                                                             __nv_bfloat16* __restrict__ y16, long long ld16,
                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                            int H, float eps) {
+                                                            int H, float eps, DropCfg drop) {
   extern __shared__ float row[];
   __shared__ float red[32];
   const size_t r = blockIdx.x;
@@ -29,8 +29,10 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   const float var = block_sum(q, red) / H;
   const float rstd = rsqrtf(var + eps);
   if (threadIdx.x == 0) { mean_out[r] = mean; rstd_out[r] = rstd; }
+  const unsigned long long dstream = drop.p > 0.f ? drop_stream(drop) : 0ull;
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    const float v = (row[i] - mean) * rstd * gamma[i] + beta[i];
+    float v = (row[i] - mean) * rstd * gamma[i] + beta[i];
+    if (drop.p > 0.f) v *= drop_scale1(drop, dstream, (unsigned long long)r * H + i);     // embeddings dropout
     if (y32) y32[r * H + i] = v;
     y16[r * ld16 + i] = __float2bfloat16_rn(v);
   }
@@ -42,7 +44,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                             const float* __restrict__ dy_a, const __nv_bfloat16* __restrict__ dy_b,
                                                             long long ldb, float* __restrict__ dz32,
-                                                            __nv_bfloat16* __restrict__ dz16, long long ld16, int H) {
+                                                            __nv_bfloat16* __restrict__ dz16, long long ld16, int H,
+                                                            DropCfg drop16) {
   extern __shared__ float sm[];
   float* gbuf = sm;          // g = dy*gamma
   float* zh = sm + H;        // zhat
@@ -61,10 +64,15 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   }
   s1 = block_sum(s1, red) / H;
   s2 = block_sum(s2, red) / H;
+  // z = dropout(dense_out) + residual: the residual branch takes dz as is (dz32), the dense branch takes mask*dz/(1-p)
+  const unsigned long long dstream = drop16.p > 0.f ? drop_stream(drop16) : 0ull;
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
     const float d = rstd * (gbuf[i] - s1 - zh[i] * s2);
     if (dz32) dz32[r * H + i] = d;
-    if (dz16) dz16[r * ld16 + i] = __float2bfloat16_rn(d);
+    if (dz16) {
+      const float m = drop16.p > 0.f ? drop_scale1(drop16, dstream, (unsigned long long)r * H + i) : 1.f;
+      dz16[r * ld16 + i] = __float2bfloat16_rn(d * m);
+    }
   }
 }
 
@@ -334,6 +342,58 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   p[i] -= (lr / bc1) * (mi / denom);
 }
 
+// dropout plumbing: the per-replay counter bump, and the keep-mask itself (for tests: lets a torch reference apply the
+// identical mask)
+__global__ void bump_counter_kernel(unsigned long long* c) { if (threadIdx.x == 0 && blockIdx.x == 0) c[0] += 1ull; }
+__global__ void dropout_scale_kernel(float* __restrict__ out, long long n, DropCfg drop) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = drop.p > 0.f ? drop_scale1(drop, drop_stream(drop), (unsigned long long)i) : 1.f;
+}
+
+// LoRA input-dropout backward: dh[m,k] += mask(m,k)/(1-p) * sum_r G[m,r] * A[r,k]   (G bf16 [M,R], A bf16 [R,K] = A_stack)
+// The un-dropped case folds this term into the dgrad GEMM (K-augmentation); with dropout the mask makes it elementwise.
+__global__ void __launch_bounds__(256) lora_dx_kernel(__nv_bfloat16* __restrict__ dh, long long lddh,
+                                                      const __nv_bfloat16* __restrict__ G, long long ldg,
+                                                      const __nv_bfloat16* __restrict__ A, long long lda, int M, int K, int R,
+                                                      DropCfg drop) {
+  __shared__ __nv_bfloat16 As[32][512 + 8];
+  __shared__ float Gs[32][32];
+  const int k0 = blockIdx.x * 512, m0 = blockIdx.y * 32;
+  for (int i = threadIdx.x; i < R * 512; i += 256) {
+    const int r = i / 512, c = i - r * 512;
+    As[r][c] = (k0 + c < K) ? A[(size_t)r * lda + k0 + c] : __float2bfloat16(0.f);
+  }
+  for (int i = threadIdx.x; i < 32 * R; i += 256) {
+    const int mm = i / R, r = i - mm * R;
+    Gs[mm][r] = (m0 + mm < M) ? __bfloat162float(G[(size_t)(m0 + mm) * ldg + r]) : 0.f;
+  }
+  __syncthreads();
+  const unsigned long long dstream = drop_stream(drop);
+  const int cg = threadIdx.x & 63, rsub = threadIdx.x >> 6;               // 64 column groups of 8, 4 rows per pass
+  const int c = cg * 8;
+  if (k0 + c >= K) return;
+  for (int mm = rsub; mm < 32; mm += 4) {
+    const int m = m0 + mm;
+    if (m >= M) break;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = 0; r < R; ++r) {
+      const float gv = Gs[mm][r];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(gv, __bfloat162float(As[r][c + j]), acc[j]);
+    }
+    const unsigned long long idx = (unsigned long long)m * K + k0 + c;     // multiple of 8
+    const uint4 r0 = drop_rand4(drop, dstream, idx >> 2), r1 = drop_rand4(drop, dstream, (idx >> 2) + 1);
+    const unsigned int rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    __nv_bfloat16* p = dh + (size_t)m * lddh + k0 + c;
+    float cur[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(p), cur);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cur[j] += (rr[j] >= drop.thresh ? drop.inv_keep : 0.f) * acc[j];
+    *reinterpret_cast<bf16x8*>(p) = pack8(cur);
+  }
+}
+
 // out_bf16[r*ldo + c] = scale * in_f32[r*si_r + c*si_c]   (LoRA factor packing into the augmented weights)
 __global__ void pack_scaled_bf16_kernel(const float* __restrict__ in, long long si_r, long long si_c,
                                         __nv_bfloat16* __restrict__ out, long long ldo, int rows, int cols, float scale) {
@@ -372,19 +432,25 @@ using namespace dalm;
 #define ST(s) ((cudaStream_t)(s))
 
 extern "C" int dalm_b200_layernorm_fwd(const float* z, const float* gamma, const float* beta, float* y32, void* y16,
-                                       long long ld16, float* mean, float* rstd, int M, int H, float eps, void* stream) {
+                                       long long ld16, float* mean, float* rstd, int M, int H, float eps, float drop_p,
+                                       unsigned long long drop_seed, unsigned long long drop_stream_id,
+                                       const void* drop_offset, void* stream) {
   DALM_REQUIRE(M > 0 && H > 0 && H * 4 <= 64 * 1024, "layernorm_fwd: bad shape M=%d H=%d", M, H);
-  layernorm_fwd_kernel<<<M, 256, H * sizeof(float), ST(stream)>>>(z, gamma, beta, y32, (__nv_bfloat16*)y16, ld16, mean, rstd, H, eps);
+  DALM_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "layernorm_fwd: dropout p must be in [0,1)");
+  layernorm_fwd_kernel<<<M, 256, H * sizeof(float), ST(stream)>>>(z, gamma, beta, y32, (__nv_bfloat16*)y16, ld16, mean, rstd, H, eps,
+                                                                  make_drop(drop_p, drop_seed, drop_stream_id, drop_offset));
   count_launch();
   return check_launch("layernorm_fwd_kernel");
 }
 extern "C" int dalm_b200_layernorm_bwd(const float* z, const float* gamma, const float* mean, const float* rstd,
                                        const float* dy_f32, const void* dy_bf16, long long ldb, float* dz32, void* dz16,
-                                       long long ld16, int M, int H, void* stream) {
+                                       long long ld16, int M, int H, float drop_p, unsigned long long drop_seed,
+                                       unsigned long long drop_stream_id, const void* drop_offset, void* stream) {
   DALM_REQUIRE(M > 0 && H > 0 && H * 8 <= 48 * 1024, "layernorm_bwd: bad shape M=%d H=%d", M, H);
   DALM_REQUIRE(dy_f32 || dy_bf16, "layernorm_bwd: no incoming gradient");
   layernorm_bwd_kernel<<<M, 256, 2 * H * sizeof(float), ST(stream)>>>(z, gamma, mean, rstd, dy_f32, (const __nv_bfloat16*)dy_bf16, ldb,
-                                                                     dz32, (__nv_bfloat16*)dz16, ld16, H);
+                                                                     dz32, (__nv_bfloat16*)dz16, ld16, H,
+                                                                     make_drop(drop_p, drop_seed, drop_stream_id, drop_offset));
   count_launch();
   return check_launch("layernorm_bwd_kernel");
 }
@@ -484,6 +550,31 @@ extern "C" int dalm_b200_pack_scaled_bf16(const float* in, long long si_r, long 
   pack_scaled_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(in, si_r, si_c, (__nv_bfloat16*)out, ldo, rows, cols, scale);
   count_launch();
   return check_launch("pack_scaled_bf16_kernel");
+}
+extern "C" int dalm_b200_bump_counter(void* counter, void* stream) {
+  bump_counter_kernel<<<1, 32, 0, ST(stream)>>>((unsigned long long*)counter);
+  count_launch();
+  return check_launch("bump_counter_kernel");
+}
+// out[i] = 0 or 1/(1-p): the scale dropout applies to element i of a tensor under (seed, stream, *offset)
+extern "C" int dalm_b200_dropout_scale(float* out, long long n, float p, unsigned long long seed, unsigned long long stream_id,
+                                       const void* offset, void* stream) {
+  DALM_REQUIRE(p >= 0.f && p < 1.f, "dropout_scale: p must be in [0,1)");
+  if (n <= 0) return 0;
+  dropout_scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(out, n, make_drop(p, seed, stream_id, offset));
+  count_launch();
+  return check_launch("dropout_scale_kernel");
+}
+extern "C" int dalm_b200_lora_dx(void* dh, long long lddh, const void* G, long long ldg, const void* A, long long lda, int M,
+                                 int K, int R, float p, unsigned long long seed, unsigned long long stream_id,
+                                 const void* offset, void* stream) {
+  DALM_REQUIRE(R >= 1 && R <= 32 && (K % 8) == 0 && (lddh % 8) == 0, "lora_dx: bad shape R=%d K=%d", R, K);
+  DALM_REQUIRE(p >= 0.f && p < 1.f, "lora_dx: p must be in [0,1)");
+  dim3 grid((K + 511) / 512, (M + 31) / 32);
+  lora_dx_kernel<<<grid, 256, 0, ST(stream)>>>((__nv_bfloat16*)dh, lddh, (const __nv_bfloat16*)G, ldg, (const __nv_bfloat16*)A, lda,
+                                               M, K, R, make_drop(p, seed, stream_id, offset));
+  count_launch();
+  return check_launch("lora_dx_kernel");
 }
 // table: device array of n_entries records {const float* in; int64 si_r, si_c; bf16* out; int64 ldo; int32 rows, cols; float scale}
 // (48 bytes each, natural alignment) — see dalm_b200/engine/lora.py:pack_table

@@ -93,6 +93,13 @@ class BertEncoder(torch.nn.Module):
             W["ln2_b"] = g(p + "output.LayerNorm.bias", f32)
             self.layers.append(W)
         self.pooler = {k: v for k, v in sd.items() if k.startswith("pooler.")}   # carried for save_pretrained only
+        # dropout (active only in train() mode, like the HF module the reference wraps; from_pretrained returns eval())
+        self.p_hidden = float(cfg.get("hidden_dropout_prob", 0.1))
+        self.p_attn = float(cfg.get("attention_probs_dropout_prob", 0.1))
+        self.p_lora = 0.05 if lora else 0.0                   # reference rag_e2e_base_model.py:151 (lora_dropout)
+        self.drop_seed = 0x5DA1B200 + lora_seed
+        self.drop_offset = torch.zeros(1, dtype=torch.int64, device=self.dev)      # bumped once per (graphed) step
+        self._call = 0
         self.lora: Optional[LoraBank] = None
         if lora:
             specs = [(f"encoder.layer.{l}.attention.self.{n}", H, H) for l in range(self.nl) for n in self.LORA_TARGETS]
@@ -100,6 +107,13 @@ class BertEncoder(torch.nn.Module):
             self.lora_flat = torch.nn.Parameter(self.lora.flat, requires_grad=True)
             self.lora_flat.grad = self.lora.grad
             self.repack_lora()
+        self.eval()
+
+    def _drop(self, p: float, call: int, layer: int, site: int):
+        """dropout descriptor of one site, or None when inactive (eval mode / p == 0)"""
+        if not self.training or p <= 0.0:
+            return None
+        return ops.Drop(p, self.drop_seed, (call << 24) | (layer << 8) | site, self.drop_offset)
 
     # ------------------------------------------------------------------------------------------------------------
     def _pack_entries(self):
@@ -125,50 +139,87 @@ class BertEncoder(torch.nn.Module):
     # ------------------------------------------------------------------------------------------------------------
     def forward_hidden(self, ids: torch.Tensor, mask: torch.Tensor, save: bool = True):
         """ids, mask: int64 [B,L] on device -> (hidden fp32 [B,L,H], ctx)"""
-        B, L = ids.shape
-        M, H, F, Ra = B * L, self.H, self.F, self.Ra
+        hs, ctx = self.forward_segments([(ids, mask)], save=save)
+        return hs[0], ctx
+
+    def forward_segments(self, segments, save: bool = True):
+        """Several (ids, mask) batches with different sequence lengths (the query batch and the passage batch of one
+        step) through ONE pass over the weights: all linear layers / norms / activations run on the concatenated token
+        rows (M = sum B_i L_i: bigger, better-filled tensor-core tiles, half the launches); only attention is launched
+        per segment. Returns ([hidden_i fp32 [B_i,L_i,H]], ctx)."""
+        H, F, Ra = self.H, self.F, self.Ra
         ctx = _Ctx()
-        ctx.B, ctx.L, ctx.mask = B, L, mask.contiguous()
-        ctx.layers = []
-        z = ops.bert_embed(ids, self.word, self.pos, self.type0)
+        ctx.segs = []
+        r0 = 0
+        for ids, mask in segments:
+            B, L = ids.shape
+            ctx.segs.append((B, L, mask.contiguous(), r0))
+            r0 += B * L
+        M = r0
+        ctx.M, ctx.layers = M, []
+        self._call += 1
+        ctx.call = call = self._call
+        ctx.training = self.training
+        z = torch.empty(M, H, dtype=f32, device=self.dev)
+        for (ids, _), (B, L, _, s0) in zip(segments, ctx.segs):
+            ops.bert_embed(ids, self.word, self.pos, self.type0, out=z[s0:s0 + B * L])
         x_aug = _aug_buf(M, H, Ra, self.dev)
-        x32, _, mean, rstd = ops.layernorm_fwd(z, self.emb_g, self.emb_b, self.eps, y16=x_aug[:, :H])
-        for W in self.layers:
+        x32, _, mean, rstd = ops.layernorm_fwd(z, self.emb_g, self.emb_b, self.eps, y16=x_aug[:, :H],
+                                               drop=self._drop(self.p_hidden, call, 255, 0))
+        for li, W in enumerate(self.layers):
             a = _Ctx()
             a.x_aug = x_aug
             if Ra:
-                ops.skinny_gemm(x_aug[:, :H], W["A_stack"], x_aug[:, H:], K=H, R=Ra)             # u = x A^T  [M,3r]
+                ops.skinny_gemm(x_aug[:, :H], W["A_stack"], x_aug[:, H:], K=H, R=Ra,              # u = dropout(x) A^T [M,3r]
+                                dropx=self._drop(self.p_lora, call, li, 3))
             qkv = ops.gemm(x_aug, W["Wqkv_aug"], bias=W["bqkv"])                                   # [M,3H] (+LoRA via K-aug)
-            att, lse = ops.attention_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], ctx.mask, B, L, self.nh, self.nh,
-                                         self.hd, causal=False)
-            z1 = ops.gemm(att, W["Wo"], out_dtype=f32, bias=W["bo"], resid=x32)                    # dense + residual
+            att = torch.empty(M, H, dtype=bf16, device=self.dev)
+            lses = []
+            for si, (B, L, mask, s0) in enumerate(ctx.segs):
+                rows = slice(s0, s0 + B * L)
+                _, lse = ops.attention_fwd(qkv[rows, :H], qkv[rows, H:2 * H], qkv[rows, 2 * H:], mask, B, L, self.nh,
+                                           self.nh, self.hd, causal=False, out=att[rows],
+                                           drop=self._drop(self.p_attn, call, li, 8 + si))
+                lses.append(lse)
+            z1 = ops.gemm(att, W["Wo"], out_dtype=f32, bias=W["bo"], resid=x32,                    # dropout(dense) + residual
+                          drop=self._drop(self.p_hidden, call, li, 1))
             h_aug = torch.empty(M, H, dtype=bf16, device=self.dev)
             h32, _, m1, r1 = ops.layernorm_fwd(z1, W["ln1_g"], W["ln1_b"], self.eps, y16=h_aug)
             pre = ops.gemm(h_aug, W["Wi"], bias=W["bi"])                                           # [M,F] pre-activation
             act = ops.gelu_fwd(pre)
-            z2 = ops.gemm(act, W["Wo2"], out_dtype=f32, bias=W["bo2"], resid=h32)
+            z2 = ops.gemm(act, W["Wo2"], out_dtype=f32, bias=W["bo2"], resid=h32, drop=self._drop(self.p_hidden, call, li, 2))
             x_aug = _aug_buf(M, H, Ra, self.dev)
             x32, _, m2, r2 = ops.layernorm_fwd(z2, W["ln2_g"], W["ln2_b"], self.eps, y16=x_aug[:, :H])
             if save:
                 a.qkv, a.att, a.lse, a.z1, a.m1, a.r1, a.h_aug, a.pre, a.act, a.z2, a.m2, a.r2 = \
-                    qkv, att, lse, z1, m1, r1, h_aug, pre, act, z2, m2, r2
+                    qkv, att, lses, z1, m1, r1, h_aug, pre, act, z2, m2, r2
                 ctx.layers.append(a)
-        return x32.view(B, L, H), ctx
+        return [x32[s0:s0 + B * L].view(B, L, H) for (B, L, _, s0) in ctx.segs], ctx
 
     # ------------------------------------------------------------------------------------------------------------
     def backward_hidden(self, ctx: _Ctx, d_hidden: torch.Tensor) -> None:
         """d_hidden fp32 [B,L,H]; accumulates LoRA gradients into self.lora.grad (base weights are frozen: PEFT mode)."""
+        self.backward_segments(ctx, [d_hidden])
+
+    def backward_segments(self, ctx: _Ctx, d_hiddens) -> None:
         if self.lora is None:
             return                                           # nothing trainable below the pooled output
-        M, H = ctx.B * ctx.L, self.H
+        M, H = ctx.M, self.H
+        d = d_hiddens[0].reshape(-1, H) if len(d_hiddens) == 1 else torch.cat([t.reshape(-1, H) for t in d_hiddens], 0)
         last, Wl = ctx.layers[self.nl - 1], self.layers[self.nl - 1]
-        last._pre = ops.layernorm_bwd(last.z2, Wl["ln2_g"], last.m2, last.r2, dy_f32=d_hidden.reshape(M, H).contiguous())
+        last._pre = ops.layernorm_bwd(last.z2, Wl["ln2_g"], last.m2, last.r2, dy_f32=d.contiguous(),
+                                      drop16=self._bdrop(ctx, self.p_hidden, self.nl - 1, 2))
         self._bwd_from_ln2(ctx, self.nl - 1)
+
+    def _bdrop(self, ctx, p: float, layer: int, site: int):
+        """the forward call's dropout descriptor, regenerated for its backward"""
+        if not ctx.training or p <= 0.0:
+            return None
+        return ops.Drop(p, self.drop_seed, (ctx.call << 24) | (layer << 8) | site, self.drop_offset)
 
     def _bwd_from_ln2(self, ctx: _Ctx, l_start: int) -> None:
         """continue the backward at layer l_start whose LN2 input gradient has already been computed (stashed in _pre)"""
-        B, L = ctx.B, ctx.L
-        M, H, Ra, r = B * L, self.H, self.Ra, self.r
+        M, H, Ra, r = ctx.M, self.H, self.Ra, self.r
         for l in range(l_start, -1, -1):
             W, a = self.layers[l], ctx.layers[l]
             dz2_32, dz2_16 = a._pre
@@ -176,27 +227,37 @@ class BertEncoder(torch.nn.Module):
             dact = ops.gemm(dz2_16, W["Wo2T"])
             ops.gelu_bwd_(a.pre, dact)
             dh_16 = ops.gemm(dact, W["WiT"])
-            dz1_32, dz1_16 = ops.layernorm_bwd(a.z1, W["ln1_g"], a.m1, a.r1, dy_f32=dz2_32, dy_bf16=dh_16)
+            dz1_32, dz1_16 = ops.layernorm_bwd(a.z1, W["ln1_g"], a.m1, a.r1, dy_f32=dz2_32, dy_bf16=dh_16,
+                                               drop16=self._bdrop(ctx, self.p_hidden, l, 1))
             datt = ops.gemm(dz1_16, W["WoT"])
             dqkv_aug = _aug_buf(M, 3 * H, Ra, self.dev)
-            ops.attention_bwd(a.qkv[:, :H], a.qkv[:, H:2 * H], a.qkv[:, 2 * H:], ctx.mask, a.att, a.lse, datt, B, L,
-                              self.nh, self.nh, self.hd, causal=False, dq=dqkv_aug[:, :H], dk=dqkv_aug[:, H:2 * H],
-                              dv=dqkv_aug[:, 2 * H:3 * H])
+            for si, ((B, L, mask, s0), lse) in enumerate(zip(ctx.segs, a.lse)):
+                rows = slice(s0, s0 + B * L)
+                ops.attention_bwd(a.qkv[rows, :H], a.qkv[rows, H:2 * H], a.qkv[rows, 2 * H:], mask, a.att[rows], lse,
+                                  datt[rows], B, L, self.nh, self.nh, self.hd, causal=False, dq=dqkv_aug[rows, :H],
+                                  dk=dqkv_aug[rows, H:2 * H], dv=dqkv_aug[rows, 2 * H:3 * H],
+                                  drop=self._bdrop(ctx, self.p_attn, l, 8 + si))
             for j, n in enumerate(self.LORA_TARGETS):
                 # g_j = dY_j (alpha/r) B_j : only the target's own column block is read
                 ops.skinny_gemm(dqkv_aug[:, j * H:(j + 1) * H], W["Bblk"][j * r:(j + 1) * r, j * H:(j + 1) * H],
                                 dqkv_aug[:, 3 * H + j * r:], K=H, R=r)
             names = [f"encoder.layer.{l}.attention.self.{n}" for n in self.LORA_TARGETS]
             # dA[rr,k] += sum_m g_j[m,rr] x[m,k]: q and k share one pass over x (16-row MMA tile), v takes a second
+            xdrop = self._bdrop(ctx, self.p_lora, l, 3)                          # dA = g^T dropout(x)
             ops.lora_wgrad_(a.x_aug[:, :H], dqkv_aug[:, 3 * H:], self.lora.gA[names[0]], H, 1, H, 2 * r, 1.0,
-                            out1=self.lora.gA[names[1]])
-            ops.lora_wgrad_(a.x_aug[:, :H], dqkv_aug[:, 3 * H + 2 * r:], self.lora.gA[names[2]], H, 1, H, r, 1.0)
+                            out1=self.lora.gA[names[1]], dropx=xdrop)
+            ops.lora_wgrad_(a.x_aug[:, :H], dqkv_aug[:, 3 * H + 2 * r:], self.lora.gA[names[2]], H, 1, H, r, 1.0, dropx=xdrop)
             for j, name in enumerate(names):
                 # dB[n,rr] += (alpha/r) * sum_m dY_j[m,n] u_j[m,rr]
                 ops.lora_wgrad_(dqkv_aug[:, j * H:(j + 1) * H], a.x_aug[:, H + j * r:], self.lora.gB[name], 1, r, H, r,
                                 self.lora.scale)
             if l == 0:
                 return
-            dx_16 = ops.gemm(dqkv_aug, W["WqkvT_aug"])
+            if xdrop is None:
+                dx_16 = ops.gemm(dqkv_aug, W["WqkvT_aug"])                        # LoRA's A-path folded into K
+            else:
+                dx_16 = ops.gemm(dqkv_aug[:, :3 * H], W["WqkvT_aug"][:, :3 * H])   # base path only ...
+                ops.lora_dx_(dx_16, dqkv_aug[:, 3 * H:], W["A_stack"], K=H, R=Ra, drop=xdrop)   # ... + mask * (g A)
             p, Wp = ctx.layers[l - 1], self.layers[l - 1]
-            p._pre = ops.layernorm_bwd(p.z2, Wp["ln2_g"], p.m2, p.r2, dy_f32=dz1_32, dy_bf16=dx_16)
+            p._pre = ops.layernorm_bwd(p.z2, Wp["ln2_g"], p.m2, p.r2, dy_f32=dz1_32, dy_bf16=dx_16,
+                                       drop16=self._bdrop(ctx, self.p_hidden, l - 1, 2))

@@ -94,6 +94,11 @@ class LlamaDecoder(torch.nn.Module):
             W["g2"] = g(p + "post_attention_layernorm.weight", f32)
             self.layers.append(W)
         self._rope_cache: Dict[int, tuple] = {}
+        # Llama has no hidden / attention dropout (attention_dropout = 0); only peft's LoRA input dropout (0.05) applies
+        self.p_lora = 0.05 if lora else 0.0
+        self.drop_seed = 0x11A3AB200 + lora_seed
+        self.drop_offset = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self._call = 0
         self.lora: Optional[LoraBank] = None
         if lora:
             outs = {"q_proj": self.Nq, "v_proj": self.Nkv}
@@ -102,6 +107,12 @@ class LlamaDecoder(torch.nn.Module):
             self.lora_flat = torch.nn.Parameter(self.lora.flat, requires_grad=True)
             self.lora_flat.grad = self.lora.grad
             self.repack_lora()
+        self.eval()                                           # like from_pretrained(): dropout only after .train()
+
+    def _drop(self, training: bool, call: int, layer: int):
+        if not training or self.p_lora <= 0.0:
+            return None
+        return ops.Drop(self.p_lora, self.drop_seed, (call << 24) | (layer << 8) | 3, self.drop_offset)
 
     # column offset / width of each LoRA target inside the fused qkv output
     def _target_cols(self, n: str):
@@ -143,14 +154,17 @@ class LlamaDecoder(torch.nn.Module):
         cos_t, sin_t = self._rope(L)
         ctx = _Ctx()
         ctx.B, ctx.L, ctx.mask, ctx.layers = B, L, mask.contiguous(), []
+        self._call += 1
+        ctx.call, ctx.training = self._call, self.training
         x = ops.embed_gather(ids, self.embed)                                    # fp32 residual stream [M,H]
-        for W in self.layers:
+        for li, W in enumerate(self.layers):
             a = _Ctx()
             a.x_in = x
             a.h1_aug = _aug_buf(M, H, Ra, self.dev)
             _, a.rstd1 = ops.rmsnorm_fwd(x, W["g1"], self.eps, h=a.h1_aug[:, :H])
             if Ra:
-                ops.skinny_gemm(a.h1_aug[:, :H], W["A_stack"], a.h1_aug[:, H:], K=H, R=Ra)   # u = h1 A^T [M,2r]
+                ops.skinny_gemm(a.h1_aug[:, :H], W["A_stack"], a.h1_aug[:, H:], K=H, R=Ra,   # u = dropout(h1) A^T [M,2r]
+                                dropx=self._drop(ctx.training, ctx.call, li))
             a.qkv = ops.gemm(a.h1_aug, W["Wqkv_aug"])                            # [M, Nq+2Nkv]
             ops.rope_(a.qkv, 0, self.nh + self.nkv, self.hd, cos_t, sin_t, L)    # q heads then k heads are adjacent
             a.att, a.lse = ops.attention_fwd(a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + self.Nkv],
@@ -201,12 +215,17 @@ class LlamaDecoder(torch.nn.Module):
                 c0, w = self._target_cols(n)
                 ops.skinny_gemm(dqkv[:, c0:c0 + w], W["Bblk"][j * r:(j + 1) * r, c0:c0 + w], dqkv[:, self.Nqkv + j * r:], K=w, R=r)
             # dA_q, dA_v in one pass over h1 (the 16-row MMA tile is exactly the two rank-8 adapters)
+            xdrop = self._drop(ctx.training, ctx.call, l)
             ops.lora_wgrad_(a.h1_aug[:, :H], dqkv[:, self.Nqkv:], self.lora.gA[names[0]], H, 1, H, 2 * r, 1.0,
-                            out1=self.lora.gA[names[1]])
+                            out1=self.lora.gA[names[1]], dropx=xdrop)
             for j, n in enumerate(self.LORA_TARGETS):
                 c0, w = self._target_cols(n)
                 ops.lora_wgrad_(dqkv[:, c0:c0 + w], a.h1_aug[:, H + j * r:], self.lora.gB[names[j]], 1, r, w, r, self.lora.scale)
             if l == 0:
                 break                                                              # embeddings frozen
-            dh1 = ops.gemm(dqkv, W["WqkvT_aug"])                                   # [M,H]
+            if xdrop is None:
+                dh1 = ops.gemm(dqkv, W["WqkvT_aug"])                               # [M,H], LoRA's A-path folded into K
+            else:
+                dh1 = ops.gemm(dqkv[:, :self.Nqkv], W["WqkvT_aug"][:, :self.Nqkv])
+                ops.lora_dx_(dh1, dqkv[:, self.Nqkv:], W["A_stack"], K=H, R=Ra, drop=xdrop)
             dx32, dx16 = ops.rmsnorm_bwd(a.x_in, W["g1"], a.rstd1, dh1, dres_in=dmid32)

@@ -34,6 +34,21 @@ def _chk(t: torch.Tensor, dtype, name: str, inner_contig: bool = True) -> None:
         raise _lib.DalmB200Error(f"{name}: innermost dimension must be contiguous")
 
 
+class Drop:
+    """dropout site descriptor: probability, seed, stream id (identifies layer / tensor / call) and an optional device
+    uint64 counter added to the stream id (see include/dalm_b200.h)"""
+    __slots__ = ("p", "seed", "stream", "offset")
+
+    def __init__(self, p: float, seed: int, stream: int, offset: Optional[torch.Tensor] = None):
+        self.p, self.seed, self.stream, self.offset = float(p), int(seed) & (2**64 - 1), int(stream) & (2**64 - 1), offset
+
+
+def _d(drop: Optional["Drop"]):
+    if drop is None or drop.p <= 0.0:
+        return (0.0, 0, 0, None)
+    return (drop.p, drop.seed, drop.stream, _p(drop.offset))
+
+
 def _ld(t: torch.Tensor) -> int:
     """row stride (elements) of a 2-D row-major view"""
     return t.stride(0) if t.dim() == 2 else t.stride(-2)
@@ -122,7 +137,7 @@ def small_matmul(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_
 # ----------------------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, out_dtype=bf16, alpha: float = 1.0,
          bias: Optional[torch.Tensor] = None, act: int = 0, resid: Optional[torch.Tensor] = None, block_n: int = 0,
-         max_ctas: int = 0, K: Optional[int] = None, N: Optional[int] = None) -> torch.Tensor:
+         max_ctas: int = 0, K: Optional[int] = None, N: Optional[int] = None, drop: Optional[Drop] = None) -> torch.Tensor:
     """out[M,N] = act(alpha * a[M,K] @ b[N,K]^T + bias) + resid.   a, b: bf16 2-D views with contiguous rows."""
     _chk(a, bf16, "gemm a"); _chk(b, bf16, "gemm b")
     M = a.shape[0]
@@ -144,7 +159,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
         timer.begin(2.0 * M * N * K)
     _lib.call("dalm_b200_gemm_bf16_tn", _p(a), _ld(a), _p(b), _ld(b), _p(out), _ld(out), 1 if out.dtype == f32 else 0,
               M, N, K, float(alpha), _p(bias), int(act), _p(resid), _ld(resid) if resid is not None else 0, rf32,
-              int(block_n), int(max_ctas), _stream())
+              int(block_n), int(max_ctas), *_d(drop), _stream())
     if timer is not None:
         timer.end()
     return out
@@ -185,21 +200,23 @@ GEMM_TIMER = None
 # attention
 # ----------------------------------------------------------------------------------------------------------------
 def attention_fwd(q, k, v, mask, B: int, L: int, Hq: int, Hkv: int, D: int, causal: bool, out=None,
-                  scale: Optional[float] = None):
+                  scale: Optional[float] = None, drop: Optional[Drop] = None):
     """q/k/v: bf16 token-major 2-D views [B*L, H*D] (may be column slices of one qkv buffer). -> (out, lse)"""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _chk(t, bf16, n)
     if out is None:
         out = torch.empty(B * L, Hq * D, dtype=bf16, device=q.device)
     lse = torch.empty(B, Hq, L, dtype=f32, device=q.device)
+    if mask is not None and mask.dtype != i64:
+        raise _lib.DalmB200Error("attention: mask must be int64")
     scale = 1.0 / math.sqrt(D) if scale is None else scale
     _lib.call("dalm_b200_attention_fwd", _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(mask), _p(out), _ld(out),
-              _p(lse), B, L, Hq, Hkv, D, float(scale), 1 if causal else 0, _stream())
+              _p(lse), B, L, Hq, Hkv, D, float(scale), 1 if causal else 0, *_d(drop), _stream())
     return out, lse
 
 
 def attention_bwd(q, k, v, mask, out, lse, d_out, B: int, L: int, Hq: int, Hkv: int, D: int, causal: bool,
-                  dq=None, dk=None, dv=None, scale: Optional[float] = None):
+                  dq=None, dk=None, dv=None, scale: Optional[float] = None, drop: Optional[Drop] = None):
     dev = q.device
     if dq is None: dq = torch.empty(B * L, Hq * D, dtype=bf16, device=dev)
     if dk is None: dk = torch.empty(B * L, Hkv * D, dtype=bf16, device=dev)
@@ -208,14 +225,14 @@ def attention_bwd(q, k, v, mask, out, lse, d_out, B: int, L: int, Hq: int, Hkv: 
     scale = 1.0 / math.sqrt(D) if scale is None else scale
     _lib.call("dalm_b200_attention_bwd", _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(mask), _p(out), _ld(out),
               _p(lse), _p(d_out), _ld(d_out), _p(delta), _p(dq), _ld(dq), _p(dk), _ld(dk), _p(dv), _ld(dv),
-              B, L, Hq, Hkv, D, float(scale), 1 if causal else 0, _stream())
+              B, L, Hq, Hkv, D, float(scale), 1 if causal else 0, *_d(drop), _stream())
     return dq, dk, dv
 
 
 # ----------------------------------------------------------------------------------------------------------------
 # row-wise
 # ----------------------------------------------------------------------------------------------------------------
-def layernorm_fwd(z, gamma, beta, eps: float, y16=None, want_f32: bool = True):
+def layernorm_fwd(z, gamma, beta, eps: float, y16=None, want_f32: bool = True, drop: Optional[Drop] = None):
     _chk(z, f32, "z")
     M, H = z.shape
     y32 = torch.empty_like(z) if want_f32 else None
@@ -223,18 +240,19 @@ def layernorm_fwd(z, gamma, beta, eps: float, y16=None, want_f32: bool = True):
         y16 = torch.empty(M, H, dtype=bf16, device=z.device)
     mean = torch.empty(M, dtype=f32, device=z.device); rstd = torch.empty_like(mean)
     _lib.call("dalm_b200_layernorm_fwd", _p(z), _p(gamma), _p(beta), _p(y32), _p(y16), _ld(y16), _p(mean), _p(rstd), M, H,
-              float(eps), _stream())
+              float(eps), *_d(drop), _stream())
     return y32, y16, mean, rstd
 
 
-def layernorm_bwd(z, gamma, mean, rstd, dy_f32=None, dy_bf16=None, want_f32: bool = True, dz16=None, want_bf16: bool = True):
+def layernorm_bwd(z, gamma, mean, rstd, dy_f32=None, dy_bf16=None, want_f32: bool = True, dz16=None, want_bf16: bool = True,
+                  drop16: Optional[Drop] = None):
     M, H = z.shape
     dz32 = torch.empty_like(z) if want_f32 else None
     if want_bf16 and dz16 is None:
         dz16 = torch.empty(M, H, dtype=bf16, device=z.device)
     _lib.call("dalm_b200_layernorm_bwd", _p(z), _p(gamma), _p(mean), _p(rstd), _p(dy_f32), _p(dy_bf16),
               _ld(dy_bf16) if dy_bf16 is not None else 0, _p(dz32), _p(dz16), _ld(dz16) if dz16 is not None else 0, M, H,
-              _stream())
+              *_d(drop16), _stream())
     return dz32, dz16
 
 
@@ -259,10 +277,10 @@ def rmsnorm_bwd(x, g, rstd, dh, dres_in=None, dres_out=None, dres16=None, want_b
     return dres_out, dres16
 
 
-def bert_embed(ids, word, pos, type_emb):
+def bert_embed(ids, word, pos, type_emb, out=None):
     B, L = ids.shape
     V, H = word.shape
-    z = torch.empty(B * L, H, dtype=f32, device=ids.device)
+    z = torch.empty(B * L, H, dtype=f32, device=ids.device) if out is None else out
     _lib.call("dalm_b200_bert_embed", _p(ids.contiguous()), _p(word), _p(pos), _p(type_emb), _p(z), B * L, L, H, V, _stream())
     return z
 
@@ -327,16 +345,36 @@ def pool_norm_bwd(emb, norm, d_emb, mask, L: int, normalize: bool = True):
     return d_hidden
 
 
-def lora_wgrad_(x, g, out, so_r: int, so_k: int, K: int, R: int, scale: float = 1.0, out1=None):
+def lora_wgrad_(x, g, out, so_r: int, so_k: int, K: int, R: int, scale: float = 1.0, out1=None, dropx: Optional[Drop] = None):
     """out[r*so_r + k*so_k] += scale * sum_m g[m,r] x[m,k]; with R == 16 rows 8..15 accumulate into out1 (same strides)"""
     M = x.shape[0]
-    _lib.call("dalm_b200_lora_wgrad", _p(x), _ld(x), _p(g), _ld(g), _p(out), _p(out1), so_r, so_k, M, K, R, float(scale), _stream())
+    _lib.call("dalm_b200_lora_wgrad", _p(x), _ld(x), _p(g), _ld(g), _p(out), _p(out1), so_r, so_k, M, K, R, float(scale),
+              *_d(dropx), _stream())
     return out
 
 
-def skinny_gemm(x, w, out, K: int, R: int):
+def skinny_gemm(x, w, out, K: int, R: int, dropx: Optional[Drop] = None):
     """out[M,R] (bf16 view) = x[M,K] @ w[R,K]^T   (R in {8,16})"""
-    _lib.call("dalm_b200_skinny_gemm", _p(x), _ld(x), _p(w), _ld(w), _p(out), _ld(out), x.shape[0], K, R, _stream())
+    _lib.call("dalm_b200_skinny_gemm", _p(x), _ld(x), _p(w), _ld(w), _p(out), _ld(out), x.shape[0], K, R, *_d(dropx), _stream())
+    return out
+
+
+def lora_dx_(dh, g, a_stack, K: int, R: int, drop: Drop):
+    """dh[m,k] += mask(m,k)/(1-p) * sum_r g[m,r] a_stack[r,k]"""
+    p, seed, stream, off = _d(drop)
+    _lib.call("dalm_b200_lora_dx", _p(dh), _ld(dh), _p(g), _ld(g), _p(a_stack), _ld(a_stack), dh.shape[0], K, R, p, seed, stream, off, _stream())
+    return dh
+
+
+def bump_counter_(counter: torch.Tensor) -> None:
+    _lib.call("dalm_b200_bump_counter", _p(counter), _stream())
+
+
+def dropout_scale(n: int, drop: Drop, device) -> torch.Tensor:
+    """the scale (0 or 1/(1-p)) dropout applies to each of n elements under `drop` — lets tests apply identical masks"""
+    out = torch.empty(n, dtype=f32, device=device)
+    p, seed, stream, off = _d(drop) if drop.p > 0 else (0.0, 0, 0, None)
+    _lib.call("dalm_b200_dropout_scale", _p(out), n, p, seed, stream, off, _stream())
     return out
 
 

@@ -144,9 +144,11 @@ def fused_rag_step(rag_model, batch: Dict[str, torch.Tensor], logit_scale: float
     g_ids, g_mask, qlen = g("generator_input_input_ids"), g("generator_input_attention_mask"), g("query_passage_input_len")
     train_enc = backward and enc.lora is not None
     train_dec = backward and dec.lora is not None
-    hq, cq = enc.forward_hidden(q_ids, q_mask, save=train_enc)
+    if enc.training or dec.training:                         # fresh dropout masks per step (also inside a graph replay)
+        ops.bump_counter_(enc.drop_offset)
+        ops.bump_counter_(dec.drop_offset)
+    (hq, hp), cqp = enc.forward_segments([(q_ids, q_mask), (p_ids, p_mask)], save=train_enc)   # one pass over the weights
     q_emb, q_norm = ops.pool_norm_fwd(hq, q_mask, rag_model.normalize)
-    hp, cp = enc.forward_hidden(p_ids, p_mask, save=train_enc)
     p_emb, p_norm = ops.pool_norm_fwd(hp, p_mask, rag_model.normalize)
     cvec, nsum = ops.marginal_counts(g_mask, qlen)
     r = ops.inbatch_loss(q_emb, p_emb, float(logit_scale), cvec, nsum, need_grad=train_enc, grad_out=grad_scale)
@@ -157,8 +159,8 @@ def fused_rag_step(rag_model, batch: Dict[str, torch.Tensor], logit_scale: float
         dec.backward_logits(cg, dl)
     if train_enc:
         L_p, L_q = p_ids.shape[1], q_ids.shape[1]
-        enc.backward_hidden(cp, ops.pool_norm_bwd(p_emb, p_norm, r["dP"], p_mask, L_p, rag_model.normalize))
-        enc.backward_hidden(cq, ops.pool_norm_bwd(q_emb, q_norm, r["dQ"], q_mask, L_q, rag_model.normalize))
+        enc.backward_segments(cqp, [ops.pool_norm_bwd(q_emb, q_norm, r["dQ"], q_mask, L_q, rag_model.normalize),
+                                    ops.pool_norm_bwd(p_emb, p_norm, r["dP"], p_mask, L_p, rag_model.normalize)])
     return {"loss": out[2], "losses": out, "S": r["S"]}
 
 
@@ -170,14 +172,15 @@ def fused_retriever_step(model, batch: Dict[str, torch.Tensor], logit_scale: flo
     g = lambda k: batch[k].to(dev, i64, non_blocking=True).contiguous()
     q_ids, q_mask, p_ids, p_mask = g("query_input_ids"), g("query_attention_mask"), g("passage_input_ids"), g("passage_attention_mask")
     train = backward and enc.lora is not None
-    hq, cq = enc.forward_hidden(q_ids, q_mask, save=train)
+    if enc.training:
+        ops.bump_counter_(enc.drop_offset)
+    (hq, hp), cqp = enc.forward_segments([(q_ids, q_mask), (p_ids, p_mask)], save=train)
     q_emb, q_norm = ops.pool_norm_fwd(hq, q_mask, model.normalize)
-    hp, cp = enc.forward_hidden(p_ids, p_mask, save=train)
     p_emb, p_norm = ops.pool_norm_fwd(hp, p_mask, model.normalize)
     r = ops.inbatch_loss(q_emb, p_emb, float(logit_scale), None, None, need_grad=train, grad_out=grad_scale)
     if train:
-        enc.backward_hidden(cp, ops.pool_norm_bwd(p_emb, p_norm, r["dP"], p_mask, p_ids.shape[1], model.normalize))
-        enc.backward_hidden(cq, ops.pool_norm_bwd(q_emb, q_norm, r["dQ"], q_mask, q_ids.shape[1], model.normalize))
+        enc.backward_segments(cqp, [ops.pool_norm_bwd(q_emb, q_norm, r["dQ"], q_mask, q_ids.shape[1], model.normalize),
+                                    ops.pool_norm_bwd(p_emb, p_norm, r["dP"], p_mask, p_ids.shape[1], model.normalize)])
     return {"loss": r["losses"][0], "losses": r["losses"], "S": r["S"]}
 
 

@@ -48,29 +48,48 @@ int dalm_b200_finalize_loss(const float* tok_lp, const int64_t* mask, int B, int
 int dalm_b200_small_matmul_f32(const float* A, const float* B, float* C, int M, int N, int K, int transA, int transB,
                                float alpha, void* stream);
 
+/* ---- dropout (reference trains under model.train(): BERT hidden / attention-probability dropout 0.1, peft LoRA input
+ * dropout 0.05). Counter-based Philox4x32-10 keyed by (seed, stream id, element index); masks are never stored, backward
+ * kernels regenerate them. Entry points that can apply dropout take (drop_p, drop_seed, drop_stream_id, drop_offset):
+ * drop_p = 0 disables it; drop_offset is an optional DEVICE uint64 added to the stream id (bumped once per step by
+ * dalm_b200_bump_counter so that a CUDA-graph replay draws fresh masks). ---- */
+int dalm_b200_bump_counter(void* counter, void* stream);
+int dalm_b200_dropout_scale(float* out, long long n, float p, unsigned long long seed, unsigned long long stream_id,
+                            const void* offset, void* stream);
+/* dh[m,k] += mask(m,k)/(1-p) * sum_r G[m,r] A[r,k]: backward of the LoRA input dropout (the p = 0 case is folded into the
+ * dgrad GEMM instead) */
+int dalm_b200_lora_dx(void* dh, long long lddh, const void* G, long long ldg, const void* A, long long lda, int M, int K,
+                      int R, float p, unsigned long long seed, unsigned long long stream_id, const void* offset,
+                      void* stream);
+
 /* ---- dense contractions (tcgen05 / TMEM / TMA) ----
  * out[M,N] = act(alpha * A[M,K] B[N,K]^T + bias) + resid. Replaces every nn.Linear forward / dgrad reached through
  * dalm/models/rag_e2e_base_model.py:93,105 and dalm/models/retriever_only_base_model.py:58 (HF modeling code -> cuBLAS). */
 int dalm_b200_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo,
                            int out_f32, int M, int N, int K, float alpha, const float* bias, int act, const void* resid,
-                           long long ldr, int resid_f32, int block_n, int max_ctas, void* stream);
+                           long long ldr, int resid_f32, int block_n, int max_ctas, float drop_p, unsigned long long drop_seed,
+    unsigned long long drop_stream_id, const void* drop_offset, void* stream);
 void dalm_b200_gemm_clear_cache(void);
 
 /* ---- attention (same call sites; HF eager/SDPA attention) ---- */
 int dalm_b200_attention_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                             const int64_t* mask, void* out, long long ldo, float* lse, int B, int L, int Hq, int Hkv,
-                            int D, float scale, int causal, void* stream);
+                            int D, float scale, int causal, float drop_p, unsigned long long drop_seed,
+    unsigned long long drop_stream_id, const void* drop_offset, void* stream);
 int dalm_b200_attention_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                             const int64_t* mask, const void* out, long long ldo, const float* lse, const void* d_out,
                             long long lddo, float* delta, void* dq, long long lddq, void* dk, long long lddk, void* dv,
-                            long long lddv, int B, int L, int Hq, int Hkv, int D, float scale, int causal, void* stream);
+                            long long lddv, int B, int L, int Hq, int Hkv, int D, float scale, int causal, float drop_p, unsigned long long drop_seed,
+    unsigned long long drop_stream_id, const void* drop_offset, void* stream);
 
 /* ---- row-wise pieces of the encoder / decoder blocks ---- */
 int dalm_b200_layernorm_fwd(const float* z, const float* gamma, const float* beta, float* y32, void* y16, long long ld16,
-                            float* mean, float* rstd, int M, int H, float eps, void* stream);
+                            float* mean, float* rstd, int M, int H, float eps, float drop_p, unsigned long long drop_seed,
+    unsigned long long drop_stream_id, const void* drop_offset, void* stream);
 int dalm_b200_layernorm_bwd(const float* z, const float* gamma, const float* mean, const float* rstd, const float* dy_f32,
                             const void* dy_bf16, long long ldb, float* dz32, void* dz16, long long ld16, int M, int H,
-                            void* stream);
+                            float drop_p, unsigned long long drop_seed,
+    unsigned long long drop_stream_id, const void* drop_offset, void* stream);
 int dalm_b200_rmsnorm_fwd(const float* x, const float* g, void* h, long long ldh, float* rstd, int M, int H, float eps,
                           void* stream);
 int dalm_b200_rmsnorm_bwd(const float* x, const float* g, const float* rstd, const void* dh, long long lddh,
@@ -93,10 +112,12 @@ int dalm_b200_pool_norm_bwd(const float* emb, const float* norm, const float* d_
 /* ---- LoRA (peft.LoraConfig r=8 alpha=16: rag_e2e_base_model.py:144-160) and optimizer (train_rage2e.py:336) ---- */
 /* out0[r*so_r + k*so_k] += scale * sum_m G[m,r] X[m,k]  (r < 8; rows 8..15 of an R=16 call go to out1): dA = g^T x, dB^T = u^T dY */
 int dalm_b200_lora_wgrad(const void* X, long long ldx, const void* G, long long ldg, float* out0, float* out1,
-                         long long so_r, long long so_k, int M, int K, int R, float scale, void* stream);
+                         long long so_r, long long so_k, int M, int K, int R, float scale, float drop_p, unsigned long long drop_seed,
+    unsigned long long drop_stream_id, const void* drop_offset, void* stream);
 /* out[M,R] (bf16) = X[M,K] . W[R,K]^T, R in {8,16}: LoRA down-projection u = x A^T and mid-gradient g = dY (sB) */
 int dalm_b200_skinny_gemm(const void* X, long long ldx, const void* W, long long ldw, void* out, long long ldo, int M,
-                          int K, int R, void* stream);
+                          int K, int R, float drop_p, unsigned long long drop_seed,
+    unsigned long long drop_stream_id, const void* drop_offset, void* stream);
 int dalm_b200_pack_scaled_bf16(const float* in, long long si_r, long long si_c, void* out, long long ldo, int rows,
                                int cols, float scale, void* stream);
 /* one launch for a whole table of pack jobs (device array of 56-byte records, see csrc/rowwise.cu PackEntry) */
