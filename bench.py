@@ -207,6 +207,7 @@ def main():
     # PEFT initialises B = 0; after a few optimizer steps it is not. Same seed on every rank (DDP broadcast semantics).
     opt = FusedAdam(model.parameters(), lr=1e-4)
     banks = model.trainable_banks()
+    model.train()                          # reference train_rage2e.py:421: dropout sites are live during the timed steps
 
     n_batches = args.warmup + args.steps
     host_batches = make_batches(n_batches, rank, world, cache_dir)
@@ -316,7 +317,7 @@ def main():
                    "global_batch": BS * world, "parallelism": f"dp{world}", "rows_used": n_batches * BS * world,
                    "dataset": "first rows of the synthetic 200k-row (Abstract,Question,Answer) 'full' set (all sequences truncated)",
                    "l2": "per-step working set (27 GB weights + 22 GB activations) >> 126 MB L2; no explicit flush",
-                   "weights": "seeded random-init (no checkpoints offline)", "dropout": "0 (parity mode)",
+                   "weights": "seeded random-init (no checkpoints offline)", "dropout": "train() mode as in the reference loop: BERT hidden 0.1 + attention-prob 0.1, LoRA input 0.05 (Philox, masks regenerated in backward)",
                    "launch": "one CUDA graph replay per step (fwd+bwd) + Adam/repack launches" if graphed is not None else "eager launches",
                    "eager_ms_per_step": eager_ms / args.steps,
                    "loss_last": float(loss.item())},

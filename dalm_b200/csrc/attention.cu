@@ -30,7 +30,8 @@ struct AttnParams {
   float scale;                      // 1/sqrt(D)
   int causal;
   DropCfg drop;                     // attention-probability dropout (BERT attention_probs_dropout_prob); p = 0 => off.
-                                    // element index of P[b,h,i,j] = ((b*Hq + h)*L + i)*L + j
+                                    // element index of P[b,h,i,j] = ((b*Hq + h)*L + i)*Lp + j, Lp = L rounded up to 8
+                                    // (rows start on a Philox group of 8, so one call covers an 8-key MMA n-tile)
 };
 
 // ---------------------------------------------------------------- fragment helpers
@@ -190,16 +191,22 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnParams p) {
       o_acc[i][2] *= corr[1]; o_acc[i][3] *= corr[1];
     }
     if (DROP) {
-      // dropout acts on the normalised probabilities; the row sum above used the un-dropped values
+      // dropout acts on the normalised probabilities; the row sum above used the un-dropped values.
+      // one Philox call per (row, 8-key n-tile); this thread uses components t*2, t*2+1
       const unsigned long long dstream = drop_stream(p.drop);
       const unsigned long long rbase = ((unsigned long long)b * p.Hq + h) * L;
+      const int lp8 = (L + 7) >> 3;
 #pragma unroll
       for (int nt = 0; nt < BKV / 8; ++nt) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int key = kv0 + nt * 8 + t * 2 + (e & 1);
-          const int qr = (e < 2) ? row_a : row_b;
-          if (qr < L && key < L) s[nt][e] *= drop_scale1(p.drop, dstream, (rbase + qr) * L + key);
+        for (int r = 0; r < 2; ++r) {
+          const int qr = r == 0 ? row_a : row_b;
+          float sc[8];
+          drop_scale8(p.drop, dstream, (rbase + qr) * lp8 + ((kv0 >> 3) + nt), sc);
+          float s0 = sc[0], s1 = sc[1];
+#pragma unroll
+          for (int j = 1; j < 4; ++j) if (t == j) { s0 = sc[2 * j]; s1 = sc[2 * j + 1]; }
+          s[nt][2 * r] *= s0; s[nt][2 * r + 1] *= s1;
         }
       }
     }
@@ -356,13 +363,20 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(AttnParams p) {
       if (DROP) {
         const unsigned long long dstream = drop_stream(p.drop);
         const unsigned long long rbase = ((unsigned long long)b * p.Hq + hq) * L;
+        const int lp8 = (L + 7) >> 3;
+        const int kg = (kv0 >> 3) + warp * 2;                    // Philox group of key_a (key_b is the next group), component g
 #pragma unroll
         for (int nt = 0; nt < BQ / 8; ++nt) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int qi = q0 + nt * 8 + t * 2 + (e & 1);
-            const int key = (e < 2) ? key_a : key_b;
-            ms[nt][e] = (qi < L && key < L) ? drop_scale1(p.drop, dstream, (rbase + qi) * L + key) : 0.f;
+          for (int c = 0; c < 2; ++c) {
+            const int qi = q0 + nt * 8 + t * 2 + c;
+            float sa[8], sb[8];
+            drop_scale8(p.drop, dstream, (rbase + qi) * lp8 + kg, sa);
+            drop_scale8(p.drop, dstream, (rbase + qi) * lp8 + kg + 1, sb);
+            float va = sa[0], vb = sb[0];
+#pragma unroll
+            for (int j = 1; j < 8; ++j) if (g == j) { va = sa[j]; vb = sb[j]; }
+            ms[nt][c] = va; ms[nt][2 + c] = vb;                  // e = c: key_a ; e = 2 + c: key_b
           }
         }
       }
@@ -529,6 +543,25 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(AttnParams p) {
         mma16816(dp[2 * nt + 1], ad, bf[2], bf[3]);
       }
     }
+    float msq[DROP ? BKV / 8 : 1][4];
+    if (DROP) {
+      const unsigned long long dstream = drop_stream(p.drop);
+      const unsigned long long rbase = ((unsigned long long)b * p.Hq + h) * L;
+      const int lp8 = (L + 7) >> 3;
+#pragma unroll
+      for (int nt = 0; nt < BKV / 8; ++nt) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int qr = r == 0 ? row_a : row_b;
+          float sc[8];
+          drop_scale8(p.drop, dstream, (rbase + qr) * lp8 + ((kv0 >> 3) + nt), sc);
+          float s0 = sc[0], s1 = sc[1];
+#pragma unroll
+          for (int j = 1; j < 4; ++j) if (t == j) { s0 = sc[2 * j]; s1 = sc[2 * j + 1]; }
+          msq[nt][2 * r] = s0; msq[nt][2 * r + 1] = s1;
+        }
+      }
+    }
     // dS = P * (dP - delta) * scale
 #pragma unroll
     for (int nt = 0; nt < BKV / 8; ++nt) {
@@ -540,11 +573,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(AttnParams p) {
         if (p.causal && (kv0 + kc) > qr) val = -INFINITY;
         const float pv = exp2f(val - lse2[e >> 1]);
         float dpv = dp[nt][e];
-        if (DROP) {
-          const unsigned long long rbase = ((unsigned long long)b * p.Hq + h) * L;
-          const int key = kv0 + kc;
-          dpv *= (qr < L && key < L) ? drop_scale1(p.drop, drop_stream(p.drop), (rbase + qr) * L + key) : 0.f;
-        }
+        if (DROP) dpv *= msq[nt][e];
         s[nt][e] = pv * (dpv - dl[e >> 1]) * p.scale;
       }
     }

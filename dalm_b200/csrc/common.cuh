@@ -111,23 +111,25 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 // null) is added to it so that a CUDA-graph replay of the step draws fresh masks (the graph bumps the counter).
 // ---------------------------------------------------------------------------------------------
 struct DropCfg {
-  float p;                              // drop probability; 0 => disabled
-  float inv_keep;                       // 1 / (1 - p)
-  unsigned int thresh;                  // keep iff rand32 >= thresh  (thresh = p * 2^32)
+  float p;                              // requested drop probability; 0 => disabled
+  float inv_keep;                       // 1 / (1 - p_eff), p_eff = thresh / 65536 (the probability actually realised)
+  unsigned int thresh;                  // keep iff rand16 >= thresh
   unsigned long long seed, stream;
   const unsigned long long* offset;     // device counter or nullptr
 };
 inline DropCfg make_drop(float p, unsigned long long seed, unsigned long long stream, const void* offset) {
   DropCfg d;
-  d.p = p; d.inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
-  double t = (double)p * 4294967296.0;
-  d.thresh = p > 0.f ? (t >= 4294967295.0 ? 4294967295u : (unsigned int)t) : 0u;
+  d.p = p;
+  double t = (double)p * 65536.0 + 0.5;
+  d.thresh = p > 0.f ? (t >= 65535.0 ? 65535u : (unsigned int)t) : 0u;
+  d.inv_keep = p > 0.f ? (float)(1.0 / (1.0 - (double)d.thresh / 65536.0)) : 1.f;
   d.seed = seed; d.stream = stream; d.offset = (const unsigned long long*)offset;
   return d;
 }
-__device__ __forceinline__ uint4 philox4x32_10(uint2 key, uint4 c) {
+// Philox4x32 with 7 rounds (the Random123 "crush-resistant" minimum; 10 is the library default's safety margin)
+__device__ __forceinline__ uint4 philox4x32_7(uint2 key, uint4 c) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < 7; ++r) {
     const unsigned int hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
     const unsigned int hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
     c = make_uint4(hi1 ^ c.y ^ key.x, lo1, hi0 ^ c.w ^ key.y, lo0);
@@ -138,16 +140,27 @@ __device__ __forceinline__ uint4 philox4x32_10(uint2 key, uint4 c) {
 __device__ __forceinline__ unsigned long long drop_stream(const DropCfg& d) {
   return d.stream + (d.offset ? (*d.offset) * 0x9E3779B97F4A7C15ull : 0ull);
 }
-// four 32-bit randoms for elements [4*idx4, 4*idx4 + 4) of the tensor the mask applies to
-__device__ __forceinline__ uint4 drop_rand4(const DropCfg& d, unsigned long long stream, unsigned long long idx4) {
-  return philox4x32_10(make_uint2((unsigned int)d.seed, (unsigned int)(d.seed >> 32)),
-                       make_uint4((unsigned int)idx4, (unsigned int)(idx4 >> 32), (unsigned int)stream, (unsigned int)(stream >> 32)));
+// One Philox call serves EIGHT consecutive elements (16 random bits each): scale[j] = 0 or 1/(1-p_eff) for elements
+// [8*idx8, 8*idx8 + 8) of the tensor the mask applies to.
+__device__ __forceinline__ void drop_scale8(const DropCfg& d, unsigned long long stream, unsigned long long idx8, float* scale) {
+  const uint4 r = philox4x32_7(make_uint2((unsigned int)d.seed, (unsigned int)(d.seed >> 32)),
+                               make_uint4((unsigned int)idx8, (unsigned int)(idx8 >> 32), (unsigned int)stream,
+                                          (unsigned int)(stream >> 32)));
+  const unsigned int w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    scale[2 * j]     = (w[j] & 0xFFFFu) >= d.thresh ? d.inv_keep : 0.f;
+    scale[2 * j + 1] = (w[j] >> 16)     >= d.thresh ? d.inv_keep : 0.f;
+  }
 }
-// scale factor (0 or 1/(1-p)) of element `idx` (scalar access: recomputes the group of 4)
+// scalar access (recomputes the group of 8): tests / cold paths
 __device__ __forceinline__ float drop_scale1(const DropCfg& d, unsigned long long stream, unsigned long long idx) {
-  const uint4 r = drop_rand4(d, stream, idx >> 2);
-  const unsigned int v = ((idx & 3) == 0) ? r.x : ((idx & 3) == 1) ? r.y : ((idx & 3) == 2) ? r.z : r.w;
-  return v >= d.thresh ? d.inv_keep : 0.f;
+  float sc[8];
+  drop_scale8(d, stream, idx >> 3, sc);
+  float v = sc[0];
+#pragma unroll
+  for (int j = 1; j < 8; ++j) if ((idx & 7) == (unsigned long long)j) v = sc[j];
+  return v;
 }
 
 }  // namespace dalm

@@ -53,14 +53,13 @@ __device__ __forceinline__ void epilogue_math(const GemmEpilogue& ep, const uint
   }
   if (ep.drop.p > 0.f) {
     const unsigned long long dstream = drop_stream(ep.drop);
-    const unsigned long long base = ((unsigned long long)row * (unsigned long long)N + (unsigned long long)col0) >> 2;
+    const unsigned long long base = ((unsigned long long)row * (unsigned long long)N + (unsigned long long)col0) >> 3;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const uint4 r = drop_rand4(ep.drop, dstream, base + g);
-      f[g * 4 + 0] *= (r.x >= ep.drop.thresh ? ep.drop.inv_keep : 0.f);
-      f[g * 4 + 1] *= (r.y >= ep.drop.thresh ? ep.drop.inv_keep : 0.f);
-      f[g * 4 + 2] *= (r.z >= ep.drop.thresh ? ep.drop.inv_keep : 0.f);
-      f[g * 4 + 3] *= (r.w >= ep.drop.thresh ? ep.drop.inv_keep : 0.f);
+    for (int g = 0; g < 4; ++g) {
+      float sc[8];
+      drop_scale8(ep.drop, dstream, base + g, sc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[g * 8 + j] *= sc[j];
     }
   }
   if (ep.resid && row_ok) {

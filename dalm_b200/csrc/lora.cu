@@ -44,13 +44,12 @@ __device__ __forceinline__ void drop_tile(__nv_bfloat16* tile, int lds, int rows
     const int m = m0 + r, k = k0 + p * 8;
     if (m < M && k < K) {
       const unsigned long long idx = (unsigned long long)m * K + k;          // multiple of 8 (K % 8 == 0)
-      const uint4 r0 = drop_rand4(d, dstream, idx >> 2), r1 = drop_rand4(d, dstream, (idx >> 2) + 1);
-      const unsigned int rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-      float f[8];
+      float sc[8], f[8];
+      drop_scale8(d, dstream, idx >> 3, sc);
       bf16x8* ptr = reinterpret_cast<bf16x8*>(tile + r * lds + p * 8);
       unpack8(*ptr, f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] *= (rr[j] >= d.thresh ? d.inv_keep : 0.f);
+      for (int j = 0; j < 8; ++j) f[j] *= sc[j];
       *ptr = pack8(f);
     }
   }

@@ -29,10 +29,35 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   const float var = block_sum(q, red) / H;
   const float rstd = rsqrtf(var + eps);
   if (threadIdx.x == 0) { mean_out[r] = mean; rstd_out[r] = rstd; }
+  if (drop.p > 0.f && (H & 7) == 0) {                          // embeddings dropout: one Philox call per 8 outputs
+    const unsigned long long dstream = drop_stream(drop);
+    for (int i8 = threadIdx.x; i8 < H / 8; i8 += blockDim.x) {
+      float sc[8];
+      drop_scale8(drop, dstream, ((unsigned long long)r * H >> 3) + i8, sc);
+      const int i0 = i8 * 8;
+      float v[8];
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + i0), g1 = *reinterpret_cast<const float4*>(gamma + i0 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + i0), b1 = *reinterpret_cast<const float4*>(beta + i0 + 4);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ((row[i0 + j] - mean) * rstd * gg[j] + bb[j]) * sc[j];
+      if (y32) {
+        *reinterpret_cast<float4*>(y32 + r * H + i0) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(y32 + r * H + i0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+      if ((ld16 & 7) == 0) *reinterpret_cast<bf16x8*>(y16 + r * ld16 + i0) = pack8(v);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y16[r * ld16 + i0 + j] = __float2bfloat16_rn(v[j]);
+      }
+    }
+    return;
+  }
   const unsigned long long dstream = drop.p > 0.f ? drop_stream(drop) : 0ull;
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
     float v = (row[i] - mean) * rstd * gamma[i] + beta[i];
-    if (drop.p > 0.f) v *= drop_scale1(drop, dstream, (unsigned long long)r * H + i);     // embeddings dropout
+    if (drop.p > 0.f) v *= drop_scale1(drop, dstream, (unsigned long long)r * H + i);
     if (y32) y32[r * H + i] = v;
     y16[r * ld16 + i] = __float2bfloat16_rn(v);
   }
@@ -65,6 +90,29 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   s1 = block_sum(s1, red) / H;
   s2 = block_sum(s2, red) / H;
   // z = dropout(dense_out) + residual: the residual branch takes dz as is (dz32), the dense branch takes mask*dz/(1-p)
+  if (drop16.p > 0.f && (H & 7) == 0) {
+    const unsigned long long dstream = drop_stream(drop16);
+    for (int i8 = threadIdx.x; i8 < H / 8; i8 += blockDim.x) {
+      float sc[8];
+      drop_scale8(drop16, dstream, ((unsigned long long)r * H >> 3) + i8, sc);
+      const int i0 = i8 * 8;
+      float d[8], dm[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { d[j] = rstd * (gbuf[i0 + j] - s1 - zh[i0 + j] * s2); dm[j] = d[j] * sc[j]; }
+      if (dz32) {
+        *reinterpret_cast<float4*>(dz32 + r * H + i0) = make_float4(d[0], d[1], d[2], d[3]);
+        *reinterpret_cast<float4*>(dz32 + r * H + i0 + 4) = make_float4(d[4], d[5], d[6], d[7]);
+      }
+      if (dz16) {
+        if ((ld16 & 7) == 0) *reinterpret_cast<bf16x8*>(dz16 + r * ld16 + i0) = pack8(dm);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dz16[r * ld16 + i0 + j] = __float2bfloat16_rn(dm[j]);
+        }
+      }
+    }
+    return;
+  }
   const unsigned long long dstream = drop16.p > 0.f ? drop_stream(drop16) : 0ull;
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
     const float d = rstd * (gbuf[i] - s1 - zh[i] * s2);
@@ -353,43 +401,47 @@ __global__ void dropout_scale_kernel(float* __restrict__ out, long long n, DropC
 
 // LoRA input-dropout backward: dh[m,k] += mask(m,k)/(1-p) * sum_r G[m,r] * A[r,k]   (G bf16 [M,R], A bf16 [R,K] = A_stack)
 // The un-dropped case folds this term into the dgrad GEMM (K-augmentation); with dropout the mask makes it elementwise.
+// HBM-bound (dh read + written once). Each thread owns 8 fixed columns: its slice of A (R x 8) stays in registers
+// (packed bf16), the CTA's rows stream through with one 16-byte load/store of dh per row.
+template <int R>
 __global__ void __launch_bounds__(256) lora_dx_kernel(__nv_bfloat16* __restrict__ dh, long long lddh,
                                                       const __nv_bfloat16* __restrict__ G, long long ldg,
-                                                      const __nv_bfloat16* __restrict__ A, long long lda, int M, int K, int R,
+                                                      const __nv_bfloat16* __restrict__ A, long long lda, int M, int K,
                                                       DropCfg drop) {
-  __shared__ __nv_bfloat16 As[32][512 + 8];
-  __shared__ float Gs[32][32];
-  const int k0 = blockIdx.x * 512, m0 = blockIdx.y * 32;
-  for (int i = threadIdx.x; i < R * 512; i += 256) {
-    const int r = i / 512, c = i - r * 512;
-    As[r][c] = (k0 + c < K) ? A[(size_t)r * lda + k0 + c] : __float2bfloat16(0.f);
-  }
-  for (int i = threadIdx.x; i < 32 * R; i += 256) {
+  constexpr int ROWS = 32;
+  __shared__ __align__(16) float Gs[ROWS][R];
+  const int m0 = blockIdx.y * ROWS;
+  for (int i = threadIdx.x; i < ROWS * R; i += 256) {
     const int mm = i / R, r = i - mm * R;
     Gs[mm][r] = (m0 + mm < M) ? __bfloat162float(G[(size_t)(m0 + mm) * ldg + r]) : 0.f;
   }
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 8;
+  bf16x8 areg[R];
+  if (c < K) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) areg[r] = *reinterpret_cast<const bf16x8*>(A + (size_t)r * lda + c);
+  }
   __syncthreads();
+  if (c >= K) return;
   const unsigned long long dstream = drop_stream(drop);
-  const int cg = threadIdx.x & 63, rsub = threadIdx.x >> 6;               // 64 column groups of 8, 4 rows per pass
-  const int c = cg * 8;
-  if (k0 + c >= K) return;
-  for (int mm = rsub; mm < 32; mm += 4) {
+  const int nrows = min(ROWS, M - m0);
+  for (int mm = 0; mm < nrows; ++mm) {
     const int m = m0 + mm;
-    if (m >= M) break;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
     for (int r = 0; r < R; ++r) {
       const float gv = Gs[mm][r];
+      float av[8];
+      unpack8(areg[r], av);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(gv, __bfloat162float(As[r][c + j]), acc[j]);
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(gv, av[j], acc[j]);
     }
-    const unsigned long long idx = (unsigned long long)m * K + k0 + c;     // multiple of 8
-    const uint4 r0 = drop_rand4(drop, dstream, idx >> 2), r1 = drop_rand4(drop, dstream, (idx >> 2) + 1);
-    const unsigned int rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-    __nv_bfloat16* p = dh + (size_t)m * lddh + k0 + c;
-    float cur[8];
+    float sc[8], cur[8];
+    drop_scale8(drop, dstream, ((unsigned long long)m * K + c) >> 3, sc);
+    __nv_bfloat16* p = dh + (size_t)m * lddh + c;
     unpack8(*reinterpret_cast<const bf16x8*>(p), cur);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) cur[j] += (rr[j] >= drop.thresh ? drop.inv_keep : 0.f) * acc[j];
+    for (int j = 0; j < 8; ++j) cur[j] = fmaf(sc[j], acc[j], cur[j]);
     *reinterpret_cast<bf16x8*>(p) = pack8(cur);
   }
 }
@@ -568,11 +620,14 @@ extern "C" int dalm_b200_dropout_scale(float* out, long long n, float p, unsigne
 extern "C" int dalm_b200_lora_dx(void* dh, long long lddh, const void* G, long long ldg, const void* A, long long lda, int M,
                                  int K, int R, float p, unsigned long long seed, unsigned long long stream_id,
                                  const void* offset, void* stream) {
-  DALM_REQUIRE(R >= 1 && R <= 32 && (K % 8) == 0 && (lddh % 8) == 0, "lora_dx: bad shape R=%d K=%d", R, K);
+  DALM_REQUIRE((R == 8 || R == 16 || R == 24) && (K % 8) == 0 && (lddh % 8) == 0 && (lda % 8) == 0, "lora_dx: bad shape R=%d K=%d", R, K);
   DALM_REQUIRE(p >= 0.f && p < 1.f, "lora_dx: p must be in [0,1)");
-  dim3 grid((K + 511) / 512, (M + 31) / 32);
-  lora_dx_kernel<<<grid, 256, 0, ST(stream)>>>((__nv_bfloat16*)dh, lddh, (const __nv_bfloat16*)G, ldg, (const __nv_bfloat16*)A, lda,
-                                               M, K, R, make_drop(p, seed, stream_id, offset));
+  dim3 grid((K / 8 + 255) / 256, (M + 31) / 32);
+  const DropCfg dc = make_drop(p, seed, stream_id, offset);
+  auto* dhp = (__nv_bfloat16*)dh; auto* gp = (const __nv_bfloat16*)G; auto* ap = (const __nv_bfloat16*)A;
+  if (R == 8)       lora_dx_kernel<8><<<grid, 256, 0, ST(stream)>>>(dhp, lddh, gp, ldg, ap, lda, M, K, dc);
+  else if (R == 16) lora_dx_kernel<16><<<grid, 256, 0, ST(stream)>>>(dhp, lddh, gp, ldg, ap, lda, M, K, dc);
+  else              lora_dx_kernel<24><<<grid, 256, 0, ST(stream)>>>(dhp, lddh, gp, ldg, ap, lda, M, K, dc);
   count_launch();
   return check_launch("lora_dx_kernel");
 }

@@ -23,7 +23,7 @@ def test_generator_statistics_and_counters(cuda_dev):
     d = ops.Drop(0.1, 1234, 77, off)
     m1 = ops.dropout_scale(n, d, cuda_dev)
     vals = torch.unique(m1)
-    assert vals.numel() == 2 and vals[0].item() == 0.0 and abs(vals[1].item() - 1 / 0.9) < 1e-6
+    assert vals.numel() == 2 and vals[0].item() == 0.0 and abs(vals[1].item() - 1 / 0.9) < 1e-4   # p quantised to 1/65536
     keep = (m1 > 0).float().mean().item()
     assert abs(keep - 0.9) < 3e-3                                  # ~10 sigma of a Bernoulli(0.9) over 2^20 draws
     assert abs(m1.mean().item() - 1.0) < 5e-3                      # unbiased: E[scale] = 1
@@ -75,7 +75,8 @@ def test_attention_probability_dropout_exact(cuda_dev, B, L, H, D):
     mask = torch.ones(B, L, dtype=torch.int64, device=dev); mask[0, L - 4:] = 0
     d = ops.Drop(0.1, 5, 3 << 8 | 8, None)
     out, lse = ops.attention_fwd(q, k, v, mask, B, L, H, H, D, False, drop=d)
-    dm = ops.dropout_scale(B * H * L * L, d, dev).view(B, H, L, L).double()
+    Lp = (L + 7) // 8 * 8                                           # mask rows are pitched to a Philox group of 8
+    dm = ops.dropout_scale(B * H * L * Lp, d, dev).view(B, H, L, Lp)[..., :L].double()
     qd, kd, vd = (t.detach().double().requires_grad_(True) for t in (q, k, v))
     qh = qd.view(B, L, H, D).transpose(1, 2); kh = kd.view(B, L, H, D).transpose(1, 2); vh = vd.view(B, L, H, D).transpose(1, 2)
     s = (qh @ kh.transpose(-1, -2) / math.sqrt(D)).masked_fill(mask.view(B, 1, 1, L) == 0, float("-inf"))
@@ -131,12 +132,13 @@ def test_bert_encoder_train_mode_matches_hf_with_replayed_masks(cuda_dev, monkey
     hid, ctx = enc.forward_hidden(ids.to(cuda_dev), mask.to(cuda_dev))
     call = ctx.call
     sc = lambda p, layer, site, shape: ops.dropout_scale(int(torch.tensor(shape).prod()), ops.Drop(p, enc.drop_seed, (call << 24) | (layer << 8) | site, enc.drop_offset), cuda_dev).view(shape).cpu()
+    Lp = (L + 7) // 8 * 8
     # HF call order: embeddings.dropout; per layer: LoRA dropout for query, key, value (our mask is shared by the three
     # adapters of a layer - documented deviation from peft's independent masks), attention probs, self-output, output
     queue = [sc(enc.p_hidden, 255, 0, (B, L, H))]
     for l in range(enc.nl):
         lm = sc(enc.p_lora, l, 3, (B, L, H))
-        queue += [lm, lm, lm, sc(enc.p_attn, l, 8, (B, nh, L, L)), sc(enc.p_hidden, l, 1, (B, L, H)), sc(enc.p_hidden, l, 2, (B, L, H))]
+        queue += [lm, lm, lm, sc(enc.p_attn, l, 8, (B, nh, L, Lp))[..., :L], sc(enc.p_hidden, l, 1, (B, L, H)), sc(enc.p_hidden, l, 2, (B, L, H))]
     ref = om.build_bert(cfg, sd)
     om.attach_lora(ref, {n: {"A": enc.lora.A[n].cpu(), "B": enc.lora.B[n].cpu()} for n, _, _ in enc.lora.specs}, dropout=0.05)
     ref.train()
