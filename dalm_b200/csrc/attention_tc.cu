@@ -1,0 +1,249 @@
+// dalm_b200 — decoder attention on the 5th-gen tensor cores (tcgen05.mma + TMEM accumulators + TMA), head_dim 128,
+// causal + key-padding mask, MHA/GQA. Forward and backward (dKdV, dQ).
+//
+// Replaces the attention inside HF LlamaForCausalLM reached through dalm/models/rag_e2e_base_model.py:105 (reference) and
+// its autograd backward; same math as csrc/attention.cu (flash-style, scores never in HBM, LSE saved, P recomputed).
+//
+// Every contraction is a 128 x 128 x 128 tcgen05 tile issued by ONE thread; the softmax / dS elementwise work runs on
+// four warps that own one TMEM lane (= one query or key row) each:
+//     forward : S = Q K^T        -> TMEM | P = exp2(S - m) -> bf16 -> 128B-swizzled smem | PV = P V          -> TMEM -> O (regs)
+//     dKdV    : S^T = K Q^T, dP^T = V dO^T -> TMEM | P^T, dS^T -> smem | dV += P^T dO, dK += dS^T Q (TMEM accumulators)
+//     dQ      : S = Q K^T, dP = dO V^T     -> TMEM | dS -> smem          | dQ += dS K                  (TMEM accumulator)
+// The token-major [tokens][d] tiles that TMA drops into shared memory serve BOTH as K-major operands (contraction over d:
+// QK^T, dO V^T) and, through MN-major descriptors, as the B operand of the contractions over tokens (P V, dS K, dS^T Q,
+// P^T dO) - no transposes anywhere.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace dalm {
+using namespace ptx;
+
+struct AttnTcParams {
+  const int64_t* mask;              // [B,L] key-padding mask or nullptr
+  __nv_bfloat16* o; long long ldo;  // forward output [B*L, Hq*128]
+  float* lse;                       // [B,Hq,L]
+  const float* delta;               // [B,Hq,L] (backward)
+  __nv_bfloat16* dq; __nv_bfloat16* dk; __nv_bfloat16* dv;
+  long long lddq, lddk, lddv;
+  int B, L, Hq, Hkv;
+  float scale;
+  int causal;
+  int qcol0, kcol0, vcol0, ocol0;   // column of head 0 inside the q / k / v / dO tensor maps
+};
+
+constexpr int TD = 128;                      // head dim
+constexpr int TB = 128;                      // tile: 128 queries x 128 keys
+constexpr int HALF_BYTES = TB * 64 * 2;      // one [128 rows x 64 cols] bf16 box = 16 KB
+constexpr int TILE_BYTES = 2 * HALF_BYTES;   // [128 x 128] bf16 as two 64-column halves
+
+// A/B K-major descriptors for k-step kk (0..7) of a [128 x 128] tile stored as two 64-col halves
+__device__ __forceinline__ uint64_t kmajor_desc(uint32_t tile, int kk) {
+  return make_sw128_kmajor_desc(tile + (kk >> 2) * HALF_BYTES) + (uint64_t)(2 * (kk & 3));
+}
+// B MN-major descriptor for k-step kk (16 token rows) of a [128 tokens x 128 d] tile stored as two 64-col halves
+__device__ __forceinline__ uint64_t mnmajor_desc(uint32_t tile, int kk) {
+  return make_sw128_mnmajor_desc(tile + kk * 16 * 128, HALF_BYTES, 1024);
+}
+// store 8 bf16 (one 16-byte piece `piece` of row `row`) into a 128B-swizzled [128 x 64] half tile
+__device__ __forceinline__ void st_sw128(unsigned char* half_tile, int row, int piece, const bf16x8& v) {
+  *reinterpret_cast<bf16x8*>(half_tile + row * 128 + ((piece ^ (row & 7)) << 4)) = v;
+}
+
+// ============================================================================================================
+// forward: grid (ceil(L/128), Hq, B), 160 threads: warps 0-3 softmax (thread = query row), warp 4 control
+// ============================================================================================================
+__global__ void __launch_bounds__(160, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                   const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sQ = smem;
+  unsigned char* sK = sQ + TILE_BYTES;
+  unsigned char* sV = sK + TILE_BYTES;
+  unsigned char* sP = sV + TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + TILE_BYTES);
+  uint64_t *q_full = bars, *kv_full = bars + 1, *kv_free = bars + 2, *s_full = bars + 3, *p_ready = bars + 4, *pv_full = bars + 5;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
+  float* sMask = reinterpret_cast<float*>(bars + 10);          // [128] additive 0 / -inf for the current key tile
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int hk = h / (p.Hq / p.Hkv);
+  const int L = p.L, q0 = qb * TB;
+  const int tok0 = b * L;
+  const int nkv = p.causal ? (min(L, q0 + TB) + TB - 1) / TB : (L + TB - 1) / TB;
+
+  if (threadIdx.x == 128) {
+    mbar_init(q_full, 1); mbar_init(kv_full, 1); mbar_init(kv_free, 1); mbar_init(s_full, 1);
+    mbar_init(p_ready, 128); mbar_init(pv_full, 1);
+    fence_mbar_init();
+    prefetch_tmap(&tm_q); prefetch_tmap(&tm_k); prefetch_tmap(&tm_v);
+  }
+  if (warp == 0) { tmem_alloc(tmem_holder, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  const uint32_t tS = tmem, tPV = tmem + 128;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---------------- control: TMA loads + MMA issue ----------------
+      mbar_arrive_expect_tx(q_full, TILE_BYTES);
+      tma_load_2d(sQ, &tm_q, q_full, p.qcol0 + h * TD, tok0 + q0);
+      tma_load_2d(sQ + HALF_BYTES, &tm_q, q_full, p.qcol0 + h * TD + 64, tok0 + q0);
+      constexpr uint32_t idesc_kk = make_idesc_bf16(TB, TB);          // S  = Q K^T   (both K-major)
+      constexpr uint32_t idesc_mn = make_idesc_bf16_bmn(TB, TD);      // PV = P V     (B = V MN-major)
+      for (int j = 0; j < nkv; ++j) {
+        const uint32_t ph = j & 1;
+        mbar_wait(kv_free, ph ^ 1);
+        mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
+        tma_load_2d(sK, &tm_k, kv_full, p.kcol0 + hk * TD, tok0 + j * TB);
+        tma_load_2d(sK + HALF_BYTES, &tm_k, kv_full, p.kcol0 + hk * TD + 64, tok0 + j * TB);
+        tma_load_2d(sV, &tm_v, kv_full, p.vcol0 + hk * TD, tok0 + j * TB);
+        tma_load_2d(sV + HALF_BYTES, &tm_v, kv_full, p.vcol0 + hk * TD + 64, tok0 + j * TB);
+        if (j == 0) mbar_wait(q_full, 0);
+        mbar_wait(kv_full, ph);
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma_f16(tS, kmajor_desc(aQ, kk), kmajor_desc(aK, kk), idesc_kk, kk != 0);
+        umma_commit(s_full);
+        mbar_wait(p_ready, ph);                                         // P tile written (and PV of block j-1 consumed)
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma_f16(tPV, kmajor_desc(aP, kk), mnmajor_desc(aV, kk), idesc_mn, kk != 0);
+        umma_commit(pv_full);
+        umma_commit(kv_free);
+      }
+    }
+  } else {
+    // ---------------- softmax warps: thread = query row ----------------
+    const int r = warp * 32 + lane;                    // TMEM lane == query row within the tile
+    const int qrow = q0 + r;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    float o_acc[TD];
+#pragma unroll
+    for (int i = 0; i < TD; ++i) o_acc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      const uint32_t ph = j & 1;
+      const int kv0 = j * TB;
+      // key validity of this tile (own barrier among the 128 softmax threads)
+      {
+        const int key = kv0 + r;
+        bool keep = key < L;
+        if (keep && p.mask) keep = p.mask[(size_t)tok0 + key] != 0;
+        named_bar_sync(1, 128);                          // previous tile's readers are done with sMask
+        sMask[r] = keep ? 0.f : -INFINITY;
+        named_bar_sync(1, 128);
+      }
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < TB; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + lane_off + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float val = __uint_as_float(v[i]) * sl2 + sMask[c + i];
+          if (p.causal && (kv0 + c + i) > qrow) val = -INFINITY;
+          mx = fmaxf(mx, val);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+      const float corr = exp2f(m_run - m_safe);
+      m_run = m_new;
+      // pass 2: P = exp2(S - m) -> bf16 -> swizzled smem (A operand of P V), row sum
+      float rs = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < TB; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + lane_off + c, v);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float val = __uint_as_float(v[i]) * sl2 + sMask[c + i];
+          if (p.causal && (kv0 + c + i) > qrow) val = -INFINITY;
+          pv[i] = exp2f(val - m_safe);
+          rs += pv[i];
+        }
+        unsigned char* half = sP + (c >> 6) * HALF_BYTES;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) st_sw128(half, r, ((c & 63) >> 3) + g, pack8(pv + g * 8));
+      }
+      l_run = l_run * corr + rs;
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(p_ready);
+      // PV of this tile -> accumulate into the register-resident O with the online-softmax correction
+      mbar_wait(pv_full, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < TD; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tPV + lane_off + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[c + i] = o_acc[c + i] * corr + __uint_as_float(v[i]);
+      }
+      tc_fence_before();
+    }
+    if (qrow < L) {
+      const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
+      __nv_bfloat16* orow = p.o + (size_t)(tok0 + qrow) * p.ldo + (size_t)h * TD;
+#pragma unroll
+      for (int g = 0; g < TD / 8; ++g) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = o_acc[g * 8 + i] * inv_l;
+        *reinterpret_cast<bf16x8*>(orow + g * 8) = pack8(f);
+      }
+      p.lse[((size_t)b * p.Hq + h) * L + qrow] = l_run > 0.f ? (m_run + log2f(l_run)) * 0.6931471805599453f : INFINITY;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
+constexpr int kFwdSmem = 4 * TILE_BYTES + 1024 + 1024;
+
+}  // namespace dalm
+
+using namespace dalm;
+
+static int tc_maps(const void* ptr, long long rows, long long cols, long long ld, CUtensorMap* m) {
+  return get_tmap(ptr, rows, cols, ld, 128, m, 0);
+}
+
+// q/k/v: bf16 token-major 2-D matrices [B*L, ncols] (row stride ld*), head h of q at column qcol0 + h*128 etc.
+extern "C" int dalm_b200_attention_tc_fwd(const void* q, long long ldq, long long qcols, int qcol0, const void* k,
+                                          long long ldk, long long kcols, int kcol0, const void* v, long long ldv,
+                                          long long vcols, int vcol0, const int64_t* mask, void* out, long long ldo,
+                                          float* lse, int B, int L, int Hq, int Hkv, int D, float scale, int causal,
+                                          void* stream) {
+  DALM_REQUIRE(D == 128, "attention_tc: head_dim must be 128 (got %d)", D);
+  DALM_REQUIRE(B > 0 && L > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0, "attention_tc: bad shape");
+  DALM_REQUIRE((ldo % 8) == 0 && ((uintptr_t)out & 15) == 0, "attention_tc: output alignment");
+  CUtensorMap mq, mk, mv;
+  const long long rows = (long long)B * L;
+  if (int e = tc_maps(q, rows, qcols, ldq, &mq)) return e;
+  if (int e = tc_maps(k, rows, kcols, ldk, &mk)) return e;
+  if (int e = tc_maps(v, rows, vcols, ldv, &mv)) return e;
+  AttnTcParams p{};
+  p.mask = mask; p.o = (__nv_bfloat16*)out; p.ldo = ldo; p.lse = lse; p.B = B; p.L = L; p.Hq = Hq; p.Hkv = Hkv;
+  p.scale = scale; p.causal = causal; p.qcol0 = qcol0; p.kcol0 = kcol0; p.vcol0 = vcol0;
+  static bool attr = false;
+  if (!attr) { DALM_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem)); attr = true; }
+  dim3 grid((L + TB - 1) / TB, Hq, B);
+  attn_fwd_tc_kernel<<<grid, 160, kFwdSmem, (cudaStream_t)stream>>>(mq, mk, mv, p);
+  count_launch();
+  return check_launch("attn_fwd_tc_kernel");
+}

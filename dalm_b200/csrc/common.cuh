@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <string.h>
 
+struct CUtensorMap_st;          // CUtensorMap (cuda.h)
+
 namespace dalm {
 
 // ---------------------------------------------------------------------------------------------
@@ -33,6 +35,10 @@ void count_launch(int n = 1);                 // bumps the global launch counter
   } while (0)
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+
+// cached TMA descriptor of a row-major [rows, cols] bf16 (or fp32) matrix with row stride ld; box = {128 bytes, box_rows},
+// 128B swizzle (defined in gemm_tcgen05.cu)
+int get_tmap(const void* ptr, long long rows, long long cols, long long ld, int box_rows, ::CUtensorMap_st* out, int f32 = 0);
 
 // ---------------------------------------------------------------------------------------------
 // warp / block reductions (shuffle based, no atomics)

@@ -8,12 +8,13 @@
 // and the lm_head. It replaces the cuBLAS calls made by HF modeling code under
 // dalm/models/rag_e2e_base_model.py:93,105 (reference) and the autograd backward of those.
 //
-// Structure (one persistent CTA per SM, 256 threads):
+// Structure (one persistent CTA per SM, 384 threads):
 //   warp 0      : TMA producer   - cp.async.bulk.tensor 128B-swizzled tiles into a STAGES-deep smem ring
 //   warp 1      : MMA issuer     - one elected lane issues tcgen05.mma (128 x BN x 16) into a double-buffered TMEM
 //                                  accumulator, tcgen05.commit releases smem slots / publishes the accumulator
 //   warp 2      : TMEM allocator
-//   warps 4..7  : epilogue       - tcgen05.ld 32x32b -> registers -> alpha/bias/GELU/residual -> bf16|fp32 -> HBM,
+//   warps 4..11 : epilogue       - tcgen05.ld 32x32b -> registers -> alpha/bias/GELU/dropout/residual -> swizzled smem
+//                                  -> TMA store (two groups of 4 warps interleave 128-byte-wide store blocks),
 //                                  overlapped with the next tile's MMAs through the second accumulator stage
 #include "common.cuh"
 #include "ptx.cuh"
@@ -92,25 +93,29 @@ __device__ __forceinline__ void epilogue_math(const GemmEpilogue& ep, const uint
 // and TMA stores: the 128 epilogue threads write their rows into shared memory (16-byte pieces XOR-swizzled by row % 8:
 // conflict-free per quarter warp, and exactly the layout CU_TENSOR_MAP_SWIZZLE_128B expects), one thread issues
 // cp.async.bulk.tensor stores of [128 rows x 128 bytes] boxes. HBM sees full 128-byte lines; ragged M / N edges are
-// clipped by the TMA unit. Two staging tiles alternate so a store overlaps the next block's TMEM reads.
+// clipped by the TMA unit. Two groups of four epilogue warps (8 warps: TMEM lane quarter = warp % 4) take alternate
+// store blocks, each with its own staging tile, so one group's TMA store overlaps the other's TMEM reads and math.
 // (Direct per-thread row stores were measured at 1170 TFLOP/s vs 1540 TFLOP/s for the bare mainloop: profiles/.)
 constexpr int kStageTileBytes = 128 * 128;
+constexpr int kEpiGroups = 2;                                   // two groups of 4 epilogue warps split a tile's store blocks
+constexpr int kGemmThreads = 128 + kEpiGroups * 128;            // warps 0-3: TMA / MMA / TMEM alloc / spare ; warps 4-11: epilogue
 template <int BN>
 __device__ __forceinline__ void epilogue_drain_tile(const GemmEpilogue& ep, const CUtensorMap* tmap_out, unsigned char* staging,
-                                                    int& sbuf, uint32_t t_row, int row_in_tile, int tile_row0, int tile_col0) {
+                                                    int grp, uint32_t t_row, int row_in_tile, int tile_row0, int tile_col0) {
   const int N = ep.N;
   const int row = tile_row0 + row_in_tile;
   const bool row_ok = row < ep.M;
   const int sb_cols = ep.out_f32 ? 32 : 64;                    // 128 bytes of output per row per store block
-  const bool issuer = (threadIdx.x == 128);                    // first epilogue thread
+  const bool issuer = (threadIdx.x == 128 + grp * 128);        // first thread of this epilogue group
+  unsigned char* tile = staging + grp * kStageTileBytes;       // one staging tile per group
+  unsigned char* st = tile + row_in_tile * 128;
+  const int sw = row_in_tile & 7;
 #pragma unroll 1
-  for (int c = 0; c < BN; c += sb_cols) {
+  for (int c = grp * sb_cols; c < BN; c += kEpiGroups * sb_cols) {   // the two groups interleave store blocks
     const int col0 = tile_col0 + c;
-    if (col0 >= N) break;                                       // uniform across the 4 epilogue warps
-    if (issuer) bulk_wait_read<1>();                            // the store that used this staging tile has read it
-    named_bar_sync(1, 128);
-    unsigned char* st = staging + sbuf * kStageTileBytes + row_in_tile * 128;
-    const int sw = row_in_tile & 7;
+    if (col0 >= N) break;                                       // uniform across the group's 4 warps
+    if (issuer) bulk_wait_read<0>();                            // the previous store has finished reading the staging tile
+    named_bar_sync(1 + grp, 128);
     if (ep.out_f32) {
       uint32_t v[32]; float f[32];
       tmem_ld_32x32(t_row + (uint32_t)c, v);
@@ -134,12 +139,11 @@ __device__ __forceinline__ void epilogue_drain_tile(const GemmEpilogue& ep, cons
       }
     }
     fence_proxy_async();                                        // generic-proxy smem writes -> visible to the TMA unit
-    named_bar_sync(1, 128);
+    named_bar_sync(1 + grp, 128);
     if (issuer) {
-      tma_store_2d(tmap_out, staging + sbuf * kStageTileBytes, col0, tile_row0);
+      tma_store_2d(tmap_out, tile, col0, tile_row0);
       bulk_commit();
     }
-    sbuf ^= 1;
   }
 }
 
@@ -155,7 +159,7 @@ template <int BN> struct GemmCfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const GemmEpilogue ep) {
   using Cfg = GemmCfg<BN>;
@@ -183,7 +187,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < Cfg::ACC_STAGES; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < Cfg::ACC_STAGES; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4 * kEpiGroups); }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -244,22 +248,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp >= 4) {
     // =============================== epilogue ===============================
-    const int q = warp - 4;                                     // TMEM lane quarter == warp % 4
+    const int q = warp & 3;                                     // TMEM lane quarter == warp % 4
+    const int grp = (warp - 4) >> 2;                            // epilogue group 0 / 1
     int acc = 0; uint32_t acc_phase = 0;
-    int sbuf = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile % num_m, n_blk = tile / num_m;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_drain_tile<BN>(ep, &tmap_out, staging, sbuf, t_row, q * 32 + lane, m_blk * BM, n_blk * BN);
+      epilogue_drain_tile<BN>(ep, &tmap_out, staging, grp, t_row, q * 32 + lane, m_blk * BM, n_blk * BN);
       // all TMEM reads of this warp are complete (wait::ld): hand the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
-    if (threadIdx.x == 128) bulk_wait<0>();                     // staging tiles must outlive their TMA reads
+    if ((threadIdx.x & 127) == 0) bulk_wait<0>();               // staging tiles must outlive their TMA reads
   }
 
   tc_fence_before();
@@ -289,7 +293,7 @@ template <int BN, int ST = 0> struct Gemm2Cfg {
 };
 
 template <int BN, int ST>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_out, const GemmEpilogue ep) {
   using Cfg = Gemm2Cfg<BN, ST>;
@@ -316,7 +320,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     // tfull: one multicast commit per tile; tempty (used on the leader): 4 epilogue warps of EACH CTA arrive
-    for (int a = 0; a < Cfg::ACC_STAGES; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+    for (int a = 0; a < Cfg::ACC_STAGES; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8 * kEpiGroups); }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -377,21 +381,21 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     }
   } else if (warp >= 4) {
     // =============================== epilogue (both CTAs, own 128 rows) ===============================
-    const int q = warp - 4;
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
     int acc = 0; uint32_t acc_phase = 0;
-    int sbuf = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile % num_m, n_blk = tile / num_m;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_drain_tile<BN>(ep, &tmap_out, staging, sbuf, t_row, q * 32 + lane, m_blk * 2 * BM + (int)rank * BM, n_blk * BN);
+      epilogue_drain_tile<BN>(ep, &tmap_out, staging, grp, t_row, q * 32 + lane, m_blk * 2 * BM + (int)rank * BM, n_blk * BN);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tempty_bar[acc], 0);   // leader's barrier
       if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
-    if (threadIdx.x == 128) bulk_wait<0>();
+    if ((threadIdx.x & 127) == 0) bulk_wait<0>();
   }
 
   tc_fence_before();
@@ -437,7 +441,7 @@ static std::mutex g_tmap_mu;
 
 // row-major [rows, cols] (bf16, or fp32 when f32 != 0) with row stride ld (elements);
 // box = {128 bytes of columns, box_rows}, 128B swizzle, OOB loads -> 0, OOB stores clipped
-static int get_tmap(const void* ptr, long long rows, long long cols, long long ld, int box_rows, CUtensorMap* out, int f32 = 0) {
+int get_tmap(const void* ptr, long long rows, long long cols, long long ld, int box_rows, CUtensorMap* out, int f32) {
   TmapKey key{ptr, rows, cols, ld, box_rows, f32};
   {
     std::lock_guard<std::mutex> g(g_tmap_mu);
@@ -479,7 +483,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   const int num_tiles = ((ep.M + 127) / 128) * ((ep.N + BN - 1) / BN);
   int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  gemm_bf16_tn_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, to, ep);
+  gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, to, ep);
   count_launch();
   return check_launch("gemm_bf16_tn_kernel");
 }
@@ -496,7 +500,7 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   const int num_tiles = ((ep.M + 255) / 256) * ((ep.N + BN - 1) / BN);
   int clusters = num_tiles < kNumSMs / 2 ? num_tiles : kNumSMs / 2;
   if (max_ctas > 0 && clusters > max_ctas / 2) clusters = max_ctas / 2 > 0 ? max_ctas / 2 : 1;
-  gemm2_bf16_tn_kernel<BN, ST><<<2 * clusters, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, to, ep);
+  gemm2_bf16_tn_kernel<BN, ST><<<2 * clusters, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, to, ep);
   count_launch();
   return check_launch("gemm2_bf16_tn_kernel");
 }

@@ -185,9 +185,26 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                               // layout type SWIZZLE_128B                bits [61,64)
   return d;
 }
+// MN-major, 128-byte-swizzled descriptor: the tile is stored [K rows][64 MN elements = 128 B]; 8-row groups along K are
+// `sbo` bytes apart, successive 64-element chunks along MN are `lbo` bytes apart (canonical layout
+// ((8,8,m),(8,k)):((1,8,LBO),(64,SBO)) in elements). Lets a row-major [tokens][d] tile feed the B operand of O = P V,
+// dQ = dS K, dK = dS^T Q, dV = P^T dO (contraction over tokens) without a transpose.
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, dense
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// same, B operand MN-major (bit 16)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(int M, int N) {
+  return make_idesc_bf16(M, N) | (1u << 16);
 }
 
 }}  // namespace dalm::ptx

@@ -215,6 +215,20 @@ def attention_fwd(q, k, v, mask, B: int, L: int, Hq: int, Hkv: int, D: int, caus
     return out, lse
 
 
+def attention_tc_fwd(q, k, v, mask, B: int, L: int, Hq: int, Hkv: int, D: int, causal: bool, out=None,
+                     scale: Optional[float] = None):
+    """tcgen05/TMEM attention forward (head_dim 128). Same contract as attention_fwd."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _chk(t, bf16, n)
+    if out is None:
+        out = torch.empty(B * L, Hq * D, dtype=bf16, device=q.device)
+    lse = torch.empty(B, Hq, L, dtype=f32, device=q.device)
+    scale = 1.0 / math.sqrt(D) if scale is None else scale
+    _lib.call("dalm_b200_attention_tc_fwd", _p(q), _ld(q), q.shape[1], 0, _p(k), _ld(k), k.shape[1], 0, _p(v), _ld(v), v.shape[1], 0,
+              _p(mask), _p(out), _ld(out), _p(lse), B, L, Hq, Hkv, D, float(scale), 1 if causal else 0, _stream())
+    return out, lse
+
+
 def attention_bwd(q, k, v, mask, out, lse, d_out, B: int, L: int, Hq: int, Hkv: int, D: int, causal: bool,
                   dq=None, dk=None, dv=None, scale: Optional[float] = None, drop: Optional[Drop] = None):
     dev = q.device

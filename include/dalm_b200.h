@@ -82,6 +82,13 @@ int dalm_b200_attention_bwd(const void* q, long long ldq, const void* k, long lo
                             long long lddv, int B, int L, int Hq, int Hkv, int D, float scale, int causal, float drop_p, unsigned long long drop_seed,
     unsigned long long drop_stream_id, const void* drop_offset, void* stream);
 
+/* tcgen05 / TMEM / TMA attention for head_dim 128 (decoder). q/k/v are bf16 token-major matrices [B*L, *cols] with row
+ * stride ld*; head h starts at column *col0 + h*128. Same outputs as dalm_b200_attention_fwd / _bwd. */
+int dalm_b200_attention_tc_fwd(const void* q, long long ldq, long long qcols, int qcol0, const void* k, long long ldk,
+                               long long kcols, int kcol0, const void* v, long long ldv, long long vcols, int vcol0,
+                               const int64_t* mask, void* out, long long ldo, float* lse, int B, int L, int Hq, int Hkv,
+                               int D, float scale, int causal, void* stream);
+
 /* ---- row-wise pieces of the encoder / decoder blocks ---- */
 int dalm_b200_layernorm_fwd(const float* z, const float* gamma, const float* beta, float* y32, void* y16, long long ld16,
                             float* mean, float* rstd, int M, int H, float eps, float drop_p, unsigned long long drop_seed,

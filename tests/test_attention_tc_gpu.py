@@ -1,0 +1,56 @@
+"""-m gpu: tcgen05/TMEM attention (head_dim 128) against the fp64 torch reference and the mma.sync kernels."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _ref(q, k, v, mask, causal, B, L, Hq, Hkv, D):
+    qh = q.double().view(B, L, Hq, D).transpose(1, 2)
+    kh = k.double().view(B, L, Hkv, D).transpose(1, 2).repeat_interleave(Hq // Hkv, dim=1)
+    vh = v.double().view(B, L, Hkv, D).transpose(1, 2).repeat_interleave(Hq // Hkv, dim=1)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(D)
+    if mask is not None:
+        s = s.masked_fill(mask.view(B, 1, 1, L) == 0, float("-inf"))
+    if causal:
+        s = s.masked_fill(torch.triu(torch.ones(L, L, device=q.device, dtype=torch.bool), 1), float("-inf"))
+    p = torch.nan_to_num(torch.softmax(s, dim=-1), nan=0.0)
+    return (p @ vh).transpose(1, 2).reshape(B * L, Hq * D)
+
+
+@pytest.mark.parametrize("B,L,Hq,Hkv,causal,pad", [
+    (2, 256, 2, 2, True, "none"), (2, 128, 2, 2, True, "none"), (3, 200, 4, 4, True, "right"), (2, 96, 4, 4, True, "left"),
+    (1, 300, 4, 2, True, "right"), (2, 384, 2, 2, False, "right"), (18, 256, 32, 32, True, "none"),
+])
+def test_attention_tc_forward(cuda_dev, B, L, Hq, Hkv, causal, pad):
+    from dalm_b200 import ops
+    D = 128
+    torch.manual_seed(B * 100 + L)
+    dev = cuda_dev
+    qkv = torch.randn(B * L, (Hq + 2 * Hkv) * D, device=dev).to(bf16)
+    q, k, v = qkv[:, :Hq * D], qkv[:, Hq * D:(Hq + Hkv) * D], qkv[:, (Hq + Hkv) * D:]
+    mask = torch.ones(B, L, dtype=torch.int64, device=dev)
+    if pad == "right":
+        for b in range(B): mask[b, L - 3 - 5 * b:] = 0
+    elif pad == "left":
+        for b in range(B): mask[b, :4 + 3 * b] = 0
+    out, lse = ops.attention_tc_fwd(q, k, v, mask, B, L, Hq, Hkv, D, causal)
+    out2, lse2 = ops.attention_fwd(q, k, v, mask, B, L, Hq, Hkv, D, causal)
+    if B * L * Hq <= 20000:
+        ref = _ref(q, k, v, mask, causal, B, L, Hq, Hkv, D)
+        rows = mask.bool().view(-1) if (causal and pad == "left") else torch.ones(B * L, dtype=torch.bool, device=dev)
+        assert _rel(out.float()[rows], ref[rows]) < 1.5e-2
+        if causal and pad == "left":
+            assert out.float()[~rows].abs().max().item() == 0.0
+    assert _rel(out.float(), out2.float()) < 1.5e-2
+    fin = torch.isfinite(lse2)
+    assert torch.equal(torch.isfinite(lse), fin)
+    assert (lse[fin] - lse2[fin]).abs().max().item() < 2e-2
