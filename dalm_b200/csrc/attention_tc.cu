@@ -52,7 +52,7 @@ __device__ __forceinline__ void st_sw128(unsigned char* half_tile, int row, int 
 // ============================================================================================================
 // forward: grid (ceil(L/128), Hq, B), 160 threads: warps 0-3 softmax (thread = query row), warp 4 control
 // ============================================================================================================
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(160, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p) {
   extern __shared__ unsigned char smem_raw[];
@@ -60,8 +60,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   unsigned char* sQ = smem;
   unsigned char* sK = sQ + TILE_BYTES;
   unsigned char* sV = sK + TILE_BYTES;
-  unsigned char* sP = sV + TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + TILE_BYTES);
+  unsigned char* sP = sK;        // P overwrites K: K is dead once S = Q K^T has retired (s_full), and K is only reloaded
+                                 // after P V has retired (kv_free). 96 KB per CTA => two CTAs per SM hide each other's
+                                 // TMA / MMA / softmax latencies.
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + TILE_BYTES);
   uint64_t *q_full = bars, *kv_full = bars + 1, *kv_free = bars + 2, *s_full = bars + 3, *p_ready = bars + 4, *pv_full = bars + 5;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
   float* sMask = reinterpret_cast<float*>(bars + 10);          // [128] additive 0 / -inf for the current key tile
@@ -166,17 +168,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         uint32_t v[32];
         tmem_ld_32x32(tS + lane_off + c, v);
         tmem_ld_wait();
-        float pv[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float val = __uint_as_float(v[i]) * sl2 + sMask[c + i];
-          if (p.causal && (kv0 + c + i) > qrow) val = -INFINITY;
-          pv[i] = exp2f(val - m_safe);
-          rs += pv[i];
-        }
         unsigned char* half = sP + (c >> 6) * HALF_BYTES;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) st_sw128(half, r, ((c & 63) >> 3) + g, pack8(pv + g * 8));
+        for (int g = 0; g < 4; ++g) {
+          float pv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float val = __uint_as_float(v[g * 8 + i]) * sl2 + sMask[c + g * 8 + i];
+            if (p.causal && (kv0 + c + g * 8 + i) > qrow) val = -INFINITY;
+            pv[i] = exp2f(val - m_safe);
+            rs += pv[i];
+          }
+          st_sw128(half, r, ((c & 63) >> 3) + g, pack8(pv));
+        }
       }
       l_run = l_run * corr + rs;
       tc_fence_before();
@@ -213,7 +217,335 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
-constexpr int kFwdSmem = 4 * TILE_BYTES + 1024 + 1024;
+// ============================================================================================================
+// backward pre-pass: delta[b,h,i] = sum_d dO[i,d] * O[i,d]   (one warp per (token, head))
+// ============================================================================================================
+__global__ void attn_tc_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ d_o,
+                                     long long lddo, float* __restrict__ delta, int B, int L, int Hq) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= B * L * Hq) return;
+  const int tok = gw / Hq, h = gw - tok * Hq;
+  float a[4], c[4];
+  const uint2 ra = *reinterpret_cast<const uint2*>(o + (size_t)tok * ldo + (size_t)h * TD + lane * 4);
+  const uint2 rc = *reinterpret_cast<const uint2*>(d_o + (size_t)tok * lddo + (size_t)h * TD + lane * 4);
+  float2 t;
+  t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ra.x)); a[0] = t.x; a[1] = t.y;
+  t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ra.y)); a[2] = t.x; a[3] = t.y;
+  t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rc.x)); c[0] = t.x; c[1] = t.y;
+  t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rc.y)); c[2] = t.x; c[3] = t.y;
+  float acc = a[0] * c[0] + a[1] * c[1] + a[2] * c[2] + a[3] * c[3];
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const int b = tok / L, l = tok - b * L;
+    delta[((size_t)b * Hq + h) * L + l] = acc;
+  }
+}
+
+// ============================================================================================================
+// backward dK, dV: grid (ceil(L/128) key tiles, Hkv, B); thread = key row. Loops over the q heads of the group and the
+// query tiles that can see this key tile. dV and dK accumulate in TMEM across ALL of them.
+// ============================================================================================================
+__global__ void __launch_bounds__(160, 1)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                       const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                       const AttnTcParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sK = smem;
+  unsigned char* sV = sK + TILE_BYTES;
+  unsigned char* sQ = sV + TILE_BYTES;
+  unsigned char* sdO = sQ + TILE_BYTES;
+  unsigned char* sPt = sdO + TILE_BYTES;
+  unsigned char* sdSt = sPt + TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdSt + TILE_BYTES);
+  uint64_t *kv_full = bars, *qdo_full = bars + 1, *st_full = bars + 2, *pt_ready = bars + 3, *mma2_done = bars + 4;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
+  float* sLse = reinterpret_cast<float*>(bars + 10);            // [128] base-2 LSE of the current query tile
+  float* sDelta = sLse + 128;                                   // [128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  const int group = p.Hq / p.Hkv;
+  const int L = p.L, kv0 = kb * TB, tok0 = b * L;
+  const int nq_tiles = (L + TB - 1) / TB;
+  const int i_begin = p.causal ? kb : 0;                        // query tiles before the key tile see none of it
+  const int n_iter = group * (nq_tiles - i_begin);
+
+  if (threadIdx.x == 128) {
+    mbar_init(kv_full, 1); mbar_init(qdo_full, 1); mbar_init(st_full, 1); mbar_init(pt_ready, 128); mbar_init(mma2_done, 1);
+    fence_mbar_init();
+    prefetch_tmap(&tm_q); prefetch_tmap(&tm_k); prefetch_tmap(&tm_v); prefetch_tmap(&tm_do);
+  }
+  if (warp == 0) { tmem_alloc(tmem_holder, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  const uint32_t tSt = tmem, tdPt = tmem + 128, tdV = tmem + 256, tdK = tmem + 384;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
+      tma_load_2d(sK, &tm_k, kv_full, p.kcol0 + hk * TD, tok0 + kv0);
+      tma_load_2d(sK + HALF_BYTES, &tm_k, kv_full, p.kcol0 + hk * TD + 64, tok0 + kv0);
+      tma_load_2d(sV, &tm_v, kv_full, p.vcol0 + hk * TD, tok0 + kv0);
+      tma_load_2d(sV + HALF_BYTES, &tm_v, kv_full, p.vcol0 + hk * TD + 64, tok0 + kv0);
+      constexpr uint32_t idesc_kk = make_idesc_bf16(TB, TB);
+      constexpr uint32_t idesc_mn = make_idesc_bf16_bmn(TB, TD);
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), aDO = smem_u32(sdO), aPt = smem_u32(sPt), aDSt = smem_u32(sdSt);
+      int it = 0;
+      for (int hq = hk * group; hq < (hk + 1) * group; ++hq) {
+        for (int i = i_begin; i < nq_tiles; ++i, ++it) {
+          const uint32_t ph = it & 1;
+          mbar_wait(mma2_done, ph ^ 1);                          // previous iteration's dV/dK MMAs have consumed Q/dO
+          mbar_arrive_expect_tx(qdo_full, 2 * TILE_BYTES);
+          tma_load_2d(sQ, &tm_q, qdo_full, p.qcol0 + hq * TD, tok0 + i * TB);
+          tma_load_2d(sQ + HALF_BYTES, &tm_q, qdo_full, p.qcol0 + hq * TD + 64, tok0 + i * TB);
+          tma_load_2d(sdO, &tm_do, qdo_full, p.ocol0 + hq * TD, tok0 + i * TB);
+          tma_load_2d(sdO + HALF_BYTES, &tm_do, qdo_full, p.ocol0 + hq * TD + 64, tok0 + i * TB);
+          if (it == 0) mbar_wait(kv_full, 0);
+          mbar_wait(qdo_full, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) umma_f16(tSt, kmajor_desc(aK, kk), kmajor_desc(aQ, kk), idesc_kk, kk != 0);    // S^T  = K Q^T
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) umma_f16(tdPt, kmajor_desc(aV, kk), kmajor_desc(aDO, kk), idesc_kk, kk != 0);  // dP^T = V dO^T
+          umma_commit(st_full);
+          mbar_wait(pt_ready, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) umma_f16(tdV, kmajor_desc(aPt, kk), mnmajor_desc(aDO, kk), idesc_mn, (it | kk) != 0);   // dV += P^T dO
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) umma_f16(tdK, kmajor_desc(aDSt, kk), mnmajor_desc(aQ, kk), idesc_mn, (it | kk) != 0);   // dK += dS^T Q
+          umma_commit(mma2_done);
+        }
+      }
+    }
+  } else {
+    const int r = warp * 32 + lane;                              // key row within the tile == TMEM lane
+    const int key = kv0 + r;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    bool key_ok = key < L;
+    if (key_ok && p.mask) key_ok = p.mask[(size_t)tok0 + key] != 0;
+    int it = 0;
+    for (int hq = hk * group; hq < (hk + 1) * group; ++hq) {
+      for (int i = i_begin; i < nq_tiles; ++i, ++it) {
+        const uint32_t ph = it & 1;
+        const int q0 = i * TB;
+        {
+          const int qi = q0 + r;
+          const size_t idx = ((size_t)b * p.Hq + hq) * L + qi;
+          named_bar_sync(1, 128);                                // readers of the previous tile's lse/delta are done
+          sLse[r] = qi < L ? p.lse[idx] * 1.4426950408889634f : INFINITY;
+          sDelta[r] = qi < L ? p.delta[idx] : 0.f;
+          named_bar_sync(1, 128);
+        }
+        mbar_wait(st_full, ph);
+        tc_fence_after();
+        mbar_wait(mma2_done, ph ^ 1);                            // previous P^T / dS^T tiles consumed by their MMAs
+#pragma unroll 1
+        for (int c = 0; c < TB; c += 32) {
+          uint32_t vs[32], vp[32];
+          tmem_ld_32x32(tSt + lane_off + c, vs);
+          tmem_ld_32x32(tdPt + lane_off + c, vp);
+          tmem_ld_wait();
+          float pt[32], ds[32];
+#pragma unroll
+          for (int x = 0; x < 32; ++x) {
+            const int qi = q0 + c + x;
+            float val = key_ok ? __uint_as_float(vs[x]) * sl2 : -INFINITY;
+            if (p.causal && key > qi) val = -INFINITY;
+            const float pr = exp2f(val - sLse[c + x]);             // lse = +inf (padding / fully masked query) -> 0
+            pt[x] = pr;
+            ds[x] = pr * (__uint_as_float(vp[x]) - sDelta[c + x]) * p.scale;
+          }
+          unsigned char* hp = sPt + (c >> 6) * HALF_BYTES;
+          unsigned char* hd = sdSt + (c >> 6) * HALF_BYTES;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            st_sw128(hp, r, ((c & 63) >> 3) + g, pack8(pt + g * 8));
+            st_sw128(hd, r, ((c & 63) >> 3) + g, pack8(ds + g * 8));
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(pt_ready);
+      }
+    }
+    // all dV / dK MMAs retired -> drain the accumulators
+    mbar_wait(mma2_done, (n_iter - 1) & 1);
+    tc_fence_after();
+    {
+      // tcgen05.ld is warp-collective (.sync.aligned): every lane issues the loads, only rows < L store
+      const bool st_ok = key < L;
+      __nv_bfloat16* dvrow = p.dv + (size_t)(tok0 + (st_ok ? key : 0)) * p.lddv + (size_t)hk * TD;
+      __nv_bfloat16* dkrow = p.dk + (size_t)(tok0 + (st_ok ? key : 0)) * p.lddk + (size_t)hk * TD;
+#pragma unroll 1
+      for (int c = 0; c < TD; c += 32) {
+        uint32_t v[32]; float f[32];
+        tmem_ld_32x32(tdV + lane_off + c, v);
+        tmem_ld_wait();
+        if (st_ok) {
+#pragma unroll
+          for (int x = 0; x < 32; ++x) f[x] = __uint_as_float(v[x]);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) *reinterpret_cast<bf16x8*>(dvrow + c + g * 8) = pack8(f + g * 8);
+        }
+        tmem_ld_32x32(tdK + lane_off + c, v);
+        tmem_ld_wait();
+        if (st_ok) {
+#pragma unroll
+          for (int x = 0; x < 32; ++x) f[x] = __uint_as_float(v[x]);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) *reinterpret_cast<bf16x8*>(dkrow + c + g * 8) = pack8(f + g * 8);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ============================================================================================================
+// backward dQ: grid (ceil(L/128) query tiles, Hq, B); thread = query row; dQ accumulates in TMEM over the key tiles
+// ============================================================================================================
+__global__ void __launch_bounds__(160, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                      const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                      const AttnTcParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sQ = smem;
+  unsigned char* sdO = sQ + TILE_BYTES;
+  unsigned char* sK = sdO + TILE_BYTES;
+  unsigned char* sV = sK + TILE_BYTES;
+  unsigned char* sdS = sV + TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + TILE_BYTES);
+  uint64_t *qdo_full = bars, *kv_full = bars + 1, *s_full = bars + 2, *ds_ready = bars + 3, *mma2_done = bars + 4;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
+  float* sMask = reinterpret_cast<float*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int hk = h / (p.Hq / p.Hkv);
+  const int L = p.L, q0 = qb * TB, tok0 = b * L;
+  const int nkv = p.causal ? (min(L, q0 + TB) + TB - 1) / TB : (L + TB - 1) / TB;
+
+  if (threadIdx.x == 128) {
+    mbar_init(qdo_full, 1); mbar_init(kv_full, 1); mbar_init(s_full, 1); mbar_init(ds_ready, 128); mbar_init(mma2_done, 1);
+    fence_mbar_init();
+    prefetch_tmap(&tm_q); prefetch_tmap(&tm_k); prefetch_tmap(&tm_v); prefetch_tmap(&tm_do);
+  }
+  if (warp == 0) { tmem_alloc(tmem_holder, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(qdo_full, 2 * TILE_BYTES);
+      tma_load_2d(sQ, &tm_q, qdo_full, p.qcol0 + h * TD, tok0 + q0);
+      tma_load_2d(sQ + HALF_BYTES, &tm_q, qdo_full, p.qcol0 + h * TD + 64, tok0 + q0);
+      tma_load_2d(sdO, &tm_do, qdo_full, p.ocol0 + h * TD, tok0 + q0);
+      tma_load_2d(sdO + HALF_BYTES, &tm_do, qdo_full, p.ocol0 + h * TD + 64, tok0 + q0);
+      constexpr uint32_t idesc_kk = make_idesc_bf16(TB, TB);
+      constexpr uint32_t idesc_mn = make_idesc_bf16_bmn(TB, TD);
+      const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV), aDS = smem_u32(sdS);
+      for (int j = 0; j < nkv; ++j) {
+        const uint32_t ph = j & 1;
+        mbar_wait(mma2_done, ph ^ 1);                            // previous dQ MMAs consumed K (and dS)
+        mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
+        tma_load_2d(sK, &tm_k, kv_full, p.kcol0 + hk * TD, tok0 + j * TB);
+        tma_load_2d(sK + HALF_BYTES, &tm_k, kv_full, p.kcol0 + hk * TD + 64, tok0 + j * TB);
+        tma_load_2d(sV, &tm_v, kv_full, p.vcol0 + hk * TD, tok0 + j * TB);
+        tma_load_2d(sV + HALF_BYTES, &tm_v, kv_full, p.vcol0 + hk * TD + 64, tok0 + j * TB);
+        if (j == 0) mbar_wait(qdo_full, 0);
+        mbar_wait(kv_full, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma_f16(tS, kmajor_desc(aQ, kk), kmajor_desc(aK, kk), idesc_kk, kk != 0);      // S  = Q K^T
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma_f16(tdP, kmajor_desc(aDO, kk), kmajor_desc(aV, kk), idesc_kk, kk != 0);    // dP = dO V^T
+        umma_commit(s_full);
+        mbar_wait(ds_ready, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma_f16(tdQ, kmajor_desc(aDS, kk), mnmajor_desc(aK, kk), idesc_mn, (j | kk) != 0);   // dQ += dS K
+        umma_commit(mma2_done);
+      }
+    }
+  } else {
+    const int r = warp * 32 + lane;
+    const int qrow = q0 + r;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    const size_t idx = ((size_t)b * p.Hq + h) * L + qrow;
+    const float lse2 = qrow < L ? p.lse[idx] * 1.4426950408889634f : INFINITY;
+    const float dl = qrow < L ? p.delta[idx] : 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      const uint32_t ph = j & 1;
+      const int kv0 = j * TB;
+      {
+        const int key = kv0 + r;
+        bool keep = key < L;
+        if (keep && p.mask) keep = p.mask[(size_t)tok0 + key] != 0;
+        named_bar_sync(1, 128);
+        sMask[r] = keep ? 0.f : -INFINITY;
+        named_bar_sync(1, 128);
+      }
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      mbar_wait(mma2_done, ph ^ 1);                              // previous dS tile consumed
+#pragma unroll 1
+      for (int c = 0; c < TB; c += 32) {
+        uint32_t vs[32], vp[32];
+        tmem_ld_32x32(tS + lane_off + c, vs);
+        tmem_ld_32x32(tdP + lane_off + c, vp);
+        tmem_ld_wait();
+        float ds[32];
+#pragma unroll
+        for (int x = 0; x < 32; ++x) {
+          float val = __uint_as_float(vs[x]) * sl2 + sMask[c + x];
+          if (p.causal && (kv0 + c + x) > qrow) val = -INFINITY;
+          const float pr = exp2f(val - lse2);
+          ds[x] = pr * (__uint_as_float(vp[x]) - dl) * p.scale;
+        }
+        unsigned char* hd = sdS + (c >> 6) * HALF_BYTES;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) st_sw128(hd, r, ((c & 63) >> 3) + g, pack8(ds + g * 8));
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(ds_ready);
+    }
+    mbar_wait(mma2_done, (nkv - 1) & 1);
+    tc_fence_after();
+    __nv_bfloat16* dqrow = p.dq + (size_t)(tok0 + (qrow < L ? qrow : 0)) * p.lddq + (size_t)h * TD;
+#pragma unroll 1
+    for (int c = 0; c < TD; c += 32) {
+      uint32_t v[32]; float f[32];
+      tmem_ld_32x32(tdQ + lane_off + c, v);
+      tmem_ld_wait();
+      if (qrow < L) {
+#pragma unroll
+        for (int x = 0; x < 32; ++x) f[x] = __uint_as_float(v[x]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) *reinterpret_cast<bf16x8*>(dqrow + c + g * 8) = pack8(f + g * 8);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+constexpr int kDkvSmem = 6 * TILE_BYTES + 1024 + 2048;
+constexpr int kDqSmem = 5 * TILE_BYTES + 1024 + 1024;
+constexpr int kFwdSmem = 3 * TILE_BYTES + 1024 + 1024;
 
 }  // namespace dalm
 
@@ -246,4 +578,44 @@ extern "C" int dalm_b200_attention_tc_fwd(const void* q, long long ldq, long lon
   attn_fwd_tc_kernel<<<grid, 160, kFwdSmem, (cudaStream_t)stream>>>(mq, mk, mv, p);
   count_launch();
   return check_launch("attn_fwd_tc_kernel");
+}
+
+// backward: d_out bf16 [B*L, Hq*128 (docols)], delta: fp32 workspace [B,Hq,L]; dq/dk/dv bf16 token-major outputs
+extern "C" int dalm_b200_attention_tc_bwd(const void* q, long long ldq, long long qcols, const void* k, long long ldk,
+                                          long long kcols, const void* v, long long ldv, long long vcols,
+                                          const int64_t* mask, const void* out, long long ldo, const float* lse,
+                                          const void* d_out, long long lddo, long long docols, float* delta, void* dq,
+                                          long long lddq, void* dk, long long lddk, void* dv, long long lddv, int B, int L,
+                                          int Hq, int Hkv, int D, float scale, int causal, void* stream) {
+  DALM_REQUIRE(D == 128, "attention_tc_bwd: head_dim must be 128 (got %d)", D);
+  DALM_REQUIRE(B > 0 && L > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0, "attention_tc_bwd: bad shape");
+  DALM_REQUIRE((lddq % 8) == 0 && (lddk % 8) == 0 && (lddv % 8) == 0 && (ldo % 4) == 0 && (lddo % 4) == 0, "attention_tc_bwd: strides");
+  DALM_REQUIRE(((uintptr_t)dq & 15) == 0 && ((uintptr_t)dk & 15) == 0 && ((uintptr_t)dv & 15) == 0, "attention_tc_bwd: output alignment");
+  CUtensorMap mq, mk, mv, mdo;
+  const long long rows = (long long)B * L;
+  if (int e = tc_maps(q, rows, qcols, ldq, &mq)) return e;
+  if (int e = tc_maps(k, rows, kcols, ldk, &mk)) return e;
+  if (int e = tc_maps(v, rows, vcols, ldv, &mv)) return e;
+  if (int e = tc_maps(d_out, rows, docols, lddo, &mdo)) return e;
+  AttnTcParams p{};
+  p.mask = mask; p.lse = const_cast<float*>(lse); p.delta = delta; p.B = B; p.L = L; p.Hq = Hq; p.Hkv = Hkv;
+  p.scale = scale; p.causal = causal;
+  p.dq = (__nv_bfloat16*)dq; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv; p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr = false;
+  if (!attr) {
+    DALM_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkvSmem));
+    DALM_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem));
+    attr = true;
+  }
+  const int total_warps = B * L * Hq;
+  attn_tc_delta_kernel<<<(total_warps * 32 + 255) / 256, 256, 0, st>>>((const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)d_out,
+                                                                      lddo, delta, B, L, Hq);
+  if (int e = check_launch("attn_tc_delta_kernel")) return e;
+  const int ntiles = (L + TB - 1) / TB;
+  attn_bwd_dkv_tc_kernel<<<dim3(ntiles, Hkv, B), 160, kDkvSmem, st>>>(mq, mk, mv, mdo, p);
+  if (int e = check_launch("attn_bwd_dkv_tc_kernel")) return e;
+  attn_bwd_dq_tc_kernel<<<dim3(ntiles, Hq, B), 160, kDqSmem, st>>>(mq, mk, mv, mdo, p);
+  count_launch(3);
+  return check_launch("attn_bwd_dq_tc_kernel");
 }

@@ -167,9 +167,9 @@ class LlamaDecoder(torch.nn.Module):
                                 dropx=self._drop(ctx.training, ctx.call, li))
             a.qkv = ops.gemm(a.h1_aug, W["Wqkv_aug"])                            # [M, Nq+2Nkv]
             ops.rope_(a.qkv, 0, self.nh + self.nkv, self.hd, cos_t, sin_t, L)    # q heads then k heads are adjacent
-            a.att, a.lse = ops.attention_fwd(a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + self.Nkv],
-                                             a.qkv[:, self.Nq + self.Nkv:], ctx.mask, B, L, self.nh, self.nkv, self.hd,
-                                             causal=True)
+            attn_fwd = ops.attention_tc_fwd if self.hd == 128 else ops.attention_fwd     # tcgen05/TMEM path for head_dim 128
+            a.att, a.lse = attn_fwd(a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + self.Nkv],
+                                    a.qkv[:, self.Nq + self.Nkv:], ctx.mask, B, L, self.nh, self.nkv, self.hd, causal=True)
             a.x_mid = ops.gemm(a.att, W["Wo"], out_dtype=f32, resid=x)
             a.h2, a.rstd2 = ops.rmsnorm_fwd(a.x_mid, W["g2"], self.eps)
             a.gu = ops.gemm(a.h2, W["Wgu"])                                       # [M,2F]
@@ -205,10 +205,11 @@ class LlamaDecoder(torch.nn.Module):
             dmid32, dmid16 = ops.rmsnorm_bwd(a.x_mid, W["g2"], a.rstd2, dh2, dres_in=dx32)
             datt = ops.gemm(dmid16, W["WoT"])                                      # [M,Nq]
             dqkv = _aug_buf(M, self.Nqkv, Ra, self.dev)
-            ops.attention_bwd(a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + self.Nkv], a.qkv[:, self.Nq + self.Nkv:],
-                              ctx.mask, a.att, a.lse, datt, B, L, self.nh, self.nkv, self.hd, causal=True,
-                              dq=dqkv[:, :self.Nq], dk=dqkv[:, self.Nq:self.Nq + self.Nkv],
-                              dv=dqkv[:, self.Nq + self.Nkv:self.Nqkv])
+            attn_bwd = ops.attention_tc_bwd if self.hd == 128 else ops.attention_bwd
+            attn_bwd(a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + self.Nkv], a.qkv[:, self.Nq + self.Nkv:],
+                     ctx.mask, a.att, a.lse, datt, B, L, self.nh, self.nkv, self.hd, causal=True,
+                     dq=dqkv[:, :self.Nq], dk=dqkv[:, self.Nq:self.Nq + self.Nkv],
+                     dv=dqkv[:, self.Nq + self.Nkv:self.Nqkv])
             ops.rope_(dqkv, 0, self.nh + self.nkv, self.hd, cos_t, sin_t, L, backward=True)
             names = [f"model.layers.{l}.self_attn.{n}" for n in self.LORA_TARGETS]
             for j, n in enumerate(self.LORA_TARGETS):

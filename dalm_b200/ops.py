@@ -229,6 +229,21 @@ def attention_tc_fwd(q, k, v, mask, B: int, L: int, Hq: int, Hkv: int, D: int, c
     return out, lse
 
 
+def attention_tc_bwd(q, k, v, mask, out, lse, d_out, B: int, L: int, Hq: int, Hkv: int, D: int, causal: bool,
+                     dq=None, dk=None, dv=None, scale: Optional[float] = None):
+    """tcgen05/TMEM attention backward (head_dim 128). Same contract as attention_bwd."""
+    dev = q.device
+    if dq is None: dq = torch.empty(B * L, Hq * D, dtype=bf16, device=dev)
+    if dk is None: dk = torch.empty(B * L, Hkv * D, dtype=bf16, device=dev)
+    if dv is None: dv = torch.empty(B * L, Hkv * D, dtype=bf16, device=dev)
+    delta = torch.empty(B, Hq, L, dtype=f32, device=dev)
+    scale = 1.0 / math.sqrt(D) if scale is None else scale
+    _lib.call("dalm_b200_attention_tc_bwd", _p(q), _ld(q), q.shape[1], _p(k), _ld(k), k.shape[1], _p(v), _ld(v), v.shape[1],
+              _p(mask), _p(out), _ld(out), _p(lse), _p(d_out), _ld(d_out), d_out.shape[1], _p(delta), _p(dq), _ld(dq),
+              _p(dk), _ld(dk), _p(dv), _ld(dv), B, L, Hq, Hkv, D, float(scale), 1 if causal else 0, _stream())
+    return dq, dk, dv
+
+
 def attention_bwd(q, k, v, mask, out, lse, d_out, B: int, L: int, Hq: int, Hkv: int, D: int, causal: bool,
                   dq=None, dk=None, dv=None, scale: Optional[float] = None, drop: Optional[Drop] = None):
     dev = q.device

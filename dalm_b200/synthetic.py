@@ -25,6 +25,8 @@ BERT_SHAPES: Dict[str, Dict] = {
 LLAMA_SHAPES: Dict[str, Dict] = {
     "llama-tiny": dict(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=2,
                        intermediate_size=256),
+    "llama-hd128": dict(hidden_size=256, num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=2,
+                        intermediate_size=512),
     "llama-mini": dict(hidden_size=512, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=4,
                        intermediate_size=1408),
     "Llama-2-7b-hf": dict(hidden_size=4096, num_hidden_layers=32, num_attention_heads=32, num_key_value_heads=32,

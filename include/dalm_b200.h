@@ -89,6 +89,12 @@ int dalm_b200_attention_tc_fwd(const void* q, long long ldq, long long qcols, in
                                const int64_t* mask, void* out, long long ldo, float* lse, int B, int L, int Hq, int Hkv,
                                int D, float scale, int causal, void* stream);
 
+int dalm_b200_attention_tc_bwd(const void* q, long long ldq, long long qcols, const void* k, long long ldk, long long kcols,
+                               const void* v, long long ldv, long long vcols, const int64_t* mask, const void* out,
+                               long long ldo, const float* lse, const void* d_out, long long lddo, long long docols,
+                               float* delta, void* dq, long long lddq, void* dk, long long lddk, void* dv, long long lddv,
+                               int B, int L, int Hq, int Hkv, int D, float scale, int causal, void* stream);
+
 /* ---- row-wise pieces of the encoder / decoder blocks ---- */
 int dalm_b200_layernorm_fwd(const float* z, const float* gamma, const float* beta, float* y32, void* y16, long long ld16,
                             float* mean, float* rstd, int M, int H, float eps, float drop_p, unsigned long long drop_seed,

@@ -63,7 +63,8 @@ def test_bert_encoder_fwd_bwd(cuda_dev, name, B, L):
     assert worst < 5e-2, worst
 
 
-@pytest.mark.parametrize("name,B,L,pad", [("llama-tiny", 3, 24, "right"), ("llama-tiny", 2, 40, "left"), ("llama-mini", 2, 64, "right")])
+@pytest.mark.parametrize("name,B,L,pad", [("llama-tiny", 3, 24, "right"), ("llama-tiny", 2, 40, "left"), ("llama-mini", 2, 64, "right"),
+                                           ("llama-hd128", 2, 150, "right"), ("llama-hd128", 2, 72, "left")])
 def test_llama_decoder_fwd_bwd(cuda_dev, name, B, L, pad):
     from dalm_b200 import ops, synthetic
     from dalm_b200.engine import params
