@@ -297,6 +297,7 @@ def main():
     if rank != 0:
         if world > 1:
             dist.barrier()
+            dist.destroy_process_group()
         return
     peaks = {}
     try:
@@ -331,7 +332,7 @@ def main():
                      "note": "achieved = sum of 2MNK over all GEMM launches / sum of their CUDA-event durations in the timed region"},
         "clocks": sampler.summary() if sampler else None,
     }
-    if args.cpu_baseline:
+    if args.cpu_baseline and world == 1:                     # reported CPU baseline: rank 0, N=1 only
         try:
             v, cores, desc = cpu_reference_samples_per_s(host_batches[0])
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc}
@@ -341,6 +342,7 @@ def main():
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -144,7 +144,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       mbar_wait(s_full, ph);
       tc_fence_after();
       // pass 1: row maximum
-      float mx = -INFINITY;
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};      // 4 independent chains (ILP)
 #pragma unroll 1
       for (int c = 0; c < TB; c += 32) {
         uint32_t v[32];
@@ -154,15 +154,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         for (int i = 0; i < 32; ++i) {
           float val = __uint_as_float(v[i]) * sl2 + sMask[c + i];
           if (p.causal && (kv0 + c + i) > qrow) val = -INFINITY;
-          mx = fmaxf(mx, val);
+          mx4[i & 3] = fmaxf(mx4[i & 3], val);
         }
       }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m_run, mx);
       const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
       const float corr = exp2f(m_run - m_safe);
       m_run = m_new;
       // pass 2: P = exp2(S - m) -> bf16 -> swizzled smem (A operand of P V), row sum
-      float rs = 0.f;
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c = 0; c < TB; c += 32) {
         uint32_t v[32];
@@ -177,12 +178,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             float val = __uint_as_float(v[g * 8 + i]) * sl2 + sMask[c + g * 8 + i];
             if (p.causal && (kv0 + c + g * 8 + i) > qrow) val = -INFINITY;
             pv[i] = exp2f(val - m_safe);
-            rs += pv[i];
+            rs4[i & 3] += pv[i];
           }
           st_sw128(half, r, ((c & 63) >> 3) + g, pack8(pv));
         }
       }
-      l_run = l_run * corr + rs;
+      l_run = l_run * corr + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(p_ready);

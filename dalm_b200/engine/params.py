@@ -70,6 +70,23 @@ def random_state_dict(kind: str, cfg: Dict, seed: int = 0, dtype=torch.float32, 
             sd[p + "post_attention_layernorm.weight"] = ones(H) + _normal(gen, (H,), std, dtype, device)
         sd["model.norm.weight"] = ones(H) + _normal(gen, (H,), std, dtype, device)
         sd["lm_head.weight"] = _normal(gen, (V, H), std, dtype, device)
+    elif kind == "falcon":
+        V = cfg["vocab_size"]
+        nh = cfg["num_attention_heads"]
+        hd = H // nh
+        F = cfg.get("ffn_hidden_size") or 4 * H
+        sd["transformer.word_embeddings.weight"] = _normal(gen, (V, H), std, dtype, device)
+        for l in range(cfg["num_hidden_layers"]):
+            p = f"transformer.h.{l}."
+            sd[p + "input_layernorm.weight"] = ones(H) + _normal(gen, (H,), std, dtype, device)
+            sd[p + "input_layernorm.bias"] = _normal(gen, (H,), std, dtype, device)
+            sd[p + "self_attention.query_key_value.weight"] = _normal(gen, ((nh + 2) * hd, H), std, dtype, device)
+            sd[p + "self_attention.dense.weight"] = _normal(gen, (H, H), std, dtype, device)
+            sd[p + "mlp.dense_h_to_4h.weight"] = _normal(gen, (F, H), std, dtype, device)
+            sd[p + "mlp.dense_4h_to_h.weight"] = _normal(gen, (H, F), std, dtype, device)
+        sd["transformer.ln_f.weight"] = ones(H) + _normal(gen, (H,), std, dtype, device)
+        sd["transformer.ln_f.bias"] = _normal(gen, (H,), std, dtype, device)
+        # lm_head is tied to the word embeddings (tie_word_embeddings=True): not stored separately
     else:
         raise ValueError(f"unknown model kind {kind!r}")
     return sd
@@ -102,5 +119,7 @@ def model_kind(cfg: Dict) -> str:
         return "bert"
     if mt == "llama":
         return "llama"
+    if mt == "falcon":
+        return "falcon"
     raise NotImplementedError(
-        f"model_type {mt!r} is not built yet in dalm_b200 (supported: bert encoders, llama decoders); see DESIGN.md")
+        f"model_type {mt!r} is not built in dalm_b200 (supported: bert encoders; llama and falcon decoders); see DESIGN.md")

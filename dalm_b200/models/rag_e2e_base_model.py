@@ -15,6 +15,7 @@ from .. import ops
 from ..engine import params
 from ..engine.bert import BertEncoder
 from ..engine.bridge import EncodeFn, GenerateFn, PoolFn
+from ..engine.falcon import FalconDecoder
 from ..engine.llama import LlamaDecoder
 
 logger = logging.getLogger(__name__)
@@ -51,8 +52,12 @@ def build_encoder(name_or_path: str, lora: bool, device: torch.device, state_dic
 def build_decoder(name_or_path: str, lora: bool, device: torch.device, state_dict: Optional[Dict] = None,
                   cfg: Optional[Dict] = None) -> LlamaDecoder:
     cfg = cfg or params.load_config(name_or_path)
-    params.model_kind(cfg)                       # raises for unsupported families (e.g. falcon: DESIGN.md "next")
+    kind = params.model_kind(cfg)                # raises for unsupported families
     sd = state_dict if state_dict is not None else params.load_state_dict(name_or_path)
+    if kind == "falcon":
+        return FalconDecoder(cfg, sd, device=device, lora=lora)       # raises for lora=True, like peft would
+    if kind != "llama":
+        raise NotImplementedError(f"generator of kind {kind!r} is not a causal decoder")
     return LlamaDecoder(cfg, sd, device=device, lora=lora)
 
 

@@ -34,6 +34,23 @@ LLAMA_SHAPES: Dict[str, Dict] = {
 }
 
 
+FALCON_SHAPES: Dict[str, Dict] = {
+    "falcon-tiny": dict(hidden_size=128, num_hidden_layers=2, num_attention_heads=2),
+    "falcon-mini": dict(hidden_size=448, num_hidden_layers=2, num_attention_heads=7),          # 7 q heads x 64, one KV head
+    "falcon-7b": dict(hidden_size=4544, num_hidden_layers=32, num_attention_heads=71),
+}
+
+
+def falcon_config(name: str, vocab_size: int = 65024) -> Dict:
+    s = FALCON_SHAPES[name]
+    return dict(
+        architectures=["FalconForCausalLM"], model_type="falcon", vocab_size=vocab_size, alibi=False,
+        new_decoder_architecture=False, multi_query=True, parallel_attn=True, bias=False, layer_norm_epsilon=1e-5,
+        rope_theta=10000.0, hidden_dropout=0.0, attention_dropout=0.0, initializer_range=0.02, bos_token_id=11,
+        eos_token_id=11, tie_word_embeddings=True, ffn_hidden_size=4 * s["hidden_size"], **s,
+    )
+
+
 def bert_config(name: str, vocab_size: int = 30522) -> Dict:
     s = BERT_SHAPES[name]
     return dict(
@@ -174,6 +191,9 @@ def write_model_dir(out_dir: str, kind: str, name: str, vocab_size: Optional[int
     elif kind == "llama":
         cfg = llama_config(name, vocab_size or 32000)
         build_llama_tokenizer(out_dir, cfg["vocab_size"])
+    elif kind == "falcon":
+        cfg = falcon_config(name, vocab_size or 65024)
+        build_llama_tokenizer(out_dir, cfg["vocab_size"])       # any causal-LM tokenizer works for the synthetic fixture
     else:
         raise ValueError(kind)
     with open(os.path.join(out_dir, "config.json"), "w") as f:

@@ -75,6 +75,17 @@ def build_llama(cfg: Dict, state_dict: Dict[str, torch.Tensor]) -> nn.Module:
     return m.float().eval()
 
 
+def build_falcon(cfg: Dict, state_dict: Dict[str, torch.Tensor]) -> nn.Module:
+    from transformers import FalconConfig, FalconForCausalLM
+
+    c = FalconConfig(**{k: v for k, v in cfg.items() if k not in ("architectures", "model_type")})
+    m = FalconForCausalLM(c)
+    sd = {k: v.float() for k, v in state_dict.items()}
+    sd.setdefault("lm_head.weight", sd["transformer.word_embeddings.weight"])          # tied
+    m.load_state_dict(sd, strict=True)
+    return m.float().eval()
+
+
 def retrieval_forward(bert: nn.Module, ids: torch.Tensor, mask: torch.Tensor, normalize: bool = True) -> torch.Tensor:
     """reference rag_e2e_base_model.py:83-99 (non-autoregressive branch): positional call => token_type_ids = 0"""
     tok = bert(ids, mask)[0]

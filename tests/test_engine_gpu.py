@@ -106,3 +106,35 @@ def test_llama_decoder_fwd_bwd(cuda_dev, name, B, L, pad):
         mod = om._get_module(ref, n)
         worst = max(worst, _rel(dec.lora.gA[n], mod.lora_A.grad), _rel(dec.lora.gB[n], mod.lora_B.grad))
     assert worst < 5e-2, worst
+
+
+@pytest.mark.parametrize("name,B,L,pad", [("falcon-tiny", 3, 40, "right"), ("falcon-mini", 2, 130, "left")])
+def test_falcon_decoder_forward(cuda_dev, name, B, L, pad):
+    """BASELINE config 5's generator family (parallel attention + MLP, MQA, LayerNorm, GELU, tied lm_head): logits and
+    the marginalised loss vs HF FalconForCausalLM; adapters are refused like peft would refuse them"""
+    from dalm_b200 import ops, synthetic
+    from dalm_b200.engine import params
+    from dalm_b200.engine.falcon import FalconDecoder
+    from oracle import models as om, losses
+    cfg = synthetic.falcon_config(name, vocab_size=504)
+    sd = params.random_state_dict("falcon", cfg, seed=4)
+    sd = {k: (v.to(bf16).float() if v.dim() == 2 else v) for k, v in sd.items()}
+    dec = FalconDecoder(cfg, sd, device=cuda_dev)
+    with pytest.raises(ValueError):
+        FalconDecoder(cfg, sd, device=cuda_dev, lora=True)
+    ref = om.build_falcon(cfg, sd)
+    g = torch.Generator().manual_seed(6)
+    ids = torch.randint(3, 504, (B, L), generator=g)
+    mask = torch.ones(B, L, dtype=torch.int64)
+    if pad == "right": mask[0, L - 7:] = 0
+    else: mask[0, :6] = 0
+    logits, _ = dec.forward_logits(ids.to(cuda_dev), mask.to(cuda_dev))
+    with torch.no_grad():
+        ref_logits = ref(input_ids=ids, attention_mask=mask).logits
+    valid = mask.bool()
+    assert _rel(logits.float().cpu()[valid], ref_logits[valid]) < 1.5e-2
+    S = torch.randn(B, B, generator=g) * 3
+    qlen = torch.tensor([3, L // 2, L + 2][:B])
+    want = losses.marginalized_loss_loopform(ref_logits, ids, mask, S, qlen)
+    got = losses.marginalized_loss_loopform(logits.float().cpu(), ids, mask, S, qlen)
+    assert abs(got.item() - want.item()) / abs(want.item()) < 1e-3

@@ -168,3 +168,38 @@ def test_trainers_end_to_end_on_toy_csv(cuda_dev, tmp_path):
     train_retriever(rdir, csv, per_device_train_batch_size=2, query_max_len=16, passage_max_len=32, num_train_epochs=1,
                     output_dir=out2, use_peft=True, use_bnb=False, with_tracking=False)
     assert os.path.exists(os.path.join(out2, "retriever", "adapter_model.bin"))
+
+
+def test_fused_step_with_frozen_falcon_generator(cuda_dev):
+    """BASELINE config 5 family at toy size: bge encoder with LoRA (use_peft='retriever') + frozen Falcon generator. The LM
+    loss reaches the retriever only through the doc log-prob term; generator backward is never launched."""
+    from dalm_b200 import synthetic, _lib
+    from dalm_b200.engine import params
+    from dalm_b200.engine.bert import BertEncoder
+    from dalm_b200.engine.falcon import FalconDecoder
+    from dalm_b200.models.rag_e2e_base_model import AutoModelForRagE2E, Mode
+    from dalm_b200.training.utils.train_utils import fused_rag_step
+    from oracle import models as om
+    bcfg, fcfg = synthetic.bert_config("bge-tiny", 600), synthetic.falcon_config("falcon-tiny", 504)
+    r16 = lambda sd: {k: (v.to(bf16).float() if v.dim() == 2 else v) for k, v in sd.items()}
+    bsd, fsd = r16(params.random_state_dict("bert", bcfg, seed=21)), r16(params.random_state_dict("falcon", fcfg, seed=22))
+    enc, dec = BertEncoder(bcfg, bsd, device=cuda_dev, lora=True), FalconDecoder(fcfg, fsd, device=cuda_dev)
+    g = torch.Generator().manual_seed(23)
+    for n, _, _ in enc.lora.specs:
+        enc.lora.B[n].copy_((torch.randn(enc.lora.B[n].shape, generator=g) * 0.02).to(cuda_dev))
+    enc.repack_lora()
+    model = AutoModelForRagE2E("", "", get_peft=Mode.RETRIEVER, _retriever=enc, _generator=dec, _load_tokenizers=False)
+    batch = _batch(4, 10, 20, 48, 600, 504, seed=24)
+    bert, falcon = om.build_bert(bcfg, bsd), om.build_falcon(fcfg, fsd)
+    om.attach_lora(bert, {n: {"A": enc.lora.A[n].cpu(), "B": enc.lora.B[n].cpu()} for n, _, _ in enc.lora.specs})
+    for p_ in falcon.parameters():
+        p_.requires_grad_(False)
+    ref = om.rag_step(bert, falcon, batch)
+    enc.lora.zero_grad()
+    out = fused_rag_step(model, batch, 100.0)
+    assert abs(out["loss"].item() - ref["loss"].item()) / abs(ref["loss"].item()) < 1e-3
+    worst = 0.0
+    for n, _, _ in enc.lora.specs:
+        worst = max(worst, _rel(enc.lora.gA[n], ref["grads"]["retriever." + n + ".lora_A"]),
+                    _rel(enc.lora.gB[n], ref["grads"]["retriever." + n + ".lora_B"]))
+    assert worst < 6e-2, worst
