@@ -117,7 +117,9 @@ def cpu_reference_samples_per_s(batch, steps: int = 1, rows: int = 6):
     from dalm_b200.engine import params
     from oracle import models as om
 
-    cores = os.cpu_count() or 1
+    # torch's CPU GEMMs stop scaling (and regress badly) long before 128 threads on these hosts: measured 0.013 samples/s
+    # with 128 threads vs 0.157 with 8; use up to 32 threads and report that count as `cores`
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     bcfg = dict(synthetic.bert_config("bge-large-en")); lcfg = dict(synthetic.llama_config("Llama-2-7b-hf"))
     batch = {k: v[:rows].clone() for k, v in batch.items()}
