@@ -13,10 +13,11 @@ class EncodeFn(torch.autograd.Function):
     LoRA bank's gradient buffer), so backward returns None for it."""
 
     @staticmethod
-    def forward(ctx, anchor, enc, ids, mask, normalize):
+    def forward(ctx, anchor, enc, ids, mask, normalize, pool_mask=None):
         hid, c = enc.forward_hidden(ids, mask, save=True)
-        emb, norm = ops.pool_norm_fwd(hid, mask, normalize)
-        ctx.enc, ctx.c, ctx.mask, ctx.normalize, ctx.L = enc, c, mask, normalize, ids.shape[1]
+        pm = mask if pool_mask is None else pool_mask          # autoregressive retrievers pool with the eos one-hot mask
+        emb, norm = ops.pool_norm_fwd(hid, pm, normalize)
+        ctx.enc, ctx.c, ctx.mask, ctx.normalize, ctx.L = enc, c, pm, normalize, ids.shape[1]
         ctx.save_for_backward(emb, norm)
         return emb
 
@@ -26,7 +27,7 @@ class EncodeFn(torch.autograd.Function):
         d_hid = ops.pool_norm_bwd(emb, norm, d_emb.contiguous().float(), ctx.mask, ctx.L, ctx.normalize)
         ctx.enc.backward_hidden(ctx.c, d_hid)
         ctx.c = None
-        return None, None, None, None, None
+        return None, None, None, None, None, None
 
 
 class GenerateFn(torch.autograd.Function):

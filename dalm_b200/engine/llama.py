@@ -63,7 +63,7 @@ class LlamaDecoder(torch.nn.Module):
         g = lambda k, dt: sd[k].to(device=self.dev, dtype=dt).contiguous()
         self.embed = g("model.embed_tokens.weight", bf16)
         self.norm_g = g("model.norm.weight", f32)
-        lm = g("lm_head.weight", bf16) if "lm_head.weight" in sd else self.embed
+        lm = g("lm_head.weight", bf16) if "lm_head.weight" in sd else self.embed      # tied / headless (AutoModel) checkpoints
         self.Vp = (self.V + 7) // 8 * 8                       # GEMM N granularity; extra rows are zero and never scored
         if self.Vp != self.V:
             lm = torch.cat([lm, torch.zeros(self.Vp - self.V, H, dtype=bf16, device=self.dev)], 0)
@@ -150,6 +150,25 @@ class LlamaDecoder(torch.nn.Module):
     def forward_logits(self, ids: torch.Tensor, mask: torch.Tensor, save: bool = True):
         """ids, mask int64 [B,L] -> (logits bf16 [B,L,V], ctx)"""
         B, L = ids.shape
+        ctx = self._forward_body(ids, mask, save)
+        logits = ops.gemm(ctx.hf, self.lm_head)                                   # bf16 [M,Vp]
+        return logits.view(B, L, self.Vp)[:, :, :self.V], ctx
+
+    def forward_hidden(self, ids: torch.Tensor, mask: torch.Tensor, save: bool = True):
+        """last hidden state (after the final RMSNorm) as fp32 [B,L,H] — what `AutoModel(...)(..., output_hidden_states=True)
+        .hidden_states[-1]` gives the reference's autoregressive-retriever branch (rag_e2e_base_model.py:84-90)"""
+        B, L = ids.shape
+        ctx = self._forward_body(ids, mask, save)
+        return ctx.hf.float().view(B, L, self.H), ctx
+
+    def backward_hidden(self, ctx: _Ctx, d_hidden: torch.Tensor) -> None:
+        """gradient w.r.t. the last hidden state (fp32 [B,L,H]) -> LoRA gradients"""
+        if self.lora is None:
+            return
+        self._backward_body(ctx, ops.cast_f32_bf16(d_hidden.reshape(ctx.B * ctx.L, self.H).contiguous()))
+
+    def _forward_body(self, ids: torch.Tensor, mask: torch.Tensor, save: bool = True):
+        B, L = ids.shape
         M, H, F, Ra = B * L, self.H, self.F, self.Ra
         cos_t, sin_t = self._rope(L)
         ctx = _Ctx()
@@ -179,8 +198,7 @@ class LlamaDecoder(torch.nn.Module):
                 ctx.layers.append(a)
         ctx.x_final = x
         ctx.hf, ctx.rstdf = ops.rmsnorm_fwd(x, self.norm_g, self.eps)
-        logits = ops.gemm(ctx.hf, self.lm_head)                                   # bf16 [M,Vp]
-        return logits.view(B, L, self.Vp)[:, :, :self.V], ctx
+        return ctx
 
     # ------------------------------------------------------------------------------------------------------------
     def backward_logits(self, ctx: _Ctx, dlogits: torch.Tensor) -> None:
@@ -195,7 +213,13 @@ class LlamaDecoder(torch.nn.Module):
             pad[:, :, :self.V] = dlogits
             dlogits = pad
         dl2 = torch.as_strided(dlogits, (M, self.Vp), (self.Vp, 1), dlogits.storage_offset())
-        dhf = ops.gemm(dl2, self.lm_headT)                                         # [M,H]
+        self._backward_body(ctx, ops.gemm(dl2, self.lm_headT))                     # dhf [M,H]
+
+    def _backward_body(self, ctx: _Ctx, dhf: torch.Tensor) -> None:
+        """from the gradient of the final-norm output (bf16 [M,H]) down through the layers"""
+        B, L = ctx.B, ctx.L
+        M, H, F, Ra, r = B * L, self.H, self.F, self.Ra, self.r
+        cos_t, sin_t = self._rope(L)
         dx32, dx16 = ops.rmsnorm_bwd(ctx.x_final, self.norm_g, ctx.rstdf, dhf)
         for l in range(self.nl - 1, -1, -1):
             W, a = self.layers[l], ctx.layers[l]

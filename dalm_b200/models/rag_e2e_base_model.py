@@ -40,13 +40,29 @@ def load_tokenizer(name_or_path: str):
 
 
 def build_encoder(name_or_path: str, lora: bool, device: torch.device, state_dict: Optional[Dict] = None,
-                  cfg: Optional[Dict] = None) -> BertEncoder:
+                  cfg: Optional[Dict] = None, autoregressive: bool = False):
+    """BERT-family encoder (bge-*), or — `retriever_is_autoregressive` — a Llama-family decoder used as an encoder
+    (last hidden state, eos pooling; LoRA targets q_proj / v_proj: reference rag_e2e_base_model.py:66-70,84-90)"""
     cfg = cfg or params.load_config(name_or_path)
-    if params.model_kind(cfg) != "bert":
-        raise NotImplementedError("retriever must be a BERT-family encoder (bge-*) in this build; autoregressive "
-                                  "retrievers are listed as 'next' in DESIGN.md")
+    kind = params.model_kind(cfg)
     sd = state_dict if state_dict is not None else params.load_state_dict(name_or_path)
+    if autoregressive:
+        if kind != "llama":
+            raise NotImplementedError("autoregressive retrievers are built for Llama-family models only")
+        return LlamaDecoder(cfg, sd, device=device, lora=lora, lora_seed=0)
+    if kind != "bert":
+        raise NotImplementedError("non-autoregressive retrievers must be BERT-family encoders (bge-*); pass "
+                                  "retriever_is_autoregressive=True for a causal LM")
     return BertEncoder(cfg, sd, device=device, lora=lora)
+
+
+def pooling_mask(attention_mask: torch.Tensor, autoregressive: bool) -> torch.Tensor:
+    """mask used by mean_pooling: the attention mask, or for autoregressive retrievers `eos_mask(attention_mask)` (one-hot
+    at the last column, reference dalm/utils.py:22-35 default padding='left') so the pool picks the final token"""
+    if not autoregressive:
+        return attention_mask
+    from ..utils import eos_mask
+    return eos_mask(attention_mask)
 
 
 def build_decoder(name_or_path: str, lora: bool, device: torch.device, state_dict: Optional[Dict] = None,
@@ -79,8 +95,6 @@ class AutoModelForRagE2E(torch.nn.Module):
         if use_bnb is not None:
             raise NotImplementedError("use_bnb (bitsandbytes NF4) is outside BASELINE.json's configs (bf16 forward); "
                                       "not built — see DESIGN.md")
-        if retriever_is_autoregressive:
-            raise NotImplementedError("retriever_is_autoregressive is not built yet — see DESIGN.md")
         get_peft = Mode(get_peft) if get_peft is not None else None
         dev = _device()
         lora_r = get_peft in (Mode.RETRIEVER, Mode.BOTH)
@@ -88,9 +102,13 @@ class AutoModelForRagE2E(torch.nn.Module):
         if not (lora_r and lora_g):
             logger.warning("dalm_b200 trains LoRA adapters only (PEFT mode); sub-models without adapters are frozen. "
                            "Full fine-tuning (reference default use_peft=None) is not built yet — see DESIGN.md")
-        self.retriever_model = _retriever if _retriever is not None else build_encoder(retriever_name, lora_r, dev)
+        self.retriever_model = (_retriever if _retriever is not None else
+                                build_encoder(retriever_name, lora_r, dev, autoregressive=retriever_is_autoregressive))
         self.generator_model = _generator if _generator is not None else build_decoder(generator_name, lora_g, dev)
         self.retriever_tokenizer = load_tokenizer(retriever_name) if _load_tokenizers else None
+        if retriever_is_autoregressive and self.retriever_tokenizer is not None:                   # reference :41-44
+            self.retriever_tokenizer.add_eos_token = True
+            self.retriever_tokenizer.pad_token = self.retriever_tokenizer.eos_token
         self.generator_tokenizer = load_tokenizer(generator_name) if _load_tokenizers else None
         self.normalize = normalize
         self.retriever_is_autoregressive = retriever_is_autoregressive
@@ -100,10 +118,11 @@ class AutoModelForRagE2E(torch.nn.Module):
         enc = self.retriever_model
         ids = input_ids.to(enc.dev, torch.int64).contiguous()
         mask = attention_mask.to(enc.dev, torch.int64).contiguous()
+        pm = pooling_mask(mask, self.retriever_is_autoregressive).contiguous()
         if enc.lora is not None and torch.is_grad_enabled():
-            return EncodeFn.apply(enc.lora_flat, enc, ids, mask, self.normalize)
+            return EncodeFn.apply(enc.lora_flat, enc, ids, mask, self.normalize, pm)
         hid, _ = enc.forward_hidden(ids, mask, save=False)
-        emb, _ = ops.pool_norm_fwd(hid, mask, self.normalize)
+        emb, _ = ops.pool_norm_fwd(hid, pm, self.normalize)
         return emb
 
     # ---- reference :101-106 -----------------------------------------------------------------------------------

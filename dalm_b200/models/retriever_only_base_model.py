@@ -9,7 +9,7 @@ import torch
 from .. import ops
 from ..engine.bert import BertEncoder
 from ..engine.bridge import EncodeFn, PoolFn
-from .rag_e2e_base_model import _device, build_encoder, load_tokenizer
+from .rag_e2e_base_model import _device, build_encoder, load_tokenizer, pooling_mask
 
 logger = logging.getLogger(__name__)
 
@@ -23,12 +23,14 @@ class AutoModelForSentenceEmbedding(torch.nn.Module):
             # the reference defaults to use_bnb=True (:15); NF4 is outside BASELINE.json's configs. Accept the default
             # silently-but-logged instead of failing every default call; compute stays bf16.
             logger.warning("use_bnb=True requested: bitsandbytes NF4 is not built in dalm_b200; running bf16 weights")
-        if is_autoregressive:
-            raise NotImplementedError("is_autoregressive retrievers are not built yet — see DESIGN.md")
         if not get_peft:
             logger.warning("get_peft=False: full fine-tuning is not built yet; the encoder is frozen (see DESIGN.md)")
-        self.model = _model if _model is not None else build_encoder(model_name, bool(get_peft), _device())
+        self.model = _model if _model is not None else build_encoder(model_name, bool(get_peft), _device(),
+                                                                     autoregressive=is_autoregressive)
         self.tokenizer = load_tokenizer(model_name) if _load_tokenizer else None
+        if is_autoregressive and self.tokenizer is not None:                                          # reference :36-38
+            self.tokenizer.add_eos_token = True
+            self.tokenizer.pad_token = self.tokenizer.eos_token
         self.normalize = normalize
         self.is_autoregressive = is_autoregressive
 
@@ -36,10 +38,11 @@ class AutoModelForSentenceEmbedding(torch.nn.Module):
         enc = self.model
         ids = input_ids.to(enc.dev, torch.int64).contiguous()
         mask = attention_mask.to(enc.dev, torch.int64).contiguous()
+        pm = pooling_mask(mask, self.is_autoregressive).contiguous()
         if enc.lora is not None and torch.is_grad_enabled():
-            return EncodeFn.apply(enc.lora_flat, enc, ids, mask, self.normalize)
+            return EncodeFn.apply(enc.lora_flat, enc, ids, mask, self.normalize, pm)
         hid, _ = enc.forward_hidden(ids, mask, save=False)
-        emb, _ = ops.pool_norm_fwd(hid, mask, self.normalize)
+        emb, _ = ops.pool_norm_fwd(hid, pm, self.normalize)
         return emb
 
     def mean_pooling(self, model_output: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:  # :66-68

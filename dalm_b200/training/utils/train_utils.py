@@ -132,6 +132,26 @@ def compute_marginalized_loss_from_logits(logits: torch.Tensor, input_tensors: t
 # ----------------------------------------------------------------------------------------------------------------
 # fused loop bodies
 # ----------------------------------------------------------------------------------------------------------------
+def _encode_pair(enc, q_ids, q_mask, p_ids, p_mask, save: bool):
+    """hidden states of the query and passage batches + a closure running the encoder backward. BERT encoders take both
+    batches through the weights in ONE pass (segments); a causal-LM retriever runs them one after the other."""
+    if hasattr(enc, "forward_segments"):
+        (hq, hp), c = enc.forward_segments([(q_ids, q_mask), (p_ids, p_mask)], save=save)
+        return hq, hp, (lambda dq, dp: enc.backward_segments(c, [dq, dp]))
+    hq, cq = enc.forward_hidden(q_ids, q_mask, save=save)
+    hp, cp = enc.forward_hidden(p_ids, p_mask, save=save)
+
+    def bwd(dq, dp):
+        enc.backward_hidden(cp, dp)
+        enc.backward_hidden(cq, dq)
+    return hq, hp, bwd
+
+
+def _pool_masks(model, q_mask, p_mask, autoregressive: bool):
+    from ...models.rag_e2e_base_model import pooling_mask
+    return pooling_mask(q_mask, autoregressive).contiguous(), pooling_mask(p_mask, autoregressive).contiguous()
+
+
 def fused_rag_step(rag_model, batch: Dict[str, torch.Tensor], logit_scale: float, backward: bool = True,
                    grad_scale: float = 1.0) -> Dict[str, torch.Tensor]:
     """reference train_rage2e.py:431-471 as one launch sequence. Gradients (LoRA) are ACCUMULATED into the banks.
@@ -147,9 +167,10 @@ def fused_rag_step(rag_model, batch: Dict[str, torch.Tensor], logit_scale: float
     if enc.training or dec.training:                         # fresh dropout masks per step (also inside a graph replay)
         ops.bump_counter_(enc.drop_offset)
         ops.bump_counter_(dec.drop_offset)
-    (hq, hp), cqp = enc.forward_segments([(q_ids, q_mask), (p_ids, p_mask)], save=train_enc)   # one pass over the weights
-    q_emb, q_norm = ops.pool_norm_fwd(hq, q_mask, rag_model.normalize)
-    p_emb, p_norm = ops.pool_norm_fwd(hp, p_mask, rag_model.normalize)
+    hq, hp, enc_bwd = _encode_pair(enc, q_ids, q_mask, p_ids, p_mask, train_enc)             # one pass over the weights (BERT)
+    q_pm, p_pm = _pool_masks(rag_model, q_mask, p_mask, getattr(rag_model, "retriever_is_autoregressive", False))
+    q_emb, q_norm = ops.pool_norm_fwd(hq, q_pm, rag_model.normalize)
+    p_emb, p_norm = ops.pool_norm_fwd(hp, p_pm, rag_model.normalize)
     cvec, nsum = ops.marginal_counts(g_mask, qlen)
     r = ops.inbatch_loss(q_emb, p_emb, float(logit_scale), cvec, nsum, need_grad=train_enc, grad_out=grad_scale)
     logits, cg = dec.forward_logits(g_ids, g_mask, save=train_dec)
@@ -159,8 +180,8 @@ def fused_rag_step(rag_model, batch: Dict[str, torch.Tensor], logit_scale: float
         dec.backward_logits(cg, dl)
     if train_enc:
         L_p, L_q = p_ids.shape[1], q_ids.shape[1]
-        enc.backward_segments(cqp, [ops.pool_norm_bwd(q_emb, q_norm, r["dQ"], q_mask, L_q, rag_model.normalize),
-                                    ops.pool_norm_bwd(p_emb, p_norm, r["dP"], p_mask, L_p, rag_model.normalize)])
+        enc_bwd(ops.pool_norm_bwd(q_emb, q_norm, r["dQ"], q_pm, L_q, rag_model.normalize),
+                ops.pool_norm_bwd(p_emb, p_norm, r["dP"], p_pm, L_p, rag_model.normalize))
     return {"loss": out[2], "losses": out, "S": r["S"]}
 
 
@@ -174,13 +195,14 @@ def fused_retriever_step(model, batch: Dict[str, torch.Tensor], logit_scale: flo
     train = backward and enc.lora is not None
     if enc.training:
         ops.bump_counter_(enc.drop_offset)
-    (hq, hp), cqp = enc.forward_segments([(q_ids, q_mask), (p_ids, p_mask)], save=train)
-    q_emb, q_norm = ops.pool_norm_fwd(hq, q_mask, model.normalize)
-    p_emb, p_norm = ops.pool_norm_fwd(hp, p_mask, model.normalize)
+    hq, hp, enc_bwd = _encode_pair(enc, q_ids, q_mask, p_ids, p_mask, train)
+    q_pm, p_pm = _pool_masks(model, q_mask, p_mask, getattr(model, "is_autoregressive", False))
+    q_emb, q_norm = ops.pool_norm_fwd(hq, q_pm, model.normalize)
+    p_emb, p_norm = ops.pool_norm_fwd(hp, p_pm, model.normalize)
     r = ops.inbatch_loss(q_emb, p_emb, float(logit_scale), None, None, need_grad=train, grad_out=grad_scale)
     if train:
-        enc.backward_segments(cqp, [ops.pool_norm_bwd(q_emb, q_norm, r["dQ"], q_mask, q_ids.shape[1], model.normalize),
-                                    ops.pool_norm_bwd(p_emb, p_norm, r["dP"], p_mask, p_ids.shape[1], model.normalize)])
+        enc_bwd(ops.pool_norm_bwd(q_emb, q_norm, r["dQ"], q_pm, q_ids.shape[1], model.normalize),
+                ops.pool_norm_bwd(p_emb, p_norm, r["dP"], p_pm, p_ids.shape[1], model.normalize))
     return {"loss": r["losses"][0], "losses": r["losses"], "S": r["S"]}
 
 

@@ -93,6 +93,15 @@ def retrieval_forward(bert: nn.Module, ids: torch.Tensor, mask: torch.Tensor, no
     return pooling.normalize(emb) if normalize else emb
 
 
+def retrieval_forward_autoregressive(llama_lm: nn.Module, ids: torch.Tensor, mask: torch.Tensor, normalize: bool = True):
+    """reference rag_e2e_base_model.py:84-90 (autoregressive branch): last hidden state of the base model, `eos_mask`
+    (one-hot at the last column, padding='left' default) as the pooling mask"""
+    base = llama_lm.model if hasattr(llama_lm, "model") else llama_lm
+    tok = base(ids, attention_mask=mask, output_hidden_states=True, return_dict=True).hidden_states[-1]
+    emb = pooling.mean_pooling(tok, pooling.eos_mask(mask))
+    return pooling.normalize(emb) if normalize else emb
+
+
 def rag_step(bert: nn.Module, llama: nn.Module, batch: Dict[str, torch.Tensor], logit_scale: float = 100.0) -> Dict:
     """One forward+backward of the loop body, reference train_rage2e.py:431-471, in fp32 on CPU."""
     for m in (bert, llama):

@@ -203,3 +203,50 @@ def test_fused_step_with_frozen_falcon_generator(cuda_dev):
         worst = max(worst, _rel(enc.lora.gA[n], ref["grads"]["retriever." + n + ".lora_A"]),
                     _rel(enc.lora.gB[n], ref["grads"]["retriever." + n + ".lora_B"]))
     assert worst < 6e-2, worst
+
+
+def test_autoregressive_retriever(cuda_dev):
+    """`is_autoregressive=True`: a causal LM as the retriever (last hidden state, eos pooling, LoRA on q_proj / v_proj) —
+    reference retriever_only_base_model.py:48-58 / rag_e2e_base_model.py:84-90"""
+    from dalm_b200 import synthetic
+    from dalm_b200.engine import params
+    from dalm_b200.engine.llama import LlamaDecoder
+    from dalm_b200.models.retriever_only_base_model import AutoModelForSentenceEmbedding
+    from dalm_b200.training.utils.train_utils import fused_retriever_step, get_cosine_sim, get_nt_xent_loss
+    from oracle import models as om, losses
+    cfg = synthetic.llama_config("llama-tiny", 400)
+    sd = {k: (v.to(bf16).float() if v.dim() == 2 else v) for k, v in params.random_state_dict("llama", cfg, seed=31).items()}
+    enc = LlamaDecoder(cfg, sd, device=cuda_dev, lora=True, lora_seed=0)
+    g = torch.Generator().manual_seed(32)
+    for n, _, _ in enc.lora.specs:
+        enc.lora.B[n].copy_((torch.randn(enc.lora.B[n].shape, generator=g) * 0.02).to(cuda_dev))
+    enc.repack_lora()
+    model = AutoModelForSentenceEmbedding("", use_bnb=False, get_peft=True, is_autoregressive=True, _model=enc, _load_tokenizer=False)
+    ref = om.build_llama(cfg, sd)
+    om.attach_lora(ref, {n: {"A": enc.lora.A[n].cpu(), "B": enc.lora.B[n].cpu()} for n, _, _ in enc.lora.specs})
+    B, Lq, Lp = 4, 12, 20
+    mk = lambda L: torch.ones(B, L, dtype=torch.int64)
+    rb = {"query_input_ids": torch.randint(3, 400, (B, Lq), generator=g), "query_attention_mask": mk(Lq),
+          "passage_input_ids": torch.randint(3, 400, (B, Lp), generator=g), "passage_attention_mask": mk(Lp)}
+    rb["query_attention_mask"][0, :3] = 0; rb["passage_attention_mask"][2, :6] = 0          # left padding (tokenizer default)
+    q = om.retrieval_forward_autoregressive(ref, rb["query_input_ids"], rb["query_attention_mask"])
+    p = om.retrieval_forward_autoregressive(ref, rb["passage_input_ids"], rb["passage_attention_mask"])
+    loss = losses.contrastive_loss(losses.get_cosine_sim(q, p, 100.0))
+    loss.backward()
+    enc.lora.zero_grad()
+    out = fused_retriever_step(model, rb, 100.0)
+    assert abs(out["loss"].item() - loss.item()) / abs(loss.item()) < 2e-2
+    worst = 0.0
+    for n, _, _ in enc.lora.specs:
+        mod = om._get_module(ref, n)
+        worst = max(worst, _rel(enc.lora.gA[n], mod.lora_A.grad), _rel(enc.lora.gB[n], mod.lora_B.grad))
+    assert worst < 8e-2, worst
+    # the wrapper's own forward (autograd bridge) gives the same embeddings and gradients
+    g_fused = enc.lora.grad.clone()
+    enc.lora.zero_grad()
+    dq = {k: v.to(cuda_dev) for k, v in rb.items()}
+    qe = model(dq["query_input_ids"], dq["query_attention_mask"]); pe = model(dq["passage_input_ids"], dq["passage_attention_mask"])
+    assert _rel(qe, q.detach()) < 2e-2
+    S = get_cosine_sim(qe, pe, 100)
+    ((get_nt_xent_loss(S) + get_nt_xent_loss(S.t())) / 2.0).backward()
+    assert _rel(enc.lora.grad, g_fused) < 2e-2
