@@ -275,7 +275,12 @@ def main():
         # per-launch CUDA events cannot be recorded inside a graph replay: the roofline pass re-runs the SAME steps with
         # eager launches (identical kernels, shapes and data) right after the timed region, events around every GEMM.
         # `launches` = kernels per timed region, counted by the library during this eager pass (a replay launches the same set)
+        # (single stream during this pass so the per-kernel event durations are not inflated by cross-stream overlap)
+        from dalm_b200.training.utils import train_utils as _tu
+        _two = _tu._TWO_STREAMS
+        _tu._TWO_STREAMS = False
         eager_ms, _, launches = timed(resident, timer, eager=True)
+        _tu._TWO_STREAMS = _two
     gsum = timer.summary()
 
     # ---- end-to-end run through the public step with host (pinned) batches: H2D inside, loss read back each step ----

@@ -147,6 +147,17 @@ def _encode_pair(enc, q_ids, q_mask, p_ids, p_mask, save: bool):
     return hq, hp, bwd
 
 
+_TWO_STREAMS = os.environ.get("DALM_B200_TWO_STREAMS", "1") != "0"
+_SIDE_STREAMS: Dict[int, torch.cuda.Stream] = {}
+
+
+def _side_stream(dev: torch.device) -> torch.cuda.Stream:
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _SIDE_STREAMS:
+        _SIDE_STREAMS[idx] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[idx]
+
+
 def _pool_masks(model, q_mask, p_mask, autoregressive: bool):
     from ...models.rag_e2e_base_model import pooling_mask
     return pooling_mask(q_mask, autoregressive).contiguous(), pooling_mask(p_mask, autoregressive).contiguous()
@@ -167,21 +178,42 @@ def fused_rag_step(rag_model, batch: Dict[str, torch.Tensor], logit_scale: float
     if enc.training or dec.training:                         # fresh dropout masks per step (also inside a graph replay)
         ops.bump_counter_(enc.drop_offset)
         ops.bump_counter_(dec.drop_offset)
-    hq, hp, enc_bwd = _encode_pair(enc, q_ids, q_mask, p_ids, p_mask, train_enc)             # one pass over the weights (BERT)
-    q_pm, p_pm = _pool_masks(rag_model, q_mask, p_mask, getattr(rag_model, "retriever_is_autoregressive", False))
-    q_emb, q_norm = ops.pool_norm_fwd(hq, q_pm, rag_model.normalize)
-    p_emb, p_norm = ops.pool_norm_fwd(hp, p_pm, rag_model.normalize)
     cvec, nsum = ops.marginal_counts(g_mask, qlen)
-    r = ops.inbatch_loss(q_emb, p_emb, float(logit_scale), cvec, nsum, need_grad=train_enc, grad_out=grad_scale)
-    logits, cg = dec.forward_logits(g_ids, g_mask, save=train_dec)
-    tok_lp, dl = ops.ce_marginal(logits, g_ids, g_mask, nsum, need_grad=train_dec, inplace=True, grad_out=grad_scale)
+    L_p, L_q = p_ids.shape[1], q_ids.shape[1]
+
+    def retriever_branch():
+        # encoder forward (both batches), pooling, fused in-batch loss (+ dQ, dP), encoder backward: independent of the decoder
+        hq, hp, enc_bwd = _encode_pair(enc, q_ids, q_mask, p_ids, p_mask, train_enc)
+        q_pm, p_pm = _pool_masks(rag_model, q_mask, p_mask, getattr(rag_model, "retriever_is_autoregressive", False))
+        q_emb, q_norm = ops.pool_norm_fwd(hq, q_pm, rag_model.normalize)
+        p_emb, p_norm = ops.pool_norm_fwd(hp, p_pm, rag_model.normalize)
+        r = ops.inbatch_loss(q_emb, p_emb, float(logit_scale), cvec, nsum, need_grad=train_enc, grad_out=grad_scale)
+        if train_enc:
+            enc_bwd(ops.pool_norm_bwd(q_emb, q_norm, r["dQ"], q_pm, L_q, rag_model.normalize),
+                    ops.pool_norm_bwd(p_emb, p_norm, r["dP"], p_pm, L_p, rag_model.normalize))
+        return r
+
+    def generator_branch():
+        logits, cg = dec.forward_logits(g_ids, g_mask, save=train_dec)
+        tok_lp, dl = ops.ce_marginal(logits, g_ids, g_mask, nsum, need_grad=train_dec, inplace=True, grad_out=grad_scale)
+        if train_dec:
+            dec.backward_logits(cg, dl)
+        return tok_lp
+
+    # The two branches only meet in the scalar loss (the LM loss reaches the retriever through c_b / N, known up front),
+    # so they run on two streams: the encoder's many small kernels fill the tails of the decoder's persistent GEMMs.
+    if _TWO_STREAMS:
+        main = torch.cuda.current_stream()
+        side = _side_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            r = retriever_branch()
+        tok_lp = generator_branch()
+        main.wait_stream(side)
+    else:
+        r = retriever_branch()
+        tok_lp = generator_branch()
     out = ops.finalize_loss(tok_lp, g_mask, nsum, r["losses"])
-    if train_dec:
-        dec.backward_logits(cg, dl)
-    if train_enc:
-        L_p, L_q = p_ids.shape[1], q_ids.shape[1]
-        enc_bwd(ops.pool_norm_bwd(q_emb, q_norm, r["dQ"], q_pm, L_q, rag_model.normalize),
-                ops.pool_norm_bwd(p_emb, p_norm, r["dP"], p_pm, L_p, rag_model.normalize))
     return {"loss": out[2], "losses": out, "S": r["S"]}
 
 
