@@ -38,6 +38,7 @@ SIGNATURES = {
     "dalm_b200_attention_bwd": [_P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _P, _L, _P, _P, _L, _P, _L, _P, _L,
                                 _I, _I, _I, _I, _I, _F, _I, *_DROP, _P],
     "dalm_b200_attention_tc_fwd": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _L, _I, _P, _P, _L, _P, _I, _I, _I, _I, _I, _F, _I, _P],
+    "dalm_b200_attention_tc_set_debug": [_P],
     "dalm_b200_attention_tc_bwd": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _P, _L, _P, _P, _L, _L, _P, _P, _L, _P, _L, _P, _L,
                                    _I, _I, _I, _I, _I, _F, _I, _P],
     "dalm_b200_layernorm_fwd": [_P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _F, *_DROP, _P],
@@ -66,6 +67,7 @@ _RESTYPES = {
     "dalm_b200_launch_count": c_longlong,
     "dalm_b200_reset_launch_count": None,
     "dalm_b200_gemm_clear_cache": None,
+    "dalm_b200_attention_tc_set_debug": None,
 }
 
 _lib = None

@@ -29,6 +29,7 @@ struct AttnTcParams {
   float scale;
   int causal;
   int qcol0, kcol0, vcol0, ocol0;   // column of head 0 inside the q / k / v / dO tensor maps
+  long long* dbg;                   // optional [64] clock64 timestamps of one CTA's phases (tuning aid), or nullptr
 };
 
 constexpr int TD = 128;                      // head dim
@@ -49,24 +50,69 @@ __device__ __forceinline__ void st_sw128(unsigned char* half_tile, int row, int 
   *reinterpret_cast<bf16x8*>(half_tile + row * 128 + ((piece ^ (row & 7)) << 4)) = v;
 }
 
+// Drain one [128 rows x 128 cols] fp32 TMEM accumulator to a bf16 token-major matrix. Full tiles go through a
+// 128B-swizzled staging tile (two 64-column halves) and two TMA stores - full 128-byte lines instead of 32 partial sectors
+// per warp store (measured: the per-thread row stores cost 10k of a forward CTA's 30k cycles). Ragged tiles (rows beyond
+// the sequence end belong to the NEXT sequence, so the TMA box must not be used) fall back to predicated row stores.
+__device__ __forceinline__ void drain_tile_bf16(uint32_t tacc, float scale, unsigned char* stage, const CUtensorMap* tm,
+                                                int col0, int row0_global, bool full_tile, bool row_ok, int r,
+                                                __nv_bfloat16* fallback_row) {
+#pragma unroll 1
+  for (int c = 0; c < TD; c += 32) {
+    uint32_t v[32]; float f[32];
+    tmem_ld_32x32(tacc + c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * scale;
+    if (full_tile) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) st_sw128(stage + (c >> 6) * HALF_BYTES, r, ((c & 63) >> 3) + g, pack8(f + g * 8));
+    } else if (row_ok) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) *reinterpret_cast<bf16x8*>(fallback_row + c + g * 8) = pack8(f + g * 8);
+    }
+  }
+  if (full_tile) {
+    fence_proxy_async();
+    named_bar_sync(1, 128);
+    if (threadIdx.x == 0) {
+      tma_store_2d(tm, stage, col0, row0_global);
+      tma_store_2d(tm, stage + HALF_BYTES, col0 + 64, row0_global);
+      bulk_commit();
+      bulk_wait<0>();
+    }
+  }
+}
+
+// key-validity bits of a 128-key tile, replicated in every lane (no shared memory, no barrier): word w, bit i = key
+// kv0 + 32 w + i is a real, un-masked key
+__device__ __forceinline__ void key_bits(const int64_t* mask_row, int kv0, int L, int lane, uint32_t* bits) {
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const int key = kv0 + w * 32 + lane;
+    bool keep = key < L;
+    if (keep && mask_row) keep = mask_row[key] != 0;
+    bits[w] = __ballot_sync(0xffffffffu, keep);
+  }
+}
+
 // ============================================================================================================
-// forward: grid (ceil(L/128), Hq, B), 160 threads: warps 0-3 softmax (thread = query row), warp 4 control
+// forward: grid (ceil(L/128), Hq, B), 160 threads: warps 0-3 softmax (thread = query row), warp 4 control.
+// O accumulates in TMEM (P V with the accumulate flag); the online-softmax correction rescales it in place.
 // ============================================================================================================
 __global__ void __launch_bounds__(160, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                   const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p) {
+                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, const AttnTcParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* sQ = smem;
   unsigned char* sK = sQ + TILE_BYTES;
   unsigned char* sV = sK + TILE_BYTES;
   unsigned char* sP = sK;        // P overwrites K: K is dead once S = Q K^T has retired (s_full), and K is only reloaded
-                                 // after P V has retired (kv_free). 96 KB per CTA => two CTAs per SM hide each other's
-                                 // TMA / MMA / softmax latencies.
+                                 // after P V has retired (kv_free). 96 KB per CTA => two CTAs per SM.
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + TILE_BYTES);
   uint64_t *q_full = bars, *kv_full = bars + 1, *kv_free = bars + 2, *s_full = bars + 3, *p_ready = bars + 4, *pv_full = bars + 5;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
-  float* sMask = reinterpret_cast<float*>(bars + 10);          // [128] additive 0 / -inf for the current key tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -74,6 +120,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const int L = p.L, q0 = qb * TB;
   const int tok0 = b * L;
   const int nkv = p.causal ? (min(L, q0 + TB) + TB - 1) / TB : (L + TB - 1) / TB;
+  const bool dbg = p.dbg != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0;
+#define TS(slot) do { if (dbg) p.dbg[slot] = clock64(); } while (0)
+  if (threadIdx.x == 0) TS(0);
 
   if (threadIdx.x == 128) {
     mbar_init(q_full, 1); mbar_init(kv_full, 1); mbar_init(kv_free, 1); mbar_init(s_full, 1);
@@ -86,7 +135,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_holder;
-  const uint32_t tS = tmem, tPV = tmem + 128;
+  const uint32_t tS = tmem, tO = tmem + 128;
+  if (threadIdx.x == 0) TS(1);
 
   if (warp == 4) {
     if (lane == 0) {
@@ -94,8 +144,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       mbar_arrive_expect_tx(q_full, TILE_BYTES);
       tma_load_2d(sQ, &tm_q, q_full, p.qcol0 + h * TD, tok0 + q0);
       tma_load_2d(sQ + HALF_BYTES, &tm_q, q_full, p.qcol0 + h * TD + 64, tok0 + q0);
-      constexpr uint32_t idesc_kk = make_idesc_bf16(TB, TB);          // S  = Q K^T   (both K-major)
-      constexpr uint32_t idesc_mn = make_idesc_bf16_bmn(TB, TD);      // PV = P V     (B = V MN-major)
+      constexpr uint32_t idesc_kk = make_idesc_bf16(TB, TB);          // S = Q K^T   (both K-major)
+      constexpr uint32_t idesc_mn = make_idesc_bf16_bmn(TB, TD);      // O += P V    (B = V MN-major)
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
       for (int j = 0; j < nkv; ++j) {
         const uint32_t ph = j & 1;
         mbar_wait(kv_free, ph ^ 1);
@@ -104,118 +155,117 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tma_load_2d(sK + HALF_BYTES, &tm_k, kv_full, p.kcol0 + hk * TD + 64, tok0 + j * TB);
         tma_load_2d(sV, &tm_v, kv_full, p.vcol0 + hk * TD, tok0 + j * TB);
         tma_load_2d(sV + HALF_BYTES, &tm_v, kv_full, p.vcol0 + hk * TD + 64, tok0 + j * TB);
+        TS(2 + j * 8);
         if (j == 0) mbar_wait(q_full, 0);
         mbar_wait(kv_full, ph);
+        TS(3 + j * 8);
         tc_fence_after();
-        const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) umma_f16(tS, kmajor_desc(aQ, kk), kmajor_desc(aK, kk), idesc_kk, kk != 0);
         umma_commit(s_full);
-        mbar_wait(p_ready, ph);                                         // P tile written (and PV of block j-1 consumed)
+        TS(4 + j * 8);
+        mbar_wait(p_ready, ph);                                         // P written, O rescaled
+        TS(5 + j * 8);
         tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) umma_f16(tPV, kmajor_desc(aP, kk), mnmajor_desc(aV, kk), idesc_mn, kk != 0);
+        for (int kk = 0; kk < 8; ++kk) umma_f16(tO, kmajor_desc(aP, kk), mnmajor_desc(aV, kk), idesc_mn, (j | kk) != 0);
         umma_commit(pv_full);
         umma_commit(kv_free);
+        TS(6 + j * 8);
       }
     }
   } else {
-    // ---------------- softmax warps: thread = query row ----------------
-    const int r = warp * 32 + lane;                    // TMEM lane == query row within the tile
+    // ---------------- softmax warps: thread = query row; the whole 128-wide S row lives in registers ----------------
+    const int r = warp * 32 + lane;
     const int qrow = q0 + r;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const float sl2 = p.scale * 1.4426950408889634f;
-    float o_acc[TD];
-#pragma unroll
-    for (int i = 0; i < TD; ++i) o_acc[i] = 0.f;
+    const int64_t* mask_row = p.mask ? p.mask + (size_t)tok0 : nullptr;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < nkv; ++j) {
       const uint32_t ph = j & 1;
       const int kv0 = j * TB;
-      // key validity of this tile (own barrier among the 128 softmax threads)
-      {
-        const int key = kv0 + r;
-        bool keep = key < L;
-        if (keep && p.mask) keep = p.mask[(size_t)tok0 + key] != 0;
-        named_bar_sync(1, 128);                          // previous tile's readers are done with sMask
-        sMask[r] = keep ? 0.f : -INFINITY;
-        named_bar_sync(1, 128);
-      }
+      uint32_t kb[4];
+      key_bits(mask_row, kv0, L, lane, kb);
+      const bool all_keys = (kb[0] & kb[1] & kb[2] & kb[3]) == 0xffffffffu;
+      const bool diag = p.causal && (kv0 + TB - 1 > q0);              // only the diagonal tile needs the causal compare
       mbar_wait(s_full, ph);
+      if (threadIdx.x == 0) TS(20 + j * 8);
       tc_fence_after();
-      // pass 1: row maximum
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};      // 4 independent chains (ILP)
-#pragma unroll 1
-      for (int c = 0; c < TB; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + lane_off + c, v);
-        tmem_ld_wait();
+      float sv[TB];
+      {
+        uint32_t* raw = reinterpret_cast<uint32_t*>(sv);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float val = __uint_as_float(v[i]) * sl2 + sMask[c + i];
-          if (p.causal && (kv0 + c + i) > qrow) val = -INFINITY;
-          mx4[i & 3] = fmaxf(mx4[i & 3], val);
+        for (int c = 0; c < TB; c += 32) tmem_ld_32x32(tS + lane_off + c, raw + c);
+        tmem_ld_wait();
+      }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (all_keys && !diag) {
+#pragma unroll
+        for (int i = 0; i < TB; ++i) { sv[i] *= sl2; mx4[i & 3] = fmaxf(mx4[i & 3], sv[i]); }
+      } else {
+        // branch-free masking (per-lane divergent selects along the diagonal were measured 5x slower): build an
+        // all-ones integer mask for dropped elements and OR in the bit pattern of -inf
+        const int dcol = diag ? (qrow - kv0) : 0x7fffffff;                 // columns > dcol are in the causal future
+#pragma unroll
+        for (int i = 0; i < TB; ++i) {
+          const int drop = ((dcol - i) >> 31) | (int)(((kb[i >> 5] >> (i & 31)) & 1u) - 1u);   // -1 if dropped, else 0
+          const uint32_t bits = (__float_as_uint(sv[i] * sl2) & ~(uint32_t)drop) | (0xff800000u & (uint32_t)drop);
+          sv[i] = __uint_as_float(bits);
+          mx4[i & 3] = fmaxf(mx4[i & 3], sv[i]);
         }
       }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      const float m_new = fmaxf(m_run, mx);
+      if (threadIdx.x == 0) TS(21 + j * 8);
+      const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])));
       const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
-      const float corr = exp2f(m_run - m_safe);
+      const float corr = ex2_approx(m_run - m_safe);                   // m_run = -inf -> 0
       m_run = m_new;
-      // pass 2: P = exp2(S - m) -> bf16 -> swizzled smem (A operand of P V), row sum
-      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (j > 0) {
+        // O of the previous tiles (in TMEM) must carry the new maximum: rescale in place once P V (j-1) has retired
+        mbar_wait(pv_full, ph ^ 1);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < TB; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + lane_off + c, v);
-        tmem_ld_wait();
-        unsigned char* half = sP + (c >> 6) * HALF_BYTES;
+        for (int c = 0; c < TD; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tO + lane_off + c, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float pv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float val = __uint_as_float(v[g * 8 + i]) * sl2 + sMask[c + g * 8 + i];
-            if (p.causal && (kv0 + c + g * 8 + i) > qrow) val = -INFINITY;
-            pv[i] = exp2f(val - m_safe);
-            rs4[i & 3] += pv[i];
-          }
-          st_sw128(half, r, ((c & 63) >> 3) + g, pack8(pv));
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * corr);
+          tmem_st_32x32(tO + lane_off + c, v);
         }
+        tmem_st_wait();
+      }
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int g = 0; g < TB / 8; ++g) {
+        float pv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { pv[i] = ex2_approx(sv[g * 8 + i] - m_safe); rs4[i & 3] += pv[i]; }
+        st_sw128(sP + (g >> 3) * HALF_BYTES, r, g & 7, pack8(pv));
       }
       l_run = l_run * corr + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(p_ready);
-      // PV of this tile -> accumulate into the register-resident O with the online-softmax correction
-      mbar_wait(pv_full, ph);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < TD; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tPV + lane_off + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c + i] = o_acc[c + i] * corr + __uint_as_float(v[i]);
-      }
-      tc_fence_before();
+      if (threadIdx.x == 0) TS(22 + j * 8);
     }
-    if (qrow < L) {
-      const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
-      __nv_bfloat16* orow = p.o + (size_t)(tok0 + qrow) * p.ldo + (size_t)h * TD;
-#pragma unroll
-      for (int g = 0; g < TD / 8; ++g) {
-        float f[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = o_acc[g * 8 + i] * inv_l;
-        *reinterpret_cast<bf16x8*>(orow + g * 8) = pack8(f);
-      }
+    // last P V retired -> normalise and store O, store LSE
+    mbar_wait(pv_full, (nkv - 1) & 1);
+    tc_fence_after();
+    if (threadIdx.x == 0) TS(23);
+    const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
+    __nv_bfloat16* orow = p.o + (size_t)(tok0 + (qrow < L ? qrow : 0)) * p.ldo + (size_t)h * TD;
+    drain_tile_bf16(tO + lane_off, inv_l, sQ /* Q is dead after the last S MMA */, &tm_o, p.ocol0 + h * TD, tok0 + q0,
+                    q0 + TB <= L, qrow < L, r, orow);
+    if (qrow < L)
       p.lse[((size_t)b * p.Hq + h) * L + qrow] = l_run > 0.f ? (m_run + log2f(l_run)) * 0.6931471805599453f : INFINITY;
-    }
   }
+  if (threadIdx.x == 0) TS(40);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+  if (threadIdx.x == 0) TS(41);
+#undef TS
 }
 
 // ============================================================================================================
@@ -249,6 +299,7 @@ __global__ void attn_tc_delta_kernel(const __nv_bfloat16* __restrict__ o, long l
 __global__ void __launch_bounds__(160, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                        const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                       const __grid_constant__ CUtensorMap tm_dk, const __grid_constant__ CUtensorMap tm_dv,
                        const AttnTcParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -345,21 +396,30 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         mbar_wait(st_full, ph);
         tc_fence_after();
         mbar_wait(mma2_done, ph ^ 1);                            // previous P^T / dS^T tiles consumed by their MMAs
+        const bool diag = p.causal && (kv0 + TB - 1 > q0);       // only the diagonal tile needs the causal compare
+        const int dropkey = key_ok ? 0 : -1;
 #pragma unroll 1
         for (int c = 0; c < TB; c += 32) {
           uint32_t vs[32], vp[32];
           tmem_ld_32x32(tSt + lane_off + c, vs);
           tmem_ld_32x32(tdPt + lane_off + c, vp);
+          float lse_c[32], del_c[32];
+#pragma unroll
+          for (int x = 0; x < 32; x += 4) {                      // per-query statistics: 128-bit broadcast reads
+            *reinterpret_cast<float4*>(lse_c + x) = *reinterpret_cast<const float4*>(sLse + c + x);
+            *reinterpret_cast<float4*>(del_c + x) = *reinterpret_cast<const float4*>(sDelta + c + x);
+          }
           tmem_ld_wait();
           float pt[32], ds[32];
+          const int qbase = q0 + c;
 #pragma unroll
           for (int x = 0; x < 32; ++x) {
-            const int qi = q0 + c + x;
-            float val = key_ok ? __uint_as_float(vs[x]) * sl2 : -INFINITY;
-            if (p.causal && key > qi) val = -INFINITY;
-            const float pr = exp2f(val - sLse[c + x]);             // lse = +inf (padding / fully masked query) -> 0
+            // branch-free masking: dropped (padding key, or key in the query's causal future) -> -inf
+            const int drop = dropkey | (diag ? ((qbase + x - key) >> 31) : 0);
+            const uint32_t bits = (__float_as_uint(__uint_as_float(vs[x]) * sl2) & ~(uint32_t)drop) | (0xff800000u & (uint32_t)drop);
+            const float pr = ex2_approx(__uint_as_float(bits) - lse_c[x]);      // lse = +inf (padding / fully masked query) -> 0
             pt[x] = pr;
-            ds[x] = pr * (__uint_as_float(vp[x]) - sDelta[c + x]) * p.scale;
+            ds[x] = pr * (__uint_as_float(vp[x]) - del_c[x]) * p.scale;
           }
           unsigned char* hp = sPt + (c >> 6) * HALF_BYTES;
           unsigned char* hd = sdSt + (c >> 6) * HALF_BYTES;
@@ -378,30 +438,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     mbar_wait(mma2_done, (n_iter - 1) & 1);
     tc_fence_after();
     {
-      // tcgen05.ld is warp-collective (.sync.aligned): every lane issues the loads, only rows < L store
-      const bool st_ok = key < L;
+      const bool st_ok = key < L, full = kv0 + TB <= L;
       __nv_bfloat16* dvrow = p.dv + (size_t)(tok0 + (st_ok ? key : 0)) * p.lddv + (size_t)hk * TD;
       __nv_bfloat16* dkrow = p.dk + (size_t)(tok0 + (st_ok ? key : 0)) * p.lddk + (size_t)hk * TD;
-#pragma unroll 1
-      for (int c = 0; c < TD; c += 32) {
-        uint32_t v[32]; float f[32];
-        tmem_ld_32x32(tdV + lane_off + c, v);
-        tmem_ld_wait();
-        if (st_ok) {
-#pragma unroll
-          for (int x = 0; x < 32; ++x) f[x] = __uint_as_float(v[x]);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) *reinterpret_cast<bf16x8*>(dvrow + c + g * 8) = pack8(f + g * 8);
-        }
-        tmem_ld_32x32(tdK + lane_off + c, v);
-        tmem_ld_wait();
-        if (st_ok) {
-#pragma unroll
-          for (int x = 0; x < 32; ++x) f[x] = __uint_as_float(v[x]);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) *reinterpret_cast<bf16x8*>(dkrow + c + g * 8) = pack8(f + g * 8);
-        }
-      }
+      // P^T / dS^T staging tiles are free once the last MMAs have retired
+      drain_tile_bf16(tdV + lane_off, 1.f, sPt, &tm_dv, hk * TD, tok0 + kv0, full, st_ok, r, dvrow);
+      drain_tile_bf16(tdK + lane_off, 1.f, sdSt, &tm_dk, hk * TD, tok0 + kv0, full, st_ok, r, dkrow);
     }
   }
   tc_fence_before();
@@ -415,7 +457,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 __global__ void __launch_bounds__(160, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                       const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
-                      const AttnTcParams p) {
+                      const __grid_constant__ CUtensorMap tm_dq, const AttnTcParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* sQ = smem;
@@ -490,14 +532,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     for (int j = 0; j < nkv; ++j) {
       const uint32_t ph = j & 1;
       const int kv0 = j * TB;
-      {
-        const int key = kv0 + r;
-        bool keep = key < L;
-        if (keep && p.mask) keep = p.mask[(size_t)tok0 + key] != 0;
-        named_bar_sync(1, 128);
-        sMask[r] = keep ? 0.f : -INFINITY;
-        named_bar_sync(1, 128);
-      }
+      uint32_t kbits[4];
+      key_bits(p.mask ? p.mask + (size_t)tok0 : nullptr, kv0, L, lane, kbits);
+      const bool diag = p.causal && (kv0 + TB - 1 > q0);
+      const int dcol = diag ? (qrow - kv0) : 0x7fffffff;           // columns > dcol are in the causal future
       mbar_wait(s_full, ph);
       tc_fence_after();
       mbar_wait(mma2_done, ph ^ 1);                              // previous dS tile consumed
@@ -507,12 +545,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         tmem_ld_32x32(tS + lane_off + c, vs);
         tmem_ld_32x32(tdP + lane_off + c, vp);
         tmem_ld_wait();
+        const uint32_t kw = kbits[c >> 5];
         float ds[32];
 #pragma unroll
         for (int x = 0; x < 32; ++x) {
-          float val = __uint_as_float(vs[x]) * sl2 + sMask[c + x];
-          if (p.causal && (kv0 + c + x) > qrow) val = -INFINITY;
-          const float pr = exp2f(val - lse2);
+          const int drop = ((dcol - (c + x)) >> 31) | (int)(((kw >> x) & 1u) - 1u);
+          const uint32_t bits = (__float_as_uint(__uint_as_float(vs[x]) * sl2) & ~(uint32_t)drop) | (0xff800000u & (uint32_t)drop);
+          const float pr = ex2_approx(__uint_as_float(bits) - lse2);
           ds[x] = pr * (__uint_as_float(vp[x]) - dl) * p.scale;
         }
         unsigned char* hd = sdS + (c >> 6) * HALF_BYTES;
@@ -526,18 +565,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     mbar_wait(mma2_done, (nkv - 1) & 1);
     tc_fence_after();
     __nv_bfloat16* dqrow = p.dq + (size_t)(tok0 + (qrow < L ? qrow : 0)) * p.lddq + (size_t)h * TD;
-#pragma unroll 1
-    for (int c = 0; c < TD; c += 32) {
-      uint32_t v[32]; float f[32];
-      tmem_ld_32x32(tdQ + lane_off + c, v);
-      tmem_ld_wait();
-      if (qrow < L) {
-#pragma unroll
-        for (int x = 0; x < 32; ++x) f[x] = __uint_as_float(v[x]);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) *reinterpret_cast<bf16x8*>(dqrow + c + g * 8) = pack8(f + g * 8);
-      }
-    }
+    drain_tile_bf16(tdQ + lane_off, 1.f, sdS /* free after the last dQ MMA */, &tm_dq, h * TD, tok0 + q0, q0 + TB <= L,
+                    qrow < L, r, dqrow);
   }
   tc_fence_before();
   __syncthreads();
@@ -552,6 +581,9 @@ constexpr int kFwdSmem = 3 * TILE_BYTES + 1024 + 1024;
 
 using namespace dalm;
 
+static long long* g_attn_dbg = nullptr;
+extern "C" void dalm_b200_attention_tc_set_debug(void* dev_buffer_64xint64) { g_attn_dbg = (long long*)dev_buffer_64xint64; }
+
 static int tc_maps(const void* ptr, long long rows, long long cols, long long ld, CUtensorMap* m) {
   return get_tmap(ptr, rows, cols, ld, 128, m, 0);
 }
@@ -565,18 +597,20 @@ extern "C" int dalm_b200_attention_tc_fwd(const void* q, long long ldq, long lon
   DALM_REQUIRE(D == 128, "attention_tc: head_dim must be 128 (got %d)", D);
   DALM_REQUIRE(B > 0 && L > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0, "attention_tc: bad shape");
   DALM_REQUIRE((ldo % 8) == 0 && ((uintptr_t)out & 15) == 0, "attention_tc: output alignment");
-  CUtensorMap mq, mk, mv;
+  CUtensorMap mq, mk, mv, mo;
   const long long rows = (long long)B * L;
   if (int e = tc_maps(q, rows, qcols, ldq, &mq)) return e;
   if (int e = tc_maps(k, rows, kcols, ldk, &mk)) return e;
   if (int e = tc_maps(v, rows, vcols, ldv, &mv)) return e;
+  if (int e = tc_maps(out, rows, (long long)Hq * TD, ldo, &mo)) return e;
   AttnTcParams p{};
   p.mask = mask; p.o = (__nv_bfloat16*)out; p.ldo = ldo; p.lse = lse; p.B = B; p.L = L; p.Hq = Hq; p.Hkv = Hkv;
   p.scale = scale; p.causal = causal; p.qcol0 = qcol0; p.kcol0 = kcol0; p.vcol0 = vcol0;
+  p.dbg = g_attn_dbg;
   static bool attr = false;
   if (!attr) { DALM_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem)); attr = true; }
   dim3 grid((L + TB - 1) / TB, Hq, B);
-  attn_fwd_tc_kernel<<<grid, 160, kFwdSmem, (cudaStream_t)stream>>>(mq, mk, mv, p);
+  attn_fwd_tc_kernel<<<grid, 160, kFwdSmem, (cudaStream_t)stream>>>(mq, mk, mv, mo, p);
   count_launch();
   return check_launch("attn_fwd_tc_kernel");
 }
@@ -598,6 +632,10 @@ extern "C" int dalm_b200_attention_tc_bwd(const void* q, long long ldq, long lon
   if (int e = tc_maps(k, rows, kcols, ldk, &mk)) return e;
   if (int e = tc_maps(v, rows, vcols, ldv, &mv)) return e;
   if (int e = tc_maps(d_out, rows, docols, lddo, &mdo)) return e;
+  CUtensorMap mdq, mdk, mdv;
+  if (int e = tc_maps(dq, rows, (long long)Hq * TD, lddq, &mdq)) return e;
+  if (int e = tc_maps(dk, rows, (long long)Hkv * TD, lddk, &mdk)) return e;
+  if (int e = tc_maps(dv, rows, (long long)Hkv * TD, lddv, &mdv)) return e;
   AttnTcParams p{};
   p.mask = mask; p.lse = const_cast<float*>(lse); p.delta = delta; p.B = B; p.L = L; p.Hq = Hq; p.Hkv = Hkv;
   p.scale = scale; p.causal = causal;
@@ -614,9 +652,9 @@ extern "C" int dalm_b200_attention_tc_bwd(const void* q, long long ldq, long lon
                                                                       lddo, delta, B, L, Hq);
   if (int e = check_launch("attn_tc_delta_kernel")) return e;
   const int ntiles = (L + TB - 1) / TB;
-  attn_bwd_dkv_tc_kernel<<<dim3(ntiles, Hkv, B), 160, kDkvSmem, st>>>(mq, mk, mv, mdo, p);
+  attn_bwd_dkv_tc_kernel<<<dim3(ntiles, Hkv, B), 160, kDkvSmem, st>>>(mq, mk, mv, mdo, mdk, mdv, p);
   if (int e = check_launch("attn_bwd_dkv_tc_kernel")) return e;
-  attn_bwd_dq_tc_kernel<<<dim3(ntiles, Hq, B), 160, kDqSmem, st>>>(mq, mk, mv, mdo, p);
+  attn_bwd_dq_tc_kernel<<<dim3(ntiles, Hq, B), 160, kDqSmem, st>>>(mq, mk, mv, mdo, mdq, p);
   count_launch(3);
   return check_launch("attn_bwd_dq_tc_kernel");
 }

@@ -89,6 +89,8 @@ int dalm_b200_attention_tc_fwd(const void* q, long long ldq, long long qcols, in
                                const int64_t* mask, void* out, long long ldo, float* lse, int B, int L, int Hq, int Hkv,
                                int D, float scale, int causal, void* stream);
 
+/* tuning aid: a device buffer of 64 int64 receives clock64 phase timestamps of one forward CTA (NULL disables) */
+void dalm_b200_attention_tc_set_debug(void* dev_buffer_64xint64);
 int dalm_b200_attention_tc_bwd(const void* q, long long ldq, long long qcols, const void* k, long long ldk, long long kcols,
                                const void* v, long long ldv, long long vcols, const int64_t* mask, const void* out,
                                long long ldo, const float* lse, const void* d_out, long long lddo, long long docols,
