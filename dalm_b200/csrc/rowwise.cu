@@ -22,7 +22,13 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   const size_t r = blockIdx.x;
   const float* zr = z + r * H;
   float s = 0.f;
-  for (int i = threadIdx.x; i < H; i += blockDim.x) { const float v = zr[i]; row[i] = v; s += v; }
+  if ((H & 3) == 0) {
+    const float4* z4 = reinterpret_cast<const float4*>(zr);
+    float4* row4 = reinterpret_cast<float4*>(row);
+    for (int i = threadIdx.x; i < H / 4; i += blockDim.x) { const float4 v = z4[i]; row4[i] = v; s += (v.x + v.y) + (v.z + v.w); }
+  } else {
+    for (int i = threadIdx.x; i < H; i += blockDim.x) { const float v = zr[i]; row[i] = v; s += v; }
+  }
   const float mean = block_sum(s, red) / H;
   float q = 0.f;
   for (int i = threadIdx.x; i < H; i += blockDim.x) { const float d = row[i] - mean; q += d * d; }
@@ -54,6 +60,21 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
     }
     return;
   }
+  if (drop.p == 0.f && (H & 3) == 0 && (ld16 & 3) == 0) {        // vectorised plain path: 4 outputs per thread per iteration
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+    for (int i = threadIdx.x; i < H / 4; i += blockDim.x) {
+      const float4 x = row4[i], g = g4[i], b = b4[i];
+      const float4 v = make_float4((x.x - mean) * rstd * g.x + b.x, (x.y - mean) * rstd * g.y + b.y,
+                                   (x.z - mean) * rstd * g.z + b.z, (x.w - mean) * rstd * g.w + b.w);
+      if (y32) reinterpret_cast<float4*>(y32 + r * H)[i] = v;
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(y16 + r * ld16 + i * 4) = pk;
+    }
+    return;
+  }
   const unsigned long long dstream = drop.p > 0.f ? drop_stream(drop) : 0ull;
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
     float v = (row[i] - mean) * rstd * gamma[i] + beta[i];
@@ -78,14 +99,37 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   const size_t r = blockIdx.x;
   const float mean = mean_in[r], rstd = rstd_in[r];
   float s1 = 0.f, s2 = 0.f;
-  for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    float dy = 0.f;
-    if (dy_a) dy += dy_a[r * H + i];
-    if (dy_b) dy += __bfloat162float(dy_b[r * ldb + i]);
-    const float g = dy * gamma[i];
-    const float zz = (z[r * H + i] - mean) * rstd;
-    gbuf[i] = g; zh[i] = zz;
-    s1 += g; s2 += g * zz;
+  if ((H & 3) == 0 && (ldb & 3) == 0) {
+    const float4* z4 = reinterpret_cast<const float4*>(z + r * H);
+    const float4* a4 = dy_a ? reinterpret_cast<const float4*>(dy_a + r * H) : nullptr;
+    const uint2* b2 = dy_b ? reinterpret_cast<const uint2*>(dy_b + r * ldb) : nullptr;
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    for (int i = threadIdx.x; i < H / 4; i += blockDim.x) {
+      float4 dy = a4 ? a4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b2) {
+        const uint2 raw = b2[i];
+        const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+        const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+        dy.x += lo.x; dy.y += lo.y; dy.z += hi.x; dy.w += hi.y;
+      }
+      const float4 gg = g4[i], zz4 = z4[i];
+      const float4 g = make_float4(dy.x * gg.x, dy.y * gg.y, dy.z * gg.z, dy.w * gg.w);
+      const float4 zz = make_float4((zz4.x - mean) * rstd, (zz4.y - mean) * rstd, (zz4.z - mean) * rstd, (zz4.w - mean) * rstd);
+      reinterpret_cast<float4*>(gbuf)[i] = g;
+      reinterpret_cast<float4*>(zh)[i] = zz;
+      s1 += (g.x + g.y) + (g.z + g.w);
+      s2 += (g.x * zz.x + g.y * zz.y) + (g.z * zz.z + g.w * zz.w);
+    }
+  } else {
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+      float dy = 0.f;
+      if (dy_a) dy += dy_a[r * H + i];
+      if (dy_b) dy += __bfloat162float(dy_b[r * ldb + i]);
+      const float g = dy * gamma[i];
+      const float zz = (z[r * H + i] - mean) * rstd;
+      gbuf[i] = g; zh[i] = zz;
+      s1 += g; s2 += g * zz;
+    }
   }
   s1 = block_sum(s1, red) / H;
   s2 = block_sum(s2, red) / H;
@@ -109,6 +153,20 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 #pragma unroll
           for (int j = 0; j < 8; ++j) dz16[r * ld16 + i0 + j] = __float2bfloat16_rn(dm[j]);
         }
+      }
+    }
+    return;
+  }
+  if (drop16.p == 0.f && (H & 3) == 0 && (ld16 & 3) == 0) {
+    for (int i = threadIdx.x; i < H / 4; i += blockDim.x) {
+      const float4 g = reinterpret_cast<const float4*>(gbuf)[i], zz = reinterpret_cast<const float4*>(zh)[i];
+      const float4 d = make_float4(rstd * (g.x - s1 - zz.x * s2), rstd * (g.y - s1 - zz.y * s2), rstd * (g.z - s1 - zz.z * s2),
+                                   rstd * (g.w - s1 - zz.w * s2));
+      if (dz32) reinterpret_cast<float4*>(dz32 + r * H)[i] = d;
+      if (dz16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(d.x, d.y), hi = __floats2bfloat162_rn(d.z, d.w);
+        uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(dz16 + r * ld16 + i * 4) = pk;
       }
     }
     return;
