@@ -33,6 +33,7 @@ SIGNATURES = {
     "dalm_b200_lora_dx": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _F, _U, _U, _P, _P],
     "dalm_b200_small_matmul_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "dalm_b200_gemm_bf16_tn": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _F, _P, _I, _P, _L, _I, _I, _I, *_DROP, _P],
+    "dalm_b200_gemm_bf16": [_I, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _F, _P, _I, _P, _L, _I, _I, _I, *_DROP, _P],
     "dalm_b200_gemm_clear_cache": [],
     "dalm_b200_attention_fwd": [_P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _I, _I, _I, _I, _I, _F, _I, *_DROP, _P],
     "dalm_b200_attention_bwd": [_P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _P, _L, _P, _P, _L, _P, _L, _P, _L,
@@ -60,6 +61,10 @@ SIGNATURES = {
     "dalm_b200_pack_table": [_P, _I, _P],
     "dalm_b200_cast_f32_bf16": [_P, _L, _P, _L, _I, _I, _P],
     "dalm_b200_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P],
+    "dalm_b200_col_reduce": [_P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _P],
+    "dalm_b200_embed_scatter_add": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "dalm_b200_masked_add": [_P, _P, _L, _P, _I, _I, *_DROP, _P],
+    "dalm_b200_adam_step_shadow": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P],
 }
 _RESTYPES = {
     "dalm_b200_last_error": c_char_p,

@@ -158,7 +158,14 @@ template <int BN> struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * kStageTileBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+// LAYOUT selects how the two bf16 operands lie in HBM (the tensor core reads either major directly; nothing is transposed):
+//   0  "TN"  A[M,K], B[N,K]  both K-contiguous                 forward y = x W^T, and PEFT dgrad against resident W^T copies
+//   1  "NN"  A[M,K], B[K,N]  B is MN-major (N-contiguous)      dgrad dx = dy W straight from W[out,in] (full fine-tuning:
+//                                                              weights change every step, so no transposed copy is kept)
+//   2  "wgrad" A[K,M], B[K,N] both MN-major                    dW[out,in] = dy^T x : contraction over the token rows
+// MN-major stage tiles are stored [64 k-rows][64 elements = 128 B] per 64-wide chunk (8 KB, chunks LBO = 8 KB apart,
+// 8-row groups SBO = 1 KB apart), each chunk one TMA box of the row-major source.
+template <int BN, int LAYOUT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const GemmEpilogue ep) {
@@ -210,8 +217,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           unsigned char* sa = smem + stage * Cfg::STAGE_BYTES;
           unsigned char* sb = sa + Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if constexpr (LAYOUT == 2) {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, &tmap_a, &full_bar[stage], m_blk * BM + c * 64, kb * BK);
+          } else {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+          }
+          if constexpr (LAYOUT >= 1) {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmap_b, &full_bar[stage], n_blk * BN + c * 64, kb * BK);
+          } else {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -219,7 +236,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN) | (LAYOUT == 2 ? (1u << 15) : 0u) | (LAYOUT >= 1 ? (1u << 16) : 0u);
+      // k-step (16 elements of K) in 16-byte units of the descriptor start address: K-major +32 B inside the swizzle atom,
+      // MN-major +16 rows * 128 B
+      constexpr uint64_t a_step = LAYOUT == 2 ? 128 : 2, b_step = LAYOUT >= 1 ? 128 : 2;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -231,13 +251,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
-          const uint64_t adesc = make_sw128_kmajor_desc(sa);
-          const uint64_t bdesc = make_sw128_kmajor_desc(sb);
+          const uint64_t adesc = LAYOUT == 2 ? make_sw128_mnmajor_desc(sa, 8192, 1024) : make_sw128_kmajor_desc(sa);
+          const uint64_t bdesc = LAYOUT >= 1 ? make_sw128_mnmajor_desc(sb, 8192, 1024) : make_sw128_kmajor_desc(sb);
           const int krem = K - kb * BK;
           const int ksteps = krem >= BK ? (BK / 16) : ((krem + 15) / 16);   // skip all-zero (OOB) k-slices
           for (int k = 0; k < ksteps; ++k) {
-            // advance 16 bf16 = 32 B inside the 128B swizzle atom: +2 in the 16-byte-unit start address field
-            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16(d_tmem, adesc + a_step * (uint64_t)k, bdesc + b_step * (uint64_t)k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -471,19 +490,19 @@ int get_tmap(const void* ptr, long long rows, long long cols, long long ld, int 
   return 0;
 }
 
-template <int BN>
+template <int BN, int LAYOUT = 0>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmEpilogue& ep,
                        int max_ctas, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    DALM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    DALM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int num_tiles = ((ep.M + 127) / 128) * ((ep.N + BN - 1) / BN);
   int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, to, ep);
+  gemm_bf16_tn_kernel<BN, LAYOUT><<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, to, ep);
   count_launch();
   return check_launch("gemm_bf16_tn_kernel");
 }
@@ -509,6 +528,12 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
 
 using namespace dalm;
 
+extern "C" int dalm_b200_gemm_bf16(int layout, const void* A, long long lda, const void* B, long long ldb, void* out,
+                                   long long ldo, int out_f32, int M, int N, int K, float alpha, const float* bias,
+                                   int act, const void* resid, long long ldr, int resid_f32, int block_n,
+                                   int max_ctas, float drop_p, unsigned long long drop_seed,
+                                   unsigned long long drop_stream_id, const void* drop_offset, void* stream);
+
 // D[M,N] = act(alpha * A[M,K] B[N,K]^T + bias) + resid
 //   A: bf16 [M,K] row stride lda;  B: bf16 [N,K] row stride ldb;  out: bf16|fp32 [M,N] row stride ldo
 //   block_n: 0 = auto, or one of 64/128/256.   max_ctas: 0 = all SMs (used by tests to force multi-tile-per-CTA paths)
@@ -517,10 +542,22 @@ extern "C" int dalm_b200_gemm_bf16_tn(const void* A, long long lda, const void* 
                                       int act, const void* resid, long long ldr, int resid_f32, int block_n,
                                       int max_ctas, float drop_p, unsigned long long drop_seed,
                                       unsigned long long drop_stream_id, const void* drop_offset, void* stream) {
+  return dalm_b200_gemm_bf16(0, A, lda, B, ldb, out, ldo, out_f32, M, N, K, alpha, bias, act, resid, ldr, resid_f32, block_n,
+                             max_ctas, drop_p, drop_seed, drop_stream_id, drop_offset, stream);
+}
+
+// layout 0: A[M,K] B[N,K] (TN)   1: A[M,K] B[K,N] (NN, dgrad from W[out,in])   2: A[K,M] B[K,N] (wgrad, contraction over rows)
+extern "C" int dalm_b200_gemm_bf16(int layout, const void* A, long long lda, const void* B, long long ldb, void* out,
+                                   long long ldo, int out_f32, int M, int N, int K, float alpha, const float* bias,
+                                   int act, const void* resid, long long ldr, int resid_f32, int block_n,
+                                   int max_ctas, float drop_p, unsigned long long drop_seed,
+                                   unsigned long long drop_stream_id, const void* drop_offset, void* stream) {
+  DALM_REQUIRE(layout >= 0 && layout <= 2, "gemm: layout must be 0 (TN), 1 (NN) or 2 (wgrad)");
   DALM_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   DALM_REQUIRE((N % 8) == 0, "gemm: N=%d must be a multiple of 8", N);
-  DALM_REQUIRE((K % 8) == 0, "gemm: K=%d must be a multiple of 8", K);
-  DALM_REQUIRE(lda >= K && ldb >= K && ldo >= N, "gemm: leading dimensions too small");
+  DALM_REQUIRE((K % 8) == 0 || layout == 2, "gemm: K=%d must be a multiple of 8", K);
+  DALM_REQUIRE((M % 8) == 0 || layout != 2, "gemm: M=%d must be a multiple of 8 for the wgrad layout", M);
+  DALM_REQUIRE(lda >= (layout == 2 ? M : K) && ldb >= (layout >= 1 ? N : K) && ldo >= N, "gemm: leading dimensions too small");
   DALM_REQUIRE((ldo % (out_f32 ? 4 : 8)) == 0, "gemm: ldo=%lld breaks 16-byte row alignment", ldo);
   DALM_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "gemm: out is not 16-byte aligned");
   if (resid) {
@@ -541,10 +578,13 @@ extern "C" int dalm_b200_gemm_bf16_tn(const void* A, long long lda, const void* 
   DALM_REQUIRE(bn == 64 || bn == 128 || bn == 256 || bn == 2128 || bn == 2256 || bn == 3256 || bn == 4256,
                "gemm: block_n must be 0, 64/128/256 (single CTA) or 2128/2256 (CTA pair)");
   const bool pair = bn > 1000;
+  DALM_REQUIRE(!(pair && layout != 0), "gemm: the CTA-pair kernel only takes the TN layout");
   const int tile_n = pair ? bn % 1000 : bn;
   CUtensorMap ta, tb, to;
-  if (int e = get_tmap(A, M, K, lda, 128, &ta)) return e;
-  if (int e = get_tmap(B, N, K, ldb, pair ? tile_n / 2 : tile_n, &tb)) return e;
+  if (layout == 2) { if (int e = get_tmap(A, K, M, lda, 64, &ta)) return e; }
+  else             { if (int e = get_tmap(A, M, K, lda, 128, &ta)) return e; }
+  if (layout >= 1) { if (int e = get_tmap(B, K, N, ldb, 64, &tb)) return e; }
+  else             { if (int e = get_tmap(B, N, K, ldb, pair ? tile_n / 2 : tile_n, &tb)) return e; }
   if (int e = get_tmap(out, M, N, ldo, 128, &to, out_f32)) return e;
   DALM_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "gemm: dropout p must be in [0,1)");
   GemmEpilogue ep{out, ldo, out_f32, bias, resid, ldr, resid_f32, act, alpha, M, N, K,
@@ -554,6 +594,16 @@ extern "C" int dalm_b200_gemm_bf16_tn(const void* A, long long lda, const void* 
   if (bn == 3256) return launch_gemm2<256, 3>(ta, tb, to, ep, max_ctas, st);     // tuning probes (fewer stages)
   if (bn == 4256) return launch_gemm2<256, 4>(ta, tb, to, ep, max_ctas, st);
   if (bn == 2128) return launch_gemm2<128>(ta, tb, to, ep, max_ctas, st);
+  if (layout == 1) {
+    if (bn == 256) return launch_gemm<256, 1>(ta, tb, to, ep, max_ctas, st);
+    if (bn == 128) return launch_gemm<128, 1>(ta, tb, to, ep, max_ctas, st);
+    return launch_gemm<64, 1>(ta, tb, to, ep, max_ctas, st);
+  }
+  if (layout == 2) {
+    if (bn == 256) return launch_gemm<256, 2>(ta, tb, to, ep, max_ctas, st);
+    if (bn == 128) return launch_gemm<128, 2>(ta, tb, to, ep, max_ctas, st);
+    return launch_gemm<64, 2>(ta, tb, to, ep, max_ctas, st);
+  }
   if (bn == 256) return launch_gemm<256>(ta, tb, to, ep, max_ctas, st);
   if (bn == 128) return launch_gemm<128>(ta, tb, to, ep, max_ctas, st);
   return launch_gemm<64>(ta, tb, to, ep, max_ctas, st);

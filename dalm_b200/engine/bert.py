@@ -21,6 +21,7 @@ from typing import Dict, List, Optional
 import torch
 
 from .. import ops
+from .dense import DenseBank
 from .lora import LoraBank
 
 bf16, f32 = torch.bfloat16, torch.float32
@@ -43,8 +44,12 @@ class BertEncoder(torch.nn.Module):
     LORA_TARGETS = ("query", "key", "value")          # reference rag_e2e_base_model.py:66-68
 
     def __init__(self, cfg: Dict, state_dict: Dict[str, torch.Tensor], device="cuda", lora: bool = False,
-                 lora_seed: int = 0):
+                 lora_seed: int = 0, full: bool = False):
+        """lora: PEFT mode (base frozen, rank-8 adapters on query/key/value). full: every parameter trainable (the
+        reference's behaviour without --use-peft): weights live in a DenseBank, no transposed copies are kept."""
         super().__init__()
+        if lora and full:
+            raise ValueError("lora and full fine-tuning are mutually exclusive for one model")
         self.cfg = cfg
         self.H = H = cfg["hidden_size"]
         self.F = F = cfg["intermediate_size"]
@@ -60,12 +65,130 @@ class BertEncoder(torch.nn.Module):
         self.Ra = 3 * self.r if lora else 0
         sd = {k[len("bert."):] if k.startswith("bert.") else k: v for k, v in state_dict.items()}
         g = lambda k, dt: sd[k].to(device=self.dev, dtype=dt).contiguous()
+        self.full: Optional[DenseBank] = None
+        self.layers: List[Dict[str, torch.Tensor]] = []
+        if full:
+            self._init_full(sd)
+        else:
+            self._init_frozen(sd, g, lora)
+        self.pooler = {k: v for k, v in sd.items() if k.startswith("pooler.")}   # carried for save_pretrained only
+        # dropout (active only in train() mode, like the HF module the reference wraps; from_pretrained returns eval())
+        self.p_hidden = float(cfg.get("hidden_dropout_prob", 0.1))
+        self.p_attn = float(cfg.get("attention_probs_dropout_prob", 0.1))
+        self.p_lora = 0.05 if lora else 0.0                   # reference rag_e2e_base_model.py:151 (lora_dropout)
+        self.drop_seed = 0x5DA1B200 + lora_seed
+        self.drop_offset = torch.zeros(1, dtype=torch.int64, device=self.dev)      # bumped once per (graphed) step
+        self._call = 0
+        self.lora: Optional[LoraBank] = None
+        if lora:
+            specs = [(f"encoder.layer.{l}.attention.self.{n}", H, H) for l in range(self.nl) for n in self.LORA_TARGETS]
+            self.lora = LoraBank(specs, r=self.r, alpha=16, dropout=0.05, device=self.dev, seed=lora_seed)
+            self.lora_flat = torch.nn.Parameter(self.lora.flat, requires_grad=True)
+            self.lora_flat.grad = self.lora.grad
+            self.repack_lora()
+        self.eval()
+
+    # ---- what is trainable ---------------------------------------------------------------------------------------
+    @property
+    def trainable(self) -> bool:
+        return self.lora is not None or self.full is not None
+
+    @property
+    def anchor(self) -> torch.nn.Parameter:
+        """the flat parameter that ties engine outputs to the autograd graph (bridge.py)"""
+        return self.lora_flat if self.lora is not None else self.full_flat
+
+    def grad_buffers(self) -> List[torch.Tensor]:
+        """flat gradient buffers for the data-parallel all-reduce"""
+        return [b.grad for b in (self.lora, self.full) if b is not None]
+
+    def banks(self) -> list:
+        return [b for b in (self.lora, self.full) if b is not None]
+
+    def zero_grad_buffers(self) -> None:
+        if self.lora is not None:
+            self.lora.zero_grad()
+        if self.full is not None:
+            self.full.zero_grad()
+
+    def _param_map(self):
+        """engine tensor -> (gradient kind, HF state-dict names whose rows it concatenates)"""
+        E = "embeddings."
+        m = [("word", "acc", [E + "word_embeddings.weight"]), ("pos", "acc", [E + "position_embeddings.weight"]),
+             ("type", "acc", [E + "token_type_embeddings.weight"]), ("emb_g", "acc", [E + "LayerNorm.weight"]),
+             ("emb_b", "acc", [E + "LayerNorm.bias"])]
+        for l in range(self.nl):
+            p = f"encoder.layer.{l}."
+            qkv = [p + f"attention.self.{n}" for n in self.LORA_TARGETS]
+            m += [(f"L{l}.Wqkv", "gemm", [n + ".weight" for n in qkv]), (f"L{l}.bqkv", "acc", [n + ".bias" for n in qkv]),
+                  (f"L{l}.Wo", "gemm", [p + "attention.output.dense.weight"]), (f"L{l}.bo", "acc", [p + "attention.output.dense.bias"]),
+                  (f"L{l}.ln1_g", "acc", [p + "attention.output.LayerNorm.weight"]),
+                  (f"L{l}.ln1_b", "acc", [p + "attention.output.LayerNorm.bias"]),
+                  (f"L{l}.Wi", "gemm", [p + "intermediate.dense.weight"]), (f"L{l}.bi", "acc", [p + "intermediate.dense.bias"]),
+                  (f"L{l}.Wo2", "gemm", [p + "output.dense.weight"]), (f"L{l}.bo2", "acc", [p + "output.dense.bias"]),
+                  (f"L{l}.ln2_g", "acc", [p + "output.LayerNorm.weight"]), (f"L{l}.ln2_b", "acc", [p + "output.LayerNorm.bias"])]
+        return m
+
+    def _init_full(self, sd) -> None:
+        pm = self._param_map()
+        self._rows = {key: [(n, int(sd[n].shape[0])) for n in names] for key, _, names in pm}
+        specs = [(key, (sum(r for _, r in self._rows[key]),) + tuple(sd[names[0]].shape[1:]), kind) for key, kind, names in pm]
+        bank = DenseBank(specs, self.dev)
+        for key, _, names in pm:
+            dst, r = bank.w32(key), 0
+            for n in names:
+                t = sd[n]
+                dst[r:r + t.shape[0]].copy_(t.to(self.dev, f32))
+                r += t.shape[0]
+        bank.sync_shadow()
+        self.full = bank
+        self.full_flat = torch.nn.Parameter(bank.p32, requires_grad=True)
+        self.full_flat.grad = bank.g32
+        self.full_flat._dalm_bank = bank
+        self.word, self.pos, self.type0 = bank.w16("word"), bank.w16("pos"), bank.w16("type")[0]
+        self.emb_g, self.emb_b = bank.w32("emb_g"), bank.w32("emb_b")
+        for l in range(self.nl):
+            k = lambda n: f"L{l}.{n}"
+            self.layers.append({"Wqkv_aug": bank.w16(k("Wqkv")), "bqkv": bank.w32(k("bqkv")), "Wo": bank.w16(k("Wo")),
+                                "bo": bank.w32(k("bo")), "ln1_g": bank.w32(k("ln1_g")), "ln1_b": bank.w32(k("ln1_b")),
+                                "Wi": bank.w16(k("Wi")), "bi": bank.w32(k("bi")), "Wo2": bank.w16(k("Wo2")),
+                                "bo2": bank.w32(k("bo2")), "ln2_g": bank.w32(k("ln2_g")), "ln2_b": bank.w32(k("ln2_b"))})
+
+    def hf_state_dict(self) -> Dict[str, torch.Tensor]:
+        """fp32 CPU tensors under HF BertModel names (save_pretrained of a fully fine-tuned encoder)"""
+        if self.full is None:
+            raise RuntimeError("hf_state_dict: only fully fine-tuned models own their weights (PEFT mode saves adapters)")
+        out = {}
+        for key, parts in self._rows.items():
+            w, r = self.full.w32(key), 0
+            for name, rows in parts:
+                out[name] = w[r:r + rows].detach().cpu().clone()
+                r += rows
+        out.update({k: v.detach().float().cpu() for k, v in self.pooler.items()})
+        return out
+
+    def load_hf_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        sd = {k[len("bert."):] if k.startswith("bert.") else k: v for k, v in sd.items()}
+        for key, parts in self._rows.items():
+            w, r = self.full.w32(key), 0
+            for name, rows in parts:
+                w[r:r + rows].copy_(sd[name].to(self.dev, f32))
+                r += rows
+        self.full.sync_shadow()
+
+    def _dgrad(self, dy: torch.Tensor, W: Dict[str, torch.Tensor], name: str) -> torch.Tensor:
+        """dx = dy W: against the resident transposed copy (frozen base) or W[out,in] itself read MN-major (full mode)"""
+        if self.full is not None:
+            return ops.gemm(dy, W[name], layout=1)
+        return ops.gemm(dy, W[name + "T"])
+
+    def _init_frozen(self, sd, g, lora: bool) -> None:
+        H = self.H
         self.word = g("embeddings.word_embeddings.weight", bf16)
         self.pos = g("embeddings.position_embeddings.weight", bf16)
         self.type0 = g("embeddings.token_type_embeddings.weight", bf16)[0].contiguous()
         self.emb_g = g("embeddings.LayerNorm.weight", f32)
         self.emb_b = g("embeddings.LayerNorm.bias", f32)
-        self.layers: List[Dict[str, torch.Tensor]] = []
         for l in range(self.nl):
             p = f"encoder.layer.{l}."
             W = {}
@@ -92,22 +215,6 @@ class BertEncoder(torch.nn.Module):
             W["ln2_g"] = g(p + "output.LayerNorm.weight", f32)
             W["ln2_b"] = g(p + "output.LayerNorm.bias", f32)
             self.layers.append(W)
-        self.pooler = {k: v for k, v in sd.items() if k.startswith("pooler.")}   # carried for save_pretrained only
-        # dropout (active only in train() mode, like the HF module the reference wraps; from_pretrained returns eval())
-        self.p_hidden = float(cfg.get("hidden_dropout_prob", 0.1))
-        self.p_attn = float(cfg.get("attention_probs_dropout_prob", 0.1))
-        self.p_lora = 0.05 if lora else 0.0                   # reference rag_e2e_base_model.py:151 (lora_dropout)
-        self.drop_seed = 0x5DA1B200 + lora_seed
-        self.drop_offset = torch.zeros(1, dtype=torch.int64, device=self.dev)      # bumped once per (graphed) step
-        self._call = 0
-        self.lora: Optional[LoraBank] = None
-        if lora:
-            specs = [(f"encoder.layer.{l}.attention.self.{n}", H, H) for l in range(self.nl) for n in self.LORA_TARGETS]
-            self.lora = LoraBank(specs, r=self.r, alpha=16, dropout=0.05, device=self.dev, seed=lora_seed)
-            self.lora_flat = torch.nn.Parameter(self.lora.flat, requires_grad=True)
-            self.lora_flat.grad = self.lora.grad
-            self.repack_lora()
-        self.eval()
 
     def _drop(self, p: float, call: int, layer: int, site: int):
         """dropout descriptor of one site, or None when inactive (eval mode / p == 0)"""
@@ -166,6 +273,9 @@ class BertEncoder(torch.nn.Module):
         x_aug = _aug_buf(M, H, Ra, self.dev)
         x32, _, mean, rstd = ops.layernorm_fwd(z, self.emb_g, self.emb_b, self.eps, y16=x_aug[:, :H],
                                                drop=self._drop(self.p_hidden, call, 255, 0))
+        if save and self.full is not None:                     # the embedding tables are trainable: keep their LN state
+            ctx.z_emb, ctx.mean_e, ctx.rstd_e = z, mean, rstd
+            ctx.ids = [ids.contiguous() for ids, _ in segments]
         for li, W in enumerate(self.layers):
             a = _Ctx()
             a.x_aug = x_aug
@@ -202,14 +312,21 @@ class BertEncoder(torch.nn.Module):
         self.backward_segments(ctx, [d_hidden])
 
     def backward_segments(self, ctx: _Ctx, d_hiddens) -> None:
-        if self.lora is None:
+        if not self.trainable:
             return                                           # nothing trainable below the pooled output
         M, H = ctx.M, self.H
         d = d_hiddens[0].reshape(-1, H) if len(d_hiddens) == 1 else torch.cat([t.reshape(-1, H) for t in d_hiddens], 0)
+        d = d.contiguous()
         last, Wl = ctx.layers[self.nl - 1], self.layers[self.nl - 1]
-        last._pre = ops.layernorm_bwd(last.z2, Wl["ln2_g"], last.m2, last.r2, dy_f32=d.contiguous(),
+        if self.full is not None:
+            ctx.acc = self.full.begin_backward()
+            ops.col_reduce_(dy_f32=d, z=last.z2, mean=last.m2, rstd=last.r2, out_sum=self.full.g(f"L{self.nl - 1}.ln2_b"),
+                            out_prod=self.full.g(f"L{self.nl - 1}.ln2_g"))
+        last._pre = ops.layernorm_bwd(last.z2, Wl["ln2_g"], last.m2, last.r2, dy_f32=d,
                                       drop16=self._bdrop(ctx, self.p_hidden, self.nl - 1, 2))
         self._bwd_from_ln2(ctx, self.nl - 1)
+        if self.full is not None:
+            self.full.end_backward()
 
     def _bdrop(self, ctx, p: float, layer: int, site: int):
         """the forward call's dropout descriptor, regenerated for its backward"""
@@ -220,16 +337,31 @@ class BertEncoder(torch.nn.Module):
     def _bwd_from_ln2(self, ctx: _Ctx, l_start: int) -> None:
         """continue the backward at layer l_start whose LN2 input gradient has already been computed (stashed in _pre)"""
         M, H, Ra, r = ctx.M, self.H, self.Ra, self.r
+        bank = self.full
+        acc = getattr(ctx, "acc", False)
+        G = (lambda l, n: bank.g(f"L{l}.{n}")) if bank is not None else None
         for l in range(l_start, -1, -1):
             W, a = self.layers[l], ctx.layers[l]
             dz2_32, dz2_16 = a._pre
             del a._pre
-            dact = ops.gemm(dz2_16, W["Wo2T"])
+            if bank is not None:                               # output.dense: dW = dz2^T act, db = colsum(dz2)
+                ops.wgrad_(dz2_16, a.act, G(l, "Wo2"), acc)
+                ops.col_reduce_(dy_bf16=dz2_16, out_sum=G(l, "bo2"))
+            dact = self._dgrad(dz2_16, W, "Wo2")
             ops.gelu_bwd_(a.pre, dact)
-            dh_16 = ops.gemm(dact, W["WiT"])
+            if bank is not None:                               # intermediate.dense
+                ops.wgrad_(dact, a.h_aug, G(l, "Wi"), acc)
+                ops.col_reduce_(dy_bf16=dact, out_sum=G(l, "bi"))
+            dh_16 = self._dgrad(dact, W, "Wi")
+            if bank is not None:                               # attention.output.LayerNorm
+                ops.col_reduce_(dy_f32=dz2_32, dy_bf16=dh_16, z=a.z1, mean=a.m1, rstd=a.r1, out_sum=G(l, "ln1_b"),
+                                out_prod=G(l, "ln1_g"))
             dz1_32, dz1_16 = ops.layernorm_bwd(a.z1, W["ln1_g"], a.m1, a.r1, dy_f32=dz2_32, dy_bf16=dh_16,
                                                drop16=self._bdrop(ctx, self.p_hidden, l, 1))
-            datt = ops.gemm(dz1_16, W["WoT"])
+            if bank is not None:                               # attention.output.dense
+                ops.wgrad_(dz1_16, a.att, G(l, "Wo"), acc)
+                ops.col_reduce_(dy_bf16=dz1_16, out_sum=G(l, "bo"))
+            datt = self._dgrad(dz1_16, W, "Wo")
             dqkv_aug = _aug_buf(M, 3 * H, Ra, self.dev)
             for si, ((B, L, mask, s0), lse) in enumerate(zip(ctx.segs, a.lse)):
                 rows = slice(s0, s0 + B * L)
@@ -237,6 +369,9 @@ class BertEncoder(torch.nn.Module):
                                   datt[rows], B, L, self.nh, self.nh, self.hd, causal=False, dq=dqkv_aug[rows, :H],
                                   dk=dqkv_aug[rows, H:2 * H], dv=dqkv_aug[rows, 2 * H:3 * H],
                                   drop=self._bdrop(ctx, self.p_attn, l, 8 + si))
+            if bank is not None:
+                self._bwd_full_tail(ctx, l, dqkv_aug, dz1_32, acc)
+                continue
             for j, n in enumerate(self.LORA_TARGETS):
                 # g_j = dY_j (alpha/r) B_j : only the target's own column block is read
                 ops.skinny_gemm(dqkv_aug[:, j * H:(j + 1) * H], W["Bblk"][j * r:(j + 1) * r, j * H:(j + 1) * H],
@@ -261,3 +396,24 @@ class BertEncoder(torch.nn.Module):
             p, Wp = ctx.layers[l - 1], self.layers[l - 1]
             p._pre = ops.layernorm_bwd(p.z2, Wp["ln2_g"], p.m2, p.r2, dy_f32=dz1_32, dy_bf16=dx_16,
                                        drop16=self._bdrop(ctx, self.p_hidden, l - 1, 2))
+
+    def _bwd_full_tail(self, ctx: _Ctx, l: int, dqkv: torch.Tensor, dz1_32: torch.Tensor, acc: bool) -> None:
+        """full fine-tuning: fused q|k|v projection gradients, then either the previous layer's output LayerNorm or (l == 0)
+        the embedding block: dropout -> LayerNorm -> word / position / token-type tables"""
+        bank, W, a, H = self.full, self.layers[l], ctx.layers[l], self.H
+        ops.wgrad_(dqkv, a.x_aug[:, :H], bank.g(f"L{l}.Wqkv"), acc)
+        ops.col_reduce_(dy_bf16=dqkv, out_sum=bank.g(f"L{l}.bqkv"))
+        dx_16 = ops.gemm(dqkv, W["Wqkv_aug"], layout=1)
+        if l > 0:
+            p, Wp = ctx.layers[l - 1], self.layers[l - 1]
+            ops.col_reduce_(dy_f32=dz1_32, dy_bf16=dx_16, z=p.z2, mean=p.m2, rstd=p.r2, out_sum=bank.g(f"L{l - 1}.ln2_b"),
+                            out_prod=bank.g(f"L{l - 1}.ln2_g"))
+            p._pre = ops.layernorm_bwd(p.z2, Wp["ln2_g"], p.m2, p.r2, dy_f32=dz1_32, dy_bf16=dx_16,
+                                       drop16=self._bdrop(ctx, self.p_hidden, l - 1, 2))
+            return
+        g = ops.masked_add(dz1_32, dx_16, drop=self._bdrop(ctx, self.p_hidden, 255, 0), out=dz1_32)   # through the embedding dropout
+        ops.col_reduce_(dy_f32=g, z=ctx.z_emb, mean=ctx.mean_e, rstd=ctx.rstd_e, out_sum=bank.g("emb_b"), out_prod=bank.g("emb_g"))
+        dz, _ = ops.layernorm_bwd(ctx.z_emb, self.emb_g, ctx.mean_e, ctx.rstd_e, dy_f32=g, want_bf16=False)
+        for ids, (B, L, _, s0) in zip(ctx.ids, ctx.segs):
+            ops.embed_scatter_add_(dz[s0:s0 + B * L], ids, bank.g("word"), bank.g("pos"), L)
+        ops.col_reduce_(dy_f32=dz, out_sum=bank.g("type")[0])                 # token_type_ids are all zero (reference quirk 7)

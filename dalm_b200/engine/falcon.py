@@ -68,11 +68,19 @@ class FalconDecoder(torch.nn.Module):
             })
         self._rope_cache: Dict[int, tuple] = {}
         self.lora = None
+        self.full = None
+        self.trainable = False                                 # forward-only: no backward is built for Falcon yet
         self.drop_offset = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.eval()
 
     def repack_lora(self) -> None:
         pass
+
+    def banks(self) -> list:
+        return []
+
+    def grad_buffers(self) -> list:
+        return []
 
     def _rope(self, L: int):
         if L not in self._rope_cache:

@@ -18,6 +18,7 @@ from typing import Dict, List, Optional
 import torch
 
 from .. import ops
+from .dense import DenseBank
 from .lora import LoraBank
 
 bf16, f32 = torch.bfloat16, torch.float32
@@ -39,8 +40,12 @@ class LlamaDecoder(torch.nn.Module):
     LORA_TARGETS = ("q_proj", "v_proj")               # reference rag_e2e_base_model.py:76-77
 
     def __init__(self, cfg: Dict, state_dict: Dict[str, torch.Tensor], device="cuda", lora: bool = False,
-                 lora_seed: int = 1):
+                 lora_seed: int = 1, full: bool = False):
+        """lora: PEFT mode (frozen base + rank-8 adapters on q_proj / v_proj). full: every parameter trainable (reference
+        behaviour without --use-peft): weights in a DenseBank (fp32 master + bf16 shadow), no transposed copies."""
         super().__init__()
+        if lora and full:
+            raise ValueError("lora and full fine-tuning are mutually exclusive for one model")
         self.cfg = cfg
         self.H = H = cfg["hidden_size"]
         self.F = F = cfg["intermediate_size"]
@@ -61,15 +66,129 @@ class LlamaDecoder(torch.nn.Module):
         self.Ra = 2 * self.r if lora else 0
         sd = state_dict
         g = lambda k, dt: sd[k].to(device=self.dev, dtype=dt).contiguous()
+        self.Vp = (self.V + 7) // 8 * 8                       # GEMM N granularity; extra rows are zero and never scored
+        self.full: Optional[DenseBank] = None
+        self.layers: List[Dict[str, torch.Tensor]] = []
+        if full:
+            self._init_full(sd)
+        else:
+            self._init_frozen(sd, g, lora)
+        self._rope_cache: Dict[int, tuple] = {}
+        # Llama has no hidden / attention dropout (attention_dropout = 0); only peft's LoRA input dropout (0.05) applies
+        self.p_lora = 0.05 if lora else 0.0
+        self.drop_seed = 0x11A3AB200 + lora_seed
+        self.drop_offset = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self._call = 0
+        self.lora: Optional[LoraBank] = None
+        if lora:
+            outs = {"q_proj": self.Nq, "v_proj": self.Nkv}
+            specs = [(f"model.layers.{l}.self_attn.{n}", H, outs[n]) for l in range(self.nl) for n in self.LORA_TARGETS]
+            self.lora = LoraBank(specs, r=self.r, alpha=16, dropout=0.05, device=self.dev, seed=lora_seed)
+            self.lora_flat = torch.nn.Parameter(self.lora.flat, requires_grad=True)
+            self.lora_flat.grad = self.lora.grad
+            self.repack_lora()
+        self.eval()                                           # like from_pretrained(): dropout only after .train()
+
+    # ---- what is trainable ---------------------------------------------------------------------------------------
+    @property
+    def trainable(self) -> bool:
+        return self.lora is not None or self.full is not None
+
+    @property
+    def anchor(self) -> torch.nn.Parameter:
+        return self.lora_flat if self.lora is not None else self.full_flat
+
+    def grad_buffers(self) -> List[torch.Tensor]:
+        return [b.grad for b in (self.lora, self.full) if b is not None]
+
+    def banks(self) -> list:
+        return [b for b in (self.lora, self.full) if b is not None]
+
+    def zero_grad_buffers(self) -> None:
+        if self.lora is not None:
+            self.lora.zero_grad()
+        if self.full is not None:
+            self.full.zero_grad()
+
+    def _param_map(self, has_head: bool):
+        m = [("embed", "acc", ["model.embed_tokens.weight"]), ("norm_g", "acc", ["model.norm.weight"])]
+        if has_head:
+            m.append(("lm_head", "gemm", ["lm_head.weight"]))
+        for l in range(self.nl):
+            p = f"model.layers.{l}."
+            m += [(f"L{l}.Wqkv", "gemm", [p + f"self_attn.{n}_proj.weight" for n in "qkv"]),
+                  (f"L{l}.Wo", "gemm", [p + "self_attn.o_proj.weight"]),
+                  (f"L{l}.Wgu", "gemm", [p + "mlp.gate_proj.weight", p + "mlp.up_proj.weight"]),
+                  (f"L{l}.Wd", "gemm", [p + "mlp.down_proj.weight"]),
+                  (f"L{l}.g1", "acc", [p + "input_layernorm.weight"]), (f"L{l}.g2", "acc", [p + "post_attention_layernorm.weight"])]
+        return m
+
+    def _init_full(self, sd) -> None:
+        has_head = "lm_head.weight" in sd
+        if not has_head and self.Vp != self.V:
+            raise NotImplementedError("full fine-tuning with tied embeddings needs vocab_size % 8 == 0")
+        pm = self._param_map(has_head)
+        self._rows = {key: [(n, int(sd[n].shape[0])) for n in names] for key, _, names in pm}
+        specs = []
+        for key, kind, names in pm:
+            rows = sum(r for _, r in self._rows[key])
+            if key == "lm_head":
+                rows = self.Vp                                                   # zero rows up to the GEMM granularity
+            specs.append((key, (rows,) + tuple(sd[names[0]].shape[1:]), kind))
+        bank = DenseBank(specs, self.dev)
+        for key, _, names in pm:
+            dst, r = bank.w32(key), 0
+            for n in names:
+                t = sd[n]
+                dst[r:r + t.shape[0]].copy_(t.to(self.dev, f32))
+                r += t.shape[0]
+        bank.sync_shadow()
+        self.full = bank
+        self.full_flat = torch.nn.Parameter(bank.p32, requires_grad=True)
+        self.full_flat.grad = bank.g32
+        self.full_flat._dalm_bank = bank
+        self.embed, self.norm_g = bank.w16("embed"), bank.w32("norm_g")
+        self.tied = not has_head
+        self.lm_head = bank.w16("lm_head") if has_head else self.embed
+        for l in range(self.nl):
+            k = lambda n: f"L{l}.{n}"
+            self.layers.append({"Wqkv_aug": bank.w16(k("Wqkv")), "Wo": bank.w16(k("Wo")), "Wgu": bank.w16(k("Wgu")),
+                                "Wd": bank.w16(k("Wd")), "g1": bank.w32(k("g1")), "g2": bank.w32(k("g2"))})
+
+    def hf_state_dict(self) -> Dict[str, torch.Tensor]:
+        """fp32 CPU tensors under HF LlamaForCausalLM names (save_pretrained of a fully fine-tuned decoder)"""
+        if self.full is None:
+            raise RuntimeError("hf_state_dict: only fully fine-tuned models own their weights (PEFT mode saves adapters)")
+        out = {}
+        for key, parts in self._rows.items():
+            w, r = self.full.w32(key), 0
+            for name, rows in parts:
+                out[name] = w[r:r + rows].detach().cpu().clone()
+                r += rows
+        return out
+
+    def load_hf_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        for key, parts in self._rows.items():
+            w, r = self.full.w32(key), 0
+            for name, rows in parts:
+                w[r:r + rows].copy_(sd[name].to(self.dev, f32))
+                r += rows
+        self.full.sync_shadow()
+
+    def _dgrad(self, dy: torch.Tensor, W: Dict[str, torch.Tensor], name: str) -> torch.Tensor:
+        if self.full is not None:
+            return ops.gemm(dy, W[name], layout=1)
+        return ops.gemm(dy, W[name + "T"])
+
+    def _init_frozen(self, sd, g, lora: bool) -> None:
+        H = self.H
         self.embed = g("model.embed_tokens.weight", bf16)
         self.norm_g = g("model.norm.weight", f32)
         lm = g("lm_head.weight", bf16) if "lm_head.weight" in sd else self.embed      # tied / headless (AutoModel) checkpoints
-        self.Vp = (self.V + 7) // 8 * 8                       # GEMM N granularity; extra rows are zero and never scored
         if self.Vp != self.V:
             lm = torch.cat([lm, torch.zeros(self.Vp - self.V, H, dtype=bf16, device=self.dev)], 0)
         self.lm_head = lm
         self.lm_headT = self.lm_head.t().contiguous()
-        self.layers: List[Dict[str, torch.Tensor]] = []
         H_, Ra = H, self.Ra
         for l in range(self.nl):
             p = f"model.layers.{l}."
@@ -93,21 +212,6 @@ class LlamaDecoder(torch.nn.Module):
             W["g1"] = g(p + "input_layernorm.weight", f32)
             W["g2"] = g(p + "post_attention_layernorm.weight", f32)
             self.layers.append(W)
-        self._rope_cache: Dict[int, tuple] = {}
-        # Llama has no hidden / attention dropout (attention_dropout = 0); only peft's LoRA input dropout (0.05) applies
-        self.p_lora = 0.05 if lora else 0.0
-        self.drop_seed = 0x11A3AB200 + lora_seed
-        self.drop_offset = torch.zeros(1, dtype=torch.int64, device=self.dev)
-        self._call = 0
-        self.lora: Optional[LoraBank] = None
-        if lora:
-            outs = {"q_proj": self.Nq, "v_proj": self.Nkv}
-            specs = [(f"model.layers.{l}.self_attn.{n}", H, outs[n]) for l in range(self.nl) for n in self.LORA_TARGETS]
-            self.lora = LoraBank(specs, r=self.r, alpha=16, dropout=0.05, device=self.dev, seed=lora_seed)
-            self.lora_flat = torch.nn.Parameter(self.lora.flat, requires_grad=True)
-            self.lora_flat.grad = self.lora.grad
-            self.repack_lora()
-        self.eval()                                           # like from_pretrained(): dropout only after .train()
 
     def _drop(self, training: bool, call: int, layer: int):
         if not training or self.p_lora <= 0.0:
@@ -162,9 +266,13 @@ class LlamaDecoder(torch.nn.Module):
         return ctx.hf.float().view(B, L, self.H), ctx
 
     def backward_hidden(self, ctx: _Ctx, d_hidden: torch.Tensor) -> None:
-        """gradient w.r.t. the last hidden state (fp32 [B,L,H]) -> LoRA gradients"""
-        if self.lora is None:
+        """gradient w.r.t. the last hidden state (fp32 [B,L,H]) -> parameter gradients"""
+        if not self.trainable:
             return
+        if self.full is not None:
+            ctx.acc = self.full.begin_backward()
+            if not ctx.acc and not self.tied:
+                self.full.g("lm_head").zero_()                 # the head is not on this path: its fresh gradient is zero
         self._backward_body(ctx, ops.cast_f32_bf16(d_hidden.reshape(ctx.B * ctx.L, self.H).contiguous()))
 
     def _forward_body(self, ids: torch.Tensor, mask: torch.Tensor, save: bool = True):
@@ -173,6 +281,7 @@ class LlamaDecoder(torch.nn.Module):
         cos_t, sin_t = self._rope(L)
         ctx = _Ctx()
         ctx.B, ctx.L, ctx.mask, ctx.layers = B, L, mask.contiguous(), []
+        ctx.ids = ids.contiguous()
         self._call += 1
         ctx.call, ctx.training = self._call, self.training
         x = ops.embed_gather(ids, self.embed)                                    # fp32 residual stream [M,H]
@@ -202,8 +311,8 @@ class LlamaDecoder(torch.nn.Module):
 
     # ------------------------------------------------------------------------------------------------------------
     def backward_logits(self, ctx: _Ctx, dlogits: torch.Tensor) -> None:
-        """dlogits bf16 [B,L,V]; accumulates LoRA gradients (base weights frozen: PEFT mode)."""
-        if self.lora is None:
+        """dlogits bf16 [B,L,V]; accumulates LoRA gradients (PEFT mode) or all parameter gradients (full mode)."""
+        if not self.trainable:
             return
         B, L = ctx.B, ctx.L
         M, H, F, Ra, r = B * L, self.H, self.F, self.Ra, self.r
@@ -213,21 +322,42 @@ class LlamaDecoder(torch.nn.Module):
             pad[:, :, :self.V] = dlogits
             dlogits = pad
         dl2 = torch.as_strided(dlogits, (M, self.Vp), (self.Vp, 1), dlogits.storage_offset())
-        self._backward_body(ctx, ops.gemm(dl2, self.lm_headT))                     # dhf [M,H]
+        if self.full is None:
+            self._backward_body(ctx, ops.gemm(dl2, self.lm_headT))                 # dhf [M,H]
+            return
+        ctx.acc = self.full.begin_backward()
+        if self.tied:                                                              # head gradient lands in the embedding table
+            ops.wgrad_(dl2, ctx.hf, self.full.g("embed"), True)
+        else:
+            ops.wgrad_(dl2, ctx.hf, self.full.g("lm_head"), ctx.acc)
+        self._backward_body(ctx, ops.gemm(dl2, self.lm_head, layout=1))
 
     def _backward_body(self, ctx: _Ctx, dhf: torch.Tensor) -> None:
         """from the gradient of the final-norm output (bf16 [M,H]) down through the layers"""
         B, L = ctx.B, ctx.L
         M, H, F, Ra, r = B * L, self.H, self.F, self.Ra, self.r
         cos_t, sin_t = self._rope(L)
+        bank = self.full
+        acc = getattr(ctx, "acc", False)
+        G = (lambda l, n: bank.g(f"L{l}.{n}")) if bank is not None else None
+        if bank is not None:
+            ops.col_reduce_(dy_bf16=dhf, z=ctx.x_final, rstd=ctx.rstdf, out_prod=bank.g("norm_g"))
         dx32, dx16 = ops.rmsnorm_bwd(ctx.x_final, self.norm_g, ctx.rstdf, dhf)
         for l in range(self.nl - 1, -1, -1):
             W, a = self.layers[l], ctx.layers[l]
-            dact = ops.gemm(dx16, W["WdT"])                                        # [M,F]
+            if bank is not None:
+                ops.wgrad_(dx16, a.act, G(l, "Wd"), acc)
+            dact = self._dgrad(dx16, W, "Wd")                                      # [M,F]
             ops.swiglu_bwd_(a.gu, dact, F)                                         # gu <- [dgate | dup]
-            dh2 = ops.gemm(a.gu, W["WguT"])                                        # [M,H]
+            if bank is not None:
+                ops.wgrad_(a.gu, a.h2, G(l, "Wgu"), acc)
+            dh2 = self._dgrad(a.gu, W, "Wgu")                                      # [M,H]
+            if bank is not None:
+                ops.col_reduce_(dy_bf16=dh2, z=a.x_mid, rstd=a.rstd2, out_prod=G(l, "g2"))
             dmid32, dmid16 = ops.rmsnorm_bwd(a.x_mid, W["g2"], a.rstd2, dh2, dres_in=dx32)
-            datt = ops.gemm(dmid16, W["WoT"])                                      # [M,Nq]
+            if bank is not None:
+                ops.wgrad_(dmid16, a.att, G(l, "Wo"), acc)
+            datt = self._dgrad(dmid16, W, "Wo")                                    # [M,Nq]
             dqkv = _aug_buf(M, self.Nqkv, Ra, self.dev)
             attn_bwd = ops.attention_tc_bwd if self.hd == 128 else ops.attention_bwd
             attn_bwd(a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + self.Nkv], a.qkv[:, self.Nq + self.Nkv:],
@@ -235,6 +365,12 @@ class LlamaDecoder(torch.nn.Module):
                      dq=dqkv[:, :self.Nq], dk=dqkv[:, self.Nq:self.Nq + self.Nkv],
                      dv=dqkv[:, self.Nq + self.Nkv:self.Nqkv])
             ops.rope_(dqkv, 0, self.nh + self.nkv, self.hd, cos_t, sin_t, L, backward=True)
+            if bank is not None:
+                ops.wgrad_(dqkv, a.h1_aug[:, :H], G(l, "Wqkv"), acc)
+                dh1 = ops.gemm(dqkv, W["Wqkv_aug"], layout=1)
+                ops.col_reduce_(dy_bf16=dh1, z=a.x_in, rstd=a.rstd1, out_prod=G(l, "g1"))
+                dx32, dx16 = ops.rmsnorm_bwd(a.x_in, W["g1"], a.rstd1, dh1, dres_in=dmid32)
+                continue
             names = [f"model.layers.{l}.self_attn.{n}" for n in self.LORA_TARGETS]
             for j, n in enumerate(self.LORA_TARGETS):
                 c0, w = self._target_cols(n)
@@ -254,3 +390,6 @@ class LlamaDecoder(torch.nn.Module):
                 dh1 = ops.gemm(dqkv[:, :self.Nqkv], W["WqkvT_aug"][:, :self.Nqkv])
                 ops.lora_dx_(dh1, dqkv[:, self.Nqkv:], W["A_stack"], K=H, R=Ra, drop=xdrop)
             dx32, dx16 = ops.rmsnorm_bwd(a.x_in, W["g1"], a.rstd1, dh1, dres_in=dmid32)
+        if bank is not None:
+            ops.embed_scatter_add_(dx32, ctx.ids, bank.g("embed"))                # embed_tokens
+            bank.end_backward()

@@ -40,7 +40,7 @@ def load_tokenizer(name_or_path: str):
 
 
 def build_encoder(name_or_path: str, lora: bool, device: torch.device, state_dict: Optional[Dict] = None,
-                  cfg: Optional[Dict] = None, autoregressive: bool = False):
+                  cfg: Optional[Dict] = None, autoregressive: bool = False, full: bool = False):
     """BERT-family encoder (bge-*), or — `retriever_is_autoregressive` — a Llama-family decoder used as an encoder
     (last hidden state, eos pooling; LoRA targets q_proj / v_proj: reference rag_e2e_base_model.py:66-70,84-90)"""
     cfg = cfg or params.load_config(name_or_path)
@@ -49,11 +49,11 @@ def build_encoder(name_or_path: str, lora: bool, device: torch.device, state_dic
     if autoregressive:
         if kind != "llama":
             raise NotImplementedError("autoregressive retrievers are built for Llama-family models only")
-        return LlamaDecoder(cfg, sd, device=device, lora=lora, lora_seed=0)
+        return LlamaDecoder(cfg, sd, device=device, lora=lora, lora_seed=0, full=full)
     if kind != "bert":
         raise NotImplementedError("non-autoregressive retrievers must be BERT-family encoders (bge-*); pass "
                                   "retriever_is_autoregressive=True for a causal LM")
-    return BertEncoder(cfg, sd, device=device, lora=lora)
+    return BertEncoder(cfg, sd, device=device, lora=lora, full=full)
 
 
 def pooling_mask(attention_mask: torch.Tensor, autoregressive: bool) -> torch.Tensor:
@@ -66,15 +66,18 @@ def pooling_mask(attention_mask: torch.Tensor, autoregressive: bool) -> torch.Te
 
 
 def build_decoder(name_or_path: str, lora: bool, device: torch.device, state_dict: Optional[Dict] = None,
-                  cfg: Optional[Dict] = None) -> LlamaDecoder:
+                  cfg: Optional[Dict] = None, full: bool = False) -> LlamaDecoder:
     cfg = cfg or params.load_config(name_or_path)
     kind = params.model_kind(cfg)                # raises for unsupported families
     sd = state_dict if state_dict is not None else params.load_state_dict(name_or_path)
     if kind == "falcon":
+        if full:
+            logger.warning("Falcon generators are forward-only in dalm_b200 (no backward built yet): the generator stays "
+                           "frozen where the reference would fine-tune it — see DESIGN.md")
         return FalconDecoder(cfg, sd, device=device, lora=lora)       # raises for lora=True, like peft would
     if kind != "llama":
         raise NotImplementedError(f"generator of kind {kind!r} is not a causal decoder")
-    return LlamaDecoder(cfg, sd, device=device, lora=lora)
+    return LlamaDecoder(cfg, sd, device=device, lora=lora, full=full)
 
 
 class AutoModelForRagE2E(torch.nn.Module):
@@ -99,12 +102,13 @@ class AutoModelForRagE2E(torch.nn.Module):
         dev = _device()
         lora_r = get_peft in (Mode.RETRIEVER, Mode.BOTH)
         lora_g = get_peft in (Mode.GENERATOR, Mode.BOTH)
-        if not (lora_r and lora_g):
-            logger.warning("dalm_b200 trains LoRA adapters only (PEFT mode); sub-models without adapters are frozen. "
-                           "Full fine-tuning (reference default use_peft=None) is not built yet — see DESIGN.md")
+        # a sub-model without adapters is FULLY fine-tuned, as in the reference (no get_peft_model => every parameter keeps
+        # requires_grad=True and Adam is built over rag_model.parameters(), train_rage2e.py:336)
         self.retriever_model = (_retriever if _retriever is not None else
-                                build_encoder(retriever_name, lora_r, dev, autoregressive=retriever_is_autoregressive))
-        self.generator_model = _generator if _generator is not None else build_decoder(generator_name, lora_g, dev)
+                                build_encoder(retriever_name, lora_r, dev, autoregressive=retriever_is_autoregressive,
+                                              full=not lora_r))
+        self.generator_model = (_generator if _generator is not None else
+                                build_decoder(generator_name, lora_g, dev, full=not lora_g))
         self.retriever_tokenizer = load_tokenizer(retriever_name) if _load_tokenizers else None
         if retriever_is_autoregressive and self.retriever_tokenizer is not None:                   # reference :41-44
             self.retriever_tokenizer.add_eos_token = True
@@ -119,8 +123,8 @@ class AutoModelForRagE2E(torch.nn.Module):
         ids = input_ids.to(enc.dev, torch.int64).contiguous()
         mask = attention_mask.to(enc.dev, torch.int64).contiguous()
         pm = pooling_mask(mask, self.retriever_is_autoregressive).contiguous()
-        if enc.lora is not None and torch.is_grad_enabled():
-            return EncodeFn.apply(enc.lora_flat, enc, ids, mask, self.normalize, pm)
+        if enc.trainable and torch.is_grad_enabled():
+            return EncodeFn.apply(enc.anchor, enc, ids, mask, self.normalize, pm)
         hid, _ = enc.forward_hidden(ids, mask, save=False)
         emb, _ = ops.pool_norm_fwd(hid, pm, self.normalize)
         return emb
@@ -132,8 +136,8 @@ class AutoModelForRagE2E(torch.nn.Module):
         dec = self.generator_model
         ids = input_ids.to(dec.dev, torch.int64).contiguous()
         mask = attention_mask.to(dec.dev, torch.int64).contiguous()
-        if dec.lora is not None and torch.is_grad_enabled():
-            return GenerateFn.apply(dec.lora_flat, dec, ids, mask)
+        if dec.trainable and torch.is_grad_enabled():
+            return GenerateFn.apply(dec.anchor, dec, ids, mask)
         logits, _ = dec.forward_logits(ids, mask, save=False)
         return logits
 
@@ -153,7 +157,8 @@ class AutoModelForRagE2E(torch.nn.Module):
 
     # ---- optimizer-facing helpers -----------------------------------------------------------------------------
     def trainable_banks(self):
-        return [m.lora for m in (self.retriever_model, self.generator_model) if m.lora is not None]
+        """LoRA banks / dense parameter banks of both sub-models (each has a flat `.grad`)"""
+        return [b for m in (self.retriever_model, self.generator_model) for b in m.banks()]
 
     def repack(self) -> None:
         """refresh the bf16 LoRA blocks inside the fused weights after an optimizer step"""

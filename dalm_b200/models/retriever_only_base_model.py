@@ -23,10 +23,9 @@ class AutoModelForSentenceEmbedding(torch.nn.Module):
             # the reference defaults to use_bnb=True (:15); NF4 is outside BASELINE.json's configs. Accept the default
             # silently-but-logged instead of failing every default call; compute stays bf16.
             logger.warning("use_bnb=True requested: bitsandbytes NF4 is not built in dalm_b200; running bf16 weights")
-        if not get_peft:
-            logger.warning("get_peft=False: full fine-tuning is not built yet; the encoder is frozen (see DESIGN.md)")
+        # get_peft=False: every parameter is trained (reference :28-33 skips get_peft_model, Adam covers model.parameters())
         self.model = _model if _model is not None else build_encoder(model_name, bool(get_peft), _device(),
-                                                                     autoregressive=is_autoregressive)
+                                                                     autoregressive=is_autoregressive, full=not get_peft)
         self.tokenizer = load_tokenizer(model_name) if _load_tokenizer else None
         if is_autoregressive and self.tokenizer is not None:                                          # reference :36-38
             self.tokenizer.add_eos_token = True
@@ -39,8 +38,8 @@ class AutoModelForSentenceEmbedding(torch.nn.Module):
         ids = input_ids.to(enc.dev, torch.int64).contiguous()
         mask = attention_mask.to(enc.dev, torch.int64).contiguous()
         pm = pooling_mask(mask, self.is_autoregressive).contiguous()
-        if enc.lora is not None and torch.is_grad_enabled():
-            return EncodeFn.apply(enc.lora_flat, enc, ids, mask, self.normalize, pm)
+        if enc.trainable and torch.is_grad_enabled():
+            return EncodeFn.apply(enc.anchor, enc, ids, mask, self.normalize, pm)
         hid, _ = enc.forward_hidden(ids, mask, save=False)
         emb, _ = ops.pool_norm_fwd(hid, pm, self.normalize)
         return emb
@@ -57,11 +56,14 @@ class AutoModelForSentenceEmbedding(torch.nn.Module):
     def print_trainable_parameters(self) -> None:
         """what `model.print_trainable_parameters()` (PEFT) prints through the reference's __getattr__ fall-through
         (train_retriever_only.py:260)"""
-        trainable = self.model.lora.numel() if self.model.lora is not None else 0
-        total = trainable + sum(t.numel() for W in self.model.layers for t in W.values()
-                                if isinstance(t, torch.Tensor) and not t.dtype.is_floating_point is False)
-        print(f"trainable params: {trainable:,d} || all params (incl. resident transposes): {total:,d} || "
-              f"trainable%: {100 * trainable / max(total, 1):.4f}")
+        trainable = sum(b.numel() for b in self.model.banks())
+        if self.model.full is not None:
+            total = trainable
+        else:
+            total = trainable + sum(t.numel() for W in self.model.layers for k, t in W.items()
+                                    if isinstance(t, torch.Tensor) and not k.endswith("T") and not k.endswith("T_aug")
+                                    and k not in ("A_stack", "Bblk"))
+        print(f"trainable params: {trainable:,d} || all params: {total:,d} || trainable%: {100 * trainable / max(total, 1):.4f}")
 
     def attach_pre_trained_peft_layers(self, peft_retriever_path: str, device: str) -> None:          # :77-83
         from ..training.utils.train_utils import load_adapter_dir

@@ -137,12 +137,19 @@ def small_matmul(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_
 # ----------------------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, out_dtype=bf16, alpha: float = 1.0,
          bias: Optional[torch.Tensor] = None, act: int = 0, resid: Optional[torch.Tensor] = None, block_n: int = 0,
-         max_ctas: int = 0, K: Optional[int] = None, N: Optional[int] = None, drop: Optional[Drop] = None) -> torch.Tensor:
-    """out[M,N] = act(alpha * a[M,K] @ b[N,K]^T + bias) + resid.   a, b: bf16 2-D views with contiguous rows."""
+         max_ctas: int = 0, K: Optional[int] = None, N: Optional[int] = None, drop: Optional[Drop] = None,
+         layout: int = 0) -> torch.Tensor:
+    """out[M,N] = act(alpha * A @ B^T-or-B + bias) + resid.   a, b: bf16 2-D views with contiguous rows.
+    layout 0 (TN): a[M,K], b[N,K]   1 (NN, dgrad against W[out,in]): a[M,K], b[K,N]   2 (wgrad): a[K,M], b[K,N]"""
     _chk(a, bf16, "gemm a"); _chk(b, bf16, "gemm b")
-    M = a.shape[0]
-    K = a.shape[1] if K is None else K
-    N = b.shape[0] if N is None else N
+    if layout == 0:
+        M, Kd, Nd = a.shape[0], a.shape[1], b.shape[0]
+    elif layout == 1:
+        M, Kd, Nd = a.shape[0], a.shape[1], b.shape[1]
+    else:
+        M, Kd, Nd = a.shape[1], a.shape[0], b.shape[1]
+    K = Kd if K is None else K
+    N = Nd if N is None else N
     if out is None:
         out = torch.empty(M, N, dtype=out_dtype, device=a.device)
     if out.dtype not in (bf16, f32):
@@ -157,7 +164,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
     timer = GEMM_TIMER
     if timer is not None:
         timer.begin(2.0 * M * N * K)
-    _lib.call("dalm_b200_gemm_bf16_tn", _p(a), _ld(a), _p(b), _ld(b), _p(out), _ld(out), 1 if out.dtype == f32 else 0,
+    _lib.call("dalm_b200_gemm_bf16", int(layout), _p(a), _ld(a), _p(b), _ld(b), _p(out), _ld(out), 1 if out.dtype == f32 else 0,
               M, N, K, float(alpha), _p(bias), int(act), _p(resid), _ld(resid) if resid is not None else 0, rf32,
               int(block_n), int(max_ctas), *_d(drop), _stream())
     if timer is not None:
@@ -435,6 +442,44 @@ def cast_f32_bf16(src, dst=None):
         dst = torch.empty(M, N, dtype=bf16, device=src.device)
     _lib.call("dalm_b200_cast_f32_bf16", _p(src), _ld(src), _p(dst), _ld(dst), M, N, _stream())
     return dst
+
+
+def wgrad_(dy, x, gw, accumulate: bool, K: Optional[int] = None) -> None:
+    """gw[out,in] (fp32) = (or +=) dy[T,out]^T @ x[T,in]: the weight gradient of y = x W^T as one tcgen05 GEMM contracting
+    over the token rows (both operands read MN-major from their row-major buffers)"""
+    gemm(dy, x, out=gw, layout=2, resid=gw if accumulate else None, K=K)
+
+
+def col_reduce_(dy_f32=None, dy_bf16=None, z=None, mean=None, rstd=None, out_sum=None, out_prod=None) -> None:
+    """out_sum[h] += sum_m dy[m,h]; out_prod[h] += sum_m dy[m,h] * (z[m,h]-mean[m]) * rstd[m]   (dy = dy_f32 + dy_bf16)"""
+    ref = dy_f32 if dy_f32 is not None else dy_bf16
+    M, H = ref.shape
+    if dy_f32 is not None:
+        _chk(dy_f32, f32, "col_reduce dy_f32", inner_contig=False)
+    if dy_bf16 is not None:
+        _chk(dy_bf16, bf16, "col_reduce dy_bf16")
+    _lib.call("dalm_b200_col_reduce", _p(dy_f32), _p(dy_bf16), _ld(dy_bf16) if dy_bf16 is not None else 0, _p(z), _p(mean),
+              _p(rstd), _p(out_sum), _p(out_prod), M, H, _stream())
+
+
+def embed_scatter_add_(d, ids, dword, dpos=None, L: int = 1) -> None:
+    M, H = d.shape
+    _lib.call("dalm_b200_embed_scatter_add", _p(d), _p(ids), _p(dword), _p(dpos), M, H, int(L), dword.shape[0], _stream())
+
+
+def masked_add(a=None, b=None, drop: Optional[Drop] = None, out=None):
+    ref = a if a is not None else b
+    M, H = ref.shape
+    if out is None:
+        out = torch.empty(M, H, dtype=f32, device=ref.device)
+    _lib.call("dalm_b200_masked_add", _p(a), _p(b), _ld(b) if b is not None else 0, _p(out), M, H, *_d(drop), _stream())
+    return out
+
+
+def adam_step_shadow_(p, g, m, v, shadow, lr: float, beta1: float, beta2: float, eps: float, step: int, grad_scale: float = 1.0):
+    _lib.call("dalm_b200_adam_step_shadow", _p(p), _p(g), _p(m), _p(v), _p(shadow), p.numel(), float(lr), float(beta1),
+              float(beta2), float(eps), int(step), float(grad_scale), _stream())
+    return p
 
 
 def adam_step_(p, g, m, v, lr: float, beta1: float, beta2: float, eps: float, step: int, grad_scale: float = 1.0):

@@ -1,5 +1,6 @@
-"""Fused Adam over the flat LoRA parameter buffers — torch.optim.Adam semantics (reference train_rage2e.py:336:
-lr, betas (0.9, 0.999), eps 1e-8, no weight decay), one kernel launch per buffer."""
+"""Fused Adam over the flat parameter buffers (LoRA banks, or the fp32 master buffer of a fully fine-tuned model together
+with its bf16 shadow) — torch.optim.Adam semantics (reference train_rage2e.py:336: lr, betas (0.9, 0.999), eps 1e-8, no
+weight decay), one kernel launch per buffer."""
 from __future__ import annotations
 
 from typing import Iterable
@@ -27,7 +28,11 @@ class FusedAdam(torch.optim.Optimizer):
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["step"] += 1
-                if p.is_cuda and p.dtype == torch.float32 and p.is_contiguous():
+                bank = getattr(p, "_dalm_bank", None)
+                if bank is not None:                  # full fine-tuning: update master + refresh the bf16 shadow in one pass
+                    ops.adam_step_shadow_(p.data, p.grad, st["exp_avg"], st["exp_avg_sq"], bank.p16, group["lr"], b1, b2,
+                                          group["eps"], st["step"])
+                elif p.is_cuda and p.dtype == torch.float32 and p.is_contiguous():
                     ops.adam_step_(p.data, p.grad, st["exp_avg"], st["exp_avg_sq"], group["lr"], b1, b2, group["eps"], st["step"])
                 else:
                     raise RuntimeError("FusedAdam: parameters must be contiguous fp32 CUDA tensors (no CPU fallback)")
@@ -37,5 +42,8 @@ class FusedAdam(torch.optim.Optimizer):
         # gradients live in persistent flat buffers that the kernels accumulate into: zero in place, never drop them
         for group in self.param_groups:
             for p in group["params"]:
-                if p.grad is not None:
+                bank = getattr(p, "_dalm_bank", None)
+                if bank is not None:
+                    bank.zero_grad()                  # weight gradients are overwritten by the next wgrad: no 4 B/param memset
+                elif p.grad is not None:
                     p.grad.zero_()

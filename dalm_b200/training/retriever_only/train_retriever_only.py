@@ -104,7 +104,7 @@ def train_retriever(
     recipe = Recipe(
         title="Running training", tracker_project="peft_contrastive_learning", build_model=build, tokenize=tokenize,
         step=lambda m, b, s, gs: fused_retriever_step(m, b, s, backward=True, grad_scale=gs), step_fn=fused_retriever_step,
-        banks=lambda m: [m.model.lora] if m.model.lora is not None else [], repack=lambda m: m.model.repack_lora(),
+        banks=lambda m: m.model.banks(), repack=lambda m: m.model.repack_lora(),
         save_final=save_final)
     run_training(recipe, dataset_or_path=dataset_or_path, per_device_train_batch_size=per_device_train_batch_size,
                  learning_rate=learning_rate, logit_scale=logit_scale, num_train_epochs=num_train_epochs,

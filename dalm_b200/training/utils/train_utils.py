@@ -173,8 +173,8 @@ def fused_rag_step(rag_model, batch: Dict[str, torch.Tensor], logit_scale: float
     q_ids, q_mask = g("retriever_query_input_ids"), g("retriever_query_attention_mask")
     p_ids, p_mask = g("retriever_passage_input_ids"), g("retriever_passage_attention_mask")
     g_ids, g_mask, qlen = g("generator_input_input_ids"), g("generator_input_attention_mask"), g("query_passage_input_len")
-    train_enc = backward and enc.lora is not None
-    train_dec = backward and dec.lora is not None
+    train_enc = backward and enc.trainable
+    train_dec = backward and dec.trainable
     if enc.training or dec.training:                         # fresh dropout masks per step (also inside a graph replay)
         ops.bump_counter_(enc.drop_offset)
         ops.bump_counter_(dec.drop_offset)
@@ -224,7 +224,7 @@ def fused_retriever_step(model, batch: Dict[str, torch.Tensor], logit_scale: flo
     dev = enc.dev
     g = lambda k: batch[k].to(dev, i64, non_blocking=True).contiguous()
     q_ids, q_mask, p_ids, p_mask = g("query_input_ids"), g("query_attention_mask"), g("passage_input_ids"), g("passage_attention_mask")
-    train = backward and enc.lora is not None
+    train = backward and enc.trainable
     if enc.training:
         ops.bump_counter_(enc.drop_offset)
     hq, hp, enc_bwd = _encode_pair(enc, q_ids, q_mask, p_ids, p_mask, train)
@@ -249,6 +249,11 @@ class GraphedStep:
                  zero_grads=None):
         dev = next(model.parameters()).device
         self.step_fn, self.model, self.logit_scale, self.grad_scale = step_fn, model, float(logit_scale), float(grad_scale)
+        if self.grad_scale != 1.0:                              # gradient accumulation: the captured wgrad GEMMs must always +=
+            for p in model.parameters():
+                bank = getattr(p, "_dalm_bank", None)
+                if bank is not None:
+                    bank.force_accumulate = True
         self.static = {k: v.to(dev, i64).contiguous().clone() for k, v in example_batch.items() if torch.is_tensor(v)}
         self.shapes = {k: tuple(v.shape) for k, v in self.static.items()}
         cur = torch.cuda.current_stream()
@@ -285,8 +290,28 @@ ADAPTER_CONFIG = {
 }
 
 
+def save_full_dir(engine_model, out_dir: str) -> None:
+    """`save_pretrained` layout of a fully fine-tuned model (what the reference's hook writes for non-PEFT sub-models,
+    train_utils.py:16-31): config.json + model.safetensors under HF parameter names, fp32"""
+    from safetensors.torch import save_file
+
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, "config.json"), "w") as f:
+        json.dump({k: v for k, v in engine_model.cfg.items() if not k.startswith("_")}, f, indent=1)
+    save_file({k: v.contiguous() for k, v in engine_model.hf_state_dict().items()}, os.path.join(out_dir, "model.safetensors"))
+
+
+def load_full_dir(engine_model, in_dir: str) -> None:
+    from ...engine import params
+
+    engine_model.load_hf_state_dict(params.load_state_dict(in_dir))
+
+
 def save_adapter_dir(engine_model, out_dir: str, task_type: str, base_name: Optional[str] = None) -> None:
     os.makedirs(out_dir, exist_ok=True)
+    if getattr(engine_model, "full", None) is not None:
+        save_full_dir(engine_model, out_dir)
+        return
     if engine_model.lora is None:
         return
     cfg = dict(ADAPTER_CONFIG, task_type=task_type, target_modules=list(engine_model.LORA_TARGETS),
@@ -339,8 +364,12 @@ def load_model_hook(models: List[torch.nn.Module], input_dir: str) -> None:
                 d = os.path.join(input_dir, name)
                 if sub.lora is not None and os.path.exists(os.path.join(d, "adapter_config.json")):
                     load_adapter_dir(sub, d)
+                elif getattr(sub, "full", None) is not None and os.path.exists(os.path.join(d, "model.safetensors")):
+                    load_full_dir(sub, d)
         elif isinstance(model, AutoModelForSentenceEmbedding):
             if model.model.lora is not None and os.path.exists(os.path.join(input_dir, "adapter_config.json")):
                 load_adapter_dir(model.model, input_dir)
+            elif getattr(model.model, "full", None) is not None and os.path.exists(os.path.join(input_dir, "model.safetensors")):
+                load_full_dir(model.model, input_dir)
         else:
             raise NotImplementedError(f"Model type {type(model)} not supported")

@@ -69,6 +69,15 @@ int dalm_b200_gemm_bf16_tn(const void* A, long long lda, const void* B, long lon
                            int out_f32, int M, int N, int K, float alpha, const float* bias, int act, const void* resid,
                            long long ldr, int resid_f32, int block_n, int max_ctas, float drop_p, unsigned long long drop_seed,
     unsigned long long drop_stream_id, const void* drop_offset, void* stream);
+/* the same kernel reading either operand MN-major straight from its row-major buffer (nothing is transposed in HBM):
+ *   layout 0: A[M,K], B[N,K]  (== dalm_b200_gemm_bf16_tn)
+ *   layout 1: A[M,K], B[K,N]  dgrad dx = dy W against W[out,in] itself — full fine-tuning (reference default use_peft=None,
+ *                             dalm/training/rag_e2e/train_rage2e.py:229-260,336) where weights change every step
+ *   layout 2: A[K,M], B[K,N]  wgrad dW[out,in] = dy^T x, contraction over token rows (autograd of nn.Linear.weight) */
+int dalm_b200_gemm_bf16(int layout, const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo,
+                        int out_f32, int M, int N, int K, float alpha, const float* bias, int act, const void* resid,
+                        long long ldr, int resid_f32, int block_n, int max_ctas, float drop_p, unsigned long long drop_seed,
+                        unsigned long long drop_stream_id, const void* drop_offset, void* stream);
 void dalm_b200_gemm_clear_cache(void);
 
 /* ---- attention (same call sites; HF eager/SDPA attention) ---- */
@@ -140,6 +149,24 @@ int dalm_b200_pack_table(const void* table, int n_entries, void* stream);
 int dalm_b200_cast_f32_bf16(const float* in, long long ldi, void* out, long long ldo, int rows, int cols, void* stream);
 int dalm_b200_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                         float eps, int step, float grad_scale, void* stream);
+
+
+/* ---- full fine-tuning: parameter gradients that are not GEMMs, and the optimizer over the fp32 master buffer ----
+ * (autograd of nn.Linear.bias / nn.LayerNorm / LlamaRMSNorm / nn.Embedding under the reference's `accelerator.backward(loss)`,
+ *  dalm/training/rag_e2e/train_rage2e.py:466, and torch.optim.Adam.step, :336,467)
+ * col_reduce: out_sum[h] += sum_m dy[m,h]; out_prod[h] += sum_m dy[m,h] * (z[m,h] - mean[m]) * rstd[m]; dy = dy_f32 + dy_bf16
+ * (either may be NULL), mean NULL for RMSNorm. */
+int dalm_b200_col_reduce(const float* dy_f32, const void* dy_bf16, long long lddy, const float* z, const float* mean,
+                         const float* rstd, float* out_sum, float* out_prod, int M, int H, void* stream);
+/* dword[ids[m],:] += d[m,:]; dpos[m % L,:] += d[m,:] (dpos may be NULL) */
+int dalm_b200_embed_scatter_add(const float* d, const int64_t* ids, float* dword, float* dpos, int M, int H, int L, int V,
+                                void* stream);
+/* out = (a_f32 + b_bf16) * dropout_scale  (gradient through the embedding dropout; out may alias a) */
+int dalm_b200_masked_add(const float* a, const void* b, long long ldb, float* out, int M, int H, float p,
+                         unsigned long long seed, unsigned long long stream_id, const void* offset, void* stream);
+/* Adam on a flat fp32 buffer (n % 4 == 0) + refresh of the bf16 shadow the GEMMs read (shadow may be NULL) */
+int dalm_b200_adam_step_shadow(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr,
+                               float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

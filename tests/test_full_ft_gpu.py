@@ -1,0 +1,321 @@
+"""-m gpu: FULL fine-tuning (the reference's default `use_peft=None` / `--no-use-peft`: Adam over every parameter,
+train_rage2e.py:336, train_retriever_only.py:262) — the MN-major GEMM layouts behind dgrad / wgrad, the parameter-gradient
+kernels, the shadowed Adam, and the whole step's gradients for EVERY parameter against the CPU fp32 oracle's autograd."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# kernels
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,bn,max_ctas", [(300, 200, 136, 0, 0), (128, 256, 64, 256, 0), (520, 1096, 328, 128, 3),
+                                               (257, 72, 1000, 64, 2), (1024, 512, 512, 256, 0)])
+def test_gemm_nn_layout_is_dgrad_against_untransposed_weight(cuda_dev, M, N, K, bn, max_ctas):
+    from dalm_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(cuda_dev, bf16)
+    w = (torch.randn(K, N, generator=g) * 0.1).to(cuda_dev, bf16)          # W[out=K, in=N]: dx = dy W
+    out = ops.gemm(a, w, layout=1, block_n=bn, max_ctas=max_ctas)
+    ref = a.float() @ w.float()
+    assert _rel(out.float(), ref) < 5e-3
+    out32 = ops.gemm(a, w, layout=1, out_dtype=f32, block_n=bn, max_ctas=max_ctas)
+    assert _rel(out32, ref) < 1e-4
+
+
+@pytest.mark.parametrize("T,M,N,bn,max_ctas", [(1000, 192, 320, 0, 0), (64, 128, 256, 256, 0), (3204, 264, 1096, 128, 4),
+                                               (777, 72, 136, 64, 2), (130, 1024, 512, 256, 0)])
+def test_gemm_wgrad_layout_contracts_over_token_rows(cuda_dev, T, M, N, bn, max_ctas):
+    from dalm_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(T + M + N)
+    dy = torch.randn(T, M, generator=g).to(cuda_dev, bf16)
+    x = torch.randn(T, N, generator=g).to(cuda_dev, bf16)
+    ref = dy.float().t() @ x.float()
+    gw = torch.full((M, N), 7.0, dtype=f32, device=cuda_dev)
+    ops.gemm(dy, x, out=gw, layout=2, block_n=bn, max_ctas=max_ctas)       # fresh gradient: written, not accumulated
+    assert _rel(gw, ref) < 1e-4
+    ops.wgrad_(dy, x, gw, accumulate=True)                                # second contribution: +=
+    assert _rel(gw, 2 * ref) < 1e-4
+    # strided views (column blocks of a fused activation buffer), as the engine passes them
+    buf = torch.randn(T, M + 64, generator=g).to(cuda_dev, bf16)
+    gw2 = torch.empty(M, N, dtype=f32, device=cuda_dev)
+    ops.wgrad_(buf[:, :M], x, gw2, accumulate=False)
+    assert _rel(gw2, buf[:, :M].float().t() @ x.float()) < 1e-4
+
+
+def test_col_reduce_bias_and_norm_gradients(cuda_dev):
+    from dalm_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for M, H in ((1000, 384), (77, 1024), (5000, 132)):
+        dya = torch.randn(M, H, generator=g).to(cuda_dev)
+        dyb = torch.randn(M, H + 8, generator=g).to(cuda_dev, bf16)[:, :H]
+        z = torch.randn(M, H, generator=g).to(cuda_dev) * 2 + 0.3
+        mean, var = z.mean(1), z.var(1, unbiased=False)
+        rstd = (var + 1e-5).rsqrt()
+        dy = dya + dyb.float()
+        zh = (z - mean[:, None]) * rstd[:, None]
+        s, p = torch.zeros(H, device=cuda_dev), torch.ones(H, device=cuda_dev)
+        ops.col_reduce_(dy_f32=dya, dy_bf16=dyb, z=z, mean=mean, rstd=rstd, out_sum=s, out_prod=p)
+        assert _rel(s, dy.sum(0)) < 1e-5 and _rel(p - 1, (dy * zh).sum(0)) < 1e-4
+        # bias gradient: bf16 only; RMSNorm gain: no mean
+        s2 = torch.zeros(H, device=cuda_dev)
+        ops.col_reduce_(dy_bf16=dyb, out_sum=s2)
+        assert _rel(s2, dyb.float().sum(0)) < 1e-5
+        p2 = torch.zeros(H, device=cuda_dev)
+        ops.col_reduce_(dy_bf16=dyb, z=z, rstd=rstd, out_prod=p2)
+        assert _rel(p2, (dyb.float() * z * rstd[:, None]).sum(0)) < 1e-4
+
+
+def test_embed_scatter_add_and_masked_add(cuda_dev):
+    from dalm_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(6)
+    B, L, H, V = 7, 12, 64, 50
+    d = torch.randn(B * L, H, generator=g).to(cuda_dev)
+    ids = torch.randint(0, V, (B, L), generator=g).to(cuda_dev)
+    dw, dp = torch.zeros(V, H, device=cuda_dev), torch.zeros(32, H, device=cuda_dev)
+    ops.embed_scatter_add_(d, ids, dw, dp, L)
+    rw = torch.zeros(V, H, device=cuda_dev).index_add_(0, ids.view(-1), d)
+    rp = torch.zeros(32, H, device=cuda_dev)
+    rp[:L] = d.view(B, L, H).sum(0)
+    assert _rel(dw, rw) < 1e-6 and _rel(dp, rp) < 1e-6
+    a = torch.randn(B * L, H, generator=g).to(cuda_dev)
+    b = torch.randn(B * L, H, generator=g).to(cuda_dev, bf16)
+    drop = ops.Drop(0.1, 1234, 99, None)
+    mask = ops.dropout_scale(B * L * H, drop, cuda_dev).view(B * L, H)
+    out = ops.masked_add(a, b, drop=drop)
+    assert torch.equal(out, (a + b.float()) * mask)
+    assert 0.05 < (mask == 0).float().mean().item() < 0.15
+    assert torch.equal(ops.masked_add(a, b, drop=None), a + b.float())
+
+
+def test_adam_shadow_matches_torch_adam(cuda_dev):
+    from dalm_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(7)
+    n = 4096 + 64
+    p0 = torch.randn(n, generator=g)
+    p = p0.clone().to(cuda_dev); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    shadow = torch.zeros(n, dtype=bf16, device=cuda_dev)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-2)
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=g)
+        ref.grad = grad.clone()
+        opt.step()
+        ops.adam_step_shadow_(p, grad.to(cuda_dev), m, v, shadow, 1e-2, 0.9, 0.999, 1e-8, step)
+    assert (p.cpu() - ref.detach()).abs().max().item() < 1e-5
+    assert torch.equal(shadow, p.to(bf16))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# whole-step parity: every parameter's gradient
+# ---------------------------------------------------------------------------------------------------------------
+def _full_models(dev, vb=600, vl=504, lora_r=False, lora_g=False):
+    from dalm_b200 import synthetic
+    from dalm_b200.engine import params
+    from dalm_b200.engine.bert import BertEncoder
+    from dalm_b200.engine.llama import LlamaDecoder
+    from dalm_b200.models.rag_e2e_base_model import AutoModelForRagE2E, Mode
+    from oracle import models as om
+    bcfg, lcfg = synthetic.bert_config("bge-tiny", vb), synthetic.llama_config("llama-tiny", vl)
+    r16 = lambda sd: {k: v.to(bf16).float() for k, v in sd.items()}            # fp32 master == bf16 shadow at the start
+    bsd, lsd = r16(params.random_state_dict("bert", bcfg, seed=11)), r16(params.random_state_dict("llama", lcfg, seed=12))
+    enc = BertEncoder(bcfg, bsd, device=dev, lora=lora_r, full=not lora_r)
+    dec = LlamaDecoder(lcfg, lsd, device=dev, lora=lora_g, full=not lora_g)
+    mode = {(False, False): None, (True, False): Mode.RETRIEVER, (False, True): Mode.GENERATOR}[(lora_r, lora_g)]
+    model = AutoModelForRagE2E("", "", get_peft=mode, _retriever=enc, _generator=dec, _load_tokenizers=False)
+    return model, enc, dec, om.build_bert(bcfg, bsd), om.build_llama(lcfg, lsd)
+
+
+def _compare_full_grads(engine, ref_grads, prefix, skip=(), tol=6e-2, abs_floor=1e-7):
+    """every HF parameter of the fully fine-tuned engine model vs the oracle's autograd gradient"""
+    worst, checked = ("", 0.0), 0
+    got = {}
+    for key, parts in engine._rows.items():
+        gw, r = engine.full.g(key), 0
+        for name, rows in parts:
+            got[name] = gw[r:r + rows]
+            r += rows
+    for name, gt in got.items():
+        if name in skip:
+            continue
+        rg = ref_grads[prefix + name]
+        if rg.norm().item() < abs_floor:                    # a mathematically zero gradient (key bias: softmax is shift
+            assert gt.float().norm().item() < 1e-4, name    # invariant): ours is bf16 rounding noise, compare absolutely
+            continue
+        e = _rel(gt, rg)
+        checked += 1
+        if e > worst[1]:
+            worst = (name, e)
+    assert worst[1] < tol, worst
+    return checked
+
+
+def _batch(B, Lq, Lp, Lg, vb, vl, seed):
+    g = torch.Generator().manual_seed(seed)
+    mk = lambda L: torch.ones(B, L, dtype=torch.int64)
+    b = {"retriever_query_input_ids": torch.randint(5, vb, (B, Lq), generator=g), "retriever_query_attention_mask": mk(Lq),
+         "retriever_passage_input_ids": torch.randint(5, vb, (B, Lp), generator=g), "retriever_passage_attention_mask": mk(Lp),
+         "generator_input_input_ids": torch.randint(3, vl, (B, Lg), generator=g), "generator_input_attention_mask": mk(Lg),
+         "query_passage_input_len": torch.randint(1, Lg + 3, (B,), generator=g)}
+    b["retriever_query_attention_mask"][0, Lq - 3:] = 0
+    b["retriever_passage_attention_mask"][1, Lp // 2:] = 0
+    b["generator_input_attention_mask"][0, :5] = 0
+    return b
+
+
+def test_full_finetune_rag_step_gradients_match_oracle(cuda_dev):
+    from dalm_b200.optim import FusedAdam
+    from dalm_b200.training.utils.train_utils import fused_rag_step
+    from oracle import models as om
+    model, enc, dec, bert, llama = _full_models(cuda_dev)
+    batch = _batch(5, 12, 24, 40, 600, 504, seed=21)
+    ref = om.rag_step(bert, llama, batch)
+    opt = FusedAdam(model.parameters(), lr=1e-3)
+    opt.zero_grad()
+    out = fused_rag_step(model, batch, 100.0)
+    got = out["losses"].cpu()
+    assert abs(got[2].item() - ref["loss"].item()) / abs(ref["loss"].item()) < 1e-3
+    n_r = _compare_full_grads(enc, ref["grads"], "retriever.")
+    n_g = _compare_full_grads(dec, ref["grads"], "generator.")
+    assert n_r > 30 and n_g > 15
+    # a second backward without zero_grad accumulates (un-fused API path / gradient accumulation)
+    g1r, g1g = enc.full.g32.clone(), dec.full.g32.clone()
+    fused_rag_step(model, batch, 100.0)
+    assert _rel(enc.full.g32, 2 * g1r) < 1e-3 and _rel(dec.full.g32, 2 * g1g) < 1e-3
+    # zero_grad + step again gives the single-step gradient back (fresh wgrads overwrite, atomics start from zero)
+    opt.zero_grad()
+    fused_rag_step(model, batch, 100.0)
+    assert _rel(enc.full.g32, g1r) < 1e-3 and _rel(dec.full.g32, g1g) < 1e-3
+    # Adam: master weights move like torch.optim.Adam on the oracle's gradients; the bf16 shadow follows the master
+    w_before = dec.full.w32("L0.Wqkv").clone()
+    opt.step()
+    delta = dec.full.w32("L0.Wqkv") - w_before
+    gq = ref["grads"]["generator.model.layers.0.self_attn.q_proj.weight"].to(cuda_dev)
+    rows = gq.shape[0]
+    big = gq.abs() > gq.abs().max() * 0.05
+    assert (torch.sign(delta[:rows][big]) == -torch.sign(gq[big])).float().mean().item() > 0.99     # first Adam step = -lr*sign(g)
+    assert abs(delta.abs().max().item() - 1e-3) < 1e-5
+    assert torch.equal(dec.full.p16, dec.full.p32.to(bf16)) and torch.equal(enc.full.p16, enc.full.p32.to(bf16))
+    l0 = out["loss"].item()
+    for _ in range(5):
+        opt.zero_grad()
+        l = fused_rag_step(model, batch, 100.0)["loss"].item()
+        opt.step()
+    assert l < l0
+
+
+def test_full_finetune_through_the_reference_style_autograd_loop(cuda_dev):
+    """the reference's loop body over the drop-in API with use_peft=None: query and passage batches are two encoder calls,
+    so the second backward must accumulate into the first one's weight gradients"""
+    from dalm_b200.optim import FusedAdam
+    from dalm_b200.training.utils.train_utils import compute_marginalized_loss_from_logits, get_cosine_sim, get_nt_xent_loss
+    from oracle import models as om
+    model, enc, dec, bert, llama = _full_models(cuda_dev, vl=500)          # vocab not a multiple of 8: padded lm_head rows
+    batch = _batch(4, 10, 20, 32, 600, 500, seed=31)
+    ref = om.rag_step(bert, llama, batch)
+    d = {k: v.to(cuda_dev) for k, v in batch.items()}
+    opt = FusedAdam(model.parameters(), lr=1e-3)
+    opt.zero_grad()
+    q = model("retrieval", d["retriever_query_input_ids"], d["retriever_query_attention_mask"])
+    p = model("retrieval", d["retriever_passage_input_ids"], d["retriever_passage_attention_mask"])
+    S = get_cosine_sim(q, p, 100)
+    loss_c = (get_nt_xent_loss(S) + get_nt_xent_loss(S.t())) / 2.0
+    lg = model("generation", d["generator_input_input_ids"], d["generator_input_attention_mask"])
+    loss = loss_c + compute_marginalized_loss_from_logits(lg, d["generator_input_input_ids"], d["generator_input_attention_mask"],
+                                                          S, d["query_passage_input_len"])
+    loss.backward()
+    assert abs(loss.item() - ref["loss"].item()) / abs(ref["loss"].item()) < 1e-3
+    _compare_full_grads(enc, ref["grads"], "retriever.")
+    _compare_full_grads(dec, ref["grads"], "generator.")
+
+
+def test_mixed_peft_retriever_lora_generator_full(cuda_dev):
+    """`--use-peft retriever`: adapters on the retriever, the generator fully fine-tuned (reference rag_e2e_base_model.py:61-80:
+    only the named sub-model goes through get_peft_model)"""
+    from dalm_b200.training.utils.train_utils import fused_rag_step
+    from oracle import models as om
+    model, enc, dec, bert, llama = _full_models(cuda_dev, lora_r=True)
+    g = torch.Generator().manual_seed(13)
+    for n, _, _ in enc.lora.specs:
+        enc.lora.B[n].copy_((torch.randn(enc.lora.B[n].shape, generator=g) * 0.02).to(cuda_dev))
+    enc.repack_lora()
+    om.attach_lora(bert, {n: {"A": enc.lora.A[n].cpu(), "B": enc.lora.B[n].cpu()} for n, _, _ in enc.lora.specs})
+    batch = _batch(4, 10, 20, 32, 600, 504, seed=41)
+    ref = om.rag_step(bert, llama, batch)
+    enc.lora.zero_grad(); dec.full.zero_grad()
+    out = fused_rag_step(model, batch, 100.0)
+    assert abs(out["loss"].item() - ref["loss"].item()) / abs(ref["loss"].item()) < 1e-3
+    _compare_full_grads(dec, ref["grads"], "generator.")
+    worst = max(max(_rel(enc.lora.gA[n], ref["grads"]["retriever." + n + ".lora_A"]),
+                    _rel(enc.lora.gB[n], ref["grads"]["retriever." + n + ".lora_B"])) for n, _, _ in enc.lora.specs)
+    assert worst < 6e-2, worst
+    assert len(model.trainable_banks()) == 2
+
+
+def test_full_finetune_retriever_only_with_dropout_and_graph(cuda_dev):
+    """train() mode (hidden / attention dropout on, incl. the embedding dropout whose gradient is masked) under a CUDA graph:
+    loss decreases and the graph's gradients equal the eager ones for the same dropout stream"""
+    from dalm_b200 import synthetic
+    from dalm_b200.engine import params
+    from dalm_b200.engine.bert import BertEncoder
+    from dalm_b200.models.retriever_only_base_model import AutoModelForSentenceEmbedding
+    from dalm_b200.optim import FusedAdam
+    from dalm_b200.training.utils.train_utils import GraphedStep, fused_retriever_step
+    bcfg = synthetic.bert_config("bge-tiny", 600)
+    enc = BertEncoder(bcfg, params.random_state_dict("bert", bcfg, seed=3), device=cuda_dev, full=True)
+    se = AutoModelForSentenceEmbedding("", use_bnb=False, get_peft=False, _model=enc, _load_tokenizer=False)
+    b = _batch(6, 12, 24, 8, 600, 504, seed=51)
+    rb = {"query_input_ids": b["retriever_query_input_ids"], "query_attention_mask": b["retriever_query_attention_mask"],
+          "passage_input_ids": b["retriever_passage_input_ids"], "passage_attention_mask": b["retriever_passage_attention_mask"]}
+    se.train()
+    opt = FusedAdam(se.parameters(), lr=2e-4)
+    graphed = GraphedStep(fused_retriever_step, se, rb, 100.0, zero_grads=opt.zero_grad)
+    losses = []
+    for i in range(12):
+        opt.zero_grad()
+        losses.append(graphed(rb)["loss"].item())
+        opt.step()
+    assert losses[-1] < losses[0], losses
+    assert all(torch.isfinite(torch.tensor(losses)))
+    assert torch.isfinite(enc.full.g32).all()
+
+
+def test_full_finetune_trainer_end_to_end_and_resume(cuda_dev, tmp_path):
+    """`dalm train-retriever-only --no-use-peft` and `dalm train-rag-e2e` without --use-peft on a toy CSV: save_pretrained
+    artefacts (config.json + model.safetensors under HF names) that reload into HF classes with moved weights"""
+    from safetensors.torch import load_file
+    from dalm_b200 import synthetic
+    from dalm_b200.training.rag_e2e.train_rage2e import train_e2e
+    from dalm_b200.training.retriever_only.train_retriever_only import train_retriever
+    from oracle import models as om
+    csv = synthetic.write_csv(str(tmp_path / "toy.csv"), 12, seed=5)
+    rdir = synthetic.write_model_dir(str(tmp_path / "bge-tiny"), "bert", "bge-tiny", vocab_size=1200)
+    gdir = synthetic.write_model_dir(str(tmp_path / "llama-tiny"), "llama", "llama-tiny", vocab_size=904)
+    out = str(tmp_path / "out_ret")
+    train_retriever(rdir, csv, per_device_train_batch_size=2, query_max_len=16, passage_max_len=32, num_train_epochs=1,
+                    output_dir=out, use_peft=False, use_bnb=False, with_tracking=False, checkpointing_steps="3")
+    sd = load_file(os.path.join(out, "retriever", "model.safetensors"))
+    sd0 = load_file(os.path.join(rdir, "model.safetensors"))
+    moved = [k for k in sd0 if k in sd and not k.startswith("pooler") and (sd[k].float() - sd0[k].float()).abs().max() > 0]
+    assert len(moved) > 30                                                    # weights, biases, LayerNorms, embeddings all moved
+    import json
+    om.build_bert(json.load(open(os.path.join(out, "retriever", "config.json"))), sd)          # loads into HF BertModel
+    train_retriever(rdir, csv, per_device_train_batch_size=2, query_max_len=16, passage_max_len=32, num_train_epochs=1,
+                    output_dir=out, use_peft=False, use_bnb=False, with_tracking=False,
+                    resume_from_checkpoint=os.path.join(out, "step_3"))
+    out2 = str(tmp_path / "out_e2e")
+    train_e2e(csv, rdir, gdir, per_device_train_batch_size=2, query_max_len=16, passage_max_len=32, generator_max_len=64,
+              num_train_epochs=1, output_dir=out2, use_peft=None, num_warmup_steps=1, with_tracking=False)
+    gsd = load_file(os.path.join(out2, "generator", "model.safetensors"))
+    g0 = load_file(os.path.join(gdir, "model.safetensors"))
+    assert sum((gsd[k].float() - g0[k].float()).abs().max() > 0 for k in g0) == len(g0)
+    om.build_llama(json.load(open(os.path.join(out2, "generator", "config.json"))), gsd)

@@ -2,7 +2,9 @@
   cfg-2  train_retriever_only bge-large-en + PEFT, per-device bs=150, Lq 50 / Lp 128
   cfg-5  train_rage2e bge-large-en + Falcon-7B, bs=18, generator seq_len 2048, use_peft=retriever (frozen generator)
 Same method as bench.py: synthetic 'full' rows, seeded random-init weights, train() mode (dropout on), one CUDA graph per step,
-CUDA-event timing, warm-up, Adam + repack included.  python tools/bench_other_configs.py [cfg2|cfg5] [steps]"""
+CUDA-event timing, warm-up, Adam + repack included.  python tools/bench_other_configs.py [cfg2|cfg5|cfg2full|cfg3full] [steps]
+  cfg2full  cfg-2 without --use-peft: every BERT-large parameter trained (wgrad GEMMs, fp32 master + Adam over 335 M parameters)
+  cfg3full  cfg-3 with use_peft=None (the reference's CLI default): bge-large AND Llama-2-7B fully fine-tuned"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -18,7 +20,8 @@ dev = torch.device("cuda:0")
 bf16 = torch.bfloat16
 g = torch.Generator().manual_seed(0)
 bcfg = dict(synthetic.bert_config("bge-large-en"), _device_rng=True)
-enc = BertEncoder(bcfg, params.random_state_dict("bert", bcfg, seed=0, dtype=bf16, device=dev), device=dev, lora=True)
+full = which.endswith("full")
+enc = BertEncoder(bcfg, params.random_state_dict("bert", bcfg, seed=0, dtype=bf16, device=dev), device=dev, lora=not full, full=full)
 
 
 def rnd(B, L, V): return torch.randint(5, V, (B, L), generator=g)
@@ -27,14 +30,30 @@ def rnd(B, L, V): return torch.randint(5, V, (B, L), generator=g)
 def ones(B, L): return torch.ones(B, L, dtype=torch.int64)
 
 
-if which == "cfg2":
+if which in ("cfg2", "cfg2full"):
     from dalm_b200.models.retriever_only_base_model import AutoModelForSentenceEmbedding
     B = 150
-    model = AutoModelForSentenceEmbedding("", use_bnb=False, get_peft=True, _model=enc, _load_tokenizer=False)
+    model = AutoModelForSentenceEmbedding("", use_bnb=False, get_peft=not full, _model=enc, _load_tokenizer=False)
     batches = [{"query_input_ids": rnd(B, 50, 30522), "query_attention_mask": ones(B, 50),
                 "passage_input_ids": rnd(B, 128, 30522), "passage_attention_mask": ones(B, 128)} for _ in range(4)]
     step_fn, label = fused_retriever_step, "cfg-2 train_retriever_only bge-large-en + PEFT, bs=150, Lq50/Lp128"
     tflop = 33.1
+    if full:
+        label, tflop = "cfg-2 WITHOUT PEFT (full fine-tuning of bge-large-en), bs=150, Lq50/Lp128", 49.2
+elif which == "cfg3full":
+    from dalm_b200.engine.llama import LlamaDecoder
+    from dalm_b200.models.rag_e2e_base_model import AutoModelForRagE2E
+    B, LG = 18, 256
+    lcfg = dict(synthetic.llama_config("Llama-2-7b-hf"), _device_rng=True)
+    dec = LlamaDecoder(lcfg, params.random_state_dict("llama", lcfg, seed=1, dtype=bf16, device=dev), device=dev, full=True)
+    torch.cuda.empty_cache()
+    model = AutoModelForRagE2E("", "", get_peft=None, _retriever=enc, _generator=dec, _load_tokenizers=False)
+    batches = [{"retriever_query_input_ids": rnd(B, 50, 30522), "retriever_query_attention_mask": ones(B, 50),
+                "retriever_passage_input_ids": rnd(B, 128, 30522), "retriever_passage_attention_mask": ones(B, 128),
+                "generator_input_input_ids": rnd(B, LG, 32000), "generator_input_attention_mask": ones(B, LG),
+                "query_passage_input_len": torch.full((B,), 200)} for _ in range(4)]
+    step_fn, label = fused_rag_step, "cfg-3 with use_peft=None (full fine-tuning of bge-large-en + Llama-2-7B), bs=18, Lq50/Lp128/Lg256"
+    tflop = 190.4
 else:
     from dalm_b200.engine.falcon import FalconDecoder
     from dalm_b200.models.rag_e2e_base_model import AutoModelForRagE2E, Mode
@@ -59,7 +78,8 @@ graphed = GraphedStep(step_fn, model, dbs[0], 100.0, zero_grads=opt.zero_grad) i
 def one(i):
     out = graphed(dbs[i % len(dbs)])
     opt.step()
-    (model.model if which == "cfg2" else model.retriever_model).repack_lora()
+    if not full:
+        (model.model if which == "cfg2" else model.retriever_model).repack_lora()
     opt.zero_grad()
     return out["loss"]
 
@@ -73,4 +93,5 @@ for i in range(steps): loss = one(i)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 print(json.dumps({"config": label, "samples_per_s": B / (ms * 1e-3), "ms_per_step": ms, "steps": steps, "algorithmic_tflop_per_step": tflop,
-                  "tflops": tflop / (ms * 1e-3), "loss_last": float(loss.item()), "dropout": "on", "launch": "CUDA graph", "n_gpus": 1}), flush=True)
+                  "tflops": tflop / (ms * 1e-3), "loss_last": float(loss.item()), "dropout": "on", "launch": "CUDA graph", "n_gpus": 1,
+                  "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}), flush=True)
