@@ -282,6 +282,9 @@ def main():
         eager_ms, _, launches = timed(resident, timer, eager=True)
         _tu._TWO_STREAMS = _two
     gsum = timer.summary()
+    if os.environ.get("DALM_B200_GEMM_SHAPES") and rank == 0:   # per-shape breakdown of the GEMM time (stderr; profiles/)
+        for tag, n, ms, tf in timer.by_shape():
+            print(f"[gemm-shape] {tag} launches={n} total_ms={ms:.3f} tflops={tf:.1f}", file=sys.stderr, flush=True)
 
     # ---- end-to-end run through the public step with host (pinned) batches: H2D inside, loss read back each step ----
     def e2e_run():

@@ -11,6 +11,7 @@ _ALIASES = [
     "training.utils", "training.utils.train_utils", "training.utils.rag_e2e_dataloader_utils",
     "training.utils.retriever_only_dataloader_utils", "training.rag_e2e", "training.rag_e2e.train_rage2e",
     "training.retriever_only", "training.retriever_only.train_retriever_only",
+    "eval", "eval.utils", "eval.eval_results", "eval.eval_retriever_only", "eval.eval_rag",
 ]
 
 

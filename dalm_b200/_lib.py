@@ -65,11 +65,14 @@ SIGNATURES = {
     "dalm_b200_embed_scatter_add": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "dalm_b200_masked_add": [_P, _P, _L, _P, _I, _I, *_DROP, _P],
     "dalm_b200_adam_step_shadow": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P],
+    "dalm_b200_topk_ip_workspace": [_I, _I],
+    "dalm_b200_topk_ip": [_P, _P, _L, _I, _I, _I, _I, _P, _P, _P, _P],
 }
 _RESTYPES = {
     "dalm_b200_last_error": c_char_p,
     "dalm_b200_version": c_char_p,
     "dalm_b200_launch_count": c_longlong,
+    "dalm_b200_topk_ip_workspace": c_longlong,
     "dalm_b200_reset_launch_count": None,
     "dalm_b200_gemm_clear_cache": None,
     "dalm_b200_attention_tc_set_debug": None,

@@ -210,9 +210,13 @@ class Accelerator:
         flat LoRA gradient buffer, issued only on steps where the optimizer will step."""
         if self.num_processes == 1 or not self.sync_gradients:
             return
+        nccl = dist.get_backend() == "nccl"
         for g in flat_grads:
-            dist.all_reduce(g, op=dist.ReduceOp.SUM)
-            g.div_(self.num_processes)
+            if nccl:
+                dist.all_reduce(g, op=dist.ReduceOp.AVG)         # one pass: no separate divide over a 27 GB full-FT buffer
+            else:
+                dist.all_reduce(g, op=dist.ReduceOp.SUM)
+                g.div_(self.num_processes)
 
     def reduce(self, tensor: torch.Tensor, reduction: str = "sum") -> torch.Tensor:
         if self.num_processes == 1:

@@ -1,6 +1,6 @@
 """`dalm` command line — the hot-path commands of the reference's typer app (dalm/cli.py:17,35-38,41-167,170-277):
-`version`, `train-rag-e2e`, `train-retriever-only`, same argument order / option names / defaults. The remaining
-reference commands (qa-gen, eval-rag, eval-retriever) belong to subsystems outside this build's scope and say so."""
+`version`, `train-rag-e2e`, `train-retriever-only`, `eval-retriever`, `eval-rag` (:313-412), same argument order / option
+names / defaults. `qa-gen` belongs to a subsystem outside this build's scope and says so."""
 from __future__ import annotations
 
 from enum import Enum
@@ -139,7 +139,71 @@ def _out_of_scope(name: str):
     return cmd
 
 
-for _n in ("qa-gen", "eval-rag", "eval-retriever"):
+class TorchDtype(str, Enum):                 # reference cli.py:24-27
+    float16 = "float16"
+    bfloat16 = "bfloat16"
+
+
+@cli.command()
+def eval_retriever(
+    dataset_path: Annotated[str, typer.Argument(help="Path to the dataset to eval with. Can be an hf dataset dir, csv file, "
+                                                     "or path to hub file.", show_default=False)],
+    retriever_name_or_path: Annotated[str, typer.Option(help="Path to pretrained retriever or identifier from huggingface.co/models.")],
+    retriever_peft_model_path: Annotated[Optional[str], typer.Option(help="Path to the fine-tuned retriever peft layers")] = None,
+    passage_column_name: Annotated[str, typer.Option(help="Name of the column containing the passage")] = "Abstract",
+    query_column_name: Annotated[str, typer.Option(help="Name of the column containing the query")] = "Question",
+    embed_dim: Annotated[int, typer.Option(help="Dimension of the model embedding")] = 1024,
+    max_length: Annotated[int, typer.Option(help="The max passage sequence length during tokenization. Longer sequences are truncated")] = 128,
+    test_batch_size: Annotated[int, typer.Option(help="Batch size (per device) for the test dataloader.")] = 8,
+    device: Annotated[str, typer.Option(help="Device. cpu or cuda.")] = "cuda",
+    torch_dtype: Annotated[TorchDtype, typer.Option(help="torch.dtype to use for tensors. float16 or bfloat16.")] = TorchDtype.float16,
+    top_k: Annotated[int, typer.Option(help="Top K retrieval")] = 10,
+    is_autoregressive: Annotated[bool, typer.Option(help="Whether the model is autoregressive.")] = False,
+) -> None:
+    """Evaluate your retriever only"""
+    from .eval.eval_retriever_only import evaluate_retriever
+
+    evaluate_retriever(dataset_or_path=dataset_path, retriever_name_or_path=retriever_name_or_path,
+                       retriever_peft_model_path=retriever_peft_model_path, passage_column_name=passage_column_name,
+                       query_column_name=query_column_name, embed_dim=embed_dim, max_length=max_length,
+                       test_batch_size=test_batch_size, device=device, torch_dtype=torch_dtype.value, top_k=top_k,
+                       is_autoregressive=is_autoregressive)
+
+
+@cli.command()
+def eval_rag(
+    dataset_path: Annotated[str, typer.Argument(help="Path to the dataset to eval with. Can be an hf dataset dir, csv file, "
+                                                     "or path to hub file.", show_default=False)],
+    retriever_name_or_path: Annotated[str, typer.Option(help="Path to pretrained retriever or identifier from huggingface.co/models.")],
+    generator_name_or_path: Annotated[str, typer.Option(help="Path to pretrained (causal) generator or identifier from huggingface.co/models.")],
+    retriever_peft_model_path: Annotated[Optional[str], typer.Option(help="Path to the fine-tuned retriever peft layers")] = None,
+    generator_peft_model_path: Annotated[Optional[str], typer.Option(help="Path to the fine-tuned generator peft layers")] = None,
+    passage_column_name: Annotated[str, typer.Option(help="Name of the column containing the passage")] = "Abstract",
+    query_column_name: Annotated[str, typer.Option(help="Name of the column containing the query")] = "Question",
+    answer_column_name: Annotated[str, typer.Option(help="Name of the column containing the Answer")] = "Answer",
+    embed_dim: Annotated[int, typer.Option(help="Dimension of the model embedding")] = 1024,
+    max_length: Annotated[int, typer.Option(help="The max passage sequence length during tokenization. Longer sequences are truncated")] = 128,
+    test_batch_size: Annotated[int, typer.Option(help="Batch size (per device) for the test dataloader.")] = 8,
+    query_batch_size: Annotated[int, typer.Option(help="Batch size (per device) for generator input")] = 16,
+    device: Annotated[str, typer.Option(help="Device. cpu or cuda.")] = "cuda",
+    torch_dtype: Annotated[TorchDtype, typer.Option(help="torch.dtype to use for tensors. float16 or bfloat16.")] = TorchDtype.float16,
+    top_k: Annotated[int, typer.Option(help="Top K retrieval")] = 10,
+    evaluate_generator: Annotated[bool, typer.Option(help="Enable generator evaluation. If false, equivalent to eval-retriever")] = True,
+    retriever_is_autoregressive: Annotated[bool, typer.Option(help="Whether the retriever is autoregressive.")] = False,
+) -> None:
+    """Evaluate your end-to-end rag generator and retriever"""
+    from .eval.eval_rag import evaluate_rag
+
+    evaluate_rag(dataset_or_path=dataset_path, retriever_name_or_path=retriever_name_or_path,
+                 generator_name_or_path=generator_name_or_path, retriever_peft_model_path=retriever_peft_model_path,
+                 generator_peft_model_path=generator_peft_model_path, passage_column_name=passage_column_name,
+                 query_column_name=query_column_name, answer_column_name=answer_column_name, embed_dim=embed_dim,
+                 max_length=max_length, test_batch_size=test_batch_size, query_batch_size=query_batch_size, device=device,
+                 torch_dtype=torch_dtype.value, top_k=top_k, evaluate_generator=evaluate_generator,
+                 retriever_is_autoregressive=retriever_is_autoregressive)
+
+
+for _n in ("qa-gen",):
     cli.command(name=_n)(_out_of_scope(_n))
 
 if __name__ == "__main__":

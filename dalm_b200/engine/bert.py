@@ -176,6 +176,32 @@ class BertEncoder(torch.nn.Module):
                 r += rows
         self.full.sync_shadow()
 
+    def enable_lora(self, lora_seed: int = 0) -> None:
+        """turn a frozen (inference-built) encoder into an adapter-carrying one — what `PeftModel.from_pretrained(base, path)`
+        does to the reference's wrapper in attach_pre_trained_peft_layers (rag_e2e_base_model.py:113-134). The fused
+        projection weights are re-laid-out with the K-augmentation columns; adapter weights are then loaded into the bank."""
+        if self.lora is not None:
+            return
+        if self.full is not None:
+            raise RuntimeError("enable_lora: this encoder is being fully fine-tuned; adapters attach to frozen bases only")
+        H, r = self.H, self.r
+        self.Ra = 3 * r
+        for W in self.layers:
+            old, oldT = W["Wqkv_aug"], W["WqkvT_aug"]
+            W["Wqkv_aug"] = _aug_buf(3 * H, H, self.Ra, self.dev, zero=True)
+            W["Wqkv_aug"][:, :H] = old[:, :H]
+            W["WqkvT_aug"] = _aug_buf(H, 3 * H, self.Ra, self.dev, zero=True)
+            W["WqkvT_aug"][:, :3 * H] = oldT[:, :3 * H]
+            W["A_stack"] = torch.zeros(64, H, dtype=bf16, device=self.dev)
+            W["Bblk"] = torch.zeros(64, 3 * H, dtype=bf16, device=self.dev)
+        specs = [(f"encoder.layer.{l}.attention.self.{n}", H, H) for l in range(self.nl) for n in self.LORA_TARGETS]
+        self.lora = LoraBank(specs, r=r, alpha=16, dropout=0.05, device=self.dev, seed=lora_seed)
+        self.lora_flat = torch.nn.Parameter(self.lora.flat, requires_grad=True)
+        self.lora_flat.grad = self.lora.grad
+        self.p_lora = 0.05
+        self._pack_tab = None
+        self.repack_lora()
+
     def _dgrad(self, dy: torch.Tensor, W: Dict[str, torch.Tensor], name: str) -> torch.Tensor:
         """dx = dy W: against the resident transposed copy (frozen base) or W[out,in] itself read MN-major (full mode)"""
         if self.full is not None:

@@ -175,6 +175,31 @@ class LlamaDecoder(torch.nn.Module):
                 r += rows
         self.full.sync_shadow()
 
+    def enable_lora(self, lora_seed: int = 1) -> None:
+        """frozen (inference-built) decoder -> adapter-carrying one, see BertEncoder.enable_lora"""
+        if self.lora is not None:
+            return
+        if self.full is not None:
+            raise RuntimeError("enable_lora: this decoder is being fully fine-tuned; adapters attach to frozen bases only")
+        H, r = self.H, self.r
+        self.Ra = 2 * r
+        for W in self.layers:
+            old, oldT = W["Wqkv_aug"], W["WqkvT_aug"]
+            W["Wqkv_aug"] = _aug_buf(self.Nqkv, H, self.Ra, self.dev, zero=True)
+            W["Wqkv_aug"][:, :H] = old[:, :H]
+            W["WqkvT_aug"] = _aug_buf(H, self.Nqkv, self.Ra, self.dev, zero=True)
+            W["WqkvT_aug"][:, :self.Nqkv] = oldT[:, :self.Nqkv]
+            W["A_stack"] = torch.zeros(64, H, dtype=bf16, device=self.dev)
+            W["Bblk"] = torch.zeros(64, self.Nqkv, dtype=bf16, device=self.dev)
+        outs = {"q_proj": self.Nq, "v_proj": self.Nkv}
+        specs = [(f"model.layers.{l}.self_attn.{n}", H, outs[n]) for l in range(self.nl) for n in self.LORA_TARGETS]
+        self.lora = LoraBank(specs, r=r, alpha=16, dropout=0.05, device=self.dev, seed=lora_seed)
+        self.lora_flat = torch.nn.Parameter(self.lora.flat, requires_grad=True)
+        self.lora_flat.grad = self.lora.grad
+        self.p_lora = 0.05
+        self._pack_tab = None
+        self.repack_lora()
+
     def _dgrad(self, dy: torch.Tensor, W: Dict[str, torch.Tensor], name: str) -> torch.Tensor:
         if self.full is not None:
             return ops.gemm(dy, W[name], layout=1)

@@ -27,6 +27,29 @@ class Mode(str, Enum):                       # reference :16-19
     BOTH = "both"
 
 
+_INFERENCE_ONLY = False
+
+
+class inference_only:
+    """context manager for evaluation code: wrappers built inside it keep sub-models WITHOUT adapters frozen (bf16 weights
+    only) instead of allocating the fp32 master / gradient banks of full fine-tuning. The reference has no such switch — it
+    builds the same modules and simply never calls backward in dalm/eval/*."""
+
+    def __enter__(self):
+        global _INFERENCE_ONLY
+        self.prev, _INFERENCE_ONLY = _INFERENCE_ONLY, True
+        return self
+
+    def __exit__(self, *exc):
+        global _INFERENCE_ONLY
+        _INFERENCE_ONLY = self.prev
+        return False
+
+
+def _want_full(lora: bool) -> bool:
+    return (not lora) and not _INFERENCE_ONLY
+
+
 def _device() -> torch.device:
     if not torch.cuda.is_available():
         raise RuntimeError("dalm_b200 needs a CUDA (sm_100a) device: there is no CPU path for the training step")
@@ -106,9 +129,9 @@ class AutoModelForRagE2E(torch.nn.Module):
         # requires_grad=True and Adam is built over rag_model.parameters(), train_rage2e.py:336)
         self.retriever_model = (_retriever if _retriever is not None else
                                 build_encoder(retriever_name, lora_r, dev, autoregressive=retriever_is_autoregressive,
-                                              full=not lora_r))
+                                              full=_want_full(lora_r)))
         self.generator_model = (_generator if _generator is not None else
-                                build_decoder(generator_name, lora_g, dev, full=not lora_g))
+                                build_decoder(generator_name, lora_g, dev, full=_want_full(lora_g)))
         self.retriever_tokenizer = load_tokenizer(retriever_name) if _load_tokenizers else None
         if retriever_is_autoregressive and self.retriever_tokenizer is not None:                   # reference :41-44
             self.retriever_tokenizer.add_eos_token = True

@@ -9,7 +9,7 @@ import torch
 from .. import ops
 from ..engine.bert import BertEncoder
 from ..engine.bridge import EncodeFn, PoolFn
-from .rag_e2e_base_model import _device, build_encoder, load_tokenizer, pooling_mask
+from .rag_e2e_base_model import _device, _want_full, build_encoder, load_tokenizer, pooling_mask
 
 logger = logging.getLogger(__name__)
 
@@ -25,7 +25,7 @@ class AutoModelForSentenceEmbedding(torch.nn.Module):
             logger.warning("use_bnb=True requested: bitsandbytes NF4 is not built in dalm_b200; running bf16 weights")
         # get_peft=False: every parameter is trained (reference :28-33 skips get_peft_model, Adam covers model.parameters())
         self.model = _model if _model is not None else build_encoder(model_name, bool(get_peft), _device(),
-                                                                     autoregressive=is_autoregressive, full=not get_peft)
+                                                                     autoregressive=is_autoregressive, full=_want_full(bool(get_peft)))
         self.tokenizer = load_tokenizer(model_name) if _load_tokenizer else None
         if is_autoregressive and self.tokenizer is not None:                                          # reference :36-38
             self.tokenizer.add_eos_token = True

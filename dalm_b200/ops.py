@@ -163,7 +163,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
         rf32 = 1 if resid.dtype == f32 else 0
     timer = GEMM_TIMER
     if timer is not None:
-        timer.begin(2.0 * M * N * K)
+        timer.begin(2.0 * M * N * K, (M, N, K, int(layout), str(out.dtype)[6:], "resid" if resid is not None else "-",
+                                      "bias" if bias is not None else "-"))
     _lib.call("dalm_b200_gemm_bf16", int(layout), _p(a), _ld(a), _p(b), _ld(b), _p(out), _ld(out), 1 if out.dtype == f32 else 0,
               M, N, K, float(alpha), _p(bias), int(act), _p(resid), _ld(resid) if resid is not None else 0, rf32,
               int(block_n), int(max_ctas), *_d(drop), _stream())
@@ -178,12 +179,14 @@ class GemmTimer:
     def __init__(self, capacity: int = 4096):
         self.ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(capacity)]
         self.flops = []
+        self.tags = []
         self.n = 0
 
-    def begin(self, flops: float) -> None:
+    def begin(self, flops: float, tag=None) -> None:
         if self.n < len(self.ev):
             self.ev[self.n][0].record()
             self.flops.append(flops)
+            self.tags.append(tag)
 
     def end(self) -> None:
         if self.n < len(self.ev):
@@ -193,6 +196,17 @@ class GemmTimer:
     def reset(self) -> None:
         self.n = 0
         self.flops = []
+        self.tags = []
+
+    def by_shape(self):
+        """[(tag, launches, total_ms, TFLOP/s)] sorted by time: which GEMM shapes the step spends its tensor time in"""
+        torch.cuda.synchronize()
+        agg = {}
+        for i in range(self.n):
+            ms = self.ev[i][0].elapsed_time(self.ev[i][1])
+            a = agg.setdefault(self.tags[i], [0, 0.0, 0.0])
+            a[0] += 1; a[1] += ms; a[2] += self.flops[i]
+        return sorted(((t, a[0], a[1], a[2] / (a[1] * 1e-3) / 1e12) for t, a in agg.items()), key=lambda r: -r[2])
 
     def summary(self):
         torch.cuda.synchronize()
@@ -486,3 +500,20 @@ def adam_step_(p, g, m, v, lr: float, beta1: float, beta2: float, eps: float, st
     _lib.call("dalm_b200_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
               int(step), float(grad_scale), _stream())
     return p
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# evaluation: exact inner-product top-k
+# ----------------------------------------------------------------------------------------------------------------
+def topk_ip(q: torch.Tensor, p: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """q fp32 [nq,D], p fp32 [N,D] (row-strided) -> (scores fp32 [nq,k] descending, idx int32 [nq,k]; -1 past N)"""
+    _chk(q, f32, "topk q"); _chk(p, f32, "topk p")
+    if not q.is_contiguous():
+        q = q.contiguous()
+    nq, D = q.shape
+    N = p.shape[0]
+    scores = torch.empty(nq, k, dtype=f32, device=q.device)
+    idx = torch.empty(nq, k, dtype=torch.int32, device=q.device)
+    ws = torch.empty(int(_lib.load().dalm_b200_topk_ip_workspace(nq, k)), dtype=torch.uint8, device=q.device)
+    _lib.call("dalm_b200_topk_ip", _p(q), _p(p), _ld(p), nq, N, D, int(k), _p(scores), _p(idx), _p(ws), _stream())
+    return scores, idx

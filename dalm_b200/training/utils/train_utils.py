@@ -323,7 +323,9 @@ def save_adapter_dir(engine_model, out_dir: str, task_type: str, base_name: Opti
 
 def load_adapter_dir(engine_model, in_dir: str) -> None:
     if engine_model.lora is None:
-        raise RuntimeError("model was built without adapters (get_peft) — nothing to load into")
+        if not hasattr(engine_model, "enable_lora"):
+            raise RuntimeError(f"{type(engine_model).__name__} cannot carry adapters")
+        engine_model.enable_lora()          # PeftModel.from_pretrained(base, path) on a base built without get_peft
     path = os.path.join(in_dir, "adapter_model.bin")
     if os.path.exists(path):
         sd = torch.load(path, map_location="cpu", weights_only=True)

@@ -168,6 +168,14 @@ int dalm_b200_masked_add(const float* a, const void* b, long long ldb, float* ou
 int dalm_b200_adam_step_shadow(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr,
                                float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
 
+/* ---- evaluation: exact maximum-inner-product top-k over the resident passage embeddings ----
+ * replaces hnswlib.Index(space="ip").knn_query of dalm/eval/utils.py:18-66 (approximate: M=100, ef 100) with an exact
+ * sweep. out_scores [nq,K] = inner products in descending order (hnswlib's distance is 1 - score), out_idx [nq,K] int32 row
+ * ids (-1 past the end when N < K); ties -> lower row id first. workspace: dalm_b200_topk_ip_workspace(nq, K) bytes. */
+long long dalm_b200_topk_ip_workspace(int nq, int K);
+int dalm_b200_topk_ip(const float* Q, const float* P, long long ldp, int nq, int N, int D, int K, float* out_scores,
+                      int* out_idx, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,8 @@ so that the CPU test-suite (and the GPU box) can pin oracle/ and dalm_b200's hos
                   and autograd gradients for seeded cases incl. left/right padding and qlen in {1, L-1, L, >L}
   pooling.npz     reference AutoModelForRagE2E.mean_pooling + F.normalize, dalm.utils.eos_mask
   preprocess.json reference batch builders (e2e + retriever-only) on synthetic rows with the fixture tokenizers
+  eval_helpers.json reference dalm/eval/utils.py helpers (precision/recall, result aggregation, unique-passage filter,
+                  tokenisation, neighbour formatting over a fixed (labels, distances) answer) — hnswlib itself is stubbed
 """
 from __future__ import annotations
 
@@ -105,6 +107,43 @@ def gen_preprocess(ref):
         json.dump({"rows": rows, "e2e": {k: v for k, v in e2e.items()}, "retriever": {k: v for k, v in ret.items()}}, f)
 
 
+def gen_eval_helpers(ref):
+    import datasets
+    from transformers import AutoTokenizer
+
+    eu = ref.eval_utils
+    out = {}
+    pr_cases = [(["a", "b", "c"], ["a"]), (["x", "y"], ["z"]), (["p", "p", "q"], ["q"]), (["only"], ["only"])]
+    out["precision_recall"] = [{"retrieved": r, "correct": c, "out": list(eu.calculate_precision_recall(r, c))} for r, c in pr_cases]
+    res = eu.calc_eval_results(7, [0.1, 0.2, 0.0, 0.1, 0.1, 0.5, 1.0], [1, 1, 0, 1, 1, 1, 1], 6)
+    out["calc_eval_results"] = {"args": [7, [0.1, 0.2, 0.0, 0.1, 0.1, 0.5, 1.0], [1, 1, 0, 1, 1, 1, 1], 6],
+                                "out": res.model_dump() if hasattr(res, "model_dump") else res.dict()}
+    rows = {"Abstract": ["p one", "p two", "p one", "p three", "p two", "p four"], "Question": [f"q{i}" for i in range(6)]}
+    ds = datasets.Dataset.from_dict(rows)
+    out["filter_unique"] = {"rows": rows, "kept_questions": list(eu.filter_unique_passages(ds, "Abstract")["Question"])}
+    tok = AutoTokenizer.from_pretrained(os.path.join(GOLD, "tok_bert"))
+    ex = {"Question": ["kato miren sol", ""], "Abstract": ["sol va kato miren " * 12, "x"]}
+    pre = eu.preprocess_function(ex, tok, query_column_name="Question", passage_column_name="Abstract", max_length=16)
+    out["preprocess_function"] = {"examples": ex, "max_length": 16, "out": {k: v for k, v in pre.items()}}
+
+    class FixedIndex:                                           # stands in for hnswlib.Index: a fixed answer
+        def set_ef(self, ef): self.ef = ef
+        def knn_query(self, q, k):
+            labels = np.array([[2, 0, 1], [1, 2, 0]])[:, :k]
+            dist = np.array([[0.05, 0.4, 1.2], [0.3, 0.31, 0.95]], dtype=np.float32)[:, :k]
+            return labels, dist
+    ids = {0: "zero", 1: "one", 2: "two"}
+    nn = {}
+    for thr in (0.7, 0.0):
+        nn[str(thr)] = [[[p, float(s)] for p, s in row] for row in eu.get_nearest_neighbours(3, FixedIndex(), np.zeros((2, 4)), ids, threshold=thr)]
+    out["nearest_neighbours"] = nn
+    batch = [{"a": [1, 2], "s": "x", "n": None}, {"a": [3, 4], "s": "y", "n": None}]
+    mc = eu.mixed_collate_fn(batch)
+    out["mixed_collate"] = {"batch": batch, "out": {k: (v.tolist() if torch.is_tensor(v) else v) for k, v in mc.items()}}
+    with open(os.path.join(GOLD, "eval_helpers.json"), "w") as f:
+        json.dump(out, f)
+
+
 def main():
     from oracle import ref_import
 
@@ -113,6 +152,7 @@ def main():
     gen_losses(ref)
     gen_pooling(ref)
     gen_preprocess(ref)
+    gen_eval_helpers(ref)
     print("golden fixtures written to", GOLD)
 
 

@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY. Used by oracle/make_golden.py to generate tests/golden/* and by tests that are skipped when
 /root/reference is absent (it never exists on the GPU box). `peft` and `accelerate` are not installed here; they are
-replaced by MagicMock stubs AFTER torch/transformers are imported (SURVEY §8c recipe), which is enough for the loss
+(and `hnswlib`, for dalm/eval/utils.py) replaced by MagicMock stubs AFTER torch/transformers are imported (SURVEY §8c recipe), which is enough for the loss
 functions, wrappers' forward/mean_pooling and the batch builders to run as the reference wrote them.
 """
 from __future__ import annotations
@@ -28,9 +28,11 @@ def load() -> SimpleNamespace:
     saved_dalm = {k: v for k, v in sys.modules.items() if k == "dalm" or k.startswith("dalm.")}
     for k in saved_dalm:
         del sys.modules[k]
-    for name in ("peft", "accelerate", "accelerate.logging", "accelerate.utils"):
+    stubbed = []
+    for name in ("peft", "accelerate", "accelerate.logging", "accelerate.utils", "hnswlib"):
         if name not in sys.modules:
             sys.modules[name] = MagicMock()
+            stubbed.append(name)
     # the repo's own `dalm` alias package installs a meta-path finder mapping dalm.* -> dalm_b200.*: park it
     parked = [f for f in sys.meta_path if getattr(f, "__name__", "") == "_LazyAlias"]
     for f in parked:
@@ -43,6 +45,7 @@ def load() -> SimpleNamespace:
         from dalm.training.utils.rag_e2e_dataloader_utils import preprocess_dataset as preprocess_e2e
         from dalm.training.utils.retriever_only_dataloader_utils import preprocess_dataset as preprocess_retriever
         from dalm.utils import eos_mask
+        from dalm.eval import utils as eval_utils
     finally:
         sys.path.remove(REFERENCE_ROOT)
         for f in parked:
@@ -51,8 +54,10 @@ def load() -> SimpleNamespace:
         for k in ref_modules:
             del sys.modules[k]
         sys.modules.update(saved_dalm)
+        for name in stubbed:            # the loaded reference modules keep their references; nobody else should see the mocks
+            sys.modules.pop(name, None)  # (transformers probes importlib.util.find_spec("peft") and chokes on a MagicMock)
     return SimpleNamespace(
         train_utils=train_utils, AutoModelForRagE2E=AutoModelForRagE2E,
         AutoModelForSentenceEmbedding=AutoModelForSentenceEmbedding, preprocess_e2e=preprocess_e2e,
-        preprocess_retriever=preprocess_retriever, eos_mask=eos_mask,
+        preprocess_retriever=preprocess_retriever, eos_mask=eos_mask, eval_utils=eval_utils,
     )

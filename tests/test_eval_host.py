@@ -1,0 +1,86 @@
+"""CPU: the evaluation helpers (reference dalm/eval/utils.py) against the committed outputs of the reference's
+own functions (tests/golden/eval_helpers.json, oracle/make_golden.py) and the exact-search oracle's conventions."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(os.path.join(GOLD, "eval_helpers.json")) as f:
+        return json.load(f)
+
+
+def test_precision_recall_and_aggregation(gold):
+    from dalm_b200.eval.utils import calc_eval_results, calculate_precision_recall
+    for c in gold["precision_recall"]:
+        assert list(calculate_precision_recall(c["retrieved"], c["correct"])) == c["out"]
+    with pytest.raises(ZeroDivisionError):                      # empty retrieved set: same failure as the reference
+        calculate_precision_recall([], ["a"])
+    r = calc_eval_results(*gold["calc_eval_results"]["args"])
+    assert r.model_dump() == gold["calc_eval_results"]["out"]
+
+
+def test_unique_passage_filter_keeps_first_occurrence(gold):
+    import datasets
+    from dalm_b200.eval.utils import filter_unique_passages
+    ds = datasets.Dataset.from_dict(gold["filter_unique"]["rows"])
+    assert list(filter_unique_passages(ds, "Abstract")["Question"]) == gold["filter_unique"]["kept_questions"]
+
+
+def test_tokenisation_is_bit_exact(gold):
+    from transformers import AutoTokenizer
+    from dalm_b200.eval.utils import preprocess_function
+    tok = AutoTokenizer.from_pretrained(os.path.join(GOLD, "tok_bert"))
+    g = gold["preprocess_function"]
+    out = preprocess_function(g["examples"], tok, query_column_name="Question", passage_column_name="Abstract",
+                              max_length=g["max_length"])
+    assert {k: v for k, v in out.items()} == g["out"]
+
+
+def test_neighbour_formatting_and_threshold(gold):
+    from dalm_b200.eval.utils import get_nearest_neighbours
+
+    class FixedIndex:
+        def set_ef(self, ef): self.ef = ef
+        def knn_query(self, q, k):
+            return (np.array([[2, 0, 1], [1, 2, 0]])[:, :k],
+                    np.array([[0.05, 0.4, 1.2], [0.3, 0.31, 0.95]], dtype=np.float32)[:, :k])
+    ids = {0: "zero", 1: "one", 2: "two"}
+    for thr, want in gold["nearest_neighbours"].items():
+        idx = FixedIndex()
+        got = get_nearest_neighbours(3, idx, np.zeros((2, 4)), ids, threshold=float(thr))
+        assert [[[p, float(s)] for p, s in row] for row in got] == want
+        assert idx.ef == 100
+
+
+def test_mixed_collate(gold):
+    from dalm_b200.eval.utils import mixed_collate_fn
+    out = mixed_collate_fn(gold["mixed_collate"]["batch"])
+    assert {k: (v.tolist() if torch.is_tensor(v) else v) for k, v in out.items()} == gold["mixed_collate"]["out"]
+
+
+def test_exact_search_oracle_conventions():
+    """oracle/topk.py: hnswlib 'ip' space — distance = 1 - <q,p>, nearest first, ties towards the lower id"""
+    from oracle import topk
+    data = np.array([[1.0, 0.0], [0.0, 1.0], [0.6, 0.8], [1.0, 0.0]])
+    labels, dist = topk.knn_query(data, np.array([[1.0, 0.0]]), 3)
+    assert labels.tolist() == [[0, 3, 2]]
+    assert np.allclose(dist, [[0.0, 0.0, 0.4]])
+
+
+def test_live_reference_helpers_if_present(gold):
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    from dalm_b200.eval import utils as ours
+    eu = ref_import.load().eval_utils
+    for r, c in ((["a", "b"], ["b"]), (["k"] * 4, ["k"]), (["m", "n", "o"], ["z"])):
+        assert ours.calculate_precision_recall(r, c) == eu.calculate_precision_recall(r, c)
+    a = (5, [0.1] * 5, [1, 0, 1, 1, 0], 3)
+    assert ours.calc_eval_results(*a).model_dump() == eu.calc_eval_results(*a).model_dump()
