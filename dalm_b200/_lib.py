@@ -67,6 +67,7 @@ SIGNATURES = {
     "dalm_b200_adam_step_shadow": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P],
     "dalm_b200_topk_ip_workspace": [_I, _I],
     "dalm_b200_topk_ip": [_P, _P, _L, _I, _I, _I, _I, _P, _P, _P, _P],
+    "dalm_b200_nf4_roundtrip": [_P, _L, _P, _P, _P],
 }
 _RESTYPES = {
     "dalm_b200_last_error": c_char_p,

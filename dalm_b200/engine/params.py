@@ -123,3 +123,27 @@ def model_kind(cfg: Dict) -> str:
         return "falcon"
     raise NotImplementedError(
         f"model_type {mt!r} is not built in dalm_b200 (supported: bert encoders; llama and falcon decoders); see DESIGN.md")
+
+
+def is_bnb_linear_weight(name: str) -> bool:
+    """the tensors `load_in_4bit` replaces: every nn.Linear weight except the LM head (transformers keeps `lm_head` and tied
+    output embeddings out of the conversion); embeddings and norms are not Linear"""
+    return (name.endswith(".weight") and "embed" not in name and "LayerNorm" not in name and "layernorm" not in name
+            and "norm.weight" not in name and "ln_f" not in name and not name.startswith("lm_head"))
+
+
+def bnb_nf4_state_dict(sd: Dict[str, torch.Tensor], device) -> Dict[str, torch.Tensor]:
+    """`use_bnb` (reference rag_e2e_base_model.py:136-142): fp32 tensors on `device` holding exactly the values the
+    reference's 4-bit model computes with — nn.Linear weights through the NF4 quantise/dequantise round trip (csrc/nf4.cu),
+    everything else through the fp16 cast transformers applies when a bitsandbytes config is given without torch_dtype."""
+    from .. import ops
+
+    out = {}
+    for k, v in sd.items():
+        t = v.to(device=device, dtype=torch.float32).contiguous().clone()
+        if t.dim() == 2 and is_bnb_linear_weight(k):
+            ops.nf4_roundtrip_(t)
+        else:
+            t = t.to(torch.float16).to(torch.float32)            # dtype casts only
+        out[k] = t
+    return out

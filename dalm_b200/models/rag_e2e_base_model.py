@@ -63,12 +63,13 @@ def load_tokenizer(name_or_path: str):
 
 
 def build_encoder(name_or_path: str, lora: bool, device: torch.device, state_dict: Optional[Dict] = None,
-                  cfg: Optional[Dict] = None, autoregressive: bool = False, full: bool = False):
+                  cfg: Optional[Dict] = None, autoregressive: bool = False, full: bool = False, bnb: bool = False):
     """BERT-family encoder (bge-*), or — `retriever_is_autoregressive` — a Llama-family decoder used as an encoder
     (last hidden state, eos pooling; LoRA targets q_proj / v_proj: reference rag_e2e_base_model.py:66-70,84-90)"""
     cfg = cfg or params.load_config(name_or_path)
     kind = params.model_kind(cfg)
     sd = state_dict if state_dict is not None else params.load_state_dict(name_or_path)
+    sd = _maybe_bnb(sd, bnb, full, device)
     if autoregressive:
         if kind != "llama":
             raise NotImplementedError("autoregressive retrievers are built for Llama-family models only")
@@ -77,6 +78,16 @@ def build_encoder(name_or_path: str, lora: bool, device: torch.device, state_dic
         raise NotImplementedError("non-autoregressive retrievers must be BERT-family encoders (bge-*); pass "
                                   "retriever_is_autoregressive=True for a causal LM")
     return BertEncoder(cfg, sd, device=device, lora=lora, full=full)
+
+
+def _maybe_bnb(sd: Dict, bnb: bool, full: bool, device) -> Dict:
+    """use_bnb: replace the checkpoint values by what the reference's NF4-loaded model computes with (engine/params.py)"""
+    if not bnb:
+        return sd
+    if full:
+        raise NotImplementedError("use_bnb without PEFT on the same sub-model: 4-bit base weights cannot be fully fine-tuned "
+                                  "(the reference's Linear4bit weights do not receive gradients either) — add it to use_peft")
+    return params.bnb_nf4_state_dict(sd, device)
 
 
 def pooling_mask(attention_mask: torch.Tensor, autoregressive: bool) -> torch.Tensor:
@@ -89,10 +100,11 @@ def pooling_mask(attention_mask: torch.Tensor, autoregressive: bool) -> torch.Te
 
 
 def build_decoder(name_or_path: str, lora: bool, device: torch.device, state_dict: Optional[Dict] = None,
-                  cfg: Optional[Dict] = None, full: bool = False) -> LlamaDecoder:
+                  cfg: Optional[Dict] = None, full: bool = False, bnb: bool = False) -> LlamaDecoder:
     cfg = cfg or params.load_config(name_or_path)
     kind = params.model_kind(cfg)                # raises for unsupported families
     sd = state_dict if state_dict is not None else params.load_state_dict(name_or_path)
+    sd = _maybe_bnb(sd, bnb, full, device)
     if kind == "falcon":
         if full:
             logger.warning("Falcon generators are forward-only in dalm_b200 (no backward built yet): the generator stays "
@@ -118,10 +130,9 @@ class AutoModelForRagE2E(torch.nn.Module):
         _load_tokenizers: bool = True,
     ) -> None:
         super().__init__()
-        if use_bnb is not None:
-            raise NotImplementedError("use_bnb (bitsandbytes NF4) is outside BASELINE.json's configs (bf16 forward); "
-                                      "not built — see DESIGN.md")
         get_peft = Mode(get_peft) if get_peft is not None else None
+        use_bnb = Mode(use_bnb) if use_bnb is not None else None
+        bnb_r, bnb_g = use_bnb in (Mode.RETRIEVER, Mode.BOTH), use_bnb in (Mode.GENERATOR, Mode.BOTH)
         dev = _device()
         lora_r = get_peft in (Mode.RETRIEVER, Mode.BOTH)
         lora_g = get_peft in (Mode.GENERATOR, Mode.BOTH)
@@ -129,9 +140,9 @@ class AutoModelForRagE2E(torch.nn.Module):
         # requires_grad=True and Adam is built over rag_model.parameters(), train_rage2e.py:336)
         self.retriever_model = (_retriever if _retriever is not None else
                                 build_encoder(retriever_name, lora_r, dev, autoregressive=retriever_is_autoregressive,
-                                              full=_want_full(lora_r)))
+                                              full=_want_full(lora_r), bnb=bnb_r))
         self.generator_model = (_generator if _generator is not None else
-                                build_decoder(generator_name, lora_g, dev, full=_want_full(lora_g)))
+                                build_decoder(generator_name, lora_g, dev, full=_want_full(lora_g), bnb=bnb_g))
         self.retriever_tokenizer = load_tokenizer(retriever_name) if _load_tokenizers else None
         if retriever_is_autoregressive and self.retriever_tokenizer is not None:                   # reference :41-44
             self.retriever_tokenizer.add_eos_token = True

@@ -19,13 +19,12 @@ class AutoModelForSentenceEmbedding(torch.nn.Module):
                  is_autoregressive: bool = False, *, _model: Optional[BertEncoder] = None,
                  _load_tokenizer: bool = True) -> None:
         super().__init__()
-        if use_bnb:
-            # the reference defaults to use_bnb=True (:15); NF4 is outside BASELINE.json's configs. Accept the default
-            # silently-but-logged instead of failing every default call; compute stays bf16.
-            logger.warning("use_bnb=True requested: bitsandbytes NF4 is not built in dalm_b200; running bf16 weights")
+        # use_bnb (the reference's default, :15): the Linear weights take the values of the NF4 quantise/dequantise round trip
+        # the reference's 4-bit model computes with (csrc/nf4.cu); they stay resident as bf16 — see DESIGN.md
         # get_peft=False: every parameter is trained (reference :28-33 skips get_peft_model, Adam covers model.parameters())
         self.model = _model if _model is not None else build_encoder(model_name, bool(get_peft), _device(),
-                                                                     autoregressive=is_autoregressive, full=_want_full(bool(get_peft)))
+                                                                     autoregressive=is_autoregressive, full=_want_full(bool(get_peft)),
+                                                                     bnb=bool(use_bnb))
         self.tokenizer = load_tokenizer(model_name) if _load_tokenizer else None
         if is_autoregressive and self.tokenizer is not None:                                          # reference :36-38
             self.tokenizer.add_eos_token = True

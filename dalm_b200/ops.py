@@ -517,3 +517,18 @@ def topk_ip(q: torch.Tensor, p: torch.Tensor, k: int) -> Tuple[torch.Tensor, tor
     ws = torch.empty(int(_lib.load().dalm_b200_topk_ip_workspace(nq, k)), dtype=torch.uint8, device=q.device)
     _lib.call("dalm_b200_topk_ip", _p(q), _p(p), _ld(p), nq, N, D, int(k), _p(scores), _p(idx), _p(ws), _stream())
     return scores, idx
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# use_bnb: NF4 round trip of a weight at load time
+# ----------------------------------------------------------------------------------------------------------------
+def nf4_roundtrip_(w: torch.Tensor, want_codes: bool = False):
+    """w fp32 contiguous (any shape) -> overwritten with dequant(quant_nf4(fp16(w))); optionally (codes uint8 [n], absmax [n/64])"""
+    _chk(w, f32, "nf4 w")
+    if not w.is_contiguous():
+        raise _lib.DalmB200Error("nf4_roundtrip_: tensor must be contiguous (blocks are taken over the flattened row-major weight)")
+    n = w.numel()
+    codes = torch.empty(n, dtype=torch.uint8, device=w.device) if want_codes else None
+    absmax = torch.empty((n + 63) // 64, dtype=f32, device=w.device) if want_codes else None
+    _lib.call("dalm_b200_nf4_roundtrip", _p(w), n, _p(codes), _p(absmax), _stream())
+    return (w, codes, absmax) if want_codes else w

@@ -176,6 +176,12 @@ long long dalm_b200_topk_ip_workspace(int nq, int K);
 int dalm_b200_topk_ip(const float* Q, const float* P, long long ldp, int nq, int N, int D, int K, float* out_scores,
                       int* out_idx, void* workspace, void* stream);
 
+/* ---- use_bnb: NF4 quantise -> dequantise of a weight, in place, at load time ----
+ * what BitsAndBytesConfig(load_in_4bit, nf4, compute bf16) makes the matmuls see (dalm/models/rag_e2e_base_model.py:136-142,
+ * retriever_only_base_model.py:85-91): fp16 cast, blocks of 64, absmax, 16 NormalFloat levels, dequantised to fp16.
+ * codes (uint8 [n]) / absmax (fp32 [ceil(n/64)]) are optional outputs. */
+int dalm_b200_nf4_roundtrip(float* w, long long n, void* codes, float* absmax, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

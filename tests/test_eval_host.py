@@ -84,3 +84,18 @@ def test_live_reference_helpers_if_present(gold):
         assert ours.calculate_precision_recall(r, c) == eu.calculate_precision_recall(r, c)
     a = (5, [0.1] * 5, [1, 0, 1, 1, 0], 3)
     assert ours.calc_eval_results(*a).model_dump() == eu.calc_eval_results(*a).model_dump()
+
+
+def test_nf4_oracle_properties():
+    """oracle/nf4.py: levels are fixed points, codes are monotone in the value, zero blocks decode to zero"""
+    from oracle import nf4
+    lv = nf4.NF4.astype(np.float32)
+    blk = np.zeros(64, np.float32); blk[:16] = lv
+    deq, codes, absmax = nf4.roundtrip(blk)
+    assert absmax.tolist() == [1.0] and codes[:16].tolist() == list(range(16))
+    assert np.array_equal(deq[:16], lv.astype(np.float16).astype(np.float32))
+    x = np.linspace(-1, 1, 64).astype(np.float32)
+    _, c, _ = nf4.roundtrip(x)
+    assert (np.diff(c.astype(int)) >= 0).all() and c[0] == 0 and c[-1] == 15
+    z, cz, az = nf4.roundtrip(np.zeros(70, np.float32))
+    assert (z == 0).all() and (cz == 7).all() and (az == 0).all()
