@@ -89,9 +89,11 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
                                                             const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                             const float* __restrict__ dy_a, const __nv_bfloat16* __restrict__ dy_b,
-                                                            long long ldb, float* __restrict__ dz32,
+                                                            long long ldb, float* dz32,
                                                             __nv_bfloat16* __restrict__ dz16, long long ld16, int H,
-                                                            DropCfg drop16) {
+                                                            DropCfg drop16, const float* dres) {
+  // dres (optional, may alias dz32): gradient arriving through a residual connection AROUND the norm (pre-LN blocks:
+  // Falcon's x_out = x + attn(LN(x)) + mlp(LN(x))), added to both outputs; each element is read and written by one thread
   extern __shared__ float sm[];
   float* gbuf = sm;          // g = dy*gamma
   float* zh = sm + H;        // zhat
@@ -160,8 +162,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   if (drop16.p == 0.f && (H & 3) == 0 && (ld16 & 3) == 0) {
     for (int i = threadIdx.x; i < H / 4; i += blockDim.x) {
       const float4 g = reinterpret_cast<const float4*>(gbuf)[i], zz = reinterpret_cast<const float4*>(zh)[i];
-      const float4 d = make_float4(rstd * (g.x - s1 - zz.x * s2), rstd * (g.y - s1 - zz.y * s2), rstd * (g.z - s1 - zz.z * s2),
-                                   rstd * (g.w - s1 - zz.w * s2));
+      float4 d = make_float4(rstd * (g.x - s1 - zz.x * s2), rstd * (g.y - s1 - zz.y * s2), rstd * (g.z - s1 - zz.z * s2),
+                             rstd * (g.w - s1 - zz.w * s2));
+      if (dres) {
+        const float4 t = reinterpret_cast<const float4*>(dres + r * H)[i];
+        d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
+      }
       if (dz32) reinterpret_cast<float4*>(dz32 + r * H)[i] = d;
       if (dz16) {
         __nv_bfloat162 lo = __floats2bfloat162_rn(d.x, d.y), hi = __floats2bfloat162_rn(d.z, d.w);
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   }
   const unsigned long long dstream = drop16.p > 0.f ? drop_stream(drop16) : 0ull;
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    const float d = rstd * (gbuf[i] - s1 - zh[i] * s2);
+    const float d = rstd * (gbuf[i] - s1 - zh[i] * s2) + (dres ? dres[r * H + i] : 0.f);
     if (dz32) dz32[r * H + i] = d;
     if (dz16) {
       const float m = drop16.p > 0.f ? drop_scale1(drop16, dstream, (unsigned long long)r * H + i) : 1.f;
@@ -560,7 +566,18 @@ extern "C" int dalm_b200_layernorm_bwd(const float* z, const float* gamma, const
   DALM_REQUIRE(dy_f32 || dy_bf16, "layernorm_bwd: no incoming gradient");
   layernorm_bwd_kernel<<<M, 256, 2 * H * sizeof(float), ST(stream)>>>(z, gamma, mean, rstd, dy_f32, (const __nv_bfloat16*)dy_bf16, ldb,
                                                                      dz32, (__nv_bfloat16*)dz16, ld16, H,
-                                                                     make_drop(drop_p, drop_seed, drop_stream_id, drop_offset));
+                                                                     make_drop(drop_p, drop_seed, drop_stream_id, drop_offset), nullptr);
+  count_launch();
+  return check_launch("layernorm_bwd_kernel");
+}
+// pre-LN variant: dz = LayerNorm-backward(dy) + dres  (dres fp32 [M,H], may alias dz32)
+extern "C" int dalm_b200_layernorm_bwd_res(const float* z, const float* gamma, const float* mean, const float* rstd,
+                                           const float* dy_f32, const void* dy_bf16, long long ldb, const float* dres,
+                                           float* dz32, void* dz16, long long ld16, int M, int H, void* stream) {
+  DALM_REQUIRE(M > 0 && H > 0 && H * 8 <= 48 * 1024, "layernorm_bwd_res: bad shape M=%d H=%d", M, H);
+  DALM_REQUIRE(dy_f32 || dy_bf16, "layernorm_bwd_res: no incoming gradient");
+  layernorm_bwd_kernel<<<M, 256, 2 * H * sizeof(float), ST(stream)>>>(z, gamma, mean, rstd, dy_f32, (const __nv_bfloat16*)dy_bf16, ldb,
+                                                                     dz32, (__nv_bfloat16*)dz16, ld16, H, make_drop(0.f, 0, 0, nullptr), dres);
   count_launch();
   return check_launch("layernorm_bwd_kernel");
 }

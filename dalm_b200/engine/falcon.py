@@ -1,32 +1,43 @@
 """Falcon decoder (Falcon-7B architecture: parallel attention + MLP, multi-query attention, LayerNorm, GELU, rotary,
-tied lm_head) — FORWARD launch sequence over the C-ABI kernels.
+tied lm_head) — forward and (full fine-tuning) backward launch sequences over the C-ABI kernels.
 
 Mirrors `self.generator_model(input_ids=..., attention_mask=...).logits` of the reference
 (dalm/models/rag_e2e_base_model.py:104-106) through HF FalconForCausalLM (`trust_remote_code=True`, :54) for BASELINE
 config 5. The reference's generator LoRA targets (`q_proj`, `v_proj`, rag_e2e_base_model.py:76-77) do not exist in
-Falcon (its fused projection is `query_key_value`), so peft would refuse `--use-peft generator|both`; with
-`--use-peft retriever` the generator is frozen and its gradient is never needed (the generator loss reaches the retriever
-only through the doc log-prob term of the in-batch kernel). This engine therefore builds the forward only and raises for
-adapter requests, exactly where peft would.
+Falcon (its fused projection is `query_key_value`), so peft refuses `--use-peft generator|both`; with `--use-peft
+retriever` or no PEFT the reference trains EVERY Falcon parameter (no get_peft_model => requires_grad stays True,
+Adam over rag_model.parameters(), train_rage2e.py:336). Two modes here:
+
+  frozen (lora=False, full=False)  forward only — evaluation, and the cheap reading of cfg-5 where only the retriever learns
+  full   (full=True)               all parameters in a DenseBank (fp32 master + bf16 shadow + fp32 gradients); the backward
+                                   RECOMPUTES each layer's forward from its saved input (one fp32 [M,H] tensor per layer):
+                                   cfg-5's 36 864 tokens x 32 layers of full activations (~140 GB) do not fit next to the
+                                   125 GB parameter bank, 21 GB of layer inputs do. Costs one extra forward (+33 % FLOPs).
 
 Per layer (bf16 weights): Wqkv [(nh+2)*hd, H] fused q|k|v (one KV head), Wd [H,H], W1 [4H,H], W2 [H,4H]; LayerNorm
 gain/bias fp32. Residual stream fp32; x_out = x + attn(LN(x)) + mlp(LN(x)) (one LayerNorm feeds both branches).
 """
 from __future__ import annotations
 
-from typing import Dict, List
+from typing import Dict, List, Optional
 
 import torch
 
 from .. import ops
+from .dense import DenseBank
 
 bf16, f32 = torch.bfloat16, torch.float32
+
+
+class _Ctx:
+    pass
 
 
 class FalconDecoder(torch.nn.Module):
     LORA_TARGETS = ()
 
-    def __init__(self, cfg: Dict, state_dict: Dict[str, torch.Tensor], device="cuda", lora: bool = False, lora_seed: int = 1):
+    def __init__(self, cfg: Dict, state_dict: Dict[str, torch.Tensor], device="cuda", lora: bool = False, lora_seed: int = 1,
+                 full: bool = False):
         super().__init__()
         if lora:
             raise ValueError("Target modules ['q_proj', 'v_proj'] not found in the base model (Falcon fuses them into "
@@ -48,16 +59,29 @@ class FalconDecoder(torch.nn.Module):
         if self.hd not in (32, 64, 128):
             raise NotImplementedError(f"head_dim {self.hd} not supported by the attention kernels")
         self.Nq, self.Nkv = self.nh * self.hd, self.hd
+        self.Vp = (self.V + 7) // 8 * 8
+        self.lora = None
+        self.full: Optional[DenseBank] = None
+        self.layers: List[Dict[str, torch.Tensor]] = []
         sd = state_dict
+        if full:
+            self._init_full(sd)
+        else:
+            self._init_frozen(sd)
+        self._rope_cache: Dict[int, tuple] = {}
+        self.drop_offset = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.eval()
+
+    # ---- parameters -----------------------------------------------------------------------------------------------
+    def _init_frozen(self, sd) -> None:
+        H = self.H
         g = lambda k, dt: sd[k].to(device=self.dev, dtype=dt).contiguous()
         self.embed = g("transformer.word_embeddings.weight", bf16)
-        self.Vp = (self.V + 7) // 8 * 8
         lm = g("lm_head.weight", bf16) if "lm_head.weight" in sd else self.embed          # tied
         if self.Vp != self.V:
             lm = torch.cat([lm, torch.zeros(self.Vp - self.V, H, dtype=bf16, device=self.dev)], 0)
         self.lm_head = lm
         self.lnf_g, self.lnf_b = g("transformer.ln_f.weight", f32), g("transformer.ln_f.bias", f32)
-        self.layers: List[Dict[str, torch.Tensor]] = []
         for l in range(self.nl):
             p = f"transformer.h.{l}."
             self.layers.append({
@@ -66,21 +90,72 @@ class FalconDecoder(torch.nn.Module):
                 "Wd": g(p + "self_attention.dense.weight", bf16),
                 "W1": g(p + "mlp.dense_h_to_4h.weight", bf16), "W2": g(p + "mlp.dense_4h_to_h.weight", bf16),
             })
-        self._rope_cache: Dict[int, tuple] = {}
-        self.lora = None
-        self.full = None
-        self.trainable = False                                 # forward-only: no backward is built for Falcon yet
-        self.drop_offset = torch.zeros(1, dtype=torch.int64, device=self.dev)
-        self.eval()
+
+    def _param_map(self, has_head: bool):
+        m = [("embed", "acc", "transformer.word_embeddings.weight"), ("lnf_g", "acc", "transformer.ln_f.weight"),
+             ("lnf_b", "acc", "transformer.ln_f.bias")]
+        if has_head:
+            m.append(("lm_head", "gemm", "lm_head.weight"))
+        for l in range(self.nl):
+            p = f"transformer.h.{l}."
+            m += [(f"L{l}.ln_g", "acc", p + "input_layernorm.weight"), (f"L{l}.ln_b", "acc", p + "input_layernorm.bias"),
+                  (f"L{l}.Wqkv", "gemm", p + "self_attention.query_key_value.weight"),
+                  (f"L{l}.Wd", "gemm", p + "self_attention.dense.weight"),
+                  (f"L{l}.W1", "gemm", p + "mlp.dense_h_to_4h.weight"), (f"L{l}.W2", "gemm", p + "mlp.dense_4h_to_h.weight")]
+        return m
+
+    def _init_full(self, sd) -> None:
+        if self.Vp != self.V:
+            raise NotImplementedError("full fine-tuning of Falcon needs vocab_size % 8 == 0 (Falcon-7B: 65024)")
+        # HF ties lm_head to word_embeddings (tie_word_embeddings=True): a separate tensor only if the checkpoint says so
+        has_head = "lm_head.weight" in sd and not self.cfg.get("tie_word_embeddings", True)
+        self._names = self._param_map(has_head)
+        bank = DenseBank([(key, tuple(sd[name].shape), kind) for key, kind, name in self._names], self.dev)
+        for key, _, name in self._names:
+            bank.w32(key).copy_(sd[name].to(self.dev, f32))
+        bank.sync_shadow()
+        self.full = bank
+        self.full_flat = torch.nn.Parameter(bank.p32, requires_grad=True)
+        self.full_flat.grad = bank.g32
+        self.full_flat._dalm_bank = bank
+        self.tied = not has_head
+        self.embed = bank.w16("embed")
+        self.lm_head = self.embed if self.tied else bank.w16("lm_head")
+        self.lnf_g, self.lnf_b = bank.w32("lnf_g"), bank.w32("lnf_b")
+        for l in range(self.nl):
+            k = lambda n: f"L{l}.{n}"
+            self.layers.append({"ln_g": bank.w32(k("ln_g")), "ln_b": bank.w32(k("ln_b")), "Wqkv": bank.w16(k("Wqkv")),
+                                "Wd": bank.w16(k("Wd")), "W1": bank.w16(k("W1")), "W2": bank.w16(k("W2"))})
+
+    def hf_state_dict(self) -> Dict[str, torch.Tensor]:
+        if self.full is None:
+            raise RuntimeError("hf_state_dict: only fully fine-tuned models own their weights")
+        out = {name: self.full.w32(key).detach().cpu().clone() for key, _, name in self._names}
+        if self.tied:
+            out["lm_head.weight"] = out["transformer.word_embeddings.weight"]
+        return out
+
+    def load_hf_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        for key, _, name in self._names:
+            self.full.w32(key).copy_(sd[name].to(self.dev, f32))
+        self.full.sync_shadow()
+
+    @property
+    def trainable(self) -> bool:
+        return self.full is not None
+
+    @property
+    def anchor(self) -> torch.nn.Parameter:
+        return self.full_flat
 
     def repack_lora(self) -> None:
         pass
 
     def banks(self) -> list:
-        return []
+        return [self.full] if self.full is not None else []
 
     def grad_buffers(self) -> list:
-        return []
+        return [b.grad for b in self.banks()]
 
     def _rope(self, L: int):
         if L not in self._rope_cache:
@@ -89,25 +164,94 @@ class FalconDecoder(torch.nn.Module):
             self._rope_cache[L] = (fr.cos().to(self.dev).contiguous(), fr.sin().to(self.dev).contiguous())
         return self._rope_cache[L]
 
+    # ---- one layer ------------------------------------------------------------------------------------------------
+    def _layer_fwd(self, W, x, mask, B, L, cos_t, sin_t, keep: bool):
+        """x fp32 [M,H] -> x_out fp32; with keep=True also everything the layer's backward needs"""
+        _, h, mean, rstd = ops.layernorm_fwd(x, W["ln_g"], W["ln_b"], self.eps, want_f32=False)   # one LN feeds both branches
+        qkv = ops.gemm(h, W["Wqkv"])                                                  # [M, (nh+2)*hd]
+        ops.rope_(qkv, 0, self.nh + 1, self.hd, cos_t, sin_t, L)                      # q heads then the single k head
+        att, lse = ops.attention_fwd(qkv[:, :self.Nq], qkv[:, self.Nq:self.Nq + self.hd], qkv[:, self.Nq + self.hd:],
+                                     mask, B, L, self.nh, 1, self.hd, causal=True)
+        t = ops.gemm(att, W["Wd"], out_dtype=f32, resid=x)                            # x + attention branch
+        if keep:
+            pre = ops.gemm(h, W["W1"])                                                # GELU's input is needed by its backward
+            h4 = ops.gelu_fwd(pre)
+        else:
+            pre, h4 = None, ops.gemm(h, W["W1"], act=1)                               # GELU(erf) fused in the epilogue
+        x_out = ops.gemm(h4, W["W2"], out_dtype=f32, resid=t)                         # + MLP branch
+        if not keep:
+            return x_out, None
+        a = _Ctx()
+        a.h, a.mean, a.rstd, a.qkv, a.att, a.lse, a.pre, a.h4 = h, mean, rstd, qkv, att, lse, pre, h4
+        return x_out, a
+
+    def _layer_bwd(self, l: int, W, x, a, dx32, dx16, mask, B, L, cos_t, sin_t, acc: bool):
+        """dx (fp32 + its bf16 copy) w.r.t. the layer output -> (dx32, dx16) w.r.t. the layer input; parameter gradients into
+        the bank. dx32 is updated in place."""
+        bank, M, H, hd = self.full, B * L, self.H, self.hd
+        G = lambda n: bank.g(f"L{l}.{n}")
+        # MLP branch
+        ops.wgrad_(dx16, a.h4, G("W2"), acc)
+        dpre = ops.gemm(dx16, W["W2"], layout=1)                                      # [M,4H] = d h4
+        ops.gelu_bwd_(a.pre, dpre)                                                    # -> d pre
+        ops.wgrad_(dpre, a.h, G("W1"), acc)
+        dh = ops.gemm(dpre, W["W1"], layout=1)                                        # [M,H] MLP part of d LN-output
+        # attention branch
+        ops.wgrad_(dx16, a.att, G("Wd"), acc)
+        datt = ops.gemm(dx16, W["Wd"], layout=1)                                      # [M,Nq]
+        dqkv = torch.empty(M, self.Nq + 2 * hd, dtype=bf16, device=self.dev)
+        ops.attention_bwd(a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + hd], a.qkv[:, self.Nq + hd:], mask, a.att, a.lse, datt,
+                          B, L, self.nh, 1, hd, causal=True, dq=dqkv[:, :self.Nq], dk=dqkv[:, self.Nq:self.Nq + hd],
+                          dv=dqkv[:, self.Nq + hd:])                                  # dK / dV summed over the 71 query heads
+        ops.rope_(dqkv, 0, self.nh + 1, hd, cos_t, sin_t, L, backward=True)
+        ops.wgrad_(dqkv, a.h, G("Wqkv"), acc)
+        dh = ops.gemm(dqkv, W["Wqkv"], layout=1, resid=dh, out=dh)                    # + attention part, accumulated in place
+        # the shared LayerNorm, and the residual connection around the whole block
+        ops.col_reduce_(dy_bf16=dh, z=x, mean=a.mean, rstd=a.rstd, out_sum=G("ln_b"), out_prod=G("ln_g"))
+        return ops.layernorm_bwd_res(x, W["ln_g"], a.mean, a.rstd, dh, dres=dx32, dz32=dx32)
+
+    # ---- whole model ----------------------------------------------------------------------------------------------
     def forward_logits(self, ids: torch.Tensor, mask: torch.Tensor, save: bool = False):
-        """ids, mask int64 [B,L] -> (logits bf16 [B,L,V], None). Nothing is saved: the decoder is frozen."""
+        """ids, mask int64 [B,L] -> (logits bf16 [B,L,V], ctx). ctx (save=True on a trainable model) holds only each layer's
+        fp32 input: the backward recomputes the rest."""
         B, L = ids.shape
-        M, H = B * L, self.H
         cos_t, sin_t = self._rope(L)
         mask = mask.contiguous()
+        keep_inputs = save and self.full is not None
+        ctx = _Ctx() if keep_inputs else None
         x = ops.embed_gather(ids, self.embed)                                         # fp32 residual stream [M,H]
+        xs = []
         for W in self.layers:
-            _, h, _, _ = ops.layernorm_fwd(x, W["ln_g"], W["ln_b"], self.eps, want_f32=False)     # one LN feeds both branches
-            qkv = ops.gemm(h, W["Wqkv"])                                              # [M, (nh+2)*hd]
-            ops.rope_(qkv, 0, self.nh + 1, self.hd, cos_t, sin_t, L)                  # q heads then the single k head
-            att, _ = ops.attention_fwd(qkv[:, :self.Nq], qkv[:, self.Nq:self.Nq + self.hd], qkv[:, self.Nq + self.hd:],
-                                       mask, B, L, self.nh, 1, self.hd, causal=True)
-            t = ops.gemm(att, W["Wd"], out_dtype=f32, resid=x)                        # x + attention branch
-            h4 = ops.gemm(h, W["W1"], act=1)                                          # GELU(erf) fused in the epilogue
-            x = ops.gemm(h4, W["W2"], out_dtype=f32, resid=t)                         # + MLP branch
-        _, hf, _, _ = ops.layernorm_fwd(x, self.lnf_g, self.lnf_b, self.eps, want_f32=False)
+            if keep_inputs:
+                xs.append(x)
+            x, _ = self._layer_fwd(W, x, mask, B, L, cos_t, sin_t, keep=False)
+        _, hf, mean_f, rstd_f = ops.layernorm_fwd(x, self.lnf_g, self.lnf_b, self.eps, want_f32=False)
         logits = ops.gemm(hf, self.lm_head)
-        return logits.view(B, L, self.Vp)[:, :, :self.V], None
+        if keep_inputs:
+            ctx.B, ctx.L, ctx.mask, ctx.ids, ctx.xs, ctx.x_final, ctx.hf, ctx.mean_f, ctx.rstd_f = \
+                B, L, mask, ids.contiguous(), xs, x, hf, mean_f, rstd_f
+        return logits.view(B, L, self.Vp)[:, :, :self.V], ctx
 
-    def backward_logits(self, ctx, dlogits) -> None:
-        return None                                                                   # frozen: nothing trainable
+    def backward_logits(self, ctx, dlogits: torch.Tensor) -> None:
+        """dlogits bf16 [B,L,V] -> gradients of every parameter (full mode); nothing to do for a frozen decoder"""
+        if self.full is None or ctx is None:
+            return
+        bank, B, L = self.full, ctx.B, ctx.L
+        M, H = B * L, self.H
+        cos_t, sin_t = self._rope(L)
+        acc = bank.begin_backward()
+        if dlogits.stride(-1) != 1 or dlogits.stride(-2) != self.Vp:
+            dlogits = dlogits.contiguous()
+        dl2 = torch.as_strided(dlogits, (M, self.Vp), (self.Vp, 1), dlogits.storage_offset())
+        # tied head: its weight gradient lands in the embedding table's (accumulating) gradient
+        ops.wgrad_(dl2, ctx.hf, bank.g("embed") if self.tied else bank.g("lm_head"), True if self.tied else acc)
+        dhf = ops.gemm(dl2, self.lm_head, layout=1)                                   # [M,H]
+        ops.col_reduce_(dy_bf16=dhf, z=ctx.x_final, mean=ctx.mean_f, rstd=ctx.rstd_f, out_sum=bank.g("lnf_b"), out_prod=bank.g("lnf_g"))
+        dx32, dx16 = ops.layernorm_bwd(ctx.x_final, self.lnf_g, ctx.mean_f, ctx.rstd_f, dy_bf16=dhf)
+        for l in range(self.nl - 1, -1, -1):
+            W, x = self.layers[l], ctx.xs[l]
+            _, a = self._layer_fwd(W, x, ctx.mask, B, L, cos_t, sin_t, keep=True)      # recompute this layer's activations
+            dx32, dx16 = self._layer_bwd(l, W, x, a, dx32, dx16, ctx.mask, B, L, cos_t, sin_t, acc)
+            del a
+        ops.embed_scatter_add_(dx32, ctx.ids, bank.g("embed"))
+        bank.end_backward()

@@ -106,10 +106,7 @@ def build_decoder(name_or_path: str, lora: bool, device: torch.device, state_dic
     sd = state_dict if state_dict is not None else params.load_state_dict(name_or_path)
     sd = _maybe_bnb(sd, bnb, full, device)
     if kind == "falcon":
-        if full:
-            logger.warning("Falcon generators are forward-only in dalm_b200 (no backward built yet): the generator stays "
-                           "frozen where the reference would fine-tune it — see DESIGN.md")
-        return FalconDecoder(cfg, sd, device=device, lora=lora)       # raises for lora=True, like peft would
+        return FalconDecoder(cfg, sd, device=device, lora=lora, full=full)   # raises for lora=True, like peft would
     if kind != "llama":
         raise NotImplementedError(f"generator of kind {kind!r} is not a causal decoder")
     return LlamaDecoder(cfg, sd, device=device, lora=lora, full=full)

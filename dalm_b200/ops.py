@@ -306,6 +306,18 @@ def layernorm_bwd(z, gamma, mean, rstd, dy_f32=None, dy_bf16=None, want_f32: boo
     return dz32, dz16
 
 
+def layernorm_bwd_res(z, gamma, mean, rstd, dy_bf16, dres, dz32=None, dz16=None):
+    """pre-LN residual block: dz = LayerNorm-backward(dy) + dres  -> (dz32, dz16); dz32 may be `dres` itself (in place)"""
+    M, H = z.shape
+    if dz32 is None:
+        dz32 = torch.empty_like(z)
+    if dz16 is None:
+        dz16 = torch.empty(M, H, dtype=bf16, device=z.device)
+    _lib.call("dalm_b200_layernorm_bwd_res", _p(z), _p(gamma), _p(mean), _p(rstd), None, _p(dy_bf16), _ld(dy_bf16), _p(dres),
+              _p(dz32), _p(dz16), _ld(dz16), M, H, _stream())
+    return dz32, dz16
+
+
 def rmsnorm_fwd(x, g, eps: float, h=None):
     _chk(x, f32, "x")
     M, H = x.shape

@@ -264,7 +264,8 @@ class GraphedStep:
                 step_fn(model, self.static, self.logit_scale, backward=True, grad_scale=self.grad_scale)
         cur.wait_stream(side)
         torch.cuda.synchronize()
-        if zero_grads is not None:
+        torch.cuda.empty_cache()                                # the capture allocates from its own pool: do not keep the warm-up's
+        if zero_grads is not None:                              # activations cached next to it (matters when HBM is nearly full)
             zero_grads()                                        # the warm-up accumulated gradients
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):

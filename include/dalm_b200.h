@@ -114,6 +114,10 @@ int dalm_b200_layernorm_bwd(const float* z, const float* gamma, const float* mea
                             const void* dy_bf16, long long ldb, float* dz32, void* dz16, long long ld16, int M, int H,
                             float drop_p, unsigned long long drop_seed,
     unsigned long long drop_stream_id, const void* drop_offset, void* stream);
+/* pre-LN blocks (Falcon): dz = LayerNorm-backward(dy) + dres, the gradient arriving around the norm; dres may alias dz32 */
+int dalm_b200_layernorm_bwd_res(const float* z, const float* gamma, const float* mean, const float* rstd, const float* dy_f32,
+                                const void* dy_bf16, long long ldb, const float* dres, float* dz32, void* dz16, long long ld16,
+                                int M, int H, void* stream);
 int dalm_b200_rmsnorm_fwd(const float* x, const float* g, void* h, long long ldh, float* rstd, int M, int H, float eps,
                           void* stream);
 int dalm_b200_rmsnorm_bwd(const float* x, const float* g, const float* rstd, const void* dh, long long lddh,

@@ -319,3 +319,58 @@ def test_full_finetune_trainer_end_to_end_and_resume(cuda_dev, tmp_path):
     g0 = load_file(os.path.join(gdir, "model.safetensors"))
     assert sum((gsd[k].float() - g0[k].float()).abs().max() > 0 for k in g0) == len(g0)
     om.build_llama(json.load(open(os.path.join(out2, "generator", "config.json"))), gsd)
+
+
+def test_falcon_full_finetune_with_recompute_matches_oracle(cuda_dev):
+    """BASELINE config 5 family at toy size with the reference's semantics for `--use-peft retriever`: LoRA retriever, Falcon
+    generator FULLY fine-tuned (MQA attention backward, parallel attn+MLP block, tied head). The backward recomputes every
+    layer from its saved input; every Falcon parameter's gradient is checked against HF FalconForCausalLM autograd."""
+    from dalm_b200 import synthetic
+    from dalm_b200.engine import params
+    from dalm_b200.engine.bert import BertEncoder
+    from dalm_b200.engine.falcon import FalconDecoder
+    from dalm_b200.models.rag_e2e_base_model import AutoModelForRagE2E, Mode
+    from dalm_b200.optim import FusedAdam
+    from dalm_b200.training.utils.train_utils import GraphedStep, fused_rag_step
+    from oracle import models as om
+    bcfg, fcfg = synthetic.bert_config("bge-tiny", 600), synthetic.falcon_config("falcon-tiny", 504)
+    r16 = lambda sd: {k: v.to(bf16).float() for k, v in sd.items()}
+    bsd, fsd = r16(params.random_state_dict("bert", bcfg, seed=21)), r16(params.random_state_dict("falcon", fcfg, seed=22))
+    enc, dec = BertEncoder(bcfg, bsd, device=cuda_dev, lora=True), FalconDecoder(fcfg, fsd, device=cuda_dev, full=True)
+    g = torch.Generator().manual_seed(23)
+    for n, _, _ in enc.lora.specs:
+        enc.lora.B[n].copy_((torch.randn(enc.lora.B[n].shape, generator=g) * 0.02).to(cuda_dev))
+    enc.repack_lora()
+    model = AutoModelForRagE2E("", "", get_peft=Mode.RETRIEVER, _retriever=enc, _generator=dec, _load_tokenizers=False)
+    batch = _batch(4, 10, 20, 48, 600, 504, seed=24)
+    bert, falcon = om.build_bert(bcfg, bsd), om.build_falcon(fcfg, fsd)
+    om.attach_lora(bert, {n: {"A": enc.lora.A[n].cpu(), "B": enc.lora.B[n].cpu()} for n, _, _ in enc.lora.specs})
+    ref = om.rag_step(bert, falcon, batch)
+    opt = FusedAdam(model.parameters(), lr=1e-3)
+    opt.zero_grad()
+    out = fused_rag_step(model, batch, 100.0)
+    assert abs(out["loss"].item() - ref["loss"].item()) / abs(ref["loss"].item()) < 1e-3
+    worst, checked = ("", 0.0), 0
+    for key, _, name in dec._names:
+        rg = ref["grads"]["generator." + name]
+        extra = ref["grads"].get("generator.lm_head.weight")
+        if name == "transformer.word_embeddings.weight" and extra is not None and extra.data_ptr() != rg.data_ptr():
+            rg = rg + extra                                                        # untied in the oracle build: sum of both uses
+        e = _rel(dec.full.g(key), rg)
+        checked += 1
+        if e > worst[1]:
+            worst = (name, e)
+    assert worst[1] < 6e-2 and checked == 3 + 6 * fcfg["num_hidden_layers"], (worst, checked)
+    w = max(max(_rel(enc.lora.gA[n], ref["grads"]["retriever." + n + ".lora_A"]),
+                _rel(enc.lora.gB[n], ref["grads"]["retriever." + n + ".lora_B"])) for n, _, _ in enc.lora.specs)
+    assert w < 6e-2, w
+    # training under a CUDA graph (recomputation inside the captured backward) decreases the loss
+    graphed = GraphedStep(fused_rag_step, model, batch, 100.0, zero_grads=opt.zero_grad)
+    losses = []
+    for _ in range(6):
+        opt.zero_grad()
+        losses.append(graphed(batch)["loss"].item())
+        opt.step(); enc.repack_lora()
+    assert losses[-1] < losses[0], losses
+    sd = dec.hf_state_dict()
+    assert torch.equal(sd["lm_head.weight"], sd["transformer.word_embeddings.weight"]) and len(sd) == 4 + 6 * fcfg["num_hidden_layers"]

@@ -20,7 +20,7 @@ dev = torch.device("cuda:0")
 bf16 = torch.bfloat16
 g = torch.Generator().manual_seed(0)
 bcfg = dict(synthetic.bert_config("bge-large-en"), _device_rng=True)
-full = which.endswith("full")
+full = which in ("cfg2full", "cfg3full")
 enc = BertEncoder(bcfg, params.random_state_dict("bert", bcfg, seed=0, dtype=bf16, device=dev), device=dev, lora=not full, full=full)
 
 
@@ -59,7 +59,8 @@ else:
     from dalm_b200.models.rag_e2e_base_model import AutoModelForRagE2E, Mode
     B, LG = 18, 2048
     fcfg = dict(synthetic.falcon_config("falcon-7b"), _device_rng=True)
-    dec = FalconDecoder(fcfg, params.random_state_dict("falcon", fcfg, seed=0, dtype=bf16, device=dev), device=dev)
+    gen_full = which == "cfg5full"        # the reference's semantics for --use-peft retriever: the generator is fully fine-tuned
+    dec = FalconDecoder(fcfg, params.random_state_dict("falcon", fcfg, seed=0, dtype=bf16, device=dev), device=dev, full=gen_full)
     torch.cuda.empty_cache()
     model = AutoModelForRagE2E("", "", get_peft=Mode.RETRIEVER, _retriever=enc, _generator=dec, _load_tokenizers=False)
     batches = [{"retriever_query_input_ids": rnd(B, 50, 30522), "retriever_query_attention_mask": ones(B, 50),
@@ -68,6 +69,9 @@ else:
                 "query_passage_input_len": torch.full((B,), 700)} for _ in range(4)]
     step_fn, label = fused_rag_step, "cfg-5 train_rage2e bge-large-en + Falcon-7B (frozen, use_peft=retriever), bs=18, Lg=2048"
     tflop = 1.935 * 2 + 0.033 * 3 + 510.3 + 43.9        # encoder fwd+bwd (PEFT) + generator forward only (SURVEY §8d terms)
+    if gen_full:
+        label = "cfg-5 train_rage2e bge-large-en (LoRA) + Falcon-7B FULLY fine-tuned (reference semantics of use_peft=retriever), bs=18, Lg=2048, layer recomputation"
+        tflop = 1.935 * 2 + 0.033 * 3 + 3 * (510.3 + 43.9)     # algorithmic full-FT work (3 x fwd); the recomputed forward is NOT counted
 
 model.train()
 opt = FusedAdam(model.parameters(), lr=1e-4)
