@@ -567,13 +567,22 @@ extern "C" int dalm_b200_gemm_bf16(int layout, const void* A, long long lda, con
   DALM_REQUIRE(act == 0 || act == 1, "gemm: act must be 0 (none) or 1 (gelu)");
   int bn = block_n;
   if (bn == 0) {
-    // tile-shape heuristic (measured, profiles/r01_gemm_probe_tma_store_epilogue.jsonl): the single-CTA 128x256 tile is
-    // the fastest whenever it yields >= 1 wave of 148 CTAs; smaller problems take the widest tile that still does.
-    // The CTA-pair kernel (block_n 2128/2256) is correct and tested but not faster on these shapes, so never auto-picked.
+    // tile-shape heuristic: estimated time = waves of 148 CTAs x tile width x an efficiency penalty for narrow tiles (a
+    // 128 x BN tile re-reads its A operand from shared memory for every BN columns: profiles/r01_gemm_probe_tiles.jsonl).
+    // The 128x256 tile wins whenever the problem has more than about one wave of work — including N = 1024 at 3 204
+    // encoder rows, where 104 tiles in ONE wave take 32 us against 54 us for 208 half-width tiles in two waves
+    // (profiles/r01_gemm_shapes_in_step.txt had those shapes at 280-410 TFLOP/s). The CTA-pair kernel (block_n 2128/2256) is
+    // correct and tested but not faster on these shapes, so never auto-picked.
     const long long m1 = (M + 127) / 128;
-    if (m1 * ((N + 255) / 256) >= kNumSMs && N >= 256) bn = 256;
-    else if (m1 * ((N + 127) / 128) >= kNumSMs && N >= 128) bn = 128;
-    else bn = 64;
+    double best = 1e30;
+    const int cand[3] = {256, 128, 64};
+    const double penalty[3] = {1.0, 1.55, 2.7};      // measured at 26700x1024x4096: 203 / 313 / 549 us
+    for (int i = 0; i < 3; ++i) {
+      if (cand[i] > 64 && N < cand[i]) continue;                // do not pad N by more than one tile
+      const long long tiles = m1 * ((N + cand[i] - 1) / cand[i]);
+      const double cost = (double)((tiles + kNumSMs - 1) / kNumSMs) * cand[i] * penalty[i];
+      if (cost < best) { best = cost; bn = cand[i]; }
+    }
   }
   DALM_REQUIRE(bn == 64 || bn == 128 || bn == 256 || bn == 2128 || bn == 2256 || bn == 3256 || bn == 4256,
                "gemm: block_n must be 0, 64/128/256 (single CTA) or 2128/2256 (CTA pair)");

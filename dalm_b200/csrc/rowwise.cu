@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(256) lora_dx_kernel(__nv_bfloat16* __restrict_
                                                       const __nv_bfloat16* __restrict__ G, long long ldg,
                                                       const __nv_bfloat16* __restrict__ A, long long lda, int M, int K,
                                                       DropCfg drop) {
-  constexpr int ROWS = 32;
+  constexpr int ROWS = 16;
   __shared__ __align__(16) float Gs[ROWS][R];
   const int m0 = blockIdx.y * ROWS;
   for (int i = threadIdx.x; i < ROWS * R; i += 256) {
@@ -489,24 +489,33 @@ __global__ void __launch_bounds__(256) lora_dx_kernel(__nv_bfloat16* __restrict_
   if (c >= K) return;
   const unsigned long long dstream = drop_stream(drop);
   const int nrows = min(ROWS, M - m0);
-  for (int mm = 0; mm < nrows; ++mm) {
-    const int m = m0 + mm;
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // four rows per step with their loads issued together: the read-modify-write of dh otherwise serialises one 16-byte
+  // load per thread per iteration (measured 47 us for 76 MB = a quarter of HBM speed)
+  for (int mm = 0; mm < nrows; mm += 4) {
+    bf16x8 raw[4];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const float gv = Gs[mm][r];
-      float av[8];
-      unpack8(areg[r], av);
+    for (int u = 0; u < 4; ++u)
+      if (mm + u < nrows) raw[u] = *reinterpret_cast<const bf16x8*>(dh + (size_t)(m0 + mm + u) * lddh + c);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(gv, av[j], acc[j]);
+    for (int u = 0; u < 4; ++u) {
+      if (mm + u >= nrows) break;
+      const int m = m0 + mm + u;
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float gv = Gs[mm + u][r];
+        float av[8];
+        unpack8(areg[r], av);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(gv, av[j], acc[j]);
+      }
+      float sc[8], cur[8];
+      drop_scale8(drop, dstream, ((unsigned long long)m * K + c) >> 3, sc);
+      unpack8(raw[u], cur);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cur[j] = fmaf(sc[j], acc[j], cur[j]);
+      *reinterpret_cast<bf16x8*>(dh + (size_t)m * lddh + c) = pack8(cur);
     }
-    float sc[8], cur[8];
-    drop_scale8(drop, dstream, ((unsigned long long)m * K + c) >> 3, sc);
-    __nv_bfloat16* p = dh + (size_t)m * lddh + c;
-    unpack8(*reinterpret_cast<const bf16x8*>(p), cur);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) cur[j] = fmaf(sc[j], acc[j], cur[j]);
-    *reinterpret_cast<bf16x8*>(p) = pack8(cur);
   }
 }
 
@@ -697,7 +706,7 @@ extern "C" int dalm_b200_lora_dx(void* dh, long long lddh, const void* G, long l
                                  const void* offset, void* stream) {
   DALM_REQUIRE((R == 8 || R == 16 || R == 24) && (K % 8) == 0 && (lddh % 8) == 0 && (lda % 8) == 0, "lora_dx: bad shape R=%d K=%d", R, K);
   DALM_REQUIRE(p >= 0.f && p < 1.f, "lora_dx: p must be in [0,1)");
-  dim3 grid((K / 8 + 255) / 256, (M + 31) / 32);
+  dim3 grid((K / 8 + 255) / 256, (M + 15) / 16);
   const DropCfg dc = make_drop(p, seed, stream_id, offset);
   auto* dhp = (__nv_bfloat16*)dh; auto* gp = (const __nv_bfloat16*)G; auto* ap = (const __nv_bfloat16*)A;
   if (R == 8)       lora_dx_kernel<8><<<grid, 256, 0, ST(stream)>>>(dhp, lddh, gp, ldg, ap, lda, M, K, dc);
