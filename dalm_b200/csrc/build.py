@@ -10,7 +10,7 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["api.cu", "loss.cu", "gemm_tcgen05.cu", "attention.cu", "rowwise.cu", "lora.cu", "attention_tc.cu", "dense_grad.cu", "topk.cu", "nf4.cu"]
+SOURCES = ["api.cu", "loss.cu", "gemm_tcgen05.cu", "attention.cu", "rowwise.cu", "lora.cu", "attention_tc.cu", "dense_grad.cu", "topk.cu", "nf4.cu", "decode.cu"]
 HEADERS = ["common.cuh", "ptx.cuh"]
 LIB = os.path.join(HERE, "libdalm_b200.so")
 NVCC_FLAGS = [

@@ -1,0 +1,214 @@
+// dalm_b200 — autoregressive greedy decoding for the evaluation path (reference dalm/eval/eval_rag.py:126-140:
+// `model.generate(**inputs, max_length=max_length, early_stopping=True)` on the generator, then exact match :268-277).
+//
+//   rope_pos_kernel      : RoPE at explicit per-token position ids (HF generate derives them from the attention mask:
+//                          cumsum(mask) - 1, so left / right padded prompts rotate differently from arange)
+//   attn_decode_kernel   : one query token per sequence against the KV cache. HBM-bound: reads the cached K and V of
+//                          one (sequence, kv head) once = 2 * T * D * 2 bytes; the current token's K / V rows are
+//                          appended to the cache by the same launch (no separate copy kernel)
+//   greedy_step_kernel   : argmax over the vocabulary row + HF's finished-sequence bookkeeping (pad after EOS), writes
+//                          the token, its attention-mask bit and its position id for the next step
+//
+// All state a step needs (next token ids, position ids, finished flags, per-step alive counts) lives in device memory,
+// so the host loop never reads anything back except an "is anyone still generating" flag every few steps.
+#include "common.cuh"
+#include <limits.h>
+
+namespace dalm {
+
+__global__ void rope_pos_kernel(__nv_bfloat16* __restrict__ buf, long long ld, int col0, int nheads, int D,
+                                const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                                const int64_t* __restrict__ pos, int T) {
+  // one CTA per token row; HF rotate_half convention, same arithmetic as rope_kernel (rowwise.cu)
+  const size_t r = blockIdx.x;
+  long long p = pos[r];
+  p = p < 0 ? 0 : (p >= T ? T - 1 : p);
+  const int half = D / 2;
+  __nv_bfloat16* base = buf + r * ld + col0;
+  for (int i = threadIdx.x; i < nheads * half; i += blockDim.x) {
+    const int h = i / half, j = i - h * half;
+    __nv_bfloat16* q = base + h * D + j;
+    const float x1 = __bfloat162float(q[0]), x2 = __bfloat162float(q[half]);
+    const float c = cos_t[(size_t)p * half + j], s = sin_t[(size_t)p * half + j];
+    q[0] = __float2bfloat16(x1 * c - x2 * s);
+    q[half] = __float2bfloat16(x2 * c + x1 * s);
+  }
+}
+
+// grid (Hq, B), 128 threads. Shared memory: q[D] | p[cur+1] | red[32] | part[128] floats.
+//   pass 1: thread-per-key scores (each thread reads whole K rows with 16-byte loads, q broadcast from smem)
+//   pass 2: block max / exp / sum
+//   pass 3: thread-per-output-column PV (128 / D thread groups split the keys, combined through smem)
+template <int D>
+__global__ void __launch_bounds__(128) attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, long long ldq, int q_col,
+                                                          int k_col, int v_col, __nv_bfloat16* __restrict__ cache_k,
+                                                          __nv_bfloat16* __restrict__ cache_v, long long cache_sb,
+                                                          long long cache_st, const int64_t* __restrict__ mask,
+                                                          long long ldm, __nv_bfloat16* __restrict__ out, long long ldo,
+                                                          int Hq, int Hkv, int cur, float scale) {
+  extern __shared__ float sm[];
+  float* sq = sm;
+  float* sp = sm + D;
+  float* red = sp + ((cur + 1 + 3) & ~3);
+  float* part = red + 32;
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int group = Hq / Hkv, kvh = h / group;
+  const __nv_bfloat16* qrow = qkv + (size_t)b * ldq + q_col + h * D;
+  const __nv_bfloat16* krow = qkv + (size_t)b * ldq + k_col + kvh * D;
+  const __nv_bfloat16* vrow = qkv + (size_t)b * ldq + v_col + kvh * D;
+  __nv_bfloat16* ck = cache_k + (size_t)b * cache_sb + kvh * D;
+  __nv_bfloat16* cv = cache_v + (size_t)b * cache_sb + kvh * D;
+  if (tid < D) {
+    sq[tid] = __bfloat162float(qrow[tid]) * scale;
+    if (h % group == 0) {                       // the first query head of each kv group appends this token's K / V
+      ck[(size_t)cur * cache_st + tid] = krow[tid];
+      cv[(size_t)cur * cache_st + tid] = vrow[tid];
+    }
+  }
+  __syncthreads();
+
+  float lmax = -INFINITY;
+  for (int t = tid; t <= cur; t += 128) {
+    // column `cur` is the token being decoded: always visible, read from the qkv row (its cache slot is written above
+    // by ANOTHER CTA of this launch, so nobody reads it back here)
+    const bool valid = (t == cur) || mask[(size_t)b * ldm + t] != 0;
+    float s = -INFINITY;
+    if (valid) {
+      const __nv_bfloat16* kp = (t == cur) ? krow : ck + (size_t)t * cache_st;
+      s = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; j += 8) {
+        float f[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(kp + j), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += sq[j + e] * f[e];
+      }
+    }
+    sp[t] = s;
+    lmax = fmaxf(lmax, s);
+  }
+  const float m = block_max(lmax, red);         // finite: column `cur` is always valid
+  float lsum = 0.f;
+  for (int t = tid; t <= cur; t += 128) {
+    const float s = sp[t];
+    const float p = (s == -INFINITY) ? 0.f : __expf(s - m);
+    sp[t] = p;
+    lsum += p;
+  }
+  const float sum = block_sum(lsum, red);
+  __syncthreads();
+
+  constexpr int G = 128 / D;                    // thread groups splitting the keys: 1 (D=128), 2 (64), 4 (32)
+  const int d = tid % D, g = tid / D;
+  float acc = 0.f;
+  for (int t = g; t <= cur; t += G) {
+    const float p = sp[t];
+    if (p != 0.f) {
+      const __nv_bfloat16* vp = (t == cur) ? vrow : cv + (size_t)t * cache_st;
+      acc += p * __bfloat162float(vp[d]);
+    }
+  }
+  if (G > 1) {
+    part[tid] = acc;
+    __syncthreads();
+    if (g == 0)
+      for (int gg = 1; gg < G; ++gg) acc += part[gg * D + d];
+  }
+  if (g == 0) out[(size_t)b * ldo + h * D + d] = __float2bfloat16(acc / sum);
+}
+
+// grid B, 256 threads. argmax over logits[b, 0..V) (ties -> lowest index, like torch.argmax), then HF's greedy bookkeeping
+// (transformers generation/utils.py _sample, do_sample=False): finished rows emit pad, a row finishes when it emits an EOS id.
+__global__ void __launch_bounds__(256) greedy_step_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, int V,
+                                                          const int64_t* __restrict__ eos_ids, int n_eos, long long pad_id,
+                                                          int* __restrict__ unfinished, int64_t* __restrict__ tokens,
+                                                          long long ldt, int64_t* __restrict__ mask, long long ldm, int col,
+                                                          int64_t* __restrict__ next_ids, int64_t* __restrict__ pos,
+                                                          int* __restrict__ alive_slot) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const __nv_bfloat16* row = logits + (size_t)b * ld;
+  float best = -INFINITY;
+  int bi = INT_MAX;
+  for (int i = tid; i < V; i += 256) {
+    const float v = __bfloat162float(row[i]);
+    if (bi == INT_MAX || v > best) { best = v; bi = i; }      // ascending i: strict > keeps the lowest index
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi != INT_MAX && (bi == INT_MAX || ov > best || (ov == best && oi < bi))) { best = ov; bi = oi; }
+  }
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  if (lane == 0) { sv[warp] = best; si[warp] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) {
+      const float ov = sv[w];
+      const int oi = si[w];
+      if (oi != INT_MAX && (bi == INT_MAX || ov > best || (ov == best && oi < bi))) { best = ov; bi = oi; }
+    }
+    int unf = unfinished[b];
+    const long long tok = unf ? (long long)bi : pad_id;
+    tokens[(size_t)b * ldt + col] = tok;
+    mask[(size_t)b * ldm + col] = 1;             // HF appends ones to the attention mask for every generated column
+    next_ids[b] = tok;
+    pos[b] += 1;                                 // position id of the new token = cumsum(mask) - 1
+    if (unf)
+      for (int e = 0; e < n_eos; ++e)
+        if (tok == eos_ids[e]) unf = 0;
+    unfinished[b] = unf;
+    if (unf) atomicAdd(alive_slot, 1);
+  }
+}
+
+}  // namespace dalm
+
+using namespace dalm;
+#define ST(s) ((cudaStream_t)(s))
+
+extern "C" int dalm_b200_rope_pos(void* buf, long long ld, int col0, int nheads, int D, const float* cos_t,
+                                  const float* sin_t, const int64_t* pos, int M, int T, void* stream) {
+  DALM_REQUIRE(M > 0 && T > 0 && nheads > 0 && (D % 2) == 0, "rope_pos: bad shape M=%d T=%d heads=%d D=%d", M, T, nheads, D);
+  DALM_REQUIRE(pos != nullptr && cos_t != nullptr && sin_t != nullptr, "rope_pos: null table / positions");
+  rope_pos_kernel<<<M, 256, 0, ST(stream)>>>((__nv_bfloat16*)buf, ld, col0, nheads, D, cos_t, sin_t, pos, T);
+  count_launch();
+  return check_launch("rope_pos_kernel");
+}
+
+extern "C" int dalm_b200_attention_decode(const void* qkv, long long ldq, int q_col, int k_col, int v_col, void* cache_k,
+                                          void* cache_v, long long cache_sb, long long cache_st, const int64_t* mask,
+                                          long long ldm, void* out, long long ldo, int B, int Hq, int Hkv, int D, int cur,
+                                          int T, float scale, void* stream) {
+  DALM_REQUIRE(B > 0 && Hq > 0 && Hkv > 0 && (Hq % Hkv) == 0, "attention_decode: bad heads B=%d Hq=%d Hkv=%d", B, Hq, Hkv);
+  DALM_REQUIRE(D == 32 || D == 64 || D == 128, "attention_decode: head_dim %d unsupported (32/64/128)", D);
+  DALM_REQUIRE(cur >= 0 && cur < T && T <= 8192, "attention_decode: column %d outside the cache of %d tokens (max 8192)", cur, T);
+  DALM_REQUIRE((ldq % 8) == 0 && (q_col % 8) == 0 && (k_col % 8) == 0 && (v_col % 8) == 0 && (cache_st % 8) == 0 &&
+                   (cache_sb % 8) == 0, "attention_decode: rows must be 16-byte aligned");
+  DALM_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)cache_k & 15) == 0 && ((uintptr_t)cache_v & 15) == 0,
+               "attention_decode: pointers must be 16-byte aligned");
+  DALM_REQUIRE(mask != nullptr && cache_st >= (long long)Hkv * D && cache_sb >= cache_st * T, "attention_decode: cache layout");
+  const size_t smem = (size_t)(D + ((cur + 1 + 3) & ~3) + 32 + 128) * sizeof(float);
+  dim3 grid(Hq, B);
+#define DALM_DECODE(DD)                                                                                                  \
+  attn_decode_kernel<DD><<<grid, 128, smem, ST(stream)>>>((const __nv_bfloat16*)qkv, ldq, q_col, k_col, v_col,           \
+                                                          (__nv_bfloat16*)cache_k, (__nv_bfloat16*)cache_v, cache_sb,    \
+                                                          cache_st, mask, ldm, (__nv_bfloat16*)out, ldo, Hq, Hkv, cur, scale)
+  if (D == 128) DALM_DECODE(128); else if (D == 64) DALM_DECODE(64); else DALM_DECODE(32);
+#undef DALM_DECODE
+  count_launch();
+  return check_launch("attn_decode_kernel");
+}
+
+extern "C" int dalm_b200_greedy_step(const void* logits, long long ld, int B, int V, const int64_t* eos_ids, int n_eos,
+                                     long long pad_id, int* unfinished, int64_t* tokens, long long ldt, int64_t* mask,
+                                     long long ldm, int col, int64_t* next_ids, int64_t* pos, int* alive_slot, void* stream) {
+  DALM_REQUIRE(B > 0 && V > 0 && col >= 0 && col < ldt && col < ldm, "greedy_step: bad shape B=%d V=%d col=%d", B, V, col);
+  DALM_REQUIRE(n_eos >= 0 && (n_eos == 0 || eos_ids != nullptr), "greedy_step: eos list");
+  DALM_REQUIRE(unfinished && tokens && mask && next_ids && pos && alive_slot, "greedy_step: null state pointer");
+  greedy_step_kernel<<<B, 256, 0, ST(stream)>>>((const __nv_bfloat16*)logits, ld, V, eos_ids, n_eos, pad_id, unfinished, tokens,
+                                                ldt, mask, ldm, col, next_ids, pos, alive_slot);
+  count_launch();
+  return check_launch("greedy_step_kernel");
+}

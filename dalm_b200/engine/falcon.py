@@ -165,11 +165,17 @@ class FalconDecoder(torch.nn.Module):
         return self._rope_cache[L]
 
     # ---- one layer ------------------------------------------------------------------------------------------------
-    def _layer_fwd(self, W, x, mask, B, L, cos_t, sin_t, keep: bool):
-        """x fp32 [M,H] -> x_out fp32; with keep=True also everything the layer's backward needs"""
+    def _layer_fwd(self, W, x, mask, B, L, cos_t, sin_t, keep: bool, pos=None, kv_sink=None):
+        """x fp32 [M,H] -> x_out fp32; with keep=True also everything the layer's backward needs. pos / kv_sink: `generate`'s
+        prefill (explicit position ids into the cos / sin tables; callback receiving the rotated qkv buffer)"""
         _, h, mean, rstd = ops.layernorm_fwd(x, W["ln_g"], W["ln_b"], self.eps, want_f32=False)   # one LN feeds both branches
         qkv = ops.gemm(h, W["Wqkv"])                                                  # [M, (nh+2)*hd]
-        ops.rope_(qkv, 0, self.nh + 1, self.hd, cos_t, sin_t, L)                      # q heads then the single k head
+        if pos is None:
+            ops.rope_(qkv, 0, self.nh + 1, self.hd, cos_t, sin_t, L)                  # q heads then the single k head
+        else:
+            ops.rope_pos_(qkv, 0, self.nh + 1, self.hd, cos_t, sin_t, pos)
+        if kv_sink is not None:
+            kv_sink(qkv)
         att, lse = ops.attention_fwd(qkv[:, :self.Nq], qkv[:, self.Nq:self.Nq + self.hd], qkv[:, self.Nq + self.hd:],
                                      mask, B, L, self.nh, 1, self.hd, causal=True)
         t = ops.gemm(att, W["Wd"], out_dtype=f32, resid=x)                            # x + attention branch
@@ -231,6 +237,42 @@ class FalconDecoder(torch.nn.Module):
             ctx.B, ctx.L, ctx.mask, ctx.ids, ctx.xs, ctx.x_final, ctx.hf, ctx.mean_f, ctx.rstd_f = \
                 B, L, mask, ids.contiguous(), xs, x, hf, mean_f, rstd_f
         return logits.view(B, L, self.Vp)[:, :, :self.V], ctx
+
+    # ---- greedy decoding with a KV cache (evaluation: reference dalm/eval/eval_rag.py:126-140) ----------------------
+    def kv_columns(self):
+        """(first K column, first V column, width) of the rotated key / value head inside a layer's qkv buffer"""
+        return self.Nq, self.Nq + self.hd, self.hd
+
+    def _prefill_last(self, ids, mask, pos, tables, sink) -> torch.Tensor:
+        B, L0 = ids.shape
+        cos_t, sin_t = tables
+        mask = mask.contiguous()
+        x = ops.embed_gather(ids, self.embed)
+        for li, W in enumerate(self.layers):
+            x, _ = self._layer_fwd(W, x, mask, B, L0, cos_t, sin_t, keep=False, pos=pos, kv_sink=lambda qkv, li=li: sink(li, qkv))
+        x_last = x.view(B, L0, self.H)[:, -1].contiguous()                            # only the last column is scored
+        _, hf, _, _ = ops.layernorm_fwd(x_last, self.lnf_g, self.lnf_b, self.eps, want_f32=False)
+        return hf
+
+    def _decode_step(self, ids, pos, caches, kmask, cur: int, tables) -> torch.Tensor:
+        """one token per sequence: ids / pos int64 [B] -> logits bf16 [B, Vp]; appends K / V at cache column `cur`"""
+        cos_t, sin_t = tables
+        x = ops.embed_gather(ids, self.embed)
+        for li, W in enumerate(self.layers):
+            _, h, _, _ = ops.layernorm_fwd(x, W["ln_g"], W["ln_b"], self.eps, want_f32=False)
+            qkv = ops.gemm(h, W["Wqkv"])
+            ops.rope_pos_(qkv, 0, self.nh + 1, self.hd, cos_t, sin_t, pos)
+            att = ops.attention_decode(qkv, 0, self.Nq, self.Nq + self.hd, caches[li][0], caches[li][1], kmask, cur,
+                                       self.nh, 1, self.hd)
+            t = ops.gemm(att, W["Wd"], out_dtype=f32, resid=x)
+            x = ops.gemm(ops.gemm(h, W["W1"], act=1), W["W2"], out_dtype=f32, resid=t)
+        _, hf, _, _ = ops.layernorm_fwd(x, self.lnf_g, self.lnf_b, self.eps, want_f32=False)
+        return ops.gemm(hf, self.lm_head)
+
+    def generate(self, input_ids: Optional[torch.Tensor] = None, attention_mask: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:
+        """HF `generate` for the call the reference makes (greedy search); see engine/decoding.py"""
+        from .decoding import greedy_generate
+        return greedy_generate(self, input_ids, attention_mask, **kw)
 
     def backward_logits(self, ctx, dlogits: torch.Tensor) -> None:
         """dlogits bf16 [B,L,V] -> gradients of every parameter (full mode); nothing to do for a frozen decoder"""

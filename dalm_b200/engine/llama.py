@@ -300,10 +300,13 @@ class LlamaDecoder(torch.nn.Module):
                 self.full.g("lm_head").zero_()                 # the head is not on this path: its fresh gradient is zero
         self._backward_body(ctx, ops.cast_f32_bf16(d_hidden.reshape(ctx.B * ctx.L, self.H).contiguous()))
 
-    def _forward_body(self, ids: torch.Tensor, mask: torch.Tensor, save: bool = True):
+    def _forward_body(self, ids: torch.Tensor, mask: torch.Tensor, save: bool = True, pos: Optional[torch.Tensor] = None,
+                      rope_tables=None, kv_sink=None):
+        """pos / rope_tables / kv_sink serve `generate`'s prefill: explicit position ids (int64 [B*L]) into cos / sin tables
+        [T, hd/2], and a callback (layer, qkv) that copies the rotated K / V columns into the KV cache"""
         B, L = ids.shape
         M, H, F, Ra = B * L, self.H, self.F, self.Ra
-        cos_t, sin_t = self._rope(L)
+        cos_t, sin_t = self._rope(L) if rope_tables is None else rope_tables
         ctx = _Ctx()
         ctx.B, ctx.L, ctx.mask, ctx.layers = B, L, mask.contiguous(), []
         ctx.ids = ids.contiguous()
@@ -319,7 +322,12 @@ class LlamaDecoder(torch.nn.Module):
                 ops.skinny_gemm(a.h1_aug[:, :H], W["A_stack"], a.h1_aug[:, H:], K=H, R=Ra,   # u = dropout(h1) A^T [M,2r]
                                 dropx=self._drop(ctx.training, ctx.call, li))
             a.qkv = ops.gemm(a.h1_aug, W["Wqkv_aug"])                            # [M, Nq+2Nkv]
-            ops.rope_(a.qkv, 0, self.nh + self.nkv, self.hd, cos_t, sin_t, L)    # q heads then k heads are adjacent
+            if pos is None:
+                ops.rope_(a.qkv, 0, self.nh + self.nkv, self.hd, cos_t, sin_t, L)    # q heads then k heads are adjacent
+            else:
+                ops.rope_pos_(a.qkv, 0, self.nh + self.nkv, self.hd, cos_t, sin_t, pos)
+            if kv_sink is not None:
+                kv_sink(li, a.qkv)
             attn_fwd = ops.attention_tc_fwd if self.hd == 128 else ops.attention_fwd     # tcgen05/TMEM path for head_dim 128
             a.att, a.lse = attn_fwd(a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + self.Nkv],
                                     a.qkv[:, self.Nq + self.Nkv:], ctx.mask, B, L, self.nh, self.nkv, self.hd, causal=True)
@@ -333,6 +341,47 @@ class LlamaDecoder(torch.nn.Module):
         ctx.x_final = x
         ctx.hf, ctx.rstdf = ops.rmsnorm_fwd(x, self.norm_g, self.eps)
         return ctx
+
+    # ------------------------------------------------------------------------------------------------------------
+    # greedy decoding with a KV cache (evaluation: reference dalm/eval/eval_rag.py:126-140 calls HF `model.generate`)
+    # ------------------------------------------------------------------------------------------------------------
+    def _decode_step(self, ids: torch.Tensor, pos: torch.Tensor, caches, kmask: torch.Tensor, cur: int, tables) -> torch.Tensor:
+        """one token per sequence: ids / pos int64 [B] (device) -> logits bf16 [B, Vp]; appends K / V at cache column `cur`"""
+        B = ids.shape[0]
+        H, F, Ra = self.H, self.F, self.Ra
+        cos_t, sin_t = tables
+        x = ops.embed_gather(ids, self.embed)                                    # fp32 residual stream [B,H]
+        for li, W in enumerate(self.layers):
+            h1_aug = _aug_buf(B, H, Ra, self.dev)
+            ops.rmsnorm_fwd(x, W["g1"], self.eps, h=h1_aug[:, :H])
+            if Ra:
+                ops.skinny_gemm(h1_aug[:, :H], W["A_stack"], h1_aug[:, H:], K=H, R=Ra)
+            qkv = ops.gemm(h1_aug, W["Wqkv_aug"])                                # [B, Nq+2Nkv]
+            ops.rope_pos_(qkv, 0, self.nh + self.nkv, self.hd, cos_t, sin_t, pos)
+            att = ops.attention_decode(qkv, 0, self.Nq, self.Nq + self.Nkv, caches[li][0], caches[li][1], kmask, cur,
+                                       self.nh, self.nkv, self.hd)
+            x_mid = ops.gemm(att, W["Wo"], out_dtype=f32, resid=x)
+            h2, _ = ops.rmsnorm_fwd(x_mid, W["g2"], self.eps)
+            act = ops.swiglu_fwd(ops.gemm(h2, W["Wgu"]), F)
+            x = ops.gemm(act, W["Wd"], out_dtype=f32, resid=x_mid)
+        hf, _ = ops.rmsnorm_fwd(x, self.norm_g, self.eps)
+        return ops.gemm(hf, self.lm_head)
+
+    def _prefill_last(self, ids, mask, pos, tables, sink) -> torch.Tensor:
+        """prompt pass of `generate`: rotated K / V of every layer go to `sink`; returns the last column's final hidden
+        state (bf16 [B,H]) — only that column is scored"""
+        B, L0 = ids.shape
+        ctx = self._forward_body(ids, mask, save=False, pos=pos, rope_tables=tables, kv_sink=sink)
+        return ctx.hf.view(B, L0, self.H)[:, -1].contiguous()
+
+    def kv_columns(self):
+        """(first K column, first V column, width) of the rotated keys / values inside a layer's qkv buffer"""
+        return self.Nq, self.Nq + self.Nkv, self.Nkv
+
+    def generate(self, input_ids: Optional[torch.Tensor] = None, attention_mask: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:
+        """HF `generate` for the call the reference makes (greedy search); see engine/decoding.py"""
+        from .decoding import greedy_generate
+        return greedy_generate(self, input_ids, attention_mask, **kw)
 
     # ------------------------------------------------------------------------------------------------------------
     def backward_logits(self, ctx: _Ctx, dlogits: torch.Tensor) -> None:

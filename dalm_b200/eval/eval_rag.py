@@ -1,11 +1,13 @@
-"""`dalm eval-rag` — reference dalm/eval/eval_rag.py:167-290. The retriever half (passage sweep, top-k, recall / precision /
-hit-rate through `rag_model.retrieval_forward`) is built; the generator half (`model.generate` + exact match, :118-165,
-:258-283) needs an autoregressive KV-cache decode path, which is a different workload from the training step this build
-covers: `evaluate_generator=True` raises NotImplementedError instead of silently skipping it."""
+"""`dalm eval-rag` — reference dalm/eval/eval_rag.py:167-290. Retriever half: passage sweep, exact top-k, recall / precision /
+hit-rate through `rag_model.retrieval_forward`. Generator half (`run_generator_on_prompts` :126-140, `eval_generator_on_batch`
+:143-164, exact match :268-283): prompts `#query# q #passage# p #answer# ` are tokenised exactly as the reference does and
+decoded by `generator_model.generate` — greedy search with a KV cache over the C-ABI kernels (engine/decoding.py), HF
+`generate` semantics for the reference's call. A checkpoint whose generation_config asks for sampling (Llama-2's does) is
+decoded greedily here; that is stated in the log line, not hidden."""
 from __future__ import annotations
 
 import logging
-from typing import Any, Final, Literal, Optional
+from typing import Any, Final, List, Literal, Optional
 
 import torch
 from torch.utils.data import DataLoader
@@ -17,6 +19,39 @@ from .utils import (calc_eval_results, construct_search_index, evaluate_retrieve
                     mixed_collate_fn, preprocess_dataset, print_eval_results)
 
 logger = logging.getLogger(__name__)
+
+
+def run_generator_on_prompts(model: Any, tokenizer: Any, prompts: List[str], max_length: int = 256) -> List[str]:
+    """Runs the generator model over the prompts (query + passage) — reference eval_rag.py:126-140. `model` is the
+    wrapper's `generator_model` (LlamaDecoder / FalconDecoder); its `generate` takes the tokenizer's tensors as they are
+    (host int64) and returns the padded prompt + continuation like HF does."""
+    inputs = tokenizer(prompts, return_tensors="pt", padding=True, truncation=True, max_length=max_length)
+    outputs = model.generate(**inputs, max_length=max_length, early_stopping=True)
+    return tokenizer.batch_decode(outputs.cpu(), skip_special_tokens=True)
+
+
+def eval_generator_on_batch(model: Any, tokenizer: Any, queries: List[str], passages: List[str], query_batch_size: int,
+                            queries_for_gen_eval: List[str], max_length: int) -> tuple:
+    """reference eval_rag.py:143-164: accumulate prompts, flush every `query_batch_size`"""
+    generated_answers_for_eval: List[str] = []
+    for _query, search_result_passage in zip(queries, passages, strict=True):
+        queries_for_gen_eval.append(f"#query# {_query} #passage# {search_result_passage} #answer# ")     # no answer in the prompt
+        if len(queries_for_gen_eval) >= query_batch_size:
+            generated_answers_for_eval.extend(run_generator_on_prompts(model, tokenizer, queries_for_gen_eval, max_length=max_length))
+            queries_for_gen_eval.clear()
+    return queries_for_gen_eval, generated_answers_for_eval
+
+
+def exact_match_hits(generated_answers: List[str], answers: List[str]) -> int:
+    """reference eval_rag.py:268-277: the text after the first `#answer#`, stripped, must equal the gold answer"""
+    hits = 0
+    for generated_answer, answer in zip(generated_answers, answers, strict=True):
+        parts = generated_answer.split("#answer#")
+        if len(parts) < 2:
+            continue
+        if parts[1].strip() == answer:
+            hits += 1
+    return hits
 
 
 def evaluate_rag(
@@ -38,10 +73,6 @@ def evaluate_rag(
     evaluate_generator: bool = True,
     retriever_is_autoregressive: bool = False,
 ) -> EvalResults:
-    if evaluate_generator:
-        raise NotImplementedError("eval-rag's generator evaluation (generate + exact match, reference eval_rag.py:118-165) needs "
-                                  "an autoregressive decode path that dalm_b200 does not build; pass evaluate_generator=False "
-                                  "(--no-evaluate-generator) for the retriever metrics")
     if not str(device).startswith("cuda"):
         raise RuntimeError("dalm_b200 evaluates on a CUDA (sm_100a) device only: there is no CPU path")
     test_dataset = load_dataset(dataset_or_path)
@@ -58,13 +89,35 @@ def evaluate_rag(
     id_to_passage = {i: p[passage_column_name] for i, p in enumerate(unique_passage_dataset)}
     index = construct_search_index(embed_dim, len(passage_embeddings), passage_embeddings)
     batch_precision, batch_recall, total_hit = [], [], 0
+    queries_for_gen_eval: List[str] = []
+    generated_answers_for_eval: List[str] = []
+    model, tokenizer = rag_model.generator_model, rag_model.generator_tokenizer
+    if evaluate_generator:
+        tokenizer.pad_token = tokenizer.eos_token                                 # reference :240
+        logger.info("generator evaluation decodes greedily (do_sample=False); a sampling generation_config is not honoured")
     loader = DataLoader(processed, batch_size=test_batch_size, shuffle=True, collate_fn=mixed_collate_fn)
     for batch in loader:
-        p_, r_, h_, _ = evaluate_retriever_on_batch(batch, passage_column_name, rag_model.retrieval_forward, index,
-                                                    selected_torch_dtype, dev, top_k, id_to_passage)
+        p_, r_, h_, top_passages = evaluate_retriever_on_batch(batch, passage_column_name, rag_model.retrieval_forward, index,
+                                                               selected_torch_dtype, dev, top_k, id_to_passage)
         batch_precision.extend(p_)
         batch_recall.extend(r_)
         total_hit += h_
+        if not evaluate_generator:
+            continue
+        queries_for_gen_eval, batch_answers = eval_generator_on_batch(model, tokenizer, batch[query_column_name], top_passages,
+                                                                      query_batch_size, queries_for_gen_eval, max_length)
+        generated_answers_for_eval.extend(batch_answers)
     results = calc_eval_results(len(processed), batch_precision, batch_recall, total_hit)
+    if not evaluate_generator:
+        print_eval_results(results)
+        return results
+    if len(queries_for_gen_eval) > 0:                                             # leftover prompts (reference :258-261)
+        generated_answers_for_eval.extend(run_generator_on_prompts(model, tokenizer, queries_for_gen_eval, max_length=max_length))
+        queries_for_gen_eval.clear()
+    # like the reference (:263-266) the gold answers are read in DATASET order while the generated ones come in the shuffled
+    # loader's order; kept as is — it is the number the reference prints
+    total_em_hit = exact_match_hits(generated_answers_for_eval, list(processed[answer_column_name]))
     print_eval_results(results)
+    print("Generator evaluation:")
+    print("Exact match:", total_em_hit / len(processed))
     return results

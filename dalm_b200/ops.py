@@ -544,3 +544,50 @@ def nf4_roundtrip_(w: torch.Tensor, want_codes: bool = False):
     absmax = torch.empty((n + 63) // 64, dtype=f32, device=w.device) if want_codes else None
     _lib.call("dalm_b200_nf4_roundtrip", _p(w), n, _p(codes), _p(absmax), _stream())
     return (w, codes, absmax) if want_codes else w
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# greedy decoding (evaluation: reference dalm/eval/eval_rag.py:126-140)
+# ----------------------------------------------------------------------------------------------------------------
+def rope_pos_(buf, col0: int, nheads: int, D: int, cos_t, sin_t, pos):
+    """in-place RoPE of `nheads` heads at explicit position ids pos[M] (int64); cos_t / sin_t fp32 [T, D/2]"""
+    _chk(buf, bf16, "rope_pos buf"); _chk(pos, i64, "rope_pos pos"); _chk(cos_t, f32, "rope_pos cos"); _chk(sin_t, f32, "rope_pos sin")
+    M = buf.shape[0]
+    if pos.numel() != M or not pos.is_contiguous():
+        raise _lib.DalmB200Error(f"rope_pos: need one contiguous position id per row ({pos.numel()} for {M} rows)")
+    _lib.call("dalm_b200_rope_pos", _p(buf), _ld(buf), col0, nheads, D, _p(cos_t), _p(sin_t), _p(pos), M, cos_t.shape[0], _stream())
+    return buf
+
+
+def attention_decode(qkv, q_col: int, k_col: int, v_col: int, cache_k, cache_v, mask, cur: int, Hq: int, Hkv: int, D: int,
+                     out=None, scale: Optional[float] = None):
+    """qkv bf16 [B, >=v_col+Hkv*D] (current token of every sequence); cache_k / cache_v bf16 [B, T, Hkv*D]; mask int64 [B, T].
+    Appends the token's K / V at column `cur` and returns the attention output bf16 [B, Hq*D]."""
+    _chk(qkv, bf16, "attention_decode qkv"); _chk(cache_k, bf16, "cache_k"); _chk(cache_v, bf16, "cache_v"); _chk(mask, i64, "mask")
+    B, T = cache_k.shape[0], cache_k.shape[1]
+    if cache_k.shape != cache_v.shape or cache_k.stride() != cache_v.stride() or cache_k.dim() != 3 or mask.shape[0] != B or mask.shape[1] < T:
+        raise _lib.DalmB200Error("attention_decode: cache_k / cache_v / mask shapes disagree")
+    if qkv.shape[0] != B:
+        raise _lib.DalmB200Error("attention_decode: one qkv row per cached sequence")
+    if out is None:
+        out = torch.empty(B, Hq * D, dtype=bf16, device=qkv.device)
+    scale = 1.0 / math.sqrt(D) if scale is None else scale
+    _lib.call("dalm_b200_attention_decode", _p(qkv), _ld(qkv), q_col, k_col, v_col, _p(cache_k), _p(cache_v),
+              cache_k.stride(0), cache_k.stride(1), _p(mask), mask.stride(0), _p(out), _ld(out), B, Hq, Hkv, D, int(cur), T,
+              float(scale), _stream())
+    return out
+
+
+def greedy_step_(logits, V: int, eos_ids, pad_id: int, unfinished, tokens, mask, col: int, next_ids, pos, alive_slot) -> None:
+    """one greedy-search step on device state (see include/dalm_b200.h): logits bf16 [B, >=V]; eos_ids int64 [n] or None;
+    unfinished int32 [B]; tokens / mask int64 [B, T]; next_ids / pos int64 [B]; alive_slot int32 [1] (zeroed by the caller)"""
+    _chk(logits, bf16, "greedy logits"); _chk(tokens, i64, "tokens"); _chk(mask, i64, "mask")
+    _chk(next_ids, i64, "next_ids"); _chk(pos, i64, "pos")
+    if unfinished.dtype != torch.int32 or alive_slot.dtype != torch.int32:
+        raise _lib.DalmB200Error("greedy_step: unfinished / alive_slot must be int32")
+    if eos_ids is not None:
+        _chk(eos_ids, i64, "eos_ids")
+    B = logits.shape[0]
+    _lib.call("dalm_b200_greedy_step", _p(logits), _ld(logits), B, int(V), _p(eos_ids), 0 if eos_ids is None else eos_ids.numel(),
+              int(pad_id), _p(unfinished), _p(tokens), tokens.stride(0), _p(mask), mask.stride(0), int(col), _p(next_ids),
+              _p(pos), _p(alive_slot), _stream())

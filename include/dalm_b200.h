@@ -186,6 +186,25 @@ int dalm_b200_topk_ip(const float* Q, const float* P, long long ldp, int nq, int
  * codes (uint8 [n]) / absmax (fp32 [ceil(n/64)]) are optional outputs. */
 int dalm_b200_nf4_roundtrip(float* w, long long n, void* codes, float* absmax, void* stream);
 
+/* ---- evaluation: greedy autoregressive decoding of the generator ----
+ * replaces `model.generate(**inputs, max_length=max_length, early_stopping=True)` of run_generator_on_prompts
+ * (dalm/eval/eval_rag.py:126-140; HF GenerationMixin greedy search with a KV cache).
+ * rope_pos: RoPE at explicit position ids pos[M] (HF generate: cumsum(attention_mask) - 1), tables cos/sin [T, D/2].
+ * attention_decode: one query token per sequence (row b of qkv: q | k | v at the given columns, already rotated) against
+ *   the bf16 KV cache [B][T][Hkv*D] (batch stride cache_sb, token stride cache_st, in elements); keys t < cur are visible
+ *   iff mask[b*ldm + t] != 0, the token itself (column cur) always; its K / V rows are appended to the cache at column cur.
+ * greedy_step: next token = argmax(logits[b, 0..V)) for unfinished rows, pad_id for finished ones; writes tokens[b, col],
+ *   mask[b, col] = 1, next_ids[b], pos[b] += 1; a row finishes when it emits one of eos_ids; *alive_slot += #unfinished
+ *   rows after this step (caller zeroes it). */
+int dalm_b200_rope_pos(void* buf, long long ld, int col0, int nheads, int D, const float* cos_t, const float* sin_t,
+                       const int64_t* pos, int M, int T, void* stream);
+int dalm_b200_attention_decode(const void* qkv, long long ldq, int q_col, int k_col, int v_col, void* cache_k, void* cache_v,
+                               long long cache_sb, long long cache_st, const int64_t* mask, long long ldm, void* out,
+                               long long ldo, int B, int Hq, int Hkv, int D, int cur, int T, float scale, void* stream);
+int dalm_b200_greedy_step(const void* logits, long long ld, int B, int V, const int64_t* eos_ids, int n_eos,
+                          long long pad_id, int* unfinished, int64_t* tokens, long long ldt, int64_t* mask, long long ldm,
+                          int col, int64_t* next_ids, int64_t* pos, int* alive_slot, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -121,4 +121,44 @@ def test_evaluate_retriever_end_to_end_with_trained_adapters(cuda_dev, tmp_path)
     with torch.no_grad():
         assert torch.equal(m1(ids, mask), m2(ids, mask))
     with pytest.raises(NotImplementedError):
-        evaluate_rag(csv, rdir, rdir, None, None, "Abstract", "Question", "Answer", 64, 32)      # generator evaluation: not built
+        evaluate_rag(csv, rdir, rdir, None, None, "Abstract", "Question", "Answer", 64, 32)      # a BERT encoder is no generator
+
+
+def test_evaluate_rag_with_generator(cuda_dev, tmp_path, capsys):
+    """`dalm eval-rag` with generator evaluation on (the reference's default): retrieve, build `#query# .. #passage# .. #answer# `
+    prompts from the top passage, decode greedily through the KV-cache kernels, score exact match (reference
+    eval_rag.py:126-164,258-283). Token-level parity of the decoding is in tests/test_generate_gpu.py; here the plumbing:
+    prompt text survives, the continuation is appended after it, batches of `query_batch_size` plus the leftover are all
+    generated, and a prompt as long as max_length is rejected exactly like HF rejects it."""
+    import csv as _csv
+
+    from dalm_b200 import synthetic
+    from dalm_b200.eval.eval_rag import evaluate_rag, run_generator_on_prompts
+    from dalm_b200.models.rag_e2e_base_model import AutoModelForRagE2E, inference_only
+    words = synthetic.word_list()
+    path = str(tmp_path / "short.csv")
+    with open(path, "w", newline="") as f:
+        w = _csv.DictWriter(f, fieldnames=["Abstract", "Question", "Answer"])
+        w.writeheader()
+        for i in range(11):                                                        # 11 rows: batches of 4 + a leftover
+            w.writerow({"Abstract": " ".join(words[20 + 6 * i:26 + 6 * i]), "Question": " ".join(words[200 + 4 * i:204 + 4 * i]),
+                        "Answer": " ".join(words[400 + i:402 + i])})
+    rdir = synthetic.write_model_dir(str(tmp_path / "bge-tiny"), "bert", "bge-tiny", vocab_size=1200)
+    gdir = synthetic.write_model_dir(str(tmp_path / "llama-tiny"), "llama", "llama-tiny", vocab_size=1200)
+    res = evaluate_rag(path, rdir, gdir, None, None, "Abstract", "Question", "Answer", embed_dim=64, max_length=96,
+                       test_batch_size=4, query_batch_size=4, top_k=3, evaluate_generator=True)
+    out = capsys.readouterr().out
+    assert res.total_examples == 11 and 0.0 <= res.recall <= 1.0
+    assert "Generator evaluation:" in out and "Exact match: 0.0" in out            # a random-init generator answers nothing
+    with inference_only():
+        rag = AutoModelForRagE2E(rdir, gdir)
+    tok = rag.generator_tokenizer
+    tok.pad_token = tok.eos_token
+    prompts = [f"#query# {' '.join(words[i:i + 4])} #passage# {' '.join(words[30 + i:36 + i])} #answer# " for i in range(3)]
+    texts = run_generator_on_prompts(rag.generator_model, tok, prompts, max_length=96)
+    assert len(texts) == 3
+    for p, t in zip(prompts, texts):
+        shown = tok.decode(tok(p)["input_ids"], skip_special_tokens=True)          # the prompt as the tokenizer round-trips it
+        assert t.startswith(shown.strip()) and len(t) > len(shown.strip())         # prompt kept, something generated after it
+    with pytest.raises(ValueError):
+        run_generator_on_prompts(rag.generator_model, tok, prompts, max_length=8)   # truncated prompt fills max_length (HF raises too)

@@ -99,3 +99,14 @@ def test_nf4_oracle_properties():
     assert (np.diff(c.astype(int)) >= 0).all() and c[0] == 0 and c[-1] == 15
     z, cz, az = nf4.roundtrip(np.zeros(70, np.float32))
     assert (z == 0).all() and (cz == 7).all() and (az == 0).all()
+
+
+def test_exact_match_rule():
+    """reference eval_rag.py:268-277: text after the FIRST `#answer#`, stripped, equals the gold answer; no marker -> skipped"""
+    from dalm_b200.eval.eval_rag import exact_match_hits
+    gen = ["#query# q #passage# p #answer# blue whale", "#query# q #passage# p #answer#  blue whale \n", "no marker here",
+           "#query# q #answer# a #answer# a", "#query# q #passage# p #answer# blue"]
+    gold = ["blue whale", "blue whale", "blue whale", "a", "blue whale"]
+    assert exact_match_hits(gen, gold) == 3
+    with pytest.raises(ValueError):
+        exact_match_hits(gen, gold[:-1])                                          # zip(strict=True) like the reference
