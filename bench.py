@@ -161,6 +161,32 @@ def cpu_reference_samples_per_s(batch, steps: int = 1, rows: int = 6):
     return rows / full, cores, desc
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of four consecutive
+    generator-forward GEMM launches inside this bench (profiles/r01_gemm_v3_ncu_full_raw.csv: gate|up, down, QKV+LoRA, o_proj
+    at cfg-3 shapes): mean of dram__bytes_read.sum + dram__bytes_write.sum over the captured launches, next to the
+    algorithmic bytes (A + B + output, + the fp32 residual where the epilogue reads one) of the same launches.
+    Returns (bytes_per_launch or None, detail dict)."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01_gemm_v3_ncu_full_raw.csv")
+    shapes = [(4608, 22016, 4096, 2, 0), (4608, 4096, 11008, 4, 4), (4608, 12288, 4112, 2, 0), (4608, 4096, 4096, 4, 4)]   # M,N,K,out B,resid B
+    algo = [2 * (m * k + n * k) + m * n * (ob + rb) for m, n, k, ob, rb in shapes]
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr = rows[0]
+        rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        ur, uw = unit[rows[1][rd]], unit[rows[1][wr]]
+        per = [float(r[rd]) * ur + float(r[wr]) * uw for r in rows[2:] if len(r) > max(rd, wr)]
+        if not per:
+            return None, {"source": "no launches in " + os.path.relpath(path, ROOT)}
+        return sum(per) / len(per), {"source": os.path.relpath(path, ROOT), "launches": len(per), "dram_bytes_per_launch": per,
+                                     "algorithmic_bytes_per_launch": algo[:len(per)],
+                                     "note": "down-proj (2nd) re-reads A on each of its 4 tile waves: 652 MB vs 342 MB"}
+    except Exception as e:
+        return None, {"source": f"unreadable ({type(e).__name__})"}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -320,6 +346,7 @@ def main():
     samples = BS * world * args.steps
     value = samples / (total_ms * 1e-3)
     gemm_tf = gsum["total_flops"] / max(gsum["total_ms"] * 1e-3, 1e-9) / 1e12
+    traffic, traffic_detail = ncu_traffic()
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": value / 7.94,
@@ -337,7 +364,8 @@ def main():
         "gpu_launches": int(launches),
         "step_tflops": STEP_TFLOP_PEFT * args.steps * world / (total_ms * 1e-3) ,
         "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf,
-                     "traffic": None, "kernel": "gemm_bf16_tn_kernel (tcgen05)", "launches_timed": gsum["launches"],
+                     "traffic": traffic, "traffic_detail": traffic_detail,
+                     "kernel": "gemm_bf16_tn_kernel (tcgen05)", "launches_timed": gsum["launches"],
                      "share_of_step": gsum["total_ms"] / eager_ms, "peak_source": peak_src,
                      "note": "achieved = sum of 2MNK over all GEMM launches / sum of their CUDA-event durations in the timed region"},
         "clocks": sampler.summary() if sampler else None,

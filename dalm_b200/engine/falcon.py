@@ -254,8 +254,8 @@ class FalconDecoder(torch.nn.Module):
         _, hf, _, _ = ops.layernorm_fwd(x_last, self.lnf_g, self.lnf_b, self.eps, want_f32=False)
         return hf
 
-    def _decode_step(self, ids, pos, caches, kmask, cur: int, tables) -> torch.Tensor:
-        """one token per sequence: ids / pos int64 [B] -> logits bf16 [B, Vp]; appends K / V at cache column `cur`"""
+    def _decode_step(self, ids, pos, caches, kmask, cur, tables) -> torch.Tensor:
+        """one token per sequence: ids / pos int64 [B] -> logits bf16 [B, Vp]; appends K / V at cache column `cur` (int, or the int32 [B] device tensor of per-row columns: CUDA-graph mode)"""
         cos_t, sin_t = tables
         x = ops.embed_gather(ids, self.embed)
         for li, W in enumerate(self.layers):

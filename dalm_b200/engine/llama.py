@@ -345,8 +345,8 @@ class LlamaDecoder(torch.nn.Module):
     # ------------------------------------------------------------------------------------------------------------
     # greedy decoding with a KV cache (evaluation: reference dalm/eval/eval_rag.py:126-140 calls HF `model.generate`)
     # ------------------------------------------------------------------------------------------------------------
-    def _decode_step(self, ids: torch.Tensor, pos: torch.Tensor, caches, kmask: torch.Tensor, cur: int, tables) -> torch.Tensor:
-        """one token per sequence: ids / pos int64 [B] (device) -> logits bf16 [B, Vp]; appends K / V at cache column `cur`"""
+    def _decode_step(self, ids: torch.Tensor, pos: torch.Tensor, caches, kmask: torch.Tensor, cur, tables) -> torch.Tensor:
+        """one token per sequence: ids / pos int64 [B] (device) -> logits bf16 [B, Vp]; appends K / V at cache column `cur` (int, or the int32 [B] device tensor of per-row columns: CUDA-graph mode)"""
         B = ids.shape[0]
         H, F, Ra = self.H, self.F, self.Ra
         cos_t, sin_t = tables

@@ -559,10 +559,19 @@ def rope_pos_(buf, col0: int, nheads: int, D: int, cos_t, sin_t, pos):
     return buf
 
 
-def attention_decode(qkv, q_col: int, k_col: int, v_col: int, cache_k, cache_v, mask, cur: int, Hq: int, Hkv: int, D: int,
+def _cur_arg(cur, B: int, what: str):
+    """host column (int) or per-row device columns (int32 [B] tensor: CUDA-graph mode) -> (host int, device pointer)"""
+    if torch.is_tensor(cur):
+        if cur.dtype != torch.int32 or not cur.is_cuda or cur.numel() != B or not cur.is_contiguous():
+            raise _lib.DalmB200Error(f"{what}: device columns must be a contiguous int32 CUDA tensor with one entry per row")
+        return 0, _p(cur)
+    return int(cur), None
+
+
+def attention_decode(qkv, q_col: int, k_col: int, v_col: int, cache_k, cache_v, mask, cur, Hq: int, Hkv: int, D: int,
                      out=None, scale: Optional[float] = None):
     """qkv bf16 [B, >=v_col+Hkv*D] (current token of every sequence); cache_k / cache_v bf16 [B, T, Hkv*D]; mask int64 [B, T].
-    Appends the token's K / V at column `cur` and returns the attention output bf16 [B, Hq*D]."""
+    Appends the token's K / V at column `cur` (int, or int32 [B] device tensor) and returns the attention output bf16 [B, Hq*D]."""
     _chk(qkv, bf16, "attention_decode qkv"); _chk(cache_k, bf16, "cache_k"); _chk(cache_v, bf16, "cache_v"); _chk(mask, i64, "mask")
     B, T = cache_k.shape[0], cache_k.shape[1]
     if cache_k.shape != cache_v.shape or cache_k.stride() != cache_v.stride() or cache_k.dim() != 3 or mask.shape[0] != B or mask.shape[1] < T:
@@ -572,22 +581,27 @@ def attention_decode(qkv, q_col: int, k_col: int, v_col: int, cache_k, cache_v, 
     if out is None:
         out = torch.empty(B, Hq * D, dtype=bf16, device=qkv.device)
     scale = 1.0 / math.sqrt(D) if scale is None else scale
+    cur_host, cur_dev = _cur_arg(cur, B, "attention_decode")
     _lib.call("dalm_b200_attention_decode", _p(qkv), _ld(qkv), q_col, k_col, v_col, _p(cache_k), _p(cache_v),
-              cache_k.stride(0), cache_k.stride(1), _p(mask), mask.stride(0), _p(out), _ld(out), B, Hq, Hkv, D, int(cur), T,
-              float(scale), _stream())
+              cache_k.stride(0), cache_k.stride(1), _p(mask), mask.stride(0), _p(out), _ld(out), B, Hq, Hkv, D, cur_host, cur_dev,
+              T, float(scale), _stream())
     return out
 
 
-def greedy_step_(logits, V: int, eos_ids, pad_id: int, unfinished, tokens, mask, col: int, next_ids, pos, alive_slot) -> None:
+def greedy_step_(logits, V: int, eos_ids, pad_id: int, unfinished, tokens, mask, col, next_ids, pos, alive) -> None:
     """one greedy-search step on device state (see include/dalm_b200.h): logits bf16 [B, >=V]; eos_ids int64 [n] or None;
-    unfinished int32 [B]; tokens / mask int64 [B, T]; next_ids / pos int64 [B]; alive_slot int32 [1] (zeroed by the caller)"""
+    unfinished int32 [B]; tokens / mask int64 [B, T]; next_ids / pos int64 [B]; alive int32 [T] (zeroed by the caller).
+    col: the column to write (int), or the int32 [B] device tensor holding each row's CURRENT column (the kernel writes
+    column + 1 and advances it: CUDA-graph mode)."""
     _chk(logits, bf16, "greedy logits"); _chk(tokens, i64, "tokens"); _chk(mask, i64, "mask")
     _chk(next_ids, i64, "next_ids"); _chk(pos, i64, "pos")
-    if unfinished.dtype != torch.int32 or alive_slot.dtype != torch.int32:
-        raise _lib.DalmB200Error("greedy_step: unfinished / alive_slot must be int32")
+    T = tokens.shape[1]
+    if unfinished.dtype != torch.int32 or alive.dtype != torch.int32 or alive.numel() < T or mask.shape[1] < T:
+        raise _lib.DalmB200Error("greedy_step: unfinished / alive must be int32, alive and mask as long as the token buffer")
     if eos_ids is not None:
         _chk(eos_ids, i64, "eos_ids")
     B = logits.shape[0]
+    col_host, cur_dev = _cur_arg(col, B, "greedy_step")
     _lib.call("dalm_b200_greedy_step", _p(logits), _ld(logits), B, int(V), _p(eos_ids), 0 if eos_ids is None else eos_ids.numel(),
-              int(pad_id), _p(unfinished), _p(tokens), tokens.stride(0), _p(mask), mask.stride(0), int(col), _p(next_ids),
-              _p(pos), _p(alive_slot), _stream())
+              int(pad_id), _p(unfinished), _p(tokens), tokens.stride(0), _p(mask), mask.stride(0), col_host, cur_dev, T,
+              _p(next_ids), _p(pos), _p(alive), _stream())

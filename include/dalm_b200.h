@@ -194,16 +194,20 @@ int dalm_b200_nf4_roundtrip(float* w, long long n, void* codes, float* absmax, v
  *   the bf16 KV cache [B][T][Hkv*D] (batch stride cache_sb, token stride cache_st, in elements); keys t < cur are visible
  *   iff mask[b*ldm + t] != 0, the token itself (column cur) always; its K / V rows are appended to the cache at column cur.
  * greedy_step: next token = argmax(logits[b, 0..V)) for unfinished rows, pad_id for finished ones; writes tokens[b, col],
- *   mask[b, col] = 1, next_ids[b], pos[b] += 1; a row finishes when it emits one of eos_ids; *alive_slot += #unfinished
- *   rows after this step (caller zeroes it). */
+ *   mask[b, col] = 1, next_ids[b], pos[b] += 1; a row finishes when it emits one of eos_ids; alive[col] += #unfinished
+ *   rows after this step (alive: int32 [T], zeroed by the caller).
+ * Device-column mode (cur_dev != NULL, int32 [B]): attention_decode takes cur = cur_dev[b], greedy_step writes column
+ *   cur_dev[b] + 1 and advances cur_dev[b]; the host `cur` / `col` arguments are ignored, so the launch sequence of a
+ *   decode step has identical arguments for every token and can be captured once in a CUDA graph and replayed. */
 int dalm_b200_rope_pos(void* buf, long long ld, int col0, int nheads, int D, const float* cos_t, const float* sin_t,
                        const int64_t* pos, int M, int T, void* stream);
 int dalm_b200_attention_decode(const void* qkv, long long ldq, int q_col, int k_col, int v_col, void* cache_k, void* cache_v,
                                long long cache_sb, long long cache_st, const int64_t* mask, long long ldm, void* out,
-                               long long ldo, int B, int Hq, int Hkv, int D, int cur, int T, float scale, void* stream);
+                               long long ldo, int B, int Hq, int Hkv, int D, int cur, const int* cur_dev, int T, float scale,
+                               void* stream);
 int dalm_b200_greedy_step(const void* logits, long long ld, int B, int V, const int64_t* eos_ids, int n_eos,
                           long long pad_id, int* unfinished, int64_t* tokens, long long ldt, int64_t* mask, long long ldm,
-                          int col, int64_t* next_ids, int64_t* pos, int* alive_slot, void* stream);
+                          int col, int* cur_dev, int T, int64_t* next_ids, int64_t* pos, int* alive, void* stream);
 
 #ifdef __cplusplus
 }

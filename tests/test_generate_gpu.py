@@ -11,7 +11,9 @@ installed transformers' `generate` by tests/test_generate_host.py) on identical 
     token-for-token equality with an fp32 run is not a meaningful bar for a bf16 forward; a wrong position id, mask or cache
     slot gives margins of ~0.5);
   * integer bookkeeping (prompt copied through, pads after EOS, stop column, output length) is bit-exact against the
-    oracle re-run on the emitted tokens.
+    oracle re-run on the emitted tokens;
+  * the default launch mode (decode step captured once as a CUDA graph, replayed per token) emits exactly the tokens of
+    the eager launch sequence.
 """
 import math
 
@@ -87,6 +89,11 @@ def test_attention_decode(cuda_dev, D, Hq, Hkv, T, cur):
     ref = torch.einsum("bht,bthd->bhd", torch.softmax(s, -1), V).reshape(B, Nq)
     assert _rel(out.float(), ref) < 5e-3                        # bf16 output rounding
     assert (out.float() - ref).abs().max().item() < 2e-2
+    # device-column mode (what a CUDA-graph replay uses): same launch, the column comes from an int32 [B] device tensor
+    ck2, cv2 = ck0.clone(), cv0.clone()
+    out2 = ops.attention_decode(qkv, 0, Nq, Nq + Nkv, ck2, cv2, mask, torch.full((B,), cur, dtype=torch.int32, device=cuda_dev),
+                                Hq, Hkv, D)
+    assert torch.equal(out2, out) and torch.equal(ck2, ck) and torch.equal(cv2, cv)
 
 
 def test_greedy_step(cuda_dev):
@@ -108,7 +115,7 @@ def test_greedy_step(cuda_dev):
     pos = torch.arange(B, dtype=i64, device=cuda_dev) * 3
     alive = torch.zeros(T, dtype=torch.int32, device=cuda_dev)
     col = 7
-    ops.greedy_step_(logits, V, eos, 77, unfinished, tokens, mask, col, next_ids, pos, alive[col:col + 1])
+    ops.greedy_step_(logits, V, eos, 77, unfinished, tokens, mask, col, next_ids, pos, alive)
     want = torch.tensor([123, 999, 5, 77, 0, 333], device=cuda_dev)          # row 0: lowest index of the tie; row 3: pad
     assert torch.equal(tokens[:, col], want) and torch.equal(next_ids, want)
     assert (tokens[:, :col] == -1).all() and (tokens[:, col + 1:] == -1).all()
@@ -121,9 +128,15 @@ def test_greedy_step(cuda_dev):
     small[0, 17] = 9.0; small[1, 32] = 9.0; small[:, 33:] = 50.0
     unf2 = torch.ones(2, dtype=torch.int32, device=cuda_dev)
     t2, m2 = torch.zeros(2, 3, dtype=i64, device=cuda_dev), torch.zeros(2, 3, dtype=i64, device=cuda_dev)
-    n2, p2, a2 = torch.zeros(2, dtype=i64, device=cuda_dev), torch.zeros(2, dtype=i64, device=cuda_dev), torch.zeros(1, dtype=torch.int32, device=cuda_dev)
+    n2, p2, a2 = torch.zeros(2, dtype=i64, device=cuda_dev), torch.zeros(2, dtype=i64, device=cuda_dev), torch.zeros(3, dtype=torch.int32, device=cuda_dev)
     ops.greedy_step_(small, 33, None, 0, unf2, t2, m2, 1, n2, p2, a2)
-    assert n2.tolist() == [17, 32] and t2[:, 1].tolist() == [17, 32] and a2.item() == 2 and unf2.tolist() == [1, 1]
+    assert n2.tolist() == [17, 32] and t2[:, 1].tolist() == [17, 32] and a2.tolist() == [0, 2, 0] and unf2.tolist() == [1, 1]
+    # device-column mode: each row's own counter names the column (current + 1) and advances; past the end it is a no-op
+    cur = torch.tensor([1, 0], dtype=torch.int32, device=cuda_dev)
+    ops.greedy_step_(small, 33, None, 0, unf2, t2, m2, cur, n2, p2, a2)
+    assert cur.tolist() == [2, 1] and t2.tolist() == [[0, 17, 17], [0, 32, 0]] and a2.tolist() == [0, 3, 1] and p2.tolist() == [2, 2]
+    ops.greedy_step_(small, 33, None, 0, unf2, t2, m2, cur, n2, p2, a2)
+    assert cur.tolist() == [2, 2] and t2.tolist() == [[0, 17, 17], [0, 32, 32]] and a2.tolist() == [0, 3, 2] and p2.tolist() == [2, 3]
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -149,11 +162,22 @@ def _check_against_oracle(dec, ref, ids, mask, T, eos, pad, monkeypatch):
         rec.append(logits[:, :V].float().cpu())
         return real(logits, V, *a, **k)
 
-    monkeypatch.setattr(ops, "greedy_step_", recording)
+    from dalm_b200.engine import decoding
     eos_list = [] if eos is None else list(eos)
-    out = dec.generate(input_ids=ids.to(dec.dev), attention_mask=mask.to(dec.dev), max_length=T, early_stopping=True,
-                       eos_token_id=eos_list, pad_token_id=pad).cpu()      # [] = no EOS (None would mean the config's)
+    gen = lambda: dec.generate(input_ids=ids.to(dec.dev), attention_mask=mask.to(dec.dev), max_length=T, early_stopping=True,
+                               eos_token_id=eos_list, pad_token_id=pad).cpu()       # [] = no EOS (None would mean the config's)
+    # pass 1: eager launches with every step's logits recorded (the recorder reads them back, which a graph capture cannot)
+    monkeypatch.setenv("DALM_B200_DECODE_GRAPH", "0")
+    monkeypatch.setattr(ops, "greedy_step_", recording)
+    out = gen()
     monkeypatch.setattr(ops, "greedy_step_", real)
+    assert decoding.LAST_RUN["graph_replays"] == 0
+    # pass 2: the default launch mode — the decode step captured once as a CUDA graph and replayed; same kernels, same
+    # arguments, so the tokens must be IDENTICAL to the eager pass
+    monkeypatch.setenv("DALM_B200_DECODE_GRAPH", "1")
+    replayed = gen()
+    assert decoding.LAST_RUN["graph_replays"] >= min(4, out.shape[1] - ids.shape[1] - 2), decoding.LAST_RUN
+    assert torch.equal(replayed, out)
     B, L0 = ids.shape
     assert out.dtype == i64 and out.shape[0] == B and L0 < out.shape[1] <= T
     assert torch.equal(out[:, :L0], ids)                                    # prompt passes through untouched

@@ -92,7 +92,8 @@ class _StubDecoder(torch.nn.Module):
         return logits
 
     def _decode_step(self, ids, pos, caches, kmask, cur, tables):
-        assert cur == self.toks.shape[1]                                     # K / V of this token go to the next free column
+        assert cur.dtype == torch.int32 and (cur == self.toks.shape[1]).all()    # K / V of this token go to the next free column
+        cur = int(cur[0])
         self.toks = torch.cat([self.toks, ids[:, None]], 1)
         self.am = torch.cat([self.am, torch.ones(len(ids), 1, dtype=torch.int64)], 1)
         assert torch.equal(kmask[:, :cur + 1], self.am)                      # the device mask has grown with the tokens
@@ -101,17 +102,23 @@ class _StubDecoder(torch.nn.Module):
         return logits
 
 
-def _emulated_greedy_step(logits, V, eos_ids, pad_id, unfinished, tokens, mask, col, next_ids, pos, alive_slot):
-    best = logits[:, :V].float().argmax(-1)
-    tok = torch.where(unfinished.bool(), best, torch.full_like(best, pad_id))
-    tokens[:, col] = tok
-    mask[:, col] = 1
-    next_ids.copy_(tok)
-    pos += 1
-    if eos_ids is not None:
-        for e in eos_ids.tolist():
-            unfinished &= (tok != e).to(torch.int32)
-    alive_slot += unfinished.sum().to(torch.int32)
+def _emulated_greedy_step(logits, V, eos_ids, pad_id, unfinished, tokens, mask, col, next_ids, pos, alive):
+    """torch restatement of dalm_b200_greedy_step's contract (include/dalm_b200.h), row by row like the kernel's CTAs"""
+    cur_dev = col if torch.is_tensor(col) else None
+    T = tokens.shape[1]
+    eos = [] if eos_ids is None else eos_ids.tolist()
+    for b in range(logits.shape[0]):
+        c = int(cur_dev[b]) + 1 if cur_dev is not None else int(col)
+        if c >= T:
+            continue                                                         # a replay past the end of the buffers is a no-op
+        tok = int(logits[b, :V].float().argmax()) if int(unfinished[b]) else int(pad_id)
+        tokens[b, c], mask[b, c], next_ids[b] = tok, 1, tok
+        pos[b] += 1
+        if int(unfinished[b]) and tok in eos:
+            unfinished[b] = 0
+        alive[c] += int(unfinished[b])
+        if cur_dev is not None:
+            cur_dev[b] = c
 
 
 @pytest.mark.parametrize("use_eos", [False, True])
