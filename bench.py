@@ -187,6 +187,11 @@ def ncu_traffic():
         return None, {"source": f"unreadable ({type(e).__name__})"}
 
 
+def workload_name(args) -> str:
+    return (f"cfg-3 train_rage2e {args.retriever} + {args.generator} + PEFT(both) LoRA r=8, bs={BS}/GPU, "
+            f"Lq{LQ}/Lp{LP}/Lg{LG}")
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,8 +208,10 @@ def main():
         line = {"metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": BS / v * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": v / 7.94, "dtype": "f32", "data": "synthetic", "impl": "reference",
-                "config": {"workload": "cfg-3 train_rage2e bge-large-en + Llama-2-7B + PEFT(both), bs=18, Lq50/Lp128/Lg256",
-                           "parallelism": "cpu"},
+                "config": {"workload": workload_name(args), "global_batch": BS * max(1, args.gpus),
+                           "parallelism": "cpu (rank 0 host cores; the other ranks exit)",
+                           "dataset": "first rows of the synthetic 200k-row (Abstract,Question,Answer) 'full' set (all sequences truncated)",
+                           "weights": "seeded random-init (no checkpoints offline)"},
                 "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc},
                 "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -351,7 +358,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": value / 7.94,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"cfg-3 train_rage2e {args.retriever} + {args.generator} + PEFT(both) LoRA r=8, bs={BS}/GPU, Lq{LQ}/Lp{LP}/Lg{LG}",
+        "config": {"workload": workload_name(args),
                    "global_batch": BS * world, "parallelism": f"dp{world}", "rows_used": n_batches * BS * world,
                    "dataset": "first rows of the synthetic 200k-row (Abstract,Question,Answer) 'full' set (all sequences truncated)",
                    "l2": "per-step working set (27 GB weights + 22 GB activations) >> 126 MB L2; no explicit flush",
