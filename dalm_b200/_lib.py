@@ -69,6 +69,7 @@ SIGNATURES = {
     "dalm_b200_topk_ip_workspace": [_I, _I],
     "dalm_b200_topk_ip": [_P, _P, _L, _I, _I, _I, _I, _P, _P, _P, _P],
     "dalm_b200_nf4_roundtrip": [_P, _L, _P, _P, _P],
+    "dalm_b200_decode_gemm": [_P, _L, _P, _L, _P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P],
     "dalm_b200_rope_pos": [_P, _L, _I, _I, _I, _P, _P, _P, _I, _I, _P],
     "dalm_b200_attention_decode": [_P, _L, _I, _I, _I, _P, _P, _L, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _P, _I, _F, _P],
     "dalm_b200_greedy_step": [_P, _L, _I, _I, _P, _I, _L, _P, _P, _L, _P, _L, _I, _P, _I, _P, _P, _P, _P],

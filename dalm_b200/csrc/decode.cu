@@ -174,10 +174,145 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const __nv_bfloat16* _
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Weight-streaming GEMM for the decode step: out[m, n] = act(sum_k A[m,k] W[n,k]) + resid[m,n] with M <= 16 token rows.
+// HBM-bound: every weight is read exactly once (N*K*2 bytes), the activations (16 x K bf16) stay in L2. The 128-row tcgen05
+// tile of the training GEMM wastes 7/8 of its A tile here and runs N = 4096 on 64 CTAs (measured 10.2 ms per token at
+// Llama-2-7B against a 2.3 ms HBM floor), so this path uses one `mma.sync.m16n8k16` row tile = the whole batch instead:
+//   CTA = 16 output columns (2 n-tiles) x all of K, 256 threads; the 8 warps interleave over 32-wide k-chunks (split-K inside
+//   the CTA), partial sums meet in shared memory. Each lane loads 16 bytes (8 consecutive k) of one weight row and of two
+//   activation rows per chunk straight from global memory into MMA fragments: lane (g, t) takes k = chunk*32 + 8t .. +7, and
+//   the SAME permutation of k inside the chunk is applied to A and W (a contraction does not care about the order), so no
+//   cross-lane exchange or ldmatrix is needed. The pieces travel through a per-lane cp.async ring (6 chunks deep).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// 16-byte asynchronous global -> shared copy (zero-fill when !ok). L1-allocating for the activations (every CTA of an SM
+// reads the same 16 x K block), L2-only for the weight stream.
+__device__ __forceinline__ void cp_async16_ca(void* smem, const void* gmem, bool ok) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(ok ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async16_cg(void* smem, const void* gmem, bool ok) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(ok ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int DG_NT = 2;                 // 8-column n-tiles per CTA
+constexpr int DG_STAGES = 6;             // k-chunks in flight per lane (each: 2 activation + DG_NT weight 16-byte pieces)
+constexpr int DG_SLOTS = 2 + DG_NT;
+constexpr int DG_SMEM = DG_STAGES * 8 * DG_SLOTS * 32 * 16;     // 96 KB: [stage][warp][slot][lane] of 16 bytes
+
+// Every lane prefetches ITS OWN fragment pieces through a private ring in shared memory (it reads back exactly the 16-byte
+// slots it copied), so the ring needs no barrier at all: `cp.async.wait_group` orders a thread's own copies. Plain register
+// loads were tried first: ptxas sank each load next to its MMA (3 loads in flight per lane instead of 16).
+__global__ void __launch_bounds__(256) decode_gemm_kernel(const __nv_bfloat16* __restrict__ A, long long lda,
+                                                          const __nv_bfloat16* __restrict__ W, long long ldw,
+                                                          void* __restrict__ out, long long ldo, int out_f32,
+                                                          const void* __restrict__ resid, long long ldr, int resid_f32, int act,
+                                                          int M, int N, int K) {
+  extern __shared__ __align__(16) unsigned char dg_smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int n0 = blockIdx.x * (DG_NT * 8);
+  const int nchunks = (K + 31) / 32;
+  const int my_chunks = nchunks > warp ? (nchunks - warp + 7) / 8 : 0;    // this warp takes chunks warp, warp + 8, ...
+  uint4* ring = reinterpret_cast<uint4*>(dg_smem) + (size_t)warp * DG_SLOTS * 32 + lane;   // + stage*8*SLOTS*32 + slot*32
+  constexpr int STAGE_STRIDE = 8 * DG_SLOTS * 32;
+  float acc[DG_NT][4];
+#pragma unroll
+  for (int i = 0; i < DG_NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  const bool row_lo = g < M, row_hi = g + 8 < M;
+  const __nv_bfloat16* a_lo_p = A + (size_t)(row_lo ? g : 0) * lda;
+  const __nv_bfloat16* a_hi_p = A + (size_t)(row_hi ? g + 8 : 0) * lda;
+  const __nv_bfloat16* w_p[DG_NT];
+  bool w_ok[DG_NT];
+#pragma unroll
+  for (int i = 0; i < DG_NT; ++i) {
+    const int n = n0 + i * 8 + g;
+    w_ok[i] = n < N;
+    w_p[i] = W + (size_t)(w_ok[i] ? n : 0) * ldw;
+  }
+  auto issue = [&](int i) {                              // i-th chunk of this warp -> ring stage i % DG_STAGES
+    if (i < my_chunks) {
+      const int k = (warp + 8 * i) * 32 + 8 * t;         // K % 8 == 0: a lane's 8 elements are all inside or all outside K
+      const bool kin = k < K;
+      const int ks = kin ? k : 0;
+      uint4* st = ring + (size_t)(i % DG_STAGES) * STAGE_STRIDE;
+      cp_async16_ca(st, a_lo_p + ks, kin && row_lo);
+      cp_async16_ca(st + 32, a_hi_p + ks, kin && row_hi);
+#pragma unroll
+      for (int j = 0; j < DG_NT; ++j) cp_async16_cg(st + (2 + j) * 32, w_p[j] + ks, kin && w_ok[j]);
+    }
+    cp_async_commit_group();                             // one group per call, empty or not: the wait below counts groups
+  };
+#pragma unroll
+  for (int i = 0; i < DG_STAGES - 1; ++i) issue(i);
+  for (int i = 0; i < my_chunks; ++i) {
+    issue(i + DG_STAGES - 1);                            // refills the stage this lane consumed in the previous iteration
+    cp_async_wait_group<DG_STAGES - 1>();                // chunk i has landed
+    const uint4* st = ring + (size_t)(i % DG_STAGES) * STAGE_STRIDE;
+    const uint4 alo = st[0], ahi = st[32];
+#pragma unroll
+    for (int j = 0; j < DG_NT; ++j) {
+      const uint4 b = st[(2 + j) * 32];
+      // fragment k-slots (2t,2t+1) and (2t+8,2t+9) are fed actual k (8t+0,1),(8t+2,3), then (8t+4,5),(8t+6,7), for A and W alike
+      mma16816(acc[j], alo.x, ahi.x, alo.y, ahi.y, b.x, b.y);
+      mma16816(acc[j], alo.z, ahi.z, alo.w, ahi.w, b.z, b.w);
+    }
+  }
+  cp_async_wait_group<0>();
+  __syncthreads();                                       // every warp is done with its ring: reuse the memory for the partials
+  float(*part)[16][DG_NT * 8 + 1] = reinterpret_cast<float(*)[16][DG_NT * 8 + 1]>(dg_smem);
+  // accumulator fragment: c0,c1 = (row g, cols 2t, 2t+1), c2,c3 = (row g+8, same cols)
+#pragma unroll
+  for (int i = 0; i < DG_NT; ++i) {
+    part[warp][g][i * 8 + 2 * t] = acc[i][0];
+    part[warp][g][i * 8 + 2 * t + 1] = acc[i][1];
+    part[warp][g + 8][i * 8 + 2 * t] = acc[i][2];
+    part[warp][g + 8][i * 8 + 2 * t + 1] = acc[i][3];
+  }
+  __syncthreads();
+  const int m = tid >> 4, nn = tid & 15, n = n0 + nn;   // 256 threads = 16 rows x 16 columns
+  if (m < M && n < N) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += part[w][m][nn];
+    if (act == 1) v = gelu_erf(v);
+    if (resid) v += resid_f32 ? static_cast<const float*>(resid)[(size_t)m * ldr + n]
+                              : __bfloat162float(static_cast<const __nv_bfloat16*>(resid)[(size_t)m * ldr + n]);
+    if (out_f32) static_cast<float*>(out)[(size_t)m * ldo + n] = v;
+    else static_cast<__nv_bfloat16*>(out)[(size_t)m * ldo + n] = __float2bfloat16(v);
+  }
+}
+
 }  // namespace dalm
 
 using namespace dalm;
 #define ST(s) ((cudaStream_t)(s))
+
+extern "C" int dalm_b200_decode_gemm(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
+                                     int out_f32, const void* resid, long long ldr, int resid_f32, int act, int M, int N, int K,
+                                     void* stream) {
+  DALM_REQUIRE(M > 0 && M <= 16 && N > 0 && K > 0, "decode_gemm: needs 1 <= M <= 16 token rows (got M=%d N=%d K=%d)", M, N, K);
+  DALM_REQUIRE((K % 8) == 0 && (lda % 8) == 0 && (ldw % 8) == 0 && lda >= K && ldw >= K && ldo >= N,
+               "decode_gemm: K and the operand row strides must be multiples of 8 elements");
+  DALM_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, "decode_gemm: operands must be 16-byte aligned");
+  DALM_REQUIRE(act == 0 || act == 1, "decode_gemm: act must be 0 (none) or 1 (gelu)");
+  DALM_REQUIRE(resid == nullptr || ldr >= N, "decode_gemm: residual row stride");
+  static bool attr = false;
+  if (!attr) { DALM_CUDA(cudaFuncSetAttribute(decode_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM)); attr = true; }
+  decode_gemm_kernel<<<(N + DG_NT * 8 - 1) / (DG_NT * 8), 256, DG_SMEM, ST(stream)>>>(
+      (const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)W, ldw, out, ldo, out_f32, resid, ldr, resid_f32, act, M, N, K);
+  count_launch();
+  return check_launch("decode_gemm_kernel");
+}
 
 extern "C" int dalm_b200_rope_pos(void* buf, long long ld, int col0, int nheads, int D, const float* cos_t,
                                   const float* sin_t, const int64_t* pos, int M, int T, void* stream) {

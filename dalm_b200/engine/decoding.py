@@ -81,7 +81,7 @@ def greedy_generate(dec, input_ids: Optional[torch.Tensor] = None, attention_mas
             caches[li][1][:, :L0].copy_(qkv[:, v0:v0 + width].view(B, L0, width))
 
         last = dec._prefill_last(ids, mask, pos_prompt, tables, sink)             # bf16 [B,H]
-        logits = ops.gemm(last, dec.lm_head)                                      # bf16 [B, Vp]
+        logits = ops.gemm_rows(last, dec.lm_head)                                 # bf16 [B, Vp]
         unfinished = torch.ones(B, dtype=torch.int32, device=dev)
         next_ids = torch.zeros(B, dtype=torch.int64, device=dev)
         pos = (mask.sum(-1) - 1).contiguous()                                     # position id of the last prompt token

@@ -260,14 +260,14 @@ class FalconDecoder(torch.nn.Module):
         x = ops.embed_gather(ids, self.embed)
         for li, W in enumerate(self.layers):
             _, h, _, _ = ops.layernorm_fwd(x, W["ln_g"], W["ln_b"], self.eps, want_f32=False)
-            qkv = ops.gemm(h, W["Wqkv"])
+            qkv = ops.gemm_rows(h, W["Wqkv"])
             ops.rope_pos_(qkv, 0, self.nh + 1, self.hd, cos_t, sin_t, pos)
             att = ops.attention_decode(qkv, 0, self.Nq, self.Nq + self.hd, caches[li][0], caches[li][1], kmask, cur,
                                        self.nh, 1, self.hd)
-            t = ops.gemm(att, W["Wd"], out_dtype=f32, resid=x)
-            x = ops.gemm(ops.gemm(h, W["W1"], act=1), W["W2"], out_dtype=f32, resid=t)
+            t = ops.gemm_rows(att, W["Wd"], out_dtype=f32, resid=x)
+            x = ops.gemm_rows(ops.gemm_rows(h, W["W1"], act=1), W["W2"], out_dtype=f32, resid=t)
         _, hf, _, _ = ops.layernorm_fwd(x, self.lnf_g, self.lnf_b, self.eps, want_f32=False)
-        return ops.gemm(hf, self.lm_head)
+        return ops.gemm_rows(hf, self.lm_head)
 
     def generate(self, input_ids: Optional[torch.Tensor] = None, attention_mask: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:
         """HF `generate` for the call the reference makes (greedy search); see engine/decoding.py"""

@@ -356,16 +356,16 @@ class LlamaDecoder(torch.nn.Module):
             ops.rmsnorm_fwd(x, W["g1"], self.eps, h=h1_aug[:, :H])
             if Ra:
                 ops.skinny_gemm(h1_aug[:, :H], W["A_stack"], h1_aug[:, H:], K=H, R=Ra)
-            qkv = ops.gemm(h1_aug, W["Wqkv_aug"])                                # [B, Nq+2Nkv]
+            qkv = ops.gemm_rows(h1_aug, W["Wqkv_aug"])                                # [B, Nq+2Nkv]
             ops.rope_pos_(qkv, 0, self.nh + self.nkv, self.hd, cos_t, sin_t, pos)
             att = ops.attention_decode(qkv, 0, self.Nq, self.Nq + self.Nkv, caches[li][0], caches[li][1], kmask, cur,
                                        self.nh, self.nkv, self.hd)
-            x_mid = ops.gemm(att, W["Wo"], out_dtype=f32, resid=x)
+            x_mid = ops.gemm_rows(att, W["Wo"], out_dtype=f32, resid=x)
             h2, _ = ops.rmsnorm_fwd(x_mid, W["g2"], self.eps)
-            act = ops.swiglu_fwd(ops.gemm(h2, W["Wgu"]), F)
-            x = ops.gemm(act, W["Wd"], out_dtype=f32, resid=x_mid)
+            act = ops.swiglu_fwd(ops.gemm_rows(h2, W["Wgu"]), F)
+            x = ops.gemm_rows(act, W["Wd"], out_dtype=f32, resid=x_mid)
         hf, _ = ops.rmsnorm_fwd(x, self.norm_g, self.eps)
-        return ops.gemm(hf, self.lm_head)
+        return ops.gemm_rows(hf, self.lm_head)
 
     def _prefill_last(self, ids, mask, pos, tables, sink) -> torch.Tensor:
         """prompt pass of `generate`: rotated K / V of every layer go to `sink`; returns the last column's final hidden

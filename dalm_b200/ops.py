@@ -6,6 +6,7 @@ Every wrapper validates device / dtype / contiguity and then passes raw pointers
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -549,6 +550,33 @@ def nf4_roundtrip_(w: torch.Tensor, want_codes: bool = False):
 # ----------------------------------------------------------------------------------------------------------------
 # greedy decoding (evaluation: reference dalm/eval/eval_rag.py:126-140)
 # ----------------------------------------------------------------------------------------------------------------
+def decode_gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *, out_dtype=bf16, act: int = 0,
+                resid: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = act(a[M,K] @ w[N,K]^T) + resid for the M <= 16 token rows of a decode step: weight-streaming kernel, every
+    weight read once. a, w bf16 with contiguous rows (row strides multiples of 8); resid / out bf16 or fp32."""
+    _chk(a, bf16, "decode_gemm a"); _chk(w, bf16, "decode_gemm w")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise _lib.DalmB200Error(f"decode_gemm: a is [{M},{K}] but w is {tuple(w.shape)}")
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=a.device)
+    if out.dtype not in (bf16, f32) or (resid is not None and resid.dtype not in (bf16, f32)):
+        raise _lib.DalmB200Error("decode_gemm: out / resid must be bf16 or fp32")
+    _lib.call("dalm_b200_decode_gemm", _p(a), _ld(a), _p(w), _ld(w), _p(out), _ld(out), 1 if out.dtype == f32 else 0, _p(resid),
+              _ld(resid) if resid is not None else 0, 1 if (resid is not None and resid.dtype == f32) else 0, int(act), M, N, K,
+              _stream())
+    return out
+
+
+def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, out_dtype=bf16, act: int = 0, resid: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a[M,K] @ w[N,K]^T for a decode step: up to 16 rows go through the weight-streaming `decode_gemm` (the 128-row tcgen05
+    tile would be 7/8 empty), larger batches through the training GEMM. DALM_B200_DECODE_GEMM=0 forces the latter."""
+    if a.shape[0] <= 16 and os.environ.get("DALM_B200_DECODE_GEMM", "1") != "0":
+        return decode_gemm(a, w, out_dtype=out_dtype, act=act, resid=resid)
+    return gemm(a, w, out_dtype=out_dtype, act=act, resid=resid)
+
+
 def rope_pos_(buf, col0: int, nheads: int, D: int, cos_t, sin_t, pos):
     """in-place RoPE of `nheads` heads at explicit position ids pos[M] (int64); cos_t / sin_t fp32 [T, D/2]"""
     _chk(buf, bf16, "rope_pos buf"); _chk(pos, i64, "rope_pos pos"); _chk(cos_t, f32, "rope_pos cos"); _chk(sin_t, f32, "rope_pos sin")

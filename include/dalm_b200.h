@@ -199,6 +199,11 @@ int dalm_b200_nf4_roundtrip(float* w, long long n, void* codes, float* absmax, v
  * Device-column mode (cur_dev != NULL, int32 [B]): attention_decode takes cur = cur_dev[b], greedy_step writes column
  *   cur_dev[b] + 1 and advances cur_dev[b]; the host `cur` / `col` arguments are ignored, so the launch sequence of a
  *   decode step has identical arguments for every token and can be captured once in a CUDA graph and replayed. */
+/* decode_gemm: out[M,N] = act(A[M,K] W[N,K]^T) + resid for the M <= 16 token rows of a decode step (every nn.Linear of the
+ *   generator once per generated token): weight-streaming mma.sync kernel, each weight read once. act 0 none / 1 gelu;
+ *   out / resid bf16 or fp32 (resid may be NULL). */
+int dalm_b200_decode_gemm(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int out_f32,
+                          const void* resid, long long ldr, int resid_f32, int act, int M, int N, int K, void* stream);
 int dalm_b200_rope_pos(void* buf, long long ld, int col0, int nheads, int D, const float* cos_t, const float* sin_t,
                        const int64_t* pos, int M, int T, void* stream);
 int dalm_b200_attention_decode(const void* qkv, long long ldq, int q_col, int k_col, int v_col, void* cache_k, void* cache_v,

@@ -96,6 +96,36 @@ def test_attention_decode(cuda_dev, D, Hq, Hkv, T, cur):
     assert torch.equal(out2, out) and torch.equal(ck2, ck) and torch.equal(cv2, cv)
 
 
+@pytest.mark.parametrize("M,N,K", [(16, 4096, 4096), (5, 24, 72), (1, 8, 8), (13, 1000, 1048), (16, 512, 11008), (3, 32008, 256)])
+def test_decode_gemm(cuda_dev, M, N, K):
+    """weight-streaming GEMM of the decode step (M <= 16 rows) vs torch fp32, every epilogue; ragged N, K tails (K % 32 != 0),
+    strided operands (the LoRA-augmented activation / weight buffers have a padded row stride)"""
+    from dalm_b200 import _lib, ops
+    g = torch.Generator().manual_seed(M * 1000 + N + K)
+    a_buf = (torch.randn(M, K + 64, generator=g) * 0.5).to(bf16).to(cuda_dev)
+    w_buf = (torch.randn(N, K + 64, generator=g) * 0.5).to(bf16).to(cuda_dev)
+    a, w = a_buf[:, :K], w_buf[:, :K]                                          # row stride K + 64
+    ref = a.float() @ w.float().t()
+    out = ops.decode_gemm(a, w)
+    assert out.dtype == bf16 and _rel(out.float(), ref) < 4e-3                 # bf16 output rounding
+    out32 = ops.decode_gemm(a, w, out_dtype=f32)
+    assert _rel(out32, ref) < 1e-4                                             # fp32 tensor-core accumulate over up to 11 008 terms
+    r32 = torch.randn(M, N, generator=g).to(cuda_dev)
+    assert _rel(ops.decode_gemm(a, w, out_dtype=f32, resid=r32), ref + r32) < 1e-4
+    r16 = r32.to(bf16)
+    assert _rel(ops.decode_gemm(a, w, out_dtype=bf16, resid=r16).float(), ref + r16.float()) < 4e-3
+    gelu = torch.nn.functional.gelu(ref)
+    assert _rel(ops.decode_gemm(a, w, out_dtype=f32, act=1), gelu) < 1e-4
+    # the same numbers as the tcgen05 GEMM the rest of the engine uses (bf16 outputs agree to rounding)
+    if M == 16:
+        assert _rel(ops.gemm(a, w).float(), out.float()) < 4e-3
+    wide = torch.zeros(M, N + 16, dtype=f32, device=cuda_dev)                  # output into a column slice
+    ops.decode_gemm(a, w, out=wide[:, 8:8 + N])
+    assert _rel(wide[:, 8:8 + N], ref) < 1e-4 and (wide[:, :8] == 0).all() and (wide[:, 8 + N:] == 0).all()
+    with pytest.raises(_lib.DalmB200Error):
+        ops.decode_gemm(torch.zeros(17, K, dtype=bf16, device=cuda_dev), w)   # more than one 16-row tile: use ops.gemm
+
+
 def test_greedy_step(cuda_dev):
     from dalm_b200 import ops
     g = torch.Generator().manual_seed(0)
@@ -216,8 +246,9 @@ def _check_against_oracle(dec, ref, ids, mask, T, eos, pad, monkeypatch):
     return out, mine
 
 
-@pytest.mark.parametrize("name,lora", [("llama-tiny", True), ("llama-hd128", False), ("llama-hd128", True)])
-def test_llama_generate(cuda_dev, monkeypatch, name, lora):
+@pytest.mark.parametrize("name,lora,rows_gemm", [("llama-tiny", True, "1"), ("llama-hd128", False, "1"), ("llama-hd128", True, "0")])
+def test_llama_generate(cuda_dev, monkeypatch, name, lora, rows_gemm):
+    monkeypatch.setenv("DALM_B200_DECODE_GEMM", rows_gemm)                    # "0": decode-step GEMMs on the training tcgen05 kernel
     from dalm_b200 import synthetic
     from dalm_b200.engine import params
     from dalm_b200.engine.llama import LlamaDecoder

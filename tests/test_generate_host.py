@@ -135,7 +135,7 @@ def test_host_loop_with_emulated_kernels(monkeypatch, use_eos):
     want = og.greedy_generate(model, ids, mask, T, eos_token_ids=eos or (), pad_token_id=(eos[0] if eos else 7))
     if use_eos:
         assert want.shape[1] < T                                             # every row finishes early: the trim path runs
-    monkeypatch.setattr(ops, "gemm", lambda a, b, **k: a)
+    monkeypatch.setattr(ops, "gemm_rows", lambda a, b, **k: a)              # the stub decoder already returns logits
     monkeypatch.setattr(ops, "greedy_step_", _emulated_greedy_step)
     dec = _StubDecoder(model, dict(cfg, eos_token_id=None))
     dec.train()
