@@ -139,7 +139,7 @@ def build_bert_tokenizer(out_dir: str, vocab_size: int = 30522) -> str:
     tok.normalizer = normalizers.BertNormalizer(lowercase=True)
     tok.pre_tokenizer = pre_tokenizers.BertPreTokenizer()
     special = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"]
-    trainer = trainers.WordPieceTrainer(vocab_size=min(vocab_size, 8000), special_tokens=special)
+    trainer = trainers.WordPieceTrainer(vocab_size=min(vocab_size, 8000), special_tokens=special, show_progress=False)
     tok.train_from_iterator(_corpus(), trainer)
     vocab = dict(tok.get_vocab())
     nxt = len(vocab)
@@ -161,7 +161,7 @@ def build_llama_tokenizer(out_dir: str, vocab_size: int = 32000) -> str:
     tok = Tokenizer(models.BPE(unk_token="<unk>", fuse_unk=True, byte_fallback=True))
     tok.pre_tokenizer = pre_tokenizers.Metaspace(replacement="▁", prepend_scheme="first", split=False)
     byte_tokens = [f"<0x{i:02X}>" for i in range(256)]
-    trainer = trainers.BpeTrainer(vocab_size=min(vocab_size, 6000), special_tokens=["<unk>", "<s>", "</s>"] + byte_tokens)
+    trainer = trainers.BpeTrainer(vocab_size=min(vocab_size, 6000), special_tokens=["<unk>", "<s>", "</s>"] + byte_tokens, show_progress=False)
     tok.train_from_iterator(_corpus(), trainer)
     vocab = tok.get_vocab()
     model_json = json.loads(tok.to_str())["model"]
