@@ -10,9 +10,10 @@ semantics (transformers GenerationMixin._sample with do_sample=False) as a launc
   step      one token per sequence: norm -> QKV GEMM -> RoPE at the token's position -> `attention_decode` (appends the
             token's K / V, attends over the cache) -> output projection -> MLP -> LM head -> `greedy_step` (argmax, pad
             after EOS, next position id, next column), all state on the device, so the launch sequence has the same
-            arguments for every token: it is captured once as a CUDA graph and replayed (DALM_B200_DECODE_GRAPH=0 launches
-            eagerly: 292 launches / 11.1 ms per token at Llama-2-7B from Python); the host reads one "anyone still
-            generating" counter every 8 tokens
+            arguments for every token and CAN be captured once as a CUDA graph and replayed (292 launches per token at
+            Llama-2-7B; issued from Python they are host-bound at ~9 ms per token). Capture has a fixed cost of several
+            hundred ms per `generate` call, so it is used for long generations only (GRAPH_MIN_STEPS; DALM_B200_DECODE_GRAPH
+            = 1 / 0 forces it on / off); the host reads one "anyone still generating" counter every 8 tokens
 
 A decoder takes part by providing `_prefill_last`, `_decode_step`, `kv_columns`, `_rope`, `lm_head`, `V`, `cfg`, `dev`.
 """
@@ -29,6 +30,7 @@ from .. import ops
 bf16 = torch.bfloat16
 logger = logging.getLogger(__name__)
 LAST_RUN = {"graph_replays": 0, "eager_steps": 0}          # how the decode steps of the most recent call were launched
+GRAPH_MIN_STEPS = 192                                       # remaining tokens from which capturing the step pays for itself
 
 
 @torch.no_grad()
@@ -98,7 +100,11 @@ def greedy_generate(dec, input_ids: Optional[torch.Tensor] = None, attention_mas
             ops.greedy_step_(lg, dec.V, eos_t, pad, unfinished, tokens, kmask, cur_row, next_ids, pos, alive)
 
         graph, replays, eager = None, 0, 0
-        use_graph = dev.type == "cuda" and os.environ.get("DALM_B200_DECODE_GRAPH", "1") != "0" and total - col >= 4
+        # Measured (profiles/r01_decode_bench.jsonl): `torch.cuda.graph` capture costs ~0.3-0.6 s per call (its entry runs
+        # gc.collect + empty_cache, and the private pool is allocated afresh) while a replayed step saves a few ms over the
+        # Python launch sequence, so by default only long generations are captured. DALM_B200_DECODE_GRAPH=1 / 0 forces it.
+        mode = os.environ.get("DALM_B200_DECODE_GRAPH", "auto")
+        use_graph = dev.type == "cuda" and ((mode == "1" and total - col >= 4) or (mode == "auto" and total - col >= GRAPH_MIN_STEPS))
         while col < total:
             if eos_list and (col - L0) % 8 == 0 and int(alive[col - 1].item()) == 0:    # one host read every 8 tokens
                 break
