@@ -130,13 +130,10 @@ def train_retriever_only(
     train_retriever(**kw)
 
 
-def _out_of_scope(name: str):
-    def cmd() -> None:
-        print(f"`dalm {name}` belongs to a reference subsystem outside dalm_b200's scope (training hot path only); "
-              "see DESIGN.md.")
-        raise typer.Exit(code=2)
-    cmd.__doc__ = f"(reference command, not part of the B200 hot-path build)"
-    return cmd
+def _out_of_scope(name: str) -> None:
+    print(f"`dalm {name}` belongs to a reference subsystem outside dalm_b200's scope (training / evaluation hot path only); "
+          "see DESIGN.md.")
+    raise typer.Exit(code=2)
 
 
 class TorchDtype(str, Enum):                 # reference cli.py:24-27
@@ -203,8 +200,19 @@ def eval_rag(
                  retriever_is_autoregressive=retriever_is_autoregressive)
 
 
-for _n in ("qa-gen",):
-    cli.command(name=_n)(_out_of_scope(_n))
+@cli.command()
+def qa_gen(                                   # reference cli.py:280-309: same arguments, so an existing command line parses
+    dataset_path: Annotated[str, typer.Argument(help="Path to the input dataset.", show_default=False)],
+    output_dir: Annotated[str, typer.Option(help="Output directory to store the resulting files")] = ".",
+    passage_column_name: Annotated[str, typer.Option(help="Column name for the passage/text")] = "Abstract",
+    title_column_name: Annotated[str, typer.Option(help="Column name for the title of the full document")] = "Title",
+    batch_size: Annotated[int, typer.Option(help="Batch size (per device) for generating question answer pairs.")] = 100,
+    sample_size: Annotated[int, typer.Option(help="Number of examples to process.")] = 1000,
+    as_csv: Annotated[bool, typer.Option(help="Save the files as CSV.")] = True,
+) -> None:
+    """(reference command — QA-pair data generation — not part of the B200 hot-path build; exits with status 2)"""
+    _out_of_scope("qa-gen")
+
 
 if __name__ == "__main__":
     cli()
