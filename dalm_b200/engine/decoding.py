@@ -30,6 +30,7 @@ from .. import ops
 bf16 = torch.bfloat16
 logger = logging.getLogger(__name__)
 LAST_RUN = {"graph_replays": 0, "eager_steps": 0}          # how the decode steps of the most recent call were launched
+MAX_CACHE_TOKENS = 8192                                     # dalm_b200_attention_decode: T <= 8192
 GRAPH_MIN_STEPS = 192                                       # remaining tokens from which capturing the step pays for itself
 
 
@@ -57,6 +58,9 @@ def greedy_generate(dec, input_ids: Optional[torch.Tensor] = None, attention_mas
     if L0 >= total:
         raise ValueError(f"Input length of input_ids is {L0}, but `max_length` is set to {total}. This can lead to unexpected "
                          "behavior. You should consider increasing `max_length` or, better yet, setting `max_new_tokens`.")
+    if total > MAX_CACHE_TOKENS:
+        raise NotImplementedError(f"generate: max_length {total} exceeds the decode attention kernel's cache limit of "
+                                  f"{MAX_CACHE_TOKENS} tokens (its score row lives in shared memory)")
     eos = dec.cfg.get("eos_token_id") if eos_token_id is None else eos_token_id
     eos_list = [] if eos is None else ([int(e) for e in eos] if isinstance(eos, (list, tuple)) else [int(eos)])
     pad = pad_token_id if pad_token_id is not None else dec.cfg.get("pad_token_id")

@@ -147,5 +147,7 @@ def test_host_loop_with_emulated_kernels(monkeypatch, use_eos):
         greedy_generate(dec, input_ids=ids, attention_mask=mask, max_length=10)
     with pytest.raises(NotImplementedError):
         greedy_generate(dec, input_ids=ids, attention_mask=mask, max_length=T, do_sample=True)
+    with pytest.raises(NotImplementedError):
+        greedy_generate(dec, input_ids=ids, attention_mask=mask, max_length=8193)       # beyond the decode kernel's cache limit
     short = greedy_generate(dec, input_ids=ids, attention_mask=mask, max_new_tokens=3, eos_token_id=None, pad_token_id=7)
     assert torch.equal(short, free[:, :13])
