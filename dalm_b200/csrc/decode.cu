@@ -11,9 +11,11 @@
 //
 // All state a step needs (next token ids, position ids, finished flags, per-step alive counts, and — in device-column mode —
 // each row's current column) lives in device memory: a decode step is then the SAME launch sequence with the same
-// arguments for every token, captured once as a CUDA graph and replayed (292 launches per token at Llama-2-7B; issued from
-// Python they cost 11 ms per token against a 2.3 ms HBM floor). The host reads back one "is anyone still generating"
-// counter every few steps.
+// arguments for every token and can be captured once as a CUDA graph and replayed (292 launches per token at Llama-2-7B).
+// The host reads back one "is anyone still generating" counter every few steps.
+// Measured (profiles/README.md, r01_decode_bench.jsonl): a decode step costs ~3.3 ms + 0.029 ms x cached tokens; the second
+// term is attn_decode_kernel's PV pass (pass 3 below walks the keys serially per thread, one dependent 2-byte load each):
+// the known limiter of this file, first item of the next round.
 #include "common.cuh"
 #include <limits.h>
 

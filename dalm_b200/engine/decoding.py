@@ -11,9 +11,9 @@ semantics (transformers GenerationMixin._sample with do_sample=False) as a launc
             token's K / V, attends over the cache) -> output projection -> MLP -> LM head -> `greedy_step` (argmax, pad
             after EOS, next position id, next column), all state on the device, so the launch sequence has the same
             arguments for every token and CAN be captured once as a CUDA graph and replayed (292 launches per token at
-            Llama-2-7B; issued from Python they are host-bound at ~9 ms per token). Capture has a fixed cost of several
-            hundred ms per `generate` call, so it is used for long generations only (GRAPH_MIN_STEPS; DALM_B200_DECODE_GRAPH
-            = 1 / 0 forces it on / off); the host reads one "anyone still generating" counter every 8 tokens
+            Llama-2-7B). Capture has a fixed cost of 50-300 ms per `generate` call, so it is used for long generations only
+            (GRAPH_MIN_STEPS; DALM_B200_DECODE_GRAPH = 1 / 0 forces it on / off); the host reads one "anyone still
+            generating" counter every 8 tokens
 
 A decoder takes part by providing `_prefill_last`, `_decode_step`, `kv_columns`, `_rope`, `lm_head`, `V`, `cfg`, `dev`.
 """
@@ -104,9 +104,10 @@ def greedy_generate(dec, input_ids: Optional[torch.Tensor] = None, attention_mas
             ops.greedy_step_(lg, dec.V, eos_t, pad, unfinished, tokens, kmask, cur_row, next_ids, pos, alive)
 
         graph, replays, eager = None, 0, 0
-        # Measured (profiles/r01_decode_bench.jsonl): `torch.cuda.graph` capture costs ~0.3-0.6 s per call (its entry runs
-        # gc.collect + empty_cache, and the private pool is allocated afresh) while a replayed step saves a few ms over the
-        # Python launch sequence, so by default only long generations are captured. DALM_B200_DECODE_GRAPH=1 / 0 forces it.
+        # Measured (profiles/r01_decode_bench.jsonl): a `torch.cuda.graph` capture costs 50-300 ms per call (its entry runs
+        # gc.collect + empty_cache, the private pool is allocated afresh) and a replayed step is only ~0.5-1 ms faster than
+        # the Python launch sequence while the step is GPU-bound (decode attention), so by default only long generations
+        # are captured. DALM_B200_DECODE_GRAPH=1 / 0 forces it.
         mode = os.environ.get("DALM_B200_DECODE_GRAPH", "auto")
         use_graph = dev.type == "cuda" and ((mode == "1" and total - col >= 4) or (mode == "auto" and total - col >= GRAPH_MIN_STEPS))
         while col < total:
