@@ -18,6 +18,7 @@
 // the known limiter of this file, first item of the next round.
 #include "common.cuh"
 #include <limits.h>
+#include <stdlib.h>
 
 namespace dalm {
 
@@ -122,6 +123,105 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const __nv_bfloat16* _
       for (int gg = 1; gg < G; ++gg) acc += part[gg * D + d];
   }
   if (g == 0) out[(size_t)b * ldo + h * D + d] = __float2bfloat16(acc / sum);
+}
+
+// CANDIDATE (not the default; DALM_B200_DECODE_ATTN=2 selects it): the same kernel with a parallel PV pass. Measured on the
+// default kernel: 0.9 us per cached key per layer, because pass 3 above walks the keys serially per thread with the V load
+// behind `if (p != 0)` (profiles/README.md, r01_decode_bench.jsonl line 4). Here 128 threads = KG key groups x D/8 lanes,
+// every lane loads 16 bytes of V unconditionally (masked keys carry p = 0; their cache rows are initialised memory) and the
+// KG partial rows meet in shared memory. Written after the round's GPU minutes were spent: its GPU tests
+// (tests/test_generate_gpu.py, DALM_B200_EXPERIMENTAL=1) have not run yet, so it is NOT wired as the default.
+// one explicit 16-byte read-only load -> 8 floats (the struct-typed loads above are split into 32-bit loads by the compiler)
+__device__ __forceinline__ void load8_nc(const __nv_bfloat16* p, float* f) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x; f[2 * i + 1] = t.y;
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) attn_decode_v2_kernel(const __nv_bfloat16* __restrict__ qkv, long long ldq, int q_col,
+                                                             int k_col, int v_col, __nv_bfloat16* __restrict__ cache_k,
+                                                             __nv_bfloat16* __restrict__ cache_v, long long cache_sb,
+                                                             long long cache_st, const int64_t* __restrict__ mask,
+                                                             long long ldm, __nv_bfloat16* __restrict__ out, long long ldo,
+                                                             int Hq, int Hkv, int cur_host, const int* __restrict__ cur_dev,
+                                                             int sp_cap, float scale) {
+  extern __shared__ float sm[];
+  float* sq = sm;
+  float* sp = sm + D;
+  float* red = sp + sp_cap;
+  float* part = red + 32;                        // [KG][D] = 1024 floats for every supported D
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int cur = cur_dev ? min(cur_dev[b], sp_cap - 1) : cur_host;
+  const int group = Hq / Hkv, kvh = h / group;
+  const __nv_bfloat16* qrow = qkv + (size_t)b * ldq + q_col + h * D;
+  const __nv_bfloat16* krow = qkv + (size_t)b * ldq + k_col + kvh * D;
+  const __nv_bfloat16* vrow = qkv + (size_t)b * ldq + v_col + kvh * D;
+  __nv_bfloat16* ck = cache_k + (size_t)b * cache_sb + kvh * D;
+  __nv_bfloat16* cv = cache_v + (size_t)b * cache_sb + kvh * D;
+  if (tid < D) {
+    sq[tid] = __bfloat162float(qrow[tid]) * scale;
+    if (h % group == 0) {
+      ck[(size_t)cur * cache_st + tid] = krow[tid];
+      cv[(size_t)cur * cache_st + tid] = vrow[tid];
+    }
+  }
+  __syncthreads();
+
+  float lmax = -INFINITY;
+  for (int t = tid; t <= cur; t += 128) {
+    const bool valid = (t == cur) || mask[(size_t)b * ldm + t] != 0;
+    const __nv_bfloat16* kp = (t == cur) ? krow : ck + (size_t)t * cache_st;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < D; j += 8) {
+      float f[8];
+      load8_nc(kp + j, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += sq[j + e] * f[e];
+    }
+    s = valid ? s : -INFINITY;
+    sp[t] = s;
+    lmax = fmaxf(lmax, s);
+  }
+  const float m = block_max(lmax, red);
+  float lsum = 0.f;
+  for (int t = tid; t <= cur; t += 128) {
+    const float s = sp[t];
+    const float p = (s == -INFINITY) ? 0.f : __expf(s - m);
+    sp[t] = p;
+    lsum += p;
+  }
+  const float sum = block_sum(lsum, red);
+  __syncthreads();
+
+  constexpr int LPK = D / 8, KG = 128 / LPK;    // lanes per key (16 bytes each), key groups: 16 x 8, 8 x 16, 4 x 32
+  const int kg = tid / LPK, dl = tid % LPK;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll 4
+  for (int t = kg; t <= cur; t += KG) {
+    const __nv_bfloat16* vp = (t == cur) ? vrow : cv + (size_t)t * cache_st;
+    float f[8];
+    load8_nc(vp + 8 * dl, f);
+    const float p = sp[t];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += p * f[e];
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) part[kg * D + 8 * dl + e] = acc[e];
+  __syncthreads();
+  if (tid < D) {
+    float o = 0.f;
+#pragma unroll
+    for (int k = 0; k < KG; ++k) o += part[k * D + tid];
+    out[(size_t)b * ldo + h * D + tid] = __float2bfloat16(o / sum);
+  }
 }
 
 // grid B, 256 threads. argmax over logits[b, 0..V) (ties -> lowest index, like torch.argmax), then HF's greedy bookkeeping
@@ -339,8 +439,21 @@ extern "C" int dalm_b200_attention_decode(const void* qkv, long long ldq, int q_
                "attention_decode: pointers must be 16-byte aligned");
   DALM_REQUIRE(mask != nullptr && cache_st >= (long long)Hkv * D && cache_sb >= cache_st * T, "attention_decode: cache layout");
   const int sp_cap = ((cur_dev ? T : cur + 1) + 3) & ~3;
-  const size_t smem = (size_t)(D + sp_cap + 32 + 128) * sizeof(float);
+  const char* variant = getenv("DALM_B200_DECODE_ATTN");
+  const bool v2 = variant != nullptr && variant[0] == '2';          // candidate kernel, see attn_decode_v2_kernel
+  const size_t smem = (size_t)(D + sp_cap + 32 + (v2 ? 1024 : 128)) * sizeof(float);
   dim3 grid(Hq, B);
+  if (v2) {
+#define DALM_DECODE2(DD)                                                                                                 \
+  attn_decode_v2_kernel<DD><<<grid, 128, smem, ST(stream)>>>((const __nv_bfloat16*)qkv, ldq, q_col, k_col, v_col,        \
+                                                             (__nv_bfloat16*)cache_k, (__nv_bfloat16*)cache_v, cache_sb, \
+                                                             cache_st, mask, ldm, (__nv_bfloat16*)out, ldo, Hq, Hkv, cur, \
+                                                             cur_dev, sp_cap, scale)
+    if (D == 128) DALM_DECODE2(128); else if (D == 64) DALM_DECODE2(64); else DALM_DECODE2(32);
+#undef DALM_DECODE2
+    count_launch();
+    return check_launch("attn_decode_v2_kernel");
+  }
 #define DALM_DECODE(DD)                                                                                                  \
   attn_decode_kernel<DD><<<grid, 128, smem, ST(stream)>>>((const __nv_bfloat16*)qkv, ldq, q_col, k_col, v_col,           \
                                                           (__nv_bfloat16*)cache_k, (__nv_bfloat16*)cache_v, cache_sb,    \
