@@ -7,6 +7,7 @@ decoded greedily here; that is stated in the log line, not hidden."""
 from __future__ import annotations
 
 import logging
+from argparse import Namespace
 from typing import Any, Final, List, Literal, Optional
 
 import torch
@@ -121,3 +122,45 @@ def evaluate_rag(
     print("Generator evaluation:")
     print("Exact match:", total_em_hit / len(processed))
     return results
+
+
+# script entry point of the reference (:27-123, :293-313): same flags and defaults, one table
+_FLAGS = [
+    ("dataset_path", dict(type=str, default=None, required=True, help="csv file or datasets directory")),
+    ("query_column_name", dict(type=str, default="query")),
+    ("passage_column_name", dict(type=str, default="passage")),
+    ("answer_column_name", dict(type=str, default="answer")),
+    ("embed_dim", dict(type=int, default=1024, help="width of the retriever's embeddings")),
+    ("max_length", dict(type=int, default=256, help="tokens per query / passage, and TOTAL tokens of a generated answer")),
+    ("retriever_name_or_path", dict(type=str, required=True)),
+    ("generator_name_or_path", dict(type=str, required=True)),
+    ("retriever_peft_model_path", dict(type=str, required=False)),
+    ("generator_peft_model_path", dict(type=str, required=False)),
+    ("test_batch_size", dict(type=int, default=8)),
+    ("query_batch_size", dict(type=int, default=16, help="prompts per generate() call")),
+    ("device", dict(type=str, default="cuda", help="must be a CUDA device: there is no CPU path")),
+    ("torch_dtype", dict(type=str, default="float16")),
+    ("top_k", dict(type=int, default=10)),
+    ("evaluate_generator", dict(action="store_true", help="also generate answers and score exact match")),
+    ("is_retriever_autoregressive", dict(action="store_true")),
+]
+
+
+def parse_args() -> Namespace:
+    from ..training.utils.loop import build_parser
+    return build_parser("RAG evaluation: retrieval metrics + greedy generation / exact match (B200-native)", _FLAGS).parse_args()
+
+
+def main() -> None:
+    a = parse_args()
+    evaluate_rag(dataset_or_path=a.dataset_path, retriever_name_or_path=a.retriever_name_or_path,
+                 generator_name_or_path=a.generator_name_or_path, retriever_peft_model_path=a.retriever_peft_model_path,
+                 generator_peft_model_path=a.generator_peft_model_path, passage_column_name=a.passage_column_name,
+                 query_column_name=a.query_column_name, answer_column_name=a.answer_column_name, embed_dim=a.embed_dim,
+                 max_length=a.max_length, test_batch_size=a.test_batch_size, query_batch_size=a.query_batch_size, device=a.device,
+                 torch_dtype=a.torch_dtype, top_k=a.top_k, evaluate_generator=a.evaluate_generator,
+                 retriever_is_autoregressive=a.is_retriever_autoregressive)
+
+
+if __name__ == "__main__":
+    main()

@@ -2,7 +2,6 @@
 and the hnswlib index replaced by the exact HBM-resident top-k (eval/utils.py)."""
 from __future__ import annotations
 
-import argparse
 import logging
 from argparse import Namespace
 from typing import Any, Final, Literal, Optional
@@ -20,25 +19,26 @@ from .utils import (calc_eval_results, construct_search_index, evaluate_retrieve
 logger = logging.getLogger(__name__)
 
 
+# script flags of the reference (:33-102): same names and defaults, one table
+_FLAGS = [
+    ("dataset_path", dict(type=str, default=None, required=True, help="csv file or datasets directory")),
+    ("query_column_name", dict(type=str, default="query")),
+    ("passage_column_name", dict(type=str, default="passage")),
+    ("embed_dim", dict(type=int, default=1024, help="width of the retriever's embeddings")),
+    ("max_length", dict(type=int, default=128, help="tokens per query / passage (truncated, padded)")),
+    ("retriever_name_or_path", dict(type=str, required=True)),
+    ("retriever_peft_model_path", dict(type=str, required=False, help="directory with trained retriever adapters")),
+    ("test_batch_size", dict(type=int, default=8)),
+    ("device", dict(type=str, default="cuda", help="must be a CUDA device: there is no CPU path")),
+    ("torch_dtype", dict(type=str, default="float16", help="float16 | bfloat16 (signature parity; the forward is bf16 + fp32 pooling)")),
+    ("top_k", dict(type=int, default=10)),
+    ("is_autoregressive", dict(action="store_true", help="the retriever is a causal LM")),
+]
+
+
 def parse_args() -> Namespace:
-    """reference :33-102 (same flags and defaults)"""
-    parser = argparse.ArgumentParser(description="Testing a PEFT model for Sematic Search task")
-    parser.add_argument("--dataset_path", type=str, default=None, required=True,
-                        help="dataset path in the local dir. Can be huggingface dataset directory or a csv file.")
-    parser.add_argument("--query_column_name", type=str, default="query", help="name of the query col")
-    parser.add_argument("--passage_column_name", type=str, default="passage", help="name of the passage col")
-    parser.add_argument("--embed_dim", type=int, default=1024, help="dimension of the model embedding")
-    parser.add_argument("--max_length", type=int, default=128,
-                        help="The maximum total input sequence length after tokenization. Longer sequences are truncated.")
-    parser.add_argument("--retriever_name_or_path", type=str, required=True,
-                        help="Path to pretrained retriever model or model identifier from huggingface.co/models.")
-    parser.add_argument("--retriever_peft_model_path", type=str, required=False, help="Path to the finetunned retriever peft layers")
-    parser.add_argument("--test_batch_size", type=int, default=8, help="Batch size (per device) for the test dataloader.")
-    parser.add_argument("--device", type=str, default="cuda", help="Device. cpu or cuda.")
-    parser.add_argument("--torch_dtype", type=str, default="float16", help="torch.dtype to use for tensors. float16 or bfloat16.")
-    parser.add_argument("--top_k", type=int, default=10, help="Top K retrieval")
-    parser.add_argument("--is_autoregressive", action="store_true", help="Whether the model is autoregressive or not")
-    return parser.parse_args()
+    from ..training.utils.loop import build_parser
+    return build_parser("Retriever evaluation: exact top-k search over the passage embeddings (B200-native)", _FLAGS).parse_args()
 
 
 def evaluate_retriever(

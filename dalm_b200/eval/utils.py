@@ -9,7 +9,7 @@ from it are >= the reference's for the same embeddings.
 from __future__ import annotations
 
 import logging
-from typing import Any, Callable, Dict, List, Tuple, cast
+from typing import Any, Callable, Dict, List, Tuple
 
 import numpy as np
 import torch
@@ -66,21 +66,20 @@ def construct_search_index(dim: int, num_elements: int, data: np.ndarray) -> Exa
 
 def get_nearest_neighbours(k: int, search_index: ExactIndex, query_embeddings: np.ndarray, ids_to_cat_dict: Dict[int, Any],
                            threshold: float = 0.7) -> List[List[Tuple[str, float]]]:
-    """reference :45-66"""
+    """reference :45-66: per query the (item, similarity) pairs of its k nearest rows whose similarity 1 - distance reaches
+    `threshold`, best first"""
     search_index.set_ef(100)
     labels, distances = search_index.knn_query(query_embeddings, k=k)
-    results = []
-    for i in range(len(labels)):
-        results.append([(ids_to_cat_dict[int(label)], (1 - distance))
-                        for label, distance in zip(labels[i], distances[i], strict=True) if (1 - distance) >= threshold])
-    return results
+    sims = 1 - distances
+    return [[(ids_to_cat_dict[int(row)], sim) for row, sim in zip(rows, row_sims, strict=True) if sim >= threshold]
+            for rows, row_sims in zip(labels, sims)]
 
 
 def calculate_precision_recall(retrieved_items: List, correct_items: List) -> Tuple[float, float]:
-    """reference :69-81 (an empty retrieved set divides by zero there too)"""
-    retrieved_set, correct_set = set(retrieved_items), set(correct_items)
-    correctly_retrieved = len(retrieved_set.intersection(correct_set))
-    return correctly_retrieved / len(retrieved_set), correctly_retrieved / len(correct_set)
+    """reference :69-81: set precision / recall (an empty retrieved set divides by zero there too)"""
+    got, want = frozenset(retrieved_items), frozenset(correct_items)
+    hits = len(got & want)
+    return hits / len(got), hits / len(want)
 
 
 def preprocess_function(examples, retriever_tokenizer, query_column_name: str = "query", passage_column_name: str = "passage",
@@ -105,25 +104,18 @@ def preprocess_dataset(dataset, tokenizer, query_column_name: str, passage_colum
 
 def filter_unique_passages(dataset, passage_column_name: str):
     """reference :133-143: keeps the FIRST row of every distinct passage, in dataset order"""
-    unique_passages = set(dataset[passage_column_name])
-
-    def _is_passage_unique(example: Dict[str, Any]) -> bool:
-        is_in = example[passage_column_name] in unique_passages
-        unique_passages.discard(example[passage_column_name])
-        return is_in
-
-    return dataset.filter(_is_passage_unique)
+    first_row: Dict[Any, int] = {}
+    for row, passage in enumerate(dataset[passage_column_name]):
+        first_row.setdefault(passage, row)
+    return dataset.select(sorted(first_row.values()))
 
 
 def mixed_collate_fn(batch: List[Dict[str, Any]]) -> Dict[str, Any]:
-    """reference :146-162"""
-    new_batch: Dict[str, Any] = {}
-    for key in batch[0].keys():
-        if isinstance(batch[0][key], str) or batch[0][key] is None:
-            new_batch[key] = cast(List[str], [sample[key] for sample in batch])
-        else:
-            new_batch[key] = torch.stack([torch.tensor(sample[key]) for sample in batch])
-    return new_batch
+    """reference :146-162: text (or missing) columns stay python lists, everything else is stacked into a tensor"""
+    head = batch[0]
+    is_text = {key: isinstance(value, str) or value is None for key, value in head.items()}
+    return {key: [sample[key] for sample in batch] if is_text[key] else torch.stack([torch.tensor(sample[key]) for sample in batch])
+            for key in head}
 
 
 def get_retriever_embeddings(forward_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor], device: str,
@@ -157,34 +149,33 @@ def get_passage_embeddings(passage_dataset, passage_column_name: str, forward_fn
 
 def evaluate_retriever_on_batch(batch, passage_column_name: str, forward_fn, search_index: ExactIndex, torch_dtype: torch.dtype,
                                 device: str, top_k: int, id_to_passage: Dict[int, str]):
-    """reference :223-271 -> (list[precision], list[recall], total_hit, list[top passage per query])"""
-    batch_precision, batch_recall, total_hit, top_passages = [], [], 0, []
+    """reference :223-271 -> (list[precision], list[recall], total_hit, list[top passage per query]); every query has exactly
+    one correct passage: its own row's"""
     with torch.no_grad():
         query_embeddings = get_retriever_embeddings(forward_fn, device, batch["retriever_query_input_ids"],
                                                     batch["retriever_query_attention_mask"])
-    search_results = get_nearest_neighbours(top_k, search_index, query_embeddings, id_to_passage, threshold=0.0)
-    correct_passages = batch[passage_column_name]
-    for i, result in enumerate(search_results):
-        retrieved = [passage for passage, score in result]
-        top_passages.append(retrieved[0])
-        correct = [correct_passages[i]]
-        precision, recall = calculate_precision_recall(retrieved, correct)
-        batch_precision.append(precision)
-        batch_recall.append(recall)
-        total_hit += any(p in retrieved for p in correct)
-    return batch_precision, batch_recall, total_hit, top_passages
+    neighbours = get_nearest_neighbours(top_k, search_index, query_embeddings, id_to_passage, threshold=0.0)
+    precisions, recalls, top_passages, hits = [], [], [], 0
+    for gold, found in zip(batch[passage_column_name], neighbours):
+        passages = [passage for passage, _similarity in found]
+        top_passages.append(passages[0])                        # closest match; an empty result raises IndexError as in the reference
+        p, r = calculate_precision_recall(passages, [gold])
+        precisions.append(p)
+        recalls.append(r)
+        hits += gold in passages
+    return precisions, recalls, hits, top_passages
 
 
 def calc_eval_results(total_examples: int, precisions: List[float], recalls: List[float], total_hit: int) -> EvalResults:
-    """reference :274-285"""
-    return EvalResults(total_examples=total_examples, recall=sum(recalls) / total_examples,
-                       precision=sum(precisions) / total_examples, hit_rate=total_hit / float(total_examples))
+    """reference :274-285: means over ALL examples"""
+    n = float(total_examples)
+    return EvalResults(total_examples=total_examples, recall=sum(recalls) / n, precision=sum(precisions) / n, hit_rate=total_hit / n)
 
 
 def print_eval_results(eval_results: EvalResults) -> None:
-    """reference :288-295"""
+    """reference :288-295 (same log lines)"""
+    shown = (("Recall", eval_results.recall), ("Precision", eval_results.precision), ("Hit Rate", eval_results.hit_rate))
     logger.info("Retriever results:")
-    logger.info(f"Recall: {eval_results.recall}")
-    logger.info(f"Precision: {eval_results.precision}")
-    logger.info(f"Hit Rate: {eval_results.hit_rate}")
-    logger.info("*************")
+    for label, value in shown:
+        logger.info(f"{label}: {value}")
+    logger.info("*" * 13)
