@@ -174,8 +174,5 @@ def calc_eval_results(total_examples: int, precisions: List[float], recalls: Lis
 
 def print_eval_results(eval_results: EvalResults) -> None:
     """reference :288-295 (same log lines)"""
-    shown = (("Recall", eval_results.recall), ("Precision", eval_results.precision), ("Hit Rate", eval_results.hit_rate))
-    logger.info("Retriever results:")
-    for label, value in shown:
-        logger.info(f"{label}: {value}")
-    logger.info("*" * 13)
+    for line in eval_results.log_lines():
+        logger.info(line)
