@@ -127,6 +127,27 @@ def test_attention_decode_candidate_v2(cuda_dev, monkeypatch, D, Hq, Hkv, T, cur
     assert _rel(cand.float(), base.float()) < 4e-3 and (cand.float() - base.float()).abs().max().item() < 2e-2
 
 
+@experimental
+def test_lean_graph_capture_candidate(cuda_dev, monkeypatch):
+    """DALM_B200_DECODE_GRAPH=2 (capture without torch.cuda.graph's gc / empty_cache entry, shared pool): same tokens as the
+    eager launch sequence, over two calls so that the second capture reuses the pool"""
+    from dalm_b200 import synthetic
+    from dalm_b200.engine import decoding, params
+    from dalm_b200.engine.llama import LlamaDecoder
+    cfg = synthetic.llama_config("llama-hd128", vocab_size=512)
+    sd = {k: (v.to(bf16).float() if v.dim() == 2 else v) for k, v in params.random_state_dict("llama", cfg, seed=2).items()}
+    dec = LlamaDecoder(cfg, sd, device=cuda_dev)
+    ids, mask = _prompt(4, 12, 512, seed=1)
+    gen = lambda T: dec.generate(input_ids=ids.to(cuda_dev), attention_mask=mask.to(cuda_dev), max_length=T, eos_token_id=[], pad_token_id=0).cpu()
+    monkeypatch.setenv("DALM_B200_DECODE_GRAPH", "0")
+    want34, want40 = gen(34), gen(40)
+    monkeypatch.setenv("DALM_B200_DECODE_GRAPH", "2")
+    got34 = gen(34)
+    assert decoding.LAST_RUN["graph_replays"] >= 18
+    got40 = gen(40)
+    assert torch.equal(got34, want34) and torch.equal(got40, want40)
+
+
 @pytest.mark.parametrize("M,N,K", [(16, 4096, 4096), (5, 24, 72), (1, 8, 8), (13, 1000, 1048), (16, 512, 11008), (3, 32008, 256)])
 def test_decode_gemm(cuda_dev, M, N, K):
     """weight-streaming GEMM of the decode step (M <= 16 rows) vs torch fp32, every epilogue; ragged N, K tails (K % 32 != 0),
