@@ -36,6 +36,9 @@ def parse():
     ap.add_argument("--retriever", type=str, default="bge-large-en")
     ap.add_argument("--generator", type=str, default="Llama-2-7b-hf")
     ap.add_argument("--cpu-baseline", type=int, default=1, help="0 to skip the bounded CPU-oracle timing on rank 0")
+    ap.add_argument("--gpu-eager-baseline", type=int, default=1, help="0 to skip the same-box HF-eager GPU baseline (rank 0, N=1)")
+    ap.add_argument("--ref-rows", type=int, default=2, help="rows per step of the bounded CPU sample (reference arm / cpu_baseline)")
+    ap.add_argument("--ref-budget-s", type=float, default=200.0, help="wall-clock budget of the reference arm's step loop")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step's launch sequence as one CUDA graph (default); 0: eager launches")
     return ap.parse_args()
 
@@ -104,61 +107,99 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle (reference loss code + HF modeling on CPU fp32) on a bounded sample of the same workload
+# CPU baseline / reference arm: the oracle (reference loss code + HF modeling code, fp32, eager PyTorch on the host cores)
+# at FULL depth (24 + 32 layers) and full widths / sequence lengths; the bound is on ROWS per step, nothing is extrapolated
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_samples_per_s(batch, steps: int = 1, rows: int = 6):
-    """Times the oracle's train step (reference loss code + HF modeling code, fp32, all host threads) on a BOUNDED sample
-    of the workload: the first `rows` samples of a bs-18 batch at the real widths and sequence lengths, with truncated
-    depth at three (encoder, decoder) settings; the per-layer and fixed costs identified from the three timings are
-    extrapolated linearly to the full 24 + 32 layers. samples/s = rows / extrapolated step time.
-    Returns (samples_per_s, cores, description)."""
+def cpu_reference_run(batch, rows: int, warmup: int, steps: int, budget_s: float):
+    """Runs the reference's loop body (train_rage2e.py:429-474: forwards, losses, backward, Adam step) on the host cores with
+    the complete bge-large + Llama-2-7B modules (LoRA r=8 on the reference's targets, train() mode, fp32 = the reference's
+    default precision) on the first `rows` samples of a bs-18 batch. `warmup` untimed + up to `steps` timed steps, stopping
+    early when `budget_s` of wall clock is spent (at least one timed step). Every reported step was really executed.
+    -> dict(value samples/s, cores, steps_run, warmup_run, s_per_step, sample)"""
     import torch
     from dalm_b200 import synthetic
-    from dalm_b200.engine import params
     from oracle import models as om
 
     # torch's CPU GEMMs stop scaling (and regress badly) long before 128 threads on these hosts: measured 0.013 samples/s
     # with 128 threads vs 0.157 with 8; use up to 32 threads and report that count as `cores`
     cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
-    bcfg = dict(synthetic.bert_config("bge-large-en")); lcfg = dict(synthetic.llama_config("Llama-2-7b-hf"))
+    t_build = time.perf_counter()
+    bcfg, lcfg = synthetic.bert_config("bge-large-en"), synthetic.llama_config("Llama-2-7b-hf")
+    bert, llama = om.build_for_timing("bert", bcfg), om.build_for_timing("llama", lcfg)
+    om.attach_lora(bert, om.timing_lora_factors("bert", bcfg), dropout=0.05)
+    om.attach_lora(llama, om.timing_lora_factors("llama", lcfg), dropout=0.05)
+    bert.train(); llama.train()
+    opt = torch.optim.Adam([p for m in (bert, llama) for p in m.parameters() if p.requires_grad], lr=1e-4)
     batch = {k: v[:rows].clone() for k, v in batch.items()}
-
-    def build(nb, nd):
-        b = dict(bcfg, num_hidden_layers=nb); l = dict(lcfg, num_hidden_layers=nd)
-        bert = om.build_bert(b, params.random_state_dict("bert", b, seed=1))
-        llama = om.build_llama(l, params.random_state_dict("llama", l, seed=2))
-        g = torch.Generator().manual_seed(3)
-        fb = {f"encoder.layer.{i}.attention.self.{n}": {"A": torch.randn(8, 1024, generator=g) * 0.03, "B": torch.zeros(1024, 8)}
-              for i in range(nb) for n in ("query", "key", "value")}
-        fl = {f"model.layers.{i}.self_attn.{n}": {"A": torch.randn(8, 4096, generator=g) * 0.015, "B": torch.zeros(4096, 8)}
-              for i in range(nd) for n in ("q_proj", "v_proj")}
-        om.attach_lora(bert, fb); om.attach_lora(llama, fl)
-        return bert, llama
-
-    def time_step(bert, llama, warm):
-        if warm:
-            om.rag_step(bert, llama, batch)                 # warm-up (allocator, thread pool)
+    t_build = time.perf_counter() - t_build
+    t_start = time.perf_counter()
+    warm_run = 0
+    for _ in range(max(warmup, 0)):
+        if warm_run >= 1 and time.perf_counter() - t_start > 0.3 * budget_s:
+            break
+        om.loop_body_step(bert, llama, batch, opt)
+        warm_run += 1
+    times = []
+    for _ in range(max(steps, 1)):
         t0 = time.perf_counter()
-        for _ in range(steps):
-            om.rag_step(bert, llama, batch)
-        return (time.perf_counter() - t0) / steps
+        om.loop_body_step(bert, llama, batch, opt)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    per = sum(times) / len(times)
+    desc = (f"MEASURED, nothing extrapolated: reference loop body (oracle: reference loss code + HF BertModel 24 layers + "
+            f"LlamaForCausalLM 32 layers, fp32, LoRA r=8 + dropout, torch.optim.Adam; {cores} threads) on the first {rows} rows "
+            f"of a bs-{BS} batch at Lq/Lp/Lg={LQ}/{LP}/{LG}: {warm_run} warm-up + {len(times)} timed steps of {per:.2f} s "
+            f"(min {min(times):.2f}, max {max(times):.2f}); model build {t_build:.0f} s outside the timed region; "
+            f"samples/s = {rows} / {per:.2f}")
+    del bert, llama, opt
+    return {"value": rows / per, "cores": cores, "steps_run": len(times), "warmup_run": warm_run, "s_per_step": per,
+            "rows": rows, "sample": desc}
 
-    # t(ne, nd) = fixed + ne * e + nd * d : three depth settings identify the three terms
-    times = {}
-    for i, (ne, nd) in enumerate(((1, 1), (1, 2), (3, 2))):
-        bert, llama = build(ne, nd)
-        times[(ne, nd)] = time_step(bert, llama, warm=False)
-        del bert, llama
-    d = max(times[(1, 2)] - times[(1, 1)], 1e-9)
-    e = max((times[(3, 2)] - times[(1, 2)]) / 2.0, 0.0)
-    fixed = max(times[(1, 1)] - e - d, 0.0)
-    full = fixed + 24 * e + 32 * d
-    desc = (f"oracle (reference loss code + HF BertModel/LlamaForCausalLM, fp32, LoRA r=8, {cores} threads) on the first {rows} "
-            f"rows of a bs-{BS} batch at full widths and Lq/Lp/Lg={LQ}/{LP}/{LG}; one timed step each at (encoder,decoder) depths "
-            f"(1,1),(1,2),(3,2): {times[(1,1)]:.2f}s/{times[(1,2)]:.2f}s/{times[(3,2)]:.2f}s -> per-layer {e:.3f}s/{d:.3f}s + fixed "
-            f"{fixed:.2f}s, extrapolated linearly to 24+32 layers = {full:.1f}s per {rows}-sample step")
-    return rows / full, cores, desc
+
+# ----------------------------------------------------------------------------------------------------------------
+# same-box GPU baseline (SURVEY §8d-ii, BASELINE.md §3 row 2): the reference's loop body over HF modules + LoRA in eager
+# PyTorch on THIS B200 - no dalm_b200 kernel on its path
+# ----------------------------------------------------------------------------------------------------------------
+def gpu_eager_baseline(dev, host_batches, warmup: int = 5, steps: int = 20):
+    import torch
+    from dalm_b200 import synthetic
+    from oracle import models as om
+
+    bcfg, lcfg = synthetic.bert_config("bge-large-en"), synthetic.llama_config("Llama-2-7b-hf")
+    bert, llama = om.build_for_timing("bert", bcfg, device=dev), om.build_for_timing("llama", lcfg, device=dev)
+    om.attach_lora(bert, om.timing_lora_factors("bert", bcfg, device=dev), dropout=0.05)
+    om.attach_lora(llama, om.timing_lora_factors("llama", lcfg, device=dev), dropout=0.05)
+    bert.train(); llama.train()
+    opt = torch.optim.Adam([p for m in (bert, llama) for p in m.parameters() if p.requires_grad], lr=1e-4)
+    batches = [{k: v.to(dev) for k, v in b.items()} for b in host_batches]
+
+    def run(autocast, w, k):
+        for i in range(w):
+            om.loop_body_step(bert, llama, batches[i % len(batches)], opt, autocast=autocast)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            loss = om.loop_body_step(bert, llama, batches[(w + i) % len(batches)], opt, autocast=autocast)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k, float(loss.item())
+
+    out = {"unit": "samples/s", "what": "reference loop body (train_rage2e.py:429-474) in eager PyTorch on this B200: HF BertModel "
+           "(24 layers) + LlamaForCausalLM (32 layers), fp32 master weights, LoRA r=8 restatement (peft absent offline) + dropout, "
+           "torch.optim.Adam, SDPA attention as transformers selects it; same synthetic batches; CUDA events; no dalm_b200 kernel"}
+    ms, loss = run(torch.bfloat16, warmup, steps)
+    out.update({"value": BS / (ms * 1e-3), "ms_per_step": ms, "precision": "bf16 autocast (accelerate --mixed_precision bf16)",
+                "warmup": warmup, "steps": steps, "loss_last": loss})
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ms32, _ = run(None, 1, 3)                              # the reference's literal default: no mixed precision, fp32 matmuls
+    out["fp32_default"] = {"value": BS / (ms32 * 1e-3), "ms_per_step": ms32, "warmup": 1, "steps": 3,
+                           "precision": "fp32, TF32 off (accelerate default: no mixed precision)"}
+    del bert, llama, opt, batches
+    torch.cuda.empty_cache()
+    return out
 
 
 def ncu_traffic():
@@ -200,19 +241,24 @@ def main():
     os.makedirs(cache_dir, exist_ok=True)
 
     if args.impl == "reference":
-        # the reference's own CPU implementation of the path (oracle port): rank 0 only
+        # the reference's own CPU implementation of the path (oracle port) on the host cores: rank 0 only. Each step is a
+        # BOUNDED SAMPLE of the workload (the first REF_ROWS rows of a bs-18 batch through the full-depth models); every step
+        # reported was executed and timed; if --steps does not fit the time budget fewer are run and `steps` says how many.
         if rank != 0:
             return
         batch = make_batches(1, 0, 1, cache_dir)[0]
-        v, cores, desc = cpu_reference_samples_per_s(batch, steps=max(1, min(args.steps, 1)))
-        line = {"metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": BS / v * 1e3, "higher_is_better": True, "scaling": "weak",
+        r = cpu_reference_run(batch, rows=args.ref_rows, warmup=args.warmup, steps=args.steps, budget_s=args.ref_budget_s)
+        v = r["value"]
+        line = {"metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": r["steps_run"],
+                "warmup": r["warmup_run"], "steps_requested": args.steps, "warmup_requested": args.warmup,
+                "ms_per_step": r["s_per_step"] * 1e3, "rows_per_step": r["rows"], "extrapolated": False,
+                "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": v / 7.94, "dtype": "f32", "data": "synthetic", "impl": "reference",
                 "config": {"workload": workload_name(args), "global_batch": BS * max(1, args.gpus),
                            "parallelism": "cpu (rank 0 host cores; the other ranks exit)",
                            "dataset": "first rows of the synthetic 200k-row (Abstract,Question,Answer) 'full' set (all sequences truncated)",
-                           "weights": "seeded random-init (no checkpoints offline)"},
-                "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc},
+                           "weights": "random (tiled N(0,0.02) block; timing only, no checkpoints offline)"},
+                "cpu_baseline": {"value": v, "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
                 "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line), flush=True)
@@ -250,6 +296,9 @@ def main():
     resident = [{k: v.to(dev) for k, v in b.items()} for b in host_batches]
     h2d_bytes = sum(v.numel() * v.element_size() for v in host_batches[0].values())
 
+    # the data-parallel reducer re-homes the LoRA gradient buffers into one arena: build it before the graph capture
+    from dalm_b200.accel import GradientSync
+    sync = GradientSync(banks, world, dev, nccl=True)
     graphed = None
     if args.graph:
         try:
@@ -258,15 +307,23 @@ def main():
             if rank == 0:
                 print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); eager launches", file=sys.stderr, flush=True)
 
-    def train_step(batch, eager=False):
+    rank_ev = []                                             # (start, compute done, step done) events of the timed steps
+
+    def train_step(batch, eager=False, record=False):
+        if record:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
         out = graphed(batch) if (graphed is not None and not eager) else fused_rag_step(model, batch, 100.0, backward=True)
-        if world > 1:
-            for b in banks:
-                dist.all_reduce(b.grad, op=dist.ReduceOp.AVG)
+        if record:
+            ev[1].record()
+        loss = sync.reduce(out["loss"])                      # ONE all-reduce: both LoRA banks' gradients (mean) + the loss (rank sum)
         opt.step()
         model.repack()
         opt.zero_grad()
-        return out["loss"]
+        if record:
+            ev[2].record()
+            rank_ev.append(ev)
+        return loss
 
     def sync_all():
         if world > 1:
@@ -285,7 +342,7 @@ def main():
         e0.record()
         loss = None
         for i in range(args.steps):
-            loss = train_step(batches[args.warmup + i], eager)
+            loss = train_step(batches[args.warmup + i], eager, record=(use_timer is None and world > 1))
         e1.record()
         sync_all()
         ops.GEMM_TIMER = None
@@ -301,6 +358,7 @@ def main():
     if sampler:
         sampler.start()
     total_ms, loss, launches = timed(resident, None if graphed is not None else timer)
+    coll_per_step = sync.collectives / (args.warmup + args.steps) if world > 1 else 0
     if sampler:
         sampler.stop_flag = True
     eager_ms = total_ms
@@ -336,6 +394,17 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item(), last
     e2e_ms, e2e_loss = e2e_run()
+
+    # per-rank step anatomy (N > 1): device time of the step's own compute vs. everything after it (collective incl. the wait
+    # for the slowest rank, Adam, repack) - names what the weak-scaling loss is made of
+    per_rank = None
+    if world > 1 and rank_ev:
+        comp = sum(e[0].elapsed_time(e[1]) for e in rank_ev) / len(rank_ev)
+        rest = sum(e[1].elapsed_time(e[2]) for e in rank_ev) / len(rank_ev)
+        t = torch.tensor([comp, rest], device=dev)
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [{"rank": i, "compute_ms": round(x[0].item(), 3), "reduce_wait_adam_ms": round(x[1].item(), 3)} for i, x in enumerate(allt)]
 
     if rank != 0:
         if world > 1:
@@ -377,10 +446,24 @@ def main():
                      "note": "achieved = sum of 2MNK over all GEMM launches / sum of their CUDA-event durations in the timed region"},
         "clocks": sampler.summary() if sampler else None,
     }
+    if per_rank is not None:
+        cm = [r["compute_ms"] for r in per_rank]
+        line["per_rank"] = per_rank
+        line["scaling_note"] = (f"step = max over ranks every step (the all-reduce is a barrier): slowest rank's own compute "
+                                f"{max(cm):.2f} ms vs fastest {min(cm):.2f} ms; {coll_per_step:g} collective(s) per step "
+                                f"({sync.arena.numel() * 4 / 1e6:.1f} MB: both LoRA banks + loss scalar in one all-reduce)")
+    if world == 1 and args.gpu_eager_baseline:               # same-box eager-PyTorch comparator (rank 0, N=1 only)
+        try:
+            graphed = None
+            torch.cuda.empty_cache()
+            line["gpu_eager_baseline"] = gpu_eager_baseline(dev, host_batches[:8])
+        except Exception as e:
+            line["gpu_eager_baseline"] = {"value": None, "unit": "samples/s", "what": f"failed: {type(e).__name__}: {e}"}
     if args.cpu_baseline and world == 1:                     # reported CPU baseline: rank 0, N=1 only
         try:
-            v, cores, desc = cpu_reference_samples_per_s(host_batches[0])
-            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc}
+            r = cpu_reference_run(host_batches[0], rows=args.ref_rows, warmup=1, steps=2, budget_s=30.0)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                                    "sample": r["sample"], "extrapolated": False}
         except Exception as e:                                   # never lose the GPU line to a host-side problem
             line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {type(e).__name__}: {e}"}

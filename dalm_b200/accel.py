@@ -44,44 +44,28 @@ def get_logger(name: str) -> _RankLogger:
     return _RankLogger(logging.getLogger(name), {})
 
 
-class ShardedLoader:
-    """Per-rank view of a DataLoader, batch-strided like accelerate's BatchSamplerShard(split_batches=False,
-    even_batches=True): rank r consumes global batches r, r+W, r+2W, ...; a short final round is completed by
-    wrapping around to the first batches so every rank runs the same number of steps."""
+class _BatchSamplerShard:
+    """Rank r's share of a batch sampler, batch-strided like accelerate's BatchSamplerShard(split_batches=False,
+    even_batches=True): global batches r, r+W, r+2W, ...; a short final round is completed by wrapping around to the first
+    batches so every rank runs the same number of steps. Only INDEX lists are walked for the other ranks' batches - no
+    sample of theirs is fetched or collated (every rank draws the same permutation from the shared, equally-seeded generator)."""
 
-    def __init__(self, loader, rank: int, world: int, skip: int = 0):
-        self.loader, self.rank, self.world, self.skip = loader, rank, world, skip
-        self.end_of_dataloader = False
+    def __init__(self, batch_sampler, rank: int, world: int, skip: int = 0):
+        self.batch_sampler, self.rank, self.world, self.skip = batch_sampler, rank, world, skip
 
     def __len__(self) -> int:
-        n = len(self.loader)
-        return (n + self.world - 1) // self.world - self.skip
-
-    def set_epoch(self, epoch: int) -> None:
-        gen = getattr(self.loader, "generator", None)
-        if gen is not None and hasattr(self, "_base_seed"):
-            gen.manual_seed(self._base_seed + epoch)
+        return max((len(self.batch_sampler) + self.world - 1) // self.world - self.skip, 0)
 
     def __iter__(self):
-        self.end_of_dataloader = False
-        total = len(self)
-        if self.world == 1:
-            for i, b in enumerate(self.loader):
-                if i < self.skip:
-                    continue
-                self.end_of_dataloader = (i - self.skip) == total - 1
-                yield b
-            return
         first: List[Any] = []
         group: List[Any] = []
         emitted = 0
-        for b in self.loader:
+        for idx in self.batch_sampler:
             if len(first) < self.world:
-                first.append(b)
-            group.append(b)
+                first.append(idx)
+            group.append(idx)
             if len(group) == self.world:
                 if emitted >= self.skip:
-                    self.end_of_dataloader = (emitted - self.skip) == total - 1
                     yield group[self.rank]
                 emitted += 1
                 group = []
@@ -90,8 +74,90 @@ class ShardedLoader:
             while len(group) < self.world:
                 group.append(first[pad % len(first)])
                 pad += 1
-            self.end_of_dataloader = True
-            yield group[self.rank]
+            if emitted >= self.skip:
+                yield group[self.rank]
+
+
+class ShardedLoader:
+    """Per-rank view of a DataLoader (accelerate's `prepare(dataloader)`): the same dataset / collate_fn / pinning behind a
+    `_BatchSamplerShard`, so a rank only materialises its own batches. `end_of_dataloader` is True while the last batch of
+    an epoch is being consumed (what `Accelerator.accumulate` needs to force a gradient sync there)."""
+
+    def __init__(self, loader, rank: int, world: int, skip: int = 0):
+        self.loader, self.rank, self.world, self.skip = loader, rank, world, skip
+        self.end_of_dataloader = False
+        self.shard = _BatchSamplerShard(loader.batch_sampler, rank, world, skip)
+        self._inner = torch.utils.data.DataLoader(loader.dataset, batch_sampler=self.shard, collate_fn=loader.collate_fn,
+                                                  num_workers=loader.num_workers, pin_memory=loader.pin_memory)
+
+    def __len__(self) -> int:
+        return len(self.shard)
+
+    def __iter__(self):
+        self.end_of_dataloader = False
+        total = len(self)
+        for i, b in enumerate(self._inner):
+            self.end_of_dataloader = i == total - 1
+            yield b
+
+
+class GradientSync:
+    """The data-parallel exchange of one optimizer step as ONE collective. The reference gets it implicitly:
+    DDP averages the gradients (train_rage2e.py:416-418,471) and `accelerator.reduce(loss, "sum")` sums the scalar loss
+    (:469) - two or more NCCL calls per step. Here every small trainable bank (the LoRA banks: 1.18 M + 4.19 M floats at
+    cfg-3) has its flat gradient buffer RE-HOMED into one fp32 arena
+
+        arena = [ bank_0.grad | bank_1.grad | ... | loss slot ]
+
+    and `reduce(loss)` issues a single all-reduce(AVG) over it; the loss slot is pre-multiplied by the world size so that
+    its average IS the rank sum the reference logs. Banks too large to copy around (a fully fine-tuned model's fp32 gradient
+    bank: 27 GB at 7 B) stay where they are and are averaged in place, in buckets (see `reduce_large`).
+    Build it BEFORE a step is captured into a CUDA graph: re-homing changes the kernels' output pointers."""
+
+    ARENA_LIMIT = 64 << 20        # floats per bank (256 MB): anything larger is a dense bank and is reduced in place
+
+    def __init__(self, banks, world: int, device, nccl: bool):
+        self.world, self.nccl, self.grad_scale = world, nccl, 1.0
+        self.small = [b for b in banks if hasattr(b, "rebind_grad") and b.grad.numel() <= self.ARENA_LIMIT]
+        self.large = [b for b in banks if b not in self.small]
+        pad = lambda n: (n + 63) // 64 * 64
+        total = sum(pad(b.grad.numel()) for b in self.small) + 64
+        self.arena = torch.zeros(total, dtype=torch.float32, device=device)
+        off = 0
+        if world > 1:                                          # single-process runs keep their buffers: nothing to exchange
+            for b in self.small:
+                n = b.grad.numel()
+                b.rebind_grad(self.arena[off:off + n])
+                off += pad(n)
+        self.loss_slot = self.arena[total - 64:total - 63]
+        self.collectives = 0                                   # issued so far (bench / tests read it)
+
+    def _avg(self, t: torch.Tensor) -> None:
+        if self.nccl:
+            dist.all_reduce(t, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t.div_(self.world)
+        self.collectives += 1
+
+    def reduce_large(self) -> None:
+        for b in self.large:
+            buckets = getattr(b, "reduce_buckets", None)
+            if buckets is None:
+                self._avg(b.grad)
+            else:
+                for lo, hi in buckets():
+                    self._avg(b.grad[lo:hi])
+
+    def reduce(self, loss: torch.Tensor) -> torch.Tensor:
+        """average every bank's gradients over the ranks and return the rank-SUMMED loss (0-d fp32 view into the arena,
+        stream-ordered like any other tensor)"""
+        if self.world == 1:
+            return loss
+        torch.mul(loss.detach().reshape(1).float(), float(self.world), out=self.loss_slot)
+        self._avg(self.arena)
+        self.reduce_large()
+        return self.loss_slot[0]
 
 
 class _SchedulerWrapper:
@@ -217,6 +283,11 @@ class Accelerator:
             else:
                 dist.all_reduce(g, op=dist.ReduceOp.SUM)
                 g.div_(self.num_processes)
+
+    def gradient_sync(self, banks) -> GradientSync:
+        """the step's single-collective reducer over the given trainable banks (see GradientSync)"""
+        nccl = self.num_processes > 1 and dist.get_backend() == "nccl"
+        return GradientSync(list(banks), self.num_processes, self.device, nccl)
 
     def reduce(self, tensor: torch.Tensor, reduction: str = "sum") -> torch.Tensor:
         if self.num_processes == 1:

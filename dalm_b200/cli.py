@@ -68,8 +68,8 @@ def train_rag_e2e(
     report_to: Annotated[str, Opt(help="tracker selection")] = "all",
     sanity_test: Annotated[bool, Opt(help="accepted, unused")] = True,
     use_peft: Annotated[Optional[PeftMode], Opt(help="which sub-models get LoRA adapters")] = None,
-    use_bnb: Annotated[Optional[PeftMode], Opt(help="NF4 quantisation (not built)")] = None,
-    retriever_is_autoregressive: Annotated[bool, Opt(help="autoregressive retriever (not built)")] = False,
+    use_bnb: Annotated[Optional[PeftMode], Opt(help="NF4 values for the named sub-models' Linear weights (bitsandbytes nf4 round trip at load; needs the same sub-model in --use-peft)")] = None,
+    retriever_is_autoregressive: Annotated[bool, Opt(help="the retriever is a causal LM (Llama family): last hidden state, eos pooling, q_proj/v_proj adapters")] = False,
 ) -> None:
     """End-to-end train an in-domain model, including the retriever and generator"""
     from transformers import SchedulerType
@@ -114,8 +114,8 @@ def train_retriever_only(
     report_to: Annotated[str, Opt(help="tracker selection")] = "all",
     sanity_test: Annotated[bool, Opt(help="accepted, unused")] = True,
     use_peft: Annotated[bool, Opt(help="train LoRA adapters")] = True,
-    use_bnb: Annotated[bool, Opt(help="NF4 quantisation (not built: runs bf16)")] = True,
-    is_autoregressive: Annotated[bool, Opt(help="autoregressive retriever (not built)")] = False,
+    use_bnb: Annotated[bool, Opt(help="NF4 values for the Linear weights (bitsandbytes nf4 round trip at load, bf16 storage; applies with --use-peft)")] = True,
+    is_autoregressive: Annotated[bool, Opt(help="the retriever is a causal LM (Llama family): last hidden state, eos pooling")] = False,
 ) -> None:
     """Train only the retriever using contrastive training"""
     from transformers import SchedulerType

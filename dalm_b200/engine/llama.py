@@ -86,6 +86,7 @@ class LlamaDecoder(torch.nn.Module):
             self.lora = LoraBank(specs, r=self.r, alpha=16, dropout=0.05, device=self.dev, seed=lora_seed)
             self.lora_flat = torch.nn.Parameter(self.lora.flat, requires_grad=True)
             self.lora_flat.grad = self.lora.grad
+            self.lora.param = self.lora_flat
             self.repack_lora()
         self.eval()                                           # like from_pretrained(): dropout only after .train()
 
@@ -196,6 +197,7 @@ class LlamaDecoder(torch.nn.Module):
         self.lora = LoraBank(specs, r=r, alpha=16, dropout=0.05, device=self.dev, seed=lora_seed)
         self.lora_flat = torch.nn.Parameter(self.lora.flat, requires_grad=True)
         self.lora_flat.grad = self.lora.grad
+        self.lora.param = self.lora_flat
         self.p_lora = 0.05
         self._pack_tab = None
         self.repack_lora()

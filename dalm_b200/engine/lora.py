@@ -16,6 +16,7 @@ class LoraBank:
         self.r, self.alpha, self.dropout = r, alpha, dropout
         self.scale = alpha / r
         self.specs = specs
+        self.param = None                 # the nn.Parameter over `flat` (set by the engine model): its .grad follows rebind_grad
         total = sum(r * i + o * r for _, i, o in specs)
         self.flat = torch.zeros(total, dtype=torch.float32, device=device)
         self.grad = torch.zeros(total, dtype=torch.float32, device=device)
@@ -38,6 +39,23 @@ class LoraBank:
 
     def numel(self) -> int:
         return self.flat.numel()
+
+    def rebind_grad(self, buf: torch.Tensor) -> None:
+        """move the flat gradient buffer (and its per-adapter views) into `buf` — a slice of the data-parallel gradient
+        arena, so that all trainable banks + the loss scalar are ONE contiguous all-reduce (accel.GradientSync). Must happen
+        before a step is captured into a CUDA graph (the kernels' output pointers change)."""
+        if buf.numel() != self.grad.numel() or buf.dtype != self.grad.dtype or not buf.is_contiguous():
+            raise ValueError("rebind_grad: buffer must be a contiguous fp32 tensor of the bank's size")
+        buf.copy_(self.grad)
+        self.grad = buf
+        off, r = 0, self.r
+        for name, fin, fout in self.specs:
+            self.gA[name] = buf[off:off + r * fin].view(r, fin)
+            off += r * fin
+            self.gB[name] = buf[off:off + fout * r].view(fout, r)
+            off += fout * r
+        if self.param is not None:
+            self.param.grad = buf
 
     def zero_grad(self) -> None:
         self.grad.zero_()

@@ -73,11 +73,17 @@ def build_encoder(name_or_path: str, lora: bool, device: torch.device, state_dic
     if autoregressive:
         if kind != "llama":
             raise NotImplementedError("autoregressive retrievers are built for Llama-family models only")
-        return LlamaDecoder(cfg, sd, device=device, lora=lora, lora_seed=0, full=full)
+        return _named(LlamaDecoder(cfg, sd, device=device, lora=lora, lora_seed=0, full=full), name_or_path)
     if kind != "bert":
         raise NotImplementedError("non-autoregressive retrievers must be BERT-family encoders (bge-*); pass "
                                   "retriever_is_autoregressive=True for a causal LM")
-    return BertEncoder(cfg, sd, device=device, lora=lora, full=full)
+    return _named(BertEncoder(cfg, sd, device=device, lora=lora, full=full), name_or_path)
+
+
+def _named(engine_model, name_or_path: str):
+    """remember where the base weights came from: written as `base_model_name_or_path` into adapter_config.json"""
+    engine_model.name_or_path = name_or_path or None
+    return engine_model
 
 
 def _maybe_bnb(sd: Dict, bnb: bool, full: bool, device) -> Dict:
@@ -106,10 +112,10 @@ def build_decoder(name_or_path: str, lora: bool, device: torch.device, state_dic
     sd = state_dict if state_dict is not None else params.load_state_dict(name_or_path)
     sd = _maybe_bnb(sd, bnb, full, device)
     if kind == "falcon":
-        return FalconDecoder(cfg, sd, device=device, lora=lora, full=full)   # raises for lora=True, like peft would
+        return _named(FalconDecoder(cfg, sd, device=device, lora=lora, full=full), name_or_path)   # raises for lora=True, like peft would
     if kind != "llama":
         raise NotImplementedError(f"generator of kind {kind!r} is not a causal decoder")
-    return LlamaDecoder(cfg, sd, device=device, lora=lora, full=full)
+    return _named(LlamaDecoder(cfg, sd, device=device, lora=lora, full=full), name_or_path)
 
 
 class AutoModelForRagE2E(torch.nn.Module):

@@ -53,6 +53,15 @@ def parse_resume(path: str, steps_per_epoch: int, loader_len: int, gas: int) -> 
     return start, resume, resume // gas
 
 
+def plan_schedule(unsharded_loader_len: int, gas: int, num_train_epochs: int, max_train_steps: Optional[int]) -> Tuple[int, int]:
+    """(max_train_steps, num_train_epochs) exactly as the reference derives them (train_rage2e.py:339-357) - from the loader
+    length BEFORE accelerator.prepare shards it, so the epoch count does not depend on the number of ranks"""
+    steps_per_epoch = math.ceil(unsharded_loader_len / gas)
+    if max_train_steps is None:
+        max_train_steps = num_train_epochs * steps_per_epoch
+    return max_train_steps, math.ceil(max_train_steps / steps_per_epoch)
+
+
 def run_training(recipe: Recipe, *, dataset_or_path: Any, per_device_train_batch_size: int, learning_rate: float,
                  logit_scale: float, num_train_epochs: int, max_train_steps: Optional[int],
                  gradient_accumulation_steps: int, lr_scheduler_type: Any, num_warmup_steps: int,
@@ -86,15 +95,16 @@ def run_training(recipe: Recipe, *, dataset_or_path: Any, per_device_train_batch
                         pin_memory=torch.cuda.is_available(), generator=gen)
 
     optimizer = FusedAdam(model.parameters(), lr=learning_rate)     # Adam, no weight decay (reference ignores the flag)
-    steps_per_epoch = math.ceil(len(loader) / gradient_accumulation_steps)
-    if max_train_steps is None:
-        max_train_steps = num_train_epochs * steps_per_epoch
+    max_train_steps, num_train_epochs = plan_schedule(len(loader), gradient_accumulation_steps, num_train_epochs, max_train_steps)
     sched_name = getattr(lr_scheduler_type, "value", lr_scheduler_type)
     scheduler = get_scheduler(name=sched_name, optimizer=optimizer, num_warmup_steps=num_warmup_steps,
                               num_training_steps=max_train_steps)
+    # The reference does all of its step / epoch arithmetic BEFORE accelerator.prepare (train_rage2e.py:339-357 vs :416):
+    # the epoch count comes from the UNSHARDED loader length, so `num_train_epochs=E` means E passes over the data on any
+    # number of ranks (each pass len/W optimizer steps per rank, the wrapped scheduler stepping W times per update so the LR
+    # schedule still ends with the last epoch); `max_train_steps` keeps its unsharded value as the early-stop bound.
     model, optimizer, loader, scheduler = accelerator.prepare(model, optimizer, loader, scheduler)
-    steps_per_epoch = math.ceil(len(loader) / gradient_accumulation_steps)
-    num_train_epochs = math.ceil(max_train_steps / steps_per_epoch)
+    steps_per_epoch = math.ceil(len(loader) / gradient_accumulation_steps)       # per rank: resume arithmetic, logging
     if checkpointing_steps is not None and str(checkpointing_steps).isdigit():
         checkpointing_steps = int(checkpointing_steps)
     if with_tracking:
@@ -122,6 +132,7 @@ def run_training(recipe: Recipe, *, dataset_or_path: Any, per_device_train_batch
     progress.update(completed)
 
     banks = recipe.banks(model)
+    sync = accelerator.gradient_sync(banks)        # ONE collective per optimizer step: both banks' gradients + the loss scalar
     last_loss = None
     use_graph = os.environ.get("DALM_B200_CUDA_GRAPH", "1") != "0" and torch.cuda.is_available()
     graphed = None
@@ -131,7 +142,7 @@ def run_training(recipe: Recipe, *, dataset_or_path: Any, per_device_train_batch
         active = loader
         if resume_from_checkpoint and epoch == start_epoch and resume_step is not None:
             active = accelerator.skip_first_batches(loader, resume_step)
-            accelerator._loader = active
+        accelerator._loader = active                # `accumulate` reads end_of_dataloader from the loader being iterated
         for step, batch in enumerate(active):
             with accelerator.accumulate(model):
                 if use_graph and graphed is None:
@@ -144,8 +155,10 @@ def run_training(recipe: Recipe, *, dataset_or_path: Any, per_device_train_batch
                         use_graph = False
                 out = (graphed(batch) if graphed is not None else
                        recipe.step(model, batch, float(logit_scale), 1.0 / gradient_accumulation_steps))
-                total_loss += accelerator.reduce(out["loss"].detach().float(), reduction="sum")   # rank-SUM (reference :469)
-                accelerator.average_gradients(b.grad for b in banks)
+                if accelerator.sync_gradients:                  # gradients averaged + loss rank-SUMMED (reference :469) in one all-reduce
+                    total_loss += sync.reduce(out["loss"])
+                else:                                           # accumulating micro-step: only the logged loss crosses ranks
+                    total_loss += accelerator.reduce(out["loss"].detach().float(), reduction="sum")
                 if accelerator.sync_gradients:
                     optimizer.step()
                     recipe.repack(model)

@@ -315,8 +315,10 @@ def save_adapter_dir(engine_model, out_dir: str, task_type: str, base_name: Opti
         return
     if engine_model.lora is None:
         return
-    cfg = dict(ADAPTER_CONFIG, task_type=task_type, target_modules=list(engine_model.LORA_TARGETS),
-               base_model_name_or_path=base_name)
+    bank = engine_model.lora
+    cfg = dict(ADAPTER_CONFIG, r=int(bank.r), lora_alpha=int(bank.alpha), lora_dropout=float(bank.dropout),
+               task_type=task_type, target_modules=list(engine_model.LORA_TARGETS),
+               base_model_name_or_path=base_name if base_name is not None else getattr(engine_model, "name_or_path", None))
     with open(os.path.join(out_dir, "adapter_config.json"), "w") as f:
         json.dump(cfg, f, indent=1)
     torch.save(engine_model.lora.peft_state_dict(), os.path.join(out_dir, "adapter_model.bin"))

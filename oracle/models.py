@@ -131,3 +131,70 @@ def retriever_step(bert: nn.Module, batch: Dict[str, torch.Tensor], logit_scale:
     loss.backward()
     grads = {"retriever." + n: p_.grad.detach().clone() for n, p_ in bert.named_parameters() if p_.grad is not None}
     return {"loss": loss.detach(), "q": q.detach(), "p": p.detach(), "S": S.detach(), "grads": grads}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# timing support for bench.py's baselines (cpu_baseline / --impl reference on host cores, gpu_eager_baseline on the B200):
+# the SAME modules as above, built without the minutes-long HF random initialisation of a 7 B model
+# ----------------------------------------------------------------------------------------------------------------
+def build_for_timing(kind: str, cfg: Dict, device="cpu", seed: int = 0) -> nn.Module:
+    """HF BertModel / LlamaForCausalLM of the given config on `device`, fp32, train() mode, parameters filled by tiling one
+    4 Mi-element N(0, 0.02) block (norm gains 1, biases from the block too). Values only need to be non-degenerate: these
+    models are TIMED, never compared. Construction skips HF's init (transformers.initialization.no_init_weights)."""
+    from transformers.initialization import no_init_weights
+
+    keep = {k: v for k, v in cfg.items() if k not in ("architectures", "model_type") and not k.startswith("_")}
+    with no_init_weights(), torch.device(device):
+        if kind == "bert":
+            from transformers import BertConfig, BertModel
+            m = BertModel(BertConfig(**keep))
+        elif kind == "llama":
+            from transformers import LlamaConfig, LlamaForCausalLM
+            m = LlamaForCausalLM(LlamaConfig(**keep))
+        else:
+            raise ValueError(kind)
+    g = torch.Generator(device=device).manual_seed(seed)
+    block = torch.empty(1 << 22, dtype=torch.float32, device=device).normal_(0.0, 0.02, generator=g)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            flat = p.data.view(-1)
+            if p.dim() == 1 and ("norm" in name.lower() and name.endswith("weight")):
+                flat.fill_(1.0)
+                continue
+            for lo in range(0, flat.numel(), block.numel()):
+                n = min(block.numel(), flat.numel() - lo)
+                flat[lo:lo + n].copy_(block[:n])
+    return m.float().train()
+
+
+def timing_lora_factors(kind: str, cfg: Dict, device="cpu", seed: int = 3) -> Dict[str, Dict[str, torch.Tensor]]:
+    """LoRA factors for the reference's targets (rag_e2e_base_model.py:66-68,76-77), A ~ small normal, B = 0 (PEFT init)"""
+    g = torch.Generator().manual_seed(seed)
+    H, nl = cfg["hidden_size"], cfg["num_hidden_layers"]
+    if kind == "bert":
+        names = [f"encoder.layer.{i}.attention.self.{n}" for i in range(nl) for n in ("query", "key", "value")]
+    else:
+        names = [f"model.layers.{i}.self_attn.{n}" for i in range(nl) for n in ("q_proj", "v_proj")]
+    return {n: {"A": (torch.randn(8, H, generator=g) / H ** 0.5).to(device), "B": torch.zeros(H, 8, device=device)} for n in names}
+
+
+def loop_body_step(bert: nn.Module, llama: nn.Module, batch: Dict[str, torch.Tensor], optimizer, logit_scale: float = 100.0,
+                   autocast: Optional[torch.dtype] = None) -> torch.Tensor:
+    """The reference's loop body, train_rage2e.py:429-474, in eager PyTorch over the HF modules: two retrieval forwards,
+    similarity, two-way contrastive loss, generator forward, marginalised loss, backward, optimizer.step, zero_grad.
+    autocast = torch.bfloat16 reproduces `accelerate launch --mixed_precision bf16`; None is the reference's default (fp32)."""
+    dev_type = next(llama.parameters()).device.type
+    ctx = torch.autocast(dev_type, dtype=autocast) if autocast is not None else torch.autocast(dev_type, enabled=False)
+    with ctx:
+        q = retrieval_forward(bert, batch["retriever_query_input_ids"], batch["retriever_query_attention_mask"])
+        p = retrieval_forward(bert, batch["retriever_passage_input_ids"], batch["retriever_passage_attention_mask"])
+        S = losses.get_cosine_sim(q, p, logit_scale)
+        Lc = losses.contrastive_loss(S)
+        logits = llama(input_ids=batch["generator_input_input_ids"], attention_mask=batch["generator_input_attention_mask"]).logits
+        Lm = losses.marginalized_loss_loopform(logits, batch["generator_input_input_ids"],
+                                               batch["generator_input_attention_mask"], S, batch["query_passage_input_len"])
+        loss = Lc + Lm
+    loss.backward()
+    optimizer.step()
+    optimizer.zero_grad()
+    return loss.detach()

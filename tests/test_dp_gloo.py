@@ -45,6 +45,21 @@ def _worker(rank, world, port, q):
     flat0, flat1 = sum(gathered[0], []), sum(gathered[1], [])
     ok = ok and len(gathered[0]) == len(gathered[1]) == 3 and not (set(flat0[:8]) & set(flat1[:8]))
     ok = ok and set(flat0) | set(flat1) == set(range(23))
+    # the step's single-collective reducer: both LoRA banks' gradients + the loss scalar in ONE all-reduce
+    from dalm_b200.engine.lora import LoraBank
+    b1, b2 = LoraBank([("m.q", 16, 24)], device="cpu", seed=1), LoraBank([("m.v", 16, 8), ("m.k", 16, 8)], device="cpu", seed=2)
+    prm = torch.nn.Parameter(b1.flat); prm.grad = b1.grad; b1.param = prm
+    sync = acc.gradient_sync([b1, b2])
+    assert prm.grad.data_ptr() == b1.grad.data_ptr() == sync.arena.data_ptr()        # re-homed into the arena
+    b1.gA["m.q"].fill_(float(rank + 1)); b1.gB["m.q"].fill_(10.0 * (rank + 1))      # written through the per-adapter views
+    b2.gB["m.k"].fill_(100.0 * (rank + 1))
+    n0 = sync.collectives
+    tot = sync.reduce(torch.tensor(2.0 * (rank + 1)))
+    ok = ok and sync.collectives == n0 + 1 and abs(tot.item() - 6.0) < 1e-6          # loss: rank SUM
+    ok = ok and torch.allclose(b1.gA["m.q"], torch.full((8, 16), 1.5)) and torch.allclose(b1.gB["m.q"], torch.full((24, 8), 15.0))
+    ok = ok and torch.allclose(b2.gB["m.k"], torch.full((8, 8), 150.0)) and b2.gA["m.v"].abs().max().item() == 0.0
+    b1.zero_grad()
+    ok = ok and sync.arena[: b1.grad.numel()].abs().max().item() == 0.0
     acc.wait_for_everyone()
     q.put((rank, bool(ok)))
     dist.destroy_process_group()

@@ -75,18 +75,78 @@ def test_resume_parsing():
     assert parse_resume("out/step_30/", steps_per_epoch=13, loader_len=25, gas=2) == (2, 10, 5)
 
 
+class _CountingSet(torch.utils.data.Dataset):
+    """dataset of the integers 0..n-1 that records which items were actually fetched"""
+
+    def __init__(self, n):
+        self.n, self.fetched = n, []
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        self.fetched.append(i)
+        return i
+
+
+def test_epoch_count_does_not_depend_on_world_size():
+    """with max_train_steps=None, num_train_epochs=E must mean E passes on any number of ranks"""
+    from dalm_b200.training.utils.loop import plan_schedule
+    assert plan_schedule(100, 1, 1, None) == (100, 1)                  # 8 ranks shard this to 13 steps/epoch: still 1 epoch
+    assert plan_schedule(100, 2, 3, None) == (150, 3)
+    assert plan_schedule(100, 1, 1, 250) == (250, 3)                   # an explicit step budget decides the epoch count
+    src = open(os.path.join(ROOT, "dalm_b200", "training", "utils", "loop.py")).read()
+    assert src.index("plan_schedule(len(loader)") < src.index("accelerator.prepare(model")   # derived before sharding
+
+
 def test_sharded_loader_matches_accelerate_semantics():
     from dalm_b200.accel import ShardedLoader
-    batches = list(range(10))
-    seen = [list(ShardedLoader(batches, r, 4)) for r in range(4)]
+    mk = lambda: torch.utils.data.DataLoader(_CountingSet(10), batch_size=1, collate_fn=lambda f: f[0])
+    seen = [list(ShardedLoader(mk(), r, 4)) for r in range(4)]
     assert seen[0] == [0, 4, 8] and seen[1] == [1, 5, 9] and seen[2] == [2, 6, 0] and seen[3] == [3, 7, 1]
-    assert all(len(ShardedLoader(batches, r, 4)) == 3 for r in range(4))
-    assert list(ShardedLoader(batches, 0, 1, skip=7)) == [7, 8, 9]
-    sl = ShardedLoader(batches, 1, 2)
+    assert all(len(ShardedLoader(mk(), r, 4)) == 3 for r in range(4))
+    assert list(ShardedLoader(mk(), 0, 1, skip=7)) == [7, 8, 9]
+    sl = ShardedLoader(mk(), 1, 2)
     out = []
     for b in sl:
         out.append((b, sl.end_of_dataloader))
     assert out[-1] == (9, True) and not out[0][1]
+
+
+def test_sharded_loader_fetches_only_its_own_batches():
+    """a rank must not materialise (fetch + collate) the other ranks' batches; all ranks still walk the SAME
+    shuffled permutation (shared seed), so their batches are disjoint and cover the epoch"""
+    from dalm_b200.accel import ShardedLoader
+    got = []
+    for r in range(4):
+        ds = _CountingSet(64)
+        g = torch.Generator(); g.manual_seed(7)
+        dl = torch.utils.data.DataLoader(ds, batch_size=4, shuffle=True, generator=g, collate_fn=lambda f: list(f))
+        batches = list(ShardedLoader(dl, r, 4))
+        assert len(batches) == 4 and len(ds.fetched) == 16             # 64 / 4 per batch / 4 ranks: own samples only
+        got.append([i for b in batches for i in b])
+    flat = sorted(i for g_ in got for i in g_)
+    assert flat == list(range(64))                                     # disjoint cover of one shared permutation
+
+
+def test_dalm_alias_is_the_same_module_object():
+    """`import dalm.X` must BE dalm_b200.X, not a second execution of it"""
+    import importlib
+    import dalm  # noqa: F401
+    import dalm_b200.models.rag_e2e_base_model as real
+    from dalm.models.rag_e2e_base_model import AutoModelForRagE2E as A1
+    from dalm.models.rag_e2e_base_model import AutoModelForRagE2E as A2
+    import dalm.models.rag_e2e_base_model as alias
+    assert alias is real and A1 is A2 and A1 is real.AutoModelForRagE2E
+    assert sys.modules["dalm_b200.models.rag_e2e_base_model"] is real and real.__spec__.name == real.__name__
+    for sub in ("training.utils.train_utils", "training.rag_e2e.train_rage2e", "training.retriever_only.train_retriever_only",
+                "eval.utils", "cli", "utils", "models.retriever_only_base_model"):
+        assert importlib.import_module("dalm." + sub) is importlib.import_module("dalm_b200." + sub)
+    import dalm.training.utils.train_utils as tu
+    from dalm_b200.models.retriever_only_base_model import AutoModelForSentenceEmbedding
+    import dalm.models.retriever_only_base_model as ro
+    assert ro.AutoModelForSentenceEmbedding is AutoModelForSentenceEmbedding     # isinstance checks in save_model_hook hold
+    assert tu.save_model_hook.__module__ == "dalm_b200.training.utils.train_utils"
 
 
 def test_scheduler_wrapper_and_accumulate():
