@@ -35,13 +35,14 @@ SIGNATURES = {
     "dalm_b200_gemm_bf16_tn": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _F, _P, _I, _P, _L, _I, _I, _I, *_DROP, _P],
     "dalm_b200_gemm_bf16": [_I, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _F, _P, _I, _P, _L, _I, _I, _I, *_DROP, _P],
     "dalm_b200_gemm_clear_cache": [],
+    "dalm_b200_gemm_set_raster": [_I],
     "dalm_b200_attention_fwd": [_P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _I, _I, _I, _I, _I, _F, _I, *_DROP, _P],
     "dalm_b200_attention_bwd": [_P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _P, _L, _P, _P, _L, _P, _L, _P, _L,
                                 _I, _I, _I, _I, _I, _F, _I, *_DROP, _P],
-    "dalm_b200_attention_tc_fwd": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _L, _I, _P, _P, _L, _P, _I, _I, _I, _I, _I, _F, _I, _P],
+    "dalm_b200_attention_tc_fwd": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _L, _I, _P, _P, _L, _P, _I, _I, _I, _I, _I, _F, _I, *_DROP, _P],
     "dalm_b200_attention_tc_set_debug": [_P],
     "dalm_b200_attention_tc_bwd": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _P, _L, _P, _P, _L, _L, _P, _P, _L, _P, _L, _P, _L,
-                                   _I, _I, _I, _I, _I, _F, _I, _P],
+                                   _I, _I, _I, _I, _I, _F, _I, *_DROP, _P],
     "dalm_b200_layernorm_fwd": [_P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _F, *_DROP, _P],
     "dalm_b200_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _L, _P, _P, _L, _I, _I, *_DROP, _P],
     "dalm_b200_layernorm_bwd_res": [_P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _L, _I, _I, _P],
@@ -81,6 +82,7 @@ _RESTYPES = {
     "dalm_b200_topk_ip_workspace": c_longlong,
     "dalm_b200_reset_launch_count": None,
     "dalm_b200_gemm_clear_cache": None,
+    "dalm_b200_gemm_set_raster": None,
     "dalm_b200_attention_tc_set_debug": None,
 }
 

@@ -5,8 +5,9 @@
 // dalm/models/rag_e2e_base_model.py:93,105 and its autograd backward. Flash-style: scores never touch HBM; the forward
 // stores only the per-row log-sum-exp, the backward recomputes P tile by tile.
 //
-// Attention is ~1 % of the step FLOPs at cfg-3, so round 1 uses warp-level mma.sync (HMMA) tiles with
-// ldmatrix-fed fragments; the tcgen05/TMEM variant is scheduled after the GEMM path.
+// These are the warp-level mma.sync (HMMA) kernels with ldmatrix-fed fragments. The training paths at head_dim 64 / 128
+// run the tcgen05/TMEM kernels of csrc/attention_tc.cu; this file serves head_dim 32 (bge-small, cfg-1) and is the
+// independent cross-check the tcgen05 kernels are tested against (same masks, same dropout element indexing).
 //
 //   forward : grid (ceil(L/64), Hq, B), 4 warps, each warp owns 16 query rows, KV streamed in 64-key tiles
 //   dKdV    : grid (ceil(L/64), Hkv, B), each warp owns 16 keys, loops over the q heads of its group and 32-query tiles

@@ -1,8 +1,11 @@
-// dalm_b200 — decoder attention on the 5th-gen tensor cores (tcgen05.mma + TMEM accumulators + TMA), head_dim 128,
-// causal + key-padding mask, MHA/GQA. Forward and backward (dKdV, dQ).
+// dalm_b200 — attention on the 5th-gen tensor cores (tcgen05.mma + TMEM accumulators + TMA), head_dim 128 or 64,
+// causal / bidirectional + key-padding mask, MHA / GQA / MQA, optional attention-probability dropout. Forward and backward
+// (dKdV, dQ).
 //
-// Replaces the attention inside HF LlamaForCausalLM reached through dalm/models/rag_e2e_base_model.py:105 (reference) and
-// its autograd backward; same math as csrc/attention.cu (flash-style, scores never in HBM, LSE saved, P recomputed).
+// Replaces the attention inside HF LlamaForCausalLM (head_dim 128), BertModel (bge-large: 16 x 64, bidirectional,
+// attention_probs_dropout_prob 0.1) and FalconForCausalLM (71 q heads / 1 kv head x 64, causal) reached through
+// dalm/models/rag_e2e_base_model.py:93,105 / retriever_only_base_model.py:58 (reference) and their autograd backward; same
+// math as csrc/attention.cu (flash-style, scores never in HBM, LSE saved, P recomputed).
 //
 // Every contraction is a 128 x 128 x 128 tcgen05 tile issued by ONE thread; the softmax / dS elementwise work runs on
 // four warps that own one TMEM lane (= one query or key row) each:
@@ -30,12 +33,23 @@ struct AttnTcParams {
   int causal;
   int qcol0, kcol0, vcol0, ocol0;   // column of head 0 inside the q / k / v / dO tensor maps
   long long* dbg;                   // optional [64] clock64 timestamps of one CTA's phases (tuning aid), or nullptr
+  DropCfg drop;                     // attention-probability dropout (BERT); p = 0 => off. Same element indexing as
+                                    // csrc/attention.cu: group ((b*Hq + h)*L + q) * ceil(L/8) + key/8, component key%8
 };
 
-constexpr int TD = 128;                      // head dim
 constexpr int TB = 128;                      // tile: 128 queries x 128 keys
 constexpr int HALF_BYTES = TB * 64 * 2;      // one [128 rows x 64 cols] bf16 box = 16 KB
-constexpr int TILE_BYTES = 2 * HALF_BYTES;   // [128 x 128] bf16 as two 64-column halves
+constexpr int TILE_BYTES = 2 * HALF_BYTES;   // [128 x 128] bf16 as two 64-column halves (P / dS tiles; Q/K/V/dO tiles at D = 128)
+template <int D> struct TcD {                // per head_dim constants: a [128 tokens x D] tile is D/64 halves
+  static constexpr int KS = D / 16;          // k-steps of the contractions over d (Q K^T, dO V^T)
+  static constexpr int HALVES = D / 64;
+  static constexpr int TILE = HALVES * HALF_BYTES;
+};
+template <int D>
+__device__ __forceinline__ void load_tile(unsigned char* dst, const CUtensorMap* tm, uint64_t* bar, int col, int row) {
+#pragma unroll
+  for (int hh = 0; hh < D / 64; ++hh) tma_load_2d(dst + hh * HALF_BYTES, tm, bar, col + hh * 64, row);
+}
 
 // A/B K-major descriptors for k-step kk (0..7) of a [128 x 128] tile stored as two 64-col halves
 __device__ __forceinline__ uint64_t kmajor_desc(uint32_t tile, int kk) {
@@ -54,6 +68,7 @@ __device__ __forceinline__ void st_sw128(unsigned char* half_tile, int row, int 
 // 128B-swizzled staging tile (two 64-column halves) and two TMA stores - full 128-byte lines instead of 32 partial sectors
 // per warp store (measured: the per-thread row stores cost 10k of a forward CTA's 30k cycles). Ragged tiles (rows beyond
 // the sequence end belong to the NEXT sequence, so the TMA box must not be used) fall back to predicated row stores.
+template <int TD>
 __device__ __forceinline__ void drain_tile_bf16(uint32_t tacc, float scale, unsigned char* stage, const CUtensorMap* tm,
                                                 int col0, int row0_global, bool full_tile, bool row_ok, int r,
                                                 __nv_bfloat16* fallback_row) {
@@ -76,8 +91,8 @@ __device__ __forceinline__ void drain_tile_bf16(uint32_t tacc, float scale, unsi
     fence_proxy_async();
     named_bar_sync(1, 128);
     if (threadIdx.x == 0) {
-      tma_store_2d(tm, stage, col0, row0_global);
-      tma_store_2d(tm, stage + HALF_BYTES, col0 + 64, row0_global);
+#pragma unroll
+      for (int hh = 0; hh < TD / 64; ++hh) tma_store_2d(tm, stage + hh * HALF_BYTES, col0 + hh * 64, row0_global);
       bulk_commit();
       bulk_wait<0>();
     }
@@ -100,17 +115,20 @@ __device__ __forceinline__ void key_bits(const int64_t* mask_row, int kv0, int L
 // forward: grid (ceil(L/128), Hq, B), 160 threads: warps 0-3 softmax (thread = query row), warp 4 control.
 // O accumulates in TMEM (P V with the accumulate flag); the online-softmax correction rescales it in place.
 // ============================================================================================================
+template <int TD, bool DROP>
 __global__ void __launch_bounds__(160, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, const AttnTcParams p) {
+  using C = TcD<TD>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* sQ = smem;
-  unsigned char* sK = sQ + TILE_BYTES;
-  unsigned char* sV = sK + TILE_BYTES;
-  unsigned char* sP = sK;        // P overwrites K: K is dead once S = Q K^T has retired (s_full), and K is only reloaded
-                                 // after P V has retired (kv_free). 96 KB per CTA => two CTAs per SM.
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + TILE_BYTES);
+  unsigned char* sK = sQ + C::TILE;
+  unsigned char* sV = sK + C::TILE;
+  // D = 128: P overwrites K (K is dead once S = Q K^T has retired (s_full), and K is only reloaded after P V has retired
+  // (kv_free)): 96 KB per CTA => two CTAs per SM. D = 64: K is only 16 KB, P (32 KB) gets its own tile: 80 KB per CTA.
+  unsigned char* sP = TD == 128 ? sK : sV + C::TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>((TD == 128 ? sV + C::TILE : sP + TILE_BYTES));
   uint64_t *q_full = bars, *kv_full = bars + 1, *kv_free = bars + 2, *s_full = bars + 3, *p_ready = bars + 4, *pv_full = bars + 5;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
 
@@ -141,27 +159,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 4) {
     if (lane == 0) {
       // ---------------- control: TMA loads + MMA issue ----------------
-      mbar_arrive_expect_tx(q_full, TILE_BYTES);
-      tma_load_2d(sQ, &tm_q, q_full, p.qcol0 + h * TD, tok0 + q0);
-      tma_load_2d(sQ + HALF_BYTES, &tm_q, q_full, p.qcol0 + h * TD + 64, tok0 + q0);
+      mbar_arrive_expect_tx(q_full, C::TILE);
+      load_tile<TD>(sQ, &tm_q, q_full, p.qcol0 + h * TD, tok0 + q0);
       constexpr uint32_t idesc_kk = make_idesc_bf16(TB, TB);          // S = Q K^T   (both K-major)
       constexpr uint32_t idesc_mn = make_idesc_bf16_bmn(TB, TD);      // O += P V    (B = V MN-major)
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
       for (int j = 0; j < nkv; ++j) {
         const uint32_t ph = j & 1;
         mbar_wait(kv_free, ph ^ 1);
-        mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
-        tma_load_2d(sK, &tm_k, kv_full, p.kcol0 + hk * TD, tok0 + j * TB);
-        tma_load_2d(sK + HALF_BYTES, &tm_k, kv_full, p.kcol0 + hk * TD + 64, tok0 + j * TB);
-        tma_load_2d(sV, &tm_v, kv_full, p.vcol0 + hk * TD, tok0 + j * TB);
-        tma_load_2d(sV + HALF_BYTES, &tm_v, kv_full, p.vcol0 + hk * TD + 64, tok0 + j * TB);
+        mbar_arrive_expect_tx(kv_full, 2 * C::TILE);
+        load_tile<TD>(sK, &tm_k, kv_full, p.kcol0 + hk * TD, tok0 + j * TB);
+        load_tile<TD>(sV, &tm_v, kv_full, p.vcol0 + hk * TD, tok0 + j * TB);
         TS(2 + j * 8);
         if (j == 0) mbar_wait(q_full, 0);
         mbar_wait(kv_full, ph);
         TS(3 + j * 8);
         tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) umma_f16(tS, kmajor_desc(aQ, kk), kmajor_desc(aK, kk), idesc_kk, kk != 0);
+        for (int kk = 0; kk < C::KS; ++kk) umma_f16(tS, kmajor_desc(aQ, kk), kmajor_desc(aK, kk), idesc_kk, kk != 0);
         umma_commit(s_full);
         TS(4 + j * 8);
         mbar_wait(p_ready, ph);                                         // P written, O rescaled
@@ -236,11 +251,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tmem_st_wait();
       }
       float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+      unsigned long long dstream = 0, dgrp0 = 0;
+      if constexpr (DROP) {
+        dstream = drop_stream(p.drop);
+        dgrp0 = (((unsigned long long)b * p.Hq + h) * L + (unsigned long long)qrow) * (unsigned long long)((L + 7) >> 3) + (unsigned long long)(kv0 >> 3);
+      }
 #pragma unroll
       for (int g = 0; g < TB / 8; ++g) {
         float pv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { pv[i] = ex2_approx(sv[g * 8 + i] - m_safe); rs4[i & 3] += pv[i]; }
+        if constexpr (DROP) {
+          // dropout acts on the normalised probabilities; the row sum above uses the un-dropped values (HF: softmax -> dropout -> @V)
+          float sc[8];
+          drop_scale8(p.drop, dstream, dgrp0 + g, sc);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pv[i] *= sc[i];
+        }
         st_sw128(sP + (g >> 3) * HALF_BYTES, r, g & 7, pack8(pv));
       }
       l_run = l_run * corr + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
@@ -255,8 +282,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     if (threadIdx.x == 0) TS(23);
     const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
     __nv_bfloat16* orow = p.o + (size_t)(tok0 + (qrow < L ? qrow : 0)) * p.ldo + (size_t)h * TD;
-    drain_tile_bf16(tO + lane_off, inv_l, sQ /* Q is dead after the last S MMA */, &tm_o, p.ocol0 + h * TD, tok0 + q0,
-                    q0 + TB <= L, qrow < L, r, orow);
+    drain_tile_bf16<TD>(tO + lane_off, inv_l, sQ /* Q is dead after the last S MMA */, &tm_o, p.ocol0 + h * TD, tok0 + q0,
+                        q0 + TB <= L, qrow < L, r, orow);
     if (qrow < L)
       p.lse[((size_t)b * p.Hq + h) * L + qrow] = l_run > 0.f ? (m_run + log2f(l_run)) * 0.6931471805599453f : INFINITY;
   }
@@ -271,20 +298,29 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 // ============================================================================================================
 // backward pre-pass: delta[b,h,i] = sum_d dO[i,d] * O[i,d]   (one warp per (token, head))
 // ============================================================================================================
+template <int TD>
 __global__ void attn_tc_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ d_o,
                                      long long lddo, float* __restrict__ delta, int B, int L, int Hq) {
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= B * L * Hq) return;
   const int tok = gw / Hq, h = gw - tok * Hq;
-  float a[4], c[4];
-  const uint2 ra = *reinterpret_cast<const uint2*>(o + (size_t)tok * ldo + (size_t)h * TD + lane * 4);
-  const uint2 rc = *reinterpret_cast<const uint2*>(d_o + (size_t)tok * lddo + (size_t)h * TD + lane * 4);
-  float2 t;
-  t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ra.x)); a[0] = t.x; a[1] = t.y;
-  t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ra.y)); a[2] = t.x; a[3] = t.y;
-  t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rc.x)); c[0] = t.x; c[1] = t.y;
-  t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rc.y)); c[2] = t.x; c[3] = t.y;
-  float acc = a[0] * c[0] + a[1] * c[1] + a[2] * c[2] + a[3] * c[3];
+  float acc;
+  if constexpr (TD == 128) {
+    float a[4], c[4];
+    const uint2 ra = *reinterpret_cast<const uint2*>(o + (size_t)tok * ldo + (size_t)h * TD + lane * 4);
+    const uint2 rc = *reinterpret_cast<const uint2*>(d_o + (size_t)tok * lddo + (size_t)h * TD + lane * 4);
+    float2 t;
+    t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ra.x)); a[0] = t.x; a[1] = t.y;
+    t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ra.y)); a[2] = t.x; a[3] = t.y;
+    t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rc.x)); c[0] = t.x; c[1] = t.y;
+    t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rc.y)); c[2] = t.x; c[3] = t.y;
+    acc = a[0] * c[0] + a[1] * c[1] + a[2] * c[2] + a[3] * c[3];
+  } else {
+    const __nv_bfloat162 ra = *reinterpret_cast<const __nv_bfloat162*>(o + (size_t)tok * ldo + (size_t)h * TD + lane * 2);
+    const __nv_bfloat162 rc = *reinterpret_cast<const __nv_bfloat162*>(d_o + (size_t)tok * lddo + (size_t)h * TD + lane * 2);
+    const float2 a = __bfloat1622float2(ra), c = __bfloat1622float2(rc);
+    acc = a.x * c.x + a.y * c.y;
+  }
   acc = warp_sum(acc);
   if (lane == 0) {
     const int b = tok / L, l = tok - b * L;
@@ -296,18 +332,20 @@ __global__ void attn_tc_delta_kernel(const __nv_bfloat16* __restrict__ o, long l
 // backward dK, dV: grid (ceil(L/128) key tiles, Hkv, B); thread = key row. Loops over the q heads of the group and the
 // query tiles that can see this key tile. dV and dK accumulate in TMEM across ALL of them.
 // ============================================================================================================
+template <int TD, bool DROP>
 __global__ void __launch_bounds__(160, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                        const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                        const __grid_constant__ CUtensorMap tm_dk, const __grid_constant__ CUtensorMap tm_dv,
                        const AttnTcParams p) {
+  using C = TcD<TD>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* sK = smem;
-  unsigned char* sV = sK + TILE_BYTES;
-  unsigned char* sQ = sV + TILE_BYTES;
-  unsigned char* sdO = sQ + TILE_BYTES;
-  unsigned char* sPt = sdO + TILE_BYTES;
+  unsigned char* sV = sK + C::TILE;
+  unsigned char* sQ = sV + C::TILE;
+  unsigned char* sdO = sQ + C::TILE;
+  unsigned char* sPt = sdO + C::TILE;
   unsigned char* sdSt = sPt + TILE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdSt + TILE_BYTES);
   uint64_t *kv_full = bars, *qdo_full = bars + 1, *st_full = bars + 2, *pt_ready = bars + 3, *mma2_done = bars + 4;
@@ -333,15 +371,13 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_holder;
-  const uint32_t tSt = tmem, tdPt = tmem + 128, tdV = tmem + 256, tdK = tmem + 384;
+  const uint32_t tSt = tmem, tdPt = tmem + 128, tdV = tmem + 256, tdK = tmem + 256 + TD;
 
   if (warp == 4) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
-      tma_load_2d(sK, &tm_k, kv_full, p.kcol0 + hk * TD, tok0 + kv0);
-      tma_load_2d(sK + HALF_BYTES, &tm_k, kv_full, p.kcol0 + hk * TD + 64, tok0 + kv0);
-      tma_load_2d(sV, &tm_v, kv_full, p.vcol0 + hk * TD, tok0 + kv0);
-      tma_load_2d(sV + HALF_BYTES, &tm_v, kv_full, p.vcol0 + hk * TD + 64, tok0 + kv0);
+      mbar_arrive_expect_tx(kv_full, 2 * C::TILE);
+      load_tile<TD>(sK, &tm_k, kv_full, p.kcol0 + hk * TD, tok0 + kv0);
+      load_tile<TD>(sV, &tm_v, kv_full, p.vcol0 + hk * TD, tok0 + kv0);
       constexpr uint32_t idesc_kk = make_idesc_bf16(TB, TB);
       constexpr uint32_t idesc_mn = make_idesc_bf16_bmn(TB, TD);
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), aDO = smem_u32(sdO), aPt = smem_u32(sPt), aDSt = smem_u32(sdSt);
@@ -350,18 +386,16 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         for (int i = i_begin; i < nq_tiles; ++i, ++it) {
           const uint32_t ph = it & 1;
           mbar_wait(mma2_done, ph ^ 1);                          // previous iteration's dV/dK MMAs have consumed Q/dO
-          mbar_arrive_expect_tx(qdo_full, 2 * TILE_BYTES);
-          tma_load_2d(sQ, &tm_q, qdo_full, p.qcol0 + hq * TD, tok0 + i * TB);
-          tma_load_2d(sQ + HALF_BYTES, &tm_q, qdo_full, p.qcol0 + hq * TD + 64, tok0 + i * TB);
-          tma_load_2d(sdO, &tm_do, qdo_full, p.ocol0 + hq * TD, tok0 + i * TB);
-          tma_load_2d(sdO + HALF_BYTES, &tm_do, qdo_full, p.ocol0 + hq * TD + 64, tok0 + i * TB);
+          mbar_arrive_expect_tx(qdo_full, 2 * C::TILE);
+          load_tile<TD>(sQ, &tm_q, qdo_full, p.qcol0 + hq * TD, tok0 + i * TB);
+          load_tile<TD>(sdO, &tm_do, qdo_full, p.ocol0 + hq * TD, tok0 + i * TB);
           if (it == 0) mbar_wait(kv_full, 0);
           mbar_wait(qdo_full, ph);
           tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) umma_f16(tSt, kmajor_desc(aK, kk), kmajor_desc(aQ, kk), idesc_kk, kk != 0);    // S^T  = K Q^T
+          for (int kk = 0; kk < C::KS; ++kk) umma_f16(tSt, kmajor_desc(aK, kk), kmajor_desc(aQ, kk), idesc_kk, kk != 0);    // S^T  = K Q^T
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) umma_f16(tdPt, kmajor_desc(aV, kk), kmajor_desc(aDO, kk), idesc_kk, kk != 0);  // dP^T = V dO^T
+          for (int kk = 0; kk < C::KS; ++kk) umma_f16(tdPt, kmajor_desc(aV, kk), kmajor_desc(aDO, kk), idesc_kk, kk != 0);  // dP^T = V dO^T
           umma_commit(st_full);
           mbar_wait(pt_ready, ph);
           tc_fence_after();
@@ -380,6 +414,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const float sl2 = p.scale * 1.4426950408889634f;
     bool key_ok = key < L;
     if (key_ok && p.mask) key_ok = p.mask[(size_t)tok0 + key] != 0;
+    unsigned long long dstream = 0;
+    const int lp8 = (L + 7) >> 3;
+    if constexpr (DROP) dstream = drop_stream(p.drop);
     int it = 0;
     for (int hq = hk * group; hq < (hk + 1) * group; ++hq) {
       for (int i = i_begin; i < nq_tiles; ++i, ++it) {
@@ -409,6 +446,29 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             *reinterpret_cast<float4*>(lse_c + x) = *reinterpret_cast<const float4*>(sLse + c + x);
             *reinterpret_cast<float4*>(del_c + x) = *reinterpret_cast<const float4*>(sDelta + c + x);
           }
+          // dropout keep bits of (query q0+c+x, this thread's key), x = 0..31. The mask is generated in groups of 8 KEYS of
+          // one query (csrc/attention.cu's indexing), i.e. ACROSS the 8 lanes that share key/8 here: each lane draws the
+          // groups of 4 queries (x = (lane & 7) + 8t), keeps only the 8 keep-bits of each draw, and the lanes of an octet
+          // exchange them with 8 shuffles - 4 Philox calls per lane per 32 queries instead of 32
+          uint32_t keepw = 0xffffffffu;
+          if constexpr (DROP) {
+            uint32_t mine = 0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int qx = q0 + c + (lane & 7) + 8 * t;
+              float sc[8];
+              drop_scale8(p.drop, dstream, (((unsigned long long)b * p.Hq + hq) * L + (unsigned long long)qx) * (unsigned long long)lp8 + (unsigned long long)(key >> 3), sc);
+#pragma unroll
+              for (int j2 = 0; j2 < 8; ++j2) mine |= (sc[j2] != 0.f ? 1u : 0u) << (8 * t + j2);
+            }
+            keepw = 0;
+#pragma unroll
+            for (int i2 = 0; i2 < 8; ++i2) {
+              const uint32_t v = __shfl_sync(0xffffffffu, mine, (lane & ~7) | i2);     // draws of queries x = i2 + 8t
+#pragma unroll
+              for (int t = 0; t < 4; ++t) keepw |= ((v >> (8 * t + (lane & 7))) & 1u) << (8 * t + i2);
+            }
+          }
           tmem_ld_wait();
           float pt[32], ds[32];
           const int qbase = q0 + c;
@@ -418,8 +478,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             const int drop = dropkey | (diag ? ((qbase + x - key) >> 31) : 0);
             const uint32_t bits = (__float_as_uint(__uint_as_float(vs[x]) * sl2) & ~(uint32_t)drop) | (0xff800000u & (uint32_t)drop);
             const float pr = ex2_approx(__uint_as_float(bits) - lse_c[x]);      // lse = +inf (padding / fully masked query) -> 0
-            pt[x] = pr;
-            ds[x] = pr * (__uint_as_float(vp[x]) - del_c[x]) * p.scale;
+            if constexpr (DROP) {
+              const float sc = ((keepw >> x) & 1u) ? p.drop.inv_keep : 0.f;     // P_drop = sc * P ; dP = sc * dP_drop
+              pt[x] = pr * sc;
+              ds[x] = pr * (__uint_as_float(vp[x]) * sc - del_c[x]) * p.scale;
+            } else {
+              pt[x] = pr;
+              ds[x] = pr * (__uint_as_float(vp[x]) - del_c[x]) * p.scale;
+            }
           }
           unsigned char* hp = sPt + (c >> 6) * HALF_BYTES;
           unsigned char* hd = sdSt + (c >> 6) * HALF_BYTES;
@@ -442,8 +508,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       __nv_bfloat16* dvrow = p.dv + (size_t)(tok0 + (st_ok ? key : 0)) * p.lddv + (size_t)hk * TD;
       __nv_bfloat16* dkrow = p.dk + (size_t)(tok0 + (st_ok ? key : 0)) * p.lddk + (size_t)hk * TD;
       // P^T / dS^T staging tiles are free once the last MMAs have retired
-      drain_tile_bf16(tdV + lane_off, 1.f, sPt, &tm_dv, hk * TD, tok0 + kv0, full, st_ok, r, dvrow);
-      drain_tile_bf16(tdK + lane_off, 1.f, sdSt, &tm_dk, hk * TD, tok0 + kv0, full, st_ok, r, dkrow);
+      drain_tile_bf16<TD>(tdV + lane_off, 1.f, sPt, &tm_dv, hk * TD, tok0 + kv0, full, st_ok, r, dvrow);
+      drain_tile_bf16<TD>(tdK + lane_off, 1.f, sdSt, &tm_dk, hk * TD, tok0 + kv0, full, st_ok, r, dkrow);
     }
   }
   tc_fence_before();
@@ -454,21 +520,22 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 // ============================================================================================================
 // backward dQ: grid (ceil(L/128) query tiles, Hq, B); thread = query row; dQ accumulates in TMEM over the key tiles
 // ============================================================================================================
+template <int TD, bool DROP>
 __global__ void __launch_bounds__(160, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                       const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                       const __grid_constant__ CUtensorMap tm_dq, const AttnTcParams p) {
+  using C = TcD<TD>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* sQ = smem;
-  unsigned char* sdO = sQ + TILE_BYTES;
-  unsigned char* sK = sdO + TILE_BYTES;
-  unsigned char* sV = sK + TILE_BYTES;
-  unsigned char* sdS = sV + TILE_BYTES;
+  unsigned char* sdO = sQ + C::TILE;
+  unsigned char* sK = sdO + C::TILE;
+  unsigned char* sV = sK + C::TILE;
+  unsigned char* sdS = sV + C::TILE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + TILE_BYTES);
   uint64_t *qdo_full = bars, *kv_full = bars + 1, *s_full = bars + 2, *ds_ready = bars + 3, *mma2_done = bars + 4;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
-  float* sMask = reinterpret_cast<float*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -490,29 +557,25 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 
   if (warp == 4) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(qdo_full, 2 * TILE_BYTES);
-      tma_load_2d(sQ, &tm_q, qdo_full, p.qcol0 + h * TD, tok0 + q0);
-      tma_load_2d(sQ + HALF_BYTES, &tm_q, qdo_full, p.qcol0 + h * TD + 64, tok0 + q0);
-      tma_load_2d(sdO, &tm_do, qdo_full, p.ocol0 + h * TD, tok0 + q0);
-      tma_load_2d(sdO + HALF_BYTES, &tm_do, qdo_full, p.ocol0 + h * TD + 64, tok0 + q0);
+      mbar_arrive_expect_tx(qdo_full, 2 * C::TILE);
+      load_tile<TD>(sQ, &tm_q, qdo_full, p.qcol0 + h * TD, tok0 + q0);
+      load_tile<TD>(sdO, &tm_do, qdo_full, p.ocol0 + h * TD, tok0 + q0);
       constexpr uint32_t idesc_kk = make_idesc_bf16(TB, TB);
       constexpr uint32_t idesc_mn = make_idesc_bf16_bmn(TB, TD);
       const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV), aDS = smem_u32(sdS);
       for (int j = 0; j < nkv; ++j) {
         const uint32_t ph = j & 1;
         mbar_wait(mma2_done, ph ^ 1);                            // previous dQ MMAs consumed K (and dS)
-        mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
-        tma_load_2d(sK, &tm_k, kv_full, p.kcol0 + hk * TD, tok0 + j * TB);
-        tma_load_2d(sK + HALF_BYTES, &tm_k, kv_full, p.kcol0 + hk * TD + 64, tok0 + j * TB);
-        tma_load_2d(sV, &tm_v, kv_full, p.vcol0 + hk * TD, tok0 + j * TB);
-        tma_load_2d(sV + HALF_BYTES, &tm_v, kv_full, p.vcol0 + hk * TD + 64, tok0 + j * TB);
+        mbar_arrive_expect_tx(kv_full, 2 * C::TILE);
+        load_tile<TD>(sK, &tm_k, kv_full, p.kcol0 + hk * TD, tok0 + j * TB);
+        load_tile<TD>(sV, &tm_v, kv_full, p.vcol0 + hk * TD, tok0 + j * TB);
         if (j == 0) mbar_wait(qdo_full, 0);
         mbar_wait(kv_full, ph);
         tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) umma_f16(tS, kmajor_desc(aQ, kk), kmajor_desc(aK, kk), idesc_kk, kk != 0);      // S  = Q K^T
+        for (int kk = 0; kk < C::KS; ++kk) umma_f16(tS, kmajor_desc(aQ, kk), kmajor_desc(aK, kk), idesc_kk, kk != 0);      // S  = Q K^T
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) umma_f16(tdP, kmajor_desc(aDO, kk), kmajor_desc(aV, kk), idesc_kk, kk != 0);    // dP = dO V^T
+        for (int kk = 0; kk < C::KS; ++kk) umma_f16(tdP, kmajor_desc(aDO, kk), kmajor_desc(aV, kk), idesc_kk, kk != 0);    // dP = dO V^T
         umma_commit(s_full);
         mbar_wait(ds_ready, ph);
         tc_fence_after();
@@ -529,6 +592,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const size_t idx = ((size_t)b * p.Hq + h) * L + qrow;
     const float lse2 = qrow < L ? p.lse[idx] * 1.4426950408889634f : INFINITY;
     const float dl = qrow < L ? p.delta[idx] : 0.f;
+    unsigned long long dstream = 0, dgrow = 0;
+    if constexpr (DROP) {
+      dstream = drop_stream(p.drop);
+      dgrow = (((unsigned long long)b * p.Hq + h) * L + (unsigned long long)qrow) * (unsigned long long)((L + 7) >> 3);
+    }
     for (int j = 0; j < nkv; ++j) {
       const uint32_t ph = j & 1;
       const int kv0 = j * TB;
@@ -544,6 +612,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         uint32_t vs[32], vp[32];
         tmem_ld_32x32(tS + lane_off + c, vs);
         tmem_ld_32x32(tdP + lane_off + c, vp);
+        float dsc[32];
+        if constexpr (DROP) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) drop_scale8(p.drop, dstream, dgrow + (unsigned long long)(((kv0 + c) >> 3) + g), dsc + g * 8);
+        }
         tmem_ld_wait();
         const uint32_t kw = kbits[c >> 5];
         float ds[32];
@@ -552,7 +625,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           const int drop = ((dcol - (c + x)) >> 31) | (int)(((kw >> x) & 1u) - 1u);
           const uint32_t bits = (__float_as_uint(__uint_as_float(vs[x]) * sl2) & ~(uint32_t)drop) | (0xff800000u & (uint32_t)drop);
           const float pr = ex2_approx(__uint_as_float(bits) - lse2);
-          ds[x] = pr * (__uint_as_float(vp[x]) - dl) * p.scale;
+          if constexpr (DROP) ds[x] = pr * (__uint_as_float(vp[x]) * dsc[x] - dl) * p.scale;
+          else                ds[x] = pr * (__uint_as_float(vp[x]) - dl) * p.scale;
         }
         unsigned char* hd = sdS + (c >> 6) * HALF_BYTES;
 #pragma unroll
@@ -565,17 +639,17 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     mbar_wait(mma2_done, (nkv - 1) & 1);
     tc_fence_after();
     __nv_bfloat16* dqrow = p.dq + (size_t)(tok0 + (qrow < L ? qrow : 0)) * p.lddq + (size_t)h * TD;
-    drain_tile_bf16(tdQ + lane_off, 1.f, sdS /* free after the last dQ MMA */, &tm_dq, h * TD, tok0 + q0, q0 + TB <= L,
-                    qrow < L, r, dqrow);
+    drain_tile_bf16<TD>(tdQ + lane_off, 1.f, sdS /* free after the last dQ MMA */, &tm_dq, h * TD, tok0 + q0, q0 + TB <= L,
+                        qrow < L, r, dqrow);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-constexpr int kDkvSmem = 6 * TILE_BYTES + 1024 + 2048;
-constexpr int kDqSmem = 5 * TILE_BYTES + 1024 + 1024;
-constexpr int kFwdSmem = 3 * TILE_BYTES + 1024 + 1024;
+template <int D> constexpr int dkv_smem() { return 4 * TcD<D>::TILE + 2 * TILE_BYTES + 1024 + 2048; }
+template <int D> constexpr int dq_smem() { return 4 * TcD<D>::TILE + TILE_BYTES + 1024 + 1024; }
+template <int D> constexpr int fwd_smem() { return 3 * TcD<D>::TILE + (D == 128 ? 0 : TILE_BYTES) + 1024 + 1024; }
 
 }  // namespace dalm
 
@@ -588,44 +662,82 @@ static int tc_maps(const void* ptr, long long rows, long long cols, long long ld
   return get_tmap(ptr, rows, cols, ld, 128, m, 0);
 }
 
-// q/k/v: bf16 token-major 2-D matrices [B*L, ncols] (row stride ld*), head h of q at column qcol0 + h*128 etc.
+template <int D, bool DROP>
+static int launch_tc_fwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo,
+                         const AttnTcParams& p, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) { DALM_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<D, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<D>())); attr = true; }
+  dim3 grid((p.L + TB - 1) / TB, p.Hq, p.B);
+  attn_fwd_tc_kernel<D, DROP><<<grid, 160, fwd_smem<D>(), st>>>(mq, mk, mv, mo, p);
+  count_launch();
+  return check_launch("attn_fwd_tc_kernel");
+}
+
+// q/k/v: bf16 token-major 2-D matrices [B*L, ncols] (row stride ld*), head h of q at column qcol0 + h*D etc.
 extern "C" int dalm_b200_attention_tc_fwd(const void* q, long long ldq, long long qcols, int qcol0, const void* k,
                                           long long ldk, long long kcols, int kcol0, const void* v, long long ldv,
                                           long long vcols, int vcol0, const int64_t* mask, void* out, long long ldo,
                                           float* lse, int B, int L, int Hq, int Hkv, int D, float scale, int causal,
-                                          void* stream) {
-  DALM_REQUIRE(D == 128, "attention_tc: head_dim must be 128 (got %d)", D);
+                                          float drop_p, unsigned long long drop_seed, unsigned long long drop_stream_id,
+                                          const void* drop_offset, void* stream) {
+  DALM_REQUIRE(D == 128 || D == 64, "attention_tc: head_dim must be 64 or 128 (got %d)", D);
   DALM_REQUIRE(B > 0 && L > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0, "attention_tc: bad shape");
   DALM_REQUIRE((ldo % 8) == 0 && ((uintptr_t)out & 15) == 0, "attention_tc: output alignment");
+  DALM_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "attention_tc: dropout p must be in [0,1)");
+  DALM_REQUIRE(drop_p == 0.f || D == 64, "attention_tc: probability dropout is built for head_dim 64 (BERT encoder); Llama has attention_dropout = 0");
   CUtensorMap mq, mk, mv, mo;
   const long long rows = (long long)B * L;
   if (int e = tc_maps(q, rows, qcols, ldq, &mq)) return e;
   if (int e = tc_maps(k, rows, kcols, ldk, &mk)) return e;
   if (int e = tc_maps(v, rows, vcols, ldv, &mv)) return e;
-  if (int e = tc_maps(out, rows, (long long)Hq * TD, ldo, &mo)) return e;
+  if (int e = tc_maps(out, rows, (long long)Hq * D, ldo, &mo)) return e;
   AttnTcParams p{};
   p.mask = mask; p.o = (__nv_bfloat16*)out; p.ldo = ldo; p.lse = lse; p.B = B; p.L = L; p.Hq = Hq; p.Hkv = Hkv;
   p.scale = scale; p.causal = causal; p.qcol0 = qcol0; p.kcol0 = kcol0; p.vcol0 = vcol0;
   p.dbg = g_attn_dbg;
-  static bool attr = false;
-  if (!attr) { DALM_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem)); attr = true; }
-  dim3 grid((L + TB - 1) / TB, Hq, B);
-  attn_fwd_tc_kernel<<<grid, 160, kFwdSmem, (cudaStream_t)stream>>>(mq, mk, mv, mo, p);
-  count_launch();
-  return check_launch("attn_fwd_tc_kernel");
+  p.drop = make_drop(drop_p, drop_seed, drop_stream_id, drop_offset);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D == 128) return launch_tc_fwd<128, false>(mq, mk, mv, mo, p, st);
+  if (drop_p > 0.f) return launch_tc_fwd<64, true>(mq, mk, mv, mo, p, st);
+  return launch_tc_fwd<64, false>(mq, mk, mv, mo, p, st);
 }
 
-// backward: d_out bf16 [B*L, Hq*128 (docols)], delta: fp32 workspace [B,Hq,L]; dq/dk/dv bf16 token-major outputs
+template <int D, bool DROP>
+static int launch_tc_bwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mdo,
+                         const CUtensorMap& mdq, const CUtensorMap& mdk, const CUtensorMap& mdv, const AttnTcParams& p,
+                         const void* out, long long ldo, const void* d_out, long long lddo, float* delta, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    DALM_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<D, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, dkv_smem<D>()));
+    DALM_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<D, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, dq_smem<D>()));
+    attr = true;
+  }
+  const int total_warps = p.B * p.L * p.Hq;
+  attn_tc_delta_kernel<D><<<(total_warps * 32 + 255) / 256, 256, 0, st>>>((const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)d_out,
+                                                                         lddo, delta, p.B, p.L, p.Hq);
+  if (int e = check_launch("attn_tc_delta_kernel")) return e;
+  const int ntiles = (p.L + TB - 1) / TB;
+  attn_bwd_dkv_tc_kernel<D, DROP><<<dim3(ntiles, p.Hkv, p.B), 160, dkv_smem<D>(), st>>>(mq, mk, mv, mdo, mdk, mdv, p);
+  if (int e = check_launch("attn_bwd_dkv_tc_kernel")) return e;
+  attn_bwd_dq_tc_kernel<D, DROP><<<dim3(ntiles, p.Hq, p.B), 160, dq_smem<D>(), st>>>(mq, mk, mv, mdo, mdq, p);
+  count_launch(3);
+  return check_launch("attn_bwd_dq_tc_kernel");
+}
+
+// backward: d_out bf16 [B*L, Hq*D (docols)], delta: fp32 workspace [B,Hq,L]; dq/dk/dv bf16 token-major outputs
 extern "C" int dalm_b200_attention_tc_bwd(const void* q, long long ldq, long long qcols, const void* k, long long ldk,
                                           long long kcols, const void* v, long long ldv, long long vcols,
                                           const int64_t* mask, const void* out, long long ldo, const float* lse,
                                           const void* d_out, long long lddo, long long docols, float* delta, void* dq,
                                           long long lddq, void* dk, long long lddk, void* dv, long long lddv, int B, int L,
-                                          int Hq, int Hkv, int D, float scale, int causal, void* stream) {
-  DALM_REQUIRE(D == 128, "attention_tc_bwd: head_dim must be 128 (got %d)", D);
+                                          int Hq, int Hkv, int D, float scale, int causal, float drop_p,
+                                          unsigned long long drop_seed, unsigned long long drop_stream_id,
+                                          const void* drop_offset, void* stream) {
+  DALM_REQUIRE(D == 128 || D == 64, "attention_tc_bwd: head_dim must be 64 or 128 (got %d)", D);
   DALM_REQUIRE(B > 0 && L > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0, "attention_tc_bwd: bad shape");
   DALM_REQUIRE((lddq % 8) == 0 && (lddk % 8) == 0 && (lddv % 8) == 0 && (ldo % 4) == 0 && (lddo % 4) == 0, "attention_tc_bwd: strides");
   DALM_REQUIRE(((uintptr_t)dq & 15) == 0 && ((uintptr_t)dk & 15) == 0 && ((uintptr_t)dv & 15) == 0, "attention_tc_bwd: output alignment");
+  DALM_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || D == 64), "attention_tc_bwd: dropout needs p in [0,1) and head_dim 64");
   CUtensorMap mq, mk, mv, mdo;
   const long long rows = (long long)B * L;
   if (int e = tc_maps(q, rows, qcols, ldq, &mq)) return e;
@@ -633,28 +745,16 @@ extern "C" int dalm_b200_attention_tc_bwd(const void* q, long long ldq, long lon
   if (int e = tc_maps(v, rows, vcols, ldv, &mv)) return e;
   if (int e = tc_maps(d_out, rows, docols, lddo, &mdo)) return e;
   CUtensorMap mdq, mdk, mdv;
-  if (int e = tc_maps(dq, rows, (long long)Hq * TD, lddq, &mdq)) return e;
-  if (int e = tc_maps(dk, rows, (long long)Hkv * TD, lddk, &mdk)) return e;
-  if (int e = tc_maps(dv, rows, (long long)Hkv * TD, lddv, &mdv)) return e;
+  if (int e = tc_maps(dq, rows, (long long)Hq * D, lddq, &mdq)) return e;
+  if (int e = tc_maps(dk, rows, (long long)Hkv * D, lddk, &mdk)) return e;
+  if (int e = tc_maps(dv, rows, (long long)Hkv * D, lddv, &mdv)) return e;
   AttnTcParams p{};
   p.mask = mask; p.lse = const_cast<float*>(lse); p.delta = delta; p.B = B; p.L = L; p.Hq = Hq; p.Hkv = Hkv;
   p.scale = scale; p.causal = causal;
   p.dq = (__nv_bfloat16*)dq; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv; p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
+  p.drop = make_drop(drop_p, drop_seed, drop_stream_id, drop_offset);
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr = false;
-  if (!attr) {
-    DALM_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkvSmem));
-    DALM_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem));
-    attr = true;
-  }
-  const int total_warps = B * L * Hq;
-  attn_tc_delta_kernel<<<(total_warps * 32 + 255) / 256, 256, 0, st>>>((const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)d_out,
-                                                                      lddo, delta, B, L, Hq);
-  if (int e = check_launch("attn_tc_delta_kernel")) return e;
-  const int ntiles = (L + TB - 1) / TB;
-  attn_bwd_dkv_tc_kernel<<<dim3(ntiles, Hkv, B), 160, kDkvSmem, st>>>(mq, mk, mv, mdo, mdk, mdv, p);
-  if (int e = check_launch("attn_bwd_dkv_tc_kernel")) return e;
-  attn_bwd_dq_tc_kernel<<<dim3(ntiles, Hq, B), 160, kDqSmem, st>>>(mq, mk, mv, mdo, mdq, p);
-  count_launch(3);
-  return check_launch("attn_bwd_dq_tc_kernel");
+  if (D == 128) return launch_tc_bwd<128, false>(mq, mk, mv, mdo, mdq, mdk, mdv, p, out, ldo, d_out, lddo, delta, st);
+  if (drop_p > 0.f) return launch_tc_bwd<64, true>(mq, mk, mv, mdo, mdq, mdk, mdv, p, out, ldo, d_out, lddo, delta, st);
+  return launch_tc_bwd<64, false>(mq, mk, mv, mdo, mdq, mdk, mdv, p, out, ldo, d_out, lddo, delta, st);
 }

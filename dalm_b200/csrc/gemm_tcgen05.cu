@@ -37,10 +37,30 @@ struct GemmEpilogue {
   float alpha;
   int M, N, K;
   DropCfg drop;         // dropout on act(alpha*acc+bias) BEFORE the residual add (BertSelfOutput / BertOutput); p = 0 => off
+  int group_m;          // tile rasterisation: bands of group_m m-tiles, n-tiles walked serpentine inside a band (0 = m-fastest)
 };
 
+// Tile rasterisation. Persistent CTA i works on tiles i, i + grid, ...: the tiles resident at one moment are ~148 consecutive
+// indices, and (L2 serving the CTAs that share a panel) DRAM sees each A panel / B panel of that footprint once per wave.
+// m-fastest order makes the footprint num_m x 4 tiles: all of A is re-read by every wave (profiles/r01_gemm_v3_ncu_full_raw.csv:
+// 652 MB for the 343 MB down-projection). Bands of group_m m-tiles make it ~square (group_m x 148/group_m), which minimises
+// rows-of-A + rows-of-B per wave, and the serpentine n order lets consecutive waves of a band re-use its A panel from L2.
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int gm, int& m_blk, int& n_blk) {
+  if (gm <= 0) { m_blk = tile % num_m; n_blk = tile / num_m; return; }
+  const int band_tiles = gm * num_n;
+  const int band = tile / band_tiles;
+  const int r = tile - band * band_tiles;
+  const int m0 = band * gm;
+  const int h = min(gm, num_m - m0);                            // the last band may be shorter
+  const int n = r / h;
+  m_blk = m0 + (r - n * h);
+  n_blk = (band & 1) ? (num_n - 1 - n) : n;
+}
+
 // Epilogue math for one thread = one output row, 32 consecutive columns [col0, col0+32): alpha, bias, GELU, residual.
-__device__ __forceinline__ void epilogue_math(const GemmEpilogue& ep, const uint32_t* v, float* f, int row, int col0, bool row_ok) {
+template <bool PRE = false>
+__device__ __forceinline__ void epilogue_math(const GemmEpilogue& ep, const uint32_t* v, float* f, int row, int col0, bool row_ok,
+                                              const float4* rpre = nullptr) {
   const int N = ep.N;
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * ep.alpha;
@@ -63,7 +83,10 @@ __device__ __forceinline__ void epilogue_math(const GemmEpilogue& ep, const uint
       for (int j = 0; j < 8; ++j) f[g * 8 + j] *= sc[j];
     }
   }
-  if (ep.resid && row_ok) {
+  if constexpr (PRE) {                                          // fp32 residual already in registers (prefetched a block ahead)
+#pragma unroll
+    for (int g = 0; g < 8; ++g) { f[g * 4 + 0] += rpre[g].x; f[g * 4 + 1] += rpre[g].y; f[g * 4 + 2] += rpre[g].z; f[g * 4 + 3] += rpre[g].w; }
+  } else if (ep.resid && row_ok) {
     if (ep.resid_f32) {
       const float* r = reinterpret_cast<const float*>(ep.resid) + (size_t)row * ep.ldr + col0;
 #pragma unroll
@@ -110,6 +133,19 @@ __device__ __forceinline__ void epilogue_drain_tile(const GemmEpilogue& ep, cons
   unsigned char* tile = staging + grp * kStageTileBytes;       // one staging tile per group
   unsigned char* st = tile + row_in_tile * 128;
   const int sw = row_in_tile & 7;
+  // fp32 residual (o_proj / down-projection: x_out = x + y): this thread's 128 bytes of the NEXT store block are fetched
+  // while the current block is processed, so the HBM latency of the residual no longer sits in the block's serial chain
+  // (tmem ld -> residual ld -> math -> st.shared -> TMA store), which made this epilogue the slowest GEMM shape in round 1
+  const bool rpf = ep.out_f32 && ep.resid != nullptr && ep.resid_f32;
+  float4 rnext[8];
+  auto fetch_resid = [&](int cc) {
+    const int cg0 = tile_col0 + cc;
+    const float* r = reinterpret_cast<const float*>(ep.resid) + (size_t)row * ep.ldr + cg0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      rnext[g] = (row_ok && cc < BN && cg0 + g * 4 < N) ? *reinterpret_cast<const float4*>(r + g * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  if (rpf) fetch_resid(grp * sb_cols);
 #pragma unroll 1
   for (int c = grp * sb_cols; c < BN; c += kEpiGroups * sb_cols) {   // the two groups interleave store blocks
     const int col0 = tile_col0 + c;
@@ -119,8 +155,15 @@ __device__ __forceinline__ void epilogue_drain_tile(const GemmEpilogue& ep, cons
     if (ep.out_f32) {
       uint32_t v[32]; float f[32];
       tmem_ld_32x32(t_row + (uint32_t)c, v);
+      float4 rcur[8];
+      if (rpf) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) rcur[g] = rnext[g];
+        fetch_resid(c + kEpiGroups * sb_cols);
+      }
       tmem_ld_wait();
-      epilogue_math(ep, v, f, row, col0, row_ok);
+      if (rpf) epilogue_math<true>(ep, v, f, row, col0, row_ok, rcur);
+      else     epilogue_math<false>(ep, v, f, row, col0, row_ok);
 #pragma unroll
       for (int g = 0; g < 8; ++g)
         *reinterpret_cast<float4*>(st + ((g ^ sw) << 4)) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
@@ -211,7 +254,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        int m_blk, n_blk;
+        tile_coords(tile, num_m, num_n, ep.group_m, m_blk, n_blk);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           unsigned char* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -271,7 +315,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int grp = (warp - 4) >> 2;                            // epilogue group 0 / 1
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      int m_blk, n_blk;
+      tile_coords(tile, num_m, num_n, ep.group_m, m_blk, n_blk);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -534,6 +579,10 @@ extern "C" int dalm_b200_gemm_bf16(int layout, const void* A, long long lda, con
                                    int max_ctas, float drop_p, unsigned long long drop_seed,
                                    unsigned long long drop_stream_id, const void* drop_offset, void* stream);
 
+// tile rasterisation override: -1 = legacy m-fastest order, 0 = automatic band height (default), > 0 = that many m-tiles
+static int g_group_m_override = 0;
+extern "C" void dalm_b200_gemm_set_raster(int group_m) { g_group_m_override = group_m; }
+
 // D[M,N] = act(alpha * A[M,K] B[N,K]^T + bias) + resid
 //   A: bf16 [M,K] row stride lda;  B: bf16 [N,K] row stride ldb;  out: bf16|fp32 [M,N] row stride ldo
 //   block_n: 0 = auto, or one of 64/128/256.   max_ctas: 0 = all SMs (used by tests to force multi-tile-per-CTA paths)
@@ -596,8 +645,23 @@ extern "C" int dalm_b200_gemm_bf16(int layout, const void* A, long long lda, con
   else             { if (int e = get_tmap(B, N, K, ldb, pair ? tile_n / 2 : tile_n, &tb)) return e; }
   if (int e = get_tmap(out, M, N, ldo, 128, &to, out_f32)) return e;
   DALM_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "gemm: dropout p must be in [0,1)");
+  // band height of the tile rasterisation: the footprint of one wave (kNumSMs tiles) is group_m x (kNumSMs / group_m) tiles;
+  // rows-of-A + rows-of-B of that footprint (= DRAM traffic per wave) is smallest for group_m = sqrt(kNumSMs * BN / 128);
+  // bands are equalised over num_m. One-wave problems keep the m-fastest order.
+  int group_m = 0;
+  {
+    const int num_m = (M + 127) / 128, num_n = (N + tile_n - 1) / tile_n;
+    if (g_group_m_override > 0) group_m = g_group_m_override;
+    else if (g_group_m_override == 0 && (long long)num_m * num_n > kNumSMs) {
+      const double ideal = sqrt((double)kNumSMs * tile_n / 128.0);
+      int nbands = (int)(num_m / ideal + 0.5);
+      if (nbands < 1) nbands = 1;
+      group_m = (num_m + nbands - 1) / nbands;
+    }
+    if (group_m >= num_m && (g_group_m_override <= 0)) group_m = 0;   // one band == m-fastest
+  }
   GemmEpilogue ep{out, ldo, out_f32, bias, resid, ldr, resid_f32, act, alpha, M, N, K,
-                  make_drop(drop_p, drop_seed, drop_stream_id, drop_offset)};
+                  make_drop(drop_p, drop_seed, drop_stream_id, drop_offset), group_m};
   cudaStream_t st = (cudaStream_t)stream;
   if (bn == 2256) return launch_gemm2<256>(ta, tb, to, ep, max_ctas, st);
   if (bn == 3256) return launch_gemm2<256, 3>(ta, tb, to, ep, max_ctas, st);     // tuning probes (fewer stages)

@@ -315,7 +315,7 @@ class BertEncoder(torch.nn.Module):
             lses = []
             for si, (B, L, mask, s0) in enumerate(ctx.segs):
                 rows = slice(s0, s0 + B * L)
-                _, lse = ops.attention_fwd(qkv[rows, :H], qkv[rows, H:2 * H], qkv[rows, 2 * H:], mask, B, L, self.nh,
+                _, lse = ops.attention_auto_fwd(qkv[rows, :H], qkv[rows, H:2 * H], qkv[rows, 2 * H:], mask, B, L, self.nh,
                                            self.nh, self.hd, causal=False, out=att[rows],
                                            drop=self._drop(self.p_attn, call, li, 8 + si))
                 lses.append(lse)
@@ -393,7 +393,7 @@ class BertEncoder(torch.nn.Module):
             dqkv_aug = _aug_buf(M, 3 * H, Ra, self.dev)
             for si, ((B, L, mask, s0), lse) in enumerate(zip(ctx.segs, a.lse)):
                 rows = slice(s0, s0 + B * L)
-                ops.attention_bwd(a.qkv[rows, :H], a.qkv[rows, H:2 * H], a.qkv[rows, 2 * H:], mask, a.att[rows], lse,
+                ops.attention_auto_bwd(a.qkv[rows, :H], a.qkv[rows, H:2 * H], a.qkv[rows, 2 * H:], mask, a.att[rows], lse,
                                   datt[rows], B, L, self.nh, self.nh, self.hd, causal=False, dq=dqkv_aug[rows, :H],
                                   dk=dqkv_aug[rows, H:2 * H], dv=dqkv_aug[rows, 2 * H:3 * H],
                                   drop=self._bdrop(ctx, self.p_attn, l, 8 + si))

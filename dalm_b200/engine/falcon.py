@@ -176,7 +176,7 @@ class FalconDecoder(torch.nn.Module):
             ops.rope_pos_(qkv, 0, self.nh + 1, self.hd, cos_t, sin_t, pos)
         if kv_sink is not None:
             kv_sink(qkv)
-        att, lse = ops.attention_fwd(qkv[:, :self.Nq], qkv[:, self.Nq:self.Nq + self.hd], qkv[:, self.Nq + self.hd:],
+        att, lse = ops.attention_auto_fwd(qkv[:, :self.Nq], qkv[:, self.Nq:self.Nq + self.hd], qkv[:, self.Nq + self.hd:],
                                      mask, B, L, self.nh, 1, self.hd, causal=True)
         t = ops.gemm(att, W["Wd"], out_dtype=f32, resid=x)                            # x + attention branch
         if keep:
@@ -206,7 +206,7 @@ class FalconDecoder(torch.nn.Module):
         ops.wgrad_(dx16, a.att, G("Wd"), acc)
         datt = ops.gemm(dx16, W["Wd"], layout=1)                                      # [M,Nq]
         dqkv = torch.empty(M, self.Nq + 2 * hd, dtype=bf16, device=self.dev)
-        ops.attention_bwd(a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + hd], a.qkv[:, self.Nq + hd:], mask, a.att, a.lse, datt,
+        ops.attention_auto_bwd(a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + hd], a.qkv[:, self.Nq + hd:], mask, a.att, a.lse, datt,
                           B, L, self.nh, 1, hd, causal=True, dq=dqkv[:, :self.Nq], dk=dqkv[:, self.Nq:self.Nq + hd],
                           dv=dqkv[:, self.Nq + hd:])                                  # dK / dV summed over the 71 query heads
         ops.rope_(dqkv, 0, self.nh + 1, hd, cos_t, sin_t, L, backward=True)

@@ -330,8 +330,7 @@ class LlamaDecoder(torch.nn.Module):
                 ops.rope_pos_(a.qkv, 0, self.nh + self.nkv, self.hd, cos_t, sin_t, pos)
             if kv_sink is not None:
                 kv_sink(li, a.qkv)
-            attn_fwd = ops.attention_tc_fwd if self.hd == 128 else ops.attention_fwd     # tcgen05/TMEM path for head_dim 128
-            a.att, a.lse = attn_fwd(a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + self.Nkv],
+            a.att, a.lse = ops.attention_auto_fwd(                                       # tcgen05/TMEM path for head_dim 64 / 128a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + self.Nkv],
                                     a.qkv[:, self.Nq + self.Nkv:], ctx.mask, B, L, self.nh, self.nkv, self.hd, causal=True)
             a.x_mid = ops.gemm(a.att, W["Wo"], out_dtype=f32, resid=x)
             a.h2, a.rstd2 = ops.rmsnorm_fwd(a.x_mid, W["g2"], self.eps)
@@ -435,8 +434,7 @@ class LlamaDecoder(torch.nn.Module):
                 ops.wgrad_(dmid16, a.att, G(l, "Wo"), acc)
             datt = self._dgrad(dmid16, W, "Wo")                                    # [M,Nq]
             dqkv = _aug_buf(M, self.Nqkv, Ra, self.dev)
-            attn_bwd = ops.attention_tc_bwd if self.hd == 128 else ops.attention_bwd
-            attn_bwd(a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + self.Nkv], a.qkv[:, self.Nq + self.Nkv:],
+            ops.attention_auto_bwd(a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + self.Nkv], a.qkv[:, self.Nq + self.Nkv:],
                      ctx.mask, a.att, a.lse, datt, B, L, self.nh, self.nkv, self.hd, causal=True,
                      dq=dqkv[:, :self.Nq], dk=dqkv[:, self.Nq:self.Nq + self.Nkv],
                      dv=dqkv[:, self.Nq + self.Nkv:self.Nqkv])

@@ -238,22 +238,24 @@ def attention_fwd(q, k, v, mask, B: int, L: int, Hq: int, Hkv: int, D: int, caus
 
 
 def attention_tc_fwd(q, k, v, mask, B: int, L: int, Hq: int, Hkv: int, D: int, causal: bool, out=None,
-                     scale: Optional[float] = None):
-    """tcgen05/TMEM attention forward (head_dim 128). Same contract as attention_fwd."""
+                     scale: Optional[float] = None, drop: Optional[Drop] = None):
+    """tcgen05/TMEM attention forward (head_dim 128 or 64; probability dropout at 64). Same contract as attention_fwd."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _chk(t, bf16, n)
     if out is None:
         out = torch.empty(B * L, Hq * D, dtype=bf16, device=q.device)
     lse = torch.empty(B, Hq, L, dtype=f32, device=q.device)
+    if mask is not None and mask.dtype != i64:
+        raise _lib.DalmB200Error("attention: mask must be int64")
     scale = 1.0 / math.sqrt(D) if scale is None else scale
     _lib.call("dalm_b200_attention_tc_fwd", _p(q), _ld(q), q.shape[1], 0, _p(k), _ld(k), k.shape[1], 0, _p(v), _ld(v), v.shape[1], 0,
-              _p(mask), _p(out), _ld(out), _p(lse), B, L, Hq, Hkv, D, float(scale), 1 if causal else 0, _stream())
+              _p(mask), _p(out), _ld(out), _p(lse), B, L, Hq, Hkv, D, float(scale), 1 if causal else 0, *_d(drop), _stream())
     return out, lse
 
 
 def attention_tc_bwd(q, k, v, mask, out, lse, d_out, B: int, L: int, Hq: int, Hkv: int, D: int, causal: bool,
-                     dq=None, dk=None, dv=None, scale: Optional[float] = None):
-    """tcgen05/TMEM attention backward (head_dim 128). Same contract as attention_bwd."""
+                     dq=None, dk=None, dv=None, scale: Optional[float] = None, drop: Optional[Drop] = None):
+    """tcgen05/TMEM attention backward (head_dim 128 or 64). Same contract as attention_bwd."""
     dev = q.device
     if dq is None: dq = torch.empty(B * L, Hq * D, dtype=bf16, device=dev)
     if dk is None: dk = torch.empty(B * L, Hkv * D, dtype=bf16, device=dev)
@@ -262,8 +264,22 @@ def attention_tc_bwd(q, k, v, mask, out, lse, d_out, B: int, L: int, Hq: int, Hk
     scale = 1.0 / math.sqrt(D) if scale is None else scale
     _lib.call("dalm_b200_attention_tc_bwd", _p(q), _ld(q), q.shape[1], _p(k), _ld(k), k.shape[1], _p(v), _ld(v), v.shape[1],
               _p(mask), _p(out), _ld(out), _p(lse), _p(d_out), _ld(d_out), d_out.shape[1], _p(delta), _p(dq), _ld(dq),
-              _p(dk), _ld(dk), _p(dv), _ld(dv), B, L, Hq, Hkv, D, float(scale), 1 if causal else 0, _stream())
+              _p(dk), _ld(dk), _p(dv), _ld(dv), B, L, Hq, Hkv, D, float(scale), 1 if causal else 0, *_d(drop), _stream())
     return dq, dk, dv
+
+
+def attention_auto_fwd(q, k, v, mask, B, L, Hq, Hkv, D, causal, out=None, scale=None, drop=None):
+    """head_dim 64 / 128 -> tcgen05 kernels (csrc/attention_tc.cu); head_dim 32 (bge-small) -> mma.sync kernels.
+    DALM_B200_ATTN_TC=0 forces the mma.sync path (cross-checks)."""
+    if D in (64, 128) and os.environ.get("DALM_B200_ATTN_TC", "1") != "0":
+        return attention_tc_fwd(q, k, v, mask, B, L, Hq, Hkv, D, causal, out=out, scale=scale, drop=drop)
+    return attention_fwd(q, k, v, mask, B, L, Hq, Hkv, D, causal, out=out, scale=scale, drop=drop)
+
+
+def attention_auto_bwd(q, k, v, mask, out, lse, d_out, B, L, Hq, Hkv, D, causal, dq=None, dk=None, dv=None, scale=None, drop=None):
+    if D in (64, 128) and os.environ.get("DALM_B200_ATTN_TC", "1") != "0":
+        return attention_tc_bwd(q, k, v, mask, out, lse, d_out, B, L, Hq, Hkv, D, causal, dq=dq, dk=dk, dv=dv, scale=scale, drop=drop)
+    return attention_bwd(q, k, v, mask, out, lse, d_out, B, L, Hq, Hkv, D, causal, dq=dq, dk=dk, dv=dv, scale=scale, drop=drop)
 
 
 def attention_bwd(q, k, v, mask, out, lse, d_out, B: int, L: int, Hq: int, Hkv: int, D: int, causal: bool,

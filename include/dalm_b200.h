@@ -79,6 +79,9 @@ int dalm_b200_gemm_bf16(int layout, const void* A, long long lda, const void* B,
                         long long ldr, int resid_f32, int block_n, int max_ctas, float drop_p, unsigned long long drop_seed,
                         unsigned long long drop_stream_id, const void* drop_offset, void* stream);
 void dalm_b200_gemm_clear_cache(void);
+/* tile rasterisation of the persistent GEMM (tuning / test hook): -1 = m-fastest order, 0 = automatic band height
+ * (default: ~square wave footprint, serpentine inside a band), > 0 = bands of that many 128-row m-tiles */
+void dalm_b200_gemm_set_raster(int group_m);
 
 /* ---- attention (same call sites; HF eager/SDPA attention) ---- */
 int dalm_b200_attention_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
@@ -91,12 +94,15 @@ int dalm_b200_attention_bwd(const void* q, long long ldq, const void* k, long lo
                             long long lddv, int B, int L, int Hq, int Hkv, int D, float scale, int causal, float drop_p, unsigned long long drop_seed,
     unsigned long long drop_stream_id, const void* drop_offset, void* stream);
 
-/* tcgen05 / TMEM / TMA attention for head_dim 128 (decoder). q/k/v are bf16 token-major matrices [B*L, *cols] with row
- * stride ld*; head h starts at column *col0 + h*128. Same outputs as dalm_b200_attention_fwd / _bwd. */
+/* tcgen05 / TMEM / TMA attention: head_dim 128 (Llama decoder) or 64 (bge-large encoder incl. attention-probability dropout;
+ * Falcon MQA decoder). q/k/v are bf16 token-major matrices [B*L, *cols] with row stride ld*; head h starts at column
+ * *col0 + h*D. Same outputs, mask semantics and dropout element indexing as dalm_b200_attention_fwd / _bwd (the mma.sync
+ * kernels, kept for head_dim 32 and as a cross-check). */
 int dalm_b200_attention_tc_fwd(const void* q, long long ldq, long long qcols, int qcol0, const void* k, long long ldk,
                                long long kcols, int kcol0, const void* v, long long ldv, long long vcols, int vcol0,
                                const int64_t* mask, void* out, long long ldo, float* lse, int B, int L, int Hq, int Hkv,
-                               int D, float scale, int causal, void* stream);
+                               int D, float scale, int causal, float drop_p, unsigned long long drop_seed,
+                               unsigned long long drop_stream_id, const void* drop_offset, void* stream);
 
 /* tuning aid: a device buffer of 64 int64 receives clock64 phase timestamps of one forward CTA (NULL disables) */
 void dalm_b200_attention_tc_set_debug(void* dev_buffer_64xint64);
@@ -104,7 +110,9 @@ int dalm_b200_attention_tc_bwd(const void* q, long long ldq, long long qcols, co
                                const void* v, long long ldv, long long vcols, const int64_t* mask, const void* out,
                                long long ldo, const float* lse, const void* d_out, long long lddo, long long docols,
                                float* delta, void* dq, long long lddq, void* dk, long long lddk, void* dv, long long lddv,
-                               int B, int L, int Hq, int Hkv, int D, float scale, int causal, void* stream);
+                               int B, int L, int Hq, int Hkv, int D, float scale, int causal, float drop_p,
+                               unsigned long long drop_seed, unsigned long long drop_stream_id, const void* drop_offset,
+                               void* stream);
 
 /* ---- row-wise pieces of the encoder / decoder blocks ---- */
 int dalm_b200_layernorm_fwd(const float* z, const float* gamma, const float* beta, float* y32, void* y16, long long ld16,

@@ -31,8 +31,15 @@ def test_rank_strided_batches(tmp_path, monkeypatch):
 
 
 def test_reference_arm_line(monkeypatch, capsys, tmp_path):
+    """the reference arm reports what it RAN: `steps` / `warmup` are the executed counts (the CLI's are kept beside them),
+    nothing is extrapolated"""
     import bench
-    monkeypatch.setattr(bench, "cpu_reference_samples_per_s", lambda batch, steps=1, rows=6: (0.25, 8, "stubbed sample"))
+    calls = {}
+
+    def fake_run(batch, rows, warmup, steps, budget_s):
+        calls.update(rows=rows, warmup=warmup, steps=steps, budget_s=budget_s)
+        return {"value": 0.25, "cores": 8, "steps_run": 2, "warmup_run": 1, "s_per_step": 8.0, "rows": rows, "sample": "stubbed sample"}
+    monkeypatch.setattr(bench, "cpu_reference_run", fake_run)
     monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--gpus", "2", "--steps", "3", "--warmup", "1"])
     monkeypatch.setenv("RANK", "1"); monkeypatch.setenv("WORLD_SIZE", "2")
     bench.main()                                                      # other ranks exit without work and without output
@@ -42,8 +49,11 @@ def test_reference_arm_line(monkeypatch, capsys, tmp_path):
     out = [l for l in capsys.readouterr().out.splitlines() if l.strip()]
     assert len(out) == 1                                              # ONE JSON line
     line = json.loads(out[0])
+    assert calls["steps"] == 3 and calls["warmup"] == 1 and calls["rows"] == 2
     assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["unit"] == "samples/s"
-    assert line["higher_is_better"] is True and line["n_gpus"] == 2 and line["steps"] == 3 and line["warmup"] == 1
+    assert line["higher_is_better"] is True and line["n_gpus"] == 2
+    assert line["steps"] == 2 and line["warmup"] == 1 and line["steps_requested"] == 3       # executed, not echoed
+    assert line["extrapolated"] is False and line["ms_per_step"] == 8000.0 and line["rows_per_step"] == 2
     assert line["value"] == 0.25 and line["cpu_baseline"] == {"value": 0.25, "unit": "samples/s", "cores": 8, "kind": "port", "sample": "stubbed sample"}
     assert line["e2e"] == {"value": 0.25, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     args = bench.parse()

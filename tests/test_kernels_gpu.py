@@ -311,3 +311,33 @@ def test_lora_wgrad_pack_adam(cuda_dev):
         opt.step()
         ops.adam_step_(p, grad, m, v, 1e-3, 0.9, 0.999, 1e-8, step)
     assert (p - p_ref.detach()).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("M,N,K,kind", [(4608, 4096, 1024, "f32+resid"), (1300, 2304, 520, "bf16"), (3204, 1024, 256, "f32+resid"),
+                                        (2000, 4096, 192, "f32")])
+def test_gemm_rasterisation_orders_give_identical_results(cuda_dev, M, N, K, kind):
+    """the tile walk (m-fastest / automatic ~square bands / explicit band heights, serpentine n order) only permutes which
+    CTA computes which tile: every order must produce bit-identical outputs, including the register-prefetched fp32 residual"""
+    from dalm_b200 import _lib, ops
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(cuda_dev, torch.bfloat16)
+    b = (torch.randn(N, K, generator=g) * 0.1).to(cuda_dev, torch.bfloat16)
+    resid = torch.randn(M, N, generator=g).to(cuda_dev) if kind == "f32+resid" else None
+    odt = torch.bfloat16 if kind == "bf16" else torch.float32
+    lib = _lib.load()
+    outs = []
+    try:
+        for gm in (-1, 0, 1, 5, 7, 64):
+            lib.dalm_b200_gemm_set_raster(gm)
+            for max_ctas in (0, 13):
+                outs.append(ops.gemm(a, b, out_dtype=odt, resid=resid, max_ctas=max_ctas))
+    finally:
+        lib.dalm_b200_gemm_set_raster(0)
+    ref = a.float() @ b.float().t() + (resid if resid is not None else 0)
+    assert ((outs[0].float() - ref).norm() / ref.norm()).item() < (5e-3 if kind == "bf16" else 1e-4)
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    if resid is not None:                                     # in-place accumulation (out aliases resid), as wgrad uses it
+        acc = resid.clone()
+        ops.gemm(a, b, out=acc, resid=acc)
+        assert torch.equal(acc, outs[0])
