@@ -26,6 +26,22 @@ METRIC = "RAG-e2e train-step samples/sec (bge-large + Llama-2-7B, bs=18)"
 BS, LQ, LP, LG = 18, 50, 128, 256
 STEP_TFLOP_PEFT = 127.6          # algorithmic TFLOP per bs-18 step in PEFT mode (fwd + dgrad + attn-bwd extra)
 
+# BASELINE.json configs this bench can run (default cfg-3 = the config the headline metric is quoted on; the others are
+# supplementary lines for `profiles/`). tflop = algorithmic TFLOP per step (SURVEY §8d table / formulae).
+CONFIGS = {
+    "cfg-3": dict(metric=METRIC, bs=18, lg=256, tflop=127.6, gen="llama", peft="both",
+                  workload="cfg-3 train_rage2e {r} + {g} + PEFT(both) LoRA r=8, bs=18/GPU, Lq50/Lp128/Lg256"),
+    "cfg-3-full": dict(metric="RAG-e2e train-step samples/sec, full fine-tuning (bge-large + Llama-2-7B, bs=18)", bs=18, lg=256, tflop=190.4,
+                       gen="llama", peft=None,
+                       workload="cfg-3/4 train_rage2e {r} + {g}, use_peft=None (the reference's CLI default: every parameter trained, fp32 Adam), bs=18/GPU, Lq50/Lp128/Lg256"),
+    "cfg-2": dict(metric="retriever-only train-step samples/sec (bge-large, bs=150)", bs=150, lg=0, tflop=33.1, gen=None, peft="retriever",
+                  workload="cfg-2 train_retriever_only {r} + PEFT LoRA r=8, per-device bs=150, Lq50/Lp128"),
+    "cfg-5": dict(metric="RAG-e2e train-step samples/sec (bge-large + Falcon-7B, seq 2048, bs=18)", bs=18, lg=2048, tflop=1669.0, gen="falcon", peft="retriever",
+                  workload="cfg-5 train_rage2e {r} (LoRA) + falcon-7b FULLY fine-tuned (reference semantics of --use-peft retriever: Falcon has no q_proj/v_proj), bs=18/GPU, Lg=2048, per-layer recomputation"),
+    "cfg-5-frozen": dict(metric="RAG-e2e train-step samples/sec (bge-large + frozen Falcon-7B, seq 2048, bs=18)", bs=18, lg=2048, tflop=558.2, gen="falcon-frozen", peft="retriever",
+                         workload="cfg-5 variant: {r} (LoRA) + falcon-7b FROZEN (forward only), bs=18/GPU, Lg=2048"),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -33,6 +49,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=str, default="cfg-3", choices=sorted(CONFIGS),
+                    help="BASELINE.json config: cfg-3 (default, the metric's config) | cfg-3-full (use_peft=None) | cfg-2 | cfg-5 | cfg-5-frozen")
     ap.add_argument("--retriever", type=str, default="bge-large-en")
     ap.add_argument("--generator", type=str, default="Llama-2-7b-hf")
     ap.add_argument("--cpu-baseline", type=int, default=1, help="0 to skip the bounded CPU-oracle timing on rank 0")
@@ -229,8 +247,29 @@ def ncu_traffic():
 
 
 def workload_name(args) -> str:
-    return (f"cfg-3 train_rage2e {args.retriever} + {args.generator} + PEFT(both) LoRA r=8, bs={BS}/GPU, "
-            f"Lq{LQ}/Lp{LP}/Lg{LG}")
+    return CONFIGS[getattr(args, "config", "cfg-3")]["workload"].format(r=args.retriever, g=args.generator)
+
+
+def random_batches(n: int, cfgd, rank: int, seed: int = 0):
+    """token-id batches for the supplementary configs: uniform random ids, all-ones masks (every sequence at full length, as in
+    the 'full' synthetic set the default config tokenises) - identical compute to tokenised text of that length"""
+    import torch
+    g = torch.Generator().manual_seed(seed * 1000 + rank)
+    B = cfgd["bs"]
+    rnd = lambda L, V: torch.randint(5, V, (B, L), generator=g)
+    ones = lambda L: torch.ones(B, L, dtype=torch.int64)
+    out = []
+    for _ in range(n):
+        if cfgd["gen"] is None:
+            out.append({"query_input_ids": rnd(LQ, 30522), "query_attention_mask": ones(LQ),
+                        "passage_input_ids": rnd(LP, 30522), "passage_attention_mask": ones(LP)})
+        else:
+            V = 32000 if cfgd["gen"] == "llama" else 65024
+            out.append({"retriever_query_input_ids": rnd(LQ, 30522), "retriever_query_attention_mask": ones(LQ),
+                        "retriever_passage_input_ids": rnd(LP, 30522), "retriever_passage_attention_mask": ones(LP),
+                        "generator_input_input_ids": rnd(cfgd["lg"], V), "generator_input_attention_mask": ones(cfgd["lg"]),
+                        "query_passage_input_len": torch.full((B,), min(200, cfgd["lg"] // 2))})
+    return out
 
 
 def main():
@@ -279,19 +318,44 @@ def main():
     from dalm_b200.training.utils.train_utils import GraphedStep, fused_rag_step
 
     _lib.call("dalm_b200_probe_device")
+    cfgd = CONFIGS[args.config]
+    B_step = cfgd["bs"]
+    bf = torch.bfloat16
     bcfg = dict(synthetic.bert_config(args.retriever), _device_rng=True)
-    lcfg = dict(synthetic.llama_config(args.generator), _device_rng=True)
-    enc = BertEncoder(bcfg, params.random_state_dict("bert", bcfg, seed=0, dtype=torch.bfloat16, device=dev), device=dev, lora=True)
-    dec = LlamaDecoder(lcfg, params.random_state_dict("llama", lcfg, seed=0, dtype=torch.bfloat16, device=dev), device=dev, lora=True)
-    torch.cuda.empty_cache()
-    model = AutoModelForRagE2E("", "", get_peft=Mode.BOTH, _retriever=enc, _generator=dec, _load_tokenizers=False)
+    full_r = cfgd["peft"] is None
+    enc = BertEncoder(bcfg, params.random_state_dict("bert", bcfg, seed=0, dtype=bf, device=dev), device=dev, lora=not full_r, full=full_r)
+    if cfgd["gen"] is None:                                   # cfg-2: retriever-only trainer (train_retriever_only.py:365-379)
+        from dalm_b200.models.retriever_only_base_model import AutoModelForSentenceEmbedding
+        from dalm_b200.training.utils.train_utils import fused_retriever_step as step_fn
+        model = AutoModelForSentenceEmbedding("", use_bnb=False, get_peft=True, _model=enc, _load_tokenizer=False)
+        banks = enc.banks()
+        repack = enc.repack_lora
+    else:
+        from dalm_b200.training.utils.train_utils import fused_rag_step as step_fn
+        if cfgd["gen"] == "llama":
+            lcfg = dict(synthetic.llama_config(args.generator), _device_rng=True)
+            dec = LlamaDecoder(lcfg, params.random_state_dict("llama", lcfg, seed=0, dtype=bf, device=dev), device=dev,
+                               lora=cfgd["peft"] == "both", full=cfgd["peft"] is None)
+        else:
+            from dalm_b200.engine.falcon import FalconDecoder
+            fcfg = dict(synthetic.falcon_config("falcon-7b"), _device_rng=True)
+            dec = FalconDecoder(fcfg, params.random_state_dict("falcon", fcfg, seed=0, dtype=bf, device=dev), device=dev,
+                                full=cfgd["gen"] == "falcon")
+        torch.cuda.empty_cache()
+        model = AutoModelForRagE2E("", "", get_peft={"both": Mode.BOTH, "retriever": Mode.RETRIEVER, None: None}[cfgd["peft"]],
+                                   _retriever=enc, _generator=dec, _load_tokenizers=False)
+        banks = model.trainable_banks()
+        repack = model.repack
     # PEFT initialises B = 0; after a few optimizer steps it is not. Same seed on every rank (DDP broadcast semantics).
     opt = FusedAdam(model.parameters(), lr=1e-4)
-    banks = model.trainable_banks()
     model.train()                          # reference train_rage2e.py:421: dropout sites are live during the timed steps
 
     n_batches = args.warmup + args.steps
-    host_batches = make_batches(n_batches, rank, world, cache_dir)
+    if args.config == "cfg-3":
+        host_batches = make_batches(n_batches, rank, world, cache_dir)
+    else:
+        host_batches = random_batches(min(n_batches, 4), cfgd, rank)
+        host_batches = [host_batches[i % len(host_batches)] for i in range(n_batches)]
     pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host_batches]
     resident = [{k: v.to(dev) for k, v in b.items()} for b in host_batches]
     h2d_bytes = sum(v.numel() * v.element_size() for v in host_batches[0].values())
@@ -300,9 +364,9 @@ def main():
     from dalm_b200.accel import GradientSync
     sync = GradientSync(banks, world, dev, nccl=True)
     graphed = None
-    if args.graph:
+    if args.graph and not sync.overlaps_backward:          # full fine-tuning on N > 1: bucket all-reduces are issued during backward
         try:
-            graphed = GraphedStep(fused_rag_step, model, resident[0], 100.0, zero_grads=opt.zero_grad)
+            graphed = GraphedStep(step_fn, model, resident[0], 100.0, zero_grads=opt.zero_grad)
         except Exception as e:
             if rank == 0:
                 print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); eager launches", file=sys.stderr, flush=True)
@@ -313,12 +377,12 @@ def main():
         if record:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             ev[0].record()
-        out = graphed(batch) if (graphed is not None and not eager) else fused_rag_step(model, batch, 100.0, backward=True)
+        out = graphed(batch) if (graphed is not None and not eager) else step_fn(model, batch, 100.0, backward=True)
         if record:
             ev[1].record()
         loss = sync.reduce(out["loss"])                      # ONE all-reduce: both LoRA banks' gradients (mean) + the loss (rank sum)
         opt.step()
-        model.repack()
+        repack()
         opt.zero_grad()
         if record:
             ev[2].record()
@@ -353,7 +417,7 @@ def main():
         return t.item(), loss, _lib.launch_count()
 
     # ---- device-resident run (value) -------------------------------------------------------------------------
-    timer = ops.GemmTimer(capacity=1200 * args.steps + 64)
+    timer = ops.GemmTimer(capacity=2000 * args.steps + 64)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -419,18 +483,20 @@ def main():
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
-    samples = BS * world * args.steps
+    samples = B_step * world * args.steps
     value = samples / (total_ms * 1e-3)
     gemm_tf = gsum["total_flops"] / max(gsum["total_ms"] * 1e-3, 1e-9) / 1e12
     traffic, traffic_detail = ncu_traffic()
     line = {
-        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": value / 7.94,
+        "metric": cfgd["metric"], "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": value / 7.94 if args.config == "cfg-3" else None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_name(args),
-                   "global_batch": BS * world, "parallelism": f"dp{world}", "rows_used": n_batches * BS * world,
-                   "dataset": "first rows of the synthetic 200k-row (Abstract,Question,Answer) 'full' set (all sequences truncated)",
-                   "l2": "per-step working set (27 GB weights + 22 GB activations) >> 126 MB L2; no explicit flush",
+                   "global_batch": B_step * world, "parallelism": f"dp{world}", "rows_used": n_batches * B_step * world,
+                   "dataset": ("first rows of the synthetic 200k-row (Abstract,Question,Answer) 'full' set (all sequences truncated)"
+                               if args.config == "cfg-3" else "uniform random token ids at the config's full sequence lengths, all-ones masks"),
+                   "l2": "per-step working set (weights + activations: tens of GB) >> 126 MB L2; no explicit flush",
                    "weights": "seeded random-init (no checkpoints offline)", "dropout": "train() mode as in the reference loop: BERT hidden 0.1 + attention-prob 0.1, LoRA input 0.05 (Philox, masks regenerated in backward)",
                    "launch": "one CUDA graph replay per step (fwd+bwd) + Adam/repack launches" if graphed is not None else "eager launches",
                    "eager_ms_per_step": eager_ms / args.steps,
@@ -438,7 +504,8 @@ def main():
         "e2e": {"value": samples / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
-        "step_tflops": STEP_TFLOP_PEFT * args.steps * world / (total_ms * 1e-3) ,
+        "step_tflops": cfgd["tflop"] * args.steps * world / (total_ms * 1e-3),
+        "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
         "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf,
                      "traffic": traffic, "traffic_detail": traffic_detail,
                      "kernel": "gemm_bf16_tn_kernel (tcgen05)", "launches_timed": gsum["launches"],
@@ -452,14 +519,14 @@ def main():
         line["scaling_note"] = (f"step = max over ranks every step (the all-reduce is a barrier): slowest rank's own compute "
                                 f"{max(cm):.2f} ms vs fastest {min(cm):.2f} ms; {coll_per_step:g} collective(s) per step "
                                 f"({sync.arena.numel() * 4 / 1e6:.1f} MB: both LoRA banks + loss scalar in one all-reduce)")
-    if world == 1 and args.gpu_eager_baseline:               # same-box eager-PyTorch comparator (rank 0, N=1 only)
+    if world == 1 and args.gpu_eager_baseline and args.config == "cfg-3":   # same-box eager-PyTorch comparator (rank 0, N=1 only)
         try:
             graphed = None
             torch.cuda.empty_cache()
             line["gpu_eager_baseline"] = gpu_eager_baseline(dev, host_batches[:8])
         except Exception as e:
             line["gpu_eager_baseline"] = {"value": None, "unit": "samples/s", "what": f"failed: {type(e).__name__}: {e}"}
-    if args.cpu_baseline and world == 1:                     # reported CPU baseline: rank 0, N=1 only
+    if args.cpu_baseline and world == 1 and args.config == "cfg-3":   # reported CPU baseline: rank 0, N=1 only
         try:
             r = cpu_reference_run(host_batches[0], rows=args.ref_rows, warmup=1, steps=2, budget_s=30.0)
             line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",

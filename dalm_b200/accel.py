@@ -131,6 +131,34 @@ class GradientSync:
                 off += pad(n)
         self.loss_slot = self.arena[total - 64:total - 63]
         self.collectives = 0                                   # issued so far (bench / tests read it)
+        # full fine-tuning: per-layer buckets are averaged on a side stream WHILE the backward of the layers below runs
+        # (what DDP's bucketed hooks give the reference, train_rage2e.py:416-418,471). `armed` is switched off on
+        # gradient-accumulation micro-steps. Collectives issued from hooks cannot sit inside a captured CUDA graph: such
+        # runs launch eagerly (a 230 ms step hides the launch cost).
+        self.armed = True
+        self.side = None
+        if world > 1 and self.large:
+            if torch.cuda.is_available() and torch.device(device).type == "cuda":
+                self.side = torch.cuda.Stream(device=device)
+            for b in self.large:
+                if hasattr(b, "bucket_hook"):
+                    b.bucket_hook = self._on_bucket
+
+    @property
+    def overlaps_backward(self) -> bool:
+        """True when collectives are issued during the backward (the step must not be a single captured CUDA graph)"""
+        return self.world > 1 and any(getattr(b, "bucket_hook", None) is not None for b in self.large)
+
+    def _on_bucket(self, bank, lo: int, hi: int) -> None:
+        if not self.armed or self.world == 1:
+            return
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream())     # the wgrads that produced [lo, hi) are ordered before it
+            with torch.cuda.stream(self.side):
+                self._avg(bank.grad[lo:hi])
+        else:
+            self._avg(bank.grad[lo:hi])
+        bank.reduced.append((lo, hi))
 
     def _avg(self, t: torch.Tensor) -> None:
         if self.nccl:
@@ -141,13 +169,15 @@ class GradientSync:
         self.collectives += 1
 
     def reduce_large(self) -> None:
+        """whatever the backward did not announce (embedding / norm / bias gradients, or everything when no hook fired)"""
         for b in self.large:
-            buckets = getattr(b, "reduce_buckets", None)
-            if buckets is None:
-                self._avg(b.grad)
-            else:
-                for lo, hi in buckets():
-                    self._avg(b.grad[lo:hi])
+            rest = b.unreduced_ranges() if hasattr(b, "unreduced_ranges") else [(0, b.grad.numel())]
+            for lo, hi in rest:
+                self._avg(b.grad[lo:hi])
+            if hasattr(b, "reduced"):
+                b.reduced = []
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)      # bucket all-reduces must land before the optimizer
 
     def reduce(self, loss: torch.Tensor) -> torch.Tensor:
         """average every bank's gradients over the ranks and return the rank-SUMMED loss (0-d fp32 view into the arena,

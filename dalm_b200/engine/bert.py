@@ -432,6 +432,7 @@ class BertEncoder(torch.nn.Module):
         ops.wgrad_(dqkv, a.x_aug[:, :H], bank.g(f"L{l}.Wqkv"), acc)
         ops.col_reduce_(dy_bf16=dqkv, out_sum=bank.g(f"L{l}.bqkv"))
         dx_16 = ops.gemm(dqkv, W["Wqkv_aug"], layout=1)
+        bank.bucket_ready(f"L{l}.")                                    # this layer's four weight gradients are final
         if l > 0:
             p, Wp = ctx.layers[l - 1], self.layers[l - 1]
             ops.col_reduce_(dy_f32=dz1_32, dy_bf16=dx_16, z=p.z2, mean=p.m2, rstd=p.r2, out_sum=bank.g(f"L{l - 1}.ln2_b"),

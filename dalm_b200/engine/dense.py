@@ -51,6 +51,11 @@ class DenseBank:
         self.p16 = torch.zeros(off, dtype=bf16, device=self.device)
         self.fresh = True                   # no gradient has been written since the last zero_grad()
         self.force_accumulate = False       # gradient accumulation under a captured graph: always +=, zero everything
+        # data-parallel overlap (accel.GradientSync): the engine announces, during backward, every contiguous range of g32
+        # whose gradients are final ("bucket = layer"); the hook all-reduces it on a side stream while the
+        # backward of the layers below is still running. Ranges not announced are reduced at the end of the step.
+        self.bucket_hook = None
+        self.reduced: List[Tuple[int, int]] = []
 
     def _view(self, buf: torch.Tensor, key: str) -> torch.Tensor:
         shape = self.shape[key]
@@ -90,6 +95,39 @@ class DenseBank:
         """bf16 shadow <- fp32 master (load time / after a checkpoint restore; the training step never needs it: the Adam
         kernel writes both)"""
         self.p16.copy_(self.p32)
+
+    # ---- data-parallel buckets ------------------------------------------------------------------------------------
+    def gemm_range(self, prefix: str) -> Tuple[int, int]:
+        """[lo, hi) element range of the "gemm"-kind entries whose key starts with `prefix` (one layer's weight gradients:
+        contiguous by construction, specs are laid out layer by layer)"""
+        lo, hi = None, None
+        for key, off in self.off.items():
+            if self.kind[key] == "gemm" and key.startswith(prefix):
+                n = 1
+                for d in self.shape[key]:
+                    n *= d
+                lo = off if lo is None else min(lo, off)
+                hi = off + n if hi is None else max(hi, off + n)
+        if lo is None:
+            raise KeyError(f"no weight-gradient entries under {prefix!r}")
+        return lo, hi
+
+    def bucket_ready(self, prefix: str) -> None:
+        """called by the engine's backward once every gradient under `prefix` has been written"""
+        if self.bucket_hook is not None:
+            lo, hi = self.gemm_range(prefix)
+            self.bucket_hook(self, lo, hi)
+
+    def unreduced_ranges(self) -> List[Tuple[int, int]]:
+        """complement of the announced (already reduced) ranges in [0, total)"""
+        out, pos = [], 0
+        for lo, hi in sorted(self.reduced):
+            if lo > pos:
+                out.append((pos, lo))
+            pos = max(pos, hi)
+        if pos < self.total:
+            out.append((pos, self.total))
+        return out
 
     # ---- gradient freshness protocol ----------------------------------------------------------------------------
     def zero_grad(self) -> None:

@@ -295,5 +295,6 @@ class FalconDecoder(torch.nn.Module):
             _, a = self._layer_fwd(W, x, ctx.mask, B, L, cos_t, sin_t, keep=True)      # recompute this layer's activations
             dx32, dx16 = self._layer_bwd(l, W, x, a, dx32, dx16, ctx.mask, B, L, cos_t, sin_t, acc)
             del a
+            bank.bucket_ready(f"L{l}.")                                                # this layer's four weight gradients are final
         ops.embed_scatter_add_(dx32, ctx.ids, bank.g("embed"))
         bank.end_backward()

@@ -330,8 +330,8 @@ class LlamaDecoder(torch.nn.Module):
                 ops.rope_pos_(a.qkv, 0, self.nh + self.nkv, self.hd, cos_t, sin_t, pos)
             if kv_sink is not None:
                 kv_sink(li, a.qkv)
-            a.att, a.lse = ops.attention_auto_fwd(                                       # tcgen05/TMEM path for head_dim 64 / 128a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + self.Nkv],
-                                    a.qkv[:, self.Nq + self.Nkv:], ctx.mask, B, L, self.nh, self.nkv, self.hd, causal=True)
+            a.att, a.lse = ops.attention_auto_fwd(a.qkv[:, :self.Nq], a.qkv[:, self.Nq:self.Nq + self.Nkv],   # tcgen05/TMEM (head_dim 64 / 128)
+                                                  a.qkv[:, self.Nq + self.Nkv:], ctx.mask, B, L, self.nh, self.nkv, self.hd, causal=True)
             a.x_mid = ops.gemm(a.att, W["Wo"], out_dtype=f32, resid=x)
             a.h2, a.rstd2 = ops.rmsnorm_fwd(a.x_mid, W["g2"], self.eps)
             a.gu = ops.gemm(a.h2, W["Wgu"])                                       # [M,2F]
@@ -405,6 +405,7 @@ class LlamaDecoder(torch.nn.Module):
             ops.wgrad_(dl2, ctx.hf, self.full.g("embed"), True)
         else:
             ops.wgrad_(dl2, ctx.hf, self.full.g("lm_head"), ctx.acc)
+            self.full.bucket_ready("lm_head")                                      # final: all-reduce it under the layers' backward
         self._backward_body(ctx, ops.gemm(dl2, self.lm_head, layout=1))
 
     def _backward_body(self, ctx: _Ctx, dhf: torch.Tensor) -> None:
@@ -444,6 +445,7 @@ class LlamaDecoder(torch.nn.Module):
                 dh1 = ops.gemm(dqkv, W["Wqkv_aug"], layout=1)
                 ops.col_reduce_(dy_bf16=dh1, z=a.x_in, rstd=a.rstd1, out_prod=G(l, "g1"))
                 dx32, dx16 = ops.rmsnorm_bwd(a.x_in, W["g1"], a.rstd1, dh1, dres_in=dmid32)
+                bank.bucket_ready(f"L{l}.")                                        # this layer's four weight gradients are final
                 continue
             names = [f"model.layers.{l}.self_attn.{n}" for n in self.LORA_TARGETS]
             for j, n in enumerate(self.LORA_TARGETS):

@@ -135,6 +135,8 @@ def run_training(recipe: Recipe, *, dataset_or_path: Any, per_device_train_batch
     sync = accelerator.gradient_sync(banks)        # ONE collective per optimizer step: both banks' gradients + the loss scalar
     last_loss = None
     use_graph = os.environ.get("DALM_B200_CUDA_GRAPH", "1") != "0" and torch.cuda.is_available()
+    if sync.overlaps_backward:          # full fine-tuning on > 1 rank: per-layer all-reduces are issued DURING the backward
+        use_graph = False               # (DDP bucket semantics), which a single captured graph cannot contain
     graphed = None
     for epoch in range(start_epoch, num_train_epochs):
         model.train()
@@ -145,6 +147,7 @@ def run_training(recipe: Recipe, *, dataset_or_path: Any, per_device_train_batch
         accelerator._loader = active                # `accumulate` reads end_of_dataloader from the loader being iterated
         for step, batch in enumerate(active):
             with accelerator.accumulate(model):
+                sync.armed = accelerator.sync_gradients     # accumulation micro-steps keep their gradients local
                 if use_graph and graphed is None:
                     from .train_utils import GraphedStep
                     try:

@@ -60,6 +60,24 @@ def _worker(rank, world, port, q):
     ok = ok and torch.allclose(b2.gB["m.k"], torch.full((8, 8), 150.0)) and b2.gA["m.v"].abs().max().item() == 0.0
     b1.zero_grad()
     ok = ok and sync.arena[: b1.grad.numel()].abs().max().item() == 0.0
+    # full fine-tuning: per-layer buckets announced during the backward are averaged right away (DDP bucket hooks), the
+    # rest (embeddings / norms) at the end of the step; every element is averaged exactly once
+    from dalm_b200.engine.dense import DenseBank
+    dbank = DenseBank([("embed", (10, 8), "acc"), ("L0.Wa", (4, 8), "gemm"), ("L0.Wb", (8, 8), "gemm"), ("L1.Wa", (4, 8), "gemm"),
+                       ("L1.Wb", (8, 8), "gemm"), ("lm_head", (10, 8), "gemm"), ("L0.g", (8,), "acc")], "cpu")
+    sync2 = acc.gradient_sync([dbank])
+    ok = ok and sync2.overlaps_backward and not acc.gradient_sync([b1]).overlaps_backward
+    dbank.g32.fill_(float(rank + 1))
+    c0 = sync2.collectives
+    dbank.bucket_ready("lm_head"); dbank.bucket_ready("L1."); dbank.bucket_ready("L0.")
+    ok = ok and sync2.collectives == c0 + 3 and torch.allclose(dbank.g("L1.Wb"), torch.full((8, 8), 1.5))
+    ok = ok and torch.allclose(dbank.g("embed"), torch.full((10, 8), float(rank + 1)))      # not announced: still local
+    sync2.reduce(torch.tensor(1.0))
+    ok = ok and torch.allclose(dbank.g32, torch.full_like(dbank.g32, 1.5)) and dbank.reduced == []
+    sync2.armed = False                                                                        # accumulation micro-step
+    dbank.g32.fill_(float(rank + 1)); c1 = sync2.collectives
+    dbank.bucket_ready("L0.")
+    ok = ok and sync2.collectives == c1 and torch.allclose(dbank.g("L0.Wa"), torch.full((4, 8), float(rank + 1)))
     acc.wait_for_everyone()
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
