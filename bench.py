@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--gpu-eager-baseline", type=int, default=1, help="0 to skip the same-box HF-eager GPU baseline (rank 0, N=1)")
     ap.add_argument("--ref-rows", type=int, default=2, help="rows per step of the bounded CPU sample (reference arm / cpu_baseline)")
     ap.add_argument("--ref-budget-s", type=float, default=200.0, help="wall-clock budget of the reference arm's step loop")
+    ap.add_argument("--through-trainer", type=int, default=1,
+                    help="1: also time the same steps through the public trainer API (dalm_b200.training...train_e2e: CSV -> "
+                         "datasets.map -> DataLoader -> scheduler -> tracker); cfg-3 only")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step's launch sequence as one CUDA graph (default); 0: eager launches")
     return ap.parse_args()
 
@@ -244,6 +247,55 @@ def ncu_traffic():
                                      "note": "down-proj (2nd) re-reads A on each of its 4 tile waves: 652 MB vs 342 MB"}
     except Exception as e:
         return None, {"source": f"unreadable ({type(e).__name__})"}
+
+
+def trainer_e2e_run(args, rank: int, world: int, cache_dir: str):
+    """The SAME workload through the repo's public entry point - `train_e2e(csv, retriever_dir, generator_dir, ...)`, the function
+    `dalm train-rag-e2e` calls (reference train_rage2e.py:229-260) - instead of bench.py's private loop: CSV on disk ->
+    load_dataset -> datasets.map tokenisation -> shuffled DataLoader + collate (pinned) -> H2D copy -> fused step (CUDA graph) ->
+    gradient sync -> Adam -> LR scheduler -> tracker. Model directories hold config + tokenizer + a random-init marker (no
+    checkpoints offline). Timed window: optimizer steps W..W+K between device synchronisations (loop.STEP_PROBE); model
+    construction and the one-off tokenisation pass happen before it and are excluded."""
+    import shutil
+    import torch
+    from dalm_b200 import synthetic
+    from dalm_b200.models.rag_e2e_base_model import Mode
+    from dalm_b200.training.rag_e2e.train_rage2e import train_e2e
+    from dalm_b200.training.utils import loop
+
+    W, K = args.warmup, args.steps
+    rows = (W + K + 2) * BS * world
+    csv = os.path.join(cache_dir, f"trainer_rows_{rows}.csv")
+    rdir, gdir = os.path.join(cache_dir, "dir_" + args.retriever), os.path.join(cache_dir, "dir_" + args.generator)
+    if rank == 0:
+        if not os.path.exists(csv):
+            synthetic.write_csv(csv, rows, seed=1234, full=True)
+        if not os.path.exists(os.path.join(rdir, "config.json")):
+            synthetic.write_model_dir(rdir, "bert", args.retriever, with_weights=False)
+        if not os.path.exists(os.path.join(gdir, "config.json")):
+            synthetic.write_model_dir(gdir, "llama", args.generator, with_weights=False)
+    if world > 1:
+        torch.distributed.barrier()
+    out = os.path.join(cache_dir, f"trainer_out_{rank}")
+    shutil.rmtree(out, ignore_errors=True)
+    loop.STEP_PROBE = {"warmup": W, "steps": K}
+    try:
+        train_e2e(csv, rdir, gdir, per_device_train_batch_size=BS, max_train_steps=(W + K) * world, num_train_epochs=1,
+                  use_peft=Mode.BOTH, num_warmup_steps=2, with_tracking=True, output_dir=None if rank else out, seed=42)
+        probe = loop.STEP_PROBE
+    finally:
+        loop.STEP_PROBE = None
+    if "seconds" not in probe:
+        return {"value": None, "unit": "samples/s", "what": "probe did not fire"}
+    t = torch.tensor([probe["seconds"]], device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    sec = t.item()
+    return {"value": BS * world * K / sec, "unit": "samples/s", "ms_per_step": sec / K * 1e3, "steps": K, "warmup": W,
+            "what": "public API: dalm_b200.training.rag_e2e.train_rage2e.train_e2e(csv, retriever_dir, generator_dir, bs=18, use_peft=both, "
+                    "with_tracking=True) on the first rows of the synthetic 200k-row CSV ('full' variant); DataLoader(shuffle, collate, "
+                    "pinned) + H2D + graph step + gradient sync + Adam + linear scheduler + jsonl tracker inside the timed window; "
+                    "model construction and the datasets.map tokenisation pass before it (excluded); wall clock between device syncs"}
 
 
 def workload_name(args) -> str:
@@ -470,6 +522,26 @@ def main():
         dist.all_gather(allt, t)
         per_rank = [{"rank": i, "compute_ms": round(x[0].item(), 3), "reduce_wait_adam_ms": round(x[1].item(), 3)} for i, x in enumerate(allt)]
 
+    # everything the JSON line needs from the live objects, then free them: the trainer run / eager baseline below build their own models
+    loss_last = float(loss.item())
+    used_graph = graphed is not None
+    arena_mb = sync.arena.numel() * 4 / 1e6
+    peak_mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
+    graphed = model = enc = opt = sync = banks = repack = resident = pinned = None
+    if cfgd["gen"] is not None:
+        dec = None
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    trainer_line = None
+    if args.through_trainer and args.config == "cfg-3":       # the same steps through the public trainer API (all ranks take part)
+        try:
+            trainer_line = trainer_e2e_run(args, rank, world, cache_dir)
+        except Exception as e:
+            trainer_line = {"value": None, "unit": "samples/s", "what": f"failed: {type(e).__name__}: {e}"}
+        gc.collect()
+        torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -498,14 +570,14 @@ def main():
                                if args.config == "cfg-3" else "uniform random token ids at the config's full sequence lengths, all-ones masks"),
                    "l2": "per-step working set (weights + activations: tens of GB) >> 126 MB L2; no explicit flush",
                    "weights": "seeded random-init (no checkpoints offline)", "dropout": "train() mode as in the reference loop: BERT hidden 0.1 + attention-prob 0.1, LoRA input 0.05 (Philox, masks regenerated in backward)",
-                   "launch": "one CUDA graph replay per step (fwd+bwd) + Adam/repack launches" if graphed is not None else "eager launches",
+                   "launch": "one CUDA graph replay per step (fwd+bwd) + Adam/repack launches" if used_graph else "eager launches",
                    "eager_ms_per_step": eager_ms / args.steps,
-                   "loss_last": float(loss.item())},
+                   "loss_last": loss_last},
         "e2e": {"value": samples / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "step_tflops": cfgd["tflop"] * args.steps * world / (total_ms * 1e-3),
-        "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+        "peak_mem_gb": peak_mem_gb,
         "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf,
                      "traffic": traffic, "traffic_detail": traffic_detail,
                      "kernel": "gemm_bf16_tn_kernel (tcgen05)", "launches_timed": gsum["launches"],
@@ -518,11 +590,11 @@ def main():
         line["per_rank"] = per_rank
         line["scaling_note"] = (f"step = max over ranks every step (the all-reduce is a barrier): slowest rank's own compute "
                                 f"{max(cm):.2f} ms vs fastest {min(cm):.2f} ms; {coll_per_step:g} collective(s) per step "
-                                f"({sync.arena.numel() * 4 / 1e6:.1f} MB: both LoRA banks + loss scalar in one all-reduce)")
+                                f"({arena_mb:.1f} MB: the small (LoRA) banks + loss scalar in one all-reduce; dense banks in per-layer buckets)")
+    if trainer_line is not None:
+        line["trainer_e2e"] = trainer_line
     if world == 1 and args.gpu_eager_baseline and args.config == "cfg-3":   # same-box eager-PyTorch comparator (rank 0, N=1 only)
         try:
-            graphed = None
-            torch.cuda.empty_cache()
             line["gpu_eager_baseline"] = gpu_eager_baseline(dev, host_batches[:8])
         except Exception as e:
             line["gpu_eager_baseline"] = {"value": None, "unit": "samples/s", "what": f"failed: {type(e).__name__}: {e}"}

@@ -41,6 +41,7 @@ SIGNATURES = {
                                 _I, _I, _I, _I, _I, _F, _I, *_DROP, _P],
     "dalm_b200_attention_tc_fwd": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _L, _I, _P, _P, _L, _P, _I, _I, _I, _I, _I, _F, _I, *_DROP, _P],
     "dalm_b200_attention_tc_set_debug": [_P],
+    "dalm_b200_attention_tc_set_mode": [_I],
     "dalm_b200_attention_tc_bwd": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _P, _L, _P, _P, _L, _L, _P, _P, _L, _P, _L, _P, _L,
                                    _I, _I, _I, _I, _I, _F, _I, *_DROP, _P],
     "dalm_b200_layernorm_fwd": [_P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _F, *_DROP, _P],
@@ -84,6 +85,7 @@ _RESTYPES = {
     "dalm_b200_gemm_clear_cache": None,
     "dalm_b200_gemm_set_raster": None,
     "dalm_b200_attention_tc_set_debug": None,
+    "dalm_b200_attention_tc_set_mode": None,
 }
 
 _lib = None

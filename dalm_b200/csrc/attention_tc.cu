@@ -647,6 +647,484 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// ============================================================================================================
+// PIPELINED, PERSISTENT backward (round 2). The two kernels above walk one hand-off chain per CTA (TMA -> MMA -> math ->
+// MMA, 1 CTA/SM because of TMEM): profiles/r01_attention_tc_ncu_details.csv shows issue slots 12-23 % busy. Here the
+// streamed operand is cut into 64-row HALF steps so that everything that repeats is double-buffered inside the 512 TMEM
+// columns and 227 KB of shared memory, and four roles run concurrently in one persistent CTA per SM:
+//     warp 0      producer : TMA loads of the resident tiles (per item) and of the streamed halves (2-stage ring)
+//     warp 1      MMA      : S/dP of half n+1 are issued BEFORE waiting for the math of half n; accumulating MMAs after it
+//     warps 2-5   math WG0 : even halves      } thread = TMEM lane (key row in dKdV, query row in dQ), 64 columns per half,
+//     warps 6-9   math WG1 : odd halves       } P / dS written as bf16 into 128B-swizzled tiles that feed the second MMAs
+// Items (dKdV: key tile x kv head x batch; dQ: query tile x head x batch) are strided over the persistent grid; the next
+// item's resident tiles are fetched while the current item's accumulators drain (WG0 / WG1 drain one accumulator each).
+// ============================================================================================================
+constexpr int CH64 = 64 * 64 * 2;            // one [64 rows x 64 cols] bf16 box = 8 KB (a 64-row tile is D/64 of these)
+__device__ __forceinline__ uint64_t kmajor_desc_r64(uint32_t tile, int kk) {      // 64-row tile, K-major, k-step kk over d
+  return make_sw128_kmajor_desc(tile + (kk >> 2) * CH64) + (uint64_t)(2 * (kk & 3));
+}
+__device__ __forceinline__ uint64_t mnmajor_desc_r64(uint32_t tile, int kk) {     // 64-row tile as MN-major B, k-step kk over its rows
+  return make_sw128_mnmajor_desc(tile + kk * 16 * 128, CH64, 1024);
+}
+template <int D>
+__device__ __forceinline__ void load_tile64(unsigned char* dst, const CUtensorMap* tm64, uint64_t* bar, int col, int row) {
+#pragma unroll
+  for (int hh = 0; hh < D / 64; ++hh) tma_load_2d(dst + hh * CH64, tm64, bar, col + hh * 64, row);
+}
+// drain one [128 rows x NC cols] fp32 TMEM accumulator (NC = 64 or 128) to bf16 HBM: one math warpgroup (128 threads,
+// named barrier `bar_id`), swizzled staging + TMA stores for full tiles, predicated row stores for ragged ones
+template <int NC>
+__device__ __forceinline__ void drain_acc_wg(uint32_t tacc, unsigned char* stage, const CUtensorMap* tm, int col0, int row0_global,
+                                             bool full_tile, bool row_ok, int r, __nv_bfloat16* fallback_row, int bar_id, bool issuer) {
+#pragma unroll 1
+  for (int c = 0; c < NC; c += 32) {
+    uint32_t v[32]; float f[32];
+    tmem_ld_32x32(tacc + c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+    if (full_tile) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) st_sw128(stage + (c >> 6) * HALF_BYTES, r, ((c & 63) >> 3) + g, pack8(f + g * 8));
+    } else if (row_ok) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) *reinterpret_cast<bf16x8*>(fallback_row + c + g * 8) = pack8(f + g * 8);
+    }
+  }
+  if (full_tile) {
+    fence_proxy_async();
+    named_bar_sync(bar_id, 128);
+    if (issuer) {
+#pragma unroll
+      for (int hh = 0; hh < NC / 64; ++hh) tma_store_2d(tm, stage + hh * HALF_BYTES, col0 + hh * 64, row0_global);
+      bulk_commit();
+      bulk_wait<0>();
+    }
+  }
+}
+
+struct PipeBars {                              // shared-memory barrier block of the pipelined kernels
+  uint64_t res_full, res_free;                 // resident tiles of the item (K,V / Q,dO): loaded / no longer read by MMAs
+  uint64_t str_full[2];                        // streamed halves landed (stage = n & 1)
+  uint64_t s_full[2];                          // S / dP of half n complete in TMEM (buffer = n & 1)
+  uint64_t p_ready[2];                         // math wrote the bf16 tiles of half n (and has finished reading S / dP)
+  uint64_t mma2_done[2];                       // accumulating MMAs of half n retired: bf16 tiles + streamed stage reusable
+  uint64_t acc_full, acc_free;                 // item's accumulators complete / drained
+  uint32_t tmem_holder, pad;
+};
+constexpr int kPipeThreads = 320;
+
+// ---- dK, dV ------------------------------------------------------------------------------------------------------
+template <int TD, bool DROP>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+attn_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_constant__ CUtensorMap tm_k,
+                         const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do64,
+                         const __grid_constant__ CUtensorMap tm_dk, const __grid_constant__ CUtensorMap tm_dv,
+                         const AttnTcParams p) {
+  using C = TcD<TD>;
+  constexpr int HT = (TD / 64) * CH64;                           // bytes of a [64 rows x TD] streamed half
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sK = smem;
+  unsigned char* sV = sK + C::TILE;
+  unsigned char* sQh = sV + C::TILE;                             // [2][HT]
+  unsigned char* sdOh = sQh + 2 * HT;                            // [2][HT]
+  unsigned char* sPT = sdOh + 2 * HT;                            // [2][16 KB]  P^T  [128 keys x 64 queries]
+  unsigned char* sdST = sPT + 2 * HALF_BYTES;                    // [2][16 KB]  dS^T
+  PipeBars* bars = reinterpret_cast<PipeBars*>(sdST + 2 * HALF_BYTES);
+  float* sLse = reinterpret_cast<float*>(bars + 1);             // [2][64] base-2 LSE of the half's queries
+  float* sDelta = sLse + 128;                                    // [2][64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = p.L, group = p.Hq / p.Hkv;
+  const int ntiles = (L + TB - 1) / TB;
+  const int n_items = ntiles * p.Hkv * p.B;
+  const int nqh = (L + 63) >> 6;                                 // 64-query halves of one sequence
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars->res_full, 1); mbar_init(&bars->res_free, 1); mbar_init(&bars->acc_full, 1); mbar_init(&bars->acc_free, 256);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->str_full[i], 1); mbar_init(&bars->s_full[i], 1); mbar_init(&bars->p_ready[i], 128); mbar_init(&bars->mma2_done[i], 1);
+    }
+    fence_mbar_init();
+    prefetch_tmap(&tm_q64); prefetch_tmap(&tm_k); prefetch_tmap(&tm_v); prefetch_tmap(&tm_do64);
+  }
+  if (warp == 1) { tmem_alloc(&bars->tmem_holder, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_holder;
+  const uint32_t tdV = tmem + 256, tdK = tmem + 256 + TD;        // S^T / dP^T buffers: tmem + t*128 (+64)
+
+  if (warp == 0) {
+    // ================= producer =================
+    if (lane == 0) {
+      int n = 0, c = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++c) {
+        const int kb = item % ntiles, hk = (item / ntiles) % p.Hkv, b = item / (ntiles * p.Hkv);
+        const int tok0 = b * L, kv0 = kb * TB;
+        mbar_wait(&bars->res_free, (c & 1) ^ 1);                 // previous item's S / dP MMAs no longer read K, V
+        mbar_arrive_expect_tx(&bars->res_full, 2 * C::TILE);
+        load_tile<TD>(sK, &tm_k, &bars->res_full, p.kcol0 + hk * TD, tok0 + kv0);
+        load_tile<TD>(sV, &tm_v, &bars->res_full, p.vcol0 + hk * TD, tok0 + kv0);
+        const int h_begin = p.causal ? 2 * kb : 0;               // query halves before the key tile see none of it
+        for (int hq = hk * group; hq < (hk + 1) * group; ++hq) {
+          for (int qh = h_begin; qh < nqh; ++qh, ++n) {
+            const int s = n & 1, u = n >> 1;
+            mbar_wait(&bars->mma2_done[s], (u & 1) ^ 1);         // stage s consumed by the accumulating MMAs of half n-2
+            mbar_arrive_expect_tx(&bars->str_full[s], 2 * HT);
+            load_tile64<TD>(sQh + s * HT, &tm_q64, &bars->str_full[s], p.qcol0 + hq * TD, tok0 + qh * 64);
+            load_tile64<TD>(sdOh + s * HT, &tm_do64, &bars->str_full[s], p.ocol0 + hq * TD, tok0 + qh * 64);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(TB, 64);          // S^T / dP^T half: [128 keys x 64 queries]
+      constexpr uint32_t idesc_acc = make_idesc_bf16_bmn(TB, TD);    // dV / dK: B = dO / Q half, MN-major
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+      auto issue_sp = [&](int n) {
+        const int s = n & 1, u = n >> 1;
+        mbar_wait(&bars->str_full[s], u & 1);
+        tc_fence_after();
+        const uint32_t tS = tmem + (uint32_t)(s * 128), aQ = smem_u32(sQh + s * HT), aDO = smem_u32(sdOh + s * HT);
+#pragma unroll
+        for (int kk = 0; kk < C::KS; ++kk) umma_f16(tS, kmajor_desc(aK, kk), kmajor_desc_r64(aQ, kk), idesc_s, kk != 0);        // S^T  = K Q^T
+#pragma unroll
+        for (int kk = 0; kk < C::KS; ++kk) umma_f16(tS + 64, kmajor_desc(aV, kk), kmajor_desc_r64(aDO, kk), idesc_s, kk != 0);  // dP^T = V dO^T
+        umma_commit(&bars->s_full[s]);
+      };
+      int n0 = 0, c = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++c) {
+        const int kb = item % ntiles;
+        const int NH = group * (nqh - (p.causal ? 2 * kb : 0));
+        mbar_wait(&bars->res_full, c & 1);
+        issue_sp(n0);
+        for (int k = 0; k < NH; ++k) {
+          const int n = n0 + k, s = n & 1, u = n >> 1;
+          if (k + 1 < NH) issue_sp(n + 1);
+          else umma_commit(&bars->res_free);                     // every S / dP MMA of this item has been issued
+          mbar_wait(&bars->p_ready[s], u & 1);
+          if (k == 0) mbar_wait(&bars->acc_free, (c & 1) ^ 1);   // previous item's accumulators drained
+          tc_fence_after();
+          const uint32_t aPT = smem_u32(sPT + s * HALF_BYTES), aDST = smem_u32(sdST + s * HALF_BYTES);
+          const uint32_t aQ = smem_u32(sQh + s * HT), aDO = smem_u32(sdOh + s * HT);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_f16(tdV, kmajor_desc(aPT, kk), mnmajor_desc_r64(aDO, kk), idesc_acc, (k | kk) != 0);   // dV += P^T dO
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_f16(tdK, kmajor_desc(aDST, kk), mnmajor_desc_r64(aQ, kk), idesc_acc, (k | kk) != 0);   // dK += dS^T Q
+          umma_commit(&bars->mma2_done[s]);
+        }
+        umma_commit(&bars->acc_full);
+        n0 += NH;
+      }
+    }
+  } else {
+    // ================= math warpgroups =================
+    const int g = (warp - 2) >> 2;                               // warpgroup 0 / 1 <-> buffer n & 1
+    const int r = (warp & 3) * 32 + lane;                        // TMEM lane == key row of the tile (lane quarter = warp % 4)
+    const int wt = threadIdx.x - 64 - g * 128;                   // 0..127 inside the warpgroup
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    const int lp8 = (L + 7) >> 3;
+    unsigned long long dstream = 0;
+    if constexpr (DROP) dstream = drop_stream(p.drop);
+    int n0 = 0, c = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++c) {
+      const int kb = item % ntiles, hk = (item / ntiles) % p.Hkv, b = item / (ntiles * p.Hkv);
+      const int tok0 = b * L, kv0 = kb * TB;
+      const int key = kv0 + r;
+      bool key_ok = key < L;
+      if (key_ok && p.mask) key_ok = p.mask[(size_t)tok0 + key] != 0;
+      const int dropkey = key_ok ? 0 : -1;
+      const int h_begin = p.causal ? 2 * kb : 0;
+      const int per_head = nqh - h_begin;
+      const int NH = group * per_head;
+      for (int k = 0; k < NH; ++k) {
+        const int n = n0 + k;
+        if ((n & 1) != g) continue;
+        const int u = n >> 1;
+        const int hq = hk * group + k / per_head, qh = h_begin + k % per_head;
+        const int qbase = qh * 64;
+        named_bar_sync(1 + g, 128);                              // the warpgroup's readers of the previous half's lse / delta are done
+        if (wt < 64) {
+          const int qi = qbase + wt;
+          const size_t idx = ((size_t)b * p.Hq + hq) * L + qi;
+          sLse[g * 64 + wt] = qi < L ? p.lse[idx] * 1.4426950408889634f : INFINITY;
+          sDelta[g * 64 + wt] = qi < L ? p.delta[idx] : 0.f;
+        }
+        named_bar_sync(1 + g, 128);
+        mbar_wait(&bars->s_full[g], u & 1);
+        tc_fence_after();
+        mbar_wait(&bars->mma2_done[g], (u & 1) ^ 1);             // P^T / dS^T tiles of half n-2 consumed by their MMAs
+        const bool diag = p.causal && (kv0 + TB - 1 > qbase);    // only halves on / below the diagonal band need the compare
+        const uint32_t tS = tmem + (uint32_t)(g * 128);
+        unsigned char* hp = sPT + g * HALF_BYTES;
+        unsigned char* hd = sdST + g * HALF_BYTES;
+#pragma unroll 1
+        for (int cc = 0; cc < 64; cc += 32) {
+          uint32_t vs[32], vp[32];
+          tmem_ld_32x32(tS + lane_off + cc, vs);
+          tmem_ld_32x32(tS + 64 + lane_off + cc, vp);
+          float lse_c[32], del_c[32];
+#pragma unroll
+          for (int x = 0; x < 32; x += 4) {
+            *reinterpret_cast<float4*>(lse_c + x) = *reinterpret_cast<const float4*>(sLse + g * 64 + cc + x);
+            *reinterpret_cast<float4*>(del_c + x) = *reinterpret_cast<const float4*>(sDelta + g * 64 + cc + x);
+          }
+          uint32_t keepw = 0xffffffffu;
+          if constexpr (DROP) {                                  // keep bits of (query qbase+cc+x, this key): see attn_bwd_dkv_tc_kernel
+            uint32_t mine = 0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int qx = qbase + cc + (lane & 7) + 8 * t;
+              float sc[8];
+              drop_scale8(p.drop, dstream, (((unsigned long long)b * p.Hq + hq) * L + (unsigned long long)qx) * (unsigned long long)lp8 + (unsigned long long)(key >> 3), sc);
+#pragma unroll
+              for (int j2 = 0; j2 < 8; ++j2) mine |= (sc[j2] != 0.f ? 1u : 0u) << (8 * t + j2);
+            }
+            keepw = 0;
+#pragma unroll
+            for (int i2 = 0; i2 < 8; ++i2) {
+              const uint32_t v = __shfl_sync(0xffffffffu, mine, (lane & ~7) | i2);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) keepw |= ((v >> (8 * t + (lane & 7))) & 1u) << (8 * t + i2);
+            }
+          }
+          tmem_ld_wait();
+          float pt[32], ds[32];
+#pragma unroll
+          for (int x = 0; x < 32; ++x) {
+            const int drop = dropkey | (diag ? ((qbase + cc + x - key) >> 31) : 0);
+            const uint32_t bits = (__float_as_uint(__uint_as_float(vs[x]) * sl2) & ~(uint32_t)drop) | (0xff800000u & (uint32_t)drop);
+            const float pr = ex2_approx(__uint_as_float(bits) - lse_c[x]);
+            if constexpr (DROP) {
+              const float sc = ((keepw >> x) & 1u) ? p.drop.inv_keep : 0.f;
+              pt[x] = pr * sc;
+              ds[x] = pr * (__uint_as_float(vp[x]) * sc - del_c[x]) * p.scale;
+            } else {
+              pt[x] = pr;
+              ds[x] = pr * (__uint_as_float(vp[x]) - del_c[x]) * p.scale;
+            }
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            st_sw128(hp, r, (cc >> 3) + q4, pack8(pt + q4 * 8));
+            st_sw128(hd, r, (cc >> 3) + q4, pack8(ds + q4 * 8));
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(&bars->p_ready[g]);
+      }
+      // ---- item end: all accumulating MMAs retired -> WG0 drains dV, WG1 drains dK ----
+      mbar_wait(&bars->acc_full, c & 1);
+      tc_fence_after();
+      {
+        const bool st_ok = key < L, full = kv0 + TB <= L;
+        const size_t rowoff = (size_t)(tok0 + (st_ok ? key : 0));
+        if (g == 0) drain_acc_wg<TD>(tdV + lane_off, sPT, &tm_dv, hk * TD, tok0 + kv0, full, st_ok, r,
+                                     p.dv + rowoff * p.lddv + (size_t)hk * TD, 1, wt == 0);
+        else        drain_acc_wg<TD>(tdK + lane_off, sdST, &tm_dk, hk * TD, tok0 + kv0, full, st_ok, r,
+                                     p.dk + rowoff * p.lddk + (size_t)hk * TD, 2, wt == 0);
+      }
+      tc_fence_before();
+      mbar_arrive(&bars->acc_free);
+      named_bar_sync(3, 256);                                    // both staging areas are free before the next item's halves write them
+      n0 += NH;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ---- dQ ----------------------------------------------------------------------------------------------------------
+template <int TD, bool DROP>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+attn_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k64,
+                        const __grid_constant__ CUtensorMap tm_v64, const __grid_constant__ CUtensorMap tm_do,
+                        const __grid_constant__ CUtensorMap tm_dq, const AttnTcParams p) {
+  using C = TcD<TD>;
+  constexpr int HT = (TD / 64) * CH64;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sQ = smem;
+  unsigned char* sdO = sQ + C::TILE;
+  unsigned char* sKh = sdO + C::TILE;                            // [2][HT]
+  unsigned char* sVh = sKh + 2 * HT;                             // [2][HT]
+  unsigned char* sdS = sVh + 2 * HT;                             // [2][16 KB]  dS [128 queries x 64 keys]
+  PipeBars* bars = reinterpret_cast<PipeBars*>(sdS + 2 * HALF_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = p.L, group = p.Hq / p.Hkv;
+  const int ntiles = (L + TB - 1) / TB;
+  const int n_items = ntiles * p.Hq * p.B;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars->res_full, 1); mbar_init(&bars->res_free, 1); mbar_init(&bars->acc_full, 1); mbar_init(&bars->acc_free, 256);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->str_full[i], 1); mbar_init(&bars->s_full[i], 1); mbar_init(&bars->p_ready[i], 128); mbar_init(&bars->mma2_done[i], 1);
+    }
+    fence_mbar_init();
+    prefetch_tmap(&tm_q); prefetch_tmap(&tm_k64); prefetch_tmap(&tm_v64); prefetch_tmap(&tm_do);
+  }
+  if (warp == 1) { tmem_alloc(&bars->tmem_holder, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_holder;
+  const uint32_t tdQ = tmem + 256;
+  // number of 64-key halves query tile qb attends to
+  auto n_halves = [&](int qb) { const int kend = p.causal ? min(L, qb * TB + TB) : L; return (kend + 63) >> 6; };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int n = 0, c = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++c) {
+        const int qb = item % ntiles, h = (item / ntiles) % p.Hq, b = item / (ntiles * p.Hq);
+        const int hk = h / group, tok0 = b * L, q0 = qb * TB;
+        mbar_wait(&bars->res_free, (c & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars->res_full, 2 * C::TILE);
+        load_tile<TD>(sQ, &tm_q, &bars->res_full, p.qcol0 + h * TD, tok0 + q0);
+        load_tile<TD>(sdO, &tm_do, &bars->res_full, p.ocol0 + h * TD, tok0 + q0);
+        const int NH = n_halves(qb);
+        for (int j = 0; j < NH; ++j, ++n) {
+          const int s = n & 1, u = n >> 1;
+          mbar_wait(&bars->mma2_done[s], (u & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars->str_full[s], 2 * HT);
+          load_tile64<TD>(sKh + s * HT, &tm_k64, &bars->str_full[s], p.kcol0 + hk * TD, tok0 + j * 64);
+          load_tile64<TD>(sVh + s * HT, &tm_v64, &bars->str_full[s], p.vcol0 + hk * TD, tok0 + j * 64);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(TB, 64);
+      constexpr uint32_t idesc_acc = make_idesc_bf16_bmn(TB, TD);
+      const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sdO);
+      auto issue_sp = [&](int n) {
+        const int s = n & 1, u = n >> 1;
+        mbar_wait(&bars->str_full[s], u & 1);
+        tc_fence_after();
+        const uint32_t tS = tmem + (uint32_t)(s * 128), aK = smem_u32(sKh + s * HT), aV = smem_u32(sVh + s * HT);
+#pragma unroll
+        for (int kk = 0; kk < C::KS; ++kk) umma_f16(tS, kmajor_desc(aQ, kk), kmajor_desc_r64(aK, kk), idesc_s, kk != 0);        // S  = Q K^T
+#pragma unroll
+        for (int kk = 0; kk < C::KS; ++kk) umma_f16(tS + 64, kmajor_desc(aDO, kk), kmajor_desc_r64(aV, kk), idesc_s, kk != 0);  // dP = dO V^T
+        umma_commit(&bars->s_full[s]);
+      };
+      int n0 = 0, c = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++c) {
+        const int NH = n_halves(item % ntiles);
+        mbar_wait(&bars->res_full, c & 1);
+        issue_sp(n0);
+        for (int k = 0; k < NH; ++k) {
+          const int n = n0 + k, s = n & 1, u = n >> 1;
+          if (k + 1 < NH) issue_sp(n + 1);
+          else umma_commit(&bars->res_free);
+          mbar_wait(&bars->p_ready[s], u & 1);
+          if (k == 0) mbar_wait(&bars->acc_free, (c & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t aDS = smem_u32(sdS + s * HALF_BYTES), aK = smem_u32(sKh + s * HT);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_f16(tdQ, kmajor_desc(aDS, kk), mnmajor_desc_r64(aK, kk), idesc_acc, (k | kk) != 0);   // dQ += dS K
+          umma_commit(&bars->mma2_done[s]);
+        }
+        umma_commit(&bars->acc_full);
+        n0 += NH;
+      }
+    }
+  } else {
+    const int g = (warp - 2) >> 2;
+    const int r = (warp & 3) * 32 + lane;                        // query row of the tile == TMEM lane
+    const int wt = threadIdx.x - 64 - g * 128;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    unsigned long long dstream = 0;
+    if constexpr (DROP) dstream = drop_stream(p.drop);
+    int n0 = 0, c = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++c) {
+      const int qb = item % ntiles, h = (item / ntiles) % p.Hq, b = item / (ntiles * p.Hq);
+      const int tok0 = b * L, q0 = qb * TB, qrow = q0 + r;
+      const size_t idx = ((size_t)b * p.Hq + h) * L + qrow;
+      const float lse2 = qrow < L ? p.lse[idx] * 1.4426950408889634f : INFINITY;
+      const float dl = qrow < L ? p.delta[idx] : 0.f;
+      unsigned long long dgrow = 0;
+      if constexpr (DROP) dgrow = (((unsigned long long)b * p.Hq + h) * L + (unsigned long long)qrow) * (unsigned long long)((L + 7) >> 3);
+      const int NH = n_halves(qb);
+      const int64_t* mrow = p.mask ? p.mask + (size_t)tok0 : nullptr;
+      for (int k = 0; k < NH; ++k) {
+        const int n = n0 + k;
+        if ((n & 1) != g) continue;
+        const int u = n >> 1, kv0 = k * 64;
+        uint32_t kbits[2];
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const int key = kv0 + w * 32 + lane;
+          bool keep = key < L;
+          if (keep && mrow) keep = mrow[key] != 0;
+          kbits[w] = __ballot_sync(0xffffffffu, keep);
+        }
+        const bool diag = p.causal && (kv0 + 63 > q0);
+        const int dcol = diag ? (qrow - kv0) : 0x7fffffff;
+        mbar_wait(&bars->s_full[g], u & 1);
+        tc_fence_after();
+        mbar_wait(&bars->mma2_done[g], (u & 1) ^ 1);             // dS tile of half n-2 consumed
+        const uint32_t tS = tmem + (uint32_t)(g * 128);
+        unsigned char* hd = sdS + g * HALF_BYTES;
+#pragma unroll 1
+        for (int cc = 0; cc < 64; cc += 32) {
+          uint32_t vs[32], vp[32];
+          tmem_ld_32x32(tS + lane_off + cc, vs);
+          tmem_ld_32x32(tS + 64 + lane_off + cc, vp);
+          float dsc[32];
+          if constexpr (DROP) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) drop_scale8(p.drop, dstream, dgrow + (unsigned long long)(((kv0 + cc) >> 3) + q4), dsc + q4 * 8);
+          }
+          tmem_ld_wait();
+          const uint32_t kw = kbits[cc >> 5];
+          float ds[32];
+#pragma unroll
+          for (int x = 0; x < 32; ++x) {
+            const int drop = ((dcol - (cc + x)) >> 31) | (int)(((kw >> x) & 1u) - 1u);
+            const uint32_t bits = (__float_as_uint(__uint_as_float(vs[x]) * sl2) & ~(uint32_t)drop) | (0xff800000u & (uint32_t)drop);
+            const float pr = ex2_approx(__uint_as_float(bits) - lse2);
+            if constexpr (DROP) ds[x] = pr * (__uint_as_float(vp[x]) * dsc[x] - dl) * p.scale;
+            else                ds[x] = pr * (__uint_as_float(vp[x]) - dl) * p.scale;
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) st_sw128(hd, r, (cc >> 3) + q4, pack8(ds + q4 * 8));
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(&bars->p_ready[g]);
+      }
+      // ---- item end: dQ complete -> WG g drains columns [g*64, g*64+64) (TD = 64: WG0 alone) ----
+      mbar_wait(&bars->acc_full, c & 1);
+      tc_fence_after();
+      if (g * 64 < TD) {
+        __nv_bfloat16* dqrow = p.dq + (size_t)(tok0 + (qrow < L ? qrow : 0)) * p.lddq + (size_t)h * TD + g * 64;
+        drain_acc_wg<64>(tdQ + lane_off + (uint32_t)(g * 64), sdS + g * HALF_BYTES, &tm_dq, h * TD + g * 64, tok0 + q0,
+                         q0 + TB <= L, qrow < L, r, dqrow, 1 + g, wt == 0);
+      }
+      tc_fence_before();
+      mbar_arrive(&bars->acc_free);
+      named_bar_sync(3, 256);
+      n0 += NH;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+template <int D> constexpr int dkv_pipe_smem() { return 2 * TcD<D>::TILE + 4 * (D / 64) * CH64 + 4 * HALF_BYTES + 1024 + 2048; }
+template <int D> constexpr int dq_pipe_smem() { return 2 * TcD<D>::TILE + 4 * (D / 64) * CH64 + 2 * HALF_BYTES + 1024 + 1024; }
+
 template <int D> constexpr int dkv_smem() { return 4 * TcD<D>::TILE + 2 * TILE_BYTES + 1024 + 2048; }
 template <int D> constexpr int dq_smem() { return 4 * TcD<D>::TILE + TILE_BYTES + 1024 + 1024; }
 template <int D> constexpr int fwd_smem() { return 3 * TcD<D>::TILE + (D == 128 ? 0 : TILE_BYTES) + 1024 + 1024; }
@@ -656,6 +1134,8 @@ template <int D> constexpr int fwd_smem() { return 3 * TcD<D>::TILE + (D == 128 
 using namespace dalm;
 
 static long long* g_attn_dbg = nullptr;
+static int g_attn_bwd_pipe = 1;               // 1: pipelined persistent backward kernels (default), 0: the one-chain-per-CTA kernels
+extern "C" void dalm_b200_attention_tc_set_mode(int pipelined_backward) { g_attn_bwd_pipe = pipelined_backward; }
 extern "C" void dalm_b200_attention_tc_set_debug(void* dev_buffer_64xint64) { g_attn_dbg = (long long*)dev_buffer_64xint64; }
 
 static int tc_maps(const void* ptr, long long rows, long long cols, long long ld, CUtensorMap* m) {
@@ -704,6 +1184,7 @@ extern "C" int dalm_b200_attention_tc_fwd(const void* q, long long ldq, long lon
 
 template <int D, bool DROP>
 static int launch_tc_bwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mdo,
+                         const CUtensorMap& mq64, const CUtensorMap& mk64, const CUtensorMap& mv64, const CUtensorMap& mdo64,
                          const CUtensorMap& mdq, const CUtensorMap& mdk, const CUtensorMap& mdv, const AttnTcParams& p,
                          const void* out, long long ldo, const void* d_out, long long lddo, float* delta, cudaStream_t st) {
   static bool attr = false;
@@ -717,6 +1198,22 @@ static int launch_tc_bwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUt
                                                                          lddo, delta, p.B, p.L, p.Hq);
   if (int e = check_launch("attn_tc_delta_kernel")) return e;
   const int ntiles = (p.L + TB - 1) / TB;
+  if (g_attn_bwd_pipe) {
+    static bool attr2 = false;
+    if (!attr2) {
+      DALM_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_pipe_kernel<D, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, dkv_pipe_smem<D>()));
+      DALM_CUDA(cudaFuncSetAttribute(attn_bwd_dq_pipe_kernel<D, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, dq_pipe_smem<D>()));
+      attr2 = true;
+    }
+    const int items_kv = ntiles * p.Hkv * p.B, items_q = ntiles * p.Hq * p.B;
+    attn_bwd_dkv_pipe_kernel<D, DROP><<<items_kv < kNumSMs ? items_kv : kNumSMs, kPipeThreads, dkv_pipe_smem<D>(), st>>>(
+        mq64, mk, mv, mdo64, mdk, mdv, p);
+    if (int e = check_launch("attn_bwd_dkv_pipe_kernel")) return e;
+    attn_bwd_dq_pipe_kernel<D, DROP><<<items_q < kNumSMs ? items_q : kNumSMs, kPipeThreads, dq_pipe_smem<D>(), st>>>(
+        mq, mk64, mv64, mdo, mdq, p);
+    count_launch(3);
+    return check_launch("attn_bwd_dq_pipe_kernel");
+  }
   attn_bwd_dkv_tc_kernel<D, DROP><<<dim3(ntiles, p.Hkv, p.B), 160, dkv_smem<D>(), st>>>(mq, mk, mv, mdo, mdk, mdv, p);
   if (int e = check_launch("attn_bwd_dkv_tc_kernel")) return e;
   attn_bwd_dq_tc_kernel<D, DROP><<<dim3(ntiles, p.Hq, p.B), 160, dq_smem<D>(), st>>>(mq, mk, mv, mdo, mdq, p);
@@ -744,6 +1241,11 @@ extern "C" int dalm_b200_attention_tc_bwd(const void* q, long long ldq, long lon
   if (int e = tc_maps(k, rows, kcols, ldk, &mk)) return e;
   if (int e = tc_maps(v, rows, vcols, ldv, &mv)) return e;
   if (int e = tc_maps(d_out, rows, docols, lddo, &mdo)) return e;
+  CUtensorMap mq64, mk64, mv64, mdo64;                         // 64-row boxes: the streamed halves of the pipelined kernels
+  if (int e = get_tmap(q, rows, qcols, ldq, 64, &mq64, 0)) return e;
+  if (int e = get_tmap(k, rows, kcols, ldk, 64, &mk64, 0)) return e;
+  if (int e = get_tmap(v, rows, vcols, ldv, 64, &mv64, 0)) return e;
+  if (int e = get_tmap(d_out, rows, docols, lddo, 64, &mdo64, 0)) return e;
   CUtensorMap mdq, mdk, mdv;
   if (int e = tc_maps(dq, rows, (long long)Hq * D, lddq, &mdq)) return e;
   if (int e = tc_maps(dk, rows, (long long)Hkv * D, lddk, &mdk)) return e;
@@ -754,7 +1256,7 @@ extern "C" int dalm_b200_attention_tc_bwd(const void* q, long long ldq, long lon
   p.dq = (__nv_bfloat16*)dq; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv; p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
   p.drop = make_drop(drop_p, drop_seed, drop_stream_id, drop_offset);
   cudaStream_t st = (cudaStream_t)stream;
-  if (D == 128) return launch_tc_bwd<128, false>(mq, mk, mv, mdo, mdq, mdk, mdv, p, out, ldo, d_out, lddo, delta, st);
-  if (drop_p > 0.f) return launch_tc_bwd<64, true>(mq, mk, mv, mdo, mdq, mdk, mdv, p, out, ldo, d_out, lddo, delta, st);
-  return launch_tc_bwd<64, false>(mq, mk, mv, mdo, mdq, mdk, mdv, p, out, ldo, d_out, lddo, delta, st);
+  if (D == 128) return launch_tc_bwd<128, false>(mq, mk, mv, mdo, mq64, mk64, mv64, mdo64, mdq, mdk, mdv, p, out, ldo, d_out, lddo, delta, st);
+  if (drop_p > 0.f) return launch_tc_bwd<64, true>(mq, mk, mv, mdo, mq64, mk64, mv64, mdo64, mdq, mdk, mdv, p, out, ldo, d_out, lddo, delta, st);
+  return launch_tc_bwd<64, false>(mq, mk, mv, mdo, mq64, mk64, mv64, mdo64, mdq, mdk, mdv, p, out, ldo, d_out, lddo, delta, st);
 }

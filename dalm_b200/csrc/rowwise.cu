@@ -407,6 +407,52 @@ __global__ void __launch_bounds__(256) pool_norm_fwd_kernel(const float* __restr
   const float s = normalize ? 1.f / fmaxf(nrm, 1e-12f) : 1.f;
   for (int i = threadIdx.x; i < H; i += blockDim.x) emb[(size_t)b * H + i] = pooled[(size_t)b * H + i] * s;
 }
+// The same forward for H % 128 == 0, spread over the machine: the one-CTA-per-sample kernel above walks the L rows serially
+// (B CTAs, 168 us for 9.4 MB = 56 GB/s at cfg-3). Here CTA (chunk, b) owns 128 columns of sample b: each of its 8 warps
+// streams the rows l = warp, warp + 8, ... (one coalesced 512-byte float4 row piece per warp-load, masked rows skipped), the
+// warps' partial sums meet in shared memory. B x H/128 CTAs (144 at cfg-3, 1200 at cfg-2). A second tiny launch normalises.
+__global__ void __launch_bounds__(256) pool_sum_kernel(const float* __restrict__ hidden, const int64_t* __restrict__ mask,
+                                                       float* __restrict__ pooled, int L, int H) {
+  __shared__ float4 part[8][32];
+  __shared__ float s_cnt;
+  const int b = blockIdx.y, c0 = blockIdx.x * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float cnt = 0.f;
+  for (int l = warp; l < L; l += 8) {
+    const float m = (float)mask[(size_t)b * L + l];
+    if (m != 0.f) {
+      const float4 v = *reinterpret_cast<const float4*>(hidden + ((size_t)b * L + l) * H + c0 + lane * 4);
+      acc.x += v.x * m; acc.y += v.y * m; acc.z += v.z * m; acc.w += v.w * m;
+    }
+  }
+  if (warp == 0) {                                               // token count of the sample (one warp)
+    for (int l = lane; l < L; l += 32) cnt += (float)mask[(size_t)b * L + l];
+    cnt = warp_sum(cnt);
+    if (lane == 0) s_cnt = cnt;
+  }
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    float4 t = part[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { const float4 u = part[w][lane]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+    const float inv = 1.f / fmaxf(s_cnt, 1e-9f);
+    t.x *= inv; t.y *= inv; t.z *= inv; t.w *= inv;
+    *reinterpret_cast<float4*>(pooled + (size_t)b * H + c0 + lane * 4) = t;
+  }
+}
+__global__ void __launch_bounds__(256) pool_finish_kernel(const float* __restrict__ pooled, float* __restrict__ emb,
+                                                          float* __restrict__ norm_out, int H, int normalize) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float sq = 0.f;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) { const float v = pooled[(size_t)b * H + i]; sq += v * v; }
+  const float nrm = sqrtf(block_sum(sq, red));
+  if (threadIdx.x == 0) norm_out[b] = nrm;
+  const float s = normalize ? 1.f / fmaxf(nrm, 1e-12f) : 1.f;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) emb[(size_t)b * H + i] = pooled[(size_t)b * H + i] * s;
+}
 // d_hidden[b,l,:] = m[b,l]/cnt * d_pooled;  d_pooled = (d_emb - emb*(emb.d_emb)) / max(norm,eps)  (if normalize)
 __global__ void __launch_bounds__(256) pool_norm_bwd_kernel(const float* __restrict__ emb, const float* __restrict__ norm_in,
                                                             const float* __restrict__ d_emb, const int64_t* __restrict__ mask,
@@ -658,6 +704,13 @@ extern "C" int dalm_b200_gelu_bwd(const void* pre, long long ldp, void* dact, lo
 }
 extern "C" int dalm_b200_pool_norm_fwd(const float* hidden, const int64_t* mask, float* pooled, float* emb, float* norm,
                                        int B, int L, int H, int normalize, void* stream) {
+  if ((H % 128) == 0 && (reinterpret_cast<uintptr_t>(hidden) & 15) == 0) {
+    pool_sum_kernel<<<dim3(H / 128, B), 256, 0, ST(stream)>>>(hidden, mask, pooled, L, H);
+    if (int e = check_launch("pool_sum_kernel")) return e;
+    pool_finish_kernel<<<B, 256, 0, ST(stream)>>>(pooled, emb, norm, H, normalize);
+    count_launch(2);
+    return check_launch("pool_finish_kernel");
+  }
   pool_norm_fwd_kernel<<<B, 256, 0, ST(stream)>>>(hidden, mask, pooled, emb, norm, L, H, normalize);
   count_launch();
   return check_launch("pool_norm_fwd_kernel");

@@ -97,10 +97,25 @@ def load_config(path: str) -> Dict:
         return json.load(f)
 
 
+RANDOM_INIT_MARKER = "dalm_b200_random_init.json"
+
+
 def load_state_dict(path: str) -> Dict[str, torch.Tensor]:
-    """Reads *.safetensors (single or sharded) or pytorch_model.bin from an HF-layout directory."""
+    """Reads *.safetensors (single or sharded) or pytorch_model.bin from an HF-layout directory. A directory written by
+    `synthetic.write_model_dir(..., with_weights=False)` carries a marker instead of weights ({"seed": n}): the public
+    architecture is then random-initialised on the fly (on the GPU when there is one) - the offline stand-in for a hub
+    checkpoint that BASELINE.json's configs prescribe ("random-init"), without writing 27 GB of Llama-2-7B to disk."""
     from safetensors.torch import load_file
 
+    marker = os.path.join(path, RANDOM_INIT_MARKER)
+    if os.path.exists(marker):
+        with open(marker) as f:
+            seed = int(json.load(f).get("seed", 0))
+        cfg = load_config(path)
+        on_gpu = torch.cuda.is_available()
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", torch.cuda.current_device()))) if on_gpu else torch.device("cpu")
+        return random_state_dict(model_kind(cfg), dict(cfg, _device_rng=on_gpu), seed=seed,
+                                 dtype=torch.bfloat16 if on_gpu else torch.float32, device=dev)
     files = sorted(f for f in os.listdir(path) if f.endswith(".safetensors") and not f.startswith("adapter"))
     sd: Dict[str, torch.Tensor] = {}
     if files:

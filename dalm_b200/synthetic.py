@@ -198,6 +198,9 @@ def write_model_dir(out_dir: str, kind: str, name: str, vocab_size: Optional[int
         raise ValueError(kind)
     with open(os.path.join(out_dir, "config.json"), "w") as f:
         json.dump(cfg, f, indent=1)
+    if not with_weights:
+        with open(os.path.join(out_dir, "dalm_b200_random_init.json"), "w") as f:      # engine/params.py: random init at load time
+            json.dump({"seed": seed}, f)
     if with_weights:
         import torch
         from safetensors.torch import save_file

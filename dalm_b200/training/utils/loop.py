@@ -21,6 +21,10 @@ from .train_utils import load_model_hook, save_model_hook
 
 logger = get_logger(__name__)
 
+# Optional measurement hook (bench.py --through-trainer): {"warmup": W, "steps": K} -> after the run also "seconds" (wall clock
+# between device synchronisations at optimizer steps W and W+K) and "steps_timed". None = off: no synchronisation is added.
+STEP_PROBE: Optional[Dict[str, Any]] = None
+
 
 @dataclass
 class Recipe:
@@ -171,6 +175,14 @@ def run_training(recipe: Recipe, *, dataset_or_path: Any, per_device_train_batch
             if accelerator.sync_gradients:
                 progress.update(1)
                 completed += 1
+                if STEP_PROBE is not None and completed in (STEP_PROBE["warmup"], STEP_PROBE["warmup"] + STEP_PROBE["steps"]):
+                    import time
+                    torch.cuda.synchronize()
+                    if completed == STEP_PROBE["warmup"]:
+                        STEP_PROBE["t0"] = time.perf_counter()
+                    else:
+                        STEP_PROBE["seconds"] = time.perf_counter() - STEP_PROBE["t0"]
+                        STEP_PROBE["steps_timed"] = STEP_PROBE["steps"]
             if (step + 1) % 100 == 0:
                 last_loss = (total_loss / (step + 1)).item()
                 logger.info(f"Step: {step + 1}, Loss: {last_loss}")

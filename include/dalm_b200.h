@@ -104,6 +104,9 @@ int dalm_b200_attention_tc_fwd(const void* q, long long ldq, long long qcols, in
                                int D, float scale, int causal, float drop_p, unsigned long long drop_seed,
                                unsigned long long drop_stream_id, const void* drop_offset, void* stream);
 
+/* backward kernel selection (test / tuning hook): 1 = pipelined persistent dKdV / dQ kernels (default), 0 = the
+ * one-chain-per-CTA kernels they replaced (kept as an independent cross-check) */
+void dalm_b200_attention_tc_set_mode(int pipelined_backward);
 /* tuning aid: a device buffer of 64 int64 receives clock64 phase timestamps of one forward CTA (NULL disables) */
 void dalm_b200_attention_tc_set_debug(void* dev_buffer_64xint64);
 int dalm_b200_attention_tc_bwd(const void* q, long long ldq, long long qcols, const void* k, long long ldk, long long kcols,

@@ -244,14 +244,16 @@ def test_embeddings_rope_swiglu_gelu(cuda_dev):
     assert _rel(d2.float(), pd.grad) < 4e-3
 
 
-def test_pool_norm(cuda_dev):
+@pytest.mark.parametrize("B,L,H", [(5, 23, 384), (18, 128, 1024), (150, 50, 1024), (3, 7, 72), (2, 300, 4096)])
+def test_pool_norm(cuda_dev, B, L, H):
+    """H % 128 == 0 takes the machine-wide two-launch forward (pool_sum + pool_finish), other widths the per-sample kernel;
+    includes a sample with ONE valid token and the golden fixture's all-masked case (clamp 1e-9)"""
     from dalm_b200 import ops
     from oracle import pooling
     torch.manual_seed(5)
-    B, L, H = 5, 23, 384
     hid = torch.randn(B, L, H, device=cuda_dev)
     mask = torch.ones(B, L, dtype=torch.int64, device=cuda_dev)
-    mask[0, 10:] = 0; mask[3, 1:] = 0
+    mask[0, min(10, L - 1):] = 0; mask[min(3, B - 1), 1:] = 0
     emb, norm = ops.pool_norm_fwd(hid, mask, True)
     hd = hid.double().cpu().requires_grad_(True)
     ref = pooling.normalize(pooling.mean_pooling(hd, mask.cpu()).double())
