@@ -25,7 +25,9 @@ struct AttnTcParams {
   const int64_t* mask;              // [B,L] key-padding mask or nullptr
   __nv_bfloat16* o; long long ldo;  // forward output [B*L, Hq*128]
   float* lse;                       // [B,Hq,L]
-  const float* delta;               // [B,Hq,L] (backward)
+  const float* delta;               // [B,Hq,Lp] (backward)  rowsum(dO * O); Lp = L rounded up to 64, pad entries 0
+  const float* nl2;                 // [B,Hq,Lp] (backward)  -lse * log2(e); pad entries (and fully masked rows) -inf
+  int Lp;
   __nv_bfloat16* dq; __nv_bfloat16* dk; __nv_bfloat16* dv;
   long long lddq, lddk, lddv;
   int B, L, Hq, Hkv;
@@ -300,7 +302,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 // ============================================================================================================
 template <int TD>
 __global__ void attn_tc_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ d_o,
-                                     long long lddo, float* __restrict__ delta, int B, int L, int Hq) {
+                                     long long lddo, const float* __restrict__ lse, float* __restrict__ delta,
+                                     float* __restrict__ nl2, int B, int L, int Lp, int Hq) {
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= B * L * Hq) return;
   const int tok = gw / Hq, h = gw - tok * Hq;
@@ -322,9 +325,14 @@ __global__ void attn_tc_delta_kernel(const __nv_bfloat16* __restrict__ o, long l
     acc = a.x * c.x + a.y * c.y;
   }
   acc = warp_sum(acc);
+  const int b = tok / L, l = tok - b * L;
+  const size_t row = ((size_t)b * Hq + h) * Lp;
   if (lane == 0) {
-    const int b = tok / L, l = tok - b * L;
-    delta[((size_t)b * Hq + h) * L + l] = acc;
+    delta[row + l] = acc;
+    nl2[row + l] = -lse[((size_t)b * Hq + h) * L + l] * 1.4426950408889634f;       // lse = +inf (fully masked query) -> -inf
+  }
+  if (l == L - 1 && L + lane < Lp) {                               // pad entries [L, Lp): queries that do not exist contribute nothing
+    for (int lp = L + lane; lp < Lp; lp += 32) { delta[row + lp] = 0.f; nl2[row + lp] = -INFINITY; }
   }
 }
 
@@ -427,7 +435,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           const size_t idx = ((size_t)b * p.Hq + hq) * L + qi;
           named_bar_sync(1, 128);                                // readers of the previous tile's lse/delta are done
           sLse[r] = qi < L ? p.lse[idx] * 1.4426950408889634f : INFINITY;
-          sDelta[r] = qi < L ? p.delta[idx] : 0.f;
+          sDelta[r] = qi < L ? p.delta[((size_t)b * p.Hq + hq) * p.Lp + qi] : 0.f;
           named_bar_sync(1, 128);
         }
         mbar_wait(st_full, ph);
@@ -591,7 +599,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const float sl2 = p.scale * 1.4426950408889634f;
     const size_t idx = ((size_t)b * p.Hq + h) * L + qrow;
     const float lse2 = qrow < L ? p.lse[idx] * 1.4426950408889634f : INFINITY;
-    const float dl = qrow < L ? p.delta[idx] : 0.f;
+    const float dl = qrow < L ? p.delta[((size_t)b * p.Hq + h) * p.Lp + qrow] : 0.f;
     unsigned long long dstream = 0, dgrow = 0;
     if constexpr (DROP) {
       dstream = drop_stream(p.drop);
@@ -650,14 +658,22 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 // ============================================================================================================
 // PIPELINED, PERSISTENT backward (round 2). The two kernels above walk one hand-off chain per CTA (TMA -> MMA -> math ->
 // MMA, 1 CTA/SM because of TMEM): profiles/r01_attention_tc_ncu_details.csv shows issue slots 12-23 % busy. Here the
-// streamed operand is cut into 64-row HALF steps so that everything that repeats is double-buffered inside the 512 TMEM
+// streamed operand is cut into 64-row HALF steps so that everything that repeats is multi-buffered inside the 512 TMEM
 // columns and 227 KB of shared memory, and four roles run concurrently in one persistent CTA per SM:
-//     warp 0      producer : TMA loads of the resident tiles (per item) and of the streamed halves (2-stage ring)
-//     warp 1      MMA      : S/dP of half n+1 are issued BEFORE waiting for the math of half n; accumulating MMAs after it
-//     warps 2-5   math WG0 : even halves      } thread = TMEM lane (key row in dKdV, query row in dQ), 64 columns per half,
-//     warps 6-9   math WG1 : odd halves       } P / dS written as bf16 into 128B-swizzled tiles that feed the second MMAs
+//     warp 0      producer : TMA loads of the resident tiles (per item) and of the streamed halves (3-4 stage ring); in dKdV
+//                            its 32 lanes also stage the halves' per-query statistics (-lse, delta) into the ring
+//     warp 1      S/dP MMAs: runs up to two halves ahead of the math (a TMEM buffer is re-armed as soon as the math warps have copied
+//                            it into registers), straight across item boundaries
+//     warp 10     accumulating MMAs: its own issuing thread, so neither stream ever waits behind the other's dependencies
+//     warps 2-5   math WG0 : columns  0-31    } of EVERY half; thread = TMEM lane (key row in dKdV, query row in dQ);
+//     warps 6-9   math WG1 : columns 32-63    } P / dS written as bf16 into 128B-swizzled tiles that feed the second MMAs
 // Items (dKdV: key tile x kv head x batch; dQ: query tile x head x batch) are strided over the persistent grid; the next
 // item's resident tiles are fetched while the current item's accumulators drain (WG0 / WG1 drain one accumulator each).
+// v1 -> v2 (profiles/r02_attn_bwd_pipe_v1_timeline_*.txt: 17 000 cycles per 4-half item): per-half global loads of lse /
+// delta sat exposed in the math warps (~2 500 cycles) -> staged by the producer; 1 300 instructions per thread-half (two warps
+// per scheduler => 2 600 cycles) -> mask-free fast path off the diagonal, softmax scale applied once in the drain; the drain
+// waited for the TMA store's global completion -> only for its shared-memory read; one item's first S/dP waited for the
+// previous item's last accumulate -> continuous S/dP stream; head_dim 64 double-buffers the resident tiles.
 // ============================================================================================================
 constexpr int CH64 = 64 * 64 * 2;            // one [64 rows x 64 cols] bf16 box = 8 KB (a 64-row tile is D/64 of these)
 __device__ __forceinline__ uint64_t kmajor_desc_r64(uint32_t tile, int kk) {      // 64-row tile, K-major, k-step kk over d
@@ -671,18 +687,20 @@ __device__ __forceinline__ void load_tile64(unsigned char* dst, const CUtensorMa
 #pragma unroll
   for (int hh = 0; hh < D / 64; ++hh) tma_load_2d(dst + hh * CH64, tm64, bar, col + hh * 64, row);
 }
-// drain one [128 rows x NC cols] fp32 TMEM accumulator (NC = 64 or 128) to bf16 HBM: one math warpgroup (128 threads,
-// named barrier `bar_id`), swizzled staging + TMA stores for full tiles, predicated row stores for ragged ones
+// drain one [128 rows x NC cols] fp32 TMEM accumulator (NC = 64 or 128), times `scale`, to bf16 HBM: one math warpgroup (128
+// threads, named barrier `bar_id`), swizzled staging + TMA stores for full tiles (the issuer waits only until the store has
+// READ the staging tile), predicated row stores for ragged ones
 template <int NC>
-__device__ __forceinline__ void drain_acc_wg(uint32_t tacc, unsigned char* stage, const CUtensorMap* tm, int col0, int row0_global,
-                                             bool full_tile, bool row_ok, int r, __nv_bfloat16* fallback_row, int bar_id, bool issuer) {
+__device__ __forceinline__ void drain_acc_wg(uint32_t tacc, float scale, unsigned char* stage, const CUtensorMap* tm, int col0,
+                                             int row0_global, bool full_tile, bool row_ok, int r, __nv_bfloat16* fallback_row,
+                                             int bar_id, bool issuer) {
 #pragma unroll 1
   for (int c = 0; c < NC; c += 32) {
     uint32_t v[32]; float f[32];
     tmem_ld_32x32(tacc + c, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * scale;
     if (full_tile) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) st_sw128(stage + (c >> 6) * HALF_BYTES, r, ((c & 63) >> 3) + g, pack8(f + g * 8));
@@ -698,21 +716,38 @@ __device__ __forceinline__ void drain_acc_wg(uint32_t tacc, unsigned char* stage
 #pragma unroll
       for (int hh = 0; hh < NC / 64; ++hh) tma_store_2d(tm, stage + hh * HALF_BYTES, col0 + hh * 64, row0_global);
       bulk_commit();
-      bulk_wait<0>();
+      bulk_wait_read<0>();
     }
   }
 }
 
-struct PipeBars {                              // shared-memory barrier block of the pipelined kernels
-  uint64_t res_full, res_free;                 // resident tiles of the item (K,V / Q,dO): loaded / no longer read by MMAs
-  uint64_t str_full[2];                        // streamed halves landed (stage = n & 1)
+struct alignas(128) PipeBars {                 // shared-memory barrier block of the pipelined kernels
+  uint64_t res_full[2], res_free[2];           // resident tiles of an item (K,V / Q,dO): loaded / no longer read by S / dP MMAs
+  uint64_t str_full[4], str_free[4];           // streamed halves landed (stage = n % NS) / consumed by the accumulating MMAs
+  uint64_t aux_full[4];                        // dKdV: -lse / delta of the half's 64 queries staged next to the stage (32 arrivals)
   uint64_t s_full[2];                          // S / dP of half n complete in TMEM (buffer = n & 1)
+  uint64_t s_free[2];                          // every math thread has pulled its S / dP columns into registers: the buffer can take half n+2
   uint64_t p_ready[2];                         // math wrote the bf16 tiles of half n (and has finished reading S / dP)
-  uint64_t mma2_done[2];                       // accumulating MMAs of half n retired: bf16 tiles + streamed stage reusable
+  uint64_t mma2_done[2];                       // accumulating MMAs of half n retired: bf16 tiles reusable
   uint64_t acc_full, acc_free;                 // item's accumulators complete / drained
   uint32_t tmem_holder, pad;
 };
-constexpr int kPipeThreads = 320;
+constexpr int kMaxKeyWords = 128;             // dQ kernel: key-validity bits staged per item for rows up to 4096 keys
+constexpr bool kShareHalf = true;             // true: both math warpgroups split every half's columns; false: they alternate halves
+constexpr int kPipeThreads = 352;             // warp 0 producer, warp 1 S/dP issuer, warps 2-9 math, warp 10 accumulate issuer
+template <int D> constexpr int pipe_stages() { return D == 128 ? 3 : 4; }   // depth of the streamed ring
+template <int D> constexpr int pipe_res() { return D == 128 ? 1 : 2; }      // resident-tile buffers (head_dim 64 has the room)
+
+__device__ __forceinline__ void pipe_bars_init(PipeBars* bars) {
+  for (int i = 0; i < 2; ++i) {
+    mbar_init(&bars->res_full[i], 1); mbar_init(&bars->res_free[i], 1);
+    mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_free[i], kShareHalf ? 256 : 128); mbar_init(&bars->p_ready[i], kShareHalf ? 256 : 128);
+    mbar_init(&bars->mma2_done[i], 1);
+  }
+  for (int i = 0; i < 4; ++i) { mbar_init(&bars->str_full[i], 1); mbar_init(&bars->str_free[i], 1); mbar_init(&bars->aux_full[i], 32); }
+  mbar_init(&bars->acc_full, 1); mbar_init(&bars->acc_free, 256);
+  fence_mbar_init();
+}
 
 // ---- dK, dV ------------------------------------------------------------------------------------------------------
 template <int TD, bool DROP>
@@ -723,30 +758,29 @@ attn_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tm_q64, const __gri
                          const AttnTcParams p) {
   using C = TcD<TD>;
   constexpr int HT = (TD / 64) * CH64;                           // bytes of a [64 rows x TD] streamed half
+  constexpr int NS = pipe_stages<TD>(), RES = pipe_res<TD>();
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* sK = smem;
-  unsigned char* sV = sK + C::TILE;
-  unsigned char* sQh = sV + C::TILE;                             // [2][HT]
-  unsigned char* sdOh = sQh + 2 * HT;                            // [2][HT]
-  unsigned char* sPT = sdOh + 2 * HT;                            // [2][16 KB]  P^T  [128 keys x 64 queries]
+  unsigned char* sK = smem;                                      // [RES][TILE]
+  unsigned char* sV = sK + RES * C::TILE;                        // [RES][TILE]
+  unsigned char* sQh = sV + RES * C::TILE;                       // [NS][HT]
+  unsigned char* sdOh = sQh + NS * HT;                           // [NS][HT]
+  unsigned char* sPT = sdOh + NS * HT;                           // [2][16 KB]  P^T  [128 keys x 64 queries]
   unsigned char* sdST = sPT + 2 * HALF_BYTES;                    // [2][16 KB]  dS^T
   PipeBars* bars = reinterpret_cast<PipeBars*>(sdST + 2 * HALF_BYTES);
-  float* sLse = reinterpret_cast<float*>(bars + 1);             // [2][64] base-2 LSE of the half's queries
-  float* sDelta = sLse + 128;                                    // [2][64]
+  float* sNl = reinterpret_cast<float*>(bars + 1);              // [NS][64]  -lse * log2(e) of the half's queries (-inf beyond L)
+  float* sDl = sNl + NS * 64;                                    // [NS][64]  delta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.L, group = p.Hq / p.Hkv;
   const int ntiles = (L + TB - 1) / TB;
   const int n_items = ntiles * p.Hkv * p.B;
   const int nqh = (L + 63) >> 6;                                 // 64-query halves of one sequence
+  const bool dbg = p.dbg != nullptr && blockIdx.x == 0;         // tuning aid: clock64 timeline of CTA 0's first halves
+#define PTS(slot) do { if (dbg && (slot) < 64) p.dbg[slot] = clock64(); } while (0)
 
   if (threadIdx.x == 0) {
-    mbar_init(&bars->res_full, 1); mbar_init(&bars->res_free, 1); mbar_init(&bars->acc_full, 1); mbar_init(&bars->acc_free, 256);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->str_full[i], 1); mbar_init(&bars->s_full[i], 1); mbar_init(&bars->p_ready[i], 128); mbar_init(&bars->mma2_done[i], 1);
-    }
-    fence_mbar_init();
+    pipe_bars_init(bars);
     prefetch_tmap(&tm_q64); prefetch_tmap(&tm_k); prefetch_tmap(&tm_v); prefetch_tmap(&tm_do64);
   }
   if (warp == 1) { tmem_alloc(&bars->tmem_holder, 512); tmem_relinquish(); }
@@ -757,71 +791,108 @@ attn_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tm_q64, const __gri
   const uint32_t tdV = tmem + 256, tdK = tmem + 256 + TD;        // S^T / dP^T buffers: tmem + t*128 (+64)
 
   if (warp == 0) {
-    // ================= producer =================
-    if (lane == 0) {
-      int n = 0, c = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++c) {
-        const int kb = item % ntiles, hk = (item / ntiles) % p.Hkv, b = item / (ntiles * p.Hkv);
-        const int tok0 = b * L, kv0 = kb * TB;
-        mbar_wait(&bars->res_free, (c & 1) ^ 1);                 // previous item's S / dP MMAs no longer read K, V
-        mbar_arrive_expect_tx(&bars->res_full, 2 * C::TILE);
-        load_tile<TD>(sK, &tm_k, &bars->res_full, p.kcol0 + hk * TD, tok0 + kv0);
-        load_tile<TD>(sV, &tm_v, &bars->res_full, p.vcol0 + hk * TD, tok0 + kv0);
-        const int h_begin = p.causal ? 2 * kb : 0;               // query halves before the key tile see none of it
-        for (int hq = hk * group; hq < (hk + 1) * group; ++hq) {
-          for (int qh = h_begin; qh < nqh; ++qh, ++n) {
-            const int s = n & 1, u = n >> 1;
-            mbar_wait(&bars->mma2_done[s], (u & 1) ^ 1);         // stage s consumed by the accumulating MMAs of half n-2
+    // ================= producer (lane 0: TMA; all lanes: cp.async of the halves' query statistics into the stage) =================
+    int n = 0, c = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++c) {
+      const int kb = item % ntiles, hk = (item / ntiles) % p.Hkv, b = item / (ntiles * p.Hkv);
+      const int tok0 = b * L, kv0 = kb * TB, rb = c % RES;
+      if (lane == 0) {
+        mbar_wait(&bars->res_free[rb], ((c / RES) & 1) ^ 1);     // the item that used this buffer no longer reads K, V
+        mbar_arrive_expect_tx(&bars->res_full[rb], 2 * C::TILE);
+        load_tile<TD>(sK + rb * C::TILE, &tm_k, &bars->res_full[rb], p.kcol0 + hk * TD, tok0 + kv0);
+        load_tile<TD>(sV + rb * C::TILE, &tm_v, &bars->res_full[rb], p.vcol0 + hk * TD, tok0 + kv0);
+      }
+      const int h_begin = p.causal ? 2 * kb : 0;                 // query halves before the key tile see none of it
+      for (int hq = hk * group; hq < (hk + 1) * group; ++hq) {
+        for (int qh = h_begin; qh < nqh; ++qh, ++n) {
+          const int s = n % NS, u = n / NS;
+          if (lane == 0) {
+            mbar_wait(&bars->str_free[s], (u & 1) ^ 1);          // stage s consumed by the accumulating MMAs of half n-NS
+            if (n < 8) PTS(56 + n);
             mbar_arrive_expect_tx(&bars->str_full[s], 2 * HT);
             load_tile64<TD>(sQh + s * HT, &tm_q64, &bars->str_full[s], p.qcol0 + hq * TD, tok0 + qh * 64);
             load_tile64<TD>(sdOh + s * HT, &tm_do64, &bars->str_full[s], p.ocol0 + hq * TD, tok0 + qh * 64);
           }
+          __syncwarp();                                          // stage s is free for everybody
+          {
+            // -lse*log2e and delta of the half's 64 queries: 8 bytes per lane and array, global -> shared asynchronously (the
+            // padded [B,Hq,Lp] layout written by the delta kernel makes every half complete); each lane's cp.async group
+            // arrives on the stage's aux barrier when it has landed - the producer never waits for a load
+            const size_t base = ((size_t)b * p.Hq + hq) * p.Lp + (size_t)qh * 64 + lane * 2;
+            const uint32_t d0 = smem_u32(sNl + s * 64 + lane * 2), d1 = smem_u32(sDl + s * 64 + lane * 2);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0), "l"(p.nl2 + base) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d1), "l"(p.delta + base) : "memory");
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->aux_full[s])) : "memory");
+          }
         }
       }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(TB, 64);          // S^T / dP^T half: [128 keys x 64 queries]
-      constexpr uint32_t idesc_acc = make_idesc_bf16_bmn(TB, TD);    // dV / dK: B = dO / Q half, MN-major
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
-      auto issue_sp = [&](int n) {
-        const int s = n & 1, u = n >> 1;
-        mbar_wait(&bars->str_full[s], u & 1);
+      auto nh_of = [&](int item) { return group * (nqh - (p.causal ? 2 * (item % ntiles) : 0)); };
+      // the S/dP stream: one half ahead of the accumulating stream, straight across item boundaries
+      int sp_item = blockIdx.x, sp_c = 0, sp_k = 0, sp_n = 0;
+      auto sp_issue = [&]() {
+        const int rb = sp_c % RES;
+        if (sp_k == 0) mbar_wait(&bars->res_full[rb], (sp_c / RES) & 1);
+        const int st = sp_n % NS, t = sp_n & 1;
+        mbar_wait(&bars->str_full[st], (sp_n / NS) & 1);
+        if (sp_n < 8) PTS(3 * sp_n);
         tc_fence_after();
-        const uint32_t tS = tmem + (uint32_t)(s * 128), aQ = smem_u32(sQh + s * HT), aDO = smem_u32(sdOh + s * HT);
+        const uint32_t aK = smem_u32(sK + rb * C::TILE), aV = smem_u32(sV + rb * C::TILE);
+        const uint32_t tS = tmem + (uint32_t)(t * 128), aQ = smem_u32(sQh + st * HT), aDO = smem_u32(sdOh + st * HT);
 #pragma unroll
         for (int kk = 0; kk < C::KS; ++kk) umma_f16(tS, kmajor_desc(aK, kk), kmajor_desc_r64(aQ, kk), idesc_s, kk != 0);        // S^T  = K Q^T
 #pragma unroll
         for (int kk = 0; kk < C::KS; ++kk) umma_f16(tS + 64, kmajor_desc(aV, kk), kmajor_desc_r64(aDO, kk), idesc_s, kk != 0);  // dP^T = V dO^T
-        umma_commit(&bars->s_full[s]);
+        umma_commit(&bars->s_full[t]);
+        ++sp_n;
+        if (++sp_k == nh_of(sp_item)) {                          // every S / dP MMA of that item has been issued
+          umma_commit(&bars->res_free[rb]);
+          sp_item += gridDim.x; ++sp_c; sp_k = 0;
+        }
       };
+      // S/dP stream: gated only by its own inputs (resident tiles, streamed stage, a TMEM buffer the math warps have emptied)
+      while (sp_item < n_items) {
+        if (sp_n >= 2) {
+          mbar_wait(&bars->s_free[sp_n & 1], ((sp_n >> 1) - 1) & 1);      // half sp_n-2 has been copied out of this buffer
+          tc_fence_after();
+        }
+        sp_issue();
+      }
+    }
+  } else if (warp == 10) {
+    // ================= accumulate issuer: dV += P^T dO, dK += dS^T Q as soon as the math warps publish a half =================
+    if (lane == 0) {
+      constexpr uint32_t idesc_acc = make_idesc_bf16_bmn(TB, TD);    // B = dO / Q half, MN-major
       int n0 = 0, c = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++c) {
-        const int kb = item % ntiles;
-        const int NH = group * (nqh - (p.causal ? 2 * kb : 0));
-        mbar_wait(&bars->res_full, c & 1);
-        issue_sp(n0);
+        const int NH = group * (nqh - (p.causal ? 2 * (item % ntiles) : 0));
         for (int k = 0; k < NH; ++k) {
           const int n = n0 + k, s = n & 1, u = n >> 1;
-          if (k + 1 < NH) issue_sp(n + 1);
-          else umma_commit(&bars->res_free);                     // every S / dP MMA of this item has been issued
           mbar_wait(&bars->p_ready[s], u & 1);
+          if (n < 8) PTS(3 * n + 1);
           if (k == 0) mbar_wait(&bars->acc_free, (c & 1) ^ 1);   // previous item's accumulators drained
+          if (n < 8) PTS(3 * n + 2);
           tc_fence_after();
+          const int st = n % NS;
           const uint32_t aPT = smem_u32(sPT + s * HALF_BYTES), aDST = smem_u32(sdST + s * HALF_BYTES);
-          const uint32_t aQ = smem_u32(sQh + s * HT), aDO = smem_u32(sdOh + s * HT);
+          const uint32_t aQ = smem_u32(sQh + st * HT), aDO = smem_u32(sdOh + st * HT);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) umma_f16(tdV, kmajor_desc(aPT, kk), mnmajor_desc_r64(aDO, kk), idesc_acc, (k | kk) != 0);   // dV += P^T dO
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) umma_f16(tdK, kmajor_desc(aDST, kk), mnmajor_desc_r64(aQ, kk), idesc_acc, (k | kk) != 0);   // dK += dS^T Q
           umma_commit(&bars->mma2_done[s]);
+          umma_commit(&bars->str_free[st]);
         }
         umma_commit(&bars->acc_full);
         n0 += NH;
       }
     }
-  } else {
+  } else if (warp < 10) {
     // ================= math warpgroups =================
     const int g = (warp - 2) >> 2;                               // warpgroup 0 / 1 <-> buffer n & 1
     const int r = (warp & 3) * 32 + lane;                        // TMEM lane == key row of the tile (lane quarter = warp % 4)
@@ -831,48 +902,58 @@ attn_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tm_q64, const __gri
     const int lp8 = (L + 7) >> 3;
     unsigned long long dstream = 0;
     if constexpr (DROP) dstream = drop_stream(p.drop);
+    // this row's key validity for the NEXT item is fetched while the current item is processed (a per-item global load in
+    // front of the first half was ~2 000 exposed cycles per item: profiles/r02_attn_bwd_pipe_v1_timeline_llama.txt)
+    auto key_valid = [&](int item) {
+      const int kb = item % ntiles, b = item / (ntiles * p.Hkv);
+      const int key = kb * TB + r;
+      bool ok = key < L;
+      if (ok && p.mask) ok = __ldg(p.mask + (size_t)b * L + key) != 0;
+      return ok;
+    };
+    bool key_ok_next = (int)blockIdx.x < n_items ? key_valid(blockIdx.x) : false;
     int n0 = 0, c = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++c) {
       const int kb = item % ntiles, hk = (item / ntiles) % p.Hkv, b = item / (ntiles * p.Hkv);
       const int tok0 = b * L, kv0 = kb * TB;
       const int key = kv0 + r;
-      bool key_ok = key < L;
-      if (key_ok && p.mask) key_ok = p.mask[(size_t)tok0 + key] != 0;
+      const bool key_ok = key_ok_next;
+      if (item + (int)gridDim.x < n_items) key_ok_next = key_valid(item + gridDim.x);
       const int dropkey = key_ok ? 0 : -1;
+      const bool warp_keys_ok = __all_sync(0xffffffffu, key_ok);  // warp-uniform: the mask-free path needs all 32 key rows real
       const int h_begin = p.causal ? 2 * kb : 0;
       const int per_head = nqh - h_begin;
       const int NH = group * per_head;
       for (int k = 0; k < NH; ++k) {
-        const int n = n0 + k;
-        if ((n & 1) != g) continue;
-        const int u = n >> 1;
+        // EVERY half is shared by both warpgroups (WG g takes query columns [32g, 32g + 32)): two warps per scheduler work on the
+        // same half, so its math latency - which the S/dP -> math -> accumulate chain is made of - halves
+        const int n = n0 + k, t = n & 1;
+        if (!kShareHalf && t != g) continue;
+        const int u = n >> 1, st = n % NS;
         const int hq = hk * group + k / per_head, qh = h_begin + k % per_head;
         const int qbase = qh * 64;
-        named_bar_sync(1 + g, 128);                              // the warpgroup's readers of the previous half's lse / delta are done
-        if (wt < 64) {
-          const int qi = qbase + wt;
-          const size_t idx = ((size_t)b * p.Hq + hq) * L + qi;
-          sLse[g * 64 + wt] = qi < L ? p.lse[idx] * 1.4426950408889634f : INFINITY;
-          sDelta[g * 64 + wt] = qi < L ? p.delta[idx] : 0.f;
-        }
-        named_bar_sync(1 + g, 128);
-        mbar_wait(&bars->s_full[g], u & 1);
+        mbar_wait(&bars->aux_full[st], (n / NS) & 1);            // -lse / delta of the half's queries are in the stage
+        mbar_wait(&bars->s_full[t], u & 1);
+        if (wt == 0 && g == 0 && n < 8) PTS(24 + 2 * n);
         tc_fence_after();
-        mbar_wait(&bars->mma2_done[g], (u & 1) ^ 1);             // P^T / dS^T tiles of half n-2 consumed by their MMAs
+        mbar_wait(&bars->mma2_done[t], (u & 1) ^ 1);             // P^T / dS^T tiles of half n-2 consumed by their MMAs
         const bool diag = p.causal && (kv0 + TB - 1 > qbase);    // only halves on / below the diagonal band need the compare
-        const uint32_t tS = tmem + (uint32_t)(g * 128);
-        unsigned char* hp = sPT + g * HALF_BYTES;
-        unsigned char* hd = sdST + g * HALF_BYTES;
+        const bool fast = warp_keys_ok && !diag;
+        const uint32_t tS = tmem + (uint32_t)(t * 128);
+        unsigned char* hp = sPT + t * HALF_BYTES;
+        unsigned char* hd = sdST + t * HALF_BYTES;
+        const float* nlq = sNl + st * 64;
+        const float* dlq = sDl + st * 64;
 #pragma unroll 1
-        for (int cc = 0; cc < 64; cc += 32) {
+        for (int cc = kShareHalf ? g * 32 : 0; cc < (kShareHalf ? g * 32 + 32 : 64); cc += 32) {
           uint32_t vs[32], vp[32];
           tmem_ld_32x32(tS + lane_off + cc, vs);
           tmem_ld_32x32(tS + 64 + lane_off + cc, vp);
-          float lse_c[32], del_c[32];
+          float nl_c[32], del_c[32];
 #pragma unroll
-          for (int x = 0; x < 32; x += 4) {
-            *reinterpret_cast<float4*>(lse_c + x) = *reinterpret_cast<const float4*>(sLse + g * 64 + cc + x);
-            *reinterpret_cast<float4*>(del_c + x) = *reinterpret_cast<const float4*>(sDelta + g * 64 + cc + x);
+          for (int x = 0; x < 32; x += 4) {                      // per-query statistics: 128-bit broadcast reads
+            *reinterpret_cast<float4*>(nl_c + x) = *reinterpret_cast<const float4*>(nlq + cc + x);
+            *reinterpret_cast<float4*>(del_c + x) = *reinterpret_cast<const float4*>(dlq + cc + x);
           }
           uint32_t keepw = 0xffffffffu;
           if constexpr (DROP) {                                  // keep bits of (query qbase+cc+x, this key): see attn_bwd_dkv_tc_kernel
@@ -894,19 +975,39 @@ attn_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tm_q64, const __gri
             }
           }
           tmem_ld_wait();
+          if (kShareHalf || cc == 32) {
+            tc_fence_before();
+            mbar_arrive(&bars->s_free[t]);                       // S^T / dP^T columns are in registers: the TMEM buffer may be overwritten
+          }
           float pt[32], ds[32];
+          if (fast) {                                            // no padding key in this warp, no causal boundary in this half
 #pragma unroll
-          for (int x = 0; x < 32; ++x) {
-            const int drop = dropkey | (diag ? ((qbase + cc + x - key) >> 31) : 0);
-            const uint32_t bits = (__float_as_uint(__uint_as_float(vs[x]) * sl2) & ~(uint32_t)drop) | (0xff800000u & (uint32_t)drop);
-            const float pr = ex2_approx(__uint_as_float(bits) - lse_c[x]);
-            if constexpr (DROP) {
-              const float sc = ((keepw >> x) & 1u) ? p.drop.inv_keep : 0.f;
-              pt[x] = pr * sc;
-              ds[x] = pr * (__uint_as_float(vp[x]) * sc - del_c[x]) * p.scale;
-            } else {
-              pt[x] = pr;
-              ds[x] = pr * (__uint_as_float(vp[x]) - del_c[x]) * p.scale;
+            for (int x = 0; x < 32; ++x) {
+              const float pr = ex2_approx(fmaf(__uint_as_float(vs[x]), sl2, nl_c[x]));     // -lse = -inf (query beyond L / fully masked) -> 0
+              if constexpr (DROP) {
+                const float sc = ((keepw >> x) & 1u) ? p.drop.inv_keep : 0.f;              // P_drop = sc * P ; dP = sc * dP_drop
+                pt[x] = pr * sc;
+                ds[x] = pr * fmaf(__uint_as_float(vp[x]), sc, -del_c[x]);
+              } else {
+                pt[x] = pr;
+                ds[x] = pr * (__uint_as_float(vp[x]) - del_c[x]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int x = 0; x < 32; ++x) {
+              // branch-free masking: dropped (padding key, or key in the query's causal future) -> -inf
+              const int drop = dropkey | (diag ? ((qbase + cc + x - key) >> 31) : 0);
+              const uint32_t bits = (__float_as_uint(__uint_as_float(vs[x]) * sl2) & ~(uint32_t)drop) | (0xff800000u & (uint32_t)drop);
+              const float pr = ex2_approx(__uint_as_float(bits) + nl_c[x]);
+              if constexpr (DROP) {
+                const float sc = ((keepw >> x) & 1u) ? p.drop.inv_keep : 0.f;
+                pt[x] = pr * sc;
+                ds[x] = pr * fmaf(__uint_as_float(vp[x]), sc, -del_c[x]);
+              } else {
+                pt[x] = pr;
+                ds[x] = pr * (__uint_as_float(vp[x]) - del_c[x]);
+              }
             }
           }
 #pragma unroll
@@ -917,25 +1018,30 @@ attn_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tm_q64, const __gri
         }
         tc_fence_before();
         fence_proxy_async();
-        mbar_arrive(&bars->p_ready[g]);
+        mbar_arrive(&bars->p_ready[t]);
+        if (wt == 0 && g == 0 && n < 8) PTS(24 + 2 * n + 1);
       }
-      // ---- item end: all accumulating MMAs retired -> WG0 drains dV, WG1 drains dK ----
+      // ---- item end: all accumulating MMAs retired -> WG0 drains dV, WG1 drains dK (dS was left unscaled: dK *= scale here) ----
       mbar_wait(&bars->acc_full, c & 1);
+      if (wt == 0 && g == 0 && c < 4) PTS(40 + 2 * c);
       tc_fence_after();
       {
         const bool st_ok = key < L, full = kv0 + TB <= L;
         const size_t rowoff = (size_t)(tok0 + (st_ok ? key : 0));
-        if (g == 0) drain_acc_wg<TD>(tdV + lane_off, sPT, &tm_dv, hk * TD, tok0 + kv0, full, st_ok, r,
+        if (g == 0) drain_acc_wg<TD>(tdV + lane_off, 1.f, sPT, &tm_dv, hk * TD, tok0 + kv0, full, st_ok, r,
                                      p.dv + rowoff * p.lddv + (size_t)hk * TD, 1, wt == 0);
-        else        drain_acc_wg<TD>(tdK + lane_off, sdST, &tm_dk, hk * TD, tok0 + kv0, full, st_ok, r,
+        else        drain_acc_wg<TD>(tdK + lane_off, p.scale, sdST, &tm_dk, hk * TD, tok0 + kv0, full, st_ok, r,
                                      p.dk + rowoff * p.lddk + (size_t)hk * TD, 2, wt == 0);
       }
       tc_fence_before();
       mbar_arrive(&bars->acc_free);
       named_bar_sync(3, 256);                                    // both staging areas are free before the next item's halves write them
+      if (wt == 0 && g == 0 && c < 4) PTS(40 + 2 * c + 1);
       n0 += NH;
     }
+    if (wt == 0) bulk_wait<0>();                                 // the last TMA stores have left before the CTA's shared memory goes away
   }
+#undef PTS
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
@@ -949,14 +1055,16 @@ attn_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                         const __grid_constant__ CUtensorMap tm_dq, const AttnTcParams p) {
   using C = TcD<TD>;
   constexpr int HT = (TD / 64) * CH64;
+  constexpr int NS = pipe_stages<TD>(), RES = pipe_res<TD>();
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* sQ = smem;
-  unsigned char* sdO = sQ + C::TILE;
-  unsigned char* sKh = sdO + C::TILE;                            // [2][HT]
-  unsigned char* sVh = sKh + 2 * HT;                             // [2][HT]
-  unsigned char* sdS = sVh + 2 * HT;                             // [2][16 KB]  dS [128 queries x 64 keys]
+  unsigned char* sQ = smem;                                      // [RES][TILE]
+  unsigned char* sdO = sQ + RES * C::TILE;                       // [RES][TILE]
+  unsigned char* sKh = sdO + RES * C::TILE;                      // [NS][HT]
+  unsigned char* sVh = sKh + NS * HT;                            // [NS][HT]
+  unsigned char* sdS = sVh + NS * HT;                            // [2][16 KB]  dS [128 queries x 64 keys]
   PipeBars* bars = reinterpret_cast<PipeBars*>(sdS + 2 * HALF_BYTES);
+  uint32_t* sKeyBits = reinterpret_cast<uint32_t*>(bars + 1);   // [2][kMaxKeyWords] validity bits of the item's key row (word w: keys 32w..)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.L, group = p.Hq / p.Hkv;
@@ -964,11 +1072,7 @@ attn_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   const int n_items = ntiles * p.Hq * p.B;
 
   if (threadIdx.x == 0) {
-    mbar_init(&bars->res_full, 1); mbar_init(&bars->res_free, 1); mbar_init(&bars->acc_full, 1); mbar_init(&bars->acc_free, 256);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->str_full[i], 1); mbar_init(&bars->s_full[i], 1); mbar_init(&bars->p_ready[i], 128); mbar_init(&bars->mma2_done[i], 1);
-    }
-    fence_mbar_init();
+    pipe_bars_init(bars);
     prefetch_tmap(&tm_q); prefetch_tmap(&tm_k64); prefetch_tmap(&tm_v64); prefetch_tmap(&tm_do);
   }
   if (warp == 1) { tmem_alloc(&bars->tmem_holder, 512); tmem_relinquish(); }
@@ -985,15 +1089,15 @@ attn_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       int n = 0, c = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++c) {
         const int qb = item % ntiles, h = (item / ntiles) % p.Hq, b = item / (ntiles * p.Hq);
-        const int hk = h / group, tok0 = b * L, q0 = qb * TB;
-        mbar_wait(&bars->res_free, (c & 1) ^ 1);
-        mbar_arrive_expect_tx(&bars->res_full, 2 * C::TILE);
-        load_tile<TD>(sQ, &tm_q, &bars->res_full, p.qcol0 + h * TD, tok0 + q0);
-        load_tile<TD>(sdO, &tm_do, &bars->res_full, p.ocol0 + h * TD, tok0 + q0);
+        const int hk = h / group, tok0 = b * L, q0 = qb * TB, rb = c % RES;
+        mbar_wait(&bars->res_free[rb], ((c / RES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars->res_full[rb], 2 * C::TILE);
+        load_tile<TD>(sQ + rb * C::TILE, &tm_q, &bars->res_full[rb], p.qcol0 + h * TD, tok0 + q0);
+        load_tile<TD>(sdO + rb * C::TILE, &tm_do, &bars->res_full[rb], p.ocol0 + h * TD, tok0 + q0);
         const int NH = n_halves(qb);
         for (int j = 0; j < NH; ++j, ++n) {
-          const int s = n & 1, u = n >> 1;
-          mbar_wait(&bars->mma2_done[s], (u & 1) ^ 1);
+          const int s = n % NS, u = n / NS;
+          mbar_wait(&bars->str_free[s], (u & 1) ^ 1);
           mbar_arrive_expect_tx(&bars->str_full[s], 2 * HT);
           load_tile64<TD>(sKh + s * HT, &tm_k64, &bars->str_full[s], p.kcol0 + hk * TD, tok0 + j * 64);
           load_tile64<TD>(sVh + s * HT, &tm_v64, &bars->str_full[s], p.vcol0 + hk * TD, tok0 + j * 64);
@@ -1003,41 +1107,57 @@ attn_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(TB, 64);
-      constexpr uint32_t idesc_acc = make_idesc_bf16_bmn(TB, TD);
-      const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sdO);
-      auto issue_sp = [&](int n) {
-        const int s = n & 1, u = n >> 1;
-        mbar_wait(&bars->str_full[s], u & 1);
+      int sp_item = blockIdx.x, sp_c = 0, sp_k = 0, sp_n = 0;
+      auto sp_issue = [&]() {
+        const int rb = sp_c % RES;
+        if (sp_k == 0) mbar_wait(&bars->res_full[rb], (sp_c / RES) & 1);
+        const int st = sp_n % NS, t = sp_n & 1;
+        mbar_wait(&bars->str_full[st], (sp_n / NS) & 1);
         tc_fence_after();
-        const uint32_t tS = tmem + (uint32_t)(s * 128), aK = smem_u32(sKh + s * HT), aV = smem_u32(sVh + s * HT);
+        const uint32_t aQ = smem_u32(sQ + rb * C::TILE), aDO = smem_u32(sdO + rb * C::TILE);
+        const uint32_t tS = tmem + (uint32_t)(t * 128), aK = smem_u32(sKh + st * HT), aV = smem_u32(sVh + st * HT);
 #pragma unroll
         for (int kk = 0; kk < C::KS; ++kk) umma_f16(tS, kmajor_desc(aQ, kk), kmajor_desc_r64(aK, kk), idesc_s, kk != 0);        // S  = Q K^T
 #pragma unroll
         for (int kk = 0; kk < C::KS; ++kk) umma_f16(tS + 64, kmajor_desc(aDO, kk), kmajor_desc_r64(aV, kk), idesc_s, kk != 0);  // dP = dO V^T
-        umma_commit(&bars->s_full[s]);
+        umma_commit(&bars->s_full[t]);
+        ++sp_n;
+        if (++sp_k == n_halves(sp_item % ntiles)) {
+          umma_commit(&bars->res_free[rb]);
+          sp_item += gridDim.x; ++sp_c; sp_k = 0;
+        }
       };
+      while (sp_item < n_items) {
+        if (sp_n >= 2) {
+          mbar_wait(&bars->s_free[sp_n & 1], ((sp_n >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        sp_issue();
+      }
+    }
+  } else if (warp == 10) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_acc = make_idesc_bf16_bmn(TB, TD);
       int n0 = 0, c = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++c) {
         const int NH = n_halves(item % ntiles);
-        mbar_wait(&bars->res_full, c & 1);
-        issue_sp(n0);
         for (int k = 0; k < NH; ++k) {
           const int n = n0 + k, s = n & 1, u = n >> 1;
-          if (k + 1 < NH) issue_sp(n + 1);
-          else umma_commit(&bars->res_free);
           mbar_wait(&bars->p_ready[s], u & 1);
           if (k == 0) mbar_wait(&bars->acc_free, (c & 1) ^ 1);
           tc_fence_after();
-          const uint32_t aDS = smem_u32(sdS + s * HALF_BYTES), aK = smem_u32(sKh + s * HT);
+          const int st = n % NS;
+          const uint32_t aDS = smem_u32(sdS + s * HALF_BYTES), aK = smem_u32(sKh + st * HT);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) umma_f16(tdQ, kmajor_desc(aDS, kk), mnmajor_desc_r64(aK, kk), idesc_acc, (k | kk) != 0);   // dQ += dS K
           umma_commit(&bars->mma2_done[s]);
+          umma_commit(&bars->str_free[st]);
         }
         umma_commit(&bars->acc_full);
         n0 += NH;
       }
     }
-  } else {
+  } else if (warp < 10) {
     const int g = (warp - 2) >> 2;
     const int r = (warp & 3) * 32 + lane;                        // query row of the tile == TMEM lane
     const int wt = threadIdx.x - 64 - g * 128;
@@ -1045,38 +1165,70 @@ attn_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     const float sl2 = p.scale * 1.4426950408889634f;
     unsigned long long dstream = 0;
     if constexpr (DROP) dstream = drop_stream(p.drop);
+    // this row's statistics of the NEXT item are fetched while the current item is processed
+    auto stats = [&](int item, float& nl, float& dl) {
+      const int qb = item % ntiles, h = (item / ntiles) % p.Hq, b = item / (ntiles * p.Hq);
+      const int qrow = qb * TB + r;
+      const size_t idx = ((size_t)b * p.Hq + h) * p.Lp + qrow;     // padded rows: no bounds test for rows of a ragged tile...
+      nl = qrow < p.Lp ? p.nl2[idx] : -INFINITY;                   // ...inside the pad; beyond it (Lp % 128 == 64) nothing exists
+      dl = qrow < p.Lp ? p.delta[idx] : 0.f;
+    };
+    // key-validity bits of an item's batch row -> sKeyBits[buf]: warp w of the 8 math warps ballots words w, w+8, ...
+    const int mw = warp - 2;
+    auto key_bits_row = [&](int item, int buf) {
+      const int b = item / (ntiles * p.Hq);
+      const int64_t* mrow = p.mask ? p.mask + (size_t)b * L : nullptr;
+      const int nwords = (L + 31) >> 5;
+      for (int w = mw; w < nwords && w < kMaxKeyWords; w += 8) {
+        const int key = w * 32 + lane;
+        bool keep = key < L;
+        if (keep && mrow) keep = __ldg(mrow + key) != 0;
+        const uint32_t bits = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) sKeyBits[buf * kMaxKeyWords + w] = bits;
+      }
+    };
+    float nl_next = 0.f, dl_next = 0.f;
+    if ((int)blockIdx.x < n_items) { stats(blockIdx.x, nl_next, dl_next); key_bits_row(blockIdx.x, 0); }
+    named_bar_sync(3, 256);
     int n0 = 0, c = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++c) {
       const int qb = item % ntiles, h = (item / ntiles) % p.Hq, b = item / (ntiles * p.Hq);
       const int tok0 = b * L, q0 = qb * TB, qrow = q0 + r;
-      const size_t idx = ((size_t)b * p.Hq + h) * L + qrow;
-      const float lse2 = qrow < L ? p.lse[idx] * 1.4426950408889634f : INFINITY;
-      const float dl = qrow < L ? p.delta[idx] : 0.f;
+      const float nl = nl_next, dl = dl_next;
+      if (item + (int)gridDim.x < n_items) {                     // next item's statistics and key bits: in flight during this item
+        stats(item + gridDim.x, nl_next, dl_next);
+        key_bits_row(item + gridDim.x, (c + 1) & 1);
+      }
+      const uint32_t* kbrow = sKeyBits + (c & 1) * kMaxKeyWords;
       unsigned long long dgrow = 0;
       if constexpr (DROP) dgrow = (((unsigned long long)b * p.Hq + h) * L + (unsigned long long)qrow) * (unsigned long long)((L + 7) >> 3);
       const int NH = n_halves(qb);
-      const int64_t* mrow = p.mask ? p.mask + (size_t)tok0 : nullptr;
       for (int k = 0; k < NH; ++k) {
-        const int n = n0 + k;
-        if ((n & 1) != g) continue;
+        const int n = n0 + k, t = n & 1;
+        if (!kShareHalf && t != g) continue;
         const int u = n >> 1, kv0 = k * 64;
         uint32_t kbits[2];
+        if (2 * k + 1 < kMaxKeyWords) { kbits[0] = kbrow[2 * k]; kbits[1] = kbrow[2 * k + 1]; }
+        else {                                                   // rows longer than the staged bits (L > 32 * kMaxKeyWords): direct
+          const int64_t* mrow = p.mask ? p.mask + (size_t)tok0 : nullptr;
 #pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          const int key = kv0 + w * 32 + lane;
-          bool keep = key < L;
-          if (keep && mrow) keep = mrow[key] != 0;
-          kbits[w] = __ballot_sync(0xffffffffu, keep);
+          for (int w = 0; w < 2; ++w) {
+            const int key = kv0 + w * 32 + lane;
+            bool keep = key < L;
+            if (keep && mrow) keep = mrow[key] != 0;
+            kbits[w] = __ballot_sync(0xffffffffu, keep);
+          }
         }
         const bool diag = p.causal && (kv0 + 63 > q0);
+        const bool fast = !diag && (kbits[0] & kbits[1]) == 0xffffffffu;
         const int dcol = diag ? (qrow - kv0) : 0x7fffffff;
-        mbar_wait(&bars->s_full[g], u & 1);
+        mbar_wait(&bars->s_full[t], u & 1);
         tc_fence_after();
-        mbar_wait(&bars->mma2_done[g], (u & 1) ^ 1);             // dS tile of half n-2 consumed
-        const uint32_t tS = tmem + (uint32_t)(g * 128);
-        unsigned char* hd = sdS + g * HALF_BYTES;
+        mbar_wait(&bars->mma2_done[t], (u & 1) ^ 1);             // dS tile of half n-2 consumed
+        const uint32_t tS = tmem + (uint32_t)(t * 128);
+        unsigned char* hd = sdS + t * HALF_BYTES;
 #pragma unroll 1
-        for (int cc = 0; cc < 64; cc += 32) {
+        for (int cc = kShareHalf ? g * 32 : 0; cc < (kShareHalf ? g * 32 + 32 : 64); cc += 32) {
           uint32_t vs[32], vp[32];
           tmem_ld_32x32(tS + lane_off + cc, vs);
           tmem_ld_32x32(tS + 64 + lane_off + cc, vp);
@@ -1086,29 +1238,42 @@ attn_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             for (int q4 = 0; q4 < 4; ++q4) drop_scale8(p.drop, dstream, dgrow + (unsigned long long)(((kv0 + cc) >> 3) + q4), dsc + q4 * 8);
           }
           tmem_ld_wait();
-          const uint32_t kw = kbits[cc >> 5];
+          if (kShareHalf || cc == 32) {
+            tc_fence_before();
+            mbar_arrive(&bars->s_free[t]);
+          }
           float ds[32];
+          if (fast) {
 #pragma unroll
-          for (int x = 0; x < 32; ++x) {
-            const int drop = ((dcol - (cc + x)) >> 31) | (int)(((kw >> x) & 1u) - 1u);
-            const uint32_t bits = (__float_as_uint(__uint_as_float(vs[x]) * sl2) & ~(uint32_t)drop) | (0xff800000u & (uint32_t)drop);
-            const float pr = ex2_approx(__uint_as_float(bits) - lse2);
-            if constexpr (DROP) ds[x] = pr * (__uint_as_float(vp[x]) * dsc[x] - dl) * p.scale;
-            else                ds[x] = pr * (__uint_as_float(vp[x]) - dl) * p.scale;
+            for (int x = 0; x < 32; ++x) {
+              const float pr = ex2_approx(fmaf(__uint_as_float(vs[x]), sl2, nl));
+              if constexpr (DROP) ds[x] = pr * fmaf(__uint_as_float(vp[x]), dsc[x], -dl);
+              else                ds[x] = pr * (__uint_as_float(vp[x]) - dl);
+            }
+          } else {
+            const uint32_t kw = kbits[cc >> 5];
+#pragma unroll
+            for (int x = 0; x < 32; ++x) {
+              const int drop = ((dcol - (cc + x)) >> 31) | (int)(((kw >> x) & 1u) - 1u);
+              const uint32_t bits = (__float_as_uint(__uint_as_float(vs[x]) * sl2) & ~(uint32_t)drop) | (0xff800000u & (uint32_t)drop);
+              const float pr = ex2_approx(__uint_as_float(bits) + nl);
+              if constexpr (DROP) ds[x] = pr * fmaf(__uint_as_float(vp[x]), dsc[x], -dl);
+              else                ds[x] = pr * (__uint_as_float(vp[x]) - dl);
+            }
           }
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) st_sw128(hd, r, (cc >> 3) + q4, pack8(ds + q4 * 8));
         }
         tc_fence_before();
         fence_proxy_async();
-        mbar_arrive(&bars->p_ready[g]);
+        mbar_arrive(&bars->p_ready[t]);
       }
-      // ---- item end: dQ complete -> WG g drains columns [g*64, g*64+64) (TD = 64: WG0 alone) ----
+      // ---- item end: dQ complete -> WG g drains columns [g*64, g*64+64) (TD = 64: WG0 alone); dS was unscaled: dQ *= scale ----
       mbar_wait(&bars->acc_full, c & 1);
       tc_fence_after();
       if (g * 64 < TD) {
         __nv_bfloat16* dqrow = p.dq + (size_t)(tok0 + (qrow < L ? qrow : 0)) * p.lddq + (size_t)h * TD + g * 64;
-        drain_acc_wg<64>(tdQ + lane_off + (uint32_t)(g * 64), sdS + g * HALF_BYTES, &tm_dq, h * TD + g * 64, tok0 + q0,
+        drain_acc_wg<64>(tdQ + lane_off + (uint32_t)(g * 64), p.scale, sdS + g * HALF_BYTES, &tm_dq, h * TD + g * 64, tok0 + q0,
                          q0 + TB <= L, qrow < L, r, dqrow, 1 + g, wt == 0);
       }
       tc_fence_before();
@@ -1116,14 +1281,20 @@ attn_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       named_bar_sync(3, 256);
       n0 += NH;
     }
+    if (wt == 0) bulk_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-template <int D> constexpr int dkv_pipe_smem() { return 2 * TcD<D>::TILE + 4 * (D / 64) * CH64 + 4 * HALF_BYTES + 1024 + 2048; }
-template <int D> constexpr int dq_pipe_smem() { return 2 * TcD<D>::TILE + 4 * (D / 64) * CH64 + 2 * HALF_BYTES + 1024 + 1024; }
+template <int D> constexpr int dkv_pipe_smem() {
+  return 2 * pipe_res<D>() * TcD<D>::TILE + 2 * pipe_stages<D>() * (D / 64) * CH64 + 4 * HALF_BYTES + 1024 + 256 + 2 * pipe_stages<D>() * 256;
+}
+template <int D> constexpr int dq_pipe_smem() {
+  return 2 * pipe_res<D>() * TcD<D>::TILE + 2 * pipe_stages<D>() * (D / 64) * CH64 + 2 * HALF_BYTES + 1024 + 256 + 2 * kMaxKeyWords * 4;
+}
+static_assert(dkv_pipe_smem<128>() <= 232448 && dq_pipe_smem<128>() <= 232448, "pipelined attention backward exceeds 227 KB of shared memory");
 
 template <int D> constexpr int dkv_smem() { return 4 * TcD<D>::TILE + 2 * TILE_BYTES + 1024 + 2048; }
 template <int D> constexpr int dq_smem() { return 4 * TcD<D>::TILE + TILE_BYTES + 1024 + 1024; }
@@ -1195,7 +1366,8 @@ static int launch_tc_bwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUt
   }
   const int total_warps = p.B * p.L * p.Hq;
   attn_tc_delta_kernel<D><<<(total_warps * 32 + 255) / 256, 256, 0, st>>>((const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)d_out,
-                                                                         lddo, delta, p.B, p.L, p.Hq);
+                                                                         lddo, p.lse, delta, delta + (size_t)p.B * p.Hq * p.Lp,
+                                                                         p.B, p.L, p.Lp, p.Hq);
   if (int e = check_launch("attn_tc_delta_kernel")) return e;
   const int ntiles = (p.L + TB - 1) / TB;
   if (g_attn_bwd_pipe) {
@@ -1221,7 +1393,7 @@ static int launch_tc_bwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUt
   return check_launch("attn_bwd_dq_tc_kernel");
 }
 
-// backward: d_out bf16 [B*L, Hq*D (docols)], delta: fp32 workspace [B,Hq,L]; dq/dk/dv bf16 token-major outputs
+// backward: d_out bf16 [B*L, Hq*D (docols)], delta: fp32 workspace of 2*B*Hq*Lp floats (Lp = L rounded up to 64); dq/dk/dv bf16 token-major outputs
 extern "C" int dalm_b200_attention_tc_bwd(const void* q, long long ldq, long long qcols, const void* k, long long ldk,
                                           long long kcols, const void* v, long long ldv, long long vcols,
                                           const int64_t* mask, const void* out, long long ldo, const float* lse,
@@ -1252,8 +1424,11 @@ extern "C" int dalm_b200_attention_tc_bwd(const void* q, long long ldq, long lon
   if (int e = tc_maps(dv, rows, (long long)Hkv * D, lddv, &mdv)) return e;
   AttnTcParams p{};
   p.mask = mask; p.lse = const_cast<float*>(lse); p.delta = delta; p.B = B; p.L = L; p.Hq = Hq; p.Hkv = Hkv;
+  p.Lp = (L + 63) / 64 * 64;
+  p.nl2 = delta + (size_t)B * Hq * p.Lp;                          // second half of the workspace (see attn_tc_delta_kernel)
   p.scale = scale; p.causal = causal;
   p.dq = (__nv_bfloat16*)dq; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv; p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
+  p.dbg = g_attn_dbg;
   p.drop = make_drop(drop_p, drop_seed, drop_stream_id, drop_offset);
   cudaStream_t st = (cudaStream_t)stream;
   if (D == 128) return launch_tc_bwd<128, false>(mq, mk, mv, mdo, mq64, mk64, mv64, mdo64, mdq, mdk, mdv, p, out, ldo, d_out, lddo, delta, st);

@@ -260,7 +260,7 @@ def attention_tc_bwd(q, k, v, mask, out, lse, d_out, B: int, L: int, Hq: int, Hk
     if dq is None: dq = torch.empty(B * L, Hq * D, dtype=bf16, device=dev)
     if dk is None: dk = torch.empty(B * L, Hkv * D, dtype=bf16, device=dev)
     if dv is None: dv = torch.empty(B * L, Hkv * D, dtype=bf16, device=dev)
-    delta = torch.empty(B, Hq, L, dtype=f32, device=dev)
+    delta = torch.empty(2, B, Hq, (L + 63) // 64 * 64, dtype=f32, device=dev)      # workspace: rowsum(dO*O) and -lse*log2e, rows padded to 64
     scale = 1.0 / math.sqrt(D) if scale is None else scale
     _lib.call("dalm_b200_attention_tc_bwd", _p(q), _ld(q), q.shape[1], _p(k), _ld(k), k.shape[1], _p(v), _ld(v), v.shape[1],
               _p(mask), _p(out), _ld(out), _p(lse), _p(d_out), _ld(d_out), d_out.shape[1], _p(delta), _p(dq), _ld(dq),

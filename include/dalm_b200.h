@@ -104,6 +104,8 @@ int dalm_b200_attention_tc_fwd(const void* q, long long ldq, long long qcols, in
                                int D, float scale, int causal, float drop_p, unsigned long long drop_seed,
                                unsigned long long drop_stream_id, const void* drop_offset, void* stream);
 
+/* attention_tc_bwd's `delta` is a caller-provided fp32 WORKSPACE of 2 * B * Hq * Lp floats, Lp = L rounded up to a multiple
+ * of 64 (rowsum(dO*O) and -lse*log2(e) per query, padded rows). */
 /* backward kernel selection (test / tuning hook): 1 = pipelined persistent dKdV / dQ kernels (default), 0 = the
  * one-chain-per-CTA kernels they replaced (kept as an independent cross-check) */
 void dalm_b200_attention_tc_set_mode(int pipelined_backward);
