@@ -1178,7 +1178,7 @@ attn_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     auto key_bits_row = [&](int item, int buf) {
       const int b = item / (ntiles * p.Hq);
       const int64_t* mrow = p.mask ? p.mask + (size_t)b * L : nullptr;
-      const int nwords = (L + 31) >> 5;
+      const int nwords = ((L + 63) >> 6) * 2;                    // two words per 64-key half, the last half may be partly beyond L
       for (int w = mw; w < nwords && w < kMaxKeyWords; w += 8) {
         const int key = w * 32 + lane;
         bool keep = key < L;

@@ -35,7 +35,8 @@ def ref64(q, k, v, mask, causal, B, L, Hq, Hkv, D, dm, d_out):
 cases = [(2, 256, 2, 2, 128, True, "none", 0.0), (3, 200, 4, 4, 128, True, "right", 0.0), (2, 96, 4, 4, 128, True, "left", 0.0),
          (1, 300, 4, 2, 128, True, "right", 0.0), (2, 384, 2, 2, 128, False, "right", 0.0), (18, 256, 32, 32, 128, True, "none", 0.0),
          (5, 50, 16, 16, 64, False, "right", 0.1), (4, 128, 16, 16, 64, False, "right", 0.1), (3, 37, 4, 4, 64, False, "none", 0.1),
-         (2, 300, 7, 1, 64, True, "left", 0.0), (1, 1024, 71, 1, 64, True, "none", 0.0), (150, 50, 16, 16, 64, False, "right", 0.1)]
+         (2, 300, 7, 1, 64, True, "left", 0.0), (1, 1024, 71, 1, 64, True, "none", 0.0), (150, 50, 16, 16, 64, False, "right", 0.1),
+         (2, 200, 2, 2, 64, False, "right", 0.1), (2, 384, 4, 2, 64, True, "right", 0.0), (3, 100, 2, 2, 128, False, "left", 0.0)]
 worst = 0.0
 for (B, L, Hq, Hkv, D, causal, pad, pd) in cases:
     torch.manual_seed(B * 1000 + L + Hq)
