@@ -276,12 +276,15 @@ def trainer_e2e_run(args, rank: int, world: int, cache_dir: str):
             synthetic.write_model_dir(gdir, "llama", args.generator, with_weights=False)
     if world > 1:
         torch.distributed.barrier()
-    out = os.path.join(cache_dir, f"trainer_out_{rank}")
-    shutil.rmtree(out, ignore_errors=True)
+    out = os.path.join(cache_dir, "trainer_out")
+    if rank == 0:
+        shutil.rmtree(out, ignore_errors=True)
+    if world > 1:
+        torch.distributed.barrier()
     loop.STEP_PROBE = {"warmup": W, "steps": K}
     try:
         train_e2e(csv, rdir, gdir, per_device_train_batch_size=BS, max_train_steps=(W + K) * world, num_train_epochs=1,
-                  use_peft=Mode.BOTH, num_warmup_steps=2, with_tracking=True, output_dir=None if rank else out, seed=42)
+                  use_peft=Mode.BOTH, num_warmup_steps=2, with_tracking=True, output_dir=out, seed=42)   # same dir on every rank
         probe = loop.STEP_PROBE
     finally:
         loop.STEP_PROBE = None
@@ -360,6 +363,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        from dalm_b200.accel import nccl_env_defaults
+        nccl_env_defaults()                                   # NCCL_MAX_CTAS before the communicator exists
         dist.init_process_group("nccl", device_id=dev)
     from dalm_b200 import _lib, ops, synthetic
     from dalm_b200.engine import params
@@ -446,7 +451,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(batches, use_timer, eager=False):
+    def timed(batches, use_timer, eager=False, record=False):
         for i in range(args.warmup):
             train_step(batches[i], eager)
         sync_all()
@@ -458,7 +463,7 @@ def main():
         e0.record()
         loss = None
         for i in range(args.steps):
-            loss = train_step(batches[args.warmup + i], eager, record=(use_timer is None and world > 1))
+            loss = train_step(batches[args.warmup + i], eager, record=record)
         e1.record()
         sync_all()
         ops.GEMM_TIMER = None
@@ -473,7 +478,7 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    total_ms, loss, launches = timed(resident, None if graphed is not None else timer)
+    total_ms, loss, launches = timed(resident, None if graphed is not None else timer, record=world > 1)
     coll_per_step = sync.collectives / (args.warmup + args.steps) if world > 1 else 0
     if sampler:
         sampler.stop_flag = True

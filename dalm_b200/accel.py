@@ -29,6 +29,15 @@ def set_seed(seed: int) -> None:
         torch.cuda.manual_seed_all(seed)
 
 
+def nccl_env_defaults() -> None:
+    """Must run before the NCCL communicator is created. Caps the CTAs (= SMs) NCCL's kernels may occupy: collectives that
+    overlap the backward share the GPU with persistent one-CTA-per-SM GEMMs, which are launched on the remaining SMs
+    (GradientSync / ops.GEMM_MAX_CTAS). DALM_B200_NCCL_CTAS overrides (0 = leave NCCL's default)."""
+    n = os.environ.get("DALM_B200_NCCL_CTAS", "8")
+    if n != "0":
+        os.environ.setdefault("NCCL_MAX_CTAS", n)
+
+
 class _RankLogger(logging.LoggerAdapter):
     """accelerate.logging.get_logger: `main_process_only` kwarg (default True)"""
 
@@ -137,6 +146,11 @@ class GradientSync:
         # runs launch eagerly (a 230 ms step hides the launch cost).
         self.armed = True
         self.side = None
+        if world > 1 and self.large and nccl:
+            from . import ops
+            reserve = int(os.environ.get("NCCL_MAX_CTAS", "0") or 0)
+            if reserve > 0:                                    # leave NCCL's CTAs their SMs (see ops.GEMM_MAX_CTAS)
+                ops.GEMM_MAX_CTAS = max(148 - reserve, 64)
         if world > 1 and self.large:
             if torch.cuda.is_available() and torch.device(device).type == "cuda":
                 self.side = torch.cuda.Stream(device=device)
@@ -233,6 +247,7 @@ class Accelerator:
                  gradient_accumulation_steps: int = 1, cpu: bool = False):
         world = int(os.environ.get("WORLD_SIZE", "1"))
         self.use_cuda = torch.cuda.is_available() and not cpu
+        nccl_env_defaults()
         if world > 1 and not (dist.is_available() and dist.is_initialized()):
             if self.use_cuda:
                 torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))

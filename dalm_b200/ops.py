@@ -162,6 +162,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
         if resid.dtype not in (bf16, f32):
             raise _lib.DalmB200Error("gemm: resid must be bf16 or fp32")
         rf32 = 1 if resid.dtype == f32 else 0
+    if max_ctas == 0 and GEMM_MAX_CTAS:
+        max_ctas = GEMM_MAX_CTAS
     timer = GEMM_TIMER
     if timer is not None:
         timer.begin(2.0 * M * N * K, (M, N, K, int(layout), str(out.dtype)[6:], "resid" if resid is not None else "-",
@@ -216,6 +218,11 @@ class GemmTimer:
 
 
 GEMM_TIMER = None
+# Persistent-GEMM grid cap (0 = one CTA per SM). accel.GradientSync lowers it while collectives overlap the backward (full
+# fine-tuning on > 1 rank): the GEMM walks its tiles with a static stride of gridDim, so a CTA that cannot be scheduled because
+# NCCL's kernels hold its SM would run ALL of its tiles after the others finished - measured at N=2: GEMMs at 813 instead of
+# 1164 TFLOP/s, the overlap bought nothing (profiles/r02_bench_cfg3_fullft_n2.json). Leaving NCCL its SMs keeps the wave intact.
+GEMM_MAX_CTAS = 0
 
 
 # ----------------------------------------------------------------------------------------------------------------
