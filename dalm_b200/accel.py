@@ -33,7 +33,7 @@ def nccl_env_defaults() -> None:
     """Must run before the NCCL communicator is created. Caps the CTAs (= SMs) NCCL's kernels may occupy: collectives that
     overlap the backward share the GPU with persistent one-CTA-per-SM GEMMs, which are launched on the remaining SMs
     (GradientSync / ops.GEMM_MAX_CTAS). DALM_B200_NCCL_CTAS overrides (0 = leave NCCL's default)."""
-    n = os.environ.get("DALM_B200_NCCL_CTAS", "8")
+    n = os.environ.get("DALM_B200_NCCL_CTAS", "16")
     if n != "0":
         os.environ.setdefault("NCCL_MAX_CTAS", n)
 
