@@ -421,7 +421,9 @@ def main():
     from dalm_b200.accel import GradientSync
     sync = GradientSync(banks, world, dev, nccl=True)
     graphed = None
-    if args.graph and not sync.overlaps_backward:          # full fine-tuning on N > 1: bucket all-reduces are issued during backward
+    big = args.config == "cfg-5"       # 125 GB of parameters + Adam state: no room for a graph's private pool NEXT TO the eager
+    #                                    roofline pass's activations; a 3 s step hides its launch overhead anyway
+    if args.graph and not sync.overlaps_backward and not big:   # full fine-tuning on N > 1: bucket all-reduces are issued during backward
         try:
             graphed = GraphedStep(step_fn, model, resident[0], 100.0, zero_grads=opt.zero_grad)
         except Exception as e:

@@ -38,6 +38,11 @@ struct GemmEpilogue {
   int M, N, K;
   DropCfg drop;         // dropout on act(alpha*acc+bias) BEFORE the residual add (BertSelfOutput / BertOutput); p = 0 => off
   int group_m;          // tile rasterisation: bands of group_m m-tiles, n-tiles walked serpentine inside a band (0 = m-fastest)
+  int fuse;             // 0: none; 1: SwiGLU forward - tile columns [0,128) = gate, [128,256) = up of the same 128 features (weight
+                        // rows interleaved); besides `out` (gate|up, the backward's input) the tile's silu(gate)*up goes to tmap_out2
+                        // 2: rotary position embedding (head_dim 128, HF rotate_half) on output columns < rope_cols
+  const float* rope_cos; const float* rope_sin;   // fuse == 2: fp32 [rope_L, 64]; the position of output row m is m % rope_L
+  int rope_L, rope_cols;
 };
 
 // Tile rasterisation. Persistent CTA i works on tiles i, i + grid, ...: the tiles resident at one moment are ~148 consecutive
@@ -123,8 +128,9 @@ constexpr int kStageTileBytes = 128 * 128;
 constexpr int kEpiGroups = 2;                                   // two groups of 4 epilogue warps split a tile's store blocks
 constexpr int kGemmThreads = 128 + kEpiGroups * 128;            // warps 0-3: TMA / MMA / TMEM alloc / spare ; warps 4-11: epilogue
 template <int BN>
-__device__ __forceinline__ void epilogue_drain_tile(const GemmEpilogue& ep, const CUtensorMap* tmap_out, unsigned char* staging,
-                                                    int grp, uint32_t t_row, int row_in_tile, int tile_row0, int tile_col0) {
+__device__ __forceinline__ void epilogue_drain_tile(const GemmEpilogue& ep, const CUtensorMap* tmap_out, const CUtensorMap* tmap_out2,
+                                                    unsigned char* staging, int grp, uint32_t t_row, int row_in_tile, int tile_row0,
+                                                    int tile_col0) {
   const int N = ep.N;
   const int row = tile_row0 + row_in_tile;
   const bool row_ok = row < ep.M;
@@ -167,6 +173,37 @@ __device__ __forceinline__ void epilogue_drain_tile(const GemmEpilogue& ep, cons
 #pragma unroll
       for (int g = 0; g < 8; ++g)
         *reinterpret_cast<float4*>(st + ((g ^ sw) << 4)) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+    } else if (ep.fuse == 2 && col0 < ep.rope_cols) {
+      // RoPE in the QKV epilogue: this 64-column block is one rotate_half HALF of a head (x1 = columns 0..63, x2 = 64..127 of the
+      // head; tiles are 256 columns = two whole heads); its partner half sits 64 TMEM columns away in the same accumulator.
+      //   x1' = x1 cos - x2 sin ,  x2' = x2 cos + x1 sin        (cos / sin of the row's position, element j = column % 64)
+      // Replaces a separate in-place pass over the q|k columns of every layer's QKV output (32 x 34 us per cfg-3 step).
+      const bool second = ((col0 >> 6) & 1) != 0;               // this block holds x2
+      const int cp = second ? c - 64 : c + 64;
+      const int pos = row_ok ? (row % ep.rope_L) : 0;
+      const float* cs = ep.rope_cos + (size_t)pos * 64;
+      const float* sn = ep.rope_sin + (size_t)pos * 64;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t vo[32], vq[32]; float f[32];
+        tmem_ld_32x32(t_row + (uint32_t)(c + h * 32), vo);
+        tmem_ld_32x32(t_row + (uint32_t)(cp + h * 32), vq);
+        float cc[32], ss[32];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          *reinterpret_cast<float4*>(cc + i) = __ldg(reinterpret_cast<const float4*>(cs + h * 32 + i));
+          *reinterpret_cast<float4*>(ss + i) = __ldg(reinterpret_cast<const float4*>(sn + h * 32 + i));
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float own = __uint_as_float(vo[i]), oth = __uint_as_float(vq[i]);
+          f[i] = second ? fmaf(own, cc[i], oth * ss[i]) : fmaf(own, cc[i], -oth * ss[i]);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<bf16x8*>(st + (((h * 4 + g) ^ sw) << 4)) = pack8(f + g * 8);
+      }
     } else {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -186,6 +223,37 @@ __device__ __forceinline__ void epilogue_drain_tile(const GemmEpilogue& ep, cons
     if (issuer) {
       tma_store_2d(tmap_out, tile, col0, tile_row0);
       bulk_commit();
+    }
+  }
+  if constexpr (BN == 256) {
+    if (ep.fuse == 1) {
+      // SwiGLU forward: act[:, 128 n_blk + 64 j + ...] = silu(gate) * up from the fp32 accumulators (gate columns 64j.., up columns
+      // 128 + 64j..): two more 128-byte-wide store blocks per tile, one per epilogue group. Replaces a separate pass that re-read
+      // the 203 MB gate|up buffer (32 x 51 us per cfg-3 step).
+      const int j = grp;
+      const int acol0 = (tile_col0 >> 1) + j * 64;              // column of the [M, N/2] activation matrix
+      if (issuer) bulk_wait_read<0>();
+      named_bar_sync(1 + grp, 128);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t vg[32], vu[32]; float f[32];
+        tmem_ld_32x32(t_row + (uint32_t)(j * 64 + h * 32), vg);
+        tmem_ld_32x32(t_row + (uint32_t)(128 + j * 64 + h * 32), vu);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float g = __uint_as_float(vg[i]);
+          f[i] = g / (1.f + __expf(-g)) * __uint_as_float(vu[i]);
+        }
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) *reinterpret_cast<bf16x8*>(st + (((h * 4 + g4) ^ sw) << 4)) = pack8(f + g4 * 8);
+      }
+      fence_proxy_async();
+      named_bar_sync(1 + grp, 128);
+      if (issuer) {
+        tma_store_2d(tmap_out2, tile, acol0, tile_row0);
+        bulk_commit();
+      }
     }
   }
 }
@@ -211,7 +279,7 @@ template <int BN> struct GemmCfg {
 template <int BN, int LAYOUT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_out, const GemmEpilogue ep) {
+                    const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2, const GemmEpilogue ep) {
   using Cfg = GemmCfg<BN>;
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
   extern __shared__ unsigned char smem_raw[];
@@ -320,7 +388,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_drain_tile<BN>(ep, &tmap_out, staging, grp, t_row, q * 32 + lane, m_blk * BM, n_blk * BN);
+      epilogue_drain_tile<BN>(ep, &tmap_out, &tmap_out2, staging, grp, t_row, q * 32 + lane, m_blk * BM, n_blk * BN);
       // all TMEM reads of this warp are complete (wait::ld): hand the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -453,7 +521,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_drain_tile<BN>(ep, &tmap_out, staging, grp, t_row, q * 32 + lane, m_blk * 2 * BM + (int)rank * BM, n_blk * BN);
+      epilogue_drain_tile<BN>(ep, &tmap_out, &tmap_out, staging, grp, t_row, q * 32 + lane, m_blk * 2 * BM + (int)rank * BM, n_blk * BN);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tempty_bar[acc], 0);   // leader's barrier
@@ -537,7 +605,7 @@ int get_tmap(const void* ptr, long long rows, long long cols, long long ld, int 
 
 template <int BN, int LAYOUT = 0>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmEpilogue& ep,
-                       int max_ctas, cudaStream_t stream) {
+                       int max_ctas, cudaStream_t stream, const CUtensorMap* to2 = nullptr) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -547,7 +615,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   const int num_tiles = ((ep.M + 127) / 128) * ((ep.N + BN - 1) / BN);
   int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  gemm_bf16_tn_kernel<BN, LAYOUT><<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, to, ep);
+  gemm_bf16_tn_kernel<BN, LAYOUT><<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, to, to2 ? *to2 : to, ep);
   count_launch();
   return check_launch("gemm_bf16_tn_kernel");
 }
@@ -661,7 +729,7 @@ extern "C" int dalm_b200_gemm_bf16(int layout, const void* A, long long lda, con
     if (group_m >= num_m && (g_group_m_override <= 0)) group_m = 0;   // one band == m-fastest
   }
   GemmEpilogue ep{out, ldo, out_f32, bias, resid, ldr, resid_f32, act, alpha, M, N, K,
-                  make_drop(drop_p, drop_seed, drop_stream_id, drop_offset), group_m};
+                  make_drop(drop_p, drop_seed, drop_stream_id, drop_offset), group_m, 0, nullptr, nullptr, 0, 0};
   cudaStream_t st = (cudaStream_t)stream;
   if (bn == 2256) return launch_gemm2<256>(ta, tb, to, ep, max_ctas, st);
   if (bn == 3256) return launch_gemm2<256, 3>(ta, tb, to, ep, max_ctas, st);     // tuning probes (fewer stages)
@@ -680,6 +748,59 @@ extern "C" int dalm_b200_gemm_bf16(int layout, const void* A, long long lda, con
   if (bn == 256) return launch_gemm<256>(ta, tb, to, ep, max_ctas, st);
   if (bn == 128) return launch_gemm<128>(ta, tb, to, ep, max_ctas, st);
   return launch_gemm<64>(ta, tb, to, ep, max_ctas, st);
+}
+
+// gate|up projection of LlamaMLP with SiLU(gate) * up fused into the epilogue (see include/dalm_b200.h)
+extern "C" int dalm_b200_gemm_bf16_swiglu(const void* A, long long lda, const void* B, long long ldb, void* gu, long long ldgu,
+                                          void* act, long long ldact, int M, int N, int K, void* stream) {
+  DALM_REQUIRE(M > 0 && K > 0 && N >= 256 && (N % 256) == 0, "gemm_swiglu: N=%d must be a positive multiple of 256 (128-feature gate / up blocks)", N);
+  DALM_REQUIRE((K % 8) == 0 && lda >= K && ldb >= K && ldgu >= N && ldact >= N / 2, "gemm_swiglu: bad K / leading dimensions");
+  DALM_REQUIRE((ldgu % 8) == 0 && (ldact % 8) == 0 && ((uintptr_t)gu & 15) == 0 && ((uintptr_t)act & 15) == 0, "gemm_swiglu: output alignment");
+  CUtensorMap ta, tb, to, to2;
+  if (int e = get_tmap(A, M, K, lda, 128, &ta)) return e;
+  if (int e = get_tmap(B, N, K, ldb, 256, &tb)) return e;
+  if (int e = get_tmap(gu, M, N, ldgu, 128, &to, 0)) return e;
+  if (int e = get_tmap(act, M, N / 2, ldact, 128, &to2, 0)) return e;
+  int group_m = 0;
+  {
+    const int num_m = (M + 127) / 128, num_n = N / 256;
+    if (g_group_m_override > 0) group_m = g_group_m_override;
+    else if (g_group_m_override == 0 && (long long)num_m * num_n > kNumSMs) {
+      int nbands = (int)(num_m / sqrt((double)kNumSMs * 2.0) + 0.5);
+      if (nbands < 1) nbands = 1;
+      group_m = (num_m + nbands - 1) / nbands;
+    }
+    if (group_m >= num_m && g_group_m_override <= 0) group_m = 0;
+  }
+  GemmEpilogue ep{gu, ldgu, 0, nullptr, nullptr, 0, 0, 0, 1.f, M, N, K, make_drop(0.f, 0, 0, nullptr), group_m, 1, nullptr, nullptr, 0, 0};
+  return launch_gemm<256>(ta, tb, to, ep, 0, (cudaStream_t)stream, &to2);
+}
+
+// fused q|k|v projection + rotary embedding: out[M,N] = A[M,K] B[N,K]^T with HF's rotate_half RoPE (head_dim 128) applied to the
+// output columns [0, rope_cols) in the epilogue. cos / sin: fp32 [L, 64]; row m sits at position m % L (token-major [B*L] rows).
+extern "C" int dalm_b200_gemm_bf16_rope(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo, int M,
+                                        int N, int K, const float* cos_t, const float* sin_t, int L, int rope_cols, void* stream) {
+  DALM_REQUIRE(M > 0 && N > 0 && K > 0 && (N % 8) == 0 && (K % 8) == 0, "gemm_rope: bad shape M=%d N=%d K=%d", M, N, K);
+  DALM_REQUIRE(rope_cols > 0 && rope_cols <= N && (rope_cols % 256) == 0, "gemm_rope: rope_cols=%d must be a multiple of 256 (whole 128-wide heads per tile)", rope_cols);
+  DALM_REQUIRE(L > 0 && cos_t != nullptr && sin_t != nullptr && ((uintptr_t)cos_t & 15) == 0 && ((uintptr_t)sin_t & 15) == 0, "gemm_rope: cos / sin tables");
+  DALM_REQUIRE(lda >= K && ldb >= K && ldo >= N && (ldo % 8) == 0 && ((uintptr_t)out & 15) == 0, "gemm_rope: leading dimensions / alignment");
+  CUtensorMap ta, tb, to;
+  if (int e = get_tmap(A, M, K, lda, 128, &ta)) return e;
+  if (int e = get_tmap(B, N, K, ldb, 256, &tb)) return e;
+  if (int e = get_tmap(out, M, N, ldo, 128, &to, 0)) return e;
+  int group_m = 0;
+  {
+    const int num_m = (M + 127) / 128, num_n = (N + 255) / 256;
+    if (g_group_m_override > 0) group_m = g_group_m_override;
+    else if (g_group_m_override == 0 && (long long)num_m * num_n > kNumSMs) {
+      int nbands = (int)(num_m / sqrt((double)kNumSMs * 2.0) + 0.5);
+      if (nbands < 1) nbands = 1;
+      group_m = (num_m + nbands - 1) / nbands;
+    }
+    if (group_m >= num_m && g_group_m_override <= 0) group_m = 0;
+  }
+  GemmEpilogue ep{out, ldo, 0, nullptr, nullptr, 0, 0, 0, 1.f, M, N, K, make_drop(0.f, 0, 0, nullptr), group_m, 2, cos_t, sin_t, L, rope_cols};
+  return launch_gemm<256>(ta, tb, to, ep, 0, (cudaStream_t)stream);
 }
 
 // drop cached tensor maps (call when operand buffers are freed / re-allocated at the same address with other shapes)

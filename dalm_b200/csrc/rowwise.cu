@@ -321,27 +321,39 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ buf, long long ld, int c
 // ------------------------------------------------------------------------------------------------------------
 // SwiGLU: gu = [gate | up] (bf16 [M,2F]);  act = silu(gate) * up
 // ------------------------------------------------------------------------------------------------------------
+// gate / up column of feature i inside a [M, 2F] gate|up buffer: il == 0: [gate 0..F | up 0..F] (HF order); il > 0: blocks of il
+// features interleaved [gate blk | up blk | gate blk+1 | ...] - the layout that puts a feature's gate AND up accumulator in the
+// same 128 x 256 GEMM tile (gemm_tcgen05.cu: SwiGLU epilogue)
+__device__ __forceinline__ int gate_col(int i, int F, int il, int& up_off) {
+  if (il == 0) { up_off = F; return i; }
+  up_off = il;
+  return (i / il) * 2 * il + (i % il);
+}
 __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gu, long long ldgu, __nv_bfloat16* __restrict__ act,
-                                  long long lda, int F) {
+                                  long long lda, int F, int il) {
   const size_t r = blockIdx.y;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= F) return;
   float g[8], u[8], o[8];
-  unpack8(*reinterpret_cast<const bf16x8*>(gu + r * ldgu + i), g);
-  unpack8(*reinterpret_cast<const bf16x8*>(gu + r * ldgu + F + i), u);
+  int uo;
+  const int gc = gate_col(i, F, il, uo);
+  unpack8(*reinterpret_cast<const bf16x8*>(gu + r * ldgu + gc), g);
+  unpack8(*reinterpret_cast<const bf16x8*>(gu + r * ldgu + gc + uo), u);
 #pragma unroll
   for (int k = 0; k < 8; ++k) o[k] = g[k] / (1.f + __expf(-g[k])) * u[k];
   *reinterpret_cast<bf16x8*>(act + r * lda + i) = pack8(o);
 }
 // in place: gu <- [dgate | dup]
 __global__ void swiglu_bwd_kernel(__nv_bfloat16* __restrict__ gu, long long ldgu, const __nv_bfloat16* __restrict__ dact,
-                                  long long ldd, int F) {
+                                  long long ldd, int F, int il) {
   const size_t r = blockIdx.y;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= F) return;
   float g[8], u[8], d[8], dg[8], du[8];
-  unpack8(*reinterpret_cast<const bf16x8*>(gu + r * ldgu + i), g);
-  unpack8(*reinterpret_cast<const bf16x8*>(gu + r * ldgu + F + i), u);
+  int uo;
+  const int gc = gate_col(i, F, il, uo);
+  unpack8(*reinterpret_cast<const bf16x8*>(gu + r * ldgu + gc), g);
+  unpack8(*reinterpret_cast<const bf16x8*>(gu + r * ldgu + gc + uo), u);
   unpack8(*reinterpret_cast<const bf16x8*>(dact + r * ldd + i), d);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -350,8 +362,8 @@ __global__ void swiglu_bwd_kernel(__nv_bfloat16* __restrict__ gu, long long ldgu
     dg[k] = d[k] * u[k] * sg * (1.f + g[k] * (1.f - sg));
     du[k] = d[k] * silu;
   }
-  *reinterpret_cast<bf16x8*>(gu + r * ldgu + i) = pack8(dg);
-  *reinterpret_cast<bf16x8*>(gu + r * ldgu + F + i) = pack8(du);
+  *reinterpret_cast<bf16x8*>(gu + r * ldgu + gc) = pack8(dg);
+  *reinterpret_cast<bf16x8*>(gu + r * ldgu + gc + uo) = pack8(du);
 }
 
 // GELU(erf) forward on a pre-activation buffer, and backward in place on the incoming gradient
@@ -674,17 +686,19 @@ extern "C" int dalm_b200_rope(void* buf, long long ld, int col0, int nheads, int
   count_launch();
   return check_launch("rope_kernel");
 }
-extern "C" int dalm_b200_swiglu_fwd(const void* gu, long long ldgu, void* act, long long lda, int M, int F, void* stream) {
+extern "C" int dalm_b200_swiglu_fwd(const void* gu, long long ldgu, void* act, long long lda, int M, int F, int interleave, void* stream) {
   DALM_REQUIRE((F % 8) == 0 && (ldgu % 8) == 0 && (lda % 8) == 0, "swiglu: F and strides must be multiples of 8");
+  DALM_REQUIRE(interleave == 0 || ((interleave % 8) == 0 && (F % interleave) == 0), "swiglu: interleave block must divide F and be a multiple of 8");
   dim3 grid((F / 8 + 255) / 256, M);
-  swiglu_fwd_kernel<<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)gu, ldgu, (__nv_bfloat16*)act, lda, F);
+  swiglu_fwd_kernel<<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)gu, ldgu, (__nv_bfloat16*)act, lda, F, interleave);
   count_launch();
   return check_launch("swiglu_fwd_kernel");
 }
-extern "C" int dalm_b200_swiglu_bwd(void* gu, long long ldgu, const void* dact, long long ldd, int M, int F, void* stream) {
+extern "C" int dalm_b200_swiglu_bwd(void* gu, long long ldgu, const void* dact, long long ldd, int M, int F, int interleave, void* stream) {
   DALM_REQUIRE((F % 8) == 0 && (ldgu % 8) == 0 && (ldd % 8) == 0, "swiglu: F and strides must be multiples of 8");
+  DALM_REQUIRE(interleave == 0 || ((interleave % 8) == 0 && (F % interleave) == 0), "swiglu: interleave block must divide F and be a multiple of 8");
   dim3 grid((F / 8 + 255) / 256, M);
-  swiglu_bwd_kernel<<<grid, 256, 0, ST(stream)>>>((__nv_bfloat16*)gu, ldgu, (const __nv_bfloat16*)dact, ldd, F);
+  swiglu_bwd_kernel<<<grid, 256, 0, ST(stream)>>>((__nv_bfloat16*)gu, ldgu, (const __nv_bfloat16*)dact, ldd, F, interleave);
   count_launch();
   return check_launch("swiglu_bwd_kernel");
 }

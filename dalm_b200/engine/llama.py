@@ -13,6 +13,7 @@ Residual stream and its gradient are fp32; every GEMM operand is bf16.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -69,6 +70,10 @@ class LlamaDecoder(torch.nn.Module):
         self.Vp = (self.V + 7) // 8 * 8                       # GEMM N granularity; extra rows are zero and never scored
         self.full: Optional[DenseBank] = None
         self.layers: List[Dict[str, torch.Tensor]] = []
+        # frozen-base modes keep the fused gate|up weight in the interleaved layout of the SwiGLU-epilogue GEMM (F % 128 == 0);
+        # a fully fine-tuned model keeps HF's [gate; up] order inside its parameter bank (un-fused activation kernel)
+        self.fuse_rope = self.hd == 128 and os.environ.get("DALM_B200_FUSE_ROPE", "1") != "0"
+        self.gu_il = 128 if (not full and F % 128 == 0 and os.environ.get("DALM_B200_FUSE_SWIGLU", "1") != "0") else 0
         if full:
             self._init_full(sd)
         else:
@@ -232,7 +237,10 @@ class LlamaDecoder(torch.nn.Module):
                 W["Bblk"] = torch.zeros(64, self.Nqkv, dtype=bf16, device=self.dev)
             W["Wo"] = g(p + "self_attn.o_proj.weight", bf16)
             W["WoT"] = W["Wo"].t().contiguous()
-            W["Wgu"] = torch.cat([g(p + "mlp.gate_proj.weight", bf16), g(p + "mlp.up_proj.weight", bf16)], 0)
+            if self.gu_il:     # gate / up rows interleaved in 128-feature blocks: SiLU(gate)*up is fused into this GEMM's epilogue
+                W["Wgu"] = ops.interleave_gate_up(g(p + "mlp.gate_proj.weight", bf16), g(p + "mlp.up_proj.weight", bf16), self.gu_il)
+            else:
+                W["Wgu"] = torch.cat([g(p + "mlp.gate_proj.weight", bf16), g(p + "mlp.up_proj.weight", bf16)], 0)
             W["WguT"] = W["Wgu"].t().contiguous()
             W["Wd"] = g(p + "mlp.down_proj.weight", bf16)
             W["WdT"] = W["Wd"].t().contiguous()
@@ -323,9 +331,15 @@ class LlamaDecoder(torch.nn.Module):
             if Ra:
                 ops.skinny_gemm(a.h1_aug[:, :H], W["A_stack"], a.h1_aug[:, H:], K=H, R=Ra,   # u = dropout(h1) A^T [M,2r]
                                 dropx=self._drop(ctx.training, ctx.call, li))
-            a.qkv = ops.gemm(a.h1_aug, W["Wqkv_aug"])                            # [M, Nq+2Nkv]
-            if pos is None:
+            rope_cols = (self.nh + self.nkv) * self.hd
+            if pos is None and self.fuse_rope and rope_cols % 256 == 0:
+                a.qkv = ops.gemm_rope(a.h1_aug, W["Wqkv_aug"], cos_t, sin_t, L, rope_cols)     # QKV (+LoRA) with RoPE in the epilogue
+            else:
+                a.qkv = ops.gemm(a.h1_aug, W["Wqkv_aug"])                        # [M, Nq+2Nkv]
+            if pos is None and not (self.fuse_rope and rope_cols % 256 == 0):
                 ops.rope_(a.qkv, 0, self.nh + self.nkv, self.hd, cos_t, sin_t, L)    # q heads then k heads are adjacent
+            elif pos is None:
+                pass
             else:
                 ops.rope_pos_(a.qkv, 0, self.nh + self.nkv, self.hd, cos_t, sin_t, pos)
             if kv_sink is not None:
@@ -334,8 +348,11 @@ class LlamaDecoder(torch.nn.Module):
                                                   a.qkv[:, self.Nq + self.Nkv:], ctx.mask, B, L, self.nh, self.nkv, self.hd, causal=True)
             a.x_mid = ops.gemm(a.att, W["Wo"], out_dtype=f32, resid=x)
             a.h2, a.rstd2 = ops.rmsnorm_fwd(a.x_mid, W["g2"], self.eps)
-            a.gu = ops.gemm(a.h2, W["Wgu"])                                       # [M,2F]
-            a.act = ops.swiglu_fwd(a.gu, F)
+            if self.gu_il:
+                a.gu, a.act = ops.gemm_swiglu(a.h2, W["Wgu"])                     # [M,2F] (interleaved) + silu(gate)*up [M,F]: one launch
+            else:
+                a.gu = ops.gemm(a.h2, W["Wgu"])                                   # [M,2F]
+                a.act = ops.swiglu_fwd(a.gu, F)
             x = ops.gemm(a.act, W["Wd"], out_dtype=f32, resid=a.x_mid)
             if save:
                 ctx.layers.append(a)
@@ -363,7 +380,7 @@ class LlamaDecoder(torch.nn.Module):
                                        self.nh, self.nkv, self.hd)
             x_mid = ops.gemm_rows(att, W["Wo"], out_dtype=f32, resid=x)
             h2, _ = ops.rmsnorm_fwd(x_mid, W["g2"], self.eps)
-            act = ops.swiglu_fwd(ops.gemm_rows(h2, W["Wgu"]), F)
+            act = ops.swiglu_fwd(ops.gemm_rows(h2, W["Wgu"]), F, interleave=self.gu_il)
             x = ops.gemm_rows(act, W["Wd"], out_dtype=f32, resid=x_mid)
         hf, _ = ops.rmsnorm_fwd(x, self.norm_g, self.eps)
         return ops.gemm_rows(hf, self.lm_head)
@@ -424,7 +441,7 @@ class LlamaDecoder(torch.nn.Module):
             if bank is not None:
                 ops.wgrad_(dx16, a.act, G(l, "Wd"), acc)
             dact = self._dgrad(dx16, W, "Wd")                                      # [M,F]
-            ops.swiglu_bwd_(a.gu, dact, F)                                         # gu <- [dgate | dup]
+            ops.swiglu_bwd_(a.gu, dact, F, interleave=self.gu_il)                  # gu <- [dgate | dup] (same layout as gu)
             if bank is not None:
                 ops.wgrad_(a.gu, a.h2, G(l, "Wgu"), acc)
             dh2 = self._dgrad(a.gu, W, "Wgu")                                      # [M,H]

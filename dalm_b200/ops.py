@@ -385,17 +385,65 @@ def rope_(buf, col0: int, nheads: int, D: int, cos_t, sin_t, L: int, backward: b
     return buf
 
 
-def swiglu_fwd(gu, F: int, act=None):
+def swiglu_fwd(gu, F: int, act=None, interleave: int = 0):
     M = gu.shape[0]
     if act is None:
         act = torch.empty(M, F, dtype=bf16, device=gu.device)
-    _lib.call("dalm_b200_swiglu_fwd", _p(gu), _ld(gu), _p(act), _ld(act), M, F, _stream())
+    _lib.call("dalm_b200_swiglu_fwd", _p(gu), _ld(gu), _p(act), _ld(act), M, F, int(interleave), _stream())
     return act
 
 
-def swiglu_bwd_(gu, dact, F: int):
-    _lib.call("dalm_b200_swiglu_bwd", _p(gu), _ld(gu), _p(dact), _ld(dact), gu.shape[0], F, _stream())
+def swiglu_bwd_(gu, dact, F: int, interleave: int = 0):
+    _lib.call("dalm_b200_swiglu_bwd", _p(gu), _ld(gu), _p(dact), _ld(dact), gu.shape[0], F, int(interleave), _stream())
     return gu
+
+
+def gemm_swiglu(a: torch.Tensor, w_il: torch.Tensor, gu: Optional[torch.Tensor] = None, act: Optional[torch.Tensor] = None):
+    """LlamaMLP's gate|up projection with SiLU(gate) * up in the GEMM epilogue. w_il: [2F, K] bf16, gate / up rows interleaved in
+    blocks of 128 features (see `interleave_gate_up`). -> (gu [M,2F] interleaved bf16, act [M,F] bf16)"""
+    _chk(a, bf16, "gemm_swiglu a"); _chk(w_il, bf16, "gemm_swiglu w")
+    M, K = a.shape
+    N = w_il.shape[0]
+    if gu is None:
+        gu = torch.empty(M, N, dtype=bf16, device=a.device)
+    if act is None:
+        act = torch.empty(M, N // 2, dtype=bf16, device=a.device)
+    timer = GEMM_TIMER
+    if timer is not None:
+        timer.begin(2.0 * M * N * K, (M, N, K, 0, "bfloat16", "swiglu", "-"))
+    _lib.call("dalm_b200_gemm_bf16_swiglu", _p(a), _ld(a), _p(w_il), _ld(w_il), _p(gu), _ld(gu), _p(act), _ld(act), M, N, K, _stream())
+    if timer is not None:
+        timer.end()
+    return gu, act
+
+
+def gemm_rope(a: torch.Tensor, w: torch.Tensor, cos_t: torch.Tensor, sin_t: torch.Tensor, L: int, rope_cols: int,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q|k|v projection with RoPE (head_dim 128) on the first `rope_cols` output columns fused into the GEMM epilogue.
+    a [M,K], w [N,K] bf16; cos_t / sin_t fp32 [L, 64]; rows are token-major (position = row % L)."""
+    _chk(a, bf16, "gemm_rope a"); _chk(w, bf16, "gemm_rope w"); _chk(cos_t, f32, "gemm_rope cos"); _chk(sin_t, f32, "gemm_rope sin")
+    M, K = a.shape
+    N = w.shape[0]
+    if cos_t.shape != (L, 64) or sin_t.shape != (L, 64) or not cos_t.is_contiguous() or not sin_t.is_contiguous():
+        raise _lib.DalmB200Error("gemm_rope: cos / sin must be contiguous fp32 [L, 64] (head_dim 128)")
+    if out is None:
+        out = torch.empty(M, N, dtype=bf16, device=a.device)
+    timer = GEMM_TIMER
+    if timer is not None:
+        timer.begin(2.0 * M * N * K, (M, N, K, 0, "bfloat16", "rope", "-"))
+    _lib.call("dalm_b200_gemm_bf16_rope", _p(a), _ld(a), _p(w), _ld(w), _p(out), _ld(out), M, N, K, _p(cos_t), _p(sin_t), int(L),
+              int(rope_cols), _stream())
+    if timer is not None:
+        timer.end()
+    return out
+
+
+def interleave_gate_up(gate_w: torch.Tensor, up_w: torch.Tensor, block: int = 128) -> torch.Tensor:
+    """[F,K] gate and up weights -> [2F,K] with rows [gate blk0 | up blk0 | gate blk1 | ...] (blocks of `block` features)"""
+    F, K = gate_w.shape
+    if F % block:
+        raise _lib.DalmB200Error(f"interleave_gate_up: F={F} is not a multiple of {block}")
+    return torch.stack([gate_w.view(F // block, block, K), up_w.view(F // block, block, K)], dim=1).reshape(2 * F, K).contiguous()
 
 
 def gelu_fwd(pre, act=None):

@@ -78,6 +78,16 @@ int dalm_b200_gemm_bf16(int layout, const void* A, long long lda, const void* B,
                         int out_f32, int M, int N, int K, float alpha, const float* bias, int act, const void* resid,
                         long long ldr, int resid_f32, int block_n, int max_ctas, float drop_p, unsigned long long drop_seed,
                         unsigned long long drop_stream_id, const void* drop_offset, void* stream);
+/* LlamaMLP gate|up projection with SiLU(gate) * up fused into the epilogue: B = the gate / up weight rows interleaved in blocks of
+ * 128 features ([gate blk | up blk | ...], N = 2F rows), so one 128 x 256 accumulator tile holds both halves of 128 features.
+ * Writes gu[M, N] (interleaved, bf16: the backward's input) AND act[M, N/2] = silu(gate) * up (bf16). N % 256 == 0. Replaces
+ * gate_proj / up_proj / act_fn of HF LlamaMLP reached through dalm/models/rag_e2e_base_model.py:105. */
+int dalm_b200_gemm_bf16_swiglu(const void* A, long long lda, const void* B, long long ldb, void* gu, long long ldgu, void* act,
+                               long long ldact, int M, int N, int K, void* stream);
+/* fused q|k|v projection + rotary position embedding (HF rotate_half, head_dim 128) on output columns [0, rope_cols); cos / sin
+ * fp32 [L, 64]; output row m is at position m % L. Replaces q_proj / k_proj / v_proj + apply_rotary_pos_emb of HF LlamaAttention. */
+int dalm_b200_gemm_bf16_rope(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo, int M, int N,
+                             int K, const float* cos_t, const float* sin_t, int L, int rope_cols, void* stream);
 void dalm_b200_gemm_clear_cache(void);
 /* tile rasterisation of the persistent GEMM (tuning / test hook): -1 = m-fastest order, 0 = automatic band height
  * (default: ~square wave footprint, serpentine inside a band), > 0 = bands of that many 128-row m-tiles */
@@ -140,8 +150,10 @@ int dalm_b200_bert_embed(const int64_t* ids, const void* word, const void* pos, 
 int dalm_b200_embed_gather(const int64_t* ids, const void* table, float* x, int M, int H, int V, void* stream);
 int dalm_b200_rope(void* buf, long long ld, int col0, int nheads, int D, const float* cos_t, const float* sin_t, int M,
                    int L, int backward, void* stream);
-int dalm_b200_swiglu_fwd(const void* gu, long long ldgu, void* act, long long lda, int M, int F, void* stream);
-int dalm_b200_swiglu_bwd(void* gu, long long ldgu, const void* dact, long long ldd, int M, int F, void* stream);
+/* gu = [gate | up] of LlamaMLP. interleave == 0: columns [gate 0..F | up 0..F] (HF order); interleave == k: blocks of k features
+ * alternate [gate blk | up blk | ...] (the layout dalm_b200_gemm_bf16_swiglu produces) */
+int dalm_b200_swiglu_fwd(const void* gu, long long ldgu, void* act, long long lda, int M, int F, int interleave, void* stream);
+int dalm_b200_swiglu_bwd(void* gu, long long ldgu, const void* dact, long long ldd, int M, int F, int interleave, void* stream);
 int dalm_b200_gelu_fwd(const void* pre, long long ldp, void* act, long long lda, int M, int F, void* stream);
 int dalm_b200_gelu_bwd(const void* pre, long long ldp, void* dact, long long ldd, int M, int F, void* stream);
 /* mean_pooling + F.normalize (rag_e2e_base_model.py:96-97,108-111; retriever_only_base_model.py:60-68) */

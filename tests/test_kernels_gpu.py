@@ -343,3 +343,65 @@ def test_gemm_rasterisation_orders_give_identical_results(cuda_dev, M, N, K, kin
         acc = resid.clone()
         ops.gemm(a, b, out=acc, resid=acc)
         assert torch.equal(acc, outs[0])
+
+
+@pytest.mark.parametrize("M,F,K", [(300, 256, 192), (4608, 1408, 512), (1000, 11008, 264), (130, 128, 72)])
+def test_gemm_with_fused_swiglu_epilogue(cuda_dev, M, F, K):
+    """gate|up projection + SiLU(gate)*up in one launch (interleaved 128-feature blocks) == separate GEMM + activation; the
+    interleaved gate|up buffer it leaves behind feeds the (interleave-aware) SwiGLU backward"""
+    from dalm_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M + F + K)
+    x = torch.randn(M, K + 8, generator=g).to(cuda_dev, torch.bfloat16)[:, :K]          # strided view, like an augmented buffer
+    wg = (torch.randn(F, K, generator=g) * 0.2).to(cuda_dev, torch.bfloat16)
+    wu = (torch.randn(F, K, generator=g) * 0.2).to(cuda_dev, torch.bfloat16)
+    w_il = ops.interleave_gate_up(wg, wu, 128)
+    gu, act = ops.gemm_swiglu(x, w_il)
+    gate = x.float() @ wg.float().t()
+    up = x.float() @ wu.float().t()
+    want = torch.nn.functional.silu(gate) * up
+    assert ((act.float() - want).norm() / want.norm()).item() < 5e-3
+    # the gate|up output is the plain GEMM result in the interleaved layout
+    gu_ref = ops.gemm(x, w_il)
+    assert torch.equal(gu, gu_ref)
+    blk = gu.float().view(M, F // 128, 2, 128)
+    assert ((blk[:, :, 0].reshape(M, F) - gate).norm() / gate.norm()).item() < 5e-3
+    assert ((blk[:, :, 1].reshape(M, F) - up).norm() / up.norm()).item() < 5e-3
+    # activation kernels on the interleaved layout == on HF's [gate | up] layout
+    gu_hf = torch.cat([blk[:, :, 0].reshape(M, F), blk[:, :, 1].reshape(M, F)], 1).to(torch.bfloat16).contiguous()
+    assert torch.equal(ops.swiglu_fwd(gu, F, interleave=128), ops.swiglu_fwd(gu_hf, F))
+    dact = torch.randn(M, F, generator=g).to(cuda_dev, torch.bfloat16)
+    d_il = ops.swiglu_bwd_(gu.clone(), dact, F, interleave=128).float().view(M, F // 128, 2, 128)
+    d_hf = ops.swiglu_bwd_(gu_hf.clone(), dact, F).float()
+    assert torch.equal(d_il[:, :, 0].reshape(M, F), d_hf[:, :F]) and torch.equal(d_il[:, :, 1].reshape(M, F), d_hf[:, F:])
+
+
+@pytest.mark.parametrize("B,L,nh,nkv,K", [(2, 24, 2, 2, 136), (18, 256, 4, 4, 264), (3, 150, 6, 2, 72)])
+def test_gemm_with_fused_rope_epilogue(cuda_dev, B, L, nh, nkv, K):
+    """q|k|v projection with RoPE (head_dim 128) in the GEMM epilogue == plain GEMM followed by the in-place rope kernel"""
+    from dalm_b200 import ops
+    D = 128
+    g = torch.Generator(device="cpu").manual_seed(B * L + K)
+    M, N = B * L, (nh + 2 * nkv) * D
+    x = torch.randn(M, K, generator=g).to(cuda_dev, torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * 0.2).to(cuda_dev, torch.bfloat16)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, D, 2, dtype=torch.float32) / D))
+    fr = torch.outer(torch.arange(L, dtype=torch.float32), inv)
+    cos_t, sin_t = fr.cos().to(cuda_dev).contiguous(), fr.sin().to(cuda_dev).contiguous()
+    rope_cols = (nh + nkv) * D
+    if rope_cols % 256:
+        with pytest.raises(Exception):
+            ops.gemm_rope(x, w, cos_t, sin_t, L, rope_cols)
+        return
+    fused = ops.gemm_rope(x, w, cos_t, sin_t, L, rope_cols)
+    # fp32 reference: rotate_half on the un-rounded projection
+    y = (x.float() @ w.float().t()).view(B, L, nh + 2 * nkv, D)
+    x1, x2 = y[..., :D // 2], y[..., D // 2:]
+    c, s_ = cos_t.view(1, L, 1, D // 2), sin_t.view(1, L, 1, D // 2)
+    rot = torch.cat([x1 * c - x2 * s_, x2 * c + x1 * s_], -1)
+    want = torch.cat([rot[:, :, :nh + nkv], y[:, :, nh + nkv:]], 2).reshape(M, N)
+    assert ((fused.float() - want).norm() / want.norm()).item() < 5e-3
+    # and against the two-launch path (which rounds to bf16 before rotating)
+    plain = ops.gemm(x, w)
+    ops.rope_(plain, 0, nh + nkv, D, cos_t, sin_t, L)
+    assert ((fused.float() - plain.float()).norm() / plain.float().norm()).item() < 6e-3
+    assert torch.equal(fused[:, rope_cols:], ops.gemm(x, w)[:, rope_cols:])          # v columns untouched
