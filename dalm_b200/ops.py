@@ -260,9 +260,17 @@ def attention_tc_fwd(q, k, v, mask, B: int, L: int, Hq: int, Hkv: int, D: int, c
     return out, lse
 
 
+_ATTN_MODE_SET = False
+
+
 def attention_tc_bwd(q, k, v, mask, out, lse, d_out, B: int, L: int, Hq: int, Hkv: int, D: int, causal: bool,
                      dq=None, dk=None, dv=None, scale: Optional[float] = None, drop: Optional[Drop] = None):
     """tcgen05/TMEM attention backward (head_dim 128 or 64). Same contract as attention_bwd."""
+    global _ATTN_MODE_SET
+    if not _ATTN_MODE_SET:                                     # A/B switch: DALM_B200_ATTN_BWD_PIPE=0 -> the one-chain-per-CTA kernels
+        _ATTN_MODE_SET = True
+        if os.environ.get("DALM_B200_ATTN_BWD_PIPE", "1") == "0":
+            _lib.load().dalm_b200_attention_tc_set_mode(0)
     dev = q.device
     if dq is None: dq = torch.empty(B * L, Hq * D, dtype=bf16, device=dev)
     if dk is None: dk = torch.empty(B * L, Hkv * D, dtype=bf16, device=dev)
