@@ -146,11 +146,11 @@ class GradientSync:
         # runs launch eagerly (a 230 ms step hides the launch cost).
         self.armed = True
         self.side = None
+        self.gemm_cap = 0
         if world > 1 and self.large and nccl:
-            from . import ops
             reserve = int(os.environ.get("NCCL_MAX_CTAS", "0") or 0)
-            if reserve > 0:                                    # leave NCCL's CTAs their SMs (see ops.GEMM_MAX_CTAS)
-                ops.GEMM_MAX_CTAS = max(148 - reserve, 64)
+            if reserve > 0:                                    # leave NCCL's CTAs their SMs (see ops.GEMM_MAX_CTAS): applied from the
+                self.gemm_cap = max(148 - reserve, 64)         # first bucket of a backward until the step's last collective is queued
         if world > 1 and self.large:
             if torch.cuda.is_available() and torch.device(device).type == "cuda":
                 self.side = torch.cuda.Stream(device=device)
@@ -166,6 +166,9 @@ class GradientSync:
     def _on_bucket(self, bank, lo: int, hi: int) -> None:
         if not self.armed or self.world == 1:
             return
+        if self.gemm_cap:
+            from . import ops
+            ops.GEMM_MAX_CTAS = self.gemm_cap                   # collectives are in flight from here on: the forward ran at full width
         if self.side is not None:
             self.side.wait_stream(torch.cuda.current_stream())     # the wgrads that produced [lo, hi) are ordered before it
             with torch.cuda.stream(self.side):
@@ -190,6 +193,9 @@ class GradientSync:
                 self._avg(b.grad[lo:hi])
             if hasattr(b, "reduced"):
                 b.reduced = []
+        if self.gemm_cap:
+            from . import ops
+            ops.GEMM_MAX_CTAS = 0
         if self.side is not None:
             torch.cuda.current_stream().wait_stream(self.side)      # bucket all-reduces must land before the optimizer
 

@@ -367,28 +367,200 @@ __global__ void swiglu_bwd_kernel(__nv_bfloat16* __restrict__ gu, long long ldgu
 }
 
 // GELU(erf) forward on a pre-activation buffer, and backward in place on the incoming gradient
+// GELU forward / backward: each thread walks GELU_ROWS rows of one 8-column group with all of its 16-byte loads issued before
+// the first use (one row per thread left HBM at 0.45 / 0.56 of the measured peak: profiles/r02_hbm_kernels_ncu.txt)
+constexpr int GELU_ROWS = 4;
 __global__ void gelu_fwd_kernel(const __nv_bfloat16* __restrict__ pre, long long ldp, __nv_bfloat16* __restrict__ act,
-                                long long lda, int F) {
-  const size_t r = blockIdx.y;
+                                long long lda, int M, int F) {
+  const size_t r0 = (size_t)blockIdx.y * GELU_ROWS;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= F) return;
-  float x[8];
-  unpack8(*reinterpret_cast<const bf16x8*>(pre + r * ldp + i), x);
+  bf16x8 raw[GELU_ROWS];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) x[k] = gelu_erf(x[k]);
-  *reinterpret_cast<bf16x8*>(act + r * lda + i) = pack8(x);
+  for (int u = 0; u < GELU_ROWS; ++u)
+    if (r0 + u < (size_t)M) raw[u] = *reinterpret_cast<const bf16x8*>(pre + (r0 + u) * ldp + i);
+#pragma unroll
+  for (int u = 0; u < GELU_ROWS; ++u) {
+    if (r0 + u >= (size_t)M) break;
+    float x[8];
+    unpack8(raw[u], x);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = gelu_erf(x[k]);
+    *reinterpret_cast<bf16x8*>(act + (r0 + u) * lda + i) = pack8(x);
+  }
 }
 __global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, long long ldp, __nv_bfloat16* __restrict__ dact,
-                                long long ldd, int F) {
-  const size_t r = blockIdx.y;
+                                long long ldd, int M, int F) {
+  const size_t r0 = (size_t)blockIdx.y * GELU_ROWS;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= F) return;
-  float x[8], d[8];
-  unpack8(*reinterpret_cast<const bf16x8*>(pre + r * ldp + i), x);
-  unpack8(*reinterpret_cast<const bf16x8*>(dact + r * ldd + i), d);
+  bf16x8 rx[GELU_ROWS], rd[GELU_ROWS];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) d[k] *= gelu_erf_grad(x[k]);
-  *reinterpret_cast<bf16x8*>(dact + r * ldd + i) = pack8(d);
+  for (int u = 0; u < GELU_ROWS; ++u)
+    if (r0 + u < (size_t)M) {
+      rx[u] = *reinterpret_cast<const bf16x8*>(pre + (r0 + u) * ldp + i);
+      rd[u] = *reinterpret_cast<const bf16x8*>(dact + (r0 + u) * ldd + i);
+    }
+#pragma unroll
+  for (int u = 0; u < GELU_ROWS; ++u) {
+    if (r0 + u >= (size_t)M) break;
+    float x[8], d[8];
+    unpack8(rx[u], x);
+    unpack8(rd[u], d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k] *= gelu_erf_grad(x[k]);
+    *reinterpret_cast<bf16x8*>(dact + (r0 + u) * ldd + i) = pack8(d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LayerNorm, one WARP per row (H = 256 NV8, NV8 <= 8: bge-large's 1024). The CTA-per-row kernels above give a 1024-wide row to
+// 256 threads - one float4 each - and spend their time in two block-wide reductions: 0.39 (fwd) / 0.62 (bwd) of the measured
+// HBM peak at cfg-2 (profiles/r02_hbm_kernels_ncu.txt), 14 % of that step. Here a lane keeps its 8 NV8 elements in registers
+// (8 consecutive floats per 256-wide chunk: one Philox group per chunk when dropout is on), statistics by warp shuffles, no
+// shared memory, 8 rows per CTA.
+// ------------------------------------------------------------------------------------------------------------
+template <int NV8>
+__global__ void __launch_bounds__(256) layernorm_fwd_warp_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, float* __restrict__ y32,
+                                                                 __nv_bfloat16* __restrict__ y16, long long ld16,
+                                                                 float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                                 int M, float eps, DropCfg drop) {
+  constexpr int H = NV8 * 256;
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= M) return;
+  float v[NV8][8];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < NV8; ++c) {
+    const float4* p = reinterpret_cast<const float4*>(z + r * H + c * 256 + lane * 8);
+    const float4 a = p[0], b = p[1];
+    v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w; v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[c][j];
+  }
+  const float mean = warp_sum(s) / H;
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < NV8; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float d = v[c][j] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) / H + eps);
+  if (lane == 0) { mean_out[r] = mean; rstd_out[r] = rstd; }
+  const unsigned long long dstream = drop.p > 0.f ? drop_stream(drop) : 0ull;
+#pragma unroll
+  for (int c = 0; c < NV8; ++c) {
+    const int i0 = c * 256 + lane * 8;
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + i0), g1 = *reinterpret_cast<const float4*>(gamma + i0 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + i0), b1 = *reinterpret_cast<const float4*>(beta + i0 + 4);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean) * rstd * gg[j] + bb[j];
+    if (drop.p > 0.f) {
+      float sc[8];
+      drop_scale8(drop, dstream, (((unsigned long long)r * H) >> 3) + (unsigned long long)(i0 >> 3), sc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] *= sc[j];
+    }
+    if (y32) {
+      *reinterpret_cast<float4*>(y32 + r * H + i0) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(y32 + r * H + i0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+    *reinterpret_cast<bf16x8*>(y16 + r * ld16 + i0) = pack8(o);
+  }
+}
+
+template <int NV8>
+__global__ void __launch_bounds__(256) layernorm_bwd_warp_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                                 const float* __restrict__ dy_a, const __nv_bfloat16* __restrict__ dy_b,
+                                                                 long long ldb, float* dz32, __nv_bfloat16* __restrict__ dz16,
+                                                                 long long ld16, int M, DropCfg drop16, const float* dres) {
+  constexpr int H = NV8 * 256;
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= M) return;
+  const float mean = mean_in[r], rstd = rstd_in[r];
+  float g[NV8][8], zh[NV8][8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < NV8; ++c) {
+    const int i0 = c * 256 + lane * 8;
+    float dy[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (dy_a) {
+      const float4 a = *reinterpret_cast<const float4*>(dy_a + r * H + i0), b = *reinterpret_cast<const float4*>(dy_a + r * H + i0 + 4);
+      dy[0] = a.x; dy[1] = a.y; dy[2] = a.z; dy[3] = a.w; dy[4] = b.x; dy[5] = b.y; dy[6] = b.z; dy[7] = b.w;
+    }
+    if (dy_b) {
+      float t[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(dy_b + r * ldb + i0), t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dy[j] += t[j];
+    }
+    const float4 z0 = *reinterpret_cast<const float4*>(z + r * H + i0), z1 = *reinterpret_cast<const float4*>(z + r * H + i0 + 4);
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + i0), g1 = *reinterpret_cast<const float4*>(gamma + i0 + 4);
+    const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      g[c][j] = dy[j] * gg[j];
+      zh[c][j] = (zz[j] - mean) * rstd;
+      s1 += g[c][j];
+      s2 += g[c][j] * zh[c][j];
+    }
+  }
+  s1 = warp_sum(s1) / H;
+  s2 = warp_sum(s2) / H;
+  const unsigned long long dstream = drop16.p > 0.f ? drop_stream(drop16) : 0ull;
+#pragma unroll
+  for (int c = 0; c < NV8; ++c) {
+    const int i0 = c * 256 + lane * 8;
+    float d[8], dm[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = rstd * (g[c][j] - s1 - zh[c][j] * s2);
+    if (dres) {                                                // residual around the norm (pre-LN blocks): added to both outputs
+      const float4 a = *reinterpret_cast<const float4*>(dres + r * H + i0), b = *reinterpret_cast<const float4*>(dres + r * H + i0 + 4);
+      d[0] += a.x; d[1] += a.y; d[2] += a.z; d[3] += a.w; d[4] += b.x; d[5] += b.y; d[6] += b.z; d[7] += b.w;
+    }
+    if (drop16.p > 0.f) {                                      // z = dropout(dense_out) + residual: the dense branch gets mask*dz/(1-p)
+      float sc[8];
+      drop_scale8(drop16, dstream, (((unsigned long long)r * H) >> 3) + (unsigned long long)(i0 >> 3), sc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dm[j] = d[j] * sc[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dm[j] = d[j];
+    }
+    if (dz32) {
+      *reinterpret_cast<float4*>(dz32 + r * H + i0) = make_float4(d[0], d[1], d[2], d[3]);
+      *reinterpret_cast<float4*>(dz32 + r * H + i0 + 4) = make_float4(d[4], d[5], d[6], d[7]);
+    }
+    if (dz16) *reinterpret_cast<bf16x8*>(dz16 + r * ld16 + i0) = pack8(dm);
+  }
+}
+
+template <int NV8>
+static int launch_ln_fwd_warp(const float* z, const float* gamma, const float* beta, float* y32, __nv_bfloat16* y16, long long ld16,
+                              float* mean, float* rstd, int M, float eps, const DropCfg& d, cudaStream_t st) {
+  layernorm_fwd_warp_kernel<NV8><<<(M + 7) / 8, 256, 0, st>>>(z, gamma, beta, y32, y16, ld16, mean, rstd, M, eps, d);
+  count_launch();
+  return check_launch("layernorm_fwd_warp_kernel");
+}
+template <int NV8>
+static int launch_ln_bwd_warp(const float* z, const float* gamma, const float* mean, const float* rstd, const float* dy_a,
+                              const __nv_bfloat16* dy_b, long long ldb, float* dz32, __nv_bfloat16* dz16, long long ld16, int M,
+                              const DropCfg& d, const float* dres, cudaStream_t st) {
+  layernorm_bwd_warp_kernel<NV8><<<(M + 7) / 8, 256, 0, st>>>(z, gamma, mean, rstd, dy_a, dy_b, ldb, dz32, dz16, ld16, M, d, dres);
+  count_launch();
+  return check_launch("layernorm_bwd_warp_kernel");
+}
+// the warp-per-row kernels serve H in {256, 512, 1024, 2048} with 16-byte aligned rows
+static bool ln_warp_ok(int H, long long ld16, const void* a, const void* b, const void* c, long long ldb) {
+  auto al = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return (H == 256 || H == 512 || H == 1024 || H == 2048) && (ld16 % 8) == 0 && (ldb % 8) == 0 && al(a) && al(b) && al(c);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -620,6 +792,16 @@ extern "C" int dalm_b200_layernorm_fwd(const float* z, const float* gamma, const
                                        const void* drop_offset, void* stream) {
   DALM_REQUIRE(M > 0 && H > 0 && H * 4 <= 64 * 1024, "layernorm_fwd: bad shape M=%d H=%d", M, H);
   DALM_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "layernorm_fwd: dropout p must be in [0,1)");
+  if (y16 != nullptr && ln_warp_ok(H, ld16, z, y32, y16, 0)) {
+    const DropCfg d = make_drop(drop_p, drop_seed, drop_stream_id, drop_offset);
+    auto* y = (__nv_bfloat16*)y16;
+    switch (H / 256) {
+      case 1: return launch_ln_fwd_warp<1>(z, gamma, beta, y32, y, ld16, mean, rstd, M, eps, d, ST(stream));
+      case 2: return launch_ln_fwd_warp<2>(z, gamma, beta, y32, y, ld16, mean, rstd, M, eps, d, ST(stream));
+      case 4: return launch_ln_fwd_warp<4>(z, gamma, beta, y32, y, ld16, mean, rstd, M, eps, d, ST(stream));
+      default: return launch_ln_fwd_warp<8>(z, gamma, beta, y32, y, ld16, mean, rstd, M, eps, d, ST(stream));
+    }
+  }
   layernorm_fwd_kernel<<<M, 256, H * sizeof(float), ST(stream)>>>(z, gamma, beta, y32, (__nv_bfloat16*)y16, ld16, mean, rstd, H, eps,
                                                                   make_drop(drop_p, drop_seed, drop_stream_id, drop_offset));
   count_launch();
@@ -631,6 +813,16 @@ extern "C" int dalm_b200_layernorm_bwd(const float* z, const float* gamma, const
                                        unsigned long long drop_stream_id, const void* drop_offset, void* stream) {
   DALM_REQUIRE(M > 0 && H > 0 && H * 8 <= 48 * 1024, "layernorm_bwd: bad shape M=%d H=%d", M, H);
   DALM_REQUIRE(dy_f32 || dy_bf16, "layernorm_bwd: no incoming gradient");
+  if (ln_warp_ok(H, dz16 ? ld16 : 0, z, dy_f32, dz32, dy_bf16 ? ldb : 0) && ((uintptr_t)dy_bf16 & 15) == 0 && ((uintptr_t)dz16 & 15) == 0) {
+    const DropCfg d = make_drop(drop_p, drop_seed, drop_stream_id, drop_offset);
+    auto* b = (const __nv_bfloat16*)dy_bf16; auto* o = (__nv_bfloat16*)dz16;
+    switch (H / 256) {
+      case 1: return launch_ln_bwd_warp<1>(z, gamma, mean, rstd, dy_f32, b, ldb, dz32, o, ld16, M, d, nullptr, ST(stream));
+      case 2: return launch_ln_bwd_warp<2>(z, gamma, mean, rstd, dy_f32, b, ldb, dz32, o, ld16, M, d, nullptr, ST(stream));
+      case 4: return launch_ln_bwd_warp<4>(z, gamma, mean, rstd, dy_f32, b, ldb, dz32, o, ld16, M, d, nullptr, ST(stream));
+      default: return launch_ln_bwd_warp<8>(z, gamma, mean, rstd, dy_f32, b, ldb, dz32, o, ld16, M, d, nullptr, ST(stream));
+    }
+  }
   layernorm_bwd_kernel<<<M, 256, 2 * H * sizeof(float), ST(stream)>>>(z, gamma, mean, rstd, dy_f32, (const __nv_bfloat16*)dy_bf16, ldb,
                                                                      dz32, (__nv_bfloat16*)dz16, ld16, H,
                                                                      make_drop(drop_p, drop_seed, drop_stream_id, drop_offset), nullptr);
@@ -643,6 +835,17 @@ extern "C" int dalm_b200_layernorm_bwd_res(const float* z, const float* gamma, c
                                            float* dz32, void* dz16, long long ld16, int M, int H, void* stream) {
   DALM_REQUIRE(M > 0 && H > 0 && H * 8 <= 48 * 1024, "layernorm_bwd_res: bad shape M=%d H=%d", M, H);
   DALM_REQUIRE(dy_f32 || dy_bf16, "layernorm_bwd_res: no incoming gradient");
+  if (ln_warp_ok(H, dz16 ? ld16 : 0, z, dy_f32, dz32, dy_bf16 ? ldb : 0) && ((uintptr_t)dy_bf16 & 15) == 0 && ((uintptr_t)dz16 & 15) == 0 &&
+      ((uintptr_t)dres & 15) == 0) {
+    const DropCfg d = make_drop(0.f, 0, 0, nullptr);
+    auto* b = (const __nv_bfloat16*)dy_bf16; auto* o = (__nv_bfloat16*)dz16;
+    switch (H / 256) {
+      case 1: return launch_ln_bwd_warp<1>(z, gamma, mean, rstd, dy_f32, b, ldb, dz32, o, ld16, M, d, dres, ST(stream));
+      case 2: return launch_ln_bwd_warp<2>(z, gamma, mean, rstd, dy_f32, b, ldb, dz32, o, ld16, M, d, dres, ST(stream));
+      case 4: return launch_ln_bwd_warp<4>(z, gamma, mean, rstd, dy_f32, b, ldb, dz32, o, ld16, M, d, dres, ST(stream));
+      default: return launch_ln_bwd_warp<8>(z, gamma, mean, rstd, dy_f32, b, ldb, dz32, o, ld16, M, d, dres, ST(stream));
+    }
+  }
   layernorm_bwd_kernel<<<M, 256, 2 * H * sizeof(float), ST(stream)>>>(z, gamma, mean, rstd, dy_f32, (const __nv_bfloat16*)dy_bf16, ldb,
                                                                      dz32, (__nv_bfloat16*)dz16, ld16, H, make_drop(0.f, 0, 0, nullptr), dres);
   count_launch();
@@ -704,15 +907,15 @@ extern "C" int dalm_b200_swiglu_bwd(void* gu, long long ldgu, const void* dact, 
 }
 extern "C" int dalm_b200_gelu_fwd(const void* pre, long long ldp, void* act, long long lda, int M, int F, void* stream) {
   DALM_REQUIRE((F % 8) == 0 && (ldp % 8) == 0 && (lda % 8) == 0, "gelu: F and strides must be multiples of 8");
-  dim3 grid((F / 8 + 255) / 256, M);
-  gelu_fwd_kernel<<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)pre, ldp, (__nv_bfloat16*)act, lda, F);
+  dim3 grid((F / 8 + 255) / 256, (M + GELU_ROWS - 1) / GELU_ROWS);
+  gelu_fwd_kernel<<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)pre, ldp, (__nv_bfloat16*)act, lda, M, F);
   count_launch();
   return check_launch("gelu_fwd_kernel");
 }
 extern "C" int dalm_b200_gelu_bwd(const void* pre, long long ldp, void* dact, long long ldd, int M, int F, void* stream) {
   DALM_REQUIRE((F % 8) == 0 && (ldp % 8) == 0 && (ldd % 8) == 0, "gelu: F and strides must be multiples of 8");
-  dim3 grid((F / 8 + 255) / 256, M);
-  gelu_bwd_kernel<<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)pre, ldp, (__nv_bfloat16*)dact, ldd, F);
+  dim3 grid((F / 8 + 255) / 256, (M + GELU_ROWS - 1) / GELU_ROWS);
+  gelu_bwd_kernel<<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)pre, ldp, (__nv_bfloat16*)dact, ldd, M, F);
   count_launch();
   return check_launch("gelu_bwd_kernel");
 }

@@ -52,17 +52,17 @@ def test_gemm_and_layernorm_sites_exact(cuda_dev):
     for bn in (64, 128, 2128):
         assert _rel(ops.gemm(a, b, out_dtype=f32, bias=bias, resid=res, drop=d, block_n=bn), ref) < 1e-5
     # layernorm: forward output dropout, backward bf16-branch mask
-    H = 256
-    z = torch.randn(M, H, device=dev); g = torch.randn(H, device=dev); be = torch.randn(H, device=dev)
-    d0 = ops.Drop(0.1, 99, 7, None)
-    y32, y16, mean, rstd = ops.layernorm_fwd(z, g, be, 1e-12, drop=d0)
-    m0 = ops.dropout_scale(M * H, d0, dev).view(M, H)
-    assert _rel(y32, torch.nn.functional.layer_norm(z, (H,), g, be, 1e-12) * m0) < 1e-5
-    dy = torch.randn(M, H, device=dev)
-    dz32, dz16 = ops.layernorm_bwd(z, g, mean, rstd, dy_f32=dy, drop16=d0)
-    dz32b, dz16b = ops.layernorm_bwd(z, g, mean, rstd, dy_f32=dy)
-    assert torch.equal(dz32, dz32b)                                # residual branch unmasked
-    assert _rel(dz16.float(), dz32 * m0) < 4e-3                    # dense branch = mask * dz / (1-p)
+    for H in (256, 1024, 384):                                     # warp-per-row kernels (256, 1024) and the CTA-per-row ones (384)
+        z = torch.randn(M, H, device=dev); g = torch.randn(H, device=dev); be = torch.randn(H, device=dev)
+        d0 = ops.Drop(0.1, 99, 7, None)
+        y32, y16, mean, rstd = ops.layernorm_fwd(z, g, be, 1e-12, drop=d0)
+        m0 = ops.dropout_scale(M * H, d0, dev).view(M, H)
+        assert _rel(y32, torch.nn.functional.layer_norm(z, (H,), g, be, 1e-12) * m0) < 1e-5
+        dy = torch.randn(M, H, device=dev)
+        dz32, dz16 = ops.layernorm_bwd(z, g, mean, rstd, dy_f32=dy, drop16=d0)
+        dz32b, dz16b = ops.layernorm_bwd(z, g, mean, rstd, dy_f32=dy)
+        assert torch.equal(dz32, dz32b)                                # residual branch unmasked
+        assert _rel(dz16.float(), dz32 * m0) < 4e-3                    # dense branch = mask * dz / (1-p)
 
 
 @pytest.mark.parametrize("B,L,H,D", [(2, 50, 4, 64), (3, 37, 2, 32)])

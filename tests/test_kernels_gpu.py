@@ -152,10 +152,11 @@ def test_attention_fwd_bwd(cuda_dev, B, L, Hq, Hkv, D, causal, pad):
 # ----------------------------------------------------------------------------------------------------------------
 # row-wise kernels
 # ----------------------------------------------------------------------------------------------------------------
-def test_layernorm_fwd_bwd(cuda_dev):
+@pytest.mark.parametrize("M,H", [(333, 1024), (26700, 1024), (77, 384), (130, 256), (9, 2048), (50, 4544)])
+def test_layernorm_fwd_bwd(cuda_dev, M, H):
+    """H in {256, 512, 1024, 2048} runs the warp-per-row kernels, other widths (bge-small 384, Falcon 4544) the CTA-per-row ones"""
     from dalm_b200 import ops
     torch.manual_seed(2)
-    M, H = 333, 1024
     z = torch.randn(M, H, device=cuda_dev) * 2 + 0.3
     g = torch.randn(H, device=cuda_dev); b = torch.randn(H, device=cuda_dev)
     y32, y16, mean, rstd = ops.layernorm_fwd(z, g, b, 1e-12)
@@ -169,6 +170,16 @@ def test_layernorm_fwd_bwd(cuda_dev):
     dz32, dz16 = ops.layernorm_bwd(z, g, mean, rstd, dy_f32=dy_a, dy_bf16=dy_b)
     assert _rel(dz32, zd.grad) < 1e-4
     assert _rel(dz16.float(), zd.grad) < 4e-3
+    # pre-LN form (Falcon): the residual's gradient is added to both outputs, in place
+    dres = torch.randn(M, H, device=cuda_dev)
+    want = zd.grad + dres.double()
+    dz32r, dz16r = ops.layernorm_bwd_res(z, g, mean, rstd, dy_b + dy_a.to(bf16) * 0, dres, dz32=dres)
+    ref2 = torch.nn.functional.layer_norm(zd.detach().requires_grad_(True), (H,), g.double(), b.double(), 1e-12)
+    # (dy_bf16-only variant: recompute the reference for that input)
+    zd2 = z.double().requires_grad_(True)
+    torch.nn.functional.layer_norm(zd2, (H,), g.double(), b.double(), 1e-12).backward(dy_b.double())
+    assert _rel(dz32r, zd2.grad + (want - zd.grad)) < 1e-4 and dz32r.data_ptr() == dres.data_ptr()
+    assert _rel(dz16r.float(), zd2.grad + (want - zd.grad)) < 4e-3
 
 
 def test_rmsnorm_fwd_bwd(cuda_dev):
