@@ -27,6 +27,7 @@ SIGNATURES = {
     "dalm_b200_marginal_counts": [_P, _P, _I, _I, _P, _P, _P],
     "dalm_b200_inbatch_loss_fwd_bwd": [_P, _P, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _F, _P],
     "dalm_b200_ce_marginal_fwd_bwd": [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _L, _F, _P],
+    "dalm_b200_ce_marginal_rows": [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _L, _F, _I, _I, _P],
     "dalm_b200_finalize_loss": [_P, _P, _I, _I, _P, _P, _P, _P],
     "dalm_b200_bump_counter": [_P, _P],
     "dalm_b200_dropout_scale": [_P, _L, _F, _U, _U, _P, _P],
@@ -36,6 +37,7 @@ SIGNATURES = {
     "dalm_b200_gemm_bf16": [_I, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _F, _P, _I, _P, _L, _I, _I, _I, *_DROP, _P],
     "dalm_b200_gemm_clear_cache": [],
     "dalm_b200_gemm_set_raster": [_I],
+    "dalm_b200_gemm_set_l2_hints": [_I],
     "dalm_b200_attention_fwd": [_P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _I, _I, _I, _I, _I, _F, _I, *_DROP, _P],
     "dalm_b200_attention_bwd": [_P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _P, _L, _P, _P, _L, _P, _L, _P, _L,
                                 _I, _I, _I, _I, _I, _F, _I, *_DROP, _P],
@@ -86,6 +88,7 @@ _RESTYPES = {
     "dalm_b200_reset_launch_count": None,
     "dalm_b200_gemm_clear_cache": None,
     "dalm_b200_gemm_set_raster": None,
+    "dalm_b200_gemm_set_l2_hints": None,
     "dalm_b200_attention_tc_set_debug": None,
     "dalm_b200_attention_tc_set_mode": None,
 }

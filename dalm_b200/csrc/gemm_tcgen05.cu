@@ -43,6 +43,8 @@ struct GemmEpilogue {
                         // 2: rotary position embedding (head_dim 128, HF rotate_half) on output columns < rope_cols
   const float* rope_cos; const float* rope_sin;   // fuse == 2: fp32 [rope_L, 64]; the position of output row m is m % rope_L
   int rope_L, rope_cols;
+  int l2_hints;         // TMA L2 eviction priorities: bit 0 = A loads evict_last (the panel the resident CTAs share across waves),
+                        // bit 1 = B loads evict_first (streamed once per band), bit 2 = output stores evict_first
 };
 
 // Tile rasterisation. Persistent CTA i works on tiles i, i + grid, ...: the tiles resident at one moment are ~148 consecutive
@@ -221,7 +223,8 @@ __device__ __forceinline__ void epilogue_drain_tile(const GemmEpilogue& ep, cons
     fence_proxy_async();                                        // generic-proxy smem writes -> visible to the TMA unit
     named_bar_sync(1 + grp, 128);
     if (issuer) {
-      tma_store_2d(tmap_out, tile, col0, tile_row0);
+      if (ep.l2_hints & 4) tma_store_2d_hint(tmap_out, tile, col0, tile_row0, l2_policy_evict_first());
+      else                 tma_store_2d(tmap_out, tile, col0, tile_row0);
       bulk_commit();
     }
   }
@@ -251,7 +254,8 @@ __device__ __forceinline__ void epilogue_drain_tile(const GemmEpilogue& ep, cons
       fence_proxy_async();
       named_bar_sync(1 + grp, 128);
       if (issuer) {
-        tma_store_2d(tmap_out2, tile, acol0, tile_row0);
+        if (ep.l2_hints & 4) tma_store_2d_hint(tmap_out2, tile, acol0, tile_row0, l2_policy_evict_first());
+        else                 tma_store_2d(tmap_out2, tile, acol0, tile_row0);
         bulk_commit();
       }
     }
@@ -321,6 +325,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // =============================== TMA producer ===============================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      const bool hint_a = (ep.l2_hints & 1) != 0, hint_b = (ep.l2_hints & 2) != 0;
+      const uint64_t pol_a = hint_a ? l2_policy_evict_last() : 0ull, pol_b = hint_b ? l2_policy_evict_first() : 0ull;
+      auto load = [](void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, bool hinted, uint64_t pol) {
+        if (hinted) tma_load_2d_hint(dst, tm, bar, c0, c1, pol);
+        else        tma_load_2d(dst, tm, bar, c0, c1);
+      };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m_blk, n_blk;
         tile_coords(tile, num_m, num_n, ep.group_m, m_blk, n_blk);
@@ -331,15 +341,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if constexpr (LAYOUT == 2) {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, &tmap_a, &full_bar[stage], m_blk * BM + c * 64, kb * BK);
+            for (int c = 0; c < BM / 64; ++c) load(sa + c * 8192, &tmap_a, &full_bar[stage], m_blk * BM + c * 64, kb * BK, hint_a, pol_a);
           } else {
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+            load(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM, hint_a, pol_a);
           }
           if constexpr (LAYOUT >= 1) {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmap_b, &full_bar[stage], n_blk * BN + c * 64, kb * BK);
+            for (int c = 0; c < BN / 64; ++c) load(sb + c * 8192, &tmap_b, &full_bar[stage], n_blk * BN + c * 64, kb * BK, hint_b, pol_b);
           } else {
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+            load(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN, hint_b, pol_b);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -647,9 +657,40 @@ extern "C" int dalm_b200_gemm_bf16(int layout, const void* A, long long lda, con
                                    int max_ctas, float drop_p, unsigned long long drop_seed,
                                    unsigned long long drop_stream_id, const void* drop_offset, void* stream);
 
-// tile rasterisation override: -1 = legacy m-fastest order, 0 = automatic band height (default), > 0 = that many m-tiles
-static int g_group_m_override = 0;
+// tile rasterisation override: -1 = m-fastest order everywhere, 0 = automatic (default: pick_group_m below), -2 = the round-2a rule
+// (bands for every multi-wave problem), > 0 = that many m-tiles per band. Initial value: env DALM_B200_GEMM_RASTER.
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+static int g_group_m_override = env_int("DALM_B200_GEMM_RASTER", 0);
 extern "C" void dalm_b200_gemm_set_raster(int group_m) { g_group_m_override = group_m; }
+// TMA L2 eviction hints (GemmEpilogue::l2_hints bit mask); initial value: env DALM_B200_GEMM_L2_HINTS
+static int g_l2_hints = env_int("DALM_B200_GEMM_L2_HINTS", 0);
+extern "C" void dalm_b200_gemm_set_l2_hints(int mask) { g_l2_hints = mask & 7; }
+
+// Band height of the tile rasterisation (0 = m-fastest). One wave = the kNumSMs tiles resident at a time.
+//  * m-fastest: a wave spans every m-tile of ~kNumSMs/num_m n-tiles, so all of A is touched by every wave. When A [M,K] is small
+//    enough to stay in L2 across waves (measured: 38 MB does, next to a bf16 output stream) DRAM sees A once and every B panel
+//    once - the algorithmic minimum (profiles/r01_gemm_v3: gate|up 447 MB vs 421, QKV 279 vs 252).
+//  * bands of g m-tiles walked serpentine in n: only the band's rows of A have to stay resident, B is streamed once per band:
+//    traffic ~ A + B * nbands. Wins when A does not fit (down-projection, K = 11008: 652 -> 559 MB) or when fp32 output + residual
+//    streams (150 MB at cfg-3) push A out of L2 anyway (o_proj: 276 -> 240 MB).
+// (profiles/r02_gemm_v4_ncu_full_raw.csv showed the cost of banding everything: B of gate|up / QKV read twice, 1.3x algorithmic.)
+static int pick_group_m(int M, int N, int K, int tile_n, bool stream_out) {
+  const int num_m = (M + 127) / 128, num_n = (N + tile_n - 1) / tile_n;
+  int group_m = 0;
+  if (g_group_m_override > 0) return g_group_m_override;
+  if (g_group_m_override == -1 || (long long)num_m * num_n <= kNumSMs) return 0;
+  const double a_bytes = 2.0 * M * K;
+  if (g_group_m_override == 0 && a_bytes <= 40e6 && !stream_out) return 0;
+  const double ideal = sqrt((double)kNumSMs * tile_n / 128.0);   // footprint of a wave ~square: min rows-of-A + rows-of-B
+  int nbands = (int)(num_m / ideal + 0.5);
+  if (nbands < 1) nbands = 1;
+  group_m = (num_m + nbands - 1) / nbands;                        // bands equalised over num_m
+  if (group_m >= num_m) group_m = 0;                              // one band == m-fastest
+  return group_m;
+}
 
 // D[M,N] = act(alpha * A[M,K] B[N,K]^T + bias) + resid
 //   A: bf16 [M,K] row stride lda;  B: bf16 [N,K] row stride ldb;  out: bf16|fp32 [M,N] row stride ldo
@@ -713,23 +754,9 @@ extern "C" int dalm_b200_gemm_bf16(int layout, const void* A, long long lda, con
   else             { if (int e = get_tmap(B, N, K, ldb, pair ? tile_n / 2 : tile_n, &tb)) return e; }
   if (int e = get_tmap(out, M, N, ldo, 128, &to, out_f32)) return e;
   DALM_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "gemm: dropout p must be in [0,1)");
-  // band height of the tile rasterisation: the footprint of one wave (kNumSMs tiles) is group_m x (kNumSMs / group_m) tiles;
-  // rows-of-A + rows-of-B of that footprint (= DRAM traffic per wave) is smallest for group_m = sqrt(kNumSMs * BN / 128);
-  // bands are equalised over num_m. One-wave problems keep the m-fastest order.
-  int group_m = 0;
-  {
-    const int num_m = (M + 127) / 128, num_n = (N + tile_n - 1) / tile_n;
-    if (g_group_m_override > 0) group_m = g_group_m_override;
-    else if (g_group_m_override == 0 && (long long)num_m * num_n > kNumSMs) {
-      const double ideal = sqrt((double)kNumSMs * tile_n / 128.0);
-      int nbands = (int)(num_m / ideal + 0.5);
-      if (nbands < 1) nbands = 1;
-      group_m = (num_m + nbands - 1) / nbands;
-    }
-    if (group_m >= num_m && (g_group_m_override <= 0)) group_m = 0;   // one band == m-fastest
-  }
+  const int group_m = pick_group_m(M, N, K, tile_n, out_f32 != 0 || resid != nullptr);
   GemmEpilogue ep{out, ldo, out_f32, bias, resid, ldr, resid_f32, act, alpha, M, N, K,
-                  make_drop(drop_p, drop_seed, drop_stream_id, drop_offset), group_m, 0, nullptr, nullptr, 0, 0};
+                  make_drop(drop_p, drop_seed, drop_stream_id, drop_offset), group_m, 0, nullptr, nullptr, 0, 0, g_l2_hints};
   cudaStream_t st = (cudaStream_t)stream;
   if (bn == 2256) return launch_gemm2<256>(ta, tb, to, ep, max_ctas, st);
   if (bn == 3256) return launch_gemm2<256, 3>(ta, tb, to, ep, max_ctas, st);     // tuning probes (fewer stages)
@@ -761,18 +788,8 @@ extern "C" int dalm_b200_gemm_bf16_swiglu(const void* A, long long lda, const vo
   if (int e = get_tmap(B, N, K, ldb, 256, &tb)) return e;
   if (int e = get_tmap(gu, M, N, ldgu, 128, &to, 0)) return e;
   if (int e = get_tmap(act, M, N / 2, ldact, 128, &to2, 0)) return e;
-  int group_m = 0;
-  {
-    const int num_m = (M + 127) / 128, num_n = N / 256;
-    if (g_group_m_override > 0) group_m = g_group_m_override;
-    else if (g_group_m_override == 0 && (long long)num_m * num_n > kNumSMs) {
-      int nbands = (int)(num_m / sqrt((double)kNumSMs * 2.0) + 0.5);
-      if (nbands < 1) nbands = 1;
-      group_m = (num_m + nbands - 1) / nbands;
-    }
-    if (group_m >= num_m && g_group_m_override <= 0) group_m = 0;
-  }
-  GemmEpilogue ep{gu, ldgu, 0, nullptr, nullptr, 0, 0, 0, 1.f, M, N, K, make_drop(0.f, 0, 0, nullptr), group_m, 1, nullptr, nullptr, 0, 0};
+  const int group_m = pick_group_m(M, N, K, 256, false);
+  GemmEpilogue ep{gu, ldgu, 0, nullptr, nullptr, 0, 0, 0, 1.f, M, N, K, make_drop(0.f, 0, 0, nullptr), group_m, 1, nullptr, nullptr, 0, 0, g_l2_hints};
   return launch_gemm<256>(ta, tb, to, ep, 0, (cudaStream_t)stream, &to2);
 }
 
@@ -788,18 +805,8 @@ extern "C" int dalm_b200_gemm_bf16_rope(const void* A, long long lda, const void
   if (int e = get_tmap(A, M, K, lda, 128, &ta)) return e;
   if (int e = get_tmap(B, N, K, ldb, 256, &tb)) return e;
   if (int e = get_tmap(out, M, N, ldo, 128, &to, 0)) return e;
-  int group_m = 0;
-  {
-    const int num_m = (M + 127) / 128, num_n = (N + 255) / 256;
-    if (g_group_m_override > 0) group_m = g_group_m_override;
-    else if (g_group_m_override == 0 && (long long)num_m * num_n > kNumSMs) {
-      int nbands = (int)(num_m / sqrt((double)kNumSMs * 2.0) + 0.5);
-      if (nbands < 1) nbands = 1;
-      group_m = (num_m + nbands - 1) / nbands;
-    }
-    if (group_m >= num_m && g_group_m_override <= 0) group_m = 0;
-  }
-  GemmEpilogue ep{out, ldo, 0, nullptr, nullptr, 0, 0, 0, 1.f, M, N, K, make_drop(0.f, 0, 0, nullptr), group_m, 2, cos_t, sin_t, L, rope_cols};
+  const int group_m = pick_group_m(M, N, K, 256, false);
+  GemmEpilogue ep{out, ldo, 0, nullptr, nullptr, 0, 0, 0, 1.f, M, N, K, make_drop(0.f, 0, 0, nullptr), group_m, 2, cos_t, sin_t, L, rope_cols, g_l2_hints};
   return launch_gemm<256>(ta, tb, to, ep, 0, (cudaStream_t)stream);
 }
 

@@ -204,6 +204,7 @@ struct CeParams {
   int64_t ldl;             // row stride in elements
   float gout;
   int cache_in_smem;       // 1: row staged in shared memory (V * sizeof(T) bytes)
+  int row0;                // first (b*L + t) row of this launch: `logits` / `dlogits` point at that row (row-chunked lm_head + CE)
 };
 
 // one CTA per (b,t) row. bf16 rows are staged in shared memory (64 KB at V=32000) so HBM sees each logit once on
@@ -213,10 +214,10 @@ __global__ void __launch_bounds__(512) ce_rows_kernel(CeParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float red[32];
   T* row_s = reinterpret_cast<T*>(smem_raw);
-  const int row = blockIdx.x;                 // = b*L + t
+  const int row = p.row0 + blockIdx.x;        // = b*L + t
   const int b = row / p.L, t = row - b * p.L;
-  const T* x = reinterpret_cast<const T*>(p.logits) + (size_t)row * p.ldl;
-  T* dx = p.dlogits ? reinterpret_cast<T*>(p.dlogits) + (size_t)row * p.ldl : nullptr;
+  const T* x = reinterpret_cast<const T*>(p.logits) + (size_t)blockIdx.x * p.ldl;
+  T* dx = p.dlogits ? reinterpret_cast<T*>(p.dlogits) + (size_t)blockIdx.x * p.ldl : nullptr;
   const int V = p.V, tid = threadIdx.x, nt = blockDim.x;
 
   float w = 0.f;
@@ -377,14 +378,18 @@ extern "C" int dalm_b200_inbatch_loss_fwd_bwd(const float* Q, const float* P, in
   return check_launch("inbatch_loss_kernel");
 }
 
-extern "C" int dalm_b200_ce_marginal_fwd_bwd(const void* logits, void* dlogits, int dtype /*0=bf16,1=f32*/,
-                                             const int64_t* ids, const int64_t* mask, const float* nsum,
-                                             float* tok_lp, int B, int L, int V, int64_t ld, float grad_out,
-                                             void* stream) {
+// rows [row0, row0 + nrows) of the flattened [B*L] token rows; `logits` / `dlogits` point at row `row0` (their own buffer may
+// hold just that chunk). tok_lp stays the whole [B,L] table (written at the global row index).
+extern "C" int dalm_b200_ce_marginal_rows(const void* logits, void* dlogits, int dtype /*0=bf16,1=f32*/,
+                                          const int64_t* ids, const int64_t* mask, const float* nsum,
+                                          float* tok_lp, int B, int L, int V, int64_t ld, float grad_out,
+                                          int row0, int nrows, void* stream) {
   DALM_REQUIRE(B > 0 && L > 1 && V > 0, "ce_marginal: bad shape B=%d L=%d V=%d", B, L, V);
   DALM_REQUIRE(dtype == 0 || dtype == 1, "ce_marginal: dtype must be 0 (bf16) or 1 (f32)");
   DALM_REQUIRE(ld >= V, "ce_marginal: ld < V");
-  CeParams p{logits, dlogits, ids, mask, nsum, tok_lp, B, L, V, ld, grad_out, 1};
+  DALM_REQUIRE(row0 >= 0 && nrows > 0 && (long long)row0 + nrows <= (long long)B * L,
+               "ce_marginal: rows [%d, %d + %d) outside the %d x %d token rows", row0, row0, nrows, B, L);
+  CeParams p{logits, dlogits, ids, mask, nsum, tok_lp, B, L, V, ld, grad_out, 1, row0};
   const size_t esz = dtype == 0 ? 2 : 4;
   size_t smem = (size_t)V * esz;
   smem = (smem + 15) & ~size_t(15);
@@ -397,10 +402,18 @@ extern "C" int dalm_b200_ce_marginal_fwd_bwd(const void* logits, void* dlogits, 
       DALM_CUDA(cudaFuncSetAttribute(ce_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set[dtype] = true;
   }
-  if (dtype == 0) ce_rows_kernel<__nv_bfloat16><<<B * L, 512, smem, (cudaStream_t)stream>>>(p);
-  else            ce_rows_kernel<float><<<B * L, 512, smem, (cudaStream_t)stream>>>(p);
+  if (dtype == 0) ce_rows_kernel<__nv_bfloat16><<<nrows, 512, smem, (cudaStream_t)stream>>>(p);
+  else            ce_rows_kernel<float><<<nrows, 512, smem, (cudaStream_t)stream>>>(p);
   count_launch();
   return check_launch("ce_rows_kernel");
+}
+
+extern "C" int dalm_b200_ce_marginal_fwd_bwd(const void* logits, void* dlogits, int dtype /*0=bf16,1=f32*/,
+                                             const int64_t* ids, const int64_t* mask, const float* nsum,
+                                             float* tok_lp, int B, int L, int V, int64_t ld, float grad_out,
+                                             void* stream) {
+  DALM_REQUIRE(B > 0 && L > 1, "ce_marginal: bad shape B=%d L=%d V=%d", B, L, V);
+  return dalm_b200_ce_marginal_rows(logits, dlogits, dtype, ids, mask, nsum, tok_lp, B, L, V, ld, grad_out, 0, B * L, stream);
 }
 
 extern "C" int dalm_b200_finalize_loss(const float* tok_lp, const int64_t* mask, int B, int L, const float* nsum,

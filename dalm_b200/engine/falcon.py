@@ -217,9 +217,9 @@ class FalconDecoder(torch.nn.Module):
         return ops.layernorm_bwd_res(x, W["ln_g"], a.mean, a.rstd, dh, dres=dx32, dz32=dx32)
 
     # ---- whole model ----------------------------------------------------------------------------------------------
-    def forward_logits(self, ids: torch.Tensor, mask: torch.Tensor, save: bool = False):
-        """ids, mask int64 [B,L] -> (logits bf16 [B,L,V], ctx). ctx (save=True on a trainable model) holds only each layer's
-        fp32 input: the backward recomputes the rest."""
+    def _forward_to_final(self, ids: torch.Tensor, mask: torch.Tensor, save: bool):
+        """-> (hf bf16 [M,H] after ln_f, ctx or None). ctx (save=True on a trainable model) holds only each layer's fp32 input:
+        the backward recomputes the rest."""
         B, L = ids.shape
         cos_t, sin_t = self._rope(L)
         mask = mask.contiguous()
@@ -232,11 +232,43 @@ class FalconDecoder(torch.nn.Module):
                 xs.append(x)
             x, _ = self._layer_fwd(W, x, mask, B, L, cos_t, sin_t, keep=False)
         _, hf, mean_f, rstd_f = ops.layernorm_fwd(x, self.lnf_g, self.lnf_b, self.eps, want_f32=False)
-        logits = ops.gemm(hf, self.lm_head)
         if keep_inputs:
             ctx.B, ctx.L, ctx.mask, ctx.ids, ctx.xs, ctx.x_final, ctx.hf, ctx.mean_f, ctx.rstd_f = \
                 B, L, mask, ids.contiguous(), xs, x, hf, mean_f, rstd_f
+        return hf, ctx
+
+    def forward_logits(self, ids: torch.Tensor, mask: torch.Tensor, save: bool = False):
+        """ids, mask int64 [B,L] -> (logits bf16 [B,L,V], ctx)"""
+        B, L = ids.shape
+        hf, ctx = self._forward_to_final(ids, mask, save)
+        logits = ops.gemm(hf, self.lm_head)
         return logits.view(B, L, self.Vp)[:, :, :self.V], ctx
+
+    def forward_final(self, ids: torch.Tensor, mask: torch.Tensor, save: bool = False):
+        """the fused step's forward: everything up to ln_f; the (tied) lm_head runs chunk by chunk inside `head_loss`, so the
+        [B,L,65024] logits (4.8 GB in bf16 at cfg-5) are never written. -> handle for head_loss / backward_final"""
+        hf, ctx = self._forward_to_final(ids, mask, save)
+        h = _Ctx()
+        h.hf, h.ctx = hf, ctx
+        return h
+
+    def head_loss(self, h, ids: torch.Tensor, mask: torch.Tensor, nsum: torch.Tensor, need_grad: bool = True, grad_out: float = 1.0):
+        """-> (tok_lp fp32 [B,L], d(hf) bf16 [M,H] or None); see engine/head.py"""
+        from .head import chunked_head_loss
+        need_grad = need_grad and self.full is not None and h.ctx is not None
+        wgrad = None
+        if need_grad:
+            bank = self.full
+            h.acc = bank.begin_backward()
+            tgt = bank.g("embed") if self.tied else bank.g("lm_head")                 # tied head: lands in the embedding gradient
+            acc0 = True if self.tied else h.acc
+            wgrad = lambda dl, x, first: ops.wgrad_(dl, x, tgt, acc0 if first else True)
+        return chunked_head_loss(h.hf, self.lm_head, None, self.V, ids, mask, nsum, need_grad, grad_out, wgrad)
+
+    def backward_final(self, h, dhf: torch.Tensor) -> None:
+        if self.full is None or h.ctx is None or dhf is None:
+            return
+        self._backward_from_dhf(h.ctx, dhf, h.acc)
 
     # ---- greedy decoding with a KV cache (evaluation: reference dalm/eval/eval_rag.py:126-140) ----------------------
     def kv_columns(self):
@@ -288,6 +320,12 @@ class FalconDecoder(torch.nn.Module):
         # tied head: its weight gradient lands in the embedding table's (accumulating) gradient
         ops.wgrad_(dl2, ctx.hf, bank.g("embed") if self.tied else bank.g("lm_head"), True if self.tied else acc)
         dhf = ops.gemm(dl2, self.lm_head, layout=1)                                   # [M,H]
+        self._backward_from_dhf(ctx, dhf, acc)
+
+    def _backward_from_dhf(self, ctx, dhf: torch.Tensor, acc: bool) -> None:
+        """from the gradient of ln_f's output (bf16 [M,H]) down through the layers (per-layer recomputation)"""
+        bank, B, L = self.full, ctx.B, ctx.L
+        cos_t, sin_t = self._rope(L)
         ops.col_reduce_(dy_bf16=dhf, z=ctx.x_final, mean=ctx.mean_f, rstd=ctx.rstd_f, out_sum=bank.g("lnf_b"), out_prod=bank.g("lnf_g"))
         dx32, dx16 = ops.layernorm_bwd(ctx.x_final, self.lnf_g, ctx.mean_f, ctx.rstd_f, dy_bf16=dhf)
         for l in range(self.nl - 1, -1, -1):

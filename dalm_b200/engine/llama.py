@@ -293,6 +293,34 @@ class LlamaDecoder(torch.nn.Module):
         logits = ops.gemm(ctx.hf, self.lm_head)                                   # bf16 [M,Vp]
         return logits.view(B, L, self.Vp)[:, :, :self.V], ctx
 
+    def forward_final(self, ids: torch.Tensor, mask: torch.Tensor, save: bool = True) -> _Ctx:
+        """the decoder up to the final RMSNorm (ctx.hf bf16 [M,H]) — the fused step's forward: the lm_head runs inside
+        `head_loss`, chunk by chunk, and no [B,L,V] logits tensor is ever written"""
+        return self._forward_body(ids, mask, save)
+
+    def head_loss(self, ctx: _Ctx, ids: torch.Tensor, mask: torch.Tensor, nsum: torch.Tensor, need_grad: bool = True,
+                  grad_out: float = 1.0):
+        """lm_head + marginalised-NLL token terms (+ the head's dgrad / wgrad) over row chunks (engine/head.py; reference
+        train_utils.py:113-138 on `generator_model(...).logits`). -> (tok_lp fp32 [B,L], d(hf) bf16 [M,H] or None)"""
+        from .head import chunked_head_loss
+        need_grad = need_grad and self.trainable
+        wgrad = None
+        if need_grad and self.full is not None:
+            ctx.acc = self.full.begin_backward()
+            tgt = self.full.g("embed") if self.tied else self.full.g("lm_head")      # tied head: gradient lands in the embedding table
+            acc0 = True if self.tied else ctx.acc
+            wgrad = lambda dl, h, first: ops.wgrad_(dl, h, tgt, acc0 if first else True)
+        tok_lp, dhf = chunked_head_loss(ctx.hf, self.lm_head, getattr(self, "lm_headT", None) if self.full is None else None, self.V,
+                                        ids, mask, nsum, need_grad, grad_out, wgrad)
+        if wgrad is not None and not self.tied:
+            self.full.bucket_ready("lm_head")                                      # final: all-reduce it under the layers' backward
+        return tok_lp, dhf
+
+    def backward_final(self, ctx: _Ctx, dhf: torch.Tensor) -> None:
+        """continues `head_loss`'s backward from d(final-norm output) down through the layers"""
+        if self.trainable and dhf is not None:
+            self._backward_body(ctx, dhf)
+
     def forward_hidden(self, ids: torch.Tensor, mask: torch.Tensor, save: bool = True):
         """last hidden state (after the final RMSNorm) as fp32 [B,L,H] — what `AutoModel(...)(..., output_hidden_states=True)
         .hidden_states[-1]` gives the reference's autoregressive-retriever branch (rag_e2e_base_model.py:84-90)"""

@@ -114,6 +114,43 @@ def ce_marginal(logits: torch.Tensor, ids: torch.Tensor, mask: torch.Tensor, nsu
     return tok_lp, dl
 
 
+def ce_marginal_rows_(chunk: torch.Tensor, ids: torch.Tensor, mask: torch.Tensor, nsum: torch.Tensor, tok_lp: torch.Tensor,
+                      row0: int, V: int, need_grad: bool = True, grad_out: float = 1.0) -> None:
+    """chunk: bf16|fp32 [n, ld >= V] = the logits of token rows [row0, row0 + n) of the flattened [B*L] rows. Writes
+    tok_lp[B,L] at those rows and (need_grad) overwrites `chunk` with d(logits) in place."""
+    if chunk.dtype not in (bf16, f32):
+        raise _lib.DalmB200Error(f"ce_marginal_rows: logits dtype {chunk.dtype} unsupported")
+    _chk(chunk, chunk.dtype, "chunk"); _chk(ids, i64, "ids"); _chk(mask, i64, "mask"); _chk(tok_lp, f32, "tok_lp")
+    if chunk.dim() != 2 or not ids.is_contiguous() or not mask.is_contiguous() or not tok_lp.is_contiguous():
+        raise _lib.DalmB200Error("ce_marginal_rows: chunk must be 2-D, ids / mask / tok_lp contiguous")
+    B, L = ids.shape
+    _lib.call("dalm_b200_ce_marginal_rows", _p(chunk), _p(chunk) if need_grad else None, 0 if chunk.dtype == bf16 else 1, _p(ids),
+              _p(mask), _p(nsum), _p(tok_lp), B, L, int(V), chunk.stride(0), float(grad_out), int(row0), chunk.shape[0], _stream())
+
+
+def head_chunk_rows(M: int, Vp: int, budget_bytes: int, tile_n: int = 256, sms: int = 148) -> int:
+    """Row-chunk height of the chunked lm_head + CE pass: the largest split into equal, 128-row-aligned chunks whose bf16
+    logits scratch [rows, Vp] stays within `budget_bytes`, choosing among the next few chunk counts the one whose GEMMs
+    waste the fewest tile waves on `sms` persistent CTAs (a chunk of m x n tiles costs ceil(m n / sms) waves)."""
+    m_tiles = (M + 127) // 128
+    n_tiles = (Vp + tile_n - 1) // tile_n
+    max_rows = max(128, budget_bytes // (2 * Vp) // 128 * 128)
+    n_min = max(1, -(-M // max_rows))
+    best = None
+    for n in range(n_min, min(m_tiles, n_min + 4) + 1):
+        per = -(-m_tiles // n)                                   # m-tiles per chunk (the last chunk may be shorter)
+        if per * 128 > max_rows and n > n_min:
+            continue
+        waves, left = 0, m_tiles
+        while left > 0:
+            k = min(per, left)
+            waves += -(-(k * n_tiles) // sms)
+            left -= k
+        if best is None or waves < best[0]:
+            best = (waves, per * 128)
+    return best[1]
+
+
 def finalize_loss(tok_lp: torch.Tensor, mask: torch.Tensor, nsum: torch.Tensor,
                   inbatch_losses: Optional[torch.Tensor]) -> torch.Tensor:
     B, L = tok_lp.shape

@@ -148,6 +148,7 @@ def _encode_pair(enc, q_ids, q_mask, p_ids, p_mask, save: bool):
 
 
 _TWO_STREAMS = os.environ.get("DALM_B200_TWO_STREAMS", "1") != "0"
+_CHUNKED_HEAD = os.environ.get("DALM_B200_CHUNKED_HEAD", "1") != "0"      # 0: materialise the [B,L,V] logits (A/B switch)
 _SIDE_STREAMS: Dict[int, torch.cuda.Stream] = {}
 
 
@@ -194,6 +195,13 @@ def fused_rag_step(rag_model, batch: Dict[str, torch.Tensor], logit_scale: float
         return r
 
     def generator_branch():
+        if _CHUNKED_HEAD and hasattr(dec, "head_loss"):
+            # lm_head + CE + the head's backward chunk by chunk over an L2-sized scratch: no [B,L,V] logits in HBM (engine/head.py)
+            cg = dec.forward_final(g_ids, g_mask, save=train_dec)
+            tok_lp, dhf = dec.head_loss(cg, g_ids, g_mask, nsum, need_grad=train_dec, grad_out=grad_scale)
+            if train_dec:
+                dec.backward_final(cg, dhf)
+            return tok_lp
         logits, cg = dec.forward_logits(g_ids, g_mask, save=train_dec)
         tok_lp, dl = ops.ce_marginal(logits, g_ids, g_mask, nsum, need_grad=train_dec, inplace=True, grad_out=grad_scale)
         if train_dec:

@@ -39,6 +39,13 @@ int dalm_b200_inbatch_loss_fwd_bwd(const float* Q, const float* P, int B, int D,
 int dalm_b200_ce_marginal_fwd_bwd(const void* logits, void* dlogits, int dtype, const int64_t* ids, const int64_t* mask,
                                   const float* nsum, float* tok_lp, int B, int L, int V, long long ld, float grad_out,
                                   void* stream);
+/* ce_marginal_rows: the same pass over token rows [row0, row0 + nrows) of the flattened [B*L] rows only; logits / dlogits
+ *   point at row `row0` (a scratch holding just that chunk), tok_lp is still the whole [B,L] table. This is what lets the
+ *   lm_head GEMM, the vocabulary CE and the head's dgrad run chunk by chunk over an L2-sized scratch, so the [B,L,V]
+ *   logits of train_utils.py:113-138 (590 MB fp32 + three more copies in the reference) never exist in HBM. */
+int dalm_b200_ce_marginal_rows(const void* logits, void* dlogits, int dtype, const int64_t* ids, const int64_t* mask,
+                               const float* nsum, float* tok_lp, int B, int L, int V, long long ld, float grad_out,
+                               int row0, int nrows, void* stream);
 /* finalize_loss: out4 = {Lc, Lm, Lc+Lm, N}; combined_loss of train_rage2e.py:467. */
 int dalm_b200_finalize_loss(const float* tok_lp, const int64_t* mask, int B, int L, const float* nsum,
                             const float* inbatch_losses, float* out4, void* stream);
@@ -89,9 +96,13 @@ int dalm_b200_gemm_bf16_swiglu(const void* A, long long lda, const void* B, long
 int dalm_b200_gemm_bf16_rope(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo, int M, int N,
                              int K, const float* cos_t, const float* sin_t, int L, int rope_cols, void* stream);
 void dalm_b200_gemm_clear_cache(void);
-/* tile rasterisation of the persistent GEMM (tuning / test hook): -1 = m-fastest order, 0 = automatic band height
- * (default: ~square wave footprint, serpentine inside a band), > 0 = bands of that many 128-row m-tiles */
+/* tile rasterisation of the persistent GEMM (tuning / test hook): -1 = m-fastest order, 0 = automatic (default: m-fastest
+ * while A [M,K] stays L2-resident next to a bf16 output, else bands with a ~square wave footprint walked serpentine),
+ * -2 = bands for every multi-wave problem, > 0 = bands of that many 128-row m-tiles. Env DALM_B200_GEMM_RASTER seeds it. */
 void dalm_b200_gemm_set_raster(int group_m);
+/* L2 eviction priorities on the GEMM's TMA traffic (bit mask; tuning hook, default 0 / env DALM_B200_GEMM_L2_HINTS):
+ * 1 = A loads evict_last, 2 = B loads evict_first, 4 = output stores evict_first */
+void dalm_b200_gemm_set_l2_hints(int mask);
 
 /* ---- attention (same call sites; HF eager/SDPA attention) ---- */
 int dalm_b200_attention_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
