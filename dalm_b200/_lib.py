@@ -58,6 +58,7 @@ SIGNATURES = {
     "dalm_b200_swiglu_bwd": [_P, _L, _P, _L, _I, _I, _I, _P],
     "dalm_b200_gemm_bf16_swiglu": [_P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _P],
     "dalm_b200_gemm_bf16_rope": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _I, _I, _P],
+    "dalm_b200_gemm_bf16_gelu": [_P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P],
     "dalm_b200_gelu_fwd": [_P, _L, _P, _L, _I, _I, _P],
     "dalm_b200_gelu_bwd": [_P, _L, _P, _L, _I, _I, _P],
     "dalm_b200_pool_norm_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],

@@ -33,7 +33,8 @@ struct GemmEpilogue {
   const void* resid;    // [M, ldr] added after activation, or nullptr (may alias out)
   long long ldr;
   int resid_f32;
-  int act;              // 0: none, 1: GELU(erf)
+  int act;              // 0: none, 1: GELU(erf), 2: GELU backward - out = bf16(alpha*acc + bias) * gelu'(resid) (resid = the bf16
+                        //    pre-activation; multiplied, not added): the dgrad GEMM of the FFN output projection emits d(pre) directly
   float alpha;
   int M, N, K;
   DropCfg drop;         // dropout on act(alpha*acc+bias) BEFORE the residual add (BertSelfOutput / BertOutput); p = 0 => off
@@ -41,6 +42,8 @@ struct GemmEpilogue {
   int fuse;             // 0: none; 1: SwiGLU forward - tile columns [0,128) = gate, [128,256) = up of the same 128 features (weight
                         // rows interleaved); besides `out` (gate|up, the backward's input) the tile's silu(gate)*up goes to tmap_out2
                         // 2: rotary position embedding (head_dim 128, HF rotate_half) on output columns < rope_cols
+                        // 3: GELU forward with both tensors kept - `out` = pre-activation (bf16, what the backward needs),
+                        //    tmap_out2 = gelu(pre) (bf16, the next GEMM's operand): one launch instead of GEMM + a 2-pass kernel
   const float* rope_cos; const float* rope_sin;   // fuse == 2: fp32 [rope_L, 64]; the position of output row m is m % rope_L
   int rope_L, rope_cols;
   int l2_hints;         // TMA L2 eviction priorities: bit 0 = A loads evict_last (the panel the resident CTAs share across waves),
@@ -111,8 +114,13 @@ __device__ __forceinline__ void epilogue_math(const GemmEpilogue& ep, const uint
           const bf16x8 t = *reinterpret_cast<const bf16x8*>(r + g * 8);
           float tf[8];
           unpack8(t, tf);
+          if (ep.act == 2) {     // same roundings as the un-fused pair (bf16 dgrad output, then gelu_bwd_kernel): bit-identical results
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[g * 8 + i] += tf[i];
+            for (int i = 0; i < 8; ++i) f[g * 8 + i] = __bfloat162float(__float2bfloat16_rn(f[g * 8 + i])) * gelu_erf_grad(tf[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[g * 8 + i] += tf[i];
+          }
         }
       }
     }
@@ -129,7 +137,7 @@ __device__ __forceinline__ void epilogue_math(const GemmEpilogue& ep, const uint
 constexpr int kStageTileBytes = 128 * 128;
 constexpr int kEpiGroups = 2;                                   // two groups of 4 epilogue warps split a tile's store blocks
 constexpr int kGemmThreads = 128 + kEpiGroups * 128;            // warps 0-3: TMA / MMA / TMEM alloc / spare ; warps 4-11: epilogue
-template <int BN>
+template <int BN, int SPECIAL = 0>        // SPECIAL 3: the GELU two-output epilogue (fuse == 3) is compiled into its own kernel
 __device__ __forceinline__ void epilogue_drain_tile(const GemmEpilogue& ep, const CUtensorMap* tmap_out, const CUtensorMap* tmap_out2,
                                                     unsigned char* staging, int grp, uint32_t t_row, int row_in_tile, int tile_row0,
                                                     int tile_col0) {
@@ -206,6 +214,52 @@ __device__ __forceinline__ void epilogue_drain_tile(const GemmEpilogue& ep, cons
         for (int g = 0; g < 4; ++g)
           *reinterpret_cast<bf16x8*>(st + (((h * 4 + g) ^ sw) << 4)) = pack8(f + g * 8);
       }
+    } else if (SPECIAL == 3) {
+      // GELU forward, both tensors: the 64-column block goes out twice through the same staging tile - first the bf16
+      // pre-activation, then gelu() of those ROUNDED values (exactly what gelu_fwd_kernel would read back from HBM).
+      bf16x8 pk[8];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (col0 + h * 32 < N) {
+          uint32_t v[32]; float f[32];
+          tmem_ld_32x32(t_row + (uint32_t)(c + h * 32), v);
+          tmem_ld_wait();
+          epilogue_math(ep, v, f, row, col0 + h * 32, row_ok);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) pk[h * 4 + g] = pack8(f + g * 8);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) pk[h * 4 + g] = bf16x8{};
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < 8; ++g) *reinterpret_cast<bf16x8*>(st + ((g ^ sw) << 4)) = pk[g];
+      fence_proxy_async();
+      named_bar_sync(1 + grp, 128);
+      if (issuer) {
+        if (ep.l2_hints & 4) tma_store_2d_hint(tmap_out, tile, col0, tile_row0, l2_policy_evict_first());
+        else                 tma_store_2d(tmap_out, tile, col0, tile_row0);
+        bulk_commit();
+      }
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {                             // overlaps the TMA unit reading the staging tile
+        float x[8];
+        unpack8(pk[g], x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = gelu_erf(x[i]);
+        pk[g] = pack8(x);
+      }
+      if (issuer) bulk_wait_read<0>();
+      named_bar_sync(1 + grp, 128);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) *reinterpret_cast<bf16x8*>(st + ((g ^ sw) << 4)) = pk[g];
+      fence_proxy_async();
+      named_bar_sync(1 + grp, 128);
+      if (issuer) {
+        tma_store_2d(tmap_out2, tile, col0, tile_row0);
+        bulk_commit();
+      }
+      continue;
     } else {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -280,7 +334,7 @@ template <int BN> struct GemmCfg {
 //   2  "wgrad" A[K,M], B[K,N] both MN-major                    dW[out,in] = dy^T x : contraction over the token rows
 // MN-major stage tiles are stored [64 k-rows][64 elements = 128 B] per 64-wide chunk (8 KB, chunks LBO = 8 KB apart,
 // 8-row groups SBO = 1 KB apart), each chunk one TMA box of the row-major source.
-template <int BN, int LAYOUT>
+template <int BN, int LAYOUT, int SPECIAL = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2, const GemmEpilogue ep) {
@@ -306,6 +360,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     prefetch_tmap(&tmap_out);
+    if (ep.fuse == 1 || ep.fuse == 3) prefetch_tmap(&tmap_out2);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -398,7 +453,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_drain_tile<BN>(ep, &tmap_out, &tmap_out2, staging, grp, t_row, q * 32 + lane, m_blk * BM, n_blk * BN);
+      epilogue_drain_tile<BN, SPECIAL>(ep, &tmap_out, &tmap_out2, staging, grp, t_row, q * 32 + lane, m_blk * BM, n_blk * BN);
       // all TMEM reads of this warp are complete (wait::ld): hand the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -613,19 +668,19 @@ int get_tmap(const void* ptr, long long rows, long long cols, long long ld, int 
   return 0;
 }
 
-template <int BN, int LAYOUT = 0>
+template <int BN, int LAYOUT = 0, int SPECIAL = 0>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmEpilogue& ep,
                        int max_ctas, cudaStream_t stream, const CUtensorMap* to2 = nullptr) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    DALM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    DALM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, LAYOUT, SPECIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int num_tiles = ((ep.M + 127) / 128) * ((ep.N + BN - 1) / BN);
   int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  gemm_bf16_tn_kernel<BN, LAYOUT><<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, to, to2 ? *to2 : to, ep);
+  gemm_bf16_tn_kernel<BN, LAYOUT, SPECIAL><<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, to, to2 ? *to2 : to, ep);
   count_launch();
   return check_launch("gemm_bf16_tn_kernel");
 }
@@ -668,6 +723,27 @@ extern "C" void dalm_b200_gemm_set_raster(int group_m) { g_group_m_override = gr
 // TMA L2 eviction hints (GemmEpilogue::l2_hints bit mask); initial value: env DALM_B200_GEMM_L2_HINTS
 static int g_l2_hints = env_int("DALM_B200_GEMM_L2_HINTS", 0);
 extern "C" void dalm_b200_gemm_set_l2_hints(int mask) { g_l2_hints = mask & 7; }
+
+// tile-shape heuristic: estimated time = waves of 148 CTAs x tile width x an efficiency penalty for narrow tiles (a
+// 128 x BN tile re-reads its A operand from shared memory for every BN columns: profiles/r01_gemm_probe_tiles.jsonl).
+// The 128x256 tile wins whenever the problem has more than about one wave of work - including N = 1024 at 3 204
+// encoder rows, where 104 tiles in ONE wave take 32 us against 54 us for 208 half-width tiles in two waves
+// (profiles/r01_gemm_shapes_in_step.txt had those shapes at 280-410 TFLOP/s). The CTA-pair kernel (block_n 2128/2256) is
+// correct and tested but not faster on these shapes, so never auto-picked.
+static int pick_block_n(int M, int N) {
+  const long long m1 = (M + 127) / 128;
+  double best = 1e30;
+  int bn = 64;
+  const int cand[3] = {256, 128, 64};
+  const double penalty[3] = {1.0, 1.55, 2.7};      // measured at 26700x1024x4096: 203 / 313 / 549 us
+  for (int i = 0; i < 3; ++i) {
+    if (cand[i] > 64 && N < cand[i]) continue;                // do not pad N by more than one tile
+    const long long tiles = m1 * ((N + cand[i] - 1) / cand[i]);
+    const double cost = (double)((tiles + kNumSMs - 1) / kNumSMs) * cand[i] * penalty[i];
+    if (cost < best) { best = cost; bn = cand[i]; }
+  }
+  return bn;
+}
 
 // Band height of the tile rasterisation (0 = m-fastest). One wave = the kNumSMs tiles resident at a time.
 //  * m-fastest: a wave spans every m-tile of ~kNumSMs/num_m n-tiles, so all of A is touched by every wave. When A [M,K] is small
@@ -722,26 +798,11 @@ extern "C" int dalm_b200_gemm_bf16(int layout, const void* A, long long lda, con
     DALM_REQUIRE((ldr % (resid_f32 ? 4 : 8)) == 0, "gemm: ldr=%lld breaks 16-byte row alignment", ldr);
     DALM_REQUIRE((reinterpret_cast<uintptr_t>(resid) & 15) == 0, "gemm: resid is not 16-byte aligned");
   }
-  DALM_REQUIRE(act == 0 || act == 1, "gemm: act must be 0 (none) or 1 (gelu)");
+  DALM_REQUIRE(act == 0 || act == 1 || act == 2, "gemm: act must be 0 (none), 1 (gelu) or 2 (gelu backward: multiply by gelu'(resid))");
+  DALM_REQUIRE(act != 2 || (resid != nullptr && !resid_f32 && !out_f32 && drop_p == 0.f),
+               "gemm: act 2 (gelu backward) needs a bf16 `resid` (the pre-activation), a bf16 output and no dropout");
   int bn = block_n;
-  if (bn == 0) {
-    // tile-shape heuristic: estimated time = waves of 148 CTAs x tile width x an efficiency penalty for narrow tiles (a
-    // 128 x BN tile re-reads its A operand from shared memory for every BN columns: profiles/r01_gemm_probe_tiles.jsonl).
-    // The 128x256 tile wins whenever the problem has more than about one wave of work — including N = 1024 at 3 204
-    // encoder rows, where 104 tiles in ONE wave take 32 us against 54 us for 208 half-width tiles in two waves
-    // (profiles/r01_gemm_shapes_in_step.txt had those shapes at 280-410 TFLOP/s). The CTA-pair kernel (block_n 2128/2256) is
-    // correct and tested but not faster on these shapes, so never auto-picked.
-    const long long m1 = (M + 127) / 128;
-    double best = 1e30;
-    const int cand[3] = {256, 128, 64};
-    const double penalty[3] = {1.0, 1.55, 2.7};      // measured at 26700x1024x4096: 203 / 313 / 549 us
-    for (int i = 0; i < 3; ++i) {
-      if (cand[i] > 64 && N < cand[i]) continue;                // do not pad N by more than one tile
-      const long long tiles = m1 * ((N + cand[i] - 1) / cand[i]);
-      const double cost = (double)((tiles + kNumSMs - 1) / kNumSMs) * cand[i] * penalty[i];
-      if (cost < best) { best = cost; bn = cand[i]; }
-    }
-  }
+  if (bn == 0) bn = pick_block_n(M, N);
   DALM_REQUIRE(bn == 64 || bn == 128 || bn == 256 || bn == 2128 || bn == 2256 || bn == 3256 || bn == 4256,
                "gemm: block_n must be 0, 64/128/256 (single CTA) or 2128/2256 (CTA pair)");
   const bool pair = bn > 1000;
@@ -791,6 +852,27 @@ extern "C" int dalm_b200_gemm_bf16_swiglu(const void* A, long long lda, const vo
   const int group_m = pick_group_m(M, N, K, 256, false);
   GemmEpilogue ep{gu, ldgu, 0, nullptr, nullptr, 0, 0, 0, 1.f, M, N, K, make_drop(0.f, 0, 0, nullptr), group_m, 1, nullptr, nullptr, 0, 0, g_l2_hints};
   return launch_gemm<256>(ta, tb, to, ep, 0, (cudaStream_t)stream, &to2);
+}
+
+// intermediate projection of a GELU MLP (BertIntermediate, Falcon dense_h_to_4h) with the activation fused into the epilogue and
+// BOTH tensors written: pre = A B^T + bias (bf16; gelu_bwd needs it) and act = gelu(pre) (bf16; the output projection's operand).
+extern "C" int dalm_b200_gemm_bf16_gelu(const void* A, long long lda, const void* B, long long ldb, void* pre, long long ldpre,
+                                        void* act, long long ldact, int M, int N, int K, const float* bias, void* stream) {
+  DALM_REQUIRE(M > 0 && N > 0 && K > 0 && (N % 8) == 0 && (K % 8) == 0, "gemm_gelu: bad shape M=%d N=%d K=%d", M, N, K);
+  DALM_REQUIRE(lda >= K && ldb >= K && ldpre >= N && ldact >= N, "gemm_gelu: leading dimensions too small");
+  DALM_REQUIRE((ldpre % 8) == 0 && (ldact % 8) == 0 && ((uintptr_t)pre & 15) == 0 && ((uintptr_t)act & 15) == 0, "gemm_gelu: output alignment");
+  const int bn = pick_block_n(M, N);
+  CUtensorMap ta, tb, to, to2;
+  if (int e = get_tmap(A, M, K, lda, 128, &ta)) return e;
+  if (int e = get_tmap(B, N, K, ldb, bn, &tb)) return e;
+  if (int e = get_tmap(pre, M, N, ldpre, 128, &to, 0)) return e;
+  if (int e = get_tmap(act, M, N, ldact, 128, &to2, 0)) return e;
+  const int group_m = pick_group_m(M, N, K, bn, false);
+  GemmEpilogue ep{pre, ldpre, 0, bias, nullptr, 0, 0, 0, 1.f, M, N, K, make_drop(0.f, 0, 0, nullptr), group_m, 3, nullptr, nullptr, 0, 0, g_l2_hints};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bn == 256) return launch_gemm<256, 0, 3>(ta, tb, to, ep, 0, st, &to2);
+  if (bn == 128) return launch_gemm<128, 0, 3>(ta, tb, to, ep, 0, st, &to2);
+  return launch_gemm<64, 0, 3>(ta, tb, to, ep, 0, st, &to2);
 }
 
 // fused q|k|v projection + rotary embedding: out[M,N] = A[M,K] B[N,K]^T with HF's rotate_half RoPE (head_dim 128) applied to the

@@ -204,11 +204,13 @@ class BertEncoder(torch.nn.Module):
         self._pack_tab = None
         self.repack_lora()
 
-    def _dgrad(self, dy: torch.Tensor, W: Dict[str, torch.Tensor], name: str) -> torch.Tensor:
-        """dx = dy W: against the resident transposed copy (frozen base) or W[out,in] itself read MN-major (full mode)"""
+    def _dgrad(self, dy: torch.Tensor, W: Dict[str, torch.Tensor], name: str, gelu_pre: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """dx = dy W: against the resident transposed copy (frozen base) or W[out,in] itself read MN-major (full mode).
+        gelu_pre: the result is a gradient w.r.t. gelu(pre) - multiply by gelu'(pre) in the epilogue (-> gradient w.r.t. pre)"""
+        kw = dict(act=2, resid=gelu_pre) if gelu_pre is not None else {}
         if self.full is not None:
-            return ops.gemm(dy, W[name], layout=1)
-        return ops.gemm(dy, W[name + "T"])
+            return ops.gemm(dy, W[name], layout=1, **kw)
+        return ops.gemm(dy, W[name + "T"], **kw)
 
     def _init_frozen(self, sd, g, lora: bool) -> None:
         H = self.H
@@ -323,8 +325,11 @@ class BertEncoder(torch.nn.Module):
                           drop=self._drop(self.p_hidden, call, li, 1))
             h_aug = torch.empty(M, H, dtype=bf16, device=self.dev)
             h32, _, m1, r1 = ops.layernorm_fwd(z1, W["ln1_g"], W["ln1_b"], self.eps, y16=h_aug)
-            pre = ops.gemm(h_aug, W["Wi"], bias=W["bi"])                                           # [M,F] pre-activation
-            act = ops.gelu_fwd(pre)
+            if ops.FUSE_GELU:
+                pre, act = ops.gemm_gelu(h_aug, W["Wi"], bias=W["bi"])                             # [M,F] pre-activation AND gelu(pre): one launch
+            else:
+                pre = ops.gemm(h_aug, W["Wi"], bias=W["bi"])
+                act = ops.gelu_fwd(pre)
             z2 = ops.gemm(act, W["Wo2"], out_dtype=f32, bias=W["bo2"], resid=h32, drop=self._drop(self.p_hidden, call, li, 2))
             x_aug = _aug_buf(M, H, Ra, self.dev)
             x32, _, m2, r2 = ops.layernorm_fwd(z2, W["ln2_g"], W["ln2_b"], self.eps, y16=x_aug[:, :H])
@@ -375,8 +380,11 @@ class BertEncoder(torch.nn.Module):
             if bank is not None:                               # output.dense: dW = dz2^T act, db = colsum(dz2)
                 ops.wgrad_(dz2_16, a.act, G(l, "Wo2"), acc)
                 ops.col_reduce_(dy_bf16=dz2_16, out_sum=G(l, "bo2"))
-            dact = self._dgrad(dz2_16, W, "Wo2")
-            ops.gelu_bwd_(a.pre, dact)
+            if ops.FUSE_GELU:
+                dact = self._dgrad(dz2_16, W, "Wo2", gelu_pre=a.pre)                               # d(pre): gelu' applied in the dgrad epilogue
+            else:
+                dact = self._dgrad(dz2_16, W, "Wo2")
+                ops.gelu_bwd_(a.pre, dact)
             if bank is not None:                               # intermediate.dense
                 ops.wgrad_(dact, a.h_aug, G(l, "Wi"), acc)
                 ops.col_reduce_(dy_bf16=dact, out_sum=G(l, "bi"))

@@ -180,8 +180,11 @@ class FalconDecoder(torch.nn.Module):
                                      mask, B, L, self.nh, 1, self.hd, causal=True)
         t = ops.gemm(att, W["Wd"], out_dtype=f32, resid=x)                            # x + attention branch
         if keep:
-            pre = ops.gemm(h, W["W1"])                                                # GELU's input is needed by its backward
-            h4 = ops.gelu_fwd(pre)
+            if ops.FUSE_GELU:
+                pre, h4 = ops.gemm_gelu(h, W["W1"])                                   # GELU's input (needed by its backward) and output, one launch
+            else:
+                pre = ops.gemm(h, W["W1"])
+                h4 = ops.gelu_fwd(pre)
         else:
             pre, h4 = None, ops.gemm(h, W["W1"], act=1)                               # GELU(erf) fused in the epilogue
         x_out = ops.gemm(h4, W["W2"], out_dtype=f32, resid=t)                         # + MLP branch
@@ -198,8 +201,11 @@ class FalconDecoder(torch.nn.Module):
         G = lambda n: bank.g(f"L{l}.{n}")
         # MLP branch
         ops.wgrad_(dx16, a.h4, G("W2"), acc)
-        dpre = ops.gemm(dx16, W["W2"], layout=1)                                      # [M,4H] = d h4
-        ops.gelu_bwd_(a.pre, dpre)                                                    # -> d pre
+        if ops.FUSE_GELU:
+            dpre = ops.gemm(dx16, W["W2"], layout=1, act=2, resid=a.pre)              # [M,4H] = d h4 * gelu'(pre) = d pre
+        else:
+            dpre = ops.gemm(dx16, W["W2"], layout=1)                                  # [M,4H] = d h4
+            ops.gelu_bwd_(a.pre, dpre)                                                # -> d pre
         ops.wgrad_(dpre, a.h, G("W1"), acc)
         dh = ops.gemm(dpre, W["W1"], layout=1)                                        # [M,H] MLP part of d LN-output
         # attention branch

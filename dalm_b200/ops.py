@@ -178,7 +178,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
          max_ctas: int = 0, K: Optional[int] = None, N: Optional[int] = None, drop: Optional[Drop] = None,
          layout: int = 0) -> torch.Tensor:
     """out[M,N] = act(alpha * A @ B^T-or-B + bias) + resid.   a, b: bf16 2-D views with contiguous rows.
-    layout 0 (TN): a[M,K], b[N,K]   1 (NN, dgrad against W[out,in]): a[M,K], b[K,N]   2 (wgrad): a[K,M], b[K,N]"""
+    layout 0 (TN): a[M,K], b[N,K]   1 (NN, dgrad against W[out,in]): a[M,K], b[K,N]   2 (wgrad): a[K,M], b[K,N]
+    act 1: GELU(erf).  act 2: GELU backward - out = bf16(alpha * A @ B + bias) * gelu'(resid), resid = the bf16 pre-activation
+    (multiplied, not added): d(pre) straight out of the output projection's dgrad GEMM."""
     _chk(a, bf16, "gemm a"); _chk(b, bf16, "gemm b")
     if layout == 0:
         M, Kd, Nd = a.shape[0], a.shape[1], b.shape[0]
@@ -460,6 +462,31 @@ def gemm_swiglu(a: torch.Tensor, w_il: torch.Tensor, gu: Optional[torch.Tensor] 
     if timer is not None:
         timer.end()
     return gu, act
+
+
+FUSE_GELU = os.environ.get("DALM_B200_FUSE_GELU", "1") != "0"     # 0: separate gelu_fwd / gelu_bwd kernels (A/B switch)
+
+
+def gemm_gelu(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, pre: Optional[torch.Tensor] = None,
+              act: Optional[torch.Tensor] = None):
+    """intermediate projection of a GELU MLP with the activation in the GEMM epilogue: -> (pre = a w^T + bias, gelu(pre)), both
+    bf16 [M,N], one launch. Bit-identical to gemm(...) followed by gelu_fwd (the activation is taken of the rounded bf16 pre)."""
+    _chk(a, bf16, "gemm_gelu a"); _chk(w, bf16, "gemm_gelu w")
+    M, K = a.shape
+    N = w.shape[0]
+    if bias is not None:
+        _chk(bias, f32, "gemm_gelu bias")
+    if pre is None:
+        pre = torch.empty(M, N, dtype=bf16, device=a.device)
+    if act is None:
+        act = torch.empty(M, N, dtype=bf16, device=a.device)
+    timer = GEMM_TIMER
+    if timer is not None:
+        timer.begin(2.0 * M * N * K, (M, N, K, 0, "bfloat16", "gelu2", "bias" if bias is not None else "-"))
+    _lib.call("dalm_b200_gemm_bf16_gelu", _p(a), _ld(a), _p(w), _ld(w), _p(pre), _ld(pre), _p(act), _ld(act), M, N, K, _p(bias), _stream())
+    if timer is not None:
+        timer.end()
+    return pre, act
 
 
 def gemm_rope(a: torch.Tensor, w: torch.Tensor, cos_t: torch.Tensor, sin_t: torch.Tensor, L: int, rope_cols: int,

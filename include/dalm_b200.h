@@ -95,6 +95,11 @@ int dalm_b200_gemm_bf16_swiglu(const void* A, long long lda, const void* B, long
  * fp32 [L, 64]; output row m is at position m % L. Replaces q_proj / k_proj / v_proj + apply_rotary_pos_emb of HF LlamaAttention. */
 int dalm_b200_gemm_bf16_rope(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo, int M, int N,
                              int K, const float* cos_t, const float* sin_t, int L, int rope_cols, void* stream);
+/* gemm_bf16_gelu: pre[M,N] = A B^T + bias (bf16) AND act[M,N] = gelu_erf(pre) (bf16) from one launch: BertIntermediate
+ * (dense + GELU, HF modeling_bert) / Falcon's dense_h_to_4h + act; the backward multiplies by gelu'(pre) inside the next dgrad
+ * GEMM (gemm_bf16 with act = 2 and resid = pre), so neither direction runs a separate activation kernel. */
+int dalm_b200_gemm_bf16_gelu(const void* A, long long lda, const void* B, long long ldb, void* pre, long long ldpre, void* act,
+                             long long ldact, int M, int N, int K, const float* bias, void* stream);
 void dalm_b200_gemm_clear_cache(void);
 /* tile rasterisation of the persistent GEMM (tuning / test hook): -1 = m-fastest order, 0 = automatic (default: m-fastest
  * while A [M,K] stays L2-resident next to a bf16 output, else bands with a ~square wave footprint walked serpentine),

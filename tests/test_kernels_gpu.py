@@ -416,3 +416,69 @@ def test_gemm_with_fused_rope_epilogue(cuda_dev, B, L, nh, nkv, K):
     ops.rope_(plain, 0, nh + nkv, D, cos_t, sin_t, L)
     assert ((fused.float() - plain.float()).norm() / plain.float().norm()).item() < 6e-3
     assert torch.equal(fused[:, rope_cols:], ops.gemm(x, w)[:, rope_cols:])          # v columns untouched
+
+
+@pytest.mark.parametrize("M,N,K,bias", [(300, 1024, 256, True), (3204, 4096, 1024, True), (260, 72, 136, False), (1000, 18176, 264, False),
+                                        (26700, 4096, 1024, True)])
+def test_gemm_with_fused_gelu_epilogues(cuda_dev, M, N, K, bias):
+    """forward: pre-activation AND gelu(pre) from one launch == GEMM followed by gelu_fwd, bit for bit; backward: the dgrad GEMM
+    with act=2 (x gelu'(pre) in the epilogue) == dgrad GEMM followed by gelu_bwd, bit for bit (TN and NN layouts); both against
+    an fp32 torch reference (HF BertIntermediate: dense -> gelu(erf))"""
+    from dalm_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    x = torch.randn(M, K + 8, generator=g).to(cuda_dev, torch.bfloat16)[:, :K]          # strided view
+    w = (torch.randn(N, K, generator=g) * 0.15).to(cuda_dev, torch.bfloat16)
+    b = torch.randn(N, generator=g).to(cuda_dev) if bias else None
+    pre, act = ops.gemm_gelu(x, w, bias=b)
+    pre_ref = ops.gemm(x, w, bias=b)
+    assert torch.equal(pre, pre_ref)
+    assert torch.equal(act, ops.gelu_fwd(pre_ref))
+    want = x.float() @ w.float().t() + (b if b is not None else 0)
+    assert ((pre.float() - want).norm() / want.norm()).item() < 5e-3
+    wa = torch.nn.functional.gelu(want)
+    assert ((act.float() - wa).norm() / wa.norm()).item() < 5e-3
+    # backward: dy [M,K2] through the output projection W2 [K2, N] (y = act W2^T): d act = dy W2, d pre = d act * gelu'(pre)
+    K2 = 136 if M > 20000 else 264
+    dy = torch.randn(M, K2, generator=g).to(cuda_dev, torch.bfloat16)
+    w2 = (torch.randn(K2, N, generator=g) * 0.1).to(cuda_dev, torch.bfloat16)          # [out=K2, in=N]
+    w2T = w2.t().contiguous()
+    for kw, wt in ((dict(), w2T), (dict(layout=1), w2)):
+        two = ops.gelu_bwd_(pre, ops.gemm(dy, wt, **kw))
+        one = ops.gemm(dy, wt, act=2, resid=pre, **kw)
+        assert torch.equal(one, two)
+    xf = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(xf).backward(dy.float() @ w2.float())
+    assert ((one.float() - xf.grad).norm() / xf.grad.norm()).item() < 8e-3
+    with pytest.raises(Exception):
+        ops.gemm(dy, w2T, act=2)                                      # needs the pre-activation
+    with pytest.raises(Exception):
+        ops.gemm(dy, w2T, act=2, resid=pre.float())                   # ... in bf16
+
+
+def test_gemm_l2_hints_and_raster_modes_do_not_change_results(cuda_dev):
+    """TMA L2 eviction priorities and the raster rule (automatic / bands everywhere / m-fastest) are performance hints only"""
+    from dalm_b200 import _lib, ops
+    g = torch.Generator(device="cpu").manual_seed(99)
+    M, N, K = 2100, 2304, 328
+    a = torch.randn(M, K, generator=g).to(cuda_dev, torch.bfloat16)
+    b = (torch.randn(N, K, generator=g) * 0.1).to(cuda_dev, torch.bfloat16)
+    r = torch.randn(M, N, generator=g).to(cuda_dev)
+    bi = torch.randn(N, generator=g).to(cuda_dev)
+    wg = ops.interleave_gate_up(b[:1152], b[1152:], 128)
+    bT = b.t().contiguous()                                           # [K, N]: the NN layout's B operand
+    lib = _lib.load()
+    base = None
+    try:
+        for raster in (0, -2, -1):
+            for hints in (0, 1, 2, 4, 7):
+                lib.dalm_b200_gemm_set_raster(raster); lib.dalm_b200_gemm_set_l2_hints(hints)
+                got = (ops.gemm(a, b), ops.gemm(a, b, out_dtype=torch.float32, resid=r, max_ctas=11), *ops.gemm_swiglu(a, wg),
+                       *ops.gemm_gelu(a, b, bias=bi), ops.gemm(a, bT, layout=1))
+                if base is None:
+                    base = got
+                    ref = a.float() @ b.float().t()
+                    assert ((got[0].float() - ref).norm() / ref.norm()).item() < 5e-3
+                for x, y in zip(got, base):
+                    assert torch.equal(x, y)
+    finally:
+        lib.dalm_b200_gemm_set_raster(0); lib.dalm_b200_gemm_set_l2_hints(0)
