@@ -224,29 +224,42 @@ def gpu_eager_baseline(dev, host_batches, warmup: int = 5, steps: int = 20):
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of four consecutive
-    generator-forward GEMM launches inside this bench (profiles/r01_gemm_v3_ncu_full_raw.csv: gate|up, down, QKV+LoRA, o_proj
-    at cfg-3 shapes): mean of dram__bytes_read.sum + dram__bytes_write.sum over the captured launches, next to the
-    algorithmic bytes (A + B + output, + the fp32 residual where the epilogue reads one) of the same launches.
+    """DRAM bytes per launch of the dominant kernel from the newest committed `ncu --set full` capture of four consecutive
+    generator-forward GEMM launches of one cfg-3 step (tools/profile_step.py under ncu: QKV+LoRA+RoPE, o_proj, gate|up+SwiGLU, down of
+    decoder layer 1): mean of dram__bytes_read.sum + dram__bytes_write.sum over the captured launches, next to the algorithmic
+    bytes (A + B + every output, + the fp32 residual where the epilogue reads one) of the same launches.
     Returns (bytes_per_launch or None, detail dict)."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01_gemm_v3_ncu_full_raw.csv")
-    shapes = [(4608, 22016, 4096, 2, 0), (4608, 4096, 11008, 4, 4), (4608, 12288, 4112, 2, 0), (4608, 4096, 4096, 4, 4)]   # M,N,K,out B,resid B
-    algo = [2 * (m * k + n * k) + m * n * (ob + rb) for m, n, k, ob, rb in shapes]
-    try:
-        rows = list(csv.reader(open(path)))
-        hdr = rows[0]
-        rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        ur, uw = unit[rows[1][rd]], unit[rows[1][wr]]
-        per = [float(r[rd]) * ur + float(r[wr]) * uw for r in rows[2:] if len(r) > max(rd, wr)]
-        if not per:
-            return None, {"source": "no launches in " + os.path.relpath(path, ROOT)}
-        return sum(per) / len(per), {"source": os.path.relpath(path, ROOT), "launches": len(per), "dram_bytes_per_launch": per,
-                                     "algorithmic_bytes_per_launch": algo[:len(per)],
-                                     "note": "down-proj (2nd) re-reads A on each of its 4 tile waves: 652 MB vs 342 MB"}
-    except Exception as e:
-        return None, {"source": f"unreadable ({type(e).__name__})"}
+    M = 4608
+    # capture file -> [(M, N, K, output bytes per element summed over outputs (x N columns), residual bytes per element)] in launch order
+    captures = [
+        ("r02b_gemm_v5_ncu_full_raw.csv", [(M, 12288, 4112, 2, 0), (M, 4096, 4096, 4, 4), (M, 22016, 4096, 3, 0), (M, 4096, 11008, 4, 4)],
+         "automatic raster + L2 hints; down-proj (4th) stays at ~1.6x: neither 50 MB operand band survives next to the other's stream"),
+        ("r02_gemm_v4_ncu_full_raw.csv", [(M, 12288, 4112, 2, 0), (M, 4096, 4096, 4, 4), (M, 22016, 4096, 3, 0), (M, 4096, 11008, 4, 4)],
+         "round-2a rule (bands for every multi-wave problem): B of QKV / gate|up read once per band"),
+        ("r01_gemm_v3_ncu_full_raw.csv", [(M, 22016, 4096, 2, 0), (M, 4096, 11008, 4, 4), (M, 12288, 4112, 2, 0), (M, 4096, 4096, 4, 4)],
+         "m-fastest everywhere: down-proj (2nd) re-reads A on each of its 4 tile waves"),
+    ]
+    for name, shapes, note in captures:
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        algo = [2 * (m * k + n * k) + m * n * (ob + rb) for m, n, k, ob, rb in shapes]      # gate|up: 2 B (gate|up) + 1 B (act = N/2 cols x 2 B)
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr = rows[0]
+            rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            ur, uw = unit[rows[1][rd]], unit[rows[1][wr]]
+            per = [float(r[rd]) * ur + float(r[wr]) * uw for r in rows[2:] if len(r) > max(rd, wr)]
+            if not per:
+                return None, {"source": "no launches in " + os.path.relpath(path, ROOT)}
+            return sum(per) / len(per), {"source": os.path.relpath(path, ROOT), "launches": len(per), "dram_bytes_per_launch": per,
+                                         "algorithmic_bytes_per_launch": algo[:len(per)],
+                                         "ratio_per_launch": [round(a / b, 3) for a, b in zip(per, algo)], "note": note}
+        except Exception as e:
+            return None, {"source": f"{name} unreadable ({type(e).__name__})"}
+    return None, {"source": "no capture under profiles/"}
 
 
 def trainer_e2e_run(args, rank: int, world: int, cache_dir: str):

@@ -42,6 +42,9 @@ struct GemmEpilogue {
   int fuse;             // 0: none; 1: SwiGLU forward - tile columns [0,128) = gate, [128,256) = up of the same 128 features (weight
                         // rows interleaved); besides `out` (gate|up, the backward's input) the tile's silu(gate)*up goes to tmap_out2
                         // 2: rotary position embedding (head_dim 128, HF rotate_half) on output columns < rope_cols
+                        // 4: SwiGLU backward in the down-projection's dgrad: the accumulator is d(act) [M,F]; with gate / up read from
+                        //    `resid` (= the interleaved gate|up buffer [M,2F], which is also `out`) the tile leaves as
+                        //    d gate = d act * up * s(g)(1 + g(1 - s(g))) and d up = d act * silu(g), written in place over gate / up
                         // 3: GELU forward with both tensors kept - `out` = pre-activation (bf16, what the backward needs),
                         //    tmap_out2 = gelu(pre) (bf16, the next GEMM's operand): one launch instead of GEMM + a 2-pass kernel
   const float* rope_cos; const float* rope_sin;   // fuse == 2: fp32 [rope_L, 64]; the position of output row m is m % rope_L
@@ -214,6 +217,58 @@ __device__ __forceinline__ void epilogue_drain_tile(const GemmEpilogue& ep, cons
         for (int g = 0; g < 4; ++g)
           *reinterpret_cast<bf16x8*>(st + (((h * 4 + g) ^ sw) << 4)) = pack8(f + g * 8);
       }
+    } else if (SPECIAL == 4) {
+      // SwiGLU backward (see GemmEpilogue::fuse): this block = 64 features f0.. of d(act); their gate columns sit at
+      // 256*(f0/128) + f0%128 of the interleaved buffer, the up columns 128 further. Same arithmetic and roundings as
+      // swiglu_bwd_kernel on a bf16 d(act), so the fused launch is bit-identical to the dgrad GEMM + that kernel.
+      const int gcol = ((col0 >> 7) << 8) + (col0 & 127);
+      const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(ep.resid) + (size_t)row * ep.ldr + gcol;
+      bf16x8 pu[8];                                            // d gate goes straight to the staging tile, d up waits in registers
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        bf16x8 gq[4], uq[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          gq[g] = row_ok ? *reinterpret_cast<const bf16x8*>(gp + h * 32 + g * 8) : bf16x8{};
+          uq[g] = row_ok ? *reinterpret_cast<const bf16x8*>(gp + 128 + h * 32 + g * 8) : bf16x8{};
+        }
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + (uint32_t)(c + h * 32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float gg[8], uu[8], dg[8], du[8];
+          unpack8(gq[g], gg);
+          unpack8(uq[g], uu);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float d = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[g * 8 + k]) * ep.alpha));
+            const float sg = 1.f / (1.f + __expf(-gg[k]));
+            const float silu = gg[k] * sg;
+            dg[k] = d * uu[k] * sg * (1.f + gg[k] * (1.f - sg));
+            du[k] = d * silu;
+          }
+          *reinterpret_cast<bf16x8*>(st + (((h * 4 + g) ^ sw) << 4)) = pack8(dg);
+          pu[h * 4 + g] = pack8(du);
+        }
+      }
+      fence_proxy_async();
+      named_bar_sync(1 + grp, 128);
+      if (issuer) {
+        tma_store_2d(tmap_out, tile, gcol, tile_row0);
+        bulk_commit();
+        bulk_wait_read<0>();
+      }
+      named_bar_sync(1 + grp, 128);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) *reinterpret_cast<bf16x8*>(st + ((g ^ sw) << 4)) = pu[g];
+      fence_proxy_async();
+      named_bar_sync(1 + grp, 128);
+      if (issuer) {
+        tma_store_2d(tmap_out, tile, gcol + 128, tile_row0);
+        bulk_commit();
+      }
+      continue;
     } else if (SPECIAL == 3) {
       // GELU forward, both tensors: the 64-column block goes out twice through the same staging tile - first the bf16
       // pre-activation, then gelu() of those ROUNDED values (exactly what gelu_fwd_kernel would read back from HBM).
@@ -720,9 +775,19 @@ static int env_int(const char* name, int dflt) {
 }
 static int g_group_m_override = env_int("DALM_B200_GEMM_RASTER", 0);
 extern "C" void dalm_b200_gemm_set_raster(int group_m) { g_group_m_override = group_m; }
-// TMA L2 eviction hints (GemmEpilogue::l2_hints bit mask); initial value: env DALM_B200_GEMM_L2_HINTS
-static int g_l2_hints = env_int("DALM_B200_GEMM_L2_HINTS", 0);
-extern "C" void dalm_b200_gemm_set_l2_hints(int mask) { g_l2_hints = mask & 7; }
+// TMA L2 eviction hints (GemmEpilogue::l2_hints bit mask): -1 = automatic (default), 0..7 = that mask on every launch.
+// Initial value: env DALM_B200_GEMM_L2_HINTS.
+static int g_l2_hints = env_int("DALM_B200_GEMM_L2_HINTS", -1);
+extern "C" void dalm_b200_gemm_set_l2_hints(int mask) { g_l2_hints = mask < 0 ? -1 : (mask & 7); }
+// Automatic choice, from profiles/r02b_gemm_l2_probe.txt (ncu DRAM bytes + CUDA-event times per raster x hint mask, cfg-3 shapes):
+// in the m-fastest regime (A [M,K] <= 40 MB, bf16 output) "A evict_last, B and stores evict_first" brings DRAM traffic from
+// 1.11-1.19x to 0.96-0.99x of the algorithmic bytes at unchanged time (QKV 289 -> 242 MB, gate|up 622 -> 514, lm_head 663 -> 592);
+// with banded rasters (A too big for L2, or fp32 output + residual streams) every mask cost 2-5 % time and did not cut traffic.
+static int pick_l2_hints(int M, int N, int K, int tile_n, int group_m, bool stream_out) {
+  if (g_l2_hints >= 0) return g_l2_hints;
+  const long long tiles = (long long)((M + 127) / 128) * ((N + tile_n - 1) / tile_n);
+  return (group_m == 0 && tiles > kNumSMs && 2.0 * M * K <= 40e6 && !stream_out) ? 7 : 0;
+}
 
 // tile-shape heuristic: estimated time = waves of 148 CTAs x tile width x an efficiency penalty for narrow tiles (a
 // 128 x BN tile re-reads its A operand from shared memory for every BN columns: profiles/r01_gemm_probe_tiles.jsonl).
@@ -817,7 +882,8 @@ extern "C" int dalm_b200_gemm_bf16(int layout, const void* A, long long lda, con
   DALM_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "gemm: dropout p must be in [0,1)");
   const int group_m = pick_group_m(M, N, K, tile_n, out_f32 != 0 || resid != nullptr);
   GemmEpilogue ep{out, ldo, out_f32, bias, resid, ldr, resid_f32, act, alpha, M, N, K,
-                  make_drop(drop_p, drop_seed, drop_stream_id, drop_offset), group_m, 0, nullptr, nullptr, 0, 0, g_l2_hints};
+                  make_drop(drop_p, drop_seed, drop_stream_id, drop_offset), group_m, 0, nullptr, nullptr, 0, 0,
+                  pick_l2_hints(M, N, K, tile_n, group_m, out_f32 != 0 || resid != nullptr)};
   cudaStream_t st = (cudaStream_t)stream;
   if (bn == 2256) return launch_gemm2<256>(ta, tb, to, ep, max_ctas, st);
   if (bn == 3256) return launch_gemm2<256, 3>(ta, tb, to, ep, max_ctas, st);     // tuning probes (fewer stages)
@@ -850,8 +916,25 @@ extern "C" int dalm_b200_gemm_bf16_swiglu(const void* A, long long lda, const vo
   if (int e = get_tmap(gu, M, N, ldgu, 128, &to, 0)) return e;
   if (int e = get_tmap(act, M, N / 2, ldact, 128, &to2, 0)) return e;
   const int group_m = pick_group_m(M, N, K, 256, false);
-  GemmEpilogue ep{gu, ldgu, 0, nullptr, nullptr, 0, 0, 0, 1.f, M, N, K, make_drop(0.f, 0, 0, nullptr), group_m, 1, nullptr, nullptr, 0, 0, g_l2_hints};
+  GemmEpilogue ep{gu, ldgu, 0, nullptr, nullptr, 0, 0, 0, 1.f, M, N, K, make_drop(0.f, 0, 0, nullptr), group_m, 1, nullptr, nullptr, 0, 0,
+                  pick_l2_hints(M, N, K, 256, group_m, false)};
   return launch_gemm<256>(ta, tb, to, ep, 0, (cudaStream_t)stream, &to2);
+}
+
+// down-projection dgrad of LlamaMLP with the SwiGLU backward in its epilogue: d(act) = dY WdT^T never reaches HBM; the interleaved
+// gate|up buffer of the forward (gemm_bf16_swiglu) is overwritten in place with [d gate | d up] (what swiglu_bwd produced).
+extern "C" int dalm_b200_gemm_bf16_swiglu_bwd(const void* dY, long long lddy, const void* WdT, long long ldw, void* gu, long long ldgu,
+                                              int M, int F, int K, void* stream) {
+  DALM_REQUIRE(M > 0 && K > 0 && F >= 256 && (F % 128) == 0, "gemm_swiglu_bwd: F=%d must be >= 256 and a multiple of 128 (interleave block)", F);
+  DALM_REQUIRE((K % 8) == 0 && lddy >= K && ldw >= K && ldgu >= 2LL * F && (ldgu % 8) == 0 && ((uintptr_t)gu & 15) == 0,
+               "gemm_swiglu_bwd: bad K / leading dimensions / alignment");
+  CUtensorMap ta, tb, to;
+  if (int e = get_tmap(dY, M, K, lddy, 128, &ta)) return e;
+  if (int e = get_tmap(WdT, F, K, ldw, 256, &tb)) return e;
+  if (int e = get_tmap(gu, M, 2LL * F, ldgu, 128, &to, 0)) return e;
+  const int group_m = pick_group_m(M, F, K, 256, false);
+  GemmEpilogue ep{gu, ldgu, 0, nullptr, gu, ldgu, 0, 0, 1.f, M, F, K, make_drop(0.f, 0, 0, nullptr), group_m, 4, nullptr, nullptr, 0, 0, 0};   // in-place output: no hints
+  return launch_gemm<256, 0, 4>(ta, tb, to, ep, 0, (cudaStream_t)stream);
 }
 
 // intermediate projection of a GELU MLP (BertIntermediate, Falcon dense_h_to_4h) with the activation fused into the epilogue and
@@ -868,7 +951,8 @@ extern "C" int dalm_b200_gemm_bf16_gelu(const void* A, long long lda, const void
   if (int e = get_tmap(pre, M, N, ldpre, 128, &to, 0)) return e;
   if (int e = get_tmap(act, M, N, ldact, 128, &to2, 0)) return e;
   const int group_m = pick_group_m(M, N, K, bn, false);
-  GemmEpilogue ep{pre, ldpre, 0, bias, nullptr, 0, 0, 0, 1.f, M, N, K, make_drop(0.f, 0, 0, nullptr), group_m, 3, nullptr, nullptr, 0, 0, g_l2_hints};
+  GemmEpilogue ep{pre, ldpre, 0, bias, nullptr, 0, 0, 0, 1.f, M, N, K, make_drop(0.f, 0, 0, nullptr), group_m, 3, nullptr, nullptr, 0, 0,
+                  pick_l2_hints(M, N, K, bn, group_m, false)};
   cudaStream_t st = (cudaStream_t)stream;
   if (bn == 256) return launch_gemm<256, 0, 3>(ta, tb, to, ep, 0, st, &to2);
   if (bn == 128) return launch_gemm<128, 0, 3>(ta, tb, to, ep, 0, st, &to2);
@@ -888,7 +972,8 @@ extern "C" int dalm_b200_gemm_bf16_rope(const void* A, long long lda, const void
   if (int e = get_tmap(B, N, K, ldb, 256, &tb)) return e;
   if (int e = get_tmap(out, M, N, ldo, 128, &to, 0)) return e;
   const int group_m = pick_group_m(M, N, K, 256, false);
-  GemmEpilogue ep{out, ldo, 0, nullptr, nullptr, 0, 0, 0, 1.f, M, N, K, make_drop(0.f, 0, 0, nullptr), group_m, 2, cos_t, sin_t, L, rope_cols, g_l2_hints};
+  GemmEpilogue ep{out, ldo, 0, nullptr, nullptr, 0, 0, 0, 1.f, M, N, K, make_drop(0.f, 0, 0, nullptr), group_m, 2, cos_t, sin_t, L, rope_cols,
+                  pick_l2_hints(M, N, K, 256, group_m, false)};
   return launch_gemm<256>(ta, tb, to, ep, 0, (cudaStream_t)stream);
 }
 

@@ -53,9 +53,90 @@ __global__ void nf4_roundtrip_kernel(float* __restrict__ w, long long n, unsigne
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// 4-bit STORAGE (DALM_B200_NF4_STORAGE=1): what bitsandbytes keeps resident - two codes per byte (first element in the high
+// nibble, as bnb's kQuantizeBlockwise packs them) + one fp32 absmax per 64-element block = 0.5625 B per parameter instead of
+// the 2 B (4 B with the resident transpose) of the dequantised-resident default. A weight is expanded to bf16 right before
+// the GEMM that needs it (bnb does the same in its forward: dequantize_4bit -> matmul), into a scratch shared by all layers.
+// ---------------------------------------------------------------------------------------------------------------------
+// one warp per 64-element block; lane l owns elements 2l, 2l+1 -> one packed byte
+__global__ void nf4_quantize_kernel(const float* __restrict__ w, long long n, unsigned char* __restrict__ packed, float* __restrict__ absmax) {
+  const long long blk = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long base = blk * 64;
+  if (base >= n) return;
+  float v[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const long long i = base + 2 * lane + j;
+    v[j] = i < n ? __half2float(__float2half_rn(w[i])) : 0.f;          // the checkpoint is cast to fp16 before quantisation
+  }
+  float m = fmaxf(fabsf(v[0]), fabsf(v[1]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const float inv = 1.0f / m;
+  if (lane == 0) absmax[blk] = m;
+  const int q0 = m > 0.f ? nf4_index(v[0] * inv) : 7, q1 = m > 0.f ? nf4_index(v[1] * inv) : 7;
+  const long long i0 = base + 2 * lane;
+  if (i0 < n) packed[i0 >> 1] = (unsigned char)((q0 << 4) | (i0 + 1 < n ? q1 : 7));
+}
+
+// bf16 out[r, c] = bf16(fp16(code * absmax))  (the value the dequantised-resident mode keeps), 16 codes per thread; a row's
+// `tail_cols` extra columns (the LoRA block of a K-augmented weight) are copied from `tail`
+__global__ void nf4_dequant_bf16_kernel(const unsigned char* __restrict__ packed, const float* __restrict__ absmax, long long rows,
+                                        int cols, __nv_bfloat16* __restrict__ out, long long ldo,
+                                        const __nv_bfloat16* __restrict__ tail, long long ldt, int tail_cols) {
+  const int groups = cols >> 4;                                         // 16-code groups per row
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long r = t / (groups + 1);
+  const int gi = (int)(t - r * (groups + 1));
+  if (r >= rows) return;
+  if (gi == groups) {                                                   // this row's tail
+    for (int c = 0; c < tail_cols; ++c) out[r * ldo + cols + c] = tail[r * ldt + c];
+    return;
+  }
+  const long long e0 = r * cols + (long long)gi * 16;                   // first element (flattened row-major weight)
+  const uint2 raw = *reinterpret_cast<const uint2*>(packed + (e0 >> 1));
+  const float m = absmax[e0 >> 6];
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(&raw);
+  float f[16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    f[2 * i]     = __half2float(__float2half_rn(kNF4Code[b[i] >> 4] * m));
+    f[2 * i + 1] = __half2float(__float2half_rn(kNF4Code[b[i] & 15] * m));
+  }
+  __nv_bfloat16* o = out + r * ldo + (long long)gi * 16;
+  *reinterpret_cast<bf16x8*>(o) = pack8(f);
+  *reinterpret_cast<bf16x8*>(o + 8) = pack8(f + 8);
+}
+
 }  // namespace dalm
 
 using namespace dalm;
+
+// w: fp32 [n] (row-major weight, flattened) -> packed codes uint8 [ceil(n/2)] + absmax fp32 [ceil(n/64)]
+extern "C" int dalm_b200_nf4_quantize(const float* w, long long n, void* packed, float* absmax, void* stream) {
+  DALM_REQUIRE(n > 0 && w && packed && absmax, "nf4_quantize: empty tensor / null output");
+  const long long threads = ((n + 63) / 64) * 32;
+  nf4_quantize_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, n, (unsigned char*)packed, absmax);
+  count_launch();
+  return check_launch("nf4_quantize_kernel");
+}
+
+// packed / absmax of a [rows, cols] weight (cols % 64 == 0: blocks never straddle rows) -> bf16 out[rows, ldo] columns [0, cols);
+// tail (bf16 [rows, ldt], may be NULL) is copied into columns [cols, cols + tail_cols)
+extern "C" int dalm_b200_nf4_dequant_bf16(const void* packed, const float* absmax, long long rows, int cols, void* out, long long ldo,
+                                          const void* tail, long long ldt, int tail_cols, void* stream) {
+  DALM_REQUIRE(rows > 0 && cols > 0 && (cols % 64) == 0, "nf4_dequant: cols=%d must be a positive multiple of 64", cols);
+  DALM_REQUIRE(ldo >= cols + tail_cols && (ldo % 8) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)packed & 7) == 0,
+               "nf4_dequant: output stride / alignment");
+  DALM_REQUIRE(tail_cols == 0 || (tail != nullptr && ldt >= tail_cols), "nf4_dequant: tail");
+  const long long threads = rows * ((cols >> 4) + 1);
+  nf4_dequant_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const unsigned char*)packed, absmax, rows, cols, (__nv_bfloat16*)out, ldo, (const __nv_bfloat16*)tail, ldt, tail_cols);
+  count_launch();
+  return check_launch("nf4_dequant_bf16_kernel");
+}
 
 // w: fp32 [n] (a row-major weight, flattened) overwritten with its NF4 round trip. codes (uint8 [n]) and absmax
 // (fp32 [ceil(n/64)]) are optional outputs for inspection / tests.

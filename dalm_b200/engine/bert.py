@@ -44,12 +44,19 @@ class BertEncoder(torch.nn.Module):
     LORA_TARGETS = ("query", "key", "value")          # reference rag_e2e_base_model.py:66-68
 
     def __init__(self, cfg: Dict, state_dict: Dict[str, torch.Tensor], device="cuda", lora: bool = False,
-                 lora_seed: int = 0, full: bool = False):
+                 lora_seed: int = 0, full: bool = False, nf4_storage: bool = False):
         """lora: PEFT mode (base frozen, rank-8 adapters on query/key/value). full: every parameter trainable (the
-        reference's behaviour without --use-peft): weights live in a DenseBank, no transposed copies are kept."""
+        reference's behaviour without --use-peft): weights live in a DenseBank, no transposed copies are kept.
+        nf4_storage: use_bnb with 4-bit storage (engine/nf4store.py) - `state_dict` holds the ORIGINAL checkpoint values."""
         super().__init__()
         if lora and full:
             raise ValueError("lora and full fine-tuning are mutually exclusive for one model")
+        if nf4_storage and full:
+            raise ValueError("4-bit base weights cannot be fully fine-tuned")
+        self.nf4 = None
+        if nf4_storage:
+            from .nf4store import Nf4Store
+            self.nf4 = Nf4Store(device)
         self.cfg = cfg
         self.H = H = cfg["hidden_size"]
         self.F = F = cfg["intermediate_size"]
@@ -64,7 +71,10 @@ class BertEncoder(torch.nn.Module):
         self.r = 8
         self.Ra = 3 * self.r if lora else 0
         sd = {k[len("bert."):] if k.startswith("bert.") else k: v for k, v in state_dict.items()}
-        g = lambda k, dt: sd[k].to(device=self.dev, dtype=dt).contiguous()
+        if self.nf4 is not None:                              # everything that is not an nn.Linear weight: transformers' fp16 cast
+            g = lambda k, dt: sd[k].to(device=self.dev, dtype=torch.float16).to(dt).contiguous()
+        else:
+            g = lambda k, dt: sd[k].to(device=self.dev, dtype=dt).contiguous()
         self.full: Optional[DenseBank] = None
         self.layers: List[Dict[str, torch.Tensor]] = []
         if full:
@@ -187,7 +197,15 @@ class BertEncoder(torch.nn.Module):
             raise RuntimeError("enable_lora: this encoder is being fully fine-tuned; adapters attach to frozen bases only")
         H, r = self.H, self.r
         self.Ra = 3 * r
-        for W in self.layers:
+        for li, W in enumerate(self.layers):
+            if self.nf4 is not None:                             # 4-bit storage: give the packed q|k|v weight its LoRA tail block
+                packed, absmax, rows, cols = self.nf4.q[(li, "Wqkv_aug")]
+                self.nf4.tails[(li, "Wqkv_aug")] = torch.zeros(rows, self.Ra, dtype=bf16, device=self.dev)
+                if self.nf4.slots["Wqkv_aug"].shape[1] < cols + 64:
+                    self.nf4.slots["Wqkv_aug"] = torch.empty(rows, cols + 64, dtype=bf16, device=self.dev)
+                W["A_stack"] = torch.zeros(64, H, dtype=bf16, device=self.dev)
+                W["Bblk"] = torch.zeros(64, 3 * H, dtype=bf16, device=self.dev)
+                continue
             old, oldT = W["Wqkv_aug"], W["WqkvT_aug"]
             W["Wqkv_aug"] = _aug_buf(3 * H, H, self.Ra, self.dev, zero=True)
             W["Wqkv_aug"][:, :H] = old[:, :H]
@@ -208,7 +226,7 @@ class BertEncoder(torch.nn.Module):
         """dx = dy W: against the resident transposed copy (frozen base) or W[out,in] itself read MN-major (full mode).
         gelu_pre: the result is a gradient w.r.t. gelu(pre) - multiply by gelu'(pre) in the epilogue (-> gradient w.r.t. pre)"""
         kw = dict(act=2, resid=gelu_pre) if gelu_pre is not None else {}
-        if self.full is not None:
+        if self.full is not None or self.nf4 is not None:
             return ops.gemm(dy, W[name], layout=1, **kw)
         return ops.gemm(dy, W[name + "T"], **kw)
 
@@ -221,6 +239,9 @@ class BertEncoder(torch.nn.Module):
         self.emb_b = g("embeddings.LayerNorm.bias", f32)
         for l in range(self.nl):
             p = f"encoder.layer.{l}."
+            if self.nf4 is not None:
+                self.layers.append(self._init_layer_nf4(sd, l, g, lora))
+                continue
             W = {}
             wq, wk, wv = (g(p + f"attention.self.{n}.weight", bf16) for n in self.LORA_TARGETS)
             W["Wqkv_aug"] = _aug_buf(3 * H, H, self.Ra, self.dev, zero=True)
@@ -246,6 +267,28 @@ class BertEncoder(torch.nn.Module):
             W["ln2_b"] = g(p + "output.LayerNorm.bias", f32)
             self.layers.append(W)
 
+    def _init_layer_nf4(self, sd, l: int, g, lora: bool):
+        """one layer in 4-bit storage (q|k|v fused row-wise, attention.output.dense, intermediate.dense, output.dense as NF4
+        codes; biases / LayerNorms through the fp16 cast)"""
+        from .nf4store import QuantLayer
+        p = f"encoder.layer.{l}."
+        H = self.H
+        raw = lambda k: sd[k].to(device=self.dev, dtype=f32)
+        W = QuantLayer(self.nf4, l)
+        self.nf4.put(l, "Wqkv_aug", torch.cat([raw(p + f"attention.self.{n}.weight") for n in self.LORA_TARGETS], 0), tail_cols=self.Ra)
+        self.nf4.put(l, "Wo", raw(p + "attention.output.dense.weight"))
+        self.nf4.put(l, "Wi", raw(p + "intermediate.dense.weight"))
+        self.nf4.put(l, "Wo2", raw(p + "output.dense.weight"))
+        W["bqkv"] = torch.cat([g(p + f"attention.self.{n}.bias", f32) for n in self.LORA_TARGETS])
+        if lora:
+            W["A_stack"] = torch.zeros(64, H, dtype=bf16, device=self.dev)
+            W["Bblk"] = torch.zeros(64, 3 * H, dtype=bf16, device=self.dev)
+        for k, n in (("bo", "attention.output.dense.bias"), ("ln1_g", "attention.output.LayerNorm.weight"),
+                     ("ln1_b", "attention.output.LayerNorm.bias"), ("bi", "intermediate.dense.bias"), ("bo2", "output.dense.bias"),
+                     ("ln2_g", "output.LayerNorm.weight"), ("ln2_b", "output.LayerNorm.bias")):
+            W[k] = g(p + n, f32)
+        return W
+
     def _drop(self, p: float, call: int, layer: int, site: int):
         """dropout descriptor of one site, or None when inactive (eval mode / p == 0)"""
         if not self.training or p <= 0.0:
@@ -259,8 +302,11 @@ class BertEncoder(torch.nn.Module):
             for j, n in enumerate(self.LORA_TARGETS):
                 name = f"encoder.layer.{l}.attention.self.{n}"
                 A, B = self.lora.A[name], self.lora.B[name]             # [r,H], [H,r] fp32
-                yield (B, r, 1, W["Wqkv_aug"][j * H:(j + 1) * H, H + j * r:], H, r, s)      # (alpha/r) * B
-                yield (A, 1, H, W["WqkvT_aug"][:, 3 * H + j * r:], H, r, 1.0)                # A^T
+                if self.nf4 is not None:                                 # 4-bit storage: LoRA columns live in the layer's tail block
+                    yield (B, r, 1, self.nf4.tail(l, "Wqkv_aug")[j * H:(j + 1) * H, j * r:], H, r, s)
+                else:
+                    yield (B, r, 1, W["Wqkv_aug"][j * H:(j + 1) * H, H + j * r:], H, r, s)      # (alpha/r) * B
+                    yield (A, 1, H, W["WqkvT_aug"][:, 3 * H + j * r:], H, r, 1.0)                # A^T
                 yield (A, H, 1, W["A_stack"][j * r:(j + 1) * r], r, H, 1.0)                  # A
                 yield (B, 1, r, W["Bblk"][j * r:(j + 1) * r, j * H:], r, H, s)               # (alpha/r) * B^T, block j
 
@@ -325,7 +371,7 @@ class BertEncoder(torch.nn.Module):
                           drop=self._drop(self.p_hidden, call, li, 1))
             h_aug = torch.empty(M, H, dtype=bf16, device=self.dev)
             h32, _, m1, r1 = ops.layernorm_fwd(z1, W["ln1_g"], W["ln1_b"], self.eps, y16=h_aug)
-            if ops.FUSE_GELU:
+            if ops.fuse_gelu(H):
                 pre, act = ops.gemm_gelu(h_aug, W["Wi"], bias=W["bi"])                             # [M,F] pre-activation AND gelu(pre): one launch
             else:
                 pre = ops.gemm(h_aug, W["Wi"], bias=W["bi"])
@@ -380,7 +426,7 @@ class BertEncoder(torch.nn.Module):
             if bank is not None:                               # output.dense: dW = dz2^T act, db = colsum(dz2)
                 ops.wgrad_(dz2_16, a.act, G(l, "Wo2"), acc)
                 ops.col_reduce_(dy_bf16=dz2_16, out_sum=G(l, "bo2"))
-            if ops.FUSE_GELU:
+            if ops.fuse_gelu(H):
                 dact = self._dgrad(dz2_16, W, "Wo2", gelu_pre=a.pre)                               # d(pre): gelu' applied in the dgrad epilogue
             else:
                 dact = self._dgrad(dz2_16, W, "Wo2")
@@ -424,7 +470,10 @@ class BertEncoder(torch.nn.Module):
                                 self.lora.scale)
             if l == 0:
                 return
-            if xdrop is None:
+            if self.nf4 is not None:                                              # expanded W[out,in] read MN-major + (g A)
+                dx_16 = ops.gemm(dqkv_aug[:, :3 * H], W["Wqkv_aug"][:, :H], layout=1)
+                ops.lora_dx_(dx_16, dqkv_aug[:, 3 * H:], W["A_stack"], K=H, R=Ra, drop=xdrop)
+            elif xdrop is None:
                 dx_16 = ops.gemm(dqkv_aug, W["WqkvT_aug"])                        # LoRA's A-path folded into K
             else:
                 dx_16 = ops.gemm(dqkv_aug[:, :3 * H], W["WqkvT_aug"][:, :3 * H])   # base path only ...

@@ -180,7 +180,7 @@ class FalconDecoder(torch.nn.Module):
                                      mask, B, L, self.nh, 1, self.hd, causal=True)
         t = ops.gemm(att, W["Wd"], out_dtype=f32, resid=x)                            # x + attention branch
         if keep:
-            if ops.FUSE_GELU:
+            if ops.fuse_gelu(self.H):
                 pre, h4 = ops.gemm_gelu(h, W["W1"])                                   # GELU's input (needed by its backward) and output, one launch
             else:
                 pre = ops.gemm(h, W["W1"])
@@ -201,7 +201,7 @@ class FalconDecoder(torch.nn.Module):
         G = lambda n: bank.g(f"L{l}.{n}")
         # MLP branch
         ops.wgrad_(dx16, a.h4, G("W2"), acc)
-        if ops.FUSE_GELU:
+        if ops.fuse_gelu(self.H):
             dpre = ops.gemm(dx16, W["W2"], layout=1, act=2, resid=a.pre)              # [M,4H] = d h4 * gelu'(pre) = d pre
         else:
             dpre = ops.gemm(dx16, W["W2"], layout=1)                                  # [M,4H] = d h4

@@ -41,12 +41,20 @@ class LlamaDecoder(torch.nn.Module):
     LORA_TARGETS = ("q_proj", "v_proj")               # reference rag_e2e_base_model.py:76-77
 
     def __init__(self, cfg: Dict, state_dict: Dict[str, torch.Tensor], device="cuda", lora: bool = False,
-                 lora_seed: int = 1, full: bool = False):
+                 lora_seed: int = 1, full: bool = False, nf4_storage: bool = False):
         """lora: PEFT mode (frozen base + rank-8 adapters on q_proj / v_proj). full: every parameter trainable (reference
         behaviour without --use-peft): weights in a DenseBank (fp32 master + bf16 shadow), no transposed copies."""
         super().__init__()
         if lora and full:
             raise ValueError("lora and full fine-tuning are mutually exclusive for one model")
+        if nf4_storage and full:
+            raise ValueError("4-bit base weights cannot be fully fine-tuned")
+        # use_bnb with 4-bit STORAGE (engine/nf4store.py): `state_dict` then holds the ORIGINAL checkpoint values; the layers'
+        # Linear weights are kept as NF4 codes and expanded to bf16 per use, everything else takes transformers' fp16 cast
+        self.nf4 = None
+        if nf4_storage:
+            from .nf4store import Nf4Store
+            self.nf4 = Nf4Store(device)
         self.cfg = cfg
         self.H = H = cfg["hidden_size"]
         self.F = F = cfg["intermediate_size"]
@@ -66,7 +74,10 @@ class LlamaDecoder(torch.nn.Module):
         self.r = 8
         self.Ra = 2 * self.r if lora else 0
         sd = state_dict
-        g = lambda k, dt: sd[k].to(device=self.dev, dtype=dt).contiguous()
+        if self.nf4 is not None:
+            g = lambda k, dt: sd[k].to(device=self.dev, dtype=torch.float16).to(dt).contiguous()
+        else:
+            g = lambda k, dt: sd[k].to(device=self.dev, dtype=dt).contiguous()
         self.Vp = (self.V + 7) // 8 * 8                       # GEMM N granularity; extra rows are zero and never scored
         self.full: Optional[DenseBank] = None
         self.layers: List[Dict[str, torch.Tensor]] = []
@@ -189,7 +200,15 @@ class LlamaDecoder(torch.nn.Module):
             raise RuntimeError("enable_lora: this decoder is being fully fine-tuned; adapters attach to frozen bases only")
         H, r = self.H, self.r
         self.Ra = 2 * r
-        for W in self.layers:
+        for li, W in enumerate(self.layers):
+            if self.nf4 is not None:                             # 4-bit storage: give the packed q|k|v weight its LoRA tail block
+                packed, absmax, rows, cols = self.nf4.q[(li, "Wqkv_aug")]
+                self.nf4.tails[(li, "Wqkv_aug")] = torch.zeros(rows, self.Ra, dtype=bf16, device=self.dev)
+                if self.nf4.slots["Wqkv_aug"].shape[1] < cols + 64:
+                    self.nf4.slots["Wqkv_aug"] = torch.empty(rows, cols + 64, dtype=bf16, device=self.dev)
+                W["A_stack"] = torch.zeros(64, H, dtype=bf16, device=self.dev)
+                W["Bblk"] = torch.zeros(64, self.Nqkv, dtype=bf16, device=self.dev)
+                continue
             old, oldT = W["Wqkv_aug"], W["WqkvT_aug"]
             W["Wqkv_aug"] = _aug_buf(self.Nqkv, H, self.Ra, self.dev, zero=True)
             W["Wqkv_aug"][:, :H] = old[:, :H]
@@ -208,7 +227,7 @@ class LlamaDecoder(torch.nn.Module):
         self.repack_lora()
 
     def _dgrad(self, dy: torch.Tensor, W: Dict[str, torch.Tensor], name: str) -> torch.Tensor:
-        if self.full is not None:
+        if self.full is not None or self.nf4 is not None:        # W[out,in] read MN-major: no transposed copy in these modes
             return ops.gemm(dy, W[name], layout=1)
         return ops.gemm(dy, W[name + "T"])
 
@@ -224,6 +243,9 @@ class LlamaDecoder(torch.nn.Module):
         H_, Ra = H, self.Ra
         for l in range(self.nl):
             p = f"model.layers.{l}."
+            if self.nf4 is not None:
+                self.layers.append(self._init_layer_nf4(sd, l, g, lora))
+                continue
             W = {}
             wqkv = torch.cat([g(p + "self_attn.q_proj.weight", bf16), g(p + "self_attn.k_proj.weight", bf16),
                               g(p + "self_attn.v_proj.weight", bf16)], 0)
@@ -248,6 +270,26 @@ class LlamaDecoder(torch.nn.Module):
             W["g2"] = g(p + "post_attention_layernorm.weight", f32)
             self.layers.append(W)
 
+    def _init_layer_nf4(self, sd, l: int, g, lora: bool):
+        """one layer in 4-bit storage: q|k|v, o, gate|up (interleaved like the resident mode), down as NF4 codes; blocks of 64
+        run along the input features, so fusing / interleaving ROWS leaves every block (and its absmax) what bitsandbytes
+        computes for the separate nn.Linear weights"""
+        from .nf4store import QuantLayer
+        p = f"model.layers.{l}."
+        raw = lambda k: sd[k].to(device=self.dev, dtype=f32)
+        W = QuantLayer(self.nf4, l)
+        self.nf4.put(l, "Wqkv_aug", torch.cat([raw(p + f"self_attn.{n}_proj.weight") for n in "qkv"], 0), tail_cols=self.Ra)
+        self.nf4.put(l, "Wo", raw(p + "self_attn.o_proj.weight"))
+        gate, up = raw(p + "mlp.gate_proj.weight"), raw(p + "mlp.up_proj.weight")
+        self.nf4.put(l, "Wgu", ops.interleave_gate_up(gate, up, self.gu_il) if self.gu_il else torch.cat([gate, up], 0))
+        self.nf4.put(l, "Wd", raw(p + "mlp.down_proj.weight"))
+        if lora:
+            W["A_stack"] = torch.zeros(64, self.H, dtype=bf16, device=self.dev)
+            W["Bblk"] = torch.zeros(64, self.Nqkv, dtype=bf16, device=self.dev)
+        W["g1"] = g(p + "input_layernorm.weight", f32)
+        W["g2"] = g(p + "post_attention_layernorm.weight", f32)
+        return W
+
     def _drop(self, training: bool, call: int, layer: int):
         if not training or self.p_lora <= 0.0:
             return None
@@ -264,8 +306,11 @@ class LlamaDecoder(torch.nn.Module):
                 name = f"model.layers.{l}.self_attn.{n}"
                 A, B = self.lora.A[name], self.lora.B[name]             # [r,H], [out,r]
                 c0, w = self._target_cols(n)
-                yield (B, r, 1, W["Wqkv_aug"][c0:c0 + w, H + j * r:], w, r, s)
-                yield (A, 1, H, W["WqkvT_aug"][:, self.Nqkv + j * r:], H, r, 1.0)
+                if self.nf4 is not None:                                 # 4-bit storage: the LoRA columns live in the layer's tail block
+                    yield (B, r, 1, self.nf4.tail(l, "Wqkv_aug")[c0:c0 + w, j * r:], w, r, s)
+                else:
+                    yield (B, r, 1, W["Wqkv_aug"][c0:c0 + w, H + j * r:], w, r, s)
+                    yield (A, 1, H, W["WqkvT_aug"][:, self.Nqkv + j * r:], H, r, 1.0)
                 yield (A, H, 1, W["A_stack"][j * r:(j + 1) * r], r, H, 1.0)
                 yield (B, 1, r, W["Bblk"][j * r:(j + 1) * r, c0:], r, w, s)
 
@@ -468,8 +513,11 @@ class LlamaDecoder(torch.nn.Module):
             W, a = self.layers[l], ctx.layers[l]
             if bank is not None:
                 ops.wgrad_(dx16, a.act, G(l, "Wd"), acc)
-            dact = self._dgrad(dx16, W, "Wd")                                      # [M,F]
-            ops.swiglu_bwd_(a.gu, dact, F, interleave=self.gu_il)                  # gu <- [dgate | dup] (same layout as gu)
+            if bank is None and self.nf4 is None and self.gu_il == 128 and F >= 256 and ops.FUSE_SWIGLU_BWD:
+                ops.gemm_swiglu_bwd_(dx16, W["WdT"], a.gu)                         # d(act) stays in TMEM; gu <- [dgate | dup] in the epilogue
+            else:
+                dact = self._dgrad(dx16, W, "Wd")                                  # [M,F]
+                ops.swiglu_bwd_(a.gu, dact, F, interleave=self.gu_il)              # gu <- [dgate | dup] (same layout as gu)
             if bank is not None:
                 ops.wgrad_(a.gu, a.h2, G(l, "Wgu"), acc)
             dh2 = self._dgrad(a.gu, W, "Wgu")                                      # [M,H]
@@ -505,7 +553,10 @@ class LlamaDecoder(torch.nn.Module):
                 ops.lora_wgrad_(dqkv[:, c0:c0 + w], a.h1_aug[:, H + j * r:], self.lora.gB[names[j]], 1, r, w, r, self.lora.scale)
             if l == 0:
                 break                                                              # embeddings frozen
-            if xdrop is None:
+            if self.nf4 is not None:                                               # base path against the expanded W[out,in] + (g A)
+                dh1 = ops.gemm(dqkv[:, :self.Nqkv], W["Wqkv_aug"][:, :H], layout=1)
+                ops.lora_dx_(dh1, dqkv[:, self.Nqkv:], W["A_stack"], K=H, R=Ra, drop=xdrop)
+            elif xdrop is None:
                 dh1 = ops.gemm(dqkv, W["WqkvT_aug"])                               # [M,H], LoRA's A-path folded into K
             else:
                 dh1 = ops.gemm(dqkv[:, :self.Nqkv], W["WqkvT_aug"][:, :self.Nqkv])

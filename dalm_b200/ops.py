@@ -106,9 +106,11 @@ def ce_marginal(logits: torch.Tensor, ids: torch.Tensor, mask: torch.Tensor, nsu
         if inplace:
             dl = logits
         else:
-            dl = torch.empty_strided(logits.shape, logits.stride(), dtype=logits.dtype, device=logits.device)
+            # whole padded rows are allocated (a [B,L,V] view of them is returned): the head's dgrad reads all ld columns
+            base = torch.empty(B * L, ld, dtype=logits.dtype, device=logits.device)
             if ld != V:
-                torch.as_strided(dl, (B * L, ld), (ld, 1), dl.storage_offset()).zero_()
+                base.zero_()
+            dl = torch.as_strided(base, (B, L, V), (L * ld, ld, 1))
     _lib.call("dalm_b200_ce_marginal_fwd_bwd", _p(logits), _p(dl), 0 if logits.dtype == bf16 else 1, _p(ids), _p(mask),
               _p(nsum), _p(tok_lp), B, L, V, ld, float(grad_out), _stream())
     return tok_lp, dl
@@ -464,7 +466,33 @@ def gemm_swiglu(a: torch.Tensor, w_il: torch.Tensor, gu: Optional[torch.Tensor] 
     return gu, act
 
 
-FUSE_GELU = os.environ.get("DALM_B200_FUSE_GELU", "1") != "0"     # 0: separate gelu_fwd / gelu_bwd kernels (A/B switch)
+# GELU in the GEMM epilogues pays only when the tile's mainloop is long enough to hide the erf / exp work of the 256 epilogue
+# threads: measured at cfg-2 (bge-large, K = 1024: 16 k-blocks per tile) the fused launches cost 10.6 ms more GEMM time than the
+# 7.1 ms of stand-alone gelu kernels they remove (profiles/r02b_bench_ab.jsonl) - so the fusion is taken from K >= 2048 (Falcon's
+# 4544-wide MLP), and BERT keeps the separate kernels. DALM_B200_FUSE_GELU_MIN_K overrides (0 = always, huge = never).
+FUSE_GELU_MIN_K = int(os.environ.get("DALM_B200_FUSE_GELU_MIN_K", "2048"))
+
+
+def fuse_gelu(K: int) -> bool:
+    return K >= FUSE_GELU_MIN_K
+FUSE_SWIGLU_BWD = os.environ.get("DALM_B200_FUSE_SWIGLU_BWD", "1") != "0"   # 0: down-proj dgrad GEMM + swiglu_bwd kernel
+
+
+def gemm_swiglu_bwd_(dy: torch.Tensor, wdT: torch.Tensor, gu: torch.Tensor) -> torch.Tensor:
+    """LlamaMLP backward through down_proj and SiLU(gate) * up in one launch: dy [M,H] (gradient of the MLP output), wdT [F,H]
+    (down_proj weight transposed), gu [M,2F] = gate|up interleaved in 128-feature blocks -> overwritten with [d gate | d up]."""
+    _chk(dy, bf16, "gemm_swiglu_bwd dy"); _chk(wdT, bf16, "gemm_swiglu_bwd w"); _chk(gu, bf16, "gemm_swiglu_bwd gu")
+    M, K = dy.shape
+    F = wdT.shape[0]
+    if gu.shape != (M, 2 * F):
+        raise _lib.DalmB200Error(f"gemm_swiglu_bwd: gu {tuple(gu.shape)} is not [{M}, {2 * F}]")
+    timer = GEMM_TIMER
+    if timer is not None:
+        timer.begin(2.0 * M * F * K, (M, F, K, 0, "bfloat16", "swiglu_bwd", "-"))
+    _lib.call("dalm_b200_gemm_bf16_swiglu_bwd", _p(dy), _ld(dy), _p(wdT), _ld(wdT), _p(gu), _ld(gu), M, F, K, _stream())
+    if timer is not None:
+        timer.end()
+    return gu
 
 
 def gemm_gelu(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, pre: Optional[torch.Tensor] = None,
@@ -676,6 +704,33 @@ def topk_ip(q: torch.Tensor, p: torch.Tensor, k: int) -> Tuple[torch.Tensor, tor
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# use_bnb with 4-bit storage: packed NF4 codes + absmax, expanded to bf16 right before the GEMM
+def nf4_quantize(w: torch.Tensor):
+    """w fp32 contiguous [rows, cols] -> (packed uint8 [rows*cols/2], absmax fp32 [rows*cols/64]); blocks of 64 over the
+    flattened row-major weight (bitsandbytes quantize_4bit, nf4, blocksize 64)"""
+    _chk(w, f32, "nf4_quantize w")
+    if not w.is_contiguous():
+        raise _lib.DalmB200Error("nf4_quantize: tensor must be contiguous")
+    n = w.numel()
+    packed = torch.empty((n + 1) // 2, dtype=torch.uint8, device=w.device)
+    absmax = torch.empty((n + 63) // 64, dtype=f32, device=w.device)
+    _lib.call("dalm_b200_nf4_quantize", _p(w), n, _p(packed), _p(absmax), _stream())
+    return packed, absmax
+
+
+def nf4_dequant_(packed: torch.Tensor, absmax: torch.Tensor, rows: int, cols: int, out: torch.Tensor,
+                 tail: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """packed / absmax of a [rows, cols] weight -> out[:, :cols] (bf16, row stride out.stride(0)); `tail` (bf16 [rows, t]) is
+    copied into out[:, cols:cols+t]"""
+    _chk(out, bf16, "nf4_dequant out")
+    t = 0 if tail is None else tail.shape[1]
+    if out.shape[0] != rows or out.shape[1] < cols + t:
+        raise _lib.DalmB200Error(f"nf4_dequant: out {tuple(out.shape)} too small for [{rows}, {cols}+{t}]")
+    _lib.call("dalm_b200_nf4_dequant_bf16", _p(packed), _p(absmax), rows, cols, _p(out), out.stride(0), _p(tail),
+              tail.stride(0) if tail is not None else 0, t, _stream())
+    return out
+
+
 # use_bnb: NF4 round trip of a weight at load time
 # ----------------------------------------------------------------------------------------------------------------
 def nf4_roundtrip_(w: torch.Tensor, want_codes: bool = False):

@@ -95,6 +95,11 @@ int dalm_b200_gemm_bf16_swiglu(const void* A, long long lda, const void* B, long
  * fp32 [L, 64]; output row m is at position m % L. Replaces q_proj / k_proj / v_proj + apply_rotary_pos_emb of HF LlamaAttention. */
 int dalm_b200_gemm_bf16_rope(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo, int M, int N,
                              int K, const float* cos_t, const float* sin_t, int L, int rope_cols, void* stream);
+/* gemm_bf16_swiglu_bwd: LlamaMLP backward through down_proj and act_fn(gate) * up in one launch: d(act)[M,F] = dY[M,K] WdT[F,K]^T
+ * stays in TMEM; gu [M,2F] (gate|up interleaved in 128-feature blocks, as gemm_bf16_swiglu left it) is overwritten in place with
+ * [d gate | d up]. Bit-identical to gemm_bf16 followed by swiglu_bwd (interleave 128). */
+int dalm_b200_gemm_bf16_swiglu_bwd(const void* dY, long long lddy, const void* WdT, long long ldw, void* gu, long long ldgu, int M,
+                                   int F, int K, void* stream);
 /* gemm_bf16_gelu: pre[M,N] = A B^T + bias (bf16) AND act[M,N] = gelu_erf(pre) (bf16) from one launch: BertIntermediate
  * (dense + GELU, HF modeling_bert) / Falcon's dense_h_to_4h + act; the backward multiplies by gelu'(pre) inside the next dgrad
  * GEMM (gemm_bf16 with act = 2 and resid = pre), so neither direction runs a separate activation kernel. */
@@ -105,8 +110,9 @@ void dalm_b200_gemm_clear_cache(void);
  * while A [M,K] stays L2-resident next to a bf16 output, else bands with a ~square wave footprint walked serpentine),
  * -2 = bands for every multi-wave problem, > 0 = bands of that many 128-row m-tiles. Env DALM_B200_GEMM_RASTER seeds it. */
 void dalm_b200_gemm_set_raster(int group_m);
-/* L2 eviction priorities on the GEMM's TMA traffic (bit mask; tuning hook, default 0 / env DALM_B200_GEMM_L2_HINTS):
- * 1 = A loads evict_last, 2 = B loads evict_first, 4 = output stores evict_first */
+/* L2 eviction priorities on the GEMM's TMA traffic: -1 = automatic (default: mask 7 for multi-wave m-fastest problems whose
+ * A operand stays L2-resident, else 0), or a bit mask applied to every launch: 1 = A loads evict_last, 2 = B loads evict_first,
+ * 4 = output stores evict_first. Env DALM_B200_GEMM_L2_HINTS seeds it. Results never depend on it. */
 void dalm_b200_gemm_set_l2_hints(int mask);
 
 /* ---- attention (same call sites; HF eager/SDPA attention) ---- */
@@ -226,6 +232,13 @@ int dalm_b200_topk_ip(const float* Q, const float* P, long long ldp, int nq, int
  * retriever_only_base_model.py:85-91): fp16 cast, blocks of 64, absmax, 16 NormalFloat levels, dequantised to fp16.
  * codes (uint8 [n]) / absmax (fp32 [ceil(n/64)]) are optional outputs. */
 int dalm_b200_nf4_roundtrip(float* w, long long n, void* codes, float* absmax, void* stream);
+/* 4-bit STORAGE of the same quantisation (what bitsandbytes' Linear4bit keeps resident): nf4_quantize packs two codes per byte
+ * (first element in the high nibble) + fp32 absmax per block of 64; nf4_dequant_bf16 expands a [rows, cols] weight (cols % 64
+ * == 0) to bf16(fp16(code * absmax)) right before the GEMM that reads it - bnb's dequantize_4bit -> matmul forward - and copies
+ * an optional bf16 tail (the LoRA block of a K-augmented weight) behind each row. */
+int dalm_b200_nf4_quantize(const float* w, long long n, void* packed, float* absmax, void* stream);
+int dalm_b200_nf4_dequant_bf16(const void* packed, const float* absmax, long long rows, int cols, void* out, long long ldo,
+                               const void* tail, long long ldt, int tail_cols, void* stream);
 
 /* ---- evaluation: greedy autoregressive decoding of the generator ----
  * replaces `model.generate(**inputs, max_length=max_length, early_stopping=True)` of run_generator_on_prompts

@@ -65,7 +65,7 @@ def run_case(name, kind, N, K):
             t = s.elapsed_time(e) / 9 * 1e-3
             print(json.dumps({"case": name, "M": M, "N": N, "K": K, "raster": r, "hints": h, "us": round(t * 1e6, 1),
                               "tflops": round(2.0 * M * N * K / t / 1e12, 1)}), flush=True)
-    lib.dalm_b200_gemm_set_raster(0); lib.dalm_b200_gemm_set_l2_hints(0)
+    lib.dalm_b200_gemm_set_raster(0); lib.dalm_b200_gemm_set_l2_hints(-1)
 
 
 if __name__ == "__main__":
