@@ -69,21 +69,36 @@ def build_encoder(name_or_path: str, lora: bool, device: torch.device, state_dic
     cfg = cfg or params.load_config(name_or_path)
     kind = params.model_kind(cfg)
     sd = state_dict if state_dict is not None else params.load_state_dict(name_or_path)
-    sd = _maybe_bnb(sd, bnb, full, device)
+    nf4 = _nf4_storage(bnb, full, kind)
+    if not nf4:
+        sd = _maybe_bnb(sd, bnb, full, device)
     if autoregressive:
         if kind != "llama":
             raise NotImplementedError("autoregressive retrievers are built for Llama-family models only")
-        return _named(LlamaDecoder(cfg, sd, device=device, lora=lora, lora_seed=0, full=full), name_or_path)
+        return _named(LlamaDecoder(cfg, sd, device=device, lora=lora, lora_seed=0, full=full, nf4_storage=nf4), name_or_path)
     if kind != "bert":
         raise NotImplementedError("non-autoregressive retrievers must be BERT-family encoders (bge-*); pass "
                                   "retriever_is_autoregressive=True for a causal LM")
-    return _named(BertEncoder(cfg, sd, device=device, lora=lora, full=full), name_or_path)
+    return _named(BertEncoder(cfg, sd, device=device, lora=lora, full=full, nf4_storage=nf4), name_or_path)
 
 
 def _named(engine_model, name_or_path: str):
     """remember where the base weights came from: written as `base_model_name_or_path` into adapter_config.json"""
     engine_model.name_or_path = name_or_path or None
     return engine_model
+
+
+def _nf4_storage(bnb: bool, full: bool, kind: str) -> bool:
+    """use_bnb + DALM_B200_NF4_STORAGE=1: keep the sub-model's Linear weights as packed NF4 codes and expand them per use
+    (engine/nf4store.py) instead of the dequantised-resident default. BERT encoders and Llama decoders."""
+    from ..engine.nf4store import storage_enabled
+    if not bnb or not storage_enabled():
+        return False
+    if full:
+        _maybe_bnb({}, True, True, None)                      # raises: 4-bit base weights cannot be fully fine-tuned
+    if kind not in ("bert", "llama"):
+        raise NotImplementedError(f"DALM_B200_NF4_STORAGE=1: 4-bit storage is built for BERT encoders and Llama decoders, not {kind!r}")
+    return True
 
 
 def _maybe_bnb(sd: Dict, bnb: bool, full: bool, device) -> Dict:
@@ -110,12 +125,14 @@ def build_decoder(name_or_path: str, lora: bool, device: torch.device, state_dic
     cfg = cfg or params.load_config(name_or_path)
     kind = params.model_kind(cfg)                # raises for unsupported families
     sd = state_dict if state_dict is not None else params.load_state_dict(name_or_path)
-    sd = _maybe_bnb(sd, bnb, full, device)
+    nf4 = _nf4_storage(bnb, full, kind)
+    if not nf4:
+        sd = _maybe_bnb(sd, bnb, full, device)
     if kind == "falcon":
         return _named(FalconDecoder(cfg, sd, device=device, lora=lora, full=full), name_or_path)   # raises for lora=True, like peft would
     if kind != "llama":
         raise NotImplementedError(f"generator of kind {kind!r} is not a causal decoder")
-    return _named(LlamaDecoder(cfg, sd, device=device, lora=lora, full=full), name_or_path)
+    return _named(LlamaDecoder(cfg, sd, device=device, lora=lora, full=full, nf4_storage=nf4), name_or_path)
 
 
 class AutoModelForRagE2E(torch.nn.Module):

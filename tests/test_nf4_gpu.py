@@ -83,3 +83,70 @@ def test_wrappers_load_through_nf4(cuda_dev, tmp_path):
     w0 = gsd["model.layers.0.mlp.down_proj.weight"].float()
     assert torch.equal(rag.generator_model.layers[0]["Wd"].cpu().float(), torch.from_numpy(nf4.roundtrip(w0.numpy())[0]).bfloat16().float())
     assert torch.equal(rag.generator_model.lm_head.cpu().float()[:904], gsd["lm_head.weight"].half().float().bfloat16().float())   # head: fp16 cast only
+
+
+@pytest.mark.parametrize("rows,cols,tail", [(48, 64, 0), (384, 384, 24), (1000, 1024, 16), (130, 4544, 0)])
+def test_nf4_packed_storage_bit_exact_vs_oracle(cuda_dev, rows, cols, tail):
+    """4-bit STORAGE: packed codes (first element in the high nibble, bitsandbytes' layout) and absmax bit-exact against the
+    oracle; the per-use expansion gives bf16(fp16(code * absmax)) = exactly what the dequantised-resident mode keeps; the LoRA
+    tail block is copied behind each row"""
+    from dalm_b200 import ops
+    from oracle import nf4
+    w = (np.random.default_rng(rows + cols).standard_normal((rows, cols)) * 0.02).astype(np.float32)
+    w[1, :64] = 0.0
+    want, codes, absmax = nf4.roundtrip(w)
+    t = torch.from_numpy(w.copy()).to(cuda_dev)
+    packed, am = ops.nf4_quantize(t)
+    assert np.array_equal(packed.cpu().numpy(), (codes[0::2] << 4) | codes[1::2])
+    assert np.array_equal(am.cpu().numpy(), absmax)
+    ld = cols + (64 if tail else 0)
+    out = torch.full((rows, ld), 7.0, dtype=torch.bfloat16, device=cuda_dev)
+    tl = torch.randn(rows, tail, device=cuda_dev).to(torch.bfloat16) if tail else None
+    ops.nf4_dequant_(packed, am, rows, cols, out, tl)
+    assert torch.equal(out[:, :cols].cpu(), torch.from_numpy(want).bfloat16())
+    resident = ops.nf4_roundtrip_(t.clone()).to(torch.bfloat16)                   # the default mode's values
+    assert torch.equal(out[:, :cols], resident)
+    if tail:
+        assert torch.equal(out[:, cols:cols + tail], tl) and float((out[:, cols + tail:] - 7.0).abs().max()) == 0.0
+
+
+def test_nf4_storage_mode_equals_resident_mode(cuda_dev, monkeypatch):
+    """DALM_B200_NF4_STORAGE=1 (weights kept as packed codes, expanded per use, dgrad against W[out,in] read MN-major) trains
+    exactly like the dequantised-resident default: same loss, same LoRA gradients (BERT encoder + Llama decoder, fused step)"""
+    from dalm_b200 import synthetic
+    from dalm_b200.engine import params
+    from dalm_b200.engine.bert import BertEncoder
+    from dalm_b200.engine.llama import LlamaDecoder
+    from dalm_b200.models.rag_e2e_base_model import AutoModelForRagE2E, Mode
+    from dalm_b200.training.utils.train_utils import fused_rag_step
+    from test_step_gpu import _batch
+    dev = cuda_dev
+    bcfg, lcfg = synthetic.bert_config("bge-tiny", 600), synthetic.llama_config("llama-mini", 500)
+    bsd = params.random_state_dict("bert", bcfg, seed=11)
+    lsd = params.random_state_dict("llama", lcfg, seed=12)
+    batch = _batch(4, 12, 24, 40, 600, 500, seed=21)
+    res = []
+    for storage in (False, True):
+        if storage:
+            enc = BertEncoder(bcfg, bsd, device=dev, lora=True, nf4_storage=True)
+            dec = LlamaDecoder(lcfg, lsd, device=dev, lora=True, nf4_storage=True)
+            assert enc.nf4.nbytes() > 0 and "WoT" not in enc.layers[0] and "WdT" not in dec.layers[0]
+        else:
+            enc = BertEncoder(bcfg, params.bnb_nf4_state_dict(bsd, dev), device=dev, lora=True)
+            dec = LlamaDecoder(lcfg, params.bnb_nf4_state_dict(lsd, dev), device=dev, lora=True)
+        g = torch.Generator().manual_seed(13)
+        for bank in (enc.lora, dec.lora):
+            for n, _, _ in bank.specs:
+                bank.B[n].copy_((torch.randn(bank.B[n].shape, generator=g) * 0.02).to(dev))
+        enc.repack_lora(); dec.repack_lora()
+        model = AutoModelForRagE2E("", "", get_peft=Mode.BOTH, _retriever=enc, _generator=dec, _load_tokenizers=False)
+        enc.lora.zero_grad(); dec.lora.zero_grad()
+        out = fused_rag_step(model, batch, 100.0)
+        res.append((out["losses"].clone(), enc.lora.grad.clone(), dec.lora.grad.clone()))
+        if storage:                                                                # the expanded weight == the resident one
+            assert torch.equal(dec.layers[0]["Wd"], dec_res_Wd) and torch.equal(enc.layers[1]["Wi"], enc_res_Wi)
+        else:
+            dec_res_Wd, enc_res_Wi = dec.layers[0]["Wd"].clone(), enc.layers[1]["Wi"].clone()
+    rel = lambda a, b: ((a - b).norm() / (b.norm() + 1e-30)).item()
+    assert (res[0][0] - res[1][0]).abs().max().item() < 2e-3 * res[0][0].abs().max().item()
+    assert rel(res[1][1], res[0][1]) < 2e-2 and rel(res[1][2], res[0][2]) < 2e-2   # same math, other GEMM layouts / rounding points
