@@ -141,6 +141,10 @@ def run_training(recipe: Recipe, *, dataset_or_path: Any, per_device_train_batch
     use_graph = os.environ.get("DALM_B200_CUDA_GRAPH", "1") != "0" and torch.cuda.is_available()
     if sync.overlaps_backward:          # full fine-tuning on > 1 rank: per-layer all-reduces are issued DURING the backward
         use_graph = False               # (DDP bucket semantics), which a single captured graph cannot contain
+    from . import negatives
+    if negatives.active():              # cross-rank negatives: an all-gather sits in the middle of the launch sequence
+        use_graph = False
+        logger.info("DALM_B200_CROSS_RANK_NEGATIVES=1: in-batch negatives are gathered over all ranks (not the reference's semantics)")
     graphed = None
     for epoch in range(start_epoch, num_train_epochs):
         model.train()

@@ -159,6 +159,17 @@ def _side_stream(dev: torch.device) -> torch.cuda.Stream:
     return _SIDE_STREAMS[idx]
 
 
+def _inbatch(q_emb, p_emb, logit_scale: float, cvec, nsum, need_grad: bool, grad_out: float):
+    """the fused in-batch loss over this rank's rows (the reference's semantics), or - DALM_B200_CROSS_RANK_NEGATIVES=1 on a
+    multi-rank job - over the all-gathered rows of every rank (training/utils/negatives.py)"""
+    from . import negatives
+    if negatives.active():
+        import torch.distributed as dist
+        return negatives.global_inbatch_loss(q_emb, p_emb, logit_scale, cvec, nsum, need_grad, grad_out, rank=dist.get_rank(),
+                                             world=dist.get_world_size(), loss_fn=ops.inbatch_loss)
+    return ops.inbatch_loss(q_emb, p_emb, float(logit_scale), cvec, nsum, need_grad=need_grad, grad_out=grad_out)
+
+
 def _pool_masks(model, q_mask, p_mask, autoregressive: bool):
     from ...models.rag_e2e_base_model import pooling_mask
     return pooling_mask(q_mask, autoregressive).contiguous(), pooling_mask(p_mask, autoregressive).contiguous()
@@ -188,7 +199,7 @@ def fused_rag_step(rag_model, batch: Dict[str, torch.Tensor], logit_scale: float
         q_pm, p_pm = _pool_masks(rag_model, q_mask, p_mask, getattr(rag_model, "retriever_is_autoregressive", False))
         q_emb, q_norm = ops.pool_norm_fwd(hq, q_pm, rag_model.normalize)
         p_emb, p_norm = ops.pool_norm_fwd(hp, p_pm, rag_model.normalize)
-        r = ops.inbatch_loss(q_emb, p_emb, float(logit_scale), cvec, nsum, need_grad=train_enc, grad_out=grad_scale)
+        r = _inbatch(q_emb, p_emb, float(logit_scale), cvec, nsum, train_enc, grad_scale)
         if train_enc:
             enc_bwd(ops.pool_norm_bwd(q_emb, q_norm, r["dQ"], q_pm, L_q, rag_model.normalize),
                     ops.pool_norm_bwd(p_emb, p_norm, r["dP"], p_pm, L_p, rag_model.normalize))
@@ -239,7 +250,7 @@ def fused_retriever_step(model, batch: Dict[str, torch.Tensor], logit_scale: flo
     q_pm, p_pm = _pool_masks(model, q_mask, p_mask, getattr(model, "is_autoregressive", False))
     q_emb, q_norm = ops.pool_norm_fwd(hq, q_pm, model.normalize)
     p_emb, p_norm = ops.pool_norm_fwd(hp, p_pm, model.normalize)
-    r = ops.inbatch_loss(q_emb, p_emb, float(logit_scale), None, None, need_grad=train, grad_out=grad_scale)
+    r = _inbatch(q_emb, p_emb, float(logit_scale), None, None, train, grad_scale)
     if train:
         enc_bwd(ops.pool_norm_bwd(q_emb, q_norm, r["dQ"], q_pm, q_ids.shape[1], model.normalize),
                 ops.pool_norm_bwd(p_emb, p_norm, r["dP"], p_pm, p_ids.shape[1], model.normalize))

@@ -92,3 +92,83 @@ def test_two_rank_data_parallel_plumbing():
     res = [q.get(timeout=120) for _ in procs]
     for p in procs: p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# cross-rank in-batch negatives (optional extension): the host logic on gloo with the fused kernel replaced by its fp64
+# restatement - every rank's slice of the global gradient, DDP-averaged, must equal the gradient of the rank-mean objective
+# ---------------------------------------------------------------------------------------------------------------------
+def _inbatch_oracle(q, p, scale, cvec, nsum, need_grad=True, grad_out=1.0):
+    """dalm_b200.ops.inbatch_loss restated with torch autograd in fp64 (same outputs, same argument meaning)"""
+    q64, p64 = q.double().requires_grad_(True), p.double().requires_grad_(True)
+    S = (q64 @ p64.t()) * scale
+    n = S.shape[0]
+    ar = torch.arange(n)
+    rows = torch.log_softmax(S, 1)[ar, ar]
+    cols = torch.log_softmax(S, 0)[ar, ar]
+    lc = -(rows + cols).mean() / 2.0
+    doc = -(cvec.double() * rows).sum() / nsum.double()[0] if cvec is not None else torch.zeros((), dtype=torch.float64)
+    ((lc + doc) * grad_out).backward()
+    return {"S": S.detach().float(), "dlp": rows.detach().float(),
+            "losses": torch.stack([lc, doc, lc + doc, nsum.double()[0] if nsum is not None else torch.zeros((), dtype=torch.float64)]).detach().float(),
+            "dQ": q64.grad.float(), "dP": p64.grad.float()}
+
+
+def _neg_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                      DALM_B200_CROSS_RANK_NEGATIVES="1")
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from dalm_b200.accel import Accelerator
+    from dalm_b200.training.utils import negatives
+    Accelerator(cpu=True)
+    assert negatives.active()
+    D, scale = 16, 20.0
+    Bs = [5, 3]                                                      # a short final batch on rank 1
+    g = torch.Generator().manual_seed(7)
+    Q = [torch.nn.functional.normalize(torch.randn(b, D, generator=g), dim=1) for b in Bs]
+    P = [torch.nn.functional.normalize(torch.randn(b, D, generator=g), dim=1) for b in Bs]
+    C = [torch.rand(b, generator=g) * 10 for b in Bs]
+    N = [torch.tensor([37.0]), torch.tensor([21.0])]
+    ok = True
+    for marg in (True, False):
+        r = negatives.global_inbatch_loss(Q[rank], P[rank], scale, C[rank] if marg else None, N[rank] if marg else None, True, 0.5,
+                                          rank=rank, world=world, loss_fn=_inbatch_oracle)
+        # the objective every rank's gradients must add up to: J = (1/W) sum_r [Lc(S_global) + doc_r]
+        qa = torch.cat(Q).double().requires_grad_(True); pa = torch.cat(P).double().requires_grad_(True)
+        S = (qa @ pa.t()) * scale
+        n = S.shape[0]; ar = torch.arange(n)
+        rows = torch.log_softmax(S, 1)[ar, ar]; cols = torch.log_softmax(S, 0)[ar, ar]
+        lc = -(rows + cols).mean() / 2.0
+        J = lc
+        docs = []
+        if marg:
+            off = 0
+            for b, c, nn in zip(Bs, C, N):
+                docs.append(-(c.double() * rows[off:off + b]).sum() / nn.double()[0]); off += b
+            J = J + sum(docs) / world
+        (J * 0.5).backward()
+        lo = sum(Bs[:rank])
+        # what a data-parallel MEAN over ranks of "this rank's rows only" yields == dJ/dq: each rank holds W x its slice
+        ok = ok and torch.allclose(r["dQ"].double() / world, qa.grad[lo:lo + Bs[rank]], atol=1e-6)
+        ok = ok and torch.allclose(r["dP"].double() / world, pa.grad[lo:lo + Bs[rank]], atol=1e-6)
+        ok = ok and abs(r["losses"][0].item() - lc.item()) < 1e-5 and r["S"].shape == (8, 8)
+        if marg:
+            ok = ok and abs(r["losses"][1].item() - docs[rank].item()) < 1e-5 and abs(r["losses"][3].item() - N[rank].item()) < 1e-6
+            ok = ok and torch.allclose(r["dlp"].double(), rows[lo:lo + Bs[rank]].detach(), atol=1e-5)
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_cross_rank_negatives_host_logic_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_neg_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]

@@ -82,3 +82,42 @@ def test_ce_fp32_inplace_and_large_vocab(cuda_dev):
     out = ops.finalize_loss(tok_lp, mask.to(dev), nsum, r["losses"])
     assert abs(out[2].item() - ref["loss"].item()) < 1e-5 * abs(ref["loss"].item())
     assert (dl.cpu().double() - ref["dlogits"]).norm() / ref["dlogits"].norm() < 1e-5
+
+
+def test_cross_rank_negatives_on_the_fused_kernel(cuda_dev):
+    """DALM_B200_CROSS_RANK_NEGATIVES: two emulated ranks (gather injected) through the real fused in-batch kernel; each rank's
+    slice of dQ / dP, divided by the world size (the data-parallel mean), equals the fp64 gradient of
+    J = (1/W) sum_r [Lc(S_global) + doc_r] for its rows; the reported losses are (global Lc, this rank's doc term)"""
+    from dalm_b200 import ops
+    from dalm_b200.training.utils import negatives
+    dev = cuda_dev
+    W, Bs, D, scale, gout = 2, [18, 18], 1024, 100.0, 1.0
+    g = torch.Generator().manual_seed(3)
+    Q = [torch.nn.functional.normalize(torch.randn(b, D, generator=g), dim=1) for b in Bs]
+    P = [torch.nn.functional.normalize(torch.randn(b, D, generator=g) + 0.5 * q, dim=1) for b, q in zip(Bs, Q)]
+    C = [torch.randint(0, 60, (b,), generator=g).float() for b in Bs]
+    N = [torch.tensor([700.0]), torch.tensor([655.0])]
+    qa = torch.cat(Q).double().requires_grad_(True); pa = torch.cat(P).double().requires_grad_(True)
+    S = (qa @ pa.t()) * scale
+    ar = torch.arange(S.shape[0])
+    rows = torch.log_softmax(S, 1)[ar, ar]; cols = torch.log_softmax(S, 0)[ar, ar]
+    lc = -(rows + cols).mean() / 2.0
+    docs, off = [], 0
+    for b, c, n in zip(Bs, C, N):
+        docs.append(-(c.double() * rows[off:off + b]).sum() / n.double()[0]); off += b
+    (lc + sum(docs) / W).backward()
+    for rank in range(W):
+        def gather(t, rank=rank):
+            # what the all-gather returns on this rank: every rank's block of the tensor being gathered, identified by its shape
+            for src in (Q, P):
+                if t.dim() == 2 and torch.equal(t.cpu(), src[rank]):
+                    return [x.to(dev) for x in src]
+            return [(c / n).to(dev) for c, n in zip(C, N)]
+        r = negatives.global_inbatch_loss(Q[rank].to(dev), P[rank].to(dev), scale, C[rank].to(dev), N[rank].to(dev), True, gout,
+                                          rank=rank, world=W, loss_fn=ops.inbatch_loss, gather=gather)
+        lo = sum(Bs[:rank])
+        rel = lambda a, b: ((a.double().cpu() - b).norm() / (b.norm() + 1e-30)).item()
+        assert rel(r["dQ"] / W, qa.grad[lo:lo + Bs[rank]]) < 1e-4 and rel(r["dP"] / W, pa.grad[lo:lo + Bs[rank]]) < 1e-4
+        assert abs(r["losses"][0].item() - lc.item()) < 1e-4 * abs(lc.item()) + 1e-6
+        assert abs(r["losses"][1].item() - docs[rank].item()) < 1e-4 * abs(docs[rank].item()) + 1e-6
+        assert r["S"].shape == (36, 36) and r["dlp"].shape == (18,)
