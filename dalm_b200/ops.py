@@ -475,7 +475,11 @@ FUSE_GELU_MIN_K = int(os.environ.get("DALM_B200_FUSE_GELU_MIN_K", "2048"))
 
 def fuse_gelu(K: int) -> bool:
     return K >= FUSE_GELU_MIN_K
-FUSE_SWIGLU_BWD = os.environ.get("DALM_B200_FUSE_SWIGLU_BWD", "1") != "0"   # 0: down-proj dgrad GEMM + swiglu_bwd kernel
+
+
+# measured (profiles/r02b_fusion_probe.jsonl): fused 466 us vs 382 us for the dgrad GEMM + swiglu_bwd kernel at the Llama-2-7B shape - the
+# epilogue's per-thread row loads of gate / up (32 lines per warp instruction) cost more than the stand-alone pass. Opt-in only.
+FUSE_SWIGLU_BWD = os.environ.get("DALM_B200_FUSE_SWIGLU_BWD", "0") == "1"
 
 
 def gemm_swiglu_bwd_(dy: torch.Tensor, wdT: torch.Tensor, gu: torch.Tensor) -> torch.Tensor:
