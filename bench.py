@@ -393,7 +393,11 @@ def main():
     bf = torch.bfloat16
     bcfg = dict(synthetic.bert_config(args.retriever), _device_rng=True)
     full_r = cfgd["peft"] is None
-    enc = BertEncoder(bcfg, params.random_state_dict("bert", bcfg, seed=0, dtype=bf, device=dev), device=dev, lora=not full_r, full=full_r)
+    # supplementary variant (not the metric's configuration): DALM_B200_BENCH_NF4=1 keeps both base models as packed NF4 codes
+    # (`use_bnb` with DALM_B200_NF4_STORAGE semantics, engine/nf4store.py) - reports what 4-bit storage costs per step and saves in HBM
+    nf4 = os.environ.get("DALM_B200_BENCH_NF4", "0") == "1" and cfgd["peft"] is not None
+    enc = BertEncoder(bcfg, params.random_state_dict("bert", bcfg, seed=0, dtype=bf, device=dev), device=dev, lora=not full_r, full=full_r,
+                      nf4_storage=nf4 and not full_r)
     if cfgd["gen"] is None:                                   # cfg-2: retriever-only trainer (train_retriever_only.py:365-379)
         from dalm_b200.models.retriever_only_base_model import AutoModelForSentenceEmbedding
         from dalm_b200.training.utils.train_utils import fused_retriever_step as step_fn
@@ -405,7 +409,7 @@ def main():
         if cfgd["gen"] == "llama":
             lcfg = dict(synthetic.llama_config(args.generator), _device_rng=True)
             dec = LlamaDecoder(lcfg, params.random_state_dict("llama", lcfg, seed=0, dtype=bf, device=dev), device=dev,
-                               lora=cfgd["peft"] == "both", full=cfgd["peft"] is None)
+                               lora=cfgd["peft"] == "both", full=cfgd["peft"] is None, nf4_storage=nf4 and cfgd["peft"] == "both")
         else:
             from dalm_b200.engine.falcon import FalconDecoder
             fcfg = dict(synthetic.falcon_config("falcon-7b"), _device_rng=True)
@@ -547,6 +551,8 @@ def main():
     used_graph = graphed is not None
     arena_mb = sync.arena.numel() * 4 / 1e6
     peak_mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
+    nf4_store_gb = sum(m.nf4.nbytes() for m in (enc, dec if cfgd["gen"] is not None else None)
+                       if getattr(m, "nf4", None) is not None) / 2 ** 30
     graphed = model = enc = opt = sync = banks = repack = resident = pinned = None
     if cfgd["gen"] is not None:
         dec = None
@@ -592,7 +598,11 @@ def main():
                    "weights": "seeded random-init (no checkpoints offline)", "dropout": "train() mode as in the reference loop: BERT hidden 0.1 + attention-prob 0.1, LoRA input 0.05 (Philox, masks regenerated in backward)",
                    "launch": "one CUDA graph replay per step (fwd+bwd) + Adam/repack launches" if used_graph else "eager launches",
                    "eager_ms_per_step": eager_ms / args.steps,
-                   "loss_last": loss_last},
+                   "loss_last": loss_last,
+                   **({"variant": "DALM_B200_BENCH_NF4=1: base weights of both models kept as packed NF4 codes (4-bit storage), "
+                                  "expanded to bf16 per GEMM; NOT the metric's configuration",
+                       "nf4_store_gb": nf4_store_gb}
+                      if nf4 else {})},
         "e2e": {"value": samples / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
