@@ -125,12 +125,13 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const __nv_bfloat16* _
   if (g == 0) out[(size_t)b * ldo + h * D + d] = __float2bfloat16(acc / sum);
 }
 
-// CANDIDATE (not the default; DALM_B200_DECODE_ATTN=2 selects it): the same kernel with a parallel PV pass. Measured on the
-// default kernel: 0.9 us per cached key per layer, because pass 3 above walks the keys serially per thread with the V load
-// behind `if (p != 0)` (profiles/README.md, r01_decode_bench.jsonl line 4). Here 128 threads = KG key groups x D/8 lanes,
-// every lane loads 16 bytes of V unconditionally (masked keys carry p = 0; their cache rows are initialised memory) and the
-// KG partial rows meet in shared memory. Written after the round's GPU minutes were spent: its GPU tests
-// (tests/test_generate_gpu.py, DALM_B200_EXPERIMENTAL=1) have not run yet, so it is NOT wired as the default.
+// DEFAULT decode attention: the kernel above with a parallel PV pass. Measured on the first kernel: 0.9 us per cached key per
+// layer, because its pass 3 walks the keys serially per thread with the V load behind `if (p != 0)` (profiles/README.md,
+// r01_decode_bench.jsonl line 4). Here 128 threads = KG key groups x D/8 lanes, every lane loads 16 bytes of V unconditionally
+// (masked keys carry p = 0; their cache rows are initialised memory) and the KG partial rows meet in shared memory.
+// Measured (profiles/r02b_decode_bench.jsonl, Llama-2-7B shape, 16 x 192 -> 256 tokens): 13.3 / 9.1 ms (graph / eager) per token
+// step with the first kernel -> 4.55 / 5.0 ms = 3 514 tokens/s = 0.50 of the HBM floor. DALM_B200_DECODE_ATTN=1 selects the first
+// kernel (kept as the cross-check of tests/test_generate_gpu.py).
 // one explicit 16-byte read-only load -> 8 floats (the struct-typed loads above are split into 32-bit loads by the compiler)
 __device__ __forceinline__ void load8_nc(const __nv_bfloat16* p, float* f) {
   const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
@@ -440,7 +441,7 @@ extern "C" int dalm_b200_attention_decode(const void* qkv, long long ldq, int q_
   DALM_REQUIRE(mask != nullptr && cache_st >= (long long)Hkv * D && cache_sb >= cache_st * T, "attention_decode: cache layout");
   const int sp_cap = ((cur_dev ? T : cur + 1) + 3) & ~3;
   const char* variant = getenv("DALM_B200_DECODE_ATTN");
-  const bool v2 = variant != nullptr && variant[0] == '2';          // candidate kernel, see attn_decode_v2_kernel
+  const bool v2 = !(variant != nullptr && variant[0] == '1');       // default: parallel-PV kernel; 1 = the first (serial-PV) kernel
   const size_t smem = (size_t)(D + sp_cap + 32 + (v2 ? 1024 : 128)) * sizeof(float);
   dim3 grid(Hq, B);
   if (v2) {

@@ -81,29 +81,33 @@ __global__ void nf4_quantize_kernel(const float* __restrict__ w, long long n, un
   if (i0 < n) packed[i0 >> 1] = (unsigned char)((q0 << 4) | (i0 + 1 < n ? q1 : 7));
 }
 
-// bf16 out[r, c] = bf16(fp16(code * absmax))  (the value the dequantised-resident mode keeps), 16 codes per thread; a row's
-// `tail_cols` extra columns (the LoRA block of a K-augmented weight) are copied from `tail`
-__global__ void nf4_dequant_bf16_kernel(const unsigned char* __restrict__ packed, const float* __restrict__ absmax, long long rows,
-                                        int cols, __nv_bfloat16* __restrict__ out, long long ldo,
-                                        const __nv_bfloat16* __restrict__ tail, long long ldt, int tail_cols) {
+// bf16 out[r, c] = bf16(fp16(code * absmax))  (the value the dequantised-resident mode keeps). grid (ceil((cols/16 + 1)/256), rows):
+// a thread expands 16 codes (8 bytes in, 32 bytes out); the sixteen levels sit in shared memory (divergent indices into
+// __constant__ memory serialise: the first version of this kernel ran at 0.95 TB/s); the last thread of a row copies the row's
+// `tail_cols` extra columns (the LoRA block of a K-augmented weight) from `tail`
+__global__ void __launch_bounds__(256) nf4_dequant_bf16_kernel(const unsigned char* __restrict__ packed, const float* __restrict__ absmax,
+                                                               long long rows, int cols, __nv_bfloat16* __restrict__ out, long long ldo,
+                                                               const __nv_bfloat16* __restrict__ tail, long long ldt, int tail_cols) {
+  __shared__ float lut[16];
+  if (threadIdx.x < 16) lut[threadIdx.x] = kNF4Code[threadIdx.x];
+  __syncthreads();
   const int groups = cols >> 4;                                         // 16-code groups per row
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long r = t / (groups + 1);
-  const int gi = (int)(t - r * (groups + 1));
-  if (r >= rows) return;
+  const long long r = blockIdx.y;
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi > groups) return;
   if (gi == groups) {                                                   // this row's tail
     for (int c = 0; c < tail_cols; ++c) out[r * ldo + cols + c] = tail[r * ldt + c];
     return;
   }
   const long long e0 = r * cols + (long long)gi * 16;                   // first element (flattened row-major weight)
-  const uint2 raw = *reinterpret_cast<const uint2*>(packed + (e0 >> 1));
-  const float m = absmax[e0 >> 6];
+  const uint2 raw = __ldg(reinterpret_cast<const uint2*>(packed + (e0 >> 1)));
+  const float m = __ldg(absmax + (e0 >> 6));
   const unsigned char* b = reinterpret_cast<const unsigned char*>(&raw);
   float f[16];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    f[2 * i]     = __half2float(__float2half_rn(kNF4Code[b[i] >> 4] * m));
-    f[2 * i + 1] = __half2float(__float2half_rn(kNF4Code[b[i] & 15] * m));
+    f[2 * i]     = __half2float(__float2half_rn(lut[b[i] >> 4] * m));
+    f[2 * i + 1] = __half2float(__float2half_rn(lut[b[i] & 15] * m));
   }
   __nv_bfloat16* o = out + r * ldo + (long long)gi * 16;
   *reinterpret_cast<bf16x8*>(o) = pack8(f);
@@ -131,8 +135,9 @@ extern "C" int dalm_b200_nf4_dequant_bf16(const void* packed, const float* absma
   DALM_REQUIRE(ldo >= cols + tail_cols && (ldo % 8) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)packed & 7) == 0,
                "nf4_dequant: output stride / alignment");
   DALM_REQUIRE(tail_cols == 0 || (tail != nullptr && ldt >= tail_cols), "nf4_dequant: tail");
-  const long long threads = rows * ((cols >> 4) + 1);
-  nf4_dequant_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  DALM_REQUIRE(rows <= 65535, "nf4_dequant: %lld rows exceed the grid's y extent", rows);
+  const dim3 grid((unsigned)(((cols >> 4) + 1 + 255) / 256), (unsigned)rows);
+  nf4_dequant_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       (const unsigned char*)packed, absmax, rows, cols, (__nv_bfloat16*)out, ldo, (const __nv_bfloat16*)tail, ldt, tail_cols);
   count_launch();
   return check_launch("nf4_dequant_bf16_kernel");
