@@ -705,11 +705,11 @@ __global__ void __launch_bounds__(256) lora_dx_kernel(__nv_bfloat16* __restrict_
   constexpr int ROWS = 16;
   __shared__ __align__(16) float Gs[ROWS][R];
   const int m0 = blockIdx.y * ROWS;
-  for (int i = threadIdx.x; i < ROWS * R; i += 256) {
+  for (int i = threadIdx.x; i < ROWS * R; i += blockDim.x) {
     const int mm = i / R, r = i - mm * R;
     Gs[mm][r] = (m0 + mm < M) ? __bfloat162float(G[(size_t)(m0 + mm) * ldg + r]) : 0.f;
   }
-  const int c = (blockIdx.x * 256 + threadIdx.x) * 8;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   bf16x8 areg[R];
   if (c < K) {
 #pragma unroll
@@ -976,12 +976,16 @@ extern "C" int dalm_b200_lora_dx(void* dh, long long lddh, const void* G, long l
                                  const void* offset, void* stream) {
   DALM_REQUIRE((R == 8 || R == 16 || R == 24) && (K % 8) == 0 && (lddh % 8) == 0 && (lda % 8) == 0, "lora_dx: bad shape R=%d K=%d", R, K);
   DALM_REQUIRE(p >= 0.f && p < 1.f, "lora_dx: p must be in [0,1)");
-  dim3 grid((K / 8 + 255) / 256, (M + 15) / 16);
+  // one thread per 8 columns: a CTA no wider than the row (bge-large, K = 1024: 128 threads - a 256-thread CTA kept half of its
+  // warps resident but idle, 107 us for 109 MB at cfg-2)
+  const int cols8 = K / 8;
+  const int threads = cols8 >= 256 ? 256 : ((cols8 + 31) / 32) * 32;
+  dim3 grid((cols8 + threads - 1) / threads, (M + 15) / 16);
   const DropCfg dc = make_drop(p, seed, stream_id, offset);
   auto* dhp = (__nv_bfloat16*)dh; auto* gp = (const __nv_bfloat16*)G; auto* ap = (const __nv_bfloat16*)A;
-  if (R == 8)       lora_dx_kernel<8><<<grid, 256, 0, ST(stream)>>>(dhp, lddh, gp, ldg, ap, lda, M, K, dc);
-  else if (R == 16) lora_dx_kernel<16><<<grid, 256, 0, ST(stream)>>>(dhp, lddh, gp, ldg, ap, lda, M, K, dc);
-  else              lora_dx_kernel<24><<<grid, 256, 0, ST(stream)>>>(dhp, lddh, gp, ldg, ap, lda, M, K, dc);
+  if (R == 8)       lora_dx_kernel<8><<<grid, threads, 0, ST(stream)>>>(dhp, lddh, gp, ldg, ap, lda, M, K, dc);
+  else if (R == 16) lora_dx_kernel<16><<<grid, threads, 0, ST(stream)>>>(dhp, lddh, gp, ldg, ap, lda, M, K, dc);
+  else              lora_dx_kernel<24><<<grid, threads, 0, ST(stream)>>>(dhp, lddh, gp, ldg, ap, lda, M, K, dc);
   count_launch();
   return check_launch("lora_dx_kernel");
 }

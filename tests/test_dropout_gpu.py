@@ -173,3 +173,20 @@ def test_bert_encoder_train_mode_matches_hf_with_replayed_masks(cuda_dev, monkey
     h2, _ = enc.forward_hidden(ids.to(cuda_dev), mask.to(cuda_dev), save=False)
     h3, _ = enc.forward_hidden(ids.to(cuda_dev), mask.to(cuda_dev), save=False)
     assert torch.equal(h2, h3)
+
+
+@pytest.mark.parametrize("M,K,R,p", [(333, 200, 8, 0.05), (1000, 1024, 24, 0.05), (130, 4096, 16, 0.05), (64, 2304, 24, 0.0)])
+def test_lora_dx_row_widths(cuda_dev, M, K, R, p):
+    """dh += mask/(1-p) * (g A) for rows narrower, equal to and wider than one CTA (the launch width follows the row width);
+    p = 0 is the un-dropped form the NF4-storage backward uses"""
+    from dalm_b200 import ops
+    dev = cuda_dev
+    g0 = torch.Generator(device="cpu").manual_seed(M + K + R)
+    a_stack = (torch.randn(64, K, generator=g0) * 0.3).to(bf16).to(dev)
+    g = (torch.randn(M, R, generator=g0) * 0.2).to(bf16).to(dev)
+    dh = (torch.randn(M, K, generator=g0) * 0.1).to(bf16).to(dev)
+    d = ops.Drop(p, 11, 2 << 8 | 3, None) if p > 0 else None
+    scale = ops.dropout_scale(M * K, d, dev).view(M, K) if d is not None else 1.0
+    ref = dh.float() + scale * (g.float() @ a_stack[:R].float())
+    ops.lora_dx_(dh, g, a_stack, K=K, R=R, drop=d)
+    assert _rel(dh.float(), ref) < 4e-3
