@@ -182,3 +182,42 @@ def test_collate_and_lora_bank_layout():
     bank2 = LoraBank([("m.q", 16, 24), ("m.v", 16, 8)], device="cpu", seed=5)
     bank2.load_peft_state_dict(sd)
     assert torch.equal(bank2.flat, bank.flat)
+
+
+def test_head_chunk_rows_plans_whole_tiles_within_budget():
+    """row-chunk planner of the chunked lm_head + CE head (dalm_b200/ops.py): 128-row aligned, scratch within the budget,
+    fewest wasted tile waves among the next few chunk counts"""
+    from dalm_b200 import ops
+    # cfg-3: 4608 rows x 32000 logits, 80 MB budget -> 4 chunks of 9 m-tiles (1 152 rows, 74 MB): 32 waves vs 36 for 6 x 6
+    assert ops.head_chunk_rows(4608, 32000, 80 << 20) == 1152
+    # cfg-5: 36 864 rows x 65 024 logits: L2-sized chunks for a frozen head, 512 MB chunks for a trainable one
+    r_l2, r_full = ops.head_chunk_rows(36864, 65024, 80 << 20), ops.head_chunk_rows(36864, 65024, 512 << 20)
+    assert r_l2 % 128 == 0 and r_l2 * 65024 * 2 <= 80 << 20 and r_full % 128 == 0 and r_full * 65024 * 2 <= 512 << 20 and r_full > r_l2
+    # tiny problems: one 128-row tile per chunk at least, never zero
+    assert ops.head_chunk_rows(5, 504, 1) == 128 and ops.head_chunk_rows(300, 1000, 128 * 1000 * 2) == 128
+    for M, Vp, budget in ((4608, 32000, 80 << 20), (200, 504, 128 * 504 * 2), (36864, 65024, 512 << 20), (1000, 30528, 64 << 20)):
+        rows = ops.head_chunk_rows(M, Vp, budget)
+        assert rows >= 128 and rows % 128 == 0
+        assert sum(min(rows, M - r0) for r0 in range(0, M, rows)) == M          # the chunks tile the rows exactly
+
+
+def test_cross_rank_negatives_switch_is_off_by_default(monkeypatch):
+    from dalm_b200.training.utils import negatives
+    monkeypatch.delenv("DALM_B200_CROSS_RANK_NEGATIVES", raising=False)
+    assert not negatives.enabled() and not negatives.active()           # the reference's rank-local negatives are the default
+    monkeypatch.setenv("DALM_B200_CROSS_RANK_NEGATIVES", "1")
+    assert negatives.enabled() and not negatives.active()               # a single-process run has nobody to gather from
+
+
+def test_nf4_storage_switch(monkeypatch):
+    from dalm_b200.engine import nf4store
+    from dalm_b200.models import rag_e2e_base_model as m
+    monkeypatch.delenv("DALM_B200_NF4_STORAGE", raising=False)
+    assert not nf4store.storage_enabled() and not m._nf4_storage(True, False, "bert")
+    monkeypatch.setenv("DALM_B200_NF4_STORAGE", "1")
+    assert m._nf4_storage(True, False, "llama") and not m._nf4_storage(False, False, "llama")
+    import pytest
+    with pytest.raises(NotImplementedError):
+        m._nf4_storage(True, False, "falcon")                            # built for BERT encoders and Llama decoders
+    with pytest.raises(NotImplementedError):
+        m._nf4_storage(True, True, "llama")                              # 4-bit base weights cannot be fully fine-tuned
