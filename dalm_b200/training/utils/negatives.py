@@ -36,14 +36,23 @@ def active() -> bool:
     return enabled() and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
-def dist_gather_rows(t: torch.Tensor) -> List[torch.Tensor]:
-    """all-gather of per-rank row blocks whose heights may differ (a short final batch on one rank): -> list of W tensors"""
+def dist_row_counts(n_rows: int, device) -> List[int]:
+    """every rank's local batch height (a short final batch on one rank makes them differ): one tiny all-gather + host read"""
     import torch.distributed as dist
     world = dist.get_world_size()
-    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    n = torch.tensor([n_rows], dtype=torch.int64, device=device)
     counts = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(counts, n)
-    counts = [int(c.item()) for c in counts]
+    return [int(c) for c in torch.cat(counts).tolist()]
+
+
+def dist_gather_rows(t: torch.Tensor, counts: Optional[List[int]] = None) -> List[torch.Tensor]:
+    """all-gather of per-rank row blocks whose heights may differ: -> list of W tensors (rank order). `counts`: the heights, if
+    the caller already exchanged them (one exchange serves all gathers of a step)"""
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    if counts is None:
+        counts = dist_row_counts(t.shape[0], t.device)
     mx = max(counts)
     pad = t if t.shape[0] == mx else torch.cat([t, t.new_zeros((mx - t.shape[0],) + tuple(t.shape[1:]))], 0)
     bufs = [torch.empty_like(pad) for _ in range(world)]
@@ -53,9 +62,13 @@ def dist_gather_rows(t: torch.Tensor) -> List[torch.Tensor]:
 
 def global_inbatch_loss(q_emb: torch.Tensor, p_emb: torch.Tensor, logit_scale: float, cvec: Optional[torch.Tensor],
                         nsum: Optional[torch.Tensor], need_grad: bool, grad_out: float, *, rank: int, world: int,
-                        loss_fn: Callable, gather: Callable[[torch.Tensor], List[torch.Tensor]] = dist_gather_rows) -> Dict[str, torch.Tensor]:
+                        loss_fn: Callable, gather: Optional[Callable[[torch.Tensor], List[torch.Tensor]]] = None) -> Dict[str, torch.Tensor]:
     """Same contract as ops.inbatch_loss for the LOCAL rows (S is the global matrix): dict(S, dlp, losses, dQ, dP).
-    loss_fn: ops.inbatch_loss (injectable so the host logic is testable on CPU); gather: rows of every rank, rank-major."""
+    loss_fn: ops.inbatch_loss (injectable so the host logic is testable on CPU); gather: rows of every rank, rank-major
+    (default: torch.distributed all-gathers sharing one exchange of the batch heights)."""
+    if gather is None:
+        counts = dist_row_counts(q_emb.shape[0], q_emb.device)
+        gather = lambda t: dist_gather_rows(t, counts)
     qs, ps = gather(q_emb.contiguous()), gather(p_emb.contiguous())
     q_all, p_all = torch.cat(qs, 0), torch.cat(ps, 0)
     lo = sum(t.shape[0] for t in qs[:rank])
