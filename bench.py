@@ -440,7 +440,9 @@ def main():
     graphed = None
     big = args.config == "cfg-5"       # 125 GB of parameters + Adam state: no room for a graph's private pool NEXT TO the eager
     #                                    roofline pass's activations; a 3 s step hides its launch overhead anyway
-    if args.graph and not sync.overlaps_backward and not big:   # full fine-tuning on N > 1: bucket all-reduces are issued during backward
+    from dalm_b200.training.utils import negatives
+    xneg = negatives.active()          # optional extension (not the reference's semantics): an all-gather sits inside the step
+    if args.graph and not sync.overlaps_backward and not big and not xneg:   # full fine-tuning on N > 1: bucket all-reduces are issued during backward
         try:
             graphed = GraphedStep(step_fn, model, resident[0], 100.0, zero_grads=opt.zero_grad)
         except Exception as e:
@@ -599,6 +601,8 @@ def main():
                    "launch": "one CUDA graph replay per step (fwd+bwd) + Adam/repack launches" if used_graph else "eager launches",
                    "eager_ms_per_step": eager_ms / args.steps,
                    "loss_last": loss_last,
+                   **({"negatives": "DALM_B200_CROSS_RANK_NEGATIVES=1: in-batch negatives all-gathered over the ranks (extension; "
+                                    "NOT the reference's rank-local semantics)"} if xneg else {}),
                    **({"variant": "DALM_B200_BENCH_NF4=1: base weights of both models kept as packed NF4 codes (4-bit storage), "
                                   "expanded to bf16 per GEMM; NOT the metric's configuration",
                        "nf4_store_gb": nf4_store_gb}

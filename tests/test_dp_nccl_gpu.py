@@ -77,3 +77,73 @@ def test_nccl_averaged_gradients_equal_mean_of_oracle_gradients():
     res = [q.get(timeout=600) for _ in procs]
     for p in procs: p.join(timeout=60)
     assert all(r[1] for r in res), res
+
+
+def _neg_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                      DALM_B200_CROSS_RANK_NEGATIVES="1")
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
+    try:
+        import torch.distributed as dist
+        torch.cuda.set_device(rank)
+        from dalm_b200.accel import Accelerator
+        from dalm_b200.models.retriever_only_base_model import AutoModelForSentenceEmbedding
+        from dalm_b200.training.utils import negatives
+        from dalm_b200.training.utils.train_utils import fused_retriever_step
+        from oracle import models as om, losses
+        import test_step_gpu as T
+        acc = Accelerator()
+        assert negatives.active()
+        dev = torch.device("cuda", rank)
+        _, enc, _, bert, _ = T._models(dev)
+        se = AutoModelForSentenceEmbedding("", use_bnb=False, get_peft=True, _model=enc, _load_tokenizer=False)
+        Bs = [6, 4]                                                            # a short batch on rank 1
+        rbs = []
+        for r in range(world):
+            b = T._batch(Bs[r], 12, 24, 8, 600, 500, seed=90 + r)
+            rbs.append({"query_input_ids": b["retriever_query_input_ids"], "query_attention_mask": b["retriever_query_attention_mask"],
+                        "passage_input_ids": b["retriever_passage_input_ids"], "passage_attention_mask": b["retriever_passage_attention_mask"]})
+        enc.lora.zero_grad()
+        out = fused_retriever_step(se, rbs[rank], 100.0)
+        sync = acc.gradient_sync(se.trainable_banks() if hasattr(se, "trainable_banks") else enc.banks())
+        sync.reduce(out["loss"])
+        torch.cuda.synchronize()
+        ok, worst = True, 0.0
+        if rank == 0:
+            # the objective: two-way contrastive loss over ALL 10 rows of both ranks (HF BERT + LoRA on CPU, fp32 autograd)
+            bert.zero_grad(set_to_none=True)
+            qs = torch.cat([om.retrieval_forward(bert, b["query_input_ids"], b["query_attention_mask"]) for b in rbs])
+            ps = torch.cat([om.retrieval_forward(bert, b["passage_input_ids"], b["passage_attention_mask"]) for b in rbs])
+            J = losses.contrastive_loss(losses.get_cosine_sim(qs, ps, 100.0))
+            J.backward()
+            ok = abs(out["loss"].item() - J.item()) / abs(J.item()) < 2e-2 and tuple(out["S"].shape) == (10, 10)
+            grads = {n: p.grad for n, p in bert.named_parameters() if p.grad is not None}
+            for n, _, _ in enc.lora.specs:
+                for g, key in ((enc.lora.gA[n] * sync.grad_scale, n + ".lora_A"), (enc.lora.gB[n] * sync.grad_scale, n + ".lora_B")):
+                    want = next(v for k, v in grads.items() if k.endswith(key + ".weight") or k.endswith(key))
+                    worst = max(worst, _rel(g, want))
+            ok = ok and worst < 8e-2
+        q.put((rank, bool(ok), worst))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        import traceback
+        q.put((rank, False, traceback.format_exc()))
+
+
+def test_cross_rank_negatives_over_nccl_match_the_global_objective():
+    """DALM_B200_CROSS_RANK_NEGATIVES=1 on two real ranks (ragged batches 6 + 4): after the data-parallel mean every LoRA gradient
+    equals the oracle's gradient of the contrastive loss over all 10 rows"""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_neg_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs: p.join(timeout=60)
+    assert all(r[1] for r in res), res
