@@ -150,3 +150,29 @@ def test_nf4_storage_mode_equals_resident_mode(cuda_dev, monkeypatch):
     rel = lambda a, b: ((a - b).norm() / (b.norm() + 1e-30)).item()
     assert (res[0][0] - res[1][0]).abs().max().item() < 2e-3 * res[0][0].abs().max().item()
     assert rel(res[1][1], res[0][1]) < 2e-2 and rel(res[1][2], res[0][2]) < 2e-2   # same math, other GEMM layouts / rounding points
+
+
+def test_wrappers_in_nf4_storage_mode(cuda_dev, tmp_path, monkeypatch):
+    """DALM_B200_NF4_STORAGE=1 through the drop-in wrappers: `use_bnb=True` keeps the encoder's Linear weights packed, embeddings
+    are identical to the dequantised-resident default (same GEMM operands), adapters attach and train"""
+    from dalm_b200 import synthetic
+    from dalm_b200.models.retriever_only_base_model import AutoModelForSentenceEmbedding
+    from dalm_b200.training.utils.train_utils import fused_retriever_step
+    rdir = synthetic.write_model_dir(str(tmp_path / "bge-tiny"), "bert", "bge-tiny", vocab_size=1200)
+    g = torch.Generator().manual_seed(5)
+    ids = torch.randint(5, 1200, (4, 24), generator=g); mask = torch.ones_like(ids); mask[1, 15:] = 0
+    m_res = AutoModelForSentenceEmbedding(rdir, use_bnb=True, get_peft=True)
+    monkeypatch.setenv("DALM_B200_NF4_STORAGE", "1")
+    m_st = AutoModelForSentenceEmbedding(rdir, use_bnb=True, get_peft=True)
+    assert m_st.model.nf4 is not None and m_res.model.nf4 is None and "WoT" not in m_st.model.layers[0]
+    with torch.no_grad():
+        e_res, e_st = m_res(ids, mask), m_st(ids, mask)
+    assert torch.equal(e_res, e_st)
+    batch = {"query_input_ids": ids, "query_attention_mask": mask, "passage_input_ids": ids.flip(1), "passage_attention_mask": mask.flip(1)}
+    for m in (m_res, m_st):                                    # same adapters -> same loss and the same LoRA gradients
+        m.model.lora.flat.copy_(m_res.model.lora.flat); m.model.repack_lora(); m.model.lora.zero_grad()
+    l_res = fused_retriever_step(m_res, batch, 100.0)["loss"].item()
+    l_st = fused_retriever_step(m_st, batch, 100.0)["loss"].item()
+    assert abs(l_res - l_st) < 1e-5 * max(1.0, abs(l_res))
+    rel = ((m_st.model.lora.grad - m_res.model.lora.grad).norm() / (m_res.model.lora.grad.norm() + 1e-30)).item()
+    assert rel < 2e-2 and m_st.model.lora.grad.abs().max().item() > 0
