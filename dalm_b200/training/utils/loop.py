@@ -95,8 +95,18 @@ def run_training(recipe: Recipe, *, dataset_or_path: Any, per_device_train_batch
 
     gen = torch.Generator()
     gen.manual_seed(seed if seed is not None else 0)          # same permutation on every rank (accelerate semantics)
-    loader = DataLoader(processed, shuffle=True, collate_fn=collate, batch_size=per_device_train_batch_size,
-                        pin_memory=torch.cuda.is_available(), generator=gen)
+    from . import packed_dataset
+    if packed_dataset.enabled():
+        # opt-in input pipeline: the tokenised set as one memory-mapped int32 matrix, a batch = one gather; same
+        # sampler, same shards, the same tensors as `collate` builds (packed_dataset.py)
+        cache_root = os.path.join(output_dir, ".packed_cache") if output_dir is not None else None
+        packed = packed_dataset.PackedDataset.from_rows(processed, packed_dataset.PackedDataset.cache_path(processed, cache_root)
+                                                        if accelerator.num_processes == 1 else None)
+        loader = DataLoader(packed, shuffle=True, collate_fn=packed.collate, batch_size=per_device_train_batch_size,
+                            pin_memory=torch.cuda.is_available(), generator=gen)
+    else:
+        loader = DataLoader(processed, shuffle=True, collate_fn=collate, batch_size=per_device_train_batch_size,
+                            pin_memory=torch.cuda.is_available(), generator=gen)
 
     optimizer = FusedAdam(model.parameters(), lr=learning_rate)     # Adam, no weight decay (reference ignores the flag)
     max_train_steps, num_train_epochs = plan_schedule(len(loader), gradient_accumulation_steps, num_train_epochs, max_train_steps)

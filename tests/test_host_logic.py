@@ -221,3 +221,57 @@ def test_nf4_storage_switch(monkeypatch):
         m._nf4_storage(True, False, "falcon")                            # built for BERT encoders and Llama decoders
     with pytest.raises(NotImplementedError):
         m._nf4_storage(True, True, "llama")                              # 4-bit base weights cannot be fully fine-tuned
+
+
+def test_packed_dataset_yields_the_same_batches_as_the_reference_pipeline(tmp_path):
+    """DALM_B200_PACKED_LOADER: the memory-mapped int32 matrix + one gather per batch gives exactly the tensors that DataLoader +
+    collate give on the tokenised rows - same shuffle, same rank shards (world 2), short last batch included; the on-disk cache
+    is re-used and rejected when the layout changes"""
+    import numpy as np
+    import torch
+    from torch.utils.data import DataLoader
+    from dalm_b200.accel import ShardedLoader
+    from dalm_b200.training.utils.loop import collate
+    from dalm_b200.training.utils.packed_dataset import PackedDataset
+    rng = np.random.default_rng(0)
+    rows = [{"retriever_query_input_ids": rng.integers(0, 30000, 5).tolist(), "retriever_query_attention_mask": rng.integers(0, 2, 5).tolist(),
+             "generator_input_input_ids": rng.integers(0, 32000, 9).tolist(), "query_passage_input_len": int(rng.integers(1, 300))}
+            for _ in range(23)]
+    path = str(tmp_path / "cache" / "packed_x")
+    packed = PackedDataset.from_rows(rows, path)
+    assert packed.matrix.shape == (23, 5 + 5 + 9 + 1) and packed.matrix.dtype == np.int32 and len(packed) == 23
+    assert [c[0] for c in packed.columns] == list(rows[0]) and packed.columns[-1][2] == 0       # the scalar feature
+    again = PackedDataset.from_rows(rows, path)                                                    # served from <path>.npy (mmap)
+    assert isinstance(again.matrix, np.memmap) and np.array_equal(again.matrix, packed.matrix)
+    wider = [dict(r, extra=1) for r in rows]
+    assert PackedDataset.from_rows(wider, path).matrix.shape[1] == 21                              # other layout: rebuilt, not re-used
+
+    def loaders():
+        out = []
+        for ds, cf in ((rows, collate), (packed, packed.collate)):
+            g = torch.Generator(); g.manual_seed(42)
+            out.append(DataLoader(ds, shuffle=True, collate_fn=cf, batch_size=4, generator=g))
+        return out
+    ref, got = loaders()
+    n = 0
+    for a, b in zip(ref, got):
+        assert list(a) == list(b)
+        for k in a:
+            assert a[k].dtype == b[k].dtype == torch.int64 and a[k].shape == b[k].shape and torch.equal(a[k], b[k])
+        n += 1
+    assert n == 6                                                                                   # 5 full batches + one of 3
+    for rank in (0, 1):                                                                             # index-level rank shards
+        ref, got = loaders()
+        for a, b in zip(ShardedLoader(ref, rank, 2), ShardedLoader(got, rank, 2)):
+            assert all(torch.equal(a[k], b[k]) for k in a)
+    import pytest
+    with pytest.raises(ValueError):
+        PackedDataset.from_rows([rows[0], dict(rows[1], generator_input_input_ids=[1, 2])])       # ragged feature: refused
+    # an HF `datasets.Dataset` (what `dataset.map(preprocess)` returns) goes column by column and gets a fingerprint-keyed cache name
+    import datasets
+    hf = datasets.Dataset.from_dict({k: [r[k] for r in rows] for k in rows[0]})
+    cp = PackedDataset.cache_path(hf, str(tmp_path / "cache"))
+    assert cp is not None and os.path.basename(cp).startswith("packed_")
+    from_hf = PackedDataset.from_rows(hf, cp)
+    assert np.array_equal(from_hf.matrix, packed.matrix) and from_hf.columns == packed.columns
+    assert PackedDataset.cache_path(rows, str(tmp_path)) is None                                   # plain lists: no fingerprint, in memory
