@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--cpu-baseline", type=int, default=1, help="0 to skip the bounded CPU-oracle timing on rank 0")
     ap.add_argument("--gpu-eager-baseline", type=int, default=1, help="0 to skip the same-box HF-eager GPU baseline (rank 0, N=1)")
     ap.add_argument("--ref-rows", type=int, default=2, help="rows per step of the bounded CPU sample (reference arm / cpu_baseline)")
-    ap.add_argument("--ref-budget-s", type=float, default=200.0, help="wall-clock budget of the reference arm's step loop")
+    ap.add_argument("--ref-budget-s", type=float, default=120.0, help="wall-clock budget of the reference arm's step loop (model build, ~1 min, comes on top)")
     ap.add_argument("--through-trainer", type=int, default=1,
                     help="1: also time the same steps through the public trainer API (dalm_b200.training...train_e2e: CSV -> "
                          "datasets.map -> DataLoader -> scheduler -> tracker); cfg-3 only")
