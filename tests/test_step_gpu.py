@@ -271,4 +271,4 @@ def test_packed_loader_trains_like_the_reference_pipeline(cuda_dev, tmp_path, mo
         losses.append(rec[-1]["train/epoch_loss"])
         if packed == "1":
             assert any(f.startswith("packed_") and f.endswith(".npy") for f in os.listdir(os.path.join(out, ".packed_cache")))
-    assert abs(losses[0] - losses[1]) < 1e-2 * abs(losses[0]), losses      # one epoch over the same rows; batch identity itself is pinned on CPU
+    assert abs(losses[0] - losses[1]) < 2e-2 * abs(losses[0]), losses      # one epoch over the same rows; batch identity itself is pinned on CPU
