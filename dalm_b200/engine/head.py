@@ -10,8 +10,10 @@ chunks of whole 128-row GEMM tiles:
     dW_head     += dlogits_chunk^T @ hf[r0:r1]   (full fine-tuning only)
 
 so forward, loss and the head's backward are one sweep over the rows; what survives it is tok_lp [B,L] (fp32) and
-dhf [M,H] (bf16). The scratch is re-used by every chunk; in PEFT mode it stays L2-resident between the three launches that
-touch it, and nothing of size V leaves the chip except the chunk's own spills.
+dhf [M,H] (bf16). The scratch is re-used by every chunk and, in PEFT mode, sized (74 MB at cfg-3) to fit the 126 MB L2 between
+the three launches that touch it; whatever part of a chunk is evicted anyway costs one extra 74 MB pass, not the reference's
+four [B,L,V] tensors. Measured at cfg-3 the step time is unchanged (131.8 vs 131.4 samples/s, profiles/r02b_bench_ab.jsonl): the
+gain is the memory (0.3 GB at cfg-3, 4.5 GB at cfg-5) and the absence of a V-sized tensor, not time.
 """
 from __future__ import annotations
 
